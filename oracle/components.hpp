@@ -1,0 +1,540 @@
+// ORACLE (test infrastructure, NOT product code).
+// CPU restatement of the PF-relevant components (physical input -> per-unit parameters -> physical output):
+//   auxiliary/input.hpp, update.hpp, output.hpp          struct layouts
+//   component/branch.hpp      calc_param_y_sym :197-227, calc_param_y_asym :228-241, get_output :94-111
+//   component/line.hpp        ctor :26-36
+//   component/transformer.hpp ctor :33-83, transformer_params :181-241, sym/asym_calc_param :243-345
+//   component/transformer_utils.hpp tap_adjust_impedance :33-47
+//   component/source.hpp      math_param :40-48, calc_param :64
+//   component/shunt.hpp       calc_param :37-51, update_params :86-98
+//   component/load_gen.hpp    set_power :86-95, sym/asym_calc_param :124-139
+//   component/appliance.hpp   get_output :67-93 ; component/node.hpp get_output :37-46
+#pragma once
+
+#include "tensor.hpp"
+#include "ybus.hpp"
+
+namespace pgm_oracle {
+
+enum class WindingType : IntS { wye = 0, wye_n = 1, delta = 2, zigzag = 3, zigzag_n = 4 };
+enum class BranchSide : IntS { from = 0, to = 1 };
+
+// ---- C-API struct layouts (natural alignment) ----
+struct NodeInput {
+    ID id;
+    double u_rated;
+};
+struct LineInput {
+    ID id, from_node, to_node;
+    IntS from_status, to_status;
+    double r1, x1, c1, tan1, r0, x0, c0, tan0, i_n;
+};
+struct TransformerInput {
+    ID id, from_node, to_node;
+    IntS from_status, to_status;
+    double u1, u2, sn, uk, pk, i0, p0, i0_zero_sequence, p0_zero_sequence;
+    IntS winding_from, winding_to, clock, tap_side, tap_pos, tap_min, tap_max, tap_nom;
+    double tap_size, uk_min, uk_max, pk_min, pk_max, r_grounding_from, x_grounding_from, r_grounding_to,
+        x_grounding_to;
+};
+struct SourceInput {
+    ID id, node;
+    IntS status;
+    double u_ref, u_ref_angle, sk, rx_ratio, z01_ratio;
+};
+struct ShuntInput {
+    ID id, node;
+    IntS status;
+    double g1, b1, g0, b0;
+};
+struct SymLoadGenInput {
+    ID id, node;
+    IntS status, type;
+    double p_specified, q_specified;
+};
+struct AsymLoadGenInput {
+    ID id, node;
+    IntS status, type;
+    double p_specified[3], q_specified[3];
+};
+struct BranchUpdate {
+    ID id;
+    IntS from_status, to_status;
+};
+struct TransformerUpdate {
+    ID id;
+    IntS from_status, to_status, tap_pos;
+};
+struct SourceUpdate {
+    ID id;
+    IntS status;
+    double u_ref, u_ref_angle, sk, rx_ratio, z01_ratio;
+};
+struct ShuntUpdate {
+    ID id;
+    IntS status;
+    double g1, b1, g0, b0;
+};
+struct SymLoadGenUpdate {
+    ID id;
+    IntS status;
+    double p_specified, q_specified;
+};
+struct AsymLoadGenUpdate {
+    ID id;
+    IntS status;
+    double p_specified[3], q_specified[3];
+};
+template <int B> struct NodeOutput {
+    ID id;
+    IntS energized;
+    double u_pu[B], u[B], u_angle[B], p[B], q[B];
+};
+template <int B> struct BranchOutput {
+    ID id;
+    IntS energized;
+    double loading;
+    double p_from[B], q_from[B], i_from[B], s_from[B], p_to[B], q_to[B], i_to[B], s_to[B];
+};
+template <int B> struct ApplianceOutput {
+    ID id;
+    IntS energized;
+    double p[B], q[B], i[B], s[B], pf[B];
+};
+static_assert(sizeof(LineInput) == 88 && sizeof(TransformerInput) == 168 && sizeof(SourceInput) == 56);
+static_assert(sizeof(SymLoadGenUpdate) == 24 && sizeof(AsymLoadGenUpdate) == 56);
+static_assert(sizeof(NodeOutput<1>) == 48 && sizeof(NodeOutput<3>) == 128);
+static_assert(sizeof(BranchOutput<1>) == 80 && sizeof(BranchOutput<3>) == 208);
+static_assert(sizeof(ApplianceOutput<1>) == 48 && sizeof(ApplianceOutput<3>) == 128);
+
+// ---- Branch ----
+struct BranchBase {
+    ID id{}, from_node{}, to_node{};
+    bool from_status{}, to_status{};
+    double base_i_from{}, base_i_to{};
+
+    bool branch_status() const { return from_status && to_status; }
+    bool set_status(IntS f, IntS t) {
+        bool changed = false;
+        if (f != na_IntS) {
+            changed = changed || (from_status != static_cast<bool>(f));
+            from_status = static_cast<bool>(f);
+        }
+        if (t != na_IntS) {
+            changed = changed || (to_status != static_cast<bool>(t));
+            to_status = static_cast<bool>(t);
+        }
+        return changed;
+    }
+    // branch.hpp:197-227
+    BranchCalcParam<1> calc_param_y_sym(cplx const& y_series, cplx const& y_shunt, cplx const& tap_ratio) const {
+        double const tap = cabs(tap_ratio);
+        BranchCalcParam<1> param{};
+        auto& yff = param.value[0].m[0][0];
+        auto& yft = param.value[1].m[0][0];
+        auto& ytf = param.value[2].m[0][0];
+        auto& ytt = param.value[3].m[0][0];
+        if (!branch_status()) {
+            if (from_status || to_status) {
+                cplx branch_shunt;
+                if (cabs(y_shunt) < numerical_tolerance) {
+                    branch_shunt = 0.0;
+                } else {
+                    branch_shunt = 0.5 * y_shunt + 1.0 / (1.0 / y_series + 2.0 / y_shunt);
+                }
+                yff = from_status ? (1.0 / tap / tap) * branch_shunt : 0.0;
+                ytt = to_status ? branch_shunt : 0.0;
+            }
+        } else {
+            ytt = y_series + 0.5 * y_shunt;
+            yff = (1.0 / tap / tap) * ytt;
+            yft = (-1.0 / std::conj(tap_ratio)) * y_series;
+            ytf = (-1.0 / tap_ratio) * y_series;
+        }
+        return param;
+    }
+    BranchCalcParam<3> calc_param_y_asym(cplx const& y1_series, cplx const& y1_shunt, cplx const& y0_series,
+                                         cplx const& y0_shunt, cplx const& tap_ratio) const {
+        auto const p1 = calc_param_y_sym(y1_series, y1_shunt, tap_ratio);
+        auto const p0 = calc_param_y_sym(y0_series, y0_shunt, tap_ratio);
+        BranchCalcParam<3> param{};
+        for (int i = 0; i < 4; ++i) {
+            cplx const v1 = p1.value[i].m[0][0];
+            cplx const v0 = p0.value[i].m[0][0];
+            param.value[i] = cmat_sm<3>((2.0 * v1 + v0) / 3.0, (v0 - v1) / 3.0);
+        }
+        return param;
+    }
+};
+
+struct Line : BranchBase {
+    double i_n{};
+    cplx y1_series, y1_shunt, y0_series, y0_shunt;
+    Line(LineInput const& in, double system_frequency, double u1, double u2) {
+        id = in.id;
+        from_node = in.from_node;
+        to_node = in.to_node;
+        from_status = in.from_status != 0;
+        to_status = in.to_status != 0;
+        i_n = in.i_n;
+        double const base_i = base_power_3p / u1 / sqrt3;
+        base_i_from = base_i_to = base_i;
+        if (cabs(u1 - u2) > numerical_tolerance) {
+            throw PgmError{"Conflicting voltage for line " + std::to_string(id)};
+        }
+        double const base_y = base_i / (u1 / sqrt3);
+        cplx const j{0.0, 1.0};
+        y1_series = 1.0 / (in.r1 + j * in.x1) / base_y;
+        y1_shunt = 2.0 * pi * system_frequency * in.c1 / base_y * (in.tan1 + j);
+        y0_series = 1.0 / (in.r0 + j * in.x0) / base_y;
+        y0_shunt = 2.0 * pi * system_frequency * in.c0 / base_y * (in.tan0 + j);
+    }
+    double loading(double /*max_s*/, double max_i) const { return max_i / i_n; }
+    double phase_shift() const { return 0.0; }
+    template <int B> BranchCalcParam<B> calc_param() const {
+        if (!(from_status || to_status)) return BranchCalcParam<B>{};
+        if constexpr (B == 1) {
+            return calc_param_y_sym(y1_series, y1_shunt, 1.0);
+        } else {
+            return calc_param_y_asym(y1_series, y1_shunt, y0_series, y0_shunt, 1.0);
+        }
+    }
+};
+
+inline double tap_adjust_impedance(double tap_pos, double tap_min, double tap_max, double tap_nom, double xk,
+                                   double xk_min, double xk_max) {
+    if (tap_pos <= std::max(tap_nom, tap_max) && tap_pos >= std::min(tap_nom, tap_max)) {
+        if (tap_max == tap_nom) return xk;
+        double const inc = (xk_max - xk) / (tap_max - tap_nom);
+        return xk + (tap_pos - tap_nom) * inc;
+    }
+    if (tap_min == tap_nom) return xk;
+    double const inc = (xk_min - xk) / (tap_min - tap_nom);
+    return xk + (tap_pos - tap_nom) * inc;
+}
+
+struct Transformer : BranchBase {
+    double u1, u2, sn, tap_size, uk, pk, i0, p0, i0_zero_sequence, p0_zero_sequence;
+    WindingType winding_from, winding_to;
+    IntS clock;
+    BranchSide tap_side;
+    IntS tap_pos, tap_min, tap_max, tap_nom, tap_direction;
+    double uk_min, uk_max, pk_min, pk_max;
+    double nominal_ratio;
+    cplx z_grounding_from, z_grounding_to;
+
+    static cplx calculate_z_pu(double r, double x, double u) {
+        r = is_nan(r) ? 0 : r;
+        x = is_nan(x) ? 0 : x;
+        double const base_z = u * u / base_power_3p;
+        return {r / base_z, x / base_z};
+    }
+    IntS tap_limit(IntS new_tap) const {
+        new_tap = std::min(new_tap, std::max(tap_max, tap_min));
+        new_tap = std::max(new_tap, std::min(tap_max, tap_min));
+        return new_tap;
+    }
+    Transformer(TransformerInput const& in, double u1_rated, double u2_rated) {
+        id = in.id;
+        from_node = in.from_node;
+        to_node = in.to_node;
+        from_status = in.from_status != 0;
+        to_status = in.to_status != 0;
+        u1 = in.u1;
+        u2 = in.u2;
+        sn = in.sn;
+        tap_size = in.tap_size;
+        uk = in.uk;
+        pk = in.pk;
+        i0 = in.i0;
+        p0 = in.p0;
+        i0_zero_sequence = is_nan(in.i0_zero_sequence) ? i0 : in.i0_zero_sequence;
+        p0_zero_sequence =
+            is_nan(in.p0_zero_sequence) ? p0 + pk * (i0_zero_sequence * i0_zero_sequence - i0 * i0) : in.p0_zero_sequence;
+        winding_from = static_cast<WindingType>(in.winding_from);
+        winding_to = static_cast<WindingType>(in.winding_to);
+        clock = in.clock;
+        tap_side = static_cast<BranchSide>(in.tap_side);
+        tap_min = in.tap_min;
+        tap_max = in.tap_max;
+        tap_nom = in.tap_nom == na_IntS ? IntS{0} : in.tap_nom;
+        tap_direction = tap_max > tap_min ? IntS{1} : IntS{-1};
+        uk_min = is_nan(in.uk_min) ? uk : in.uk_min;
+        uk_max = is_nan(in.uk_max) ? uk : in.uk_max;
+        pk_min = is_nan(in.pk_min) ? pk : in.pk_min;
+        pk_max = is_nan(in.pk_max) ? pk : in.pk_max;
+        base_i_from = base_power_3p / u1_rated / sqrt3;
+        base_i_to = base_power_3p / u2_rated / sqrt3;
+        nominal_ratio = u1_rated / u2_rated;
+        z_grounding_from = calculate_z_pu(in.r_grounding_from, in.x_grounding_from, u1_rated);
+        z_grounding_to = calculate_z_pu(in.r_grounding_to, in.x_grounding_to, u2_rated);
+        if (in.tap_pos == na_IntS) {
+            tap_pos = in.tap_nom == na_IntS ? IntS{0} : in.tap_nom;
+        } else {
+            tap_pos = in.tap_pos;
+        }
+        bool const clock_is_even = (clock % 2) == 0;
+        bool const is_from_wye = winding_from == WindingType::wye || winding_from == WindingType::wye_n;
+        bool const is_to_wye = winding_to == WindingType::wye || winding_to == WindingType::wye_n;
+        if (clock_is_even != (is_from_wye == is_to_wye)) {
+            throw PgmError{"Invalid clock for transformer " + std::to_string(id)};
+        }
+        clock = static_cast<IntS>((clock % 12 + 12) % 12);
+        tap_pos = tap_limit(tap_pos);
+    }
+    bool set_tap(IntS new_tap) {
+        if (new_tap == na_IntS || new_tap == tap_pos) return false;
+        tap_pos = tap_limit(new_tap);
+        return true;
+    }
+    double loading(double max_s, double /*max_i*/) const { return max_s / sn; }
+    double phase_shift() const { return clock * deg_30; }
+
+    struct Params {
+        cplx y_series, y_shunt, y0_shunt;
+        double k;
+    };
+    Params transformer_params() const {
+        double const base_y_to = base_i_to * base_i_to / base_power_1p;
+        double ru1 = u1, ru2 = u2;
+        if (tap_side == BranchSide::from) {
+            ru1 += tap_direction * (tap_pos - tap_nom) * tap_size;
+        } else {
+            ru2 += tap_direction * (tap_pos - tap_nom) * tap_size;
+        }
+        double const k = (ru1 / ru2) / nominal_ratio;
+        double const uk_t = tap_adjust_impedance(tap_pos, tap_min, tap_max, tap_nom, uk, uk_min, uk_max);
+        double const pk_t = tap_adjust_impedance(tap_pos, tap_min, tap_max, tap_nom, pk, pk_min, pk_max);
+        cplx z_series{};
+        double const uk_sign = (uk_t >= 0) ? 1.0 : -1.0;
+        double const z_series_abs = cabs(uk_t) * ru2 * ru2 / sn;
+        z_series.real(pk_t * ru2 * ru2 / sn / sn);
+        double const zi2 = z_series_abs * z_series_abs - z_series.real() * z_series.real();
+        z_series.imag(uk_sign * (zi2 > 0.0 ? std::sqrt(zi2) : 0.0));
+        cplx const y_series = (1.0 / z_series) / base_y_to;
+        auto shunt = [&](double i0_, double p0_) {
+            cplx y;
+            double const y_abs = i0_ * sn / ru2 / ru2;
+            y.real(p0_ / ru2 / ru2);
+            double const yi2 = y_abs * y_abs - y.real() * y.real();
+            y.imag(yi2 > 0.0 ? -std::sqrt(yi2) : 0.0);
+            return y / base_y_to;
+        };
+        return {y_series, shunt(i0, p0), shunt(i0_zero_sequence, p0_zero_sequence), k};
+    }
+    template <int B> BranchCalcParam<B> calc_param() const {
+        if (!(from_status || to_status)) return BranchCalcParam<B>{};
+        cplx const j{0.0, 1.0};
+        auto const [y_series, y_shunt, y0_shunt, k] = transformer_params();
+        if constexpr (B == 1) {
+            return calc_param_y_sym(y_series, y_shunt, k * std::exp(j * (clock * deg_30)));
+        } else {
+            auto const param1 = calc_param_y_sym(y_series, y_shunt, k * std::exp(j * (clock * deg_30)));
+            auto const param2 = calc_param_y_sym(y_series, y_shunt, k * std::exp(j * (-clock * deg_30)));
+            BranchCalcParam<1> param0{};
+            auto& p0ff = param0.value[0].m[0][0];
+            auto& p0tt = param0.value[3].m[0][0];
+            using enum WindingType;
+            if (winding_from == wye_n && winding_to == wye_n) {
+                double phase_shift_0 = 0.0;
+                if (clock == 2 || clock == 6 || clock == 10) phase_shift_0 = 6.0 * deg_30;
+                cplx const z0_series = 1.0 / y_series + 3.0 * (z_grounding_to + z_grounding_from / k / k);
+                cplx const y0_series = 1.0 / z0_series;
+                param0 = calc_param_y_sym(y0_series, y0_shunt, k * std::exp(j * phase_shift_0));
+            } else if (winding_from == wye_n && from_status) {
+                cplx y0 = y0_shunt;
+                if (winding_to == delta) y0 += y_series;
+                if (y0 != cplx{0.0, 0.0}) {
+                    cplx const z0 = 1.0 / y0 + 3.0 * z_grounding_from / k / k;
+                    y0 = 1.0 / z0;
+                    p0ff = y0 / k / k;
+                }
+            } else if (winding_to == wye_n && to_status) {
+                cplx y0 = y0_shunt;
+                if (winding_from == delta) y0 += y_series;
+                if (y0 != cplx{0.0, 0.0}) {
+                    cplx const z0 = 1.0 / y0 + 3.0 * z_grounding_to;
+                    y0 = 1.0 / z0;
+                    p0tt = y0;
+                }
+            }
+            if (winding_from == zigzag_n && from_status) {
+                cplx const z0_series = (1.0 / y_series) * 0.1 + 3.0 * z_grounding_from / k / k;
+                p0ff = (1.0 / z0_series) / k / k;
+            }
+            if (winding_to == zigzag_n && to_status) {
+                cplx const z0_series = (1.0 / y_series) * 0.1 + 3.0 * z_grounding_to;
+                p0tt = 1.0 / z0_series;
+            }
+            double const low_susceptance = -transformer_low_susceptance_ratio * sn / base_power_3p / uk;
+            auto zero_seq_available = [](WindingType this_side, WindingType other_side) {
+                switch (this_side) {
+                case wye_n:
+                    return other_side == wye_n || other_side == delta;
+                case zigzag_n:
+                    return true;
+                default:
+                    return false;
+                }
+            };
+            if (!zero_seq_available(winding_from, winding_to) && from_status) p0ff += cplx{0.0, low_susceptance};
+            if (!zero_seq_available(winding_to, winding_from) && to_status) p0tt += cplx{0.0, low_susceptance};
+            CMat<3> const sm = get_sym_matrix();
+            CMat<3> const smi = get_sym_matrix_inv();
+            BranchCalcParam<3> param;
+            for (int i = 0; i != 4; ++i) {
+                CMat<3> y012{};
+                y012.m[0][0] = param0.value[i].m[0][0];
+                y012.m[1][1] = param1.value[i].m[0][0];
+                y012.m[2][2] = param2.value[i].m[0][0];
+                param.value[i] = dot(dot(sm, y012), smi);
+            }
+            return param;
+        }
+    }
+};
+
+// ---- Appliances ----
+struct ApplianceBase {
+    ID id{}, node{};
+    bool status{};
+    double base_i{};
+    bool set_status(IntS s) {
+        if (s == na_IntS) return false;
+        if (static_cast<bool>(s) == status) return false;
+        status = static_cast<bool>(s);
+        return true;
+    }
+    template <int B>
+    ApplianceOutput<B> get_output(ApplianceSolverOutput<B> const& so, double direction) const {
+        ApplianceOutput<B> out{};
+        out.id = id;
+        out.energized = status ? 1 : 0;
+        for (int p = 0; p < B; ++p) {
+            out.p[p] = base_power<B> * so.s.v[p].real() * direction;
+            out.q[p] = base_power<B> * so.s.v[p].imag() * direction;
+            out.s[p] = base_power<B> * cabs(so.s.v[p]);
+            out.i[p] = base_i * cabs(so.i.v[p]);
+            out.pf[p] = out.s[p] < numerical_tolerance ? 0.0 : out.p[p] / out.s[p];
+        }
+        return out;
+    }
+    template <int B> ApplianceOutput<B> get_null_output() const {
+        ApplianceOutput<B> out{};
+        out.id = id;
+        out.energized = 0;
+        return out;
+    }
+};
+
+struct Source : ApplianceBase {
+    double u_ref, u_ref_angle, sk, rx_ratio, z01_ratio;
+    Source(SourceInput const& in, double u) {
+        id = in.id;
+        node = in.node;
+        status = in.status != 0;
+        base_i = base_power_3p / u / sqrt3;
+        u_ref = in.u_ref;
+        u_ref_angle = is_nan(in.u_ref_angle) ? 0.0 : in.u_ref_angle;
+        sk = is_nan(in.sk) ? default_source_sk : in.sk;
+        rx_ratio = is_nan(in.rx_ratio) ? default_source_rx_ratio : in.rx_ratio;
+        z01_ratio = is_nan(in.z01_ratio) ? default_source_z01_ratio : in.z01_ratio;
+    }
+    SourceCalcParam math_param() const {
+        double const z_abs = base_power_3p / sk;
+        double const x1 = z_abs / std::sqrt(rx_ratio * rx_ratio + 1.0);
+        double const r1 = x1 * rx_ratio;
+        cplx const y1_ref = 1.0 / cplx{r1, x1};
+        cplx const y0_ref = y1_ref / z01_ratio;
+        return {y1_ref, y0_ref};
+    }
+    cplx calc_param() const { return u_ref * std::exp(cplx{0.0, 1.0} * u_ref_angle); }
+};
+
+struct Shunt : ApplianceBase {
+    double base_y{nan}, g1{nan}, b1{nan}, g0{nan}, b0{nan};
+    cplx y1{nan}, y0{nan};
+    Shunt(ShuntInput const& in, double u) {
+        id = in.id;
+        node = in.node;
+        status = in.status != 0;
+        base_i = base_power_3p / u / sqrt3;
+        base_y = base_i / (u / sqrt3);
+        update_params(in.g1, in.b1, in.g0, in.b0);
+    }
+    static bool update_param(double value, double& target) {
+        if (is_nan(value) || value == target) return false;
+        target = value;
+        return true;
+    }
+    bool update_params(double ng1, double nb1, double ng0, double nb0) {
+        bool changed = update_param(ng1, g1);
+        changed = update_param(nb1, b1) || changed;
+        changed = update_param(ng0, g0) || changed;
+        changed = update_param(nb0, b0) || changed;
+        if (changed) {
+            y1 = (g1 + cplx{0.0, 1.0} * b1) / base_y;
+            y0 = (g0 + cplx{0.0, 1.0} * b0) / base_y;
+        }
+        return changed;
+    }
+    template <int B> CMat<B> calc_param() const {
+        if (!status) return CMat<B>{};
+        if constexpr (B == 1) {
+            return cmat_diag<1>(y1);
+        } else {
+            return cmat_sm<3>((2.0 * y1 + y0) / 3.0, (y0 - y1) / 3.0);
+        }
+    }
+};
+
+// LoadGen<loadgen symmetry LB, direction>
+struct LoadGen : ApplianceBase {
+    int lb{1};          // 1 = sym_load/sym_gen, 3 = asym_load/asym_gen
+    double direction{}; // +1 generator, -1 load
+    LoadGenType type{};
+    cplx s_specified[3]{{nan, nan}, {nan, nan}, {nan, nan}};
+
+    LoadGen(ID id_, ID node_, IntS status_, IntS type_, double u, int lb_, double direction_, double const* p,
+            double const* q) {
+        id = id_;
+        node = node_;
+        status = status_ != 0;
+        base_i = base_power_3p / u / sqrt3;
+        lb = lb_;
+        direction = direction_;
+        type = static_cast<LoadGenType>(type_);
+        set_power(p, q);
+    }
+    void set_power(double const* new_p, double const* new_q) {
+        double const scalar = direction / (lb == 1 ? base_power_3p : base_power_1p);
+        for (int i = 0; i < lb; ++i) {
+            double ps = s_specified[i].real();
+            double qs = s_specified[i].imag();
+            if (!is_nan(new_p[i])) ps = scalar * new_p[i];
+            if (!is_nan(new_q[i])) qs = scalar * new_q[i];
+            s_specified[i] = cplx{ps, qs};
+        }
+    }
+    template <int B> CVec<B> calc_param() const {
+        if (!status) return CVec<B>{};
+        if constexpr (B == 1) {
+            if (lb == 1) {
+                if (is_nan(s_specified[0].real()) || is_nan(s_specified[0].imag())) return {cplx{nan, nan}};
+                return {s_specified[0]};
+            }
+            // mean_val over the three phases (Eigen mean = sum / 3)
+            return {(s_specified[0] + s_specified[1] + s_specified[2]) / 3.0};
+        } else {
+            if (lb == 1) {
+                if (is_nan(s_specified[0].real()) || is_nan(s_specified[0].imag())) return vec_piecewise<cplx, 3>(cplx{nan, nan});
+                return vec_piecewise<cplx, 3>(s_specified[0]);
+            }
+            CVec<3> r;
+            for (int i = 0; i < 3; ++i) r.v[i] = s_specified[i];
+            return r;
+        }
+    }
+};
+
+} // namespace pgm_oracle

@@ -1,0 +1,100 @@
+"""numpy dtypes of the PF-relevant component structs at the power-grid-model C-API boundary.
+
+Layouts follow the reference's generated headers (natural C alignment):
+``power_grid_model/auxiliary/input.hpp``, ``update.hpp``, ``output.hpp`` (source of truth:
+``code_generation/data/attribute_classes/{input,update,output}.json``); the reference's Python wrapper builds the
+same dtypes at run time from ``PGM_meta_*`` (``src/power_grid_model/_core/power_grid_meta.py``).
+"""
+import numpy as np
+
+NA_INT_ID = np.iinfo(np.int32).min
+NA_INT_S = np.iinfo(np.int8).min
+
+
+def _dt(fields):
+    return np.dtype(fields, align=True)
+
+
+_branch_head = [("id", "i4"), ("from_node", "i4"), ("to_node", "i4"), ("from_status", "i1"), ("to_status", "i1")]
+_appliance_head = [("id", "i4"), ("node", "i4"), ("status", "i1")]
+
+INPUT = {
+    "node": _dt([("id", "i4"), ("u_rated", "f8")]),
+    "line": _dt(_branch_head + [(n, "f8") for n in ("r1", "x1", "c1", "tan1", "r0", "x0", "c0", "tan0", "i_n")]),
+    "transformer": _dt(
+        _branch_head
+        + [(n, "f8") for n in ("u1", "u2", "sn", "uk", "pk", "i0", "p0", "i0_zero_sequence", "p0_zero_sequence")]
+        + [(n, "i1") for n in ("winding_from", "winding_to", "clock", "tap_side", "tap_pos", "tap_min", "tap_max", "tap_nom")]
+        + [
+            (n, "f8")
+            for n in (
+                "tap_size", "uk_min", "uk_max", "pk_min", "pk_max",
+                "r_grounding_from", "x_grounding_from", "r_grounding_to", "x_grounding_to",
+            )
+        ]
+    ),
+    "source": _dt(_appliance_head + [(n, "f8") for n in ("u_ref", "u_ref_angle", "sk", "rx_ratio", "z01_ratio")]),
+    "shunt": _dt(_appliance_head + [(n, "f8") for n in ("g1", "b1", "g0", "b0")]),
+    "sym_load": _dt(_appliance_head + [("type", "i1"), ("p_specified", "f8"), ("q_specified", "f8")]),
+    "asym_load": _dt(_appliance_head + [("type", "i1"), ("p_specified", "f8", (3,)), ("q_specified", "f8", (3,))]),
+}
+INPUT["sym_gen"] = INPUT["sym_load"]
+INPUT["asym_gen"] = INPUT["asym_load"]
+
+UPDATE = {
+    "line": _dt([("id", "i4"), ("from_status", "i1"), ("to_status", "i1")]),
+    "transformer": _dt([("id", "i4"), ("from_status", "i1"), ("to_status", "i1"), ("tap_pos", "i1")]),
+    "source": _dt([("id", "i4"), ("status", "i1")] + [(n, "f8") for n in ("u_ref", "u_ref_angle", "sk", "rx_ratio", "z01_ratio")]),
+    "shunt": _dt([("id", "i4"), ("status", "i1")] + [(n, "f8") for n in ("g1", "b1", "g0", "b0")]),
+    "sym_load": _dt([("id", "i4"), ("status", "i1"), ("p_specified", "f8"), ("q_specified", "f8")]),
+    "asym_load": _dt([("id", "i4"), ("status", "i1"), ("p_specified", "f8", (3,)), ("q_specified", "f8", (3,))]),
+}
+UPDATE["sym_gen"] = UPDATE["sym_load"]
+UPDATE["asym_gen"] = UPDATE["asym_load"]
+
+
+def _real(sym):
+    return ("f8",) if sym else ("f8", (3,))
+
+
+def output_dtypes(sym: bool):
+    r = _real(sym)
+    node = _dt([("id", "i4"), ("energized", "i1")] + [(n, *r) for n in ("u_pu", "u", "u_angle", "p", "q")])
+    branch = _dt(
+        [("id", "i4"), ("energized", "i1"), ("loading", "f8")]
+        + [(n, *r) for n in ("p_from", "q_from", "i_from", "s_from", "p_to", "q_to", "i_to", "s_to")]
+    )
+    appliance = _dt([("id", "i4"), ("energized", "i1")] + [(n, *r) for n in ("p", "q", "i", "s", "pf")])
+    return {
+        "node": node, "line": branch, "transformer": branch, "shunt": appliance, "source": appliance,
+        "sym_gen": appliance, "asym_gen": appliance, "sym_load": appliance, "asym_load": appliance,
+    }
+
+
+SYM_OUTPUT = output_dtypes(True)
+ASYM_OUTPUT = output_dtypes(False)
+
+# component storage order of the reference (all_components.hpp:36-39), PF subset
+COMPONENT_ORDER = ("node", "line", "transformer", "shunt", "source", "sym_gen", "asym_gen", "sym_load", "asym_load")
+UPDATABLE = ("line", "transformer", "shunt", "source", "sym_gen", "asym_gen", "sym_load", "asym_load")
+
+
+def initialize_array(kind: str, component: str, shape, sym: bool = True):
+    """Array filled with the reference's null values (NaN / INT_MIN), like power_grid_model.initialize_array."""
+    table = {"input": INPUT, "update": UPDATE, "sym_output": SYM_OUTPUT, "asym_output": ASYM_OUTPUT}[kind]
+    arr = np.zeros(shape, dtype=table[component])
+    for name in arr.dtype.names:
+        base = arr.dtype[name].base
+        if base == np.float64:
+            arr[name] = np.nan
+        elif base == np.int32:
+            arr[name] = NA_INT_ID
+        else:
+            arr[name] = NA_INT_S
+    return arr
+
+
+assert INPUT["line"].itemsize == 88 and INPUT["transformer"].itemsize == 168 and INPUT["source"].itemsize == 56
+assert UPDATE["sym_load"].itemsize == 24 and UPDATE["asym_load"].itemsize == 56
+assert SYM_OUTPUT["node"].itemsize == 48 and ASYM_OUTPUT["node"].itemsize == 128
+assert SYM_OUTPUT["line"].itemsize == 80 and ASYM_OUTPUT["line"].itemsize == 208
