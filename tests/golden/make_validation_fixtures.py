@@ -1,0 +1,51 @@
+"""Collects the reference's power-flow validation cases (tests/data/power_flow/**) whose components are in the PF subset
+this repo implements into ONE fixture file, tests/golden/power_flow_cases.json.
+
+Run here (the build container has /root/reference; the GPU box does not):
+    python tests/golden/make_validation_fixtures.py
+Each case keeps: params (methods, rtol, atol), input, optional update_batch and the reference's golden outputs
+(sym_output / asym_output / *_batch). Attributes are stored as the reference stores them (row dicts, or compact rows
+with an `attributes` table).  `inf`-like strings are kept verbatim and decoded by the test loader.
+"""
+import json
+import os
+import sys
+
+REF = "/root/reference/tests/data/power_flow"
+SUPPORTED = {"node", "line", "transformer", "source", "shunt", "sym_load", "sym_gen", "asym_load", "asym_gen"}
+IGNORED_INPUT = {"fault", "sym_voltage_sensor", "sym_power_sensor", "asym_voltage_sensor", "asym_power_sensor"}  # not used by PF
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "power_flow_cases.json")
+
+
+def main():
+    cases = {}
+    skipped = {}
+    for dirpath, _, files in sorted(os.walk(REF)):
+        if "params.json" not in files or "input.json" not in files:
+            continue
+        name = os.path.relpath(dirpath, REF)
+        params = json.load(open(os.path.join(dirpath, "params.json")))
+        inp = json.load(open(os.path.join(dirpath, "input.json")))
+        comps = set(inp["data"].keys())
+        unsupported = comps - SUPPORTED - IGNORED_INPUT
+        if unsupported:
+            skipped[name] = "unsupported components: " + ", ".join(sorted(unsupported))
+            continue
+        if "raises" in params or "xfail" in params or "tap_changing_strategy" in params:
+            skipped[name] = "expects an error / optimizer"
+            continue
+        case = {"params": params, "input": inp}
+        for f in ("update_batch", "sym_output", "asym_output", "sym_output_batch", "asym_output_batch"):
+            p = os.path.join(dirpath, f + ".json")
+            if os.path.exists(p):
+                case[f] = json.load(open(p))
+        cases[name] = case
+    json.dump({"source": "PowerGridModel/power-grid-model tests/data/power_flow (MPL-2.0)", "cases": cases, "skipped": skipped},
+              open(OUT, "w"), separators=(",", ":"))
+    print(f"{len(cases)} cases -> {OUT} ({os.path.getsize(OUT)} bytes); skipped {len(skipped)}")
+    for k, v in skipped.items():
+        print("  skipped", k, ":", v)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
