@@ -1,0 +1,215 @@
+/* pgm_b200 -- C-ABI of the B200-native batch power-flow engine.
+ *
+ * Two seams, both plain C (pointers + sizes, no C++/torch types):
+ *
+ *  1. ENGINE level  = the reference's math-solver seam.  One engine == one math sub-grid == what the reference builds
+ *     from a `MathModelTopology` (calculation_parameters.hpp:160-213) as `YBus<sym>` + `MathSolver<sym>`
+ *     (math_solver/math_solver_dispatch.hpp:26-107, math_solver/math_solver.hpp:43-64).  It replaces
+ *     `MathSolverBase<sym>::run_power_flow(input, err_tol, max_iter, cache_run, log, method, y_bus)` called once per
+ *     scenario by `MainModelImpl::calculate_` (main_model_impl.hpp:310-312) with ONE call over all scenarios.
+ *
+ *  2. MODEL level   = the reference's `PGM_create_model` / `PGM_calculate` seam
+ *     (power_grid_model_c/include/power_grid_model_c/model.h:43-48, 116-118) for the PF component subset, with the
+ *     dataset handles flattened into structs of caller-owned buffers (same struct layouts as the reference's
+ *     `PGM_def_input_* / update_* / sym_output_* / asym_output_*` components, see pgm_b200.structs).  It replaces the
+ *     CPU thread-pool dispatcher `JobDispatch::batch_calculation` (job_dispatch.hpp:37-68).
+ *
+ * Complex numbers are interleaved (re, im) doubles.  B = 1 (symmetric) or 3 (asymmetric); tensors are row-major
+ * [r][c].  All index types are int64 like the reference's `Idx`; ids are int32 (`ID`), enums int8 (`IntS`).
+ * Every function returns 0 on success or a PGMB_ERR_* code; the message is available from pgmb_last_error()
+ * (thread-local, like one PGM_Handle per thread).  Nothing here ever falls back to a CPU solver: if no CUDA device
+ * is usable, create/run calls fail with PGMB_ERR_CUDA.
+ */
+#ifndef PGM_B200_H
+#define PGM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PGMB_API __attribute__((visibility("default")))
+
+enum {
+    PGMB_OK = 0,
+    PGMB_ERR_INVALID = 1, /* invalid argument / unsupported option */
+    PGMB_ERR_CUDA = 2,    /* CUDA runtime error or no device */
+    PGMB_ERR_BATCH = 3,   /* at least one scenario failed: see status[] (PGM_batch_error analogue) */
+    PGMB_ERR_INTERNAL = 4
+};
+
+/* per-scenario status (the reference throws IterationDiverge / SparseMatrixError per scenario,
+ * common/exception.hpp:89-110; job_dispatch.hpp:181-224 collects them) */
+enum { PGMB_SCN_OK = 0, PGMB_SCN_DIVERGED = 1, PGMB_SCN_SINGULAR = 2, PGMB_SCN_ERROR = 3 };
+
+/* CalculationMethod, common/enum.hpp:33-41 */
+enum {
+    PGMB_METHOD_DEFAULT = -128,
+    PGMB_METHOD_LINEAR = 0,
+    PGMB_METHOD_NEWTON_RAPHSON = 1,
+    PGMB_METHOD_ITERATIVE_CURRENT = 3,
+    PGMB_METHOD_LINEAR_CURRENT = 4
+};
+
+PGMB_API const char* pgmb_last_error(void);
+PGMB_API int pgmb_device_count(void);
+PGMB_API const char* pgmb_version(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * ENGINE level
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* MathModelTopology as arrays (calculation_parameters.hpp:160-213); grouped index vectors in sparse (indptr) form */
+typedef struct pgmb_math_topology {
+    int64_t n_bus;
+    const double* phase_shift;        /* [n_bus] */
+    int64_t n_branch;
+    const int64_t* branch_bus_idx;    /* [n_branch][2], -1 = disconnected side */
+    int64_t n_fill_in;
+    const int64_t* fill_in;           /* [n_fill_in][2] */
+    const int64_t* sources_per_bus;   /* indptr [n_bus + 1] */
+    const int64_t* shunts_per_bus;    /* indptr [n_bus + 1] */
+    const int64_t* load_gens_per_bus; /* indptr [n_bus + 1] */
+    const int8_t* load_gen_type;      /* [n_load_gen] LoadGenType: 0 const_pq, 1 const_y, 2 const_i */
+} pgmb_math_topology;
+
+/* MathModelParam<sym> (calculation_parameters.hpp:240-255) */
+typedef struct pgmb_math_param {
+    const double* branch_param; /* [n_branch][4 (ff,ft,tf,tt)][B][B] complex */
+    const double* shunt_param;  /* [n_shunt][B][B] complex */
+    const double* source_param; /* [n_source][2 (y1, y0)] complex  (SourceCalcParam) */
+} pgmb_math_param;
+
+typedef struct pgmb_run_options {
+    int32_t method;   /* PGMB_METHOD_* */
+    double err_tol;   /* PGM_Options.err_tol, default 1e-8 */
+    int64_t max_iter; /* PGM_Options.max_iter, default 20 */
+} pgmb_run_options;
+
+/* PowerFlowInput<sym> for n_scenarios scenarios (calculation_parameters.hpp:270-277) */
+typedef struct pgmb_pf_input {
+    int64_t n_scenarios;
+    const double* source_u_ref; /* [n_scenarios][n_source] complex; or [n_source] when source_is_shared != 0 */
+    int32_t source_is_shared;
+    const double* s_injection;  /* [n_scenarios][n_load_gen][B] complex, per-unit, injection direction */
+} pgmb_pf_input;
+
+/* SolverOutput<sym> for n_scenarios scenarios (calculation_parameters.hpp:338-350); any pointer may be NULL */
+typedef struct pgmb_solver_output {
+    double* u;             /* [n_scenarios][n_bus][B] complex */
+    double* bus_injection; /* [n_scenarios][n_bus][B] complex */
+    double* branch;        /* [n_scenarios][n_branch][4 (s_f, s_t, i_f, i_t)][B] complex */
+    double* source;        /* [n_scenarios][n_source][2 (s, i)][B] complex */
+    double* shunt;         /* [n_scenarios][n_shunt][2 (s, i)][B] complex */
+    double* load_gen;      /* [n_scenarios][n_load_gen][2 (s, i)][B] complex */
+    int32_t* status;       /* [n_scenarios] PGMB_SCN_* */
+    int32_t* n_iter;       /* [n_scenarios] iterations used (the reference only logs it, iterative_pf_solver.hpp:87) */
+    double* max_dev;       /* [n_scenarios] last max |dU| */
+} pgmb_solver_output;
+
+typedef struct pgmb_engine pgmb_engine;
+
+/* Symbolic stage, once per topology: Y-bus CSR + LU pattern with fill-ins (YBusStructure, y_bus.hpp:122-293) and
+ * the elimination schedule (flattened index walk of SparseLUSolver::prefactorize, sparse_lu_solver.hpp:346-495),
+ * uploaded to `device`. */
+PGMB_API int pgmb_engine_create(const pgmb_math_topology* topo, int32_t symmetric, int32_t device, pgmb_engine** out);
+PGMB_API void pgmb_engine_destroy(pgmb_engine* engine);
+
+/* Y-bus assembly (YBus::update_admittance, y_bus.hpp:342-431) + upload. */
+PGMB_API int pgmb_engine_set_param(pgmb_engine* engine, const pgmb_math_param* param);
+
+/* Structure introspection for parity tests: name in {row_indptr, col_indices, bus_entry, row_indptr_lu,
+ * col_indices_lu, diag_lu, map_lu_y_bus, lu_transpose_entry, y_bus_entry_indptr, level_ptr, level_rows};
+ * admittance via pgmb_engine_get_admittance ([nnz][B][B] complex). Pointers stay valid until destroy/set_param. */
+PGMB_API int pgmb_engine_get_index(pgmb_engine* engine, const char* name, const int64_t** data, int64_t* size);
+PGMB_API int pgmb_engine_get_admittance(pgmb_engine* engine, const double** data, int64_t* size);
+
+/* Batch power flow, host buffers in / host buffers out (copies inside). Returns PGMB_ERR_BATCH when some scenario
+ * failed; the other scenarios' results are valid (BatchCalculationError semantics, job_dispatch.hpp:208-224). */
+PGMB_API int pgmb_engine_run(pgmb_engine* engine, const pgmb_run_options* opt, const pgmb_pf_input* input,
+                             const pgmb_solver_output* output);
+
+/* Device-resident variant used for kernel timing: stage inputs once, run the solver kernels on them (no host
+ * transfers), read kernel time measured with CUDA events on the engine's stream. */
+PGMB_API int pgmb_engine_stage(pgmb_engine* engine, const pgmb_pf_input* input);
+PGMB_API int pgmb_engine_solve_staged(pgmb_engine* engine, const pgmb_run_options* opt, float* solve_kernel_ms);
+PGMB_API int pgmb_engine_fetch(pgmb_engine* engine, const pgmb_solver_output* output);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * MODEL level (component structs; layouts == the reference's dataset structs, see pgm_b200/structs.py)
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct pgmb_component_buffer {
+    int64_t n;        /* elements (input) or elements per scenario (uniform batch); -1 => sparse batch, use indptr */
+    const int64_t* indptr; /* [n_scenarios + 1] for sparse batches, else NULL */
+    const void* data; /* packed row buffer of the component's struct */
+} pgmb_component_buffer;
+
+/* order = component storage order of the reference (all_components.hpp:36-39), PF subset */
+typedef struct pgmb_input_data {
+    pgmb_component_buffer node, line, transformer, shunt, source, sym_gen, asym_gen, sym_load, asym_load;
+} pgmb_input_data;
+
+typedef struct pgmb_update_data {
+    int64_t n_scenarios;
+    pgmb_component_buffer line, transformer, shunt, source, sym_gen, asym_gen, sym_load, asym_load;
+} pgmb_update_data;
+
+/* caller-owned output buffers [n_scenarios][n_component]; NULL = component not requested
+ * (only components present in the output dataset are produced, main_model_impl.hpp:450-460) */
+typedef struct pgmb_output_data {
+    void *node, *line, *transformer, *shunt, *source, *sym_gen, *asym_gen, *sym_load, *asym_load;
+} pgmb_output_data;
+
+/* PGM_Options (power_grid_model_c/src/options.hpp:16-27), PF subset */
+typedef struct pgmb_options {
+    int32_t calculation_method; /* PGMB_METHOD_* */
+    int32_t symmetric;          /* 1 symmetric, 0 asymmetric */
+    double err_tol;
+    int64_t max_iter;
+    int32_t n_devices;          /* GPUs of this process to shard scenarios over; 0 = all visible */
+    int32_t first_device;
+} pgmb_options;
+
+typedef struct pgmb_model pgmb_model;
+
+/* PGM_create_model (model.h:43-48) */
+PGMB_API int pgmb_model_create(double system_frequency, const pgmb_input_data* input, pgmb_model** out);
+PGMB_API void pgmb_model_destroy(pgmb_model* model);
+/* PGM_update_model (model.h:54): permanent update with scenario 0 of `update` */
+PGMB_API int pgmb_model_update(pgmb_model* model, const pgmb_update_data* update);
+/* PGM_calculate (model.h:116-118): update == NULL => single calculation, else batch.
+ * n_iter / status: optional [n_scenarios] arrays. */
+PGMB_API int pgmb_model_calculate(pgmb_model* model, const pgmb_options* opt, const pgmb_update_data* update,
+                                  const pgmb_output_data* output, int32_t* n_iter, int32_t* status);
+/* Math model export for parity tests (same names as pgmb_engine_get_index plus: slack_bus, phase_shift (f64),
+ * branch_bus_idx, fill_in, sources_per_bus, shunts_per_bus, load_gens_per_bus, load_gen_type, node_coupling ...) */
+PGMB_API int pgmb_model_get_index(pgmb_model* model, int64_t math_group, const char* name, const int64_t** data,
+                                  int64_t* size);
+PGMB_API int pgmb_model_get_real(pgmb_model* model, int64_t math_group, int32_t symmetric, const char* name,
+                                 const double** data, int64_t* size);
+PGMB_API int64_t pgmb_model_n_math_groups(pgmb_model* model);
+/* timing of the last calculate call, milliseconds: [0] host prepare, [1] H2D, [2] solve kernels (CUDA events),
+ * [3] output kernels, [4] D2H, [5] total wall */
+PGMB_API int pgmb_model_last_timing(pgmb_model* model, double* ms6);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Benchmark input: the reference's fictional grid generator (tests/benchmark_cpp/fictional_grid_generator.hpp)
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct pgmb_grid_option {
+    int64_t n_node_total_specified, n_mv_feeder, n_node_per_mv_feeder, n_lv_feeder, n_connection_per_lv_feeder;
+    int32_t has_mv_ring, has_lv_ring;
+} pgmb_grid_option;
+typedef struct pgmb_fictional_grid pgmb_fictional_grid;
+PGMB_API int pgmb_fictional_grid_create(const pgmb_grid_option* option, uint32_t seed, pgmb_fictional_grid** out);
+PGMB_API void pgmb_fictional_grid_destroy(pgmb_fictional_grid* grid);
+/* component in {node,line,transformer,shunt,source,sym_load,asym_load}; data points at packed input structs */
+PGMB_API int pgmb_fictional_grid_get(pgmb_fictional_grid* grid, const char* component, const void** data, int64_t* n);
+/* load-profile batch (generate_batch_input): fills caller buffers [batch_size][n_sym_load] / [batch_size][n_asym_load] */
+PGMB_API int pgmb_fictional_grid_batch(pgmb_fictional_grid* grid, int64_t batch_size, uint32_t seed, void* sym_load_update,
+                                       void* asym_load_update);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGM_B200_H */

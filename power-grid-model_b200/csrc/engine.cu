@@ -1,0 +1,292 @@
+#include "engine.hpp"
+
+#include <cstdlib>
+#include <cstring>
+
+namespace pgmb {
+
+namespace {
+template <class To, class From> std::vector<To> narrow_vec(std::vector<From> const& v) {
+    std::vector<To> out(v.size());
+    for (size_t i = 0; i != v.size(); ++i) out[i] = static_cast<To>(v[i]);
+    return out;
+}
+int env_int(char const* name, int fallback) {
+    char const* v = std::getenv(name);
+    return (v != nullptr && *v != '\0') ? std::atoi(v) : fallback;
+}
+} // namespace
+
+Engine::Engine(MathTopology topo, bool symmetric, int device)
+    : topo_{std::move(topo)}, symmetric_{symmetric}, B_{symmetric ? 1 : 3}, device_{device}, pattern_{topo_}, schedule_{pattern_} {
+    if (device < 0) return; // symbolic-only engine (structure introspection on hosts without a GPU); it cannot run
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+        throw CudaError("no CUDA device available: pgm_b200 has no CPU fallback");
+    }
+    if (device >= n_dev) throw InvalidArgument("device index out of range");
+    if (pattern_.nnz_lu >= (Idx{1} << 30)) throw InvalidArgument("LU pattern too large for 32-bit device indices");
+    PGMB_CUDA(cudaSetDevice(device_));
+    PGMB_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    PGMB_CUDA(cudaEventCreate(&ev0_));
+    PGMB_CUDA(cudaEventCreate(&ev1_));
+    upload_structure();
+}
+
+Engine::~Engine() {
+    if (device_ < 0) return;
+    cudaSetDevice(device_);
+    if (ev0_ != nullptr) cudaEventDestroy(ev0_);
+    if (ev1_ != nullptr) cudaEventDestroy(ev1_);
+    if (stream_ != nullptr) cudaStreamDestroy(stream_);
+}
+
+void Engine::upload_structure() {
+    Idx const n_bus = topo_.n_bus;
+    d_row_ptr_.upload(narrow_vec<int32_t>(pattern_.row_indptr_lu), stream_);
+    d_col_idx_.upload(narrow_vec<int32_t>(pattern_.col_indices_lu), stream_);
+    d_diag_.upload(narrow_vec<int32_t>(pattern_.diag_lu), stream_);
+    d_map_y_.upload(narrow_vec<int32_t>(pattern_.map_lu_y_bus), stream_);
+    d_level_ptr_.upload(schedule_.level_ptr, stream_);
+    d_level_rows_.upload(schedule_.level_rows, stream_);
+    d_upd_ptr_.upload(schedule_.upd_ptr, stream_);
+    d_upd_u_.upload(schedule_.upd_u, stream_);
+    d_upd_a_.upload(schedule_.upd_a, stream_);
+    d_lg_ptr_.upload(narrow_vec<int32_t>(topo_.load_gens_per_bus), stream_);
+    d_src_ptr_.upload(narrow_vec<int32_t>(topo_.sources_per_bus), stream_);
+    d_lg_type_.upload(topo_.load_gen_type, stream_);
+    d_y_row_ptr_.upload(narrow_vec<int32_t>(pattern_.row_indptr), stream_);
+    d_y_col_idx_.upload(narrow_vec<int32_t>(pattern_.col_indices), stream_);
+    d_branch_bus_.upload(narrow_vec<int32_t>(topo_.branch_bus_idx), stream_);
+    auto group_of = [n_bus](std::vector<Idx> const& indptr) {
+        std::vector<int32_t> out(indptr.empty() ? 0 : indptr.back());
+        for (Idx b = 0; b != n_bus; ++b)
+            for (Idx k = indptr[b]; k != indptr[b + 1]; ++k) out[k] = static_cast<int32_t>(b);
+        return out;
+    };
+    d_shunt_bus_.upload(group_of(topo_.shunts_per_bus), stream_);
+    d_lg_bus_.upload(group_of(topo_.load_gens_per_bus), stream_);
+    d_src_bus_.upload(group_of(topo_.sources_per_bus), stream_);
+    d_phase_shift_.upload(topo_.phase_shift, stream_);
+    PGMB_CUDA(cudaStreamSynchronize(stream_)); // temporaries above must outlive the copies
+
+    ds_.n_bus = static_cast<int32_t>(n_bus);
+    ds_.nnz = static_cast<int32_t>(pattern_.nnz);
+    ds_.nnz_lu = static_cast<int32_t>(pattern_.nnz_lu);
+    ds_.n_level = schedule_.n_level();
+    ds_.n_load_gen = static_cast<int32_t>(topo_.n_load_gen());
+    ds_.n_source = static_cast<int32_t>(topo_.n_source());
+    ds_.n_branch = static_cast<int32_t>(topo_.n_branch());
+    ds_.n_shunt = static_cast<int32_t>(topo_.n_shunt());
+    ds_.row_ptr = d_row_ptr_.get();
+    ds_.col_idx = d_col_idx_.get();
+    ds_.diag = d_diag_.get();
+    ds_.map_y = d_map_y_.get();
+    ds_.level_ptr = d_level_ptr_.get();
+    ds_.level_rows = d_level_rows_.get();
+    ds_.upd_ptr = d_upd_ptr_.get();
+    ds_.upd_u = d_upd_u_.get();
+    ds_.upd_a = d_upd_a_.get();
+    ds_.lg_ptr = d_lg_ptr_.get();
+    ds_.lg_type = d_lg_type_.get();
+    ds_.src_ptr = d_src_ptr_.get();
+    ds_.y_row_ptr = d_y_row_ptr_.get();
+    ds_.y_col_idx = d_y_col_idx_.get();
+    ds_.branch_bus = d_branch_bus_.get();
+    ds_.shunt_bus = d_shunt_bus_.get();
+    ds_.lg_bus = d_lg_bus_.get();
+    ds_.src_bus = d_src_bus_.get();
+    ds_.phase_shift = d_phase_shift_.get();
+}
+
+// YBus::update_admittance_entries (y_bus.hpp:400-431): sum of the contributions of each entry, in element order
+void Engine::set_param(double const* branch_param, double const* shunt_param, double const* source_param) {
+    if (device_ >= 0) PGMB_CUDA(cudaSetDevice(device_));
+    int const bb2 = B_ * B_ * 2;
+    branch_param_.assign(branch_param, branch_param + topo_.n_branch() * 4 * bb2);
+    shunt_param_.assign(shunt_param, shunt_param + topo_.n_shunt() * bb2);
+    source_param_.assign(source_param, source_param + topo_.n_source() * 4);
+    admittance_.assign(pattern_.nnz * bb2, 0.0);
+    for (Idx entry = 0; entry != pattern_.nnz; ++entry) {
+        double* y = &admittance_[entry * bb2];
+        for (Idx e = pattern_.y_bus_entry_indptr[entry]; e != pattern_.y_bus_entry_indptr[entry + 1]; ++e) {
+            int const kind = pattern_.element_type[e];
+            double const* src = kind == 4 ? &shunt_param_[pattern_.element_idx[e] * bb2]
+                                          : &branch_param_[(pattern_.element_idx[e] * 4 + kind) * bb2];
+            for (int i = 0; i != bb2; ++i) y[i] += src[i];
+        }
+    }
+    // y_ref tensor of each source (SourceCalcParam::y_ref, calculation_parameters.hpp:215-227)
+    std::vector<double> yref(topo_.n_source() * bb2, 0.0);
+    for (Idx s = 0; s != topo_.n_source(); ++s) {
+        std::complex<double> const y1{source_param_[4 * s], source_param_[4 * s + 1]};
+        std::complex<double> const y0{source_param_[4 * s + 2], source_param_[4 * s + 3]};
+        if (B_ == 1) {
+            yref[2 * s] = y1.real();
+            yref[2 * s + 1] = y1.imag();
+        } else {
+            std::complex<double> const ys = (2.0 * y1 + y0) / 3.0;
+            std::complex<double> const ym = (y0 - y1) / 3.0;
+            for (int r = 0; r != 3; ++r)
+                for (int c = 0; c != 3; ++c) {
+                    std::complex<double> const v = r == c ? ys : ym;
+                    yref[s * bb2 + (r * 3 + c) * 2] = v.real();
+                    yref[s * bb2 + (r * 3 + c) * 2 + 1] = v.imag();
+                }
+        }
+    }
+    param_set_ = true;
+    if (device_ < 0) return;
+    d_ydata_.upload(admittance_, stream_);
+    d_src_yref_.upload(yref, stream_);
+    d_src_y1y0_.upload(source_param_, stream_);
+    d_branch_param_.upload(branch_param_, stream_);
+    d_shunt_param_.upload(shunt_param_, stream_);
+    PGMB_CUDA(cudaStreamSynchronize(stream_));
+    ds_.ydata = d_ydata_.get();
+    ds_.src_yref = d_src_yref_.get();
+    ds_.src_y1y0 = d_src_y1y0_.get();
+    ds_.branch_param = d_branch_param_.get();
+    ds_.shunt_param = d_shunt_param_.get();
+    param_set_ = true;
+}
+
+void Engine::choose_tiling(int64_t n_scn) {
+    cudaDeviceProp prop{};
+    PGMB_CUDA(cudaGetDeviceProperties(&prop, device_));
+    int const sm = prop.multiProcessorCount;
+    int t = 4;
+    for (int cand : {32, 16, 8, 4}) {
+        if ((n_scn + cand - 1) / cand >= (3 * sm) / 4) {
+            t = cand;
+            break;
+        }
+    }
+    tile_width_ = env_int("PGMB_TILE", t);
+    if (tile_width_ != 4 && tile_width_ != 8 && tile_width_ != 16 && tile_width_ != 32) tile_width_ = t;
+    n_slot_ = env_int("PGMB_SLOTS", 512 / tile_width_);
+    if (n_slot_ < 1) n_slot_ = 1;
+    if (n_slot_ * tile_width_ > 1024) n_slot_ = 1024 / tile_width_;
+}
+
+void Engine::stage(PfInputView const& in) {
+    if (device_ < 0) throw CudaError("engine was created without a CUDA device (symbolic only): pgm_b200 has no CPU fallback");
+    if (!param_set_) throw InvalidArgument("pgmb_engine_set_param must be called before running");
+    if (!symmetric_) throw InvalidArgument("asymmetric calculation is not implemented on the GPU yet");
+    PGMB_CUDA(cudaSetDevice(device_));
+    int64_t const n = in.n_scenarios;
+    choose_tiling(n);
+    int const T = tile_width_;
+    int64_t const n_tile = (n + T - 1) / T;
+    int const N = 2 * B_;
+    size_t const nb = static_cast<size_t>(topo_.n_bus);
+    d_jac_.ensure(static_cast<size_t>(n_tile) * pattern_.nnz_lu * N * N * T);
+    d_xvec_.ensure(n_tile * nb * N * T);
+    d_pol_.ensure(n_tile * nb * N * T);
+    d_u_.ensure(n_tile * nb * N * T);
+    d_perm_.ensure(n_tile * nb * T * (B_ == 1 ? 1 : 2 * N));
+    d_sinj_.ensure(static_cast<size_t>(n_tile) * topo_.n_load_gen() * 2 * B_ * T + 1);
+    d_usrc_.ensure(static_cast<size_t>(n_tile) * topo_.n_source() * 2 * T + 1);
+    d_status_.ensure(n + 1);
+    d_n_iter_.ensure(n + 1);
+    d_max_dev_.ensure(n + 1);
+    size_t const n_sinj = static_cast<size_t>(n) * topo_.n_load_gen() * 2 * B_;
+    size_t const n_usrc = static_cast<size_t>(in.source_is_shared ? 1 : n) * topo_.n_source() * 2;
+    d_in_sinj_.ensure(n_sinj + 1);
+    d_in_usrc_.ensure(n_usrc + 1);
+    if (n_sinj != 0) PGMB_CUDA(cudaMemcpyAsync(d_in_sinj_.get(), in.s_injection, n_sinj * sizeof(double), cudaMemcpyHostToDevice, stream_));
+    if (n_usrc != 0) PGMB_CUDA(cudaMemcpyAsync(d_in_usrc_.get(), in.source_u_ref, n_usrc * sizeof(double), cudaMemcpyHostToDevice, stream_));
+    // host layout per load_gen: [B] complex = (re, im) interleaved; tile layout wants re[B], im[B]: for B = 1 identical
+    launch_to_tile(T, d_in_sinj_.get(), d_sinj_.get(), n, static_cast<int>(topo_.n_load_gen()), 2 * B_, 0, stream_);
+    launch_to_tile(T, d_in_usrc_.get(), d_usrc_.get(), n, static_cast<int>(topo_.n_source()), 2, in.source_is_shared ? 1 : 0, stream_);
+    db_.n_scn = n;
+    db_.n_tile = static_cast<int32_t>(n_tile);
+    db_.jac = d_jac_.get();
+    db_.xvec = d_xvec_.get();
+    db_.pol = d_pol_.get();
+    db_.u = d_u_.get();
+    db_.perm = d_perm_.get();
+    db_.sinj = d_sinj_.get();
+    db_.usrc = d_usrc_.get();
+    db_.status = d_status_.get();
+    db_.n_iter = d_n_iter_.get();
+    db_.max_dev = d_max_dev_.get();
+    PGMB_CUDA(cudaStreamSynchronize(stream_));
+}
+
+float Engine::solve_staged(SolveOptions const& opt_in) {
+    if (device_ < 0) throw CudaError("engine was created without a CUDA device (symbolic only)");
+    PGMB_CUDA(cudaSetDevice(device_));
+    if (db_.n_scn == 0) return 0.0f;
+    SolveOptions opt = opt_in;
+    // all loads const_y => the reference forces the linear method (math_solver.hpp:36-37, 48)
+    bool const all_const_y = std::all_of(topo_.load_gen_type.begin(), topo_.load_gen_type.end(), [](int8_t t) { return t == 1; });
+    if (all_const_y) opt.method = 0;
+    if (opt.method == -128) opt.method = 1;
+    last_method_ = opt.method;
+    PGMB_CUDA(cudaEventRecord(ev0_, stream_));
+    switch (opt.method) {
+    case 1:
+        launch_nr_sym(tile_width_, ds_, db_, opt, n_slot_, stream_);
+        break;
+    default:
+        throw InvalidArgument("calculation method " + std::to_string(opt.method) + " is not implemented on the GPU yet");
+    }
+    PGMB_CUDA(cudaGetLastError());
+    PGMB_CUDA(cudaEventRecord(ev1_, stream_));
+    PGMB_CUDA(cudaEventSynchronize(ev1_));
+    float ms = 0.0f;
+    PGMB_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
+    return ms;
+}
+
+void Engine::fetch(SolverOutputView const& out) {
+    if (device_ < 0) throw CudaError("engine was created without a CUDA device (symbolic only)");
+    PGMB_CUDA(cudaSetDevice(device_));
+    int64_t const n = db_.n_scn;
+    if (n == 0) return;
+    int const c2 = 2 * B_;
+    auto want = [&](double* host, DevBuf<double>& buf, size_t per_scn) -> double* {
+        if (host == nullptr) return nullptr;
+        buf.ensure(static_cast<size_t>(n) * per_scn + 1);
+        return buf.get();
+    };
+    double* const du = want(out.u, d_out_u_, topo_.n_bus * c2);
+    double* const di = want(out.bus_injection, d_out_inj_, topo_.n_bus * c2);
+    double* const dbr = want(out.branch, d_out_branch_, topo_.n_branch() * 4 * c2);
+    double* const dsrc = want(out.source, d_out_source_, topo_.n_source() * 2 * c2);
+    double* const dsh = want(out.shunt, d_out_shunt_, topo_.n_shunt() * 2 * c2);
+    double* const dlg = want(out.load_gen, d_out_lg_, topo_.n_load_gen() * 2 * c2);
+    launch_math_result_sym(tile_width_, ds_, db_, last_method_ == 0 ? 1 : 0, du, di, dbr, dsrc, dsh, dlg, stream_);
+    PGMB_CUDA(cudaGetLastError());
+    auto back = [&](void* host, void const* dev, size_t bytes) {
+        if (host != nullptr && bytes != 0) PGMB_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, stream_));
+    };
+    back(out.u, du, sizeof(double) * n * topo_.n_bus * c2);
+    back(out.bus_injection, di, sizeof(double) * n * topo_.n_bus * c2);
+    back(out.branch, dbr, sizeof(double) * n * topo_.n_branch() * 4 * c2);
+    back(out.source, dsrc, sizeof(double) * n * topo_.n_source() * 2 * c2);
+    back(out.shunt, dsh, sizeof(double) * n * topo_.n_shunt() * 2 * c2);
+    back(out.load_gen, dlg, sizeof(double) * n * topo_.n_load_gen() * 2 * c2);
+    back(out.status, d_status_.get(), sizeof(int32_t) * n);
+    back(out.n_iter, d_n_iter_.get(), sizeof(int32_t) * n);
+    back(out.max_dev, d_max_dev_.get(), sizeof(double) * n);
+    PGMB_CUDA(cudaStreamSynchronize(stream_));
+}
+
+int Engine::run(SolveOptions const& opt, PfInputView const& in, SolverOutputView const& out) {
+    stage(in);
+    solve_staged(opt);
+    std::vector<int32_t> status_local;
+    SolverOutputView o = out;
+    if (o.status == nullptr) {
+        status_local.resize(in.n_scenarios);
+        o.status = status_local.data();
+    }
+    fetch(o);
+    int failed = 0;
+    for (int64_t s = 0; s != in.n_scenarios; ++s) failed += o.status[s] != 0 ? 1 : 0;
+    return failed;
+}
+
+} // namespace pgmb

@@ -1,0 +1,159 @@
+// Engine = one math sub-grid on one GPU: symbolic structure (shared by all scenarios), Y-bus values, and the batched
+// solver kernels.  Host-side replacement of YBus<sym> + MathSolver<sym> (math_solver/y_bus.hpp:297-592,
+// math_solver/math_solver.hpp:26-183) for whole batches of scenarios.
+#pragma once
+
+#include "kernels.cuh"
+#include "symbolic.hpp"
+
+#include <cuda_runtime.h>
+
+#include <complex>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace pgmb {
+
+struct CudaError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+struct InvalidArgument : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+#define PGMB_CUDA(expr)                                                                                              \
+    do {                                                                                                             \
+        cudaError_t const err__ = (expr);                                                                            \
+        if (err__ != cudaSuccess) {                                                                                  \
+            throw ::pgmb::CudaError(std::string(#expr) + " failed: " + cudaGetErrorString(err__));                   \
+        }                                                                                                            \
+    } while (0)
+
+// owning device buffer
+template <class T> class DevBuf {
+  public:
+    DevBuf() = default;
+    DevBuf(DevBuf const&) = delete;
+    DevBuf& operator=(DevBuf const&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p_{o.p_}, n_{o.n_} { o.p_ = nullptr; o.n_ = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) {
+            release();
+            p_ = o.p_;
+            n_ = o.n_;
+            o.p_ = nullptr;
+            o.n_ = 0;
+        }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void ensure(size_t n) { // grow-only
+        if (n <= n_) return;
+        release();
+        if (n == 0) return;
+        PGMB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p_), n * sizeof(T)));
+        n_ = n;
+    }
+    void upload(std::vector<T> const& h, cudaStream_t st) {
+        ensure(h.size());
+        if (!h.empty()) PGMB_CUDA(cudaMemcpyAsync(p_, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+    }
+    T* get() const { return p_; }
+    size_t size() const { return n_; }
+
+  private:
+    void release() {
+        if (p_ != nullptr) cudaFree(p_);
+        p_ = nullptr;
+        n_ = 0;
+    }
+    T* p_{nullptr};
+    size_t n_{0};
+};
+
+struct PfInputView {
+    int64_t n_scenarios;
+    double const* source_u_ref;
+    bool source_is_shared;
+    double const* s_injection;
+};
+struct SolverOutputView {
+    double *u, *bus_injection, *branch, *source, *shunt, *load_gen;
+    int32_t *status, *n_iter;
+    double* max_dev;
+};
+
+class Engine {
+  public:
+    Engine(MathTopology topo, bool symmetric, int device);
+    ~Engine();
+    Engine(Engine const&) = delete;
+    Engine& operator=(Engine const&) = delete;
+
+    // branch_param [n_branch][4][B][B], shunt_param [n_shunt][B][B], source_param [n_source][2] (all complex)
+    void set_param(double const* branch_param, double const* shunt_param, double const* source_param);
+
+    void stage(PfInputView const& in);                      // H2D + layout conversion
+    float solve_staged(SolveOptions const& opt);            // kernels only; returns solver-kernel milliseconds
+    void fetch(SolverOutputView const& out);                // result extraction + D2H
+    int run(SolveOptions const& opt, PfInputView const& in, SolverOutputView const& out); // returns #failed
+
+    MathTopology const& topology() const { return topo_; }
+    LuPattern const& pattern() const { return pattern_; }
+    EliminationSchedule const& schedule() const { return schedule_; }
+    std::vector<double> const& admittance() const { return admittance_; } // [nnz][B][B] complex
+    int device() const { return device_; }
+    int phases() const { return B_; }
+    int tile_width() const { return tile_width_; }
+    cudaStream_t stream() const { return stream_; }
+    DevStructure const& dev_structure() const { return ds_; }
+    DevBatch const& dev_batch() const { return db_; }
+    int last_method() const { return last_method_; }
+
+  private:
+    MathTopology topo_;
+    bool symmetric_;
+    int B_;
+    int device_;
+    LuPattern pattern_;
+    EliminationSchedule schedule_;
+    std::vector<double> admittance_;
+    std::vector<double> branch_param_, shunt_param_, source_param_;
+    bool param_set_{false};
+    cudaStream_t stream_{};
+    cudaEvent_t ev0_{}, ev1_{};
+
+    // device structure
+    DevBuf<int32_t> d_row_ptr_, d_col_idx_, d_diag_, d_map_y_, d_level_ptr_, d_level_rows_, d_upd_ptr_, d_upd_u_, d_upd_a_,
+        d_lg_ptr_, d_src_ptr_, d_y_row_ptr_, d_y_col_idx_, d_branch_bus_, d_shunt_bus_, d_lg_bus_, d_src_bus_;
+    DevBuf<int8_t> d_lg_type_;
+    DevBuf<double> d_ydata_, d_src_yref_, d_src_y1y0_, d_branch_param_, d_shunt_param_, d_phase_shift_;
+    DevStructure ds_{};
+
+    // batch buffers
+    int tile_width_{8};
+    int n_slot_{64};
+    DevBuf<double> d_jac_, d_xvec_, d_pol_, d_u_, d_sinj_, d_usrc_, d_max_dev_, d_in_sinj_, d_in_usrc_;
+    DevBuf<double> d_out_u_, d_out_inj_, d_out_branch_, d_out_source_, d_out_shunt_, d_out_lg_;
+    DevBuf<uint8_t> d_perm_;
+    DevBuf<int32_t> d_status_, d_n_iter_;
+    DevBatch db_{};
+    int last_method_{1};
+
+    void upload_structure();
+    void choose_tiling(int64_t n_scn);
+};
+
+// kernel launchers (nr_sym.cu, result_sym.cu)
+void launch_nr_sym(int tile_width, DevStructure const& s, DevBatch const& b, SolveOptions const& opt, int n_slot,
+                   cudaStream_t st);
+void launch_to_tile(int tile_width, double const* src, double* dst, int64_t n_scn, int n_item, int n_comp, int shared_src,
+                    cudaStream_t st);
+void launch_from_tile(int tile_width, double const* src, double* dst, int64_t n_scn, int n_item, int n_comp,
+                      cudaStream_t st);
+void launch_math_result_sym(int tile_width, DevStructure const& s, DevBatch const& b, int force_const_y, double* out_u,
+                            double* out_inj, double* out_branch, double* out_source, double* out_shunt, double* out_lg,
+                            cudaStream_t st);
+
+} // namespace pgmb

@@ -1,0 +1,69 @@
+// Device-side data layout shared by the kernels and the engine (host).
+//
+// Scenario-interleaved structure of arrays: scenarios are grouped in tiles of T consecutive scenarios; every per-scenario
+// quantity q[item][component] of a tile is stored as q[item][component][T] (scenario fastest), so the T lanes that work
+// on the same matrix entry for T scenarios touch T consecutive doubles (T*8 bytes, 2 sectors for T = 8, 8 for T = 32).
+// One thread block owns one tile for the whole Newton-Raphson loop: no grid-wide synchronisation is ever needed.
+#pragma once
+
+#include <cstdint>
+
+namespace pgmb {
+
+struct DevStructure {
+    int32_t n_bus, nnz, nnz_lu, n_level, n_load_gen, n_source, n_branch, n_shunt;
+    // LU pattern (with fill-ins), CSR
+    int32_t const* row_ptr;   // [n_bus + 1]
+    int32_t const* col_idx;   // [nnz_lu]
+    int32_t const* diag;      // [n_bus]
+    int32_t const* map_y;     // [nnz_lu] -> Y-bus entry, -1 for fill-ins
+    // elimination schedule
+    int32_t const* level_ptr;  // [n_level + 1]
+    int32_t const* level_rows; // [n_bus]
+    int32_t const* upd_ptr;    // [nnz_lu + 1]
+    int32_t const* upd_u;      // U entry (c, j)
+    int32_t const* upd_a;      // target entry (k, j)
+    // appliances per bus
+    int32_t const* lg_ptr;    // [n_bus + 1]
+    int8_t const* lg_type;    // [n_load_gen]
+    int32_t const* src_ptr;   // [n_bus + 1]
+    // Y-bus CSR (without fill-ins) for result extraction
+    int32_t const* y_row_ptr; // [n_bus + 1]
+    int32_t const* y_col_idx; // [nnz]
+    // branches / shunts for result extraction
+    int32_t const* branch_bus; // [n_branch][2]
+    int32_t const* shunt_bus;  // [n_shunt]
+    int32_t const* lg_bus;     // [n_load_gen]
+    int32_t const* src_bus;    // [n_source]
+    // values shared by all scenarios (complex, B x B row-major)
+    double const* ydata;        // [nnz][B*B][2]
+    double const* src_yref;     // [n_source][B*B][2]   y_ref tensor of each source
+    double const* src_y1y0;     // [n_source][2][2]     y1, y0
+    double const* branch_param; // [n_branch][4][B*B][2]
+    double const* shunt_param;  // [n_shunt][B*B][2]
+    double const* phase_shift;  // [n_bus]
+};
+
+// per-batch device buffers, tile layout (see above); B = phases, N = 2B
+struct DevBatch {
+    int64_t n_scn;
+    int32_t n_tile;
+    double* jac;   // [tile][nnz_lu][N*N][T]   NR Jacobian / LU factors (col-major blocks)
+    double* xvec;  // [tile][n_bus][N][T]      rhs -> forward-substituted -> solution of the linear system
+    double* pol;   // [tile][n_bus][N][T]      theta[B], V[B]
+    double* u;     // [tile][n_bus][2B][T]     re[B], im[B]
+    uint8_t* perm; // [tile][n_bus][2*N][T]    block permutations p[N], q[N]  (sym: packed into one byte: bit0 p, bit1 q)
+    double* sinj;  // [tile][n_load_gen][2B][T] re[B], im[B]
+    double* usrc;  // [tile][n_source][2][T]   source reference voltage (re, im)
+    int32_t* status; // [n_scn]
+    int32_t* n_iter; // [n_scn]
+    double* max_dev; // [n_scn]
+};
+
+struct SolveOptions {
+    int32_t method;
+    double err_tol;
+    int32_t max_iter;
+};
+
+} // namespace pgmb

@@ -1,0 +1,193 @@
+// Symbolic stage of the engine (host, once per topology): Y-bus CSR, LU pattern with fill-ins, and the elimination
+// schedule every scenario shares.
+//
+// Replaces, for the GPU engine, what the reference computes in
+//   YBusStructure::YBusStructure            (math_solver/y_bus.hpp:122-293)   -> LuPattern
+//   the index walk of SparseLUSolver::prefactorize (col_position_idx / find_entry,
+//                                            math_solver/sparse_lu_solver.hpp:360, 402-414, 437-489, 734-748)
+//                                                                              -> EliminationSchedule
+// The reference redoes that index walk inside every factorisation; here it is flattened once into integer arrays:
+// for every strictly-lower entry (k, c) the list of (U entry (c, j), target entry (k, j)) pairs, and rows grouped into
+// dependency levels (row k depends on the rows c < k it has an entry for), so that a thread block can process all rows
+// of a level concurrently.  Row-by-row ("IKJ") elimination performs exactly the reference's floating-point operations
+// on each entry, in the same order (updates to an entry arrive in ascending pivot order).
+#pragma once
+
+#include <algorithm>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace pgmb {
+
+using Idx = int64_t;
+
+struct MathTopology {
+    Idx n_bus{};
+    std::vector<double> phase_shift;
+    std::vector<Idx> branch_bus_idx; // [n_branch][2]
+    std::vector<Idx> fill_in;        // [n_fill][2]
+    std::vector<Idx> sources_per_bus, shunts_per_bus, load_gens_per_bus; // indptr
+    std::vector<int8_t> load_gen_type;
+    Idx slack_bus{};
+    bool is_radial{};
+
+    Idx n_branch() const { return static_cast<Idx>(branch_bus_idx.size() / 2); }
+    Idx n_fill() const { return static_cast<Idx>(fill_in.size() / 2); }
+    Idx n_source() const { return sources_per_bus.empty() ? 0 : sources_per_bus.back(); }
+    Idx n_shunt() const { return shunts_per_bus.empty() ? 0 : shunts_per_bus.back(); }
+    Idx n_load_gen() const { return load_gens_per_bus.empty() ? 0 : load_gens_per_bus.back(); }
+};
+
+// element kinds follow YBusElementType (common/enum.hpp:79-87): 0..3 = branch ff/ft/tf/tt, 4 = shunt
+struct LuPattern {
+    Idx n_bus{}, nnz{}, nnz_lu{};
+    std::vector<Idx> row_indptr, col_indices, bus_entry;
+    std::vector<Idx> y_bus_entry_indptr;
+    std::vector<int8_t> element_type;
+    std::vector<Idx> element_idx;
+    std::vector<Idx> row_indptr_lu, col_indices_lu, diag_lu, map_lu_y_bus, lu_transpose_entry;
+
+    explicit LuPattern(MathTopology const& topo) {
+        n_bus = topo.n_bus;
+        struct Item {
+            Idx row, col;
+            int8_t kind; // 0..4 as above, 5 = fill-in
+            Idx idx;
+        };
+        std::vector<Item> items;
+        items.reserve(4 * topo.n_branch() + topo.n_shunt() + 2 * topo.n_fill());
+        for (Idx b = 0; b != topo.n_branch(); ++b) {
+            Idx const side[2] = {topo.branch_bus_idx[2 * b], topo.branch_bus_idx[2 * b + 1]};
+            for (int k = 0; k != 4; ++k) {
+                Idx const r = side[k / 2], c = side[k % 2];
+                if (r != -1 && c != -1) items.push_back({r, c, static_cast<int8_t>(k), b});
+            }
+        }
+        for (Idx bus = 0; bus != n_bus; ++bus)
+            for (Idx s = topo.shunts_per_bus[bus]; s != topo.shunts_per_bus[bus + 1]; ++s) items.push_back({bus, bus, 4, s});
+        for (Idx f = 0; f != topo.n_fill(); ++f) {
+            Idx const i = topo.fill_in[2 * f], j = topo.fill_in[2 * f + 1];
+            if (i != -1 && j != -1) {
+                items.push_back({i, j, 5, f});
+                items.push_back({j, i, 5, f});
+            }
+        }
+        // the reference's two-pass stable counting sort == one stable sort on (row, col): contributions to one entry
+        // keep their insertion order, which fixes the floating-point summation order of the admittance
+        std::stable_sort(items.begin(), items.end(),
+                         [](Item const& x, Item const& y) { return x.row != y.row ? x.row < y.row : x.col < y.col; });
+
+        row_indptr.assign(n_bus + 1, 0);
+        row_indptr_lu.assign(n_bus + 1, 0);
+        bus_entry.assign(n_bus, -1);
+        diag_lu.assign(n_bus, -1);
+        y_bus_entry_indptr.push_back(0);
+        if (items.empty()) { // single bus without branch or shunt: one artificial diagonal entry
+            if (n_bus != 1) throw std::invalid_argument("math topology has a bus without any admittance entry");
+            row_indptr = {0, 1};
+            col_indices = {0};
+            bus_entry = {0};
+            y_bus_entry_indptr = {0, 0};
+            row_indptr_lu = {0, 1};
+            col_indices_lu = {0};
+            diag_lu = {0};
+            map_lu_y_bus = {0};
+            lu_transpose_entry = {0};
+            nnz = nnz_lu = 1;
+            return;
+        }
+        for (size_t i = 0; i != items.size();) {
+            Idx const r = items[i].row, c = items[i].col;
+            bool const fill = items[i].kind == 5;
+            size_t j = i;
+            while (j != items.size() && items[j].row == r && items[j].col == c) ++j;
+            col_indices_lu.push_back(c);
+            ++row_indptr_lu[r + 1];
+            if (fill) {
+                if (j - i != 1) throw std::invalid_argument("fill-in duplicates an existing Y-bus entry");
+                map_lu_y_bus.push_back(-1);
+            } else {
+                map_lu_y_bus.push_back(static_cast<Idx>(col_indices.size()));
+                if (r == c) {
+                    bus_entry[r] = static_cast<Idx>(col_indices.size());
+                    diag_lu[r] = static_cast<Idx>(col_indices_lu.size()) - 1;
+                }
+                col_indices.push_back(c);
+                ++row_indptr[r + 1];
+                for (size_t e = i; e != j; ++e) {
+                    element_type.push_back(items[e].kind);
+                    element_idx.push_back(items[e].idx);
+                }
+                y_bus_entry_indptr.push_back(static_cast<Idx>(element_type.size()));
+            }
+            i = j;
+        }
+        for (Idx r = 0; r != n_bus; ++r) {
+            row_indptr[r + 1] += row_indptr[r];
+            row_indptr_lu[r + 1] += row_indptr_lu[r];
+            if (diag_lu[r] < 0) throw std::invalid_argument("math topology has a bus without a diagonal entry");
+        }
+        nnz = row_indptr.back();
+        nnz_lu = row_indptr_lu.back();
+        lu_transpose_entry.resize(nnz_lu);
+        for (Idx r = 0; r != n_bus; ++r)
+            for (Idx k = row_indptr_lu[r]; k != row_indptr_lu[r + 1]; ++k) lu_transpose_entry[k] = find_lu(col_indices_lu[k], r);
+    }
+
+    Idx find_lu(Idx row, Idx col) const {
+        auto const first = col_indices_lu.begin() + row_indptr_lu[row];
+        auto const last = col_indices_lu.begin() + row_indptr_lu[row + 1];
+        auto const it = std::lower_bound(first, last, col);
+        if (it == last || *it != col) {
+            throw std::invalid_argument("LU pattern is not structurally symmetric / closed under fill-in at (" +
+                                        std::to_string(row) + ", " + std::to_string(col) + ")");
+        }
+        return static_cast<Idx>(it - col_indices_lu.begin());
+    }
+};
+
+struct EliminationSchedule {
+    // for LU entry e: pairs [upd_ptr[e], upd_ptr[e+1]) -- non-empty only for strictly-lower entries (k, c):
+    //   upd_u = entry (c, j), upd_a = entry (k, j), for every j > c in row c, ascending j
+    std::vector<int32_t> upd_ptr, upd_u, upd_a;
+    // rows grouped by dependency level, ascending row inside a level
+    std::vector<int32_t> level_ptr, level_rows;
+    std::vector<int32_t> row_level;
+    int32_t max_row_entries{};
+    int64_t n_block_updates{};
+
+    explicit EliminationSchedule(LuPattern const& p) {
+        Idx const n = p.n_bus;
+        upd_ptr.assign(p.nnz_lu + 1, 0);
+        row_level.assign(n, 0);
+        for (Idx k = 0; k != n; ++k) {
+            max_row_entries = std::max<int32_t>(max_row_entries, static_cast<int32_t>(p.row_indptr_lu[k + 1] - p.row_indptr_lu[k]));
+            int32_t level = 0;
+            for (Idx e = p.row_indptr_lu[k]; e != p.diag_lu[k]; ++e) {
+                Idx const c = p.col_indices_lu[e];
+                level = std::max(level, row_level[c] + 1);
+                for (Idx ue = p.diag_lu[c] + 1; ue != p.row_indptr_lu[c + 1]; ++ue) {
+                    upd_u.push_back(static_cast<int32_t>(ue));
+                    upd_a.push_back(static_cast<int32_t>(p.find_lu(k, p.col_indices_lu[ue])));
+                }
+                upd_ptr[e + 1] = static_cast<int32_t>(upd_u.size());
+            }
+            // entries from the diagonal on carry no updates
+            for (Idx e = p.diag_lu[k]; e != p.row_indptr_lu[k + 1]; ++e) upd_ptr[e + 1] = static_cast<int32_t>(upd_u.size());
+            row_level[k] = level;
+        }
+        n_block_updates = static_cast<int64_t>(upd_u.size());
+        int32_t const n_level = n == 0 ? 0 : *std::max_element(row_level.begin(), row_level.end()) + 1;
+        level_ptr.assign(n_level + 1, 0);
+        for (Idx k = 0; k != n; ++k) ++level_ptr[row_level[k] + 1];
+        for (int32_t l = 0; l != n_level; ++l) level_ptr[l + 1] += level_ptr[l];
+        level_rows.resize(n);
+        std::vector<int32_t> cursor(level_ptr.begin(), level_ptr.end() - 1);
+        for (Idx k = 0; k != n; ++k) level_rows[cursor[row_level[k]]++] = static_cast<int32_t>(k);
+    }
+    int32_t n_level() const { return static_cast<int32_t>(level_ptr.size()) - 1; }
+};
+
+} // namespace pgmb

@@ -104,3 +104,56 @@ def three_bus_grid(sym=True, const_z=False, diverge=False, singular=False):
         "bus_injection": np.array([pw(np.conj(branch0_i_f) * u0), pw(np.conj(branch0_i_t) * u1 + np.conj(branch1_i_f) * u1), pw(0.0)]),
     }
     return grid, expected
+
+
+def random_grid(n_node, n_extra_edges=0, seed=0, n_shunt=2, n_source=1):
+    """Random symmetric math grid: a random tree plus `n_extra_edges` mesh edges, ordered by the (pinned) oracle
+    symbolic stage so that radial grids have no fill-ins and meshed ones carry the reference's fill-in list."""
+    rng = np.random.default_rng(seed)
+    edges = [(int(rng.integers(0, i)), i) for i in range(1, n_node)]
+    while len(edges) < n_node - 1 + n_extra_edges:
+        a, b = (int(x) for x in rng.integers(0, n_node, 2))
+        if a != b:
+            edges.append((a, b))
+    n_branch = len(edges)
+    src_nodes = [0] + [int(x) for x in rng.integers(1, n_node, n_source - 1)]
+    shunt_nodes = [int(x) for x in rng.integers(0, n_node, n_shunt)]
+    lg_nodes = [int(x) for x in rng.integers(1, n_node, int(1.5 * n_node))]
+    lg_types = rng.integers(0, 3, len(lg_nodes))
+    bag = orc.topology(n_node, edges, [[1, 1]] * n_branch, [0.0] * n_branch, src_nodes, [1] * n_source,
+                       shunt_node_idx=shunt_nodes, load_gen_node_idx=lg_nodes, load_gen_type=lg_types)
+    assert bag.i64("n_math")[0] == 1
+    n_lg = len(lg_nodes)
+    # parameters in component order, then permuted into math order through the coupling
+    z = rng.uniform(0.002, 0.02, n_branch) + 1j * rng.uniform(0.005, 0.05, n_branch)
+    ys = 1.0 / z
+    ysh = 1j * rng.uniform(0.0, 1e-3, n_branch)
+    tap = np.where(rng.random(n_branch) < 0.1, rng.uniform(0.95, 1.05, n_branch), 1.0)
+    bp_comp = np.stack([(ys + 0.5 * ysh) / tap**2, -ys / tap, -ys / tap, ys + 0.5 * ysh], axis=1)
+    coup_branch = bag.i64("coup.branch").reshape(-1, 2)
+    bp = np.zeros_like(bp_comp)
+    bp[coup_branch[:, 1]] = bp_comp
+    sh_comp = rng.uniform(0, 0.01, n_shunt) + 1j * rng.uniform(-0.02, 0.02, n_shunt)
+    sh = np.zeros_like(sh_comp)
+    sh[bag.i64("coup.shunt").reshape(-1, 2)[:, 1]] = sh_comp
+    src_param = np.tile(np.array([[1.0 / (0.0005 + 0.005j), 1.0 / (0.001 + 0.01j)]]), (n_source, 1))
+    grid = orc.MathGrid(
+        sym=True, phase_shift=bag.f64("g0.phase_shift"), branch_bus_idx=bag.i64("g0.branch_bus_idx"),
+        sources_per_bus=bag.i64("g0.sources_per_bus"), shunts_per_bus=bag.i64("g0.shunts_per_bus"),
+        load_gens_per_bus=bag.i64("g0.load_gens_per_bus"), load_gen_type=bag.i64("g0.load_gen_type"),
+        branch_param=bp, shunt_param=sh, source_param=src_param, source_u_ref=[1.02] * n_source,
+        s_injection=np.zeros(n_lg), fill_in=bag.i64("g0.fill_in"),
+    )
+    return grid
+
+
+def random_scenarios(grid, n_scn, seed=0, scale=0.6):
+    """(n_scn, n_load_gen) complex per-unit injections (loads negative) and (n_scn, n_source) reference voltages"""
+    rng = np.random.default_rng(seed + 1000)
+    n_lg = len(grid.load_gen_type)
+    p = -rng.uniform(0.0, scale / max(n_lg, 1), (n_scn, n_lg)) * rng.uniform(0.0, 2.0, (n_scn, 1))
+    q = p * rng.uniform(-0.2, 0.6, (n_scn, n_lg))
+    gen = rng.random((n_scn, n_lg)) < 0.1
+    s = np.where(gen, -0.5 * (p + 1j * q), p + 1j * q)
+    u_ref = rng.uniform(0.98, 1.06, (n_scn, len(grid.source_u_ref))) * np.exp(1j * rng.uniform(-0.05, 0.05, (n_scn, 1)))
+    return s, u_ref
