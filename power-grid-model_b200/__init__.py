@@ -2,3 +2,5 @@
 from . import structs  # noqa: F401
 from ._lib import BatchError, PgmB200Error, lib  # noqa: F401
 from .engine import Engine  # noqa: F401
+from .fictional_grid import BENCHMARK_OPTION, FictionalGrid  # noqa: F401
+from .model import PowerGridModel  # noqa: F401

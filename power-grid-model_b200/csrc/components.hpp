@@ -1,0 +1,455 @@
+// Physical component data -> per-unit calculation parameters and back to physical outputs (host).
+// Formulas follow the reference operation by operation so that parameters are bit-identical:
+//   Branch::calc_param_y_sym / calc_param_y_asym   component/branch.hpp:197-245
+//   Line                                           component/line.hpp:26-58
+//   Transformer::transformer_params / *_calc_param component/transformer.hpp:181-345, transformer_utils.hpp:33-47
+//   Source::math_param / calc_param                component/source.hpp:40-48, 64
+//   Shunt::calc_param / update_params              component/shunt.hpp:37-51, 86-98
+//   LoadGen::set_power / calc_param                component/load_gen.hpp:86-95, 124-139
+// Struct layouts are the reference's dataset structs (auxiliary/input.hpp, update.hpp, output.hpp).
+// Design: plain records + free functions (no class hierarchy, no virtual dispatch); a parameter is a small complex
+// tensor written straight into the flat arrays the engine uploads.
+#pragma once
+
+#include <cmath>
+#include <complex>
+#include <cstdint>
+#include <limits>
+#include <numbers>
+
+namespace pgmb {
+
+using ID = int32_t;
+using IntS = int8_t;
+using cplx = std::complex<double>;
+
+constexpr double kNaN = std::numeric_limits<double>::quiet_NaN();
+constexpr IntS kNaIntS = std::numeric_limits<IntS>::min();
+constexpr ID kNaID = std::numeric_limits<ID>::min();
+constexpr double kSqrt3 = std::numbers::sqrt3;
+constexpr double kPi = std::numbers::pi;
+constexpr double kDeg30 = (1.0 / 6.0) * kPi;
+constexpr double kBasePower3p = 1e6;
+constexpr double kBasePower1p = kBasePower3p / 3.0;
+constexpr double kNumTol = 1e-8;
+constexpr cplx kA2{-0.5, -kSqrt3 / 2.0};
+constexpr cplx kA{-0.5, kSqrt3 / 2.0};
+
+// ---- dataset structs ------------------------------------------------------------------------------------------
+struct NodeInput {
+    ID id;
+    double u_rated;
+};
+struct LineInput {
+    ID id, from_node, to_node;
+    IntS from_status, to_status;
+    double r1, x1, c1, tan1, r0, x0, c0, tan0, i_n;
+};
+struct TransformerInput {
+    ID id, from_node, to_node;
+    IntS from_status, to_status;
+    double u1, u2, sn, uk, pk, i0, p0, i0_zero_sequence, p0_zero_sequence;
+    IntS winding_from, winding_to, clock, tap_side, tap_pos, tap_min, tap_max, tap_nom;
+    double tap_size, uk_min, uk_max, pk_min, pk_max, r_grounding_from, x_grounding_from, r_grounding_to, x_grounding_to;
+};
+struct SourceInput {
+    ID id, node;
+    IntS status;
+    double u_ref, u_ref_angle, sk, rx_ratio, z01_ratio;
+};
+struct ShuntInput {
+    ID id, node;
+    IntS status;
+    double g1, b1, g0, b0;
+};
+struct SymLoadGenInput {
+    ID id, node;
+    IntS status, type;
+    double p_specified, q_specified;
+};
+struct AsymLoadGenInput {
+    ID id, node;
+    IntS status, type;
+    double p_specified[3], q_specified[3];
+};
+struct BranchUpdate {
+    ID id;
+    IntS from_status, to_status;
+};
+struct TransformerUpdate {
+    ID id;
+    IntS from_status, to_status, tap_pos;
+};
+struct SourceUpdate {
+    ID id;
+    IntS status;
+    double u_ref, u_ref_angle, sk, rx_ratio, z01_ratio;
+};
+struct ShuntUpdate {
+    ID id;
+    IntS status;
+    double g1, b1, g0, b0;
+};
+struct SymLoadGenUpdate {
+    ID id;
+    IntS status;
+    double p_specified, q_specified;
+};
+struct AsymLoadGenUpdate {
+    ID id;
+    IntS status;
+    double p_specified[3], q_specified[3];
+};
+template <int B> struct NodeOutput {
+    ID id;
+    IntS energized;
+    double u_pu[B], u[B], u_angle[B], p[B], q[B];
+};
+template <int B> struct BranchOutput {
+    ID id;
+    IntS energized;
+    double loading;
+    double p_from[B], q_from[B], i_from[B], s_from[B], p_to[B], q_to[B], i_to[B], s_to[B];
+};
+template <int B> struct ApplianceOutput {
+    ID id;
+    IntS energized;
+    double p[B], q[B], i[B], s[B], pf[B];
+};
+static_assert(sizeof(NodeInput) == 16 && sizeof(LineInput) == 88 && sizeof(TransformerInput) == 168);
+static_assert(sizeof(SourceInput) == 56 && sizeof(ShuntInput) == 48 && sizeof(SymLoadGenInput) == 32);
+static_assert(sizeof(AsymLoadGenInput) == 64 && sizeof(SymLoadGenUpdate) == 24 && sizeof(AsymLoadGenUpdate) == 56);
+static_assert(sizeof(NodeOutput<1>) == 48 && sizeof(NodeOutput<3>) == 128 && sizeof(BranchOutput<1>) == 80);
+static_assert(sizeof(BranchOutput<3>) == 208 && sizeof(ApplianceOutput<1>) == 48 && sizeof(ApplianceOutput<3>) == 128);
+
+// ---- mutable state of the components (what updates may change) --------------------------------------------------------
+struct BranchState {
+    bool from_status, to_status;
+};
+struct TransformerState {
+    IntS tap_pos;
+};
+struct SourceState {
+    bool status;
+    double u_ref, u_ref_angle, sk, rx_ratio, z01_ratio;
+};
+struct ShuntState {
+    bool status;
+    double g1, b1, g0, b0;
+    cplx y1, y0;
+};
+struct LoadGenState {
+    bool status;
+    cplx s[3]; // per-unit specified power in injection direction; [0] only for symmetric loads
+};
+
+// write a B x B complex tensor (row-major, interleaved) --------------------------------------------------------------
+template <int B> inline void put_scalar_tensor(double* out, cplx const& s, cplx const& m) {
+    for (int r = 0; r != B; ++r)
+        for (int c = 0; c != B; ++c) {
+            cplx const v = (r == c) ? s : m;
+            out[2 * (r * B + c)] = v.real();
+            out[2 * (r * B + c) + 1] = v.imag();
+        }
+}
+
+// ---- branches -----------------------------------------------------------------------------------------------------
+struct SymBranchParam {
+    cplx yff{}, yft{}, ytf{}, ytt{};
+};
+
+// pi-model seen from the "to" side with complex tap ratio (branch.hpp:197-227)
+inline SymBranchParam branch_pi_model(bool from_status, bool to_status, cplx const& y_series, cplx const& y_shunt,
+                                      cplx const& tap_ratio) {
+    double const tap = std::sqrt(std::norm(tap_ratio));
+    SymBranchParam p;
+    if (!(from_status && to_status)) {
+        if (from_status || to_status) {
+            cplx branch_shunt;
+            if (std::sqrt(std::norm(y_shunt)) < kNumTol) {
+                branch_shunt = 0.0;
+            } else {
+                branch_shunt = 0.5 * y_shunt + 1.0 / (1.0 / y_series + 2.0 / y_shunt);
+            }
+            p.yff = from_status ? (1.0 / tap / tap) * branch_shunt : 0.0;
+            p.ytt = to_status ? branch_shunt : 0.0;
+        }
+    } else {
+        p.ytt = y_series + 0.5 * y_shunt;
+        p.yff = (1.0 / tap / tap) * p.ytt;
+        p.yft = (-1.0 / std::conj(tap_ratio)) * y_series;
+        p.ytf = (-1.0 / tap_ratio) * y_series;
+    }
+    return p;
+}
+
+struct LineConst { // derived once at construction (line.hpp:26-36)
+    double base_i;
+    cplx y1_series, y1_shunt, y0_series, y0_shunt;
+};
+inline LineConst line_constants(LineInput const& in, double system_frequency, double u_rated) {
+    LineConst c;
+    c.base_i = kBasePower3p / u_rated / kSqrt3;
+    double const base_y = c.base_i / (u_rated / kSqrt3);
+    cplx const j{0.0, 1.0};
+    c.y1_series = 1.0 / (in.r1 + j * in.x1) / base_y;
+    c.y1_shunt = 2.0 * kPi * system_frequency * in.c1 / base_y * (in.tan1 + j);
+    c.y0_series = 1.0 / (in.r0 + j * in.x0) / base_y;
+    c.y0_shunt = 2.0 * kPi * system_frequency * in.c0 / base_y * (in.tan0 + j);
+    return c;
+}
+// out: [4][B][B] complex
+template <int B> inline void line_param(LineConst const& c, BranchState const& st, double* out) {
+    SymBranchParam const p1 = branch_pi_model(st.from_status, st.to_status, c.y1_series, c.y1_shunt, 1.0);
+    cplx const v1[4] = {p1.yff, p1.yft, p1.ytf, p1.ytt};
+    if constexpr (B == 1) {
+        for (int k = 0; k != 4; ++k) put_scalar_tensor<1>(out + 2 * k, v1[k], 0.0);
+    } else {
+        SymBranchParam const p0 = branch_pi_model(st.from_status, st.to_status, c.y0_series, c.y0_shunt, 1.0);
+        cplx const v0[4] = {p0.yff, p0.yft, p0.ytf, p0.ytt};
+        for (int k = 0; k != 4; ++k) put_scalar_tensor<3>(out + 18 * k, (2.0 * v1[k] + v0[k]) / 3.0, (v0[k] - v1[k]) / 3.0);
+    }
+}
+
+struct TransformerConst { // transformer.hpp:33-83
+    double u1, u2, sn, tap_size, uk, pk, i0, p0, i0_zero, p0_zero;
+    IntS winding_from, winding_to, clock, tap_side, tap_min, tap_max, tap_nom, tap_direction;
+    double uk_min, uk_max, pk_min, pk_max;
+    double base_i_from, base_i_to, nominal_ratio;
+    cplx z_grounding_from, z_grounding_to;
+    IntS initial_tap_pos;
+    bool clock_valid;
+};
+inline IntS tap_limit(TransformerConst const& c, IntS tap) {
+    tap = std::min(tap, std::max(c.tap_max, c.tap_min));
+    tap = std::max(tap, std::min(c.tap_max, c.tap_min));
+    return tap;
+}
+inline TransformerConst transformer_constants(TransformerInput const& in, double u1_rated, double u2_rated) {
+    auto nan_or = [](double v, double fallback) { return std::isnan(v) ? fallback : v; };
+    auto z_pu = [](double r, double x, double u) {
+        r = std::isnan(r) ? 0 : r;
+        x = std::isnan(x) ? 0 : x;
+        double const base_z = u * u / kBasePower3p;
+        return cplx{r / base_z, x / base_z};
+    };
+    TransformerConst c{};
+    c.u1 = in.u1;
+    c.u2 = in.u2;
+    c.sn = in.sn;
+    c.tap_size = in.tap_size;
+    c.uk = in.uk;
+    c.pk = in.pk;
+    c.i0 = in.i0;
+    c.p0 = in.p0;
+    c.i0_zero = nan_or(in.i0_zero_sequence, c.i0);
+    c.p0_zero = std::isnan(in.p0_zero_sequence) ? c.p0 + c.pk * (c.i0_zero * c.i0_zero - c.i0 * c.i0) : in.p0_zero_sequence;
+    c.winding_from = in.winding_from;
+    c.winding_to = in.winding_to;
+    c.tap_side = in.tap_side;
+    c.tap_min = in.tap_min;
+    c.tap_max = in.tap_max;
+    c.tap_nom = in.tap_nom == kNaIntS ? IntS{0} : in.tap_nom;
+    c.tap_direction = c.tap_max > c.tap_min ? IntS{1} : IntS{-1};
+    c.uk_min = nan_or(in.uk_min, c.uk);
+    c.uk_max = nan_or(in.uk_max, c.uk);
+    c.pk_min = nan_or(in.pk_min, c.pk);
+    c.pk_max = nan_or(in.pk_max, c.pk);
+    c.base_i_from = kBasePower3p / u1_rated / kSqrt3;
+    c.base_i_to = kBasePower3p / u2_rated / kSqrt3;
+    c.nominal_ratio = u1_rated / u2_rated;
+    c.z_grounding_from = z_pu(in.r_grounding_from, in.x_grounding_from, u1_rated);
+    c.z_grounding_to = z_pu(in.r_grounding_to, in.x_grounding_to, u2_rated);
+    IntS const tap0 = in.tap_pos == kNaIntS ? c.tap_nom : in.tap_pos;
+    bool const even = (in.clock % 2) == 0;
+    bool const from_wye = in.winding_from == 0 || in.winding_from == 1;
+    bool const to_wye = in.winding_to == 0 || in.winding_to == 1;
+    c.clock_valid = (even == (from_wye == to_wye));
+    c.clock = static_cast<IntS>((in.clock % 12 + 12) % 12);
+    c.initial_tap_pos = tap_limit(c, tap0);
+    return c;
+}
+inline double tap_adjust_impedance(double tap_pos, double tap_min, double tap_max, double tap_nom, double xk, double xk_min,
+                                   double xk_max) {
+    if (tap_pos <= std::max(tap_nom, tap_max) && tap_pos >= std::min(tap_nom, tap_max)) {
+        if (tap_max == tap_nom) return xk;
+        double const step = (xk_max - xk) / (tap_max - tap_nom);
+        return xk + (tap_pos - tap_nom) * step;
+    }
+    if (tap_min == tap_nom) return xk;
+    double const step = (xk_min - xk) / (tap_min - tap_nom);
+    return xk + (tap_pos - tap_nom) * step;
+}
+template <int B>
+inline void transformer_param(TransformerConst const& c, BranchState const& st, IntS tap_pos, double* out) {
+    cplx const j{0.0, 1.0};
+    // transformer_params (transformer.hpp:181-241)
+    double const base_y_to = c.base_i_to * c.base_i_to / kBasePower1p;
+    double u1 = c.u1, u2 = c.u2;
+    if (c.tap_side == 0) {
+        u1 += c.tap_direction * (tap_pos - c.tap_nom) * c.tap_size;
+    } else {
+        u2 += c.tap_direction * (tap_pos - c.tap_nom) * c.tap_size;
+    }
+    double const k = (u1 / u2) / c.nominal_ratio;
+    double const uk = tap_adjust_impedance(tap_pos, c.tap_min, c.tap_max, c.tap_nom, c.uk, c.uk_min, c.uk_max);
+    double const pk = tap_adjust_impedance(tap_pos, c.tap_min, c.tap_max, c.tap_nom, c.pk, c.pk_min, c.pk_max);
+    cplx z_series{};
+    double const uk_sign = (uk >= 0) ? 1.0 : -1.0;
+    double const z_abs = std::abs(uk) * u2 * u2 / c.sn;
+    z_series.real(pk * u2 * u2 / c.sn / c.sn);
+    double const zi2 = z_abs * z_abs - z_series.real() * z_series.real();
+    z_series.imag(uk_sign * (zi2 > 0.0 ? std::sqrt(zi2) : 0.0));
+    cplx const y_series = (1.0 / z_series) / base_y_to;
+    auto magnetising = [&](double i0, double p0) {
+        cplx y;
+        double const y_abs = i0 * c.sn / u2 / u2;
+        y.real(p0 / u2 / u2);
+        double const yi2 = y_abs * y_abs - y.real() * y.real();
+        y.imag(yi2 > 0.0 ? -std::sqrt(yi2) : 0.0);
+        return y / base_y_to;
+    };
+    cplx const y_shunt = magnetising(c.i0, c.p0);
+    cplx const y0_shunt = magnetising(c.i0_zero, c.p0_zero);
+
+    SymBranchParam const p1 = branch_pi_model(st.from_status, st.to_status, y_series, y_shunt, k * std::exp(j * (c.clock * kDeg30)));
+    if constexpr (B == 1) {
+        cplx const v[4] = {p1.yff, p1.yft, p1.ytf, p1.ytt};
+        for (int i = 0; i != 4; ++i) put_scalar_tensor<1>(out + 2 * i, v[i], 0.0);
+    } else {
+        SymBranchParam const p2 = branch_pi_model(st.from_status, st.to_status, y_series, y_shunt, k * std::exp(j * (-c.clock * kDeg30)));
+        SymBranchParam p0;
+        constexpr IntS wye_n = 1, delta = 2, zigzag_n = 4;
+        if (c.winding_from == wye_n && c.winding_to == wye_n) {
+            double shift0 = 0.0;
+            if (c.clock == 2 || c.clock == 6 || c.clock == 10) shift0 = 6.0 * kDeg30;
+            cplx const z0_series = 1.0 / y_series + 3.0 * (c.z_grounding_to + c.z_grounding_from / k / k);
+            cplx const y0_series = 1.0 / z0_series;
+            p0 = branch_pi_model(st.from_status, st.to_status, y0_series, y0_shunt, k * std::exp(j * shift0));
+        } else if (c.winding_from == wye_n && st.from_status) {
+            cplx y0 = y0_shunt;
+            if (c.winding_to == delta) y0 += y_series;
+            if (y0 != cplx{0.0, 0.0}) {
+                cplx const z0 = 1.0 / y0 + 3.0 * c.z_grounding_from / k / k;
+                y0 = 1.0 / z0;
+                p0.yff = y0 / k / k;
+            }
+        } else if (c.winding_to == wye_n && st.to_status) {
+            cplx y0 = y0_shunt;
+            if (c.winding_from == delta) y0 += y_series;
+            if (y0 != cplx{0.0, 0.0}) {
+                cplx const z0 = 1.0 / y0 + 3.0 * c.z_grounding_to;
+                y0 = 1.0 / z0;
+                p0.ytt = y0;
+            }
+        }
+        if (c.winding_from == zigzag_n && st.from_status) {
+            cplx const z0_series = (1.0 / y_series) * 0.1 + 3.0 * c.z_grounding_from / k / k;
+            p0.yff = (1.0 / z0_series) / k / k;
+        }
+        if (c.winding_to == zigzag_n && st.to_status) {
+            cplx const z0_series = (1.0 / y_series) * 0.1 + 3.0 * c.z_grounding_to;
+            p0.ytt = 1.0 / z0_series;
+        }
+        double const low_susceptance = -1e-8 * c.sn / kBasePower3p / c.uk;
+        auto zero_seq_available = [](IntS self, IntS other) {
+            if (self == wye_n) return other == wye_n || other == delta;
+            return self == zigzag_n;
+        };
+        if (!zero_seq_available(c.winding_from, c.winding_to) && st.from_status) p0.yff += cplx{0.0, low_susceptance};
+        if (!zero_seq_available(c.winding_to, c.winding_from) && st.to_status) p0.ytt += cplx{0.0, low_susceptance};
+        // y_abc = A diag(y0, y1, y2) A^-1, evaluated as (A * D) * A^-1 with sequential dot products
+        cplx const A[3][3] = {{1.0, 1.0, 1.0}, {1.0, kA2, kA}, {1.0, kA, kA2}};
+        cplx Ai[3][3] = {{1.0, 1.0, 1.0}, {1.0, kA, kA2}, {1.0, kA2, kA}};
+        for (auto& row : Ai)
+            for (auto& x : row) x = x / 3.0;
+        cplx const s0[4] = {p0.yff, p0.yft, p0.ytf, p0.ytt};
+        cplx const s1[4] = {p1.yff, p1.yft, p1.ytf, p1.ytt};
+        cplx const s2[4] = {p2.yff, p2.yft, p2.ytf, p2.ytt};
+        for (int i = 0; i != 4; ++i) {
+            cplx D[3][3] = {};
+            D[0][0] = s0[i];
+            D[1][1] = s1[i];
+            D[2][2] = s2[i];
+            cplx AD[3][3];
+            for (int r = 0; r != 3; ++r)
+                for (int q = 0; q != 3; ++q) {
+                    cplx s = A[r][0] * D[0][q];
+                    for (int m = 1; m != 3; ++m) s += A[r][m] * D[m][q];
+                    AD[r][q] = s;
+                }
+            for (int r = 0; r != 3; ++r)
+                for (int q = 0; q != 3; ++q) {
+                    cplx s = AD[r][0] * Ai[0][q];
+                    for (int m = 1; m != 3; ++m) s += AD[r][m] * Ai[m][q];
+                    out[18 * i + 2 * (r * 3 + q)] = s.real();
+                    out[18 * i + 2 * (r * 3 + q) + 1] = s.imag();
+                }
+        }
+    }
+}
+
+// ---- source / shunt / load_gen ------------------------------------------------------------------------------------
+inline void source_param(SourceState const& s, double* out4) { // y1, y0 (source.hpp:40-48)
+    double const z_abs = kBasePower3p / s.sk;
+    double const x1 = z_abs / std::sqrt(s.rx_ratio * s.rx_ratio + 1.0);
+    double const r1 = x1 * s.rx_ratio;
+    cplx const y1 = 1.0 / cplx{r1, x1};
+    cplx const y0 = y1 / s.z01_ratio;
+    out4[0] = y1.real();
+    out4[1] = y1.imag();
+    out4[2] = y0.real();
+    out4[3] = y0.imag();
+}
+inline cplx source_u_ref(SourceState const& s) { return s.u_ref * std::exp(cplx{0.0, 1.0} * s.u_ref_angle); }
+
+inline bool shunt_set(ShuntState& st, double base_y, double g1, double b1, double g0, double b0) { // shunt.hpp:86-107
+    auto upd = [](double v, double& target) {
+        if (std::isnan(v) || v == target) return false;
+        target = v;
+        return true;
+    };
+    bool changed = upd(g1, st.g1);
+    changed = upd(b1, st.b1) || changed;
+    changed = upd(g0, st.g0) || changed;
+    changed = upd(b0, st.b0) || changed;
+    if (changed) {
+        st.y1 = (st.g1 + cplx{0.0, 1.0} * st.b1) / base_y;
+        st.y0 = (st.g0 + cplx{0.0, 1.0} * st.b0) / base_y;
+    }
+    return changed;
+}
+template <int B> inline void shunt_param(ShuntState const& st, double* out) {
+    if (!st.status) {
+        put_scalar_tensor<B>(out, 0.0, 0.0);
+    } else if constexpr (B == 1) {
+        put_scalar_tensor<1>(out, st.y1, 0.0);
+    } else {
+        put_scalar_tensor<3>(out, (2.0 * st.y1 + st.y0) / 3.0, (st.y0 - st.y1) / 3.0);
+    }
+}
+
+// per-unit injection of a load/generator for a B-phase calculation; lb = phases of the component (1 or 3)
+template <int B> inline void load_gen_injection(LoadGenState const& st, int lb, cplx* out) {
+    if (!st.status) {
+        for (int p = 0; p != B; ++p) out[p] = 0.0;
+        return;
+    }
+    if constexpr (B == 1) {
+        if (lb == 1) {
+            bool const bad = std::isnan(st.s[0].real()) || std::isnan(st.s[0].imag());
+            out[0] = bad ? cplx{kNaN, kNaN} : st.s[0];
+        } else {
+            out[0] = (st.s[0] + st.s[1] + st.s[2]) / 3.0;
+        }
+    } else {
+        if (lb == 1) {
+            bool const bad = std::isnan(st.s[0].real()) || std::isnan(st.s[0].imag());
+            for (int p = 0; p != 3; ++p) out[p] = bad ? cplx{kNaN, kNaN} : st.s[0];
+        } else {
+            for (int p = 0; p != 3; ++p) out[p] = st.s[p];
+        }
+    }
+}
+
+} // namespace pgmb

@@ -1,0 +1,680 @@
+#include "model.hpp"
+
+#include <cstring>
+
+namespace pgmb {
+
+namespace {
+using Clock = std::chrono::steady_clock;
+double ms_since(Clock::time_point t0) { return std::chrono::duration<double, std::milli>(Clock::now() - t0).count(); }
+
+template <class T> std::pair<T const*, T const*> scenario_span(ComponentBuffer const& b, Idx s) {
+    if (b.data == nullptr) return {nullptr, nullptr};
+    auto const* p = static_cast<T const*>(b.data);
+    if (b.indptr != nullptr) return {p + b.indptr[s], p + b.indptr[s + 1]};
+    if (b.n < 0) throw InvalidArgument("sparse batch buffer without indptr");
+    return {p + s * b.n, p + (s + 1) * b.n};
+}
+} // namespace
+
+Model::Model(double system_frequency, InputData const& in) : freq_{system_frequency} {
+    auto add_id = [this](ID id) {
+        if (!all_ids_.emplace(id, 0).second) throw InvalidArgument("Conflicting id detected: " + std::to_string(id) + "\n");
+    };
+    auto const* nodes = static_cast<NodeInput const*>(in.node.data);
+    for (Idx i = 0; i != in.node.n; ++i) {
+        add_id(nodes[i].id);
+        node_idx_[nodes[i].id] = i;
+        node_.push_back(nodes[i]);
+    }
+    auto u_rated = [this](ID id) { return node_[node_seq(id)].u_rated; };
+    auto const* lines = static_cast<LineInput const*>(in.line.data);
+    for (Idx i = 0; i != in.line.n; ++i) {
+        LineInput const& l = lines[i];
+        add_id(l.id);
+        double const u1 = u_rated(l.from_node), u2 = u_rated(l.to_node);
+        if (std::abs(u1 - u2) > kNumTol) throw InvalidArgument("Conflicting voltage for line " + std::to_string(l.id) + "\n");
+        line_idx_[l.id] = i;
+        line_in_.push_back(l);
+        line_c_.push_back(line_constants(l, freq_, u1));
+        branch_st_.push_back({l.from_status != 0, l.to_status != 0});
+    }
+    auto const* trafos = static_cast<TransformerInput const*>(in.transformer.data);
+    for (Idx i = 0; i != in.transformer.n; ++i) {
+        TransformerInput const& t = trafos[i];
+        add_id(t.id);
+        trafo_idx_[t.id] = i;
+        trafo_in_.push_back(t);
+        trafo_c_.push_back(transformer_constants(t, u_rated(t.from_node), u_rated(t.to_node)));
+        if (!trafo_c_.back().clock_valid) throw InvalidArgument("Invalid clock for transformer " + std::to_string(t.id) + "\n");
+        branch_st_.push_back({t.from_status != 0, t.to_status != 0});
+        trafo_st_.push_back({trafo_c_.back().initial_tap_pos});
+    }
+    auto const* shunts = static_cast<ShuntInput const*>(in.shunt.data);
+    for (Idx i = 0; i != in.shunt.n; ++i) {
+        ShuntInput const& s = shunts[i];
+        add_id(s.id);
+        shunt_idx_[s.id] = i;
+        shunt_in_.push_back(s);
+        double const u = u_rated(s.node);
+        double const base_i = kBasePower3p / u / kSqrt3;
+        shunt_base_y_.push_back(base_i / (u / kSqrt3));
+        ShuntState st{s.status != 0, kNaN, kNaN, kNaN, kNaN, cplx{kNaN, 0.0}, cplx{kNaN, 0.0}};
+        shunt_set(st, shunt_base_y_.back(), s.g1, s.b1, s.g0, s.b0);
+        shunt_st_.push_back(st);
+    }
+    auto const* sources = static_cast<SourceInput const*>(in.source.data);
+    for (Idx i = 0; i != in.source.n; ++i) {
+        SourceInput const& s = sources[i];
+        add_id(s.id);
+        (void)u_rated(s.node);
+        source_idx_[s.id] = i;
+        source_in_.push_back(s);
+        source_st_.push_back({s.status != 0, s.u_ref, std::isnan(s.u_ref_angle) ? 0.0 : s.u_ref_angle,
+                              std::isnan(s.sk) ? 1e10 : s.sk, std::isnan(s.rx_ratio) ? 0.1 : s.rx_ratio,
+                              std::isnan(s.z01_ratio) ? 1.0 : s.z01_ratio});
+    }
+    auto add_lg = [&](auto const* p, Idx n, int lb, double direction) {
+        for (Idx i = 0; i != n; ++i) {
+            add_id(p[i].id);
+            Idx const node = node_seq(p[i].node);
+            lg_idx_[p[i].id] = static_cast<Idx>(lg_.size());
+            lg_.push_back({p[i].id, node, lb, direction, kBasePower3p / node_[node].u_rated / kSqrt3, p[i].type});
+            LoadGenState st{p[i].status != 0, {cplx{kNaN, kNaN}, cplx{kNaN, kNaN}, cplx{kNaN, kNaN}}};
+            lg_st_.push_back(st);
+            if constexpr (std::is_same_v<std::remove_cvref_t<decltype(p[i])>, SymLoadGenInput>) {
+                set_load_power(static_cast<Idx>(lg_.size()) - 1, &p[i].p_specified, &p[i].q_specified);
+            } else {
+                set_load_power(static_cast<Idx>(lg_.size()) - 1, p[i].p_specified, p[i].q_specified);
+            }
+        }
+    };
+    n_sym_gen_ = in.sym_gen.n;
+    n_asym_gen_ = in.asym_gen.n;
+    n_sym_load_ = in.sym_load.n;
+    n_asym_load_ = in.asym_load.n;
+    add_lg(static_cast<SymLoadGenInput const*>(in.sym_gen.data), in.sym_gen.n, 1, 1.0);
+    add_lg(static_cast<AsymLoadGenInput const*>(in.asym_gen.data), in.asym_gen.n, 3, 1.0);
+    add_lg(static_cast<SymLoadGenInput const*>(in.sym_load.data), in.sym_load.n, 1, -1.0);
+    add_lg(static_cast<AsymLoadGenInput const*>(in.asym_load.data), in.asym_load.n, 3, -1.0);
+}
+
+Idx Model::node_seq(ID id) const {
+    auto it = node_idx_.find(id);
+    if (it == node_idx_.end()) throw InvalidArgument("The id cannot be found: " + std::to_string(id) + "\n");
+    return it->second;
+}
+
+// LoadGen::set_power (load_gen.hpp:86-95): NaN keeps the present value
+void Model::set_load_power(Idx i, double const* p, double const* q) {
+    double const scalar = lg_[i].direction / (lg_[i].lb == 1 ? kBasePower3p : kBasePower1p);
+    for (int k = 0; k != lg_[i].lb; ++k) {
+        double ps = lg_st_[i].s[k].real(), qs = lg_st_[i].s[k].imag();
+        if (!std::isnan(p[k])) ps = scalar * p[k];
+        if (!std::isnan(q[k])) qs = scalar * q[k];
+        lg_st_[i].s[k] = cplx{ps, qs};
+    }
+}
+
+void Model::prepare_topology() {
+    if (topo_valid_) return;
+    GridGraph g;
+    g.n_node = static_cast<Idx>(node_.size());
+    for (Idx i = 0; i != n_line(); ++i) {
+        g.branch_node.push_back({node_seq(line_in_[i].from_node), node_seq(line_in_[i].to_node)});
+        g.branch_status.push_back({static_cast<int8_t>(branch_st_[i].from_status), static_cast<int8_t>(branch_st_[i].to_status)});
+        g.branch_shift.push_back(0.0);
+    }
+    for (Idx i = 0; i != n_trafo(); ++i) {
+        auto const& st = branch_st_[n_line() + i];
+        g.branch_node.push_back({node_seq(trafo_in_[i].from_node), node_seq(trafo_in_[i].to_node)});
+        g.branch_status.push_back({static_cast<int8_t>(st.from_status), static_cast<int8_t>(st.to_status)});
+        g.branch_shift.push_back(trafo_c_[i].clock * kDeg30);
+    }
+    for (auto const& s : shunt_in_) g.shunt_node.push_back(node_seq(s.node));
+    for (size_t i = 0; i != source_in_.size(); ++i) {
+        g.source_node.push_back(node_seq(source_in_[i].node));
+        g.source_status.push_back(static_cast<int8_t>(source_st_[i].status));
+    }
+    for (auto const& l : lg_) {
+        g.load_gen_node.push_back(l.node);
+        g.load_gen_type.push_back(l.type);
+    }
+    topo_ = build_topology(g);
+    engines_.clear();
+    engines_.resize(topo_.math.size());
+    param_valid_[0] = param_valid_[1] = false;
+    index_cache_.clear();
+    real_cache_.clear();
+    topo_valid_ = true;
+}
+
+template <int B>
+void Model::param_arrays(Idx group, std::vector<double>& bp, std::vector<double>& sp, std::vector<double>& srcp) const {
+    constexpr int bb2 = B * B * 2;
+    auto const& m = topo_.math[group];
+    bp.assign(m.n_branch() * 4 * bb2, 0.0);
+    sp.assign(m.n_shunt() * bb2, 0.0);
+    srcp.assign(m.n_source() * 4, 0.0);
+    for (Idx i = 0; i != n_line(); ++i) {
+        Coupling const c = topo_.branch[i];
+        if (c.group == group) line_param<B>(line_c_[i], branch_st_[i], &bp[c.pos * 4 * bb2]);
+    }
+    for (Idx i = 0; i != n_trafo(); ++i) {
+        Coupling const c = topo_.branch[n_line() + i];
+        if (c.group == group) transformer_param<B>(trafo_c_[i], branch_st_[n_line() + i], trafo_st_[i].tap_pos, &bp[c.pos * 4 * bb2]);
+    }
+    for (size_t i = 0; i != shunt_in_.size(); ++i) {
+        Coupling const c = topo_.shunt[i];
+        if (c.group == group) shunt_param<B>(shunt_st_[i], &sp[c.pos * bb2]);
+    }
+    for (size_t i = 0; i != source_in_.size(); ++i) {
+        Coupling const c = topo_.source[i];
+        if (c.group == group) source_param(source_st_[i], &srcp[c.pos * 4]);
+    }
+}
+
+template <int B> void Model::prepare_engines() {
+    prepare_topology();
+    constexpr int si = B == 1 ? 0 : 1;
+    for (size_t g = 0; g != topo_.math.size(); ++g) {
+        auto& e = engines_[g].engine[si];
+        bool const fresh = !e;
+        if (fresh) e = std::make_unique<Engine>(topo_.math[g], B == 1, device_);
+        if (fresh || !param_valid_[si]) {
+            std::vector<double> bp, sp, srcp;
+            param_arrays<B>(static_cast<Idx>(g), bp, sp, srcp);
+            e->set_param(bp.data(), sp.data(), srcp.data());
+        }
+    }
+    param_valid_[si] = true;
+}
+
+// PowerFlowInput of the current state: sinj[g] = [n_lg][B] complex, uref[g] = [n_src] complex (appended)
+template <int B>
+void Model::gather_pf_input(std::vector<std::vector<double>>& sinj, std::vector<std::vector<double>>& uref) const {
+    for (size_t g = 0; g != topo_.math.size(); ++g) {
+        size_t const off_s = sinj[g].size(), off_u = uref[g].size();
+        sinj[g].resize(off_s + topo_.math[g].n_load_gen() * B * 2, 0.0);
+        uref[g].resize(off_u + topo_.math[g].n_source() * 2, 0.0);
+    }
+    std::vector<size_t> base_s(topo_.math.size()), base_u(topo_.math.size());
+    for (size_t g = 0; g != topo_.math.size(); ++g) {
+        base_s[g] = sinj[g].size() - topo_.math[g].n_load_gen() * B * 2;
+        base_u[g] = uref[g].size() - topo_.math[g].n_source() * 2;
+    }
+    for (size_t i = 0; i != lg_.size(); ++i) {
+        Coupling const c = topo_.load_gen[i];
+        if (c.group == -1) continue;
+        cplx v[B];
+        load_gen_injection<B>(lg_st_[i], lg_[i].lb, v);
+        double* o = &sinj[c.group][base_s[c.group] + c.pos * B * 2];
+        for (int p = 0; p != B; ++p) {
+            o[2 * p] = v[p].real();
+            o[2 * p + 1] = v[p].imag();
+        }
+    }
+    for (size_t i = 0; i != source_in_.size(); ++i) {
+        Coupling const c = topo_.source[i];
+        if (c.group == -1) continue;
+        cplx const u = source_u_ref(source_st_[i]);
+        uref[c.group][base_u[c.group] + c.pos * 2] = u.real();
+        uref[c.group][base_u[c.group] + c.pos * 2 + 1] = u.imag();
+    }
+}
+
+void Model::mark(bool topo, bool param, Saved* saved) {
+    if (topo) {
+        topo_valid_ = false;
+        if (saved != nullptr) saved->topo = true;
+    }
+    if (topo || param) {
+        param_valid_[0] = param_valid_[1] = false;
+        if (saved != nullptr) saved->param = true;
+    }
+}
+
+void Model::apply_scenario(UpdateData const& u, Idx s, Saved* saved) {
+    auto find = [](auto const& upd, Idx pos, Idx n_in_scenario, Idx n_comp, std::unordered_map<ID, Idx> const& map, Idx offset) {
+        if (upd.id == kNaID) {
+            if (n_in_scenario != n_comp) throw InvalidArgument("update without ids must cover every element of the component");
+            return offset + pos;
+        }
+        auto it = map.find(upd.id);
+        if (it == map.end()) throw InvalidArgument("The id cannot be found: " + std::to_string(upd.id) + "\n");
+        return it->second;
+    };
+    auto set_status = [](bool& st, IntS v) {
+        if (v == kNaIntS || static_cast<bool>(v) == st) return false;
+        st = static_cast<bool>(v);
+        return true;
+    };
+    {
+        auto [b, e] = scenario_span<BranchUpdate>(u.line, s);
+        for (auto p = b; p != e; ++p) {
+            Idx const i = find(*p, p - b, e - b, n_line(), line_idx_, 0);
+            if (saved != nullptr) saved->branch.emplace_back(i, branch_st_[i]);
+            bool changed = set_status(branch_st_[i].from_status, p->from_status);
+            changed = set_status(branch_st_[i].to_status, p->to_status) || changed;
+            mark(changed, changed, saved);
+        }
+    }
+    {
+        auto [b, e] = scenario_span<TransformerUpdate>(u.transformer, s);
+        for (auto p = b; p != e; ++p) {
+            Idx const i = find(*p, p - b, e - b, n_trafo(), trafo_idx_, 0);
+            Idx const bi = n_line() + i;
+            if (saved != nullptr) {
+                saved->branch.emplace_back(bi, branch_st_[bi]);
+                saved->trafo.emplace_back(i, trafo_st_[i]);
+            }
+            bool topo = set_status(branch_st_[bi].from_status, p->from_status);
+            topo = set_status(branch_st_[bi].to_status, p->to_status) || topo;
+            bool tap = false;
+            if (p->tap_pos != kNaIntS && p->tap_pos != trafo_st_[i].tap_pos) {
+                trafo_st_[i].tap_pos = tap_limit(trafo_c_[i], p->tap_pos);
+                tap = true;
+            }
+            mark(topo, tap || topo, saved);
+        }
+    }
+    {
+        auto [b, e] = scenario_span<ShuntUpdate>(u.shunt, s);
+        for (auto p = b; p != e; ++p) {
+            Idx const i = find(*p, p - b, e - b, static_cast<Idx>(shunt_in_.size()), shunt_idx_, 0);
+            if (saved != nullptr) saved->shunt.emplace_back(i, shunt_st_[i]);
+            bool changed = set_status(shunt_st_[i].status, p->status);
+            changed = shunt_set(shunt_st_[i], shunt_base_y_[i], p->g1, p->b1, p->g0, p->b0) || changed;
+            mark(false, changed, saved);
+        }
+    }
+    {
+        auto [b, e] = scenario_span<SourceUpdate>(u.source, s);
+        for (auto p = b; p != e; ++p) {
+            Idx const i = find(*p, p - b, e - b, static_cast<Idx>(source_in_.size()), source_idx_, 0);
+            if (saved != nullptr) saved->source.emplace_back(i, source_st_[i]);
+            auto& st = source_st_[i];
+            bool const topo = set_status(st.status, p->status);
+            if (!std::isnan(p->u_ref)) st.u_ref = p->u_ref;
+            if (!std::isnan(p->u_ref_angle)) st.u_ref_angle = p->u_ref_angle;
+            bool param = false;
+            if (!std::isnan(p->sk)) st.sk = p->sk, param = true;
+            if (!std::isnan(p->rx_ratio)) st.rx_ratio = p->rx_ratio, param = true;
+            if (!std::isnan(p->z01_ratio)) st.z01_ratio = p->z01_ratio, param = true;
+            mark(topo, param || topo, saved);
+        }
+    }
+    auto upd_lg = [&](auto tag, ComponentBuffer const& buf, Idx offset, Idx count) {
+        using U = decltype(tag);
+        auto [b, e] = scenario_span<U>(buf, s);
+        for (auto p = b; p != e; ++p) {
+            Idx const i = find(*p, p - b, e - b, count, lg_idx_, offset);
+            if (i < offset || i >= offset + count) throw InvalidArgument("The id cannot be found: " + std::to_string(p->id) + "\n");
+            if (saved != nullptr) saved->lg.emplace_back(i, lg_st_[i]);
+            set_status(lg_st_[i].status, p->status);
+            if constexpr (std::is_same_v<U, SymLoadGenUpdate>) {
+                set_load_power(i, &p->p_specified, &p->q_specified);
+            } else {
+                set_load_power(i, p->p_specified, p->q_specified);
+            }
+        }
+    };
+    upd_lg(SymLoadGenUpdate{}, u.sym_gen, 0, n_sym_gen_);
+    upd_lg(AsymLoadGenUpdate{}, u.asym_gen, n_sym_gen_, n_asym_gen_);
+    upd_lg(SymLoadGenUpdate{}, u.sym_load, n_sym_gen_ + n_asym_gen_, n_sym_load_);
+    upd_lg(AsymLoadGenUpdate{}, u.asym_load, n_sym_gen_ + n_asym_gen_ + n_sym_load_, n_asym_load_);
+}
+
+void Model::restore(Saved const& s) {
+    for (auto it = s.branch.rbegin(); it != s.branch.rend(); ++it) branch_st_[it->first] = it->second;
+    for (auto it = s.trafo.rbegin(); it != s.trafo.rend(); ++it) trafo_st_[it->first] = it->second;
+    for (auto it = s.source.rbegin(); it != s.source.rend(); ++it) source_st_[it->first] = it->second;
+    for (auto it = s.shunt.rbegin(); it != s.shunt.rend(); ++it) shunt_st_[it->first] = it->second;
+    for (auto it = s.lg.rbegin(); it != s.lg.rend(); ++it) lg_st_[it->first] = it->second;
+    if (s.topo) topo_valid_ = false;
+    if (s.param) param_valid_[0] = param_valid_[1] = false;
+}
+
+void Model::update_permanent(UpdateData const& update) { apply_scenario(update, 0, nullptr); }
+
+// ---- output conversion (host, v1) ------------------------------------------------------------------------------------
+// so[0..5] = u, bus_injection(unused), branch, source, shunt, load_gen per group, scenario-major
+template <int B>
+void Model::write_output(Idx n_scn, Idx first, OutputData const& out, std::vector<std::vector<double>> const (&so)[6]) const {
+    constexpr int c2 = 2 * B;
+    constexpr double base_power = B == 1 ? kBasePower3p : kBasePower1p;
+    constexpr double u_scale = B == 1 ? 1.0 : 1.0 / kSqrt3;
+    auto cabs = [](double re, double im) { return std::sqrt(re * re + im * im); };
+    Idx const nn = static_cast<Idx>(node_.size());
+    auto group_n = [&](Idx g, int what) -> Idx {
+        auto const& m = topo_.math[g];
+        switch (what) {
+        case 0: return m.n_bus;
+        case 2: return m.n_branch();
+        case 3: return m.n_source();
+        case 4: return m.n_shunt();
+        default: return m.n_load_gen();
+        }
+    };
+    for (Idx s = 0; s != n_scn; ++s) {
+        Idx const os = first + s;
+        auto appliance = [&](Coupling c, int what, double base_i, double direction, ID id, bool status) {
+            ApplianceOutput<B> o{};
+            o.id = id;
+            if (c.group == -1) return o;
+            o.energized = status ? 1 : 0;
+            double const* v = &so[what][c.group][(s * group_n(c.group, what) + c.pos) * 2 * c2];
+            for (int p = 0; p != B; ++p) {
+                double const sr = v[2 * p], sim = v[2 * p + 1], ir = v[c2 + 2 * p], ii = v[c2 + 2 * p + 1];
+                o.p[p] = base_power * sr * direction;
+                o.q[p] = base_power * sim * direction;
+                o.s[p] = base_power * cabs(sr, sim);
+                o.i[p] = base_i * cabs(ir, ii);
+                o.pf[p] = o.s[p] < kNumTol ? 0.0 : o.p[p] / o.s[p];
+            }
+            return o;
+        };
+        if (out.node != nullptr) {
+            std::vector<cplx> inj(nn * B, cplx{});
+            auto add = [&](Idx node, Coupling c, int what) {
+                if (c.group == -1) return;
+                double const* v = &so[what][c.group][(s * group_n(c.group, what) + c.pos) * 2 * c2];
+                for (int p = 0; p != B; ++p) inj[node * B + p] += cplx{v[2 * p], v[2 * p + 1]};
+            };
+            for (size_t i = 0; i != source_in_.size(); ++i) add(node_idx_.at(source_in_[i].node), topo_.source[i], 3);
+            Idx const o_sg = 0, o_ag = n_sym_gen_, o_sl = n_sym_gen_ + n_asym_gen_, o_al = o_sl + n_sym_load_;
+            for (Idx i = o_sl; i != o_sl + n_sym_load_; ++i) add(lg_[i].node, topo_.load_gen[i], 5);
+            for (Idx i = o_sg; i != o_sg + n_sym_gen_; ++i) add(lg_[i].node, topo_.load_gen[i], 5);
+            for (Idx i = o_al; i != o_al + n_asym_load_; ++i) add(lg_[i].node, topo_.load_gen[i], 5);
+            for (Idx i = o_ag; i != o_ag + n_asym_gen_; ++i) add(lg_[i].node, topo_.load_gen[i], 5);
+            auto* dst = static_cast<NodeOutput<B>*>(out.node) + os * nn;
+            for (Idx i = 0; i != nn; ++i) {
+                NodeOutput<B> o{};
+                o.id = node_[i].id;
+                Coupling const c = topo_.node[i];
+                if (c.group != -1) {
+                    o.energized = 1;
+                    double const* u = &so[0][c.group][(s * topo_.math[c.group].n_bus + c.pos) * c2];
+                    for (int p = 0; p != B; ++p) {
+                        o.u_pu[p] = cabs(u[2 * p], u[2 * p + 1]);
+                        o.u[p] = u_scale * node_[i].u_rated * o.u_pu[p];
+                        o.u_angle[p] = std::atan2(u[2 * p + 1], u[2 * p]);
+                        o.p[p] = base_power * inj[i * B + p].real();
+                        o.q[p] = base_power * inj[i * B + p].imag();
+                    }
+                }
+                dst[i] = o;
+            }
+        }
+        auto branch = [&](Idx seq, ID id, double base_i_from, double base_i_to, double sn, double i_n) {
+            BranchOutput<B> o{};
+            o.id = id;
+            Coupling const c = topo_.branch[seq];
+            if (c.group == -1) return o;
+            o.energized = (branch_st_[seq].from_status || branch_st_[seq].to_status) ? 1 : 0;
+            double const* v = &so[2][c.group][(s * topo_.math[c.group].n_branch() + c.pos) * 4 * c2];
+            double sum_sf = 0, sum_st = 0, max_if = 0, max_it = 0;
+            for (int p = 0; p != B; ++p) {
+                double const* sf = v + 2 * p;
+                double const* st = v + c2 + 2 * p;
+                double const* i_f = v + 2 * c2 + 2 * p;
+                double const* i_t = v + 3 * c2 + 2 * p;
+                o.p_from[p] = base_power * sf[0];
+                o.q_from[p] = base_power * sf[1];
+                o.i_from[p] = base_i_from * cabs(i_f[0], i_f[1]);
+                o.s_from[p] = base_power * cabs(sf[0], sf[1]);
+                o.p_to[p] = base_power * st[0];
+                o.q_to[p] = base_power * st[1];
+                o.i_to[p] = base_i_to * cabs(i_t[0], i_t[1]);
+                o.s_to[p] = base_power * cabs(st[0], st[1]);
+                sum_sf = p == 0 ? o.s_from[p] : sum_sf + o.s_from[p];
+                sum_st = p == 0 ? o.s_to[p] : sum_st + o.s_to[p];
+                max_if = p == 0 ? o.i_from[p] : std::max(max_if, o.i_from[p]);
+                max_it = p == 0 ? o.i_to[p] : std::max(max_it, o.i_to[p]);
+            }
+            o.loading = sn > 0.0 ? std::max(sum_sf, sum_st) / sn : std::max(max_if, max_it) / i_n;
+            return o;
+        };
+        if (out.line != nullptr) {
+            auto* dst = static_cast<BranchOutput<B>*>(out.line) + os * n_line();
+            for (Idx i = 0; i != n_line(); ++i) dst[i] = branch(i, line_in_[i].id, line_c_[i].base_i, line_c_[i].base_i, -1.0, line_in_[i].i_n);
+        }
+        if (out.transformer != nullptr) {
+            auto* dst = static_cast<BranchOutput<B>*>(out.transformer) + os * n_trafo();
+            for (Idx i = 0; i != n_trafo(); ++i)
+                dst[i] = branch(n_line() + i, trafo_in_[i].id, trafo_c_[i].base_i_from, trafo_c_[i].base_i_to, trafo_c_[i].sn, 0.0);
+        }
+        if (out.shunt != nullptr) {
+            Idx const n = static_cast<Idx>(shunt_in_.size());
+            auto* dst = static_cast<ApplianceOutput<B>*>(out.shunt) + os * n;
+            for (Idx i = 0; i != n; ++i) {
+                double const u = node_[node_idx_.at(shunt_in_[i].node)].u_rated;
+                dst[i] = appliance(topo_.shunt[i], 4, kBasePower3p / u / kSqrt3, -1.0, shunt_in_[i].id, shunt_st_[i].status);
+            }
+        }
+        if (out.source != nullptr) {
+            Idx const n = static_cast<Idx>(source_in_.size());
+            auto* dst = static_cast<ApplianceOutput<B>*>(out.source) + os * n;
+            for (Idx i = 0; i != n; ++i) {
+                double const u = node_[node_idx_.at(source_in_[i].node)].u_rated;
+                dst[i] = appliance(topo_.source[i], 3, kBasePower3p / u / kSqrt3, 1.0, source_in_[i].id, source_st_[i].status);
+            }
+        }
+        auto lg_out = [&](void* base, Idx begin, Idx count) {
+            if (base == nullptr) return;
+            auto* dst = static_cast<ApplianceOutput<B>*>(base) + os * count;
+            for (Idx k = 0; k != count; ++k) {
+                Idx const i = begin + k;
+                dst[k] = appliance(topo_.load_gen[i], 5, lg_[i].base_i, lg_[i].direction, lg_[i].id, lg_st_[i].status);
+            }
+        };
+        lg_out(out.sym_gen, 0, n_sym_gen_);
+        lg_out(out.asym_gen, n_sym_gen_, n_asym_gen_);
+        lg_out(out.sym_load, n_sym_gen_ + n_asym_gen_, n_sym_load_);
+        lg_out(out.asym_load, n_sym_gen_ + n_asym_gen_ + n_sym_load_, n_asym_load_);
+    }
+}
+
+template <int B>
+int64_t Model::run_block(ModelOptions const& opt, Idx n_scn, std::vector<std::vector<double>> const& sinj,
+                         std::vector<std::vector<double>> const& uref, OutputData const& out, Idx first, int32_t* n_iter,
+                         int32_t* status) {
+    constexpr int si = B == 1 ? 0 : 1;
+    constexpr int c2 = 2 * B;
+    std::vector<std::vector<double>> so[6];
+    for (auto& v : so) v.resize(topo_.math.size());
+    std::vector<int32_t> st_all(n_scn, 0), it_all(n_scn, 0);
+    for (size_t g = 0; g != topo_.math.size(); ++g) {
+        auto const& m = topo_.math[g];
+        Engine& e = *engines_[g].engine[si];
+        so[0][g].resize(n_scn * m.n_bus * c2);
+        so[2][g].resize(n_scn * m.n_branch() * 4 * c2);
+        so[3][g].resize(n_scn * m.n_source() * 2 * c2);
+        so[4][g].resize(n_scn * m.n_shunt() * 2 * c2);
+        so[5][g].resize(n_scn * m.n_load_gen() * 2 * c2);
+        std::vector<int32_t> st(n_scn), it(n_scn);
+        SolverOutputView view{so[0][g].data(), nullptr, so[2][g].data(), so[3][g].data(), so[4][g].data(), so[5][g].data(),
+                              st.data(), it.data(), nullptr};
+        auto t0 = Clock::now();
+        e.stage({n_scn, uref[g].data(), false, sinj[g].data()});
+        timing[1] += ms_since(t0);
+        timing[2] += e.solve_staged({opt.method, opt.err_tol, static_cast<int32_t>(opt.max_iter)});
+        t0 = Clock::now();
+        e.fetch(view);
+        timing[4] += ms_since(t0);
+        for (Idx s = 0; s != n_scn; ++s) {
+            if (st_all[s] == 0) st_all[s] = st[s];
+            it_all[s] = std::max(it_all[s], it[s]);
+        }
+    }
+    auto t0 = Clock::now();
+    write_output<B>(n_scn, first, out, so);
+    timing[3] += ms_since(t0);
+    int64_t failed = 0;
+    for (Idx s = 0; s != n_scn; ++s) {
+        if (n_iter != nullptr) n_iter[first + s] = it_all[s];
+        if (status != nullptr) status[first + s] = st_all[s];
+        if (st_all[s] != 0) {
+            ++failed;
+            batch_message += "Error in batch #" + std::to_string(first + s) + ": " +
+                             (st_all[s] == 1 ? "Iteration failed to converge after " + std::to_string(opt.max_iter) + " iterations!"
+                                             : "Sparse matrix error, possibly singular matrix!") + "\n";
+        }
+    }
+    return failed;
+}
+
+template <int B>
+int64_t Model::calculate_impl(ModelOptions const& opt, UpdateData const* update, OutputData const& out, int32_t* n_iter,
+                              int32_t* status) {
+    auto const t_all = Clock::now();
+    for (double& t : timing) t = 0.0;
+    batch_message.clear();
+    device_ = opt.device;
+    int64_t failed = 0;
+    auto t0 = Clock::now();
+    if (update == nullptr) {
+        prepare_engines<B>();
+        std::vector<std::vector<double>> sinj(topo_.math.size()), uref(topo_.math.size());
+        gather_pf_input<B>(sinj, uref);
+        timing[0] += ms_since(t0);
+        failed = run_block<B>(opt, 1, sinj, uref, out, 0, n_iter, status);
+    } else {
+        Idx const n = update->n_scenarios;
+        // does any scenario touch something other than loads / generators / source references?
+        bool const structural = update->line.data != nullptr || update->transformer.data != nullptr ||
+                                update->shunt.data != nullptr;
+        bool source_param_change = false;
+        if (update->source.data != nullptr) {
+            for (Idx s = 0; s != n && !source_param_change; ++s) {
+                auto [b, e] = scenario_span<SourceUpdate>(update->source, s);
+                for (auto p = b; p != e; ++p)
+                    if (p->status != kNaIntS || !std::isnan(p->sk) || !std::isnan(p->rx_ratio) || !std::isnan(p->z01_ratio))
+                        source_param_change = true;
+            }
+        }
+        if (!structural && !source_param_change) {
+            // fast path: one engine call for the whole batch
+            prepare_engines<B>();
+            std::vector<std::vector<double>> sinj(topo_.math.size()), uref(topo_.math.size());
+            for (Idx s = 0; s != n; ++s) {
+                Saved saved;
+                apply_scenario(*update, s, &saved);
+                gather_pf_input<B>(sinj, uref);
+                restore(saved);
+            }
+            timing[0] += ms_since(t0);
+            if (n != 0) failed = run_block<B>(opt, n, sinj, uref, out, 0, n_iter, status);
+        } else {
+            // general path: scenario by scenario (topology / parameters may change), still on the GPU
+            for (Idx s = 0; s != n; ++s) {
+                Saved saved;
+                try {
+                    apply_scenario(*update, s, &saved);
+                    prepare_engines<B>();
+                    std::vector<std::vector<double>> sinj(topo_.math.size()), uref(topo_.math.size());
+                    gather_pf_input<B>(sinj, uref);
+                    failed += run_block<B>(opt, 1, sinj, uref, out, s, n_iter, status);
+                } catch (CudaError const&) {
+                    restore(saved);
+                    throw;
+                } catch (std::exception const& ex) {
+                    ++failed;
+                    if (status != nullptr) status[s] = 3;
+                    batch_message += "Error in batch #" + std::to_string(s) + ": " + ex.what() + "\n";
+                }
+                restore(saved);
+            }
+        }
+    }
+    timing[5] = ms_since(t_all);
+    return failed;
+}
+
+int64_t Model::calculate(ModelOptions const& opt, UpdateData const* update, OutputData const& out, int32_t* n_iter,
+                         int32_t* status) {
+    return opt.symmetric ? calculate_impl<1>(opt, update, out, n_iter, status)
+                         : calculate_impl<3>(opt, update, out, n_iter, status);
+}
+
+// ---- introspection -----------------------------------------------------------------------------------------------
+Idx Model::n_math_groups() {
+    prepare_topology();
+    return static_cast<Idx>(topo_.math.size());
+}
+
+std::vector<int64_t> const& Model::get_index(Idx group, std::string const& name) {
+    prepare_topology();
+    std::string const key = std::to_string(group) + "." + name;
+    auto it = index_cache_.find(key);
+    if (it != index_cache_.end()) return it->second;
+    std::vector<int64_t> v;
+    auto coupling = [](std::vector<Coupling> const& c) {
+        std::vector<int64_t> o;
+        for (auto const& x : c) {
+            o.push_back(x.group);
+            o.push_back(x.pos);
+        }
+        return o;
+    };
+    if (name == "coup.node") v = coupling(topo_.node);
+    else if (name == "coup.branch") v = coupling(topo_.branch);
+    else if (name == "coup.shunt") v = coupling(topo_.shunt);
+    else if (name == "coup.load_gen") v = coupling(topo_.load_gen);
+    else if (name == "coup.source") v = coupling(topo_.source);
+    else {
+        if (group < 0 || group >= static_cast<Idx>(topo_.math.size())) throw InvalidArgument("math group out of range");
+        auto const& m = topo_.math[group];
+        if (name == "slack_bus") v = {m.slack_bus};
+        else if (name == "is_radial") v = {m.is_radial ? 1 : 0};
+        else if (name == "branch_bus_idx") v = m.branch_bus_idx;
+        else if (name == "fill_in") v = m.fill_in;
+        else if (name == "sources_per_bus") v = m.sources_per_bus;
+        else if (name == "shunts_per_bus") v = m.shunts_per_bus;
+        else if (name == "load_gens_per_bus") v = m.load_gens_per_bus;
+        else if (name == "load_gen_type") v.assign(m.load_gen_type.begin(), m.load_gen_type.end());
+        else {
+            LuPattern const p{m};
+            if (name == "row_indptr") v = p.row_indptr;
+            else if (name == "col_indices") v = p.col_indices;
+            else if (name == "bus_entry") v = p.bus_entry;
+            else if (name == "row_indptr_lu") v = p.row_indptr_lu;
+            else if (name == "col_indices_lu") v = p.col_indices_lu;
+            else if (name == "diag_lu") v = p.diag_lu;
+            else if (name == "map_lu_y_bus") v = p.map_lu_y_bus;
+            else if (name == "lu_transpose_entry") v = p.lu_transpose_entry;
+            else throw InvalidArgument("unknown index array: " + name);
+        }
+    }
+    return index_cache_.emplace(key, std::move(v)).first->second;
+}
+
+std::vector<double> const& Model::get_real(Idx group, bool symmetric, std::string const& name) {
+    prepare_topology();
+    if (group < 0 || group >= static_cast<Idx>(topo_.math.size())) throw InvalidArgument("math group out of range");
+    std::string const key = std::to_string(group) + (symmetric ? ".s." : ".a.") + name;
+    real_cache_.erase(key);
+    std::vector<double> v;
+    if (name == "phase_shift") {
+        v = topo_.math[group].phase_shift;
+    } else {
+        std::vector<double> bp, sp, srcp;
+        std::vector<std::vector<double>> sinj(topo_.math.size()), uref(topo_.math.size());
+        if (symmetric) {
+            param_arrays<1>(group, bp, sp, srcp);
+            gather_pf_input<1>(sinj, uref);
+        } else {
+            param_arrays<3>(group, bp, sp, srcp);
+            gather_pf_input<3>(sinj, uref);
+        }
+        if (name == "branch_param") v = bp;
+        else if (name == "shunt_param") v = sp;
+        else if (name == "source_param") v = srcp;
+        else if (name == "s_injection") v = sinj[group];
+        else if (name == "source_u_ref") v = uref[group];
+        else throw InvalidArgument("unknown real array: " + name);
+    }
+    return real_cache_.emplace(key, std::move(v)).first->second;
+}
+
+} // namespace pgmb

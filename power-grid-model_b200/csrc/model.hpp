@@ -1,0 +1,140 @@
+// Model level (host): the PF slice of the reference's MainModel behind a flat C interface.
+//   construction            main_core/input.hpp:49-86 (components built with the rated voltage of their nodes)
+//   topology / parameters   calculation_preparation.hpp:131-156, 240-279 ; main_core/y_bus.hpp:186-212
+//   PF input                main_core/calculation_input_preparation.hpp:163-188
+//   update / restore        main_model_impl.hpp:139-160, 254-261 ; main_core/update.hpp:58-155
+//   batch dispatch          job_dispatch.hpp:37-68 -- replaced: scenarios that only change loads / source references are
+//                           solved in ONE engine call; other scenarios fall back to per-scenario engine calls (still GPU)
+//   output                  main_core/output.hpp:60-187 ; topological_node_output.hpp:72-117
+#pragma once
+
+#include "components.hpp"
+#include "engine.hpp"
+#include "topology.hpp"
+
+#include <chrono>
+#include <map>
+#include <unordered_map>
+
+namespace pgmb {
+
+struct ComponentBuffer {
+    int64_t n;
+    int64_t const* indptr;
+    void const* data;
+};
+struct InputData {
+    ComponentBuffer node, line, transformer, shunt, source, sym_gen, asym_gen, sym_load, asym_load;
+};
+struct UpdateData {
+    int64_t n_scenarios;
+    ComponentBuffer line, transformer, shunt, source, sym_gen, asym_gen, sym_load, asym_load;
+};
+struct OutputData {
+    void *node, *line, *transformer, *shunt, *source, *sym_gen, *asym_gen, *sym_load, *asym_load;
+};
+struct ModelOptions {
+    int32_t method;
+    bool symmetric;
+    double err_tol;
+    int64_t max_iter;
+    int32_t device;
+};
+
+struct BatchFailure : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+class Model {
+  public:
+    Model(double system_frequency, InputData const& in);
+
+    // single (update == nullptr) or batch calculation; returns number of failed scenarios
+    int64_t calculate(ModelOptions const& opt, UpdateData const* update, OutputData const& out, int32_t* n_iter,
+                      int32_t* status);
+    void update_permanent(UpdateData const& update);
+
+    // introspection for parity tests
+    Idx n_math_groups();
+    std::vector<int64_t> const& get_index(Idx group, std::string const& name);
+    std::vector<double> const& get_real(Idx group, bool symmetric, std::string const& name);
+    double timing[6]{};
+    std::string batch_message;
+
+  private:
+    double freq_;
+    // static data
+    std::vector<NodeInput> node_;
+    std::vector<LineInput> line_in_;
+    std::vector<LineConst> line_c_;
+    std::vector<TransformerInput> trafo_in_;
+    std::vector<TransformerConst> trafo_c_;
+    std::vector<SourceInput> source_in_;
+    std::vector<ShuntInput> shunt_in_;
+    std::vector<double> shunt_base_y_;
+    struct LoadGenStatic {
+        ID id;
+        Idx node;
+        int lb;           // phases of the component
+        double direction; // +1 generator, -1 load
+        double base_i;
+        IntS type;
+    };
+    std::vector<LoadGenStatic> lg_;
+    Idx n_sym_gen_{}, n_asym_gen_{}, n_sym_load_{}, n_asym_load_{};
+    // mutable state
+    std::vector<BranchState> branch_st_; // lines then transformers
+    std::vector<TransformerState> trafo_st_;
+    std::vector<SourceState> source_st_;
+    std::vector<ShuntState> shunt_st_;
+    std::vector<LoadGenState> lg_st_;
+    // id lookup
+    std::unordered_map<ID, Idx> node_idx_, line_idx_, trafo_idx_, shunt_idx_, source_idx_, lg_idx_;
+    std::unordered_map<ID, int> all_ids_;
+
+    // caches
+    bool topo_valid_{false};
+    bool param_valid_[2]{false, false};
+    TopologyResult topo_;
+    struct GroupEngines {
+        std::unique_ptr<Engine> engine[2]; // [sym, asym]
+    };
+    std::vector<GroupEngines> engines_;
+    int device_{0};
+    std::map<std::string, std::vector<int64_t>> index_cache_;
+    std::map<std::string, std::vector<double>> real_cache_;
+
+    Idx n_line() const { return static_cast<Idx>(line_in_.size()); }
+    Idx n_trafo() const { return static_cast<Idx>(trafo_in_.size()); }
+    Idx node_seq(ID id) const;
+    void prepare_topology();
+    template <int B> void prepare_engines();
+    template <int B> void param_arrays(Idx group, std::vector<double>& bp, std::vector<double>& sp, std::vector<double>& srcp) const;
+    template <int B> void gather_pf_input(std::vector<std::vector<double>>& sinj, std::vector<std::vector<double>>& uref) const;
+
+    struct Saved {
+        std::vector<std::pair<Idx, BranchState>> branch;
+        std::vector<std::pair<Idx, TransformerState>> trafo;
+        std::vector<std::pair<Idx, SourceState>> source;
+        std::vector<std::pair<Idx, ShuntState>> shunt;
+        std::vector<std::pair<Idx, LoadGenState>> lg;
+        bool topo{false}, param{false};
+    };
+    void apply_scenario(UpdateData const& u, Idx s, Saved* saved);
+    void restore(Saved const& saved);
+    void mark(bool topo, bool param, Saved* saved);
+    void set_load_power(Idx i, double const* p, double const* q);
+
+    template <int B>
+    int64_t calculate_impl(ModelOptions const& opt, UpdateData const* update, OutputData const& out, int32_t* n_iter,
+                           int32_t* status);
+    template <int B>
+    int64_t run_block(ModelOptions const& opt, Idx n_scn, std::vector<std::vector<double>> const& sinj,
+                      std::vector<std::vector<double>> const& uref, OutputData const& out, Idx first_scenario,
+                      int32_t* n_iter, int32_t* status);
+    template <int B>
+    void write_output(Idx n_scn, Idx first_scenario, OutputData const& out,
+                      std::vector<std::vector<double>> const (&so)[6]) const;
+};
+
+} // namespace pgmb
