@@ -189,6 +189,11 @@ PGMB_API int pgmb_model_get_index(pgmb_model* model, int64_t math_group, const c
 PGMB_API int pgmb_model_get_real(pgmb_model* model, int64_t math_group, int32_t symmetric, const char* name,
                                  const double** data, int64_t* size);
 PGMB_API int64_t pgmb_model_n_math_groups(pgmb_model* model);
+/* PowerFlowInput of every scenario of `update` for one math group (prepare_power_flow_input after applying the scenario's
+ * update, main_core/calculation_input_preparation.hpp:163-188): s_injection [n_scenarios][n_load_gen][B] complex,
+ * source_u_ref [n_scenarios][n_source] complex; caller-allocated. Only valid for batches that change loads / sources. */
+PGMB_API int pgmb_model_batch_pf_input(pgmb_model* model, const pgmb_update_data* update, int32_t symmetric,
+                                       int64_t math_group, double* s_injection, double* source_u_ref);
 /* timing of the last calculate call, milliseconds: [0] host prepare, [1] H2D, [2] solve kernels (CUDA events),
  * [3] output kernels, [4] D2H, [5] total wall */
 PGMB_API int pgmb_model_last_timing(pgmb_model* model, double* ms6);

@@ -72,6 +72,14 @@ int64_t pgmb_model_n_math_groups(pgmb_model* model) {
     return n;
 }
 
+int pgmb_model_batch_pf_input(pgmb_model* model, const pgmb_update_data* update, int32_t symmetric, int64_t math_group,
+                              double* s_injection, double* source_u_ref) {
+    return guarded([&] {
+        if (model == nullptr || update == nullptr || s_injection == nullptr || source_u_ref == nullptr) throw InvalidArgument("null argument");
+        model->model->batch_pf_input(update_of(*update), symmetric != 0, math_group, s_injection, source_u_ref);
+    });
+}
+
 int pgmb_model_get_index(pgmb_model* model, int64_t math_group, const char* name, const int64_t** data, int64_t* size) {
     return guarded([&] {
         if (model == nullptr || name == nullptr) throw InvalidArgument("null argument");

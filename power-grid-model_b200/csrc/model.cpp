@@ -337,6 +337,28 @@ void Model::restore(Saved const& s) {
 
 void Model::update_permanent(UpdateData const& update) { apply_scenario(update, 0, nullptr); }
 
+void Model::batch_pf_input(UpdateData const& update, bool symmetric, Idx group, double* s_injection, double* source_u_ref) {
+    prepare_topology();
+    if (group < 0 || group >= static_cast<Idx>(topo_.math.size())) throw InvalidArgument("math group out of range");
+    std::vector<std::vector<double>> sinj(topo_.math.size()), uref(topo_.math.size());
+    for (Idx s = 0; s != update.n_scenarios; ++s) {
+        Saved saved;
+        apply_scenario(update, s, &saved);
+        bool const structural = saved.topo || saved.param;
+        if (!structural) {
+            if (symmetric) {
+                gather_pf_input<1>(sinj, uref);
+            } else {
+                gather_pf_input<3>(sinj, uref);
+            }
+        }
+        restore(saved);
+        if (structural) throw InvalidArgument("batch changes topology or parameters: no common math model");
+    }
+    std::memcpy(s_injection, sinj[group].data(), sinj[group].size() * sizeof(double));
+    std::memcpy(source_u_ref, uref[group].data(), uref[group].size() * sizeof(double));
+}
+
 // ---- output conversion (host, v1) ------------------------------------------------------------------------------------
 // so[0..5] = u, bus_injection(unused), branch, source, shunt, load_gen per group, scenario-major
 template <int B>

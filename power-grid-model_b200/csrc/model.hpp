@@ -53,6 +53,7 @@ class Model {
     int64_t calculate(ModelOptions const& opt, UpdateData const* update, OutputData const& out, int32_t* n_iter,
                       int32_t* status);
     void update_permanent(UpdateData const& update);
+    void batch_pf_input(UpdateData const& update, bool symmetric, Idx group, double* s_injection, double* source_u_ref);
 
     // introspection for parity tests
     Idx n_math_groups();

@@ -129,6 +129,18 @@ class PowerGridModel:
         check(lib().pgmb_model_last_timing(self._h, t))
         return dict(zip(("prepare", "stage", "solve_kernel", "output", "fetch", "total"), list(t)))
 
+    def batch_pf_input(self, update_data, symmetric=True, group=0):
+        """PowerFlowInput of every scenario for one math group: (s_injection (n_scn, n_load_gen, B), u_ref (n_scn, n_source))"""
+        upd, keep = self._update_struct(update_data, batch=True)
+        B = 1 if symmetric else 3
+        n_lg = int(self.math_index(group, "load_gens_per_bus")[-1])
+        n_src = int(self.math_index(group, "sources_per_bus")[-1])
+        s = np.zeros((upd.n_scenarios, n_lg, B), np.complex128)
+        u = np.zeros((upd.n_scenarios, n_src), np.complex128)
+        check(lib().pgmb_model_batch_pf_input(self._h, C.byref(upd), C.c_int32(int(symmetric)), C.c_int64(group),
+                                              s.ctypes.data_as(C.c_void_p), u.ctypes.data_as(C.c_void_p)))
+        return s, u
+
     # -- introspection (parity tests) ---------------------------------------------------------------------------------
     def n_math_groups(self):
         return int(lib().pgmb_model_n_math_groups(self._h))

@@ -59,8 +59,11 @@ def _compare_with_oracle(res, ref, n_scn):
             elif name == "u_angle":
                 assert np.max(np.abs(np.angle(np.exp(1j * (a - e))))) < 1e-9, (comp, name)
             else:
-                scale = np.maximum(np.abs(e), 1e-3 if name in ("pf", "loading") else 1.0)  # W / A floor for ~0 flows
-                assert np.max(np.abs(a - e) / scale) < 1e-6, (comp, name, np.max(np.abs(a - e) / scale))
+                # 1e-6 relative, plus an absolute floor of 1e-9 pu (1 MVA base => 1e-3 W/var/VA; currents: 1e-7 A) for
+                # flows that are ~0 by cancellation (e.g. the no-load side of an LV transformer)
+                atol = 1e-3 if name[0] in "pqs" and name != "pf" else (1e-7 if name.startswith("i") else 1e-9)
+                err = np.abs(a - e) - (1e-6 * np.abs(e) + atol)
+                assert np.max(err) <= 0, (comp, name, np.max(np.abs(a - e)))
 
 
 @pytest.mark.parametrize("rings", [False, True])
