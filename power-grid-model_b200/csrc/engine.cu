@@ -1,5 +1,6 @@
 #include "engine.hpp"
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -211,6 +212,11 @@ void Engine::stage(PfInputView const& in) {
     db_.status = d_status_.get();
     db_.n_iter = d_n_iter_.get();
     db_.max_dev = d_max_dev_.get();
+    db_.phase_cycles = nullptr;
+    if (env_int("PGMB_DEBUG_PHASES", 0) != 0) {
+        d_phase_.ensure(static_cast<size_t>(n_tile) * 8);
+        db_.phase_cycles = d_phase_.get();
+    }
     PGMB_CUDA(cudaStreamSynchronize(stream_));
 }
 
@@ -224,6 +230,7 @@ float Engine::solve_staged(SolveOptions const& opt_in) {
     if (all_const_y) opt.method = 0;
     if (opt.method == -128) opt.method = 1;
     last_method_ = opt.method;
+    if (db_.phase_cycles != nullptr) PGMB_CUDA(cudaMemsetAsync(db_.phase_cycles, 0, sizeof(unsigned long long) * db_.n_tile * 8, stream_));
     PGMB_CUDA(cudaEventRecord(ev0_, stream_));
     switch (opt.method) {
     case 1:
@@ -237,6 +244,15 @@ float Engine::solve_staged(SolveOptions const& opt_in) {
     PGMB_CUDA(cudaEventSynchronize(ev1_));
     float ms = 0.0f;
     PGMB_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
+    if (db_.phase_cycles != nullptr) {
+        std::vector<unsigned long long> h(static_cast<size_t>(db_.n_tile) * 8);
+        PGMB_CUDA(cudaMemcpy(h.data(), db_.phase_cycles, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        double avg[8] = {};
+        for (int t = 0; t != db_.n_tile; ++t)
+            for (int k = 0; k != 8; ++k) avg[k] += static_cast<double>(h[t * 8 + k]) / db_.n_tile;
+        std::fprintf(stderr, "[pgmb phases, kcycles/tile] init: up0 %.0f up_rest %.0f down_rest %.0f down0 %.0f | iter: up0 %.0f up_rest %.0f down_rest %.0f down0 %.0f\n",
+                     avg[0] / 1e3, avg[1] / 1e3, avg[2] / 1e3, avg[3] / 1e3, avg[4] / 1e3, avg[5] / 1e3, avg[6] / 1e3, avg[7] / 1e3);
+    }
     return ms;
 }
 

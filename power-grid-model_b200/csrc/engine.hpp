@@ -138,6 +138,7 @@ class Engine {
     DevBuf<double> d_out_u_, d_out_inj_, d_out_branch_, d_out_source_, d_out_shunt_, d_out_lg_;
     DevBuf<uint8_t> d_perm_;
     DevBuf<int32_t> d_status_, d_n_iter_;
+    DevBuf<unsigned long long> d_phase_;
     DevBatch db_{};
     int last_method_{1};
 

@@ -58,6 +58,7 @@ struct DevBatch {
     int32_t* status; // [n_scn]
     int32_t* n_iter; // [n_scn]
     double* max_dev; // [n_scn]
+    unsigned long long* phase_cycles; // optional [n_tile][8] clock64 totals per phase (PGMB_DEBUG_PHASES), may be null
 };
 
 struct SolveOptions {

@@ -341,13 +341,19 @@ template <int T, Mode mode> __device__ __forceinline__ double down_row(DevStruct
 
 template <int T, Mode mode>
 __device__ __forceinline__ void sweeps(DevStructure const& s, Tile<T> const& t, int slot, int n_slot, bool active,
-                                       bool& singular, double& dev) {
+                                       bool& singular, double& dev, unsigned long long* phase) {
+    long long t0 = clock64();
     for (int lv = 0; lv < s.n_level; ++lv) {
         int const b = __ldg(s.level_ptr + lv), e = __ldg(s.level_ptr + lv + 1);
         if (active) {
             for (int i = b + slot; i < e; i += n_slot) singular |= up_row<T, mode>(s, t, __ldg(s.level_rows + i));
         }
         __syncthreads();
+        if (phase != nullptr && threadIdx.x == 0) {
+            long long const t1 = clock64();
+            phase[lv == 0 ? 0 : 1] += (unsigned long long)(t1 - t0);
+            t0 = t1;
+        }
     }
     for (int lv = s.n_level - 1; lv >= 0; --lv) {
         int const b = __ldg(s.level_ptr + lv), e = __ldg(s.level_ptr + lv + 1);
@@ -355,6 +361,11 @@ __device__ __forceinline__ void sweeps(DevStructure const& s, Tile<T> const& t, 
             for (int i = b + slot; i < e; i += n_slot) dev = fmax(dev, down_row<T, mode>(s, t, __ldg(s.level_rows + i)));
         }
         __syncthreads();
+        if (phase != nullptr && threadIdx.x == 0) {
+            long long const t1 = clock64();
+            phase[lv == 0 ? 3 : 2] += (unsigned long long)(t1 - t0);
+            t0 = t1;
+        }
     }
 }
 
@@ -395,7 +406,7 @@ template <int T> __global__ void nr_sym_kernel(DevStructure s, DevBatch b, Solve
     {
         bool singular = false;
         double dev = 0.0;
-        sweeps<T, Mode::linear_init>(s, t, slot, n_slot, !done, singular, dev);
+        sweeps<T, Mode::linear_init>(s, t, slot, n_slot, !done, singular, dev, b.phase_cycles ? b.phase_cycles + tile * 8 : nullptr);
         if (singular) sh_singular[lane] = 1;
         __syncthreads();
         if (!done && sh_singular[lane]) {
@@ -416,7 +427,7 @@ template <int T> __global__ void nr_sym_kernel(DevStructure s, DevBatch b, Solve
         if (!__syncthreads_or(!done)) break;
         bool singular = false;
         double dev = 0.0;
-        sweeps<T, Mode::newton>(s, t, slot, n_slot, !done, singular, dev);
+        sweeps<T, Mode::newton>(s, t, slot, n_slot, !done, singular, dev, b.phase_cycles ? b.phase_cycles + tile * 8 + 4 : nullptr);
         if (!done) {
             if (singular) sh_singular[lane] = 1;
             atomicMax(&sh_dev[lane], (unsigned long long)__double_as_longlong(dev)); // dev >= 0: order-preserving
