@@ -19,7 +19,7 @@ int env_int(char const* name, int fallback) {
 } // namespace
 
 Engine::Engine(MathTopology topo, bool symmetric, int device)
-    : topo_{std::move(topo)}, symmetric_{symmetric}, B_{symmetric ? 1 : 3}, device_{device}, pattern_{topo_}, schedule_{pattern_} {
+    : topo_{std::move(topo)}, symmetric_{symmetric}, B_{symmetric ? 1 : 3}, device_{device}, pattern_{topo_}, schedule_{pattern_}, program_{pattern_, schedule_, topo_} {
     if (device < 0) return; // symbolic-only engine (structure introspection on hosts without a GPU); it cannot run
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
@@ -55,6 +55,7 @@ void Engine::upload_structure() {
     d_upd_a_.upload(schedule_.upd_a, stream_);
     d_lg_ptr_.upload(narrow_vec<int32_t>(topo_.load_gens_per_bus), stream_);
     d_src_ptr_.upload(narrow_vec<int32_t>(topo_.sources_per_bus), stream_);
+    d_prog_.upload(program_.words, stream_);
     d_lg_type_.upload(topo_.load_gen_type, stream_);
     d_y_row_ptr_.upload(narrow_vec<int32_t>(pattern_.row_indptr), stream_);
     d_y_col_idx_.upload(narrow_vec<int32_t>(pattern_.col_indices), stream_);
@@ -98,6 +99,8 @@ void Engine::upload_structure() {
     ds_.lg_bus = d_lg_bus_.get();
     ds_.src_bus = d_src_bus_.get();
     ds_.phase_shift = d_phase_shift_.get();
+    ds_.prog = d_prog_.get();
+    ds_.prog_words = static_cast<int32_t>(program_.words.size());
 }
 
 // YBus::update_admittance_entries (y_bus.hpp:400-431): sum of the contributions of each entry, in element order
@@ -234,7 +237,11 @@ float Engine::solve_staged(SolveOptions const& opt_in) {
     PGMB_CUDA(cudaEventRecord(ev0_, stream_));
     switch (opt.method) {
     case 1:
-        launch_nr_sym(tile_width_, ds_, db_, opt, n_slot_, stream_);
+        if (env_int("PGMB_KERNEL", 2) == 1) {
+            launch_nr_sym(tile_width_, ds_, db_, opt, n_slot_, stream_);
+        } else {
+            launch_nr_sym_v2(tile_width_, ds_, db_, opt, n_slot_, stream_);
+        }
         break;
     default:
         throw InvalidArgument("calculation method " + std::to_string(opt.method) + " is not implemented on the GPU yet");

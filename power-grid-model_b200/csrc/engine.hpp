@@ -102,6 +102,7 @@ class Engine {
     MathTopology const& topology() const { return topo_; }
     LuPattern const& pattern() const { return pattern_; }
     EliminationSchedule const& schedule() const { return schedule_; }
+    RowProgram const& program() const { return program_; }
     std::vector<double> const& admittance() const { return admittance_; } // [nnz][B][B] complex
     int device() const { return device_; }
     int phases() const { return B_; }
@@ -118,6 +119,7 @@ class Engine {
     int device_;
     LuPattern pattern_;
     EliminationSchedule schedule_;
+    RowProgram program_;
     std::vector<double> admittance_;
     std::vector<double> branch_param_, shunt_param_, source_param_;
     bool param_set_{false};
@@ -126,7 +128,7 @@ class Engine {
 
     // device structure
     DevBuf<int32_t> d_row_ptr_, d_col_idx_, d_diag_, d_map_y_, d_level_ptr_, d_level_rows_, d_upd_ptr_, d_upd_u_, d_upd_a_,
-        d_lg_ptr_, d_src_ptr_, d_y_row_ptr_, d_y_col_idx_, d_branch_bus_, d_shunt_bus_, d_lg_bus_, d_src_bus_;
+        d_lg_ptr_, d_src_ptr_, d_prog_, d_y_row_ptr_, d_y_col_idx_, d_branch_bus_, d_shunt_bus_, d_lg_bus_, d_src_bus_;
     DevBuf<int8_t> d_lg_type_;
     DevBuf<double> d_ydata_, d_src_yref_, d_src_y1y0_, d_branch_param_, d_shunt_param_, d_phase_shift_;
     DevStructure ds_{};
@@ -149,6 +151,8 @@ class Engine {
 // kernel launchers (nr_sym.cu, result_sym.cu)
 void launch_nr_sym(int tile_width, DevStructure const& s, DevBatch const& b, SolveOptions const& opt, int n_slot,
                    cudaStream_t st);
+void launch_nr_sym_v2(int tile_width, DevStructure const& s, DevBatch const& b, SolveOptions const& opt, int n_slot,
+                      cudaStream_t st);
 void launch_to_tile(int tile_width, double const* src, double* dst, int64_t n_scn, int n_item, int n_comp, int shared_src,
                     cudaStream_t st);
 void launch_from_tile(int tile_width, double const* src, double* dst, int64_t n_scn, int n_item, int n_comp,

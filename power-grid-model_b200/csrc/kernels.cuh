@@ -42,6 +42,9 @@ struct DevStructure {
     double const* branch_param; // [n_branch][4][B*B][2]
     double const* shunt_param;  // [n_shunt][B*B][2]
     double const* phase_shift;  // [n_bus]
+    // row programs (symbolic.hpp RowProgram): level_ptr | task_off | records
+    int32_t const* prog;
+    int32_t prog_words;
 };
 
 // per-batch device buffers, tile layout (see above); B = phases, N = 2B

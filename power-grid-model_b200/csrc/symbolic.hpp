@@ -190,4 +190,58 @@ struct EliminationSchedule {
     int32_t n_level() const { return static_cast<int32_t>(level_ptr.size()) - 1; }
 };
 
+// Row programs: the per-row index data of both sweeps packed into one int32 blob in execution (level) order, so that a
+// thread block can stage it in shared memory with one bulk copy (TMA) and never chase global index arrays.
+//   blob = [level_ptr (n_level + 1)] [task_off (n_bus)] [records ...]        (all offsets in words from blob start)
+//   record (6 words header): row | k_diag | ky_diag | n_lower + (n_upper << 12) + (tree << 24) | lg_start + (n_lg << 24)
+//                            | src_start + (n_src << 24)
+//     tree rows only:  n_lower x (c, ky, k_diag_of_c, k_of_U(c,row))  then  n_upper x (k, j, ky)
+// A "tree row" is a row whose Schur updates all land on its own diagonal block (every lower neighbour c has the single
+// upper entry (c, row)) and that has at most one upper entry: all rows of a radial grid, and the tree part of a meshed one.
+// Such a row is processed entirely in registers; other rows use the generic path on the global index arrays.
+struct RowProgram {
+    std::vector<int32_t> words;
+    int32_t n_tree_rows{};
+
+    RowProgram(LuPattern const& p, EliminationSchedule const& sch, MathTopology const& topo) {
+        Idx const n = p.n_bus;
+        int32_t const n_level = sch.n_level();
+        words.assign(static_cast<size_t>(n_level) + 1 + n, 0);
+        for (int32_t l = 0; l <= n_level; ++l) words[l] = sch.level_ptr[l];
+        for (Idx i = 0; i != n; ++i) {
+            Idx const row = sch.level_rows[i];
+            words[n_level + 1 + i] = static_cast<int32_t>(words.size());
+            Idx const rb = p.row_indptr_lu[row], re = p.row_indptr_lu[row + 1], dg = p.diag_lu[row];
+            Idx const n_lower = dg - rb, n_upper = re - dg - 1;
+            Idx const lg0 = topo.load_gens_per_bus[row], n_lg = topo.load_gens_per_bus[row + 1] - lg0;
+            Idx const s0 = topo.sources_per_bus[row], n_src = topo.sources_per_bus[row + 1] - s0;
+            bool tree = n_upper <= 1 && n_lower < 4096 && n_lg < 128 && n_src < 128 && lg0 < (1 << 24) && s0 < (1 << 24);
+            for (Idx e = rb; e != dg && tree; ++e) {
+                tree = sch.upd_ptr[e + 1] - sch.upd_ptr[e] == 1 && sch.upd_a[sch.upd_ptr[e]] == dg;
+            }
+            words.push_back(static_cast<int32_t>(row));
+            words.push_back(static_cast<int32_t>(dg));
+            words.push_back(static_cast<int32_t>(p.map_lu_y_bus[dg]));
+            words.push_back(static_cast<int32_t>((tree ? n_lower : 0) | ((tree ? n_upper : 0) << 12) | ((tree ? 1 : 0) << 24)));
+            words.push_back(static_cast<int32_t>(tree ? (lg0 | (n_lg << 24)) : 0));
+            words.push_back(static_cast<int32_t>(tree ? (s0 | (n_src << 24)) : 0));
+            if (!tree) continue;
+            ++n_tree_rows;
+            for (Idx e = rb; e != dg; ++e) {
+                Idx const c = p.col_indices_lu[e];
+                words.push_back(static_cast<int32_t>(c));
+                words.push_back(static_cast<int32_t>(p.map_lu_y_bus[e]));
+                words.push_back(static_cast<int32_t>(p.diag_lu[c]));
+                words.push_back(sch.upd_u[sch.upd_ptr[e]]);
+            }
+            for (Idx e = dg + 1; e != re; ++e) {
+                words.push_back(static_cast<int32_t>(e));
+                words.push_back(static_cast<int32_t>(p.col_indices_lu[e]));
+                words.push_back(static_cast<int32_t>(p.map_lu_y_bus[e]));
+            }
+        }
+        while (words.size() % 4 != 0) words.push_back(0); // 16-byte granularity for the bulk copy
+    }
+};
+
 } // namespace pgmb
