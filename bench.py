@@ -191,13 +191,25 @@ def main():
     dev_time = max_over_ranks(kernel_ms / 1e3)
     value = world * N_SCN * args.steps / dev_time
 
-    # ---- end-to-end arm: public model API, host buffers in / host structs out ----
+    # ---- end-to-end arm: public model API, HOST (pinned) update buffers in / HOST (pinned) output structs out ----
+    def pinned(shape, dtype):
+        n = int(np.prod(shape)) * dtype.itemsize
+        return torch.empty(max(n, 1), dtype=torch.uint8, pin_memory=True).numpy()[:n].view(dtype).reshape(shape)
+
+    host_update = {}
+    for k, v in update.items():
+        host_update[k] = pinned(v.shape, v.dtype)
+        host_update[k][...] = v
+    out_dtypes = pgm_b200.structs.SYM_OUTPUT
+    host_out = {c: pinned((N_SCN, len(grid.input_data[c])), out_dtypes[c]) for c in
+                ("node", "line", "transformer", "shunt", "source", "sym_load", "asym_load")}
+    calc["output_buffers"] = host_out
     for _ in range(args.warmup):
-        model.calculate_power_flow(update_data=update, **calc)
+        model.calculate_power_flow(update_data=host_update, **calc)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        res = model.calculate_power_flow(update_data=update, **calc)
+        res = model.calculate_power_flow(update_data=host_update, **calc)
     barrier()
     e2e_time = max_over_ranks(time.perf_counter() - t0)
     clocks = sampler.stop() if rank == 0 else None

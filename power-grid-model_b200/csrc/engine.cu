@@ -156,9 +156,9 @@ void Engine::set_param(double const* branch_param, double const* shunt_param, do
 }
 
 void Engine::choose_tiling(int64_t n_scn) {
-    cudaDeviceProp prop{};
-    PGMB_CUDA(cudaGetDeviceProperties(&prop, device_));
-    int const sm = prop.multiProcessorCount;
+    static int sm_cache[64] = {};
+    if (sm_cache[device_ % 64] == 0) PGMB_CUDA(cudaDeviceGetAttribute(&sm_cache[device_ % 64], cudaDevAttrMultiProcessorCount, device_));
+    int const sm = sm_cache[device_ % 64];
     int t = 4;
     for (int cand : {32, 16, 8, 4}) {
         if ((n_scn + cand - 1) / cand >= (3 * sm) / 4) {
@@ -173,12 +173,11 @@ void Engine::choose_tiling(int64_t n_scn) {
     if (n_slot_ * tile_width_ > 1024) n_slot_ = 1024 / tile_width_;
 }
 
-void Engine::stage(PfInputView const& in) {
+void Engine::allocate_batch(int64_t n) {
     if (device_ < 0) throw CudaError("engine was created without a CUDA device (symbolic only): pgm_b200 has no CPU fallback");
     if (!param_set_) throw InvalidArgument("pgmb_engine_set_param must be called before running");
     if (!symmetric_) throw InvalidArgument("asymmetric calculation is not implemented on the GPU yet");
     PGMB_CUDA(cudaSetDevice(device_));
-    int64_t const n = in.n_scenarios;
     choose_tiling(n);
     int const T = tile_width_;
     int64_t const n_tile = (n + T - 1) / T;
@@ -190,19 +189,11 @@ void Engine::stage(PfInputView const& in) {
     d_u_.ensure(n_tile * nb * N * T);
     d_perm_.ensure(n_tile * nb * T * (B_ == 1 ? 1 : 2 * N));
     d_sinj_.ensure(static_cast<size_t>(n_tile) * topo_.n_load_gen() * 2 * B_ * T + 1);
+    d_lg_status_.ensure(static_cast<size_t>(n_tile) * topo_.n_load_gen() * T + 1);
     d_usrc_.ensure(static_cast<size_t>(n_tile) * topo_.n_source() * 2 * T + 1);
     d_status_.ensure(n + 1);
     d_n_iter_.ensure(n + 1);
     d_max_dev_.ensure(n + 1);
-    size_t const n_sinj = static_cast<size_t>(n) * topo_.n_load_gen() * 2 * B_;
-    size_t const n_usrc = static_cast<size_t>(in.source_is_shared ? 1 : n) * topo_.n_source() * 2;
-    d_in_sinj_.ensure(n_sinj + 1);
-    d_in_usrc_.ensure(n_usrc + 1);
-    if (n_sinj != 0) PGMB_CUDA(cudaMemcpyAsync(d_in_sinj_.get(), in.s_injection, n_sinj * sizeof(double), cudaMemcpyHostToDevice, stream_));
-    if (n_usrc != 0) PGMB_CUDA(cudaMemcpyAsync(d_in_usrc_.get(), in.source_u_ref, n_usrc * sizeof(double), cudaMemcpyHostToDevice, stream_));
-    // host layout per load_gen: [B] complex = (re, im) interleaved; tile layout wants re[B], im[B]: for B = 1 identical
-    launch_to_tile(T, d_in_sinj_.get(), d_sinj_.get(), n, static_cast<int>(topo_.n_load_gen()), 2 * B_, 0, stream_);
-    launch_to_tile(T, d_in_usrc_.get(), d_usrc_.get(), n, static_cast<int>(topo_.n_source()), 2, in.source_is_shared ? 1 : 0, stream_);
     db_.n_scn = n;
     db_.n_tile = static_cast<int32_t>(n_tile);
     db_.jac = d_jac_.get();
@@ -215,11 +206,51 @@ void Engine::stage(PfInputView const& in) {
     db_.status = d_status_.get();
     db_.n_iter = d_n_iter_.get();
     db_.max_dev = d_max_dev_.get();
+    db_.lg_status = d_lg_status_.get();
     db_.phase_cycles = nullptr;
     if (env_int("PGMB_DEBUG_PHASES", 0) != 0) {
         d_phase_.ensure(static_cast<size_t>(n_tile) * 8);
         db_.phase_cycles = d_phase_.get();
     }
+}
+
+void Engine::stage(PfInputView const& in) {
+    int64_t const n = in.n_scenarios;
+    allocate_batch(n);
+    int const T = tile_width_;
+    size_t const n_sinj = static_cast<size_t>(n) * topo_.n_load_gen() * 2 * B_;
+    size_t const n_usrc = static_cast<size_t>(in.source_is_shared ? 1 : n) * topo_.n_source() * 2;
+    d_in_sinj_.ensure(n_sinj + 1);
+    d_in_usrc_.ensure(n_usrc + 1);
+    if (n_sinj != 0) PGMB_CUDA(cudaMemcpyAsync(d_in_sinj_.get(), in.s_injection, n_sinj * sizeof(double), cudaMemcpyHostToDevice, stream_));
+    if (n_usrc != 0) PGMB_CUDA(cudaMemcpyAsync(d_in_usrc_.get(), in.source_u_ref, n_usrc * sizeof(double), cudaMemcpyHostToDevice, stream_));
+    // host layout per load_gen: [B] complex = (re, im) interleaved; tile layout wants re[B], im[B]: for B = 1 identical
+    launch_to_tile(T, d_in_sinj_.get(), d_sinj_.get(), n, static_cast<int>(topo_.n_load_gen()), 2 * B_, 0, stream_);
+    launch_to_tile(T, d_in_usrc_.get(), d_usrc_.get(), n, static_cast<int>(topo_.n_source()), 2, in.source_is_shared ? 1 : 0, stream_);
+    PGMB_CUDA(cudaMemsetAsync(d_lg_status_.get(), 1, d_lg_status_.size(), stream_));
+    PGMB_CUDA(cudaStreamSynchronize(stream_));
+}
+
+void Engine::stage_device(int64_t n, double const* source_u_ref, bool source_is_shared) {
+    allocate_batch(n);
+    size_t const n_usrc = static_cast<size_t>(source_is_shared ? 1 : n) * topo_.n_source() * 2;
+    d_in_usrc_.ensure(n_usrc + 1);
+    if (n_usrc != 0) PGMB_CUDA(cudaMemcpyAsync(d_in_usrc_.get(), source_u_ref, n_usrc * sizeof(double), cudaMemcpyHostToDevice, stream_));
+    launch_to_tile(tile_width_, d_in_usrc_.get(), d_usrc_.get(), n, static_cast<int>(topo_.n_source()), 2, source_is_shared ? 1 : 0, stream_);
+    PGMB_CUDA(cudaStreamSynchronize(stream_)); // source_u_ref may be a temporary of the caller
+}
+
+void Engine::apply_load_updates(DevModelTables const& m, DevUpdateBuffers const& ub) {
+    PGMB_CUDA(cudaSetDevice(device_));
+    launch_apply_load_update_sym(tile_width_, ds_, db_, m, ub, stream_);
+    PGMB_CUDA(cudaGetLastError());
+}
+
+void Engine::fetch_status(int32_t* status, int32_t* n_iter) {
+    PGMB_CUDA(cudaSetDevice(device_));
+    if (db_.n_scn == 0) return;
+    PGMB_CUDA(cudaMemcpyAsync(status, d_status_.get(), sizeof(int32_t) * db_.n_scn, cudaMemcpyDeviceToHost, stream_));
+    PGMB_CUDA(cudaMemcpyAsync(n_iter, d_n_iter_.get(), sizeof(int32_t) * db_.n_scn, cudaMemcpyDeviceToHost, stream_));
     PGMB_CUDA(cudaStreamSynchronize(stream_));
 }
 

@@ -95,6 +95,11 @@ class Engine {
     void set_param(double const* branch_param, double const* shunt_param, double const* source_param);
 
     void stage(PfInputView const& in);                      // H2D + layout conversion
+    // device path of the model level: allocate the batch, upload per-scenario source references; load injections are then
+    // produced on the device by apply_load_updates()
+    void stage_device(int64_t n_scn, double const* source_u_ref, bool source_is_shared);
+    void apply_load_updates(DevModelTables const& m, DevUpdateBuffers const& ub);
+    void fetch_status(int32_t* status, int32_t* n_iter);
     float solve_staged(SolveOptions const& opt);            // kernels only; returns solver-kernel milliseconds
     void fetch(SolverOutputView const& out);                // result extraction + D2H
     int run(SolveOptions const& opt, PfInputView const& in, SolverOutputView const& out); // returns #failed
@@ -138,7 +143,7 @@ class Engine {
     int n_slot_{64};
     DevBuf<double> d_jac_, d_xvec_, d_pol_, d_u_, d_sinj_, d_usrc_, d_max_dev_, d_in_sinj_, d_in_usrc_;
     DevBuf<double> d_out_u_, d_out_inj_, d_out_branch_, d_out_source_, d_out_shunt_, d_out_lg_;
-    DevBuf<uint8_t> d_perm_;
+    DevBuf<uint8_t> d_perm_, d_lg_status_;
     DevBuf<int32_t> d_status_, d_n_iter_;
     DevBuf<unsigned long long> d_phase_;
     DevBatch db_{};
@@ -146,6 +151,7 @@ class Engine {
 
     void upload_structure();
     void choose_tiling(int64_t n_scn);
+    void allocate_batch(int64_t n_scn);
 };
 
 // kernel launchers (nr_sym.cu, result_sym.cu)
@@ -153,6 +159,15 @@ void launch_nr_sym(int tile_width, DevStructure const& s, DevBatch const& b, Sol
                    cudaStream_t st);
 void launch_nr_sym_v2(int tile_width, DevStructure const& s, DevBatch const& b, SolveOptions const& opt, int n_slot,
                       cudaStream_t st);
+void launch_apply_load_update_sym(int tw, DevStructure const& s, DevBatch const& b, DevModelTables const& m,
+                                  DevUpdateBuffers const& ub, cudaStream_t st);
+void launch_source_result_sym(int tw, DevStructure const& s, DevBatch const& b, int force_const_y, double* out, cudaStream_t st);
+void launch_pack_node_sym(int tw, DevStructure const& s, DevBatch const& b, DevModelTables const& m, int force_const_y,
+                          double const* src_res, void* out, cudaStream_t st);
+void launch_pack_branch_sym(int tw, DevStructure const& s, DevBatch const& b, DevModelTables const& m, int first, int count,
+                            void* out, cudaStream_t st);
+void launch_pack_appliance_sym(int tw, DevStructure const& s, DevBatch const& b, DevModelTables const& m, int force_const_y,
+                               int first, int count, double const* src_res, void* out, cudaStream_t st);
 void launch_to_tile(int tile_width, double const* src, double* dst, int64_t n_scn, int n_item, int n_comp, int shared_src,
                     cudaStream_t st);
 void launch_from_tile(int tile_width, double const* src, double* dst, int64_t n_scn, int n_item, int n_comp,

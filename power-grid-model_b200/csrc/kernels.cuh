@@ -61,7 +61,45 @@ struct DevBatch {
     int32_t* status; // [n_scn]
     int32_t* n_iter; // [n_scn]
     double* max_dev; // [n_scn]
+    uint8_t* lg_status; // [tile][n_load_gen][T] per-scenario status of each load_gen (device update path), may be null
     unsigned long long* phase_cycles; // optional [n_tile][8] clock64 totals per phase (PGMB_DEBUG_PHASES), may be null
+};
+
+// component-level tables of one math group for the device-side update and output kernels (model level)
+struct DevModelTables {
+    int32_t n_node, n_branch_comp, n_appliance;
+    // nodes
+    int32_t const* node_id;
+    double const* node_u_rated;
+    int32_t const* node_bus;      // math bus or -1 (not connected to a source)
+    int32_t const* node_app_ptr;  // CSR over nodes
+    int32_t const* node_app;      // (kind << 28) | math index ; kind 0 = source, 1 = load_gen; reference summation order
+    // branch components: lines then transformers
+    int32_t const* branch_id;
+    int32_t const* branch_math;   // math branch or -1
+    double const* branch_base_i;  // [n][2] from, to
+    double const* branch_rating;  // > 0: sn (loading = max_s / sn) ; < 0: -i_n (loading = max_i / i_n)
+    uint8_t const* branch_energized;
+    // appliances: shunt, source, sym_gen, asym_gen, sym_load, asym_load (concatenated in this order)
+    int32_t const* app_id;
+    int32_t const* app_math;      // math index inside its kind or -1
+    int8_t const* app_kind;       // 0 shunt, 1 source, 2 load_gen
+    double const* app_base_i;
+    double const* app_dir;        // injection direction
+    uint8_t const* app_status;    // shunt / source status (load_gen status is per scenario: DevBatch.lg_status)
+    // load update application: per math load_gen
+    int8_t const* lg_phases;      // 1 (sym component) or 3 (asym component)
+    int8_t const* lg_upd_buf;     // update buffer 0..3 (sym_gen, asym_gen, sym_load, asym_load) or -1 = never updated
+    int32_t const* lg_upd_pos;    // element position inside one scenario of that buffer
+    double const* lg_base_s;      // [n_lg][3][2] per-unit specified power of the permanent state
+    uint8_t const* lg_base_status;
+    double const* lg_scale;       // direction / base_power of the component
+};
+
+struct DevUpdateBuffers {
+    void const* data[4];          // device copies of the scenario-major update rows
+    int64_t n_per_scenario[4];
+    int64_t first_scenario;       // scenario offset of this chunk inside the caller's buffers
 };
 
 struct SolveOptions {

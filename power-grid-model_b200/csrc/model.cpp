@@ -141,6 +141,7 @@ void Model::prepare_topology() {
         g.load_gen_type.push_back(l.type);
     }
     topo_ = build_topology(g);
+    dev_.reset();
     engines_.clear();
     engines_.resize(topo_.math.size());
     param_valid_[0] = param_valid_[1] = false;
@@ -575,7 +576,22 @@ int64_t Model::calculate_impl(ModelOptions const& opt, UpdateData const* update,
                         source_param_change = true;
             }
         }
-        if (!structural && !source_param_change) {
+        bool device_done = false;
+        if constexpr (B == 1) {
+            if (!structural && !source_param_change && device_path_eligible(*update)) {
+                prepare_engines<B>();
+                timing[0] += ms_since(t0);
+                int64_t const r = run_batch_device(opt, *update, out, n_iter, status);
+                if (r >= 0) {
+                    failed = r;
+                    device_done = true;
+                }
+                t0 = Clock::now();
+            }
+        }
+        if (device_done) {
+            // results written by the device path
+        } else if (!structural && !source_param_change) {
             // fast path: one engine call for the whole batch
             prepare_engines<B>();
             std::vector<std::vector<double>> sinj(topo_.math.size()), uref(topo_.math.size());

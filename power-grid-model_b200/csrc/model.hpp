@@ -14,6 +14,7 @@
 
 #include <chrono>
 #include <map>
+#include <memory>
 #include <unordered_map>
 
 namespace pgmb {
@@ -133,6 +134,12 @@ class Model {
     int64_t run_block(ModelOptions const& opt, Idx n_scn, std::vector<std::vector<double>> const& sinj,
                       std::vector<std::vector<double>> const& uref, OutputData const& out, Idx first_scenario,
                       int32_t* n_iter, int32_t* status);
+    // ---- device path (model_device.cpp): updates applied and output structs written by CUDA kernels ----
+    struct DeviceSide;
+    std::shared_ptr<DeviceSide> dev_;
+    bool device_path_eligible(UpdateData const& update) const;
+    int64_t run_batch_device(ModelOptions const& opt, UpdateData const& update, OutputData const& out, int32_t* n_iter,
+                             int32_t* status);
     template <int B>
     void write_output(Idx n_scn, Idx first_scenario, OutputData const& out,
                       std::vector<std::vector<double>> const (&so)[6]) const;

@@ -1,0 +1,372 @@
+// Device path of the model level: for batches that only change loads / generators (and source references), the raw update
+// rows are copied to the GPU once, applied there for every scenario, solved, and the caller's output structs are written by
+// kernels straight into a device image of the caller's buffers, which is then copied back with one DMA per component.
+// Host work per batch: one pass over the ids of scenario 0 (update element -> load_gen mapping), pinned-memory detection,
+// kernel launches.  Replaces, for such batches, the per-scenario update -> prepare_power_flow_input -> output_result ->
+// restore loop of the reference (job_dispatch.hpp:88-138, job_adapter.hpp:127-139).
+#include "model.hpp"
+
+#include <cstring>
+
+namespace pgmb {
+
+namespace {
+using Clock = std::chrono::steady_clock;
+double ms_since(Clock::time_point t0) { return std::chrono::duration<double, std::milli>(Clock::now() - t0).count(); }
+
+bool is_device_accessible_host(void const* p) { // pinned (page-locked) host memory?
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeHost;
+}
+} // namespace
+
+struct Model::DeviceSide {
+    // static tables (valid while the topology / permanent state is unchanged)
+    DevBuf<int32_t> node_id, node_bus, node_app_ptr, node_app, branch_id, branch_math, app_id, app_math, lg_upd_pos;
+    DevBuf<double> node_u_rated, branch_base_i, branch_rating, app_base_i, app_dir, lg_base_s, lg_scale;
+    DevBuf<uint8_t> branch_energized, app_status, lg_base_status;
+    DevBuf<int8_t> app_kind, lg_phases, lg_upd_buf;
+    DevModelTables t{};
+    Idx n_app_first[6]{}; // first appliance index of shunt, source, sym_gen, asym_gen, sym_load, asym_load
+    // per-batch buffers
+    DevBuf<unsigned char> upd[4];
+    DevBuf<unsigned char> out[9];
+    DevBuf<double> src_res;
+    DevBuf<int32_t> flag;
+    // pinned staging for pageable caller buffers
+    unsigned char* pinned{nullptr};
+    size_t pinned_size{0};
+    ~DeviceSide() {
+        if (pinned != nullptr) cudaFreeHost(pinned);
+    }
+    unsigned char* staging(size_t bytes) {
+        if (bytes > pinned_size) {
+            if (pinned != nullptr) cudaFreeHost(pinned);
+            pinned = nullptr;
+            PGMB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&pinned), bytes));
+            pinned_size = bytes;
+        }
+        return pinned;
+    }
+};
+
+bool Model::device_path_eligible(UpdateData const& u) const {
+    if (topo_.math.size() != 1) return false;
+    ComponentBuffer const* bufs[4] = {&u.sym_gen, &u.asym_gen, &u.sym_load, &u.asym_load};
+    for (auto const* b : bufs) {
+        if (b->data != nullptr && (b->indptr != nullptr || b->n < 0)) return false; // sparse batches: host path
+    }
+    return u.n_scenarios > 0;
+}
+
+// returns number of failed scenarios, or -1 when the batch turned out not to be uniform (caller falls back to the host path)
+int64_t Model::run_batch_device(ModelOptions const& opt, UpdateData const& update, OutputData const& out, int32_t* n_iter,
+                                int32_t* status) {
+    auto t0 = Clock::now();
+    Engine& e = *engines_[0].engine[0];
+    cudaStream_t const st = e.stream();
+    MathTopology const& m = topo_.math[0];
+    Idx const n_scn = update.n_scenarios;
+    Idx const nn = static_cast<Idx>(node_.size());
+    Idx const n_lg_math = m.n_load_gen();
+    if (!dev_) dev_ = std::make_shared<DeviceSide>();
+    DeviceSide& d = *dev_;
+
+    // ---- tables (rebuilt per call: a few thousand elements; the permanent state may have changed) ----
+    {
+        std::vector<int32_t> node_id(nn), node_bus(nn), app_ptr(nn + 1, 0), app;
+        std::vector<double> u_rated(nn);
+        std::vector<std::vector<int32_t>> per_node(nn);
+        for (size_t i = 0; i != source_in_.size(); ++i)
+            if (topo_.source[i].group == 0) per_node[node_idx_.at(source_in_[i].node)].push_back(static_cast<int32_t>(topo_.source[i].pos));
+        Idx const o_sg = 0, o_ag = n_sym_gen_, o_sl = n_sym_gen_ + n_asym_gen_, o_al = o_sl + n_sym_load_;
+        auto add_lg = [&](Idx begin, Idx count) {
+            for (Idx i = begin; i != begin + count; ++i)
+                if (topo_.load_gen[i].group == 0) per_node[lg_[i].node].push_back(static_cast<int32_t>((1u << 28) | topo_.load_gen[i].pos));
+        };
+        add_lg(o_sl, n_sym_load_);
+        add_lg(o_sg, n_sym_gen_);
+        add_lg(o_al, n_asym_load_);
+        add_lg(o_ag, n_asym_gen_);
+        for (Idx i = 0; i != nn; ++i) {
+            node_id[i] = node_[i].id;
+            u_rated[i] = node_[i].u_rated;
+            node_bus[i] = topo_.node[i].group == 0 ? static_cast<int32_t>(topo_.node[i].pos) : -1;
+            app.insert(app.end(), per_node[i].begin(), per_node[i].end());
+            app_ptr[i + 1] = static_cast<int32_t>(app.size());
+        }
+        Idx const nb = n_line() + n_trafo();
+        std::vector<int32_t> b_id(nb), b_math(nb);
+        std::vector<double> b_base(2 * nb), b_rating(nb);
+        std::vector<uint8_t> b_en(nb);
+        for (Idx i = 0; i != nb; ++i) {
+            bool const is_line = i < n_line();
+            Idx const k = is_line ? i : i - n_line();
+            b_id[i] = is_line ? line_in_[k].id : trafo_in_[k].id;
+            b_math[i] = topo_.branch[i].group == 0 ? static_cast<int32_t>(topo_.branch[i].pos) : -1;
+            b_base[2 * i] = is_line ? line_c_[k].base_i : trafo_c_[k].base_i_from;
+            b_base[2 * i + 1] = is_line ? line_c_[k].base_i : trafo_c_[k].base_i_to;
+            b_rating[i] = is_line ? -line_in_[k].i_n : trafo_c_[k].sn;
+            b_en[i] = (branch_st_[i].from_status || branch_st_[i].to_status) ? 1 : 0;
+        }
+        Idx const n_app = static_cast<Idx>(shunt_in_.size() + source_in_.size() + lg_.size());
+        std::vector<int32_t> a_id(n_app), a_math(n_app);
+        std::vector<int8_t> a_kind(n_app);
+        std::vector<double> a_base(n_app), a_dir(n_app);
+        std::vector<uint8_t> a_status(n_app);
+        Idx k = 0;
+        d.n_app_first[0] = k;
+        for (size_t i = 0; i != shunt_in_.size(); ++i, ++k) {
+            a_id[k] = shunt_in_[i].id;
+            a_math[k] = topo_.shunt[i].group == 0 ? static_cast<int32_t>(topo_.shunt[i].pos) : -1;
+            a_kind[k] = 0;
+            a_base[k] = kBasePower3p / node_[node_idx_.at(shunt_in_[i].node)].u_rated / kSqrt3;
+            a_dir[k] = -1.0;
+            a_status[k] = shunt_st_[i].status ? 1 : 0;
+        }
+        d.n_app_first[1] = k;
+        for (size_t i = 0; i != source_in_.size(); ++i, ++k) {
+            a_id[k] = source_in_[i].id;
+            a_math[k] = topo_.source[i].group == 0 ? static_cast<int32_t>(topo_.source[i].pos) : -1;
+            a_kind[k] = 1;
+            a_base[k] = kBasePower3p / node_[node_idx_.at(source_in_[i].node)].u_rated / kSqrt3;
+            a_dir[k] = 1.0;
+            a_status[k] = source_st_[i].status ? 1 : 0;
+        }
+        d.n_app_first[2] = k;
+        d.n_app_first[3] = k + n_sym_gen_;
+        d.n_app_first[4] = k + n_sym_gen_ + n_asym_gen_;
+        d.n_app_first[5] = k + n_sym_gen_ + n_asym_gen_ + n_sym_load_;
+        for (size_t i = 0; i != lg_.size(); ++i, ++k) {
+            a_id[k] = lg_[i].id;
+            a_math[k] = topo_.load_gen[i].group == 0 ? static_cast<int32_t>(topo_.load_gen[i].pos) : -1;
+            a_kind[k] = 2;
+            a_base[k] = lg_[i].base_i;
+            a_dir[k] = lg_[i].direction;
+            a_status[k] = lg_st_[i].status ? 1 : 0;
+        }
+        // load update mapping from the ids of scenario 0 (an independent batch repeats them in every scenario)
+        std::vector<int8_t> lg_phases(n_lg_math, 1), lg_buf(n_lg_math, -1);
+        std::vector<int32_t> lg_pos(n_lg_math, 0);
+        std::vector<double> lg_base(n_lg_math * 6, 0.0), lg_scale(n_lg_math, 0.0);
+        std::vector<uint8_t> lg_st(n_lg_math, 0);
+        for (size_t i = 0; i != lg_.size(); ++i) {
+            Coupling const c = topo_.load_gen[i];
+            if (c.group != 0) continue;
+            lg_phases[c.pos] = static_cast<int8_t>(lg_[i].lb);
+            for (int p = 0; p != 3; ++p) {
+                lg_base[(c.pos * 3 + p) * 2] = lg_st_[i].s[p].real();
+                lg_base[(c.pos * 3 + p) * 2 + 1] = lg_st_[i].s[p].imag();
+            }
+            lg_scale[c.pos] = lg_[i].direction / (lg_[i].lb == 1 ? kBasePower3p : kBasePower1p);
+            lg_st[c.pos] = lg_st_[i].status ? 1 : 0;
+        }
+        ComponentBuffer const* bufs[4] = {&update.sym_gen, &update.asym_gen, &update.sym_load, &update.asym_load};
+        Idx const first[4] = {0, n_sym_gen_, n_sym_gen_ + n_asym_gen_, n_sym_gen_ + n_asym_gen_ + n_sym_load_};
+        Idx const count[4] = {n_sym_gen_, n_asym_gen_, n_sym_load_, n_asym_load_};
+        size_t const row_size[4] = {sizeof(SymLoadGenUpdate), sizeof(AsymLoadGenUpdate), sizeof(SymLoadGenUpdate), sizeof(AsymLoadGenUpdate)};
+        for (int bfr = 0; bfr != 4; ++bfr) {
+            if (bufs[bfr]->data == nullptr) continue;
+            auto const* base = static_cast<unsigned char const*>(bufs[bfr]->data);
+            std::vector<char> seen(count[bfr], 0);
+            for (Idx kpos = 0; kpos != bufs[bfr]->n; ++kpos) {
+                ID id;
+                std::memcpy(&id, base + kpos * row_size[bfr], sizeof(ID));
+                Idx seq;
+                if (id == kNaID) {
+                    if (bufs[bfr]->n != count[bfr]) throw InvalidArgument("update without ids must cover every element of the component");
+                    seq = first[bfr] + kpos;
+                } else {
+                    auto it = lg_idx_.find(id);
+                    if (it == lg_idx_.end() || it->second < first[bfr] || it->second >= first[bfr] + count[bfr])
+                        throw InvalidArgument("The id cannot be found: " + std::to_string(id) + "\n");
+                    seq = it->second;
+                }
+                if (seen[seq - first[bfr]]) return -1; // same element updated twice in one scenario: host path keeps the order
+                seen[seq - first[bfr]] = 1;
+                Coupling const c = topo_.load_gen[seq];
+                if (c.group != 0) continue;
+                lg_buf[c.pos] = static_cast<int8_t>(bfr);
+                lg_pos[c.pos] = static_cast<int32_t>(kpos);
+            }
+        }
+        d.node_id.upload(node_id, st);
+        d.node_bus.upload(node_bus, st);
+        d.node_app_ptr.upload(app_ptr, st);
+        d.node_app.upload(app, st);
+        d.node_u_rated.upload(u_rated, st);
+        d.branch_id.upload(b_id, st);
+        d.branch_math.upload(b_math, st);
+        d.branch_base_i.upload(b_base, st);
+        d.branch_rating.upload(b_rating, st);
+        d.branch_energized.upload(b_en, st);
+        d.app_id.upload(a_id, st);
+        d.app_math.upload(a_math, st);
+        d.app_kind.upload(a_kind, st);
+        d.app_base_i.upload(a_base, st);
+        d.app_dir.upload(a_dir, st);
+        d.app_status.upload(a_status, st);
+        d.lg_phases.upload(lg_phases, st);
+        d.lg_upd_buf.upload(lg_buf, st);
+        d.lg_upd_pos.upload(lg_pos, st);
+        d.lg_base_s.upload(lg_base, st);
+        d.lg_base_status.upload(lg_st, st);
+        d.lg_scale.upload(lg_scale, st);
+        PGMB_CUDA(cudaStreamSynchronize(st)); // host vectors die at the end of this scope
+        d.t = DevModelTables{static_cast<int32_t>(nn), static_cast<int32_t>(nb), static_cast<int32_t>(n_app),
+                             d.node_id.get(), d.node_u_rated.get(), d.node_bus.get(), d.node_app_ptr.get(), d.node_app.get(),
+                             d.branch_id.get(), d.branch_math.get(), d.branch_base_i.get(), d.branch_rating.get(),
+                             d.branch_energized.get(), d.app_id.get(), d.app_math.get(), d.app_kind.get(), d.app_base_i.get(),
+                             d.app_dir.get(), d.app_status.get(), d.lg_phases.get(), d.lg_upd_buf.get(), d.lg_upd_pos.get(),
+                             d.lg_base_s.get(), d.lg_base_status.get(), d.lg_scale.get()};
+    }
+
+    // ---- ids must repeat in every scenario (independent batch, main_core/update.hpp:58-83) ----
+    {
+        ComponentBuffer const* bufs[4] = {&update.sym_gen, &update.asym_gen, &update.sym_load, &update.asym_load};
+        size_t const row_size[4] = {sizeof(SymLoadGenUpdate), sizeof(AsymLoadGenUpdate), sizeof(SymLoadGenUpdate), sizeof(AsymLoadGenUpdate)};
+        for (int bfr = 0; bfr != 4; ++bfr) {
+            if (bufs[bfr]->data == nullptr) continue;
+            auto const* base = static_cast<unsigned char const*>(bufs[bfr]->data);
+            Idx const n = bufs[bfr]->n;
+            size_t const rs = row_size[bfr];
+            for (Idx s = 1; s < n_scn; ++s) {
+                unsigned char const* row = base + s * n * rs;
+                for (Idx kpos = 0; kpos != n; ++kpos) {
+                    if (std::memcmp(row + kpos * rs, base + kpos * rs, sizeof(ID)) != 0) return -1;
+                }
+            }
+        }
+    }
+    // per-scenario source references (u_ref / u_ref_angle updates are allowed on this path)
+    std::vector<double> uref;
+    bool uref_shared = true;
+    if (update.source.data != nullptr) {
+        uref_shared = false;
+        std::vector<std::vector<double>> sinj_unused(1), u(1);
+        for (Idx s = 0; s != n_scn; ++s) {
+            Saved saved;
+            UpdateData only_source{};
+            only_source.n_scenarios = update.n_scenarios;
+            only_source.source = update.source;
+            apply_scenario(only_source, s, &saved);
+            size_t const off = u[0].size();
+            u[0].resize(off + m.n_source() * 2);
+            for (size_t i = 0; i != source_in_.size(); ++i) {
+                Coupling const c = topo_.source[i];
+                if (c.group != 0) continue;
+                cplx const v = source_u_ref(source_st_[i]);
+                u[0][off + c.pos * 2] = v.real();
+                u[0][off + c.pos * 2 + 1] = v.imag();
+            }
+            restore(saved);
+        }
+        uref = std::move(u[0]);
+    } else {
+        uref.assign(m.n_source() * 2, 0.0);
+        for (size_t i = 0; i != source_in_.size(); ++i) {
+            Coupling const c = topo_.source[i];
+            if (c.group != 0) continue;
+            cplx const v = source_u_ref(source_st_[i]);
+            uref[c.pos * 2] = v.real();
+            uref[c.pos * 2 + 1] = v.imag();
+        }
+    }
+    timing[0] += ms_since(t0);
+
+    // ---- H2D: raw update rows ----
+    t0 = Clock::now();
+    e.stage_device(n_scn, uref.data(), uref_shared);
+    DevUpdateBuffers ub{};
+    {
+        ComponentBuffer const* bufs[4] = {&update.sym_gen, &update.asym_gen, &update.sym_load, &update.asym_load};
+        size_t const row_size[4] = {sizeof(SymLoadGenUpdate), sizeof(AsymLoadGenUpdate), sizeof(SymLoadGenUpdate), sizeof(AsymLoadGenUpdate)};
+        for (int bfr = 0; bfr != 4; ++bfr) {
+            if (bufs[bfr]->data == nullptr || bufs[bfr]->n == 0) continue;
+            size_t const bytes = static_cast<size_t>(n_scn) * bufs[bfr]->n * row_size[bfr];
+            d.upd[bfr].ensure(bytes);
+            PGMB_CUDA(cudaMemcpyAsync(d.upd[bfr].get(), bufs[bfr]->data, bytes, cudaMemcpyHostToDevice, st));
+            ub.data[bfr] = d.upd[bfr].get();
+            ub.n_per_scenario[bfr] = bufs[bfr]->n;
+        }
+    }
+    e.apply_load_updates(d.t, ub);
+    PGMB_CUDA(cudaStreamSynchronize(st));
+    timing[1] += ms_since(t0);
+
+    // ---- solve ----
+    timing[2] += e.solve_staged({opt.method, opt.err_tol, static_cast<int32_t>(opt.max_iter)});
+
+    // ---- output structs on the device, then one DMA per requested component ----
+    t0 = Clock::now();
+    int const tw = e.tile_width();
+    DevStructure const& ds = e.dev_structure();
+    DevBatch const& db = e.dev_batch();
+    int const force_const_y = e.last_method() == 0 ? 1 : 0;
+    d.src_res.ensure(static_cast<size_t>(n_scn) * m.n_source() * 4 + 1);
+    launch_source_result_sym(tw, ds, db, force_const_y, d.src_res.get(), st);
+    struct Req {
+        void* host;
+        int slot;
+        size_t row;
+        Idx count;
+    };
+    Req const reqs[9] = {
+        {out.node, 0, sizeof(NodeOutput<1>), nn},
+        {out.line, 1, sizeof(BranchOutput<1>), n_line()},
+        {out.transformer, 2, sizeof(BranchOutput<1>), n_trafo()},
+        {out.shunt, 3, sizeof(ApplianceOutput<1>), static_cast<Idx>(shunt_in_.size())},
+        {out.source, 4, sizeof(ApplianceOutput<1>), static_cast<Idx>(source_in_.size())},
+        {out.sym_gen, 5, sizeof(ApplianceOutput<1>), n_sym_gen_},
+        {out.asym_gen, 6, sizeof(ApplianceOutput<1>), n_asym_gen_},
+        {out.sym_load, 7, sizeof(ApplianceOutput<1>), n_sym_load_},
+        {out.asym_load, 8, sizeof(ApplianceOutput<1>), n_asym_load_},
+    };
+    for (Req const& r : reqs) {
+        if (r.host == nullptr || r.count == 0) continue;
+        d.out[r.slot].ensure(static_cast<size_t>(n_scn) * r.count * r.row);
+        void* dst = d.out[r.slot].get();
+        switch (r.slot) {
+        case 0: launch_pack_node_sym(tw, ds, db, d.t, force_const_y, d.src_res.get(), dst, st); break;
+        case 1: launch_pack_branch_sym(tw, ds, db, d.t, 0, static_cast<int>(n_line()), dst, st); break;
+        case 2: launch_pack_branch_sym(tw, ds, db, d.t, static_cast<int>(n_line()), static_cast<int>(n_trafo()), dst, st); break;
+        default:
+            launch_pack_appliance_sym(tw, ds, db, d.t, force_const_y, static_cast<int>(d.n_app_first[r.slot - 3]),
+                                      static_cast<int>(r.count), d.src_res.get(), dst, st);
+        }
+    }
+    PGMB_CUDA(cudaGetLastError());
+    PGMB_CUDA(cudaStreamSynchronize(st));
+    timing[3] += ms_since(t0);
+
+    t0 = Clock::now();
+    for (Req const& r : reqs) {
+        if (r.host == nullptr || r.count == 0) continue;
+        size_t const bytes = static_cast<size_t>(n_scn) * r.count * r.row;
+        PGMB_CUDA(cudaMemcpyAsync(r.host, d.out[r.slot].get(), bytes, cudaMemcpyDeviceToHost, st));
+    }
+    std::vector<int32_t> st_local(n_scn), it_local(n_scn);
+    e.fetch_status(st_local.data(), it_local.data());
+    PGMB_CUDA(cudaStreamSynchronize(st));
+    timing[4] += ms_since(t0);
+
+    int64_t failed = 0;
+    for (Idx s = 0; s != n_scn; ++s) {
+        if (n_iter != nullptr) n_iter[s] = it_local[s];
+        if (status != nullptr) status[s] = st_local[s];
+        if (st_local[s] != 0) {
+            ++failed;
+            batch_message += "Error in batch #" + std::to_string(s) + ": " +
+                             (st_local[s] == 1 ? "Iteration failed to converge after " + std::to_string(opt.max_iter) + " iterations!"
+                                               : "Sparse matrix error, possibly singular matrix!") + "\n";
+        }
+    }
+    (void)is_device_accessible_host;
+    return failed;
+}
+
+} // namespace pgmb

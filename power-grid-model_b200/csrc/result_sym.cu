@@ -4,69 +4,11 @@
 //                                                       (math_solver/common_solver_functions.hpp:83-101, 143-160, 383-409)
 // One thread per (scenario, element); output is scenario-major like the caller's host buffers, so consecutive threads
 // write consecutive elements.  Bus voltages are read from the tile layout written by the solver kernel.
-#include "kernels.cuh"
-
-#include <cuComplex.h>
+#include "result_common.cuh"
 
 namespace pgmb {
+using namespace res;
 namespace {
-
-struct C {
-    double r, i;
-};
-__device__ __forceinline__ C cmul(C a, C b) { return {a.r * b.r - a.i * b.i, a.r * b.i + a.i * b.r}; }
-__device__ __forceinline__ C cadd(C a, C b) { return {a.r + b.r, a.i + b.i}; }
-__device__ __forceinline__ C csub(C a, C b) { return {a.r - b.r, a.i - b.i}; }
-__device__ __forceinline__ C conj(C a) { return {a.r, -a.i}; }
-__device__ __forceinline__ C cscale(C a, double s) { return {a.r * s, a.i * s}; }
-// complex division as libgcc's __divdc3 performs it for finite, well-scaled operands (Smith's algorithm)
-__device__ __forceinline__ C cdiv(C x, C y) {
-    double ratio, denom;
-    C out;
-    if (fabs(y.r) < fabs(y.i)) {
-        ratio = y.r / y.i;
-        denom = (y.r * ratio) + y.i;
-        out.r = ((x.r * ratio) + x.i) / denom;
-        out.i = ((x.i * ratio) - x.r) / denom;
-    } else {
-        ratio = y.i / y.r;
-        denom = (y.i * ratio) + y.r;
-        out.r = ((x.i * ratio) + x.r) / denom;
-        out.i = (x.i - (x.r * ratio)) / denom;
-    }
-    return out;
-}
-__device__ __forceinline__ C ldc(double const* p, int64_t k) { return {__ldg(p + 2 * k), __ldg(p + 2 * k + 1)}; }
-
-template <int T> struct UView {
-    double const* u;
-    int n_bus;
-    __device__ __forceinline__ C get(int64_t scn, int bus) const {
-        int64_t const tile = scn / T;
-        int const lane = scn % T;
-        double const* p = u + ((tile * n_bus + bus) * 2) * T + lane;
-        return {p[0], p[T]};
-    }
-};
-
-template <int T> __device__ __forceinline__ C bus_injection(DevStructure const& s, UView<T> const& uv, int64_t scn, int bus) {
-    C i_inj{0.0, 0.0};
-    for (int k = __ldg(s.y_row_ptr + bus), ke = __ldg(s.y_row_ptr + bus + 1); k < ke; ++k) {
-        i_inj = cadd(i_inj, cmul(ldc(s.ydata, k), uv.get(scn, __ldg(s.y_col_idx + k))));
-    }
-    return cmul(conj(i_inj), uv.get(scn, bus));
-}
-
-template <int T>
-__device__ __forceinline__ C load_gen_s(DevStructure const& s, double const* sinj, int64_t scn, int lg, C u, int type) {
-    int64_t const tile = scn / T;
-    int const lane = scn % T;
-    double const* p = sinj + ((tile * s.n_load_gen + lg) * 2) * T + lane;
-    C const sv{p[0], p[T]};
-    if (type == 0) return sv;
-    if (type == 1) return cscale(sv, u.r * u.r + u.i * u.i);
-    return cscale(sv, sqrt(u.r * u.r + u.i * u.i));
-}
 
 template <int T>
 __global__ void math_result_sym_kernel(DevStructure s, DevBatch b, int force_const_y, double* out_u, double* out_inj,
@@ -134,35 +76,8 @@ __global__ void math_result_sym_kernel(DevStructure s, DevBatch b, int force_con
     }
     r -= s.n_load_gen;
     if (out_source == nullptr) return;
-    // source r
-    int const bus = __ldg(s.src_bus + r);
-    C const u = uv.get(scn, bus);
-    C i_lg{0.0, 0.0};
-    for (int lg = __ldg(s.lg_ptr + bus), lge = __ldg(s.lg_ptr + bus + 1); lg < lge; ++lg) {
-        C const sv = load_gen_s<T>(s, b.sinj, scn, lg, u, force_const_y ? 1 : __ldg(s.lg_type + lg));
-        i_lg = cadd(i_lg, conj(cdiv(sv, u)));
-    }
-    C const i_inj_t = csub(conj(cdiv(bus_injection<T>(s, uv, scn, bus), u)), i_lg);
-    int const sb = __ldg(s.src_ptr + bus), se = __ldg(s.src_ptr + bus + 1);
-    C i_src;
-    if (se - sb == 1) {
-        i_src = i_inj_t;
-    } else {
-        int64_t const tile = scn / T;
-        int const lane = scn % T;
-        C y_ref_t{0.0, 0.0}, i_ref_t{0.0, 0.0};
-        for (int k = sb; k < se; ++k) y_ref_t = cadd(y_ref_t, ldc(s.src_y1y0, 2 * k));
-        C const z_ref_t = cdiv(C{1.0, 0.0}, y_ref_t);
-        for (int k = sb; k < se; ++k) {
-            double const* p = b.usrc + ((tile * s.n_source + k) * 2) * T + lane;
-            i_ref_t = cadd(i_ref_t, cmul(C{p[0], p[T]}, ldc(s.src_y1y0, 2 * k)));
-        }
-        double const* p = b.usrc + ((tile * s.n_source + r) * 2) * T + lane;
-        C const ratio = cmul(ldc(s.src_y1y0, 2 * r), z_ref_t);
-        C const lhs = cmul(ratio, csub(cmul(C{p[0], p[T]}, y_ref_t), i_ref_t));
-        i_src = cadd(lhs, cmul(ratio, i_inj_t));
-    }
-    C const sv = cmul(u, conj(i_src));
+    C sv, i_src;
+    source_result<T>(s, b, uv, scn, (int)r, force_const_y, sv, i_src);
     double* o = out_source + (scn * s.n_source + r) * 4;
     o[0] = sv.r, o[1] = sv.i, o[2] = i_src.r, o[3] = i_src.i;
 }

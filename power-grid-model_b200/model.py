@@ -81,7 +81,7 @@ class PowerGridModel:
     # -- calculation ------------------------------------------------------------------------------------------------
     def calculate_power_flow(self, *, symmetric=True, error_tolerance=1e-8, max_iterations=20,
                              calculation_method="newton_raphson", update_data=None, threading=-1,
-                             output_component_types=None, continue_on_batch_error=False, device=0):
+                             output_component_types=None, continue_on_batch_error=False, device=0, output_buffers=None):
         """Same contract as the reference: without ``update_data`` a single calculation returning 1-D arrays, with it a
         batch returning (n_scenarios, n_elements) arrays.  ``threading`` is accepted for signature compatibility; the
         scenario loop runs on the GPU."""
@@ -103,7 +103,11 @@ class PowerGridModel:
         out = _lib.OutputDataC()
         result = {}
         for c in comps:
-            arr = np.zeros((n_scn, self._counts[c]), dtype=table[c])
+            if output_buffers is not None and c in output_buffers:  # caller-owned (e.g. pinned) buffers, like the C API
+                arr = output_buffers[c]
+                assert arr.dtype == table[c] and arr.shape == (n_scn, self._counts[c]) and arr.flags.c_contiguous
+            else:
+                arr = np.empty((n_scn, self._counts[c]), dtype=table[c])
             result[c] = arr
             if arr.size:
                 setattr(out, c, arr.ctypes.data)
