@@ -209,7 +209,7 @@ void Engine::allocate_batch(int64_t n) {
     db_.lg_status = d_lg_status_.get();
     db_.phase_cycles = nullptr;
     if (env_int("PGMB_DEBUG_PHASES", 0) != 0) {
-        d_phase_.ensure(static_cast<size_t>(n_tile) * 8);
+        d_phase_.ensure(static_cast<size_t>(n_tile) * 16);
         db_.phase_cycles = d_phase_.get();
     }
 }
@@ -264,7 +264,7 @@ float Engine::solve_staged(SolveOptions const& opt_in) {
     if (all_const_y) opt.method = 0;
     if (opt.method == -128) opt.method = 1;
     last_method_ = opt.method;
-    if (db_.phase_cycles != nullptr) PGMB_CUDA(cudaMemsetAsync(db_.phase_cycles, 0, sizeof(unsigned long long) * db_.n_tile * 8, stream_));
+    if (db_.phase_cycles != nullptr) PGMB_CUDA(cudaMemsetAsync(db_.phase_cycles, 0, sizeof(unsigned long long) * db_.n_tile * 16, stream_));
     PGMB_CUDA(cudaEventRecord(ev0_, stream_));
     switch (opt.method) {
     case 1:
@@ -283,11 +283,13 @@ float Engine::solve_staged(SolveOptions const& opt_in) {
     float ms = 0.0f;
     PGMB_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
     if (db_.phase_cycles != nullptr) {
-        std::vector<unsigned long long> h(static_cast<size_t>(db_.n_tile) * 8);
+        std::vector<unsigned long long> h(static_cast<size_t>(db_.n_tile) * 16);
         PGMB_CUDA(cudaMemcpy(h.data(), db_.phase_cycles, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-        double avg[8] = {};
+        double avg[16] = {};
         for (int t = 0; t != db_.n_tile; ++t)
-            for (int k = 0; k != 8; ++k) avg[k] += static_cast<double>(h[t * 8 + k]) / db_.n_tile;
+            for (int k = 0; k != 16; ++k) avg[k] += static_cast<double>(h[t * 16 + k]) / db_.n_tile;
+        std::fprintf(stderr, "[pgmb row profile, kcycles/tile, thread 0 tree rows of narrow levels] pass1 %.0f diag+upper %.0f loads/src %.0f pass2 %.0f factor %.0f finish %.0f\n",
+                     avg[8] / 1e3, avg[9] / 1e3, avg[10] / 1e3, avg[11] / 1e3, avg[12] / 1e3, avg[13] / 1e3);
         std::fprintf(stderr, "[pgmb phases, kcycles/tile] init: up0 %.0f up_rest %.0f down_rest %.0f down0 %.0f | iter: up0 %.0f up_rest %.0f down_rest %.0f down0 %.0f\n",
                      avg[0] / 1e3, avg[1] / 1e3, avg[2] / 1e3, avg[3] / 1e3, avg[4] / 1e3, avg[5] / 1e3, avg[6] / 1e3, avg[7] / 1e3);
     }

@@ -91,7 +91,7 @@ template <int T> __global__ void nr_sym_kernel(DevStructure s, DevBatch b, Solve
     {
         bool singular = false;
         double dev = 0.0;
-        sweeps<T, Mode::linear_init>(s, t, slot, n_slot, !done, singular, dev, b.phase_cycles ? b.phase_cycles + tile * 8 : nullptr);
+        sweeps<T, Mode::linear_init>(s, t, slot, n_slot, !done, singular, dev, b.phase_cycles ? b.phase_cycles + tile * 16 : nullptr);
         if (singular) sh_singular[lane] = 1;
         __syncthreads();
         if (!done && sh_singular[lane]) {
@@ -112,7 +112,7 @@ template <int T> __global__ void nr_sym_kernel(DevStructure s, DevBatch b, Solve
         if (!__syncthreads_or(!done)) break;
         bool singular = false;
         double dev = 0.0;
-        sweeps<T, Mode::newton>(s, t, slot, n_slot, !done, singular, dev, b.phase_cycles ? b.phase_cycles + tile * 8 + 4 : nullptr);
+        sweeps<T, Mode::newton>(s, t, slot, n_slot, !done, singular, dev, b.phase_cycles ? b.phase_cycles + tile * 16 + 4 : nullptr);
         if (!done) {
             if (singular) sh_singular[lane] = 1;
             atomicMax(&sh_dev[lane], (unsigned long long)__double_as_longlong(dev)); // dev >= 0: order-preserving

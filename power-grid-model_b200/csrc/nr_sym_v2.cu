@@ -378,7 +378,7 @@ template <int T> __global__ void nr_sym_v2_kernel(DevStructure s, DevBatch b, So
     int status = kStatusOk;
     int num_iter = 0;
     double max_dev = INFINITY;
-    unsigned long long* const phase = b.phase_cycles ? b.phase_cycles + tile * 8 : nullptr;
+    unsigned long long* const phase = b.phase_cycles ? b.phase_cycles + tile * 16 : nullptr;
     {
         bool singular = false;
         double dev = 0.0;
