@@ -4,3 +4,4 @@ from ._lib import BatchError, PgmB200Error, lib  # noqa: F401
 from .engine import Engine  # noqa: F401
 from .fictional_grid import BENCHMARK_OPTION, FictionalGrid  # noqa: F401
 from .model import PowerGridModel  # noqa: F401
+from . import distributed  # noqa: F401,E402

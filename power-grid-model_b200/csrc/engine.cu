@@ -1,5 +1,6 @@
 #include "engine.hpp"
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -152,6 +153,7 @@ void Engine::set_param(double const* branch_param, double const* shunt_param, do
     ds_.src_y1y0 = d_src_y1y0_.get();
     ds_.branch_param = d_branch_param_.get();
     ds_.shunt_param = d_shunt_param_.get();
+    ic_factor_valid_ = false; // parameters_changed (iterative_current_pf_solver.hpp:162)
     param_set_ = true;
 }
 
@@ -274,8 +276,27 @@ float Engine::solve_staged(SolveOptions const& opt_in) {
             launch_nr_sym_v2(tile_width_, ds_, db_, opt, n_slot_, stream_);
         }
         break;
+    case 0:
+        launch_linear_sym(tile_width_, ds_, db_, n_slot_, stream_);
+        break;
+    case 3:
+    case 4: {
+        if (!ic_factor_valid_) {
+            d_ic_factor_.ensure(static_cast<size_t>(pattern_.nnz_lu) * 2);
+            d_ic_flag_.ensure(1);
+            launch_ic_factor(ds_, d_ic_factor_.get(), reinterpret_cast<int*>(d_ic_flag_.get()), stream_);
+            ic_factor_valid_ = true;
+        }
+        SolveOptions ic = opt;
+        if (opt.method == 4) { // linear_current = one iteration, no tolerance (math_solver.hpp:151-156)
+            ic.err_tol = INFINITY;
+            ic.max_iter = 1;
+        }
+        launch_ic_iterate_sym(tile_width_, ds_, db_, ic, d_ic_factor_.get(), reinterpret_cast<int const*>(d_ic_flag_.get()), n_slot_, stream_);
+        break;
+    }
     default:
-        throw InvalidArgument("calculation method " + std::to_string(opt.method) + " is not implemented on the GPU yet");
+        throw InvalidArgument("calculation method " + std::to_string(opt.method) + " is not a power-flow method");
     }
     PGMB_CUDA(cudaGetLastError());
     PGMB_CUDA(cudaEventRecord(ev1_, stream_));

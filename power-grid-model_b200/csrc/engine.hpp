@@ -146,6 +146,9 @@ class Engine {
     DevBuf<uint8_t> d_perm_, d_lg_status_;
     DevBuf<int32_t> d_status_, d_n_iter_;
     DevBuf<unsigned long long> d_phase_;
+    DevBuf<double> d_ic_factor_; // shared iterative-current factor [nnz_lu][2]
+    DevBuf<int32_t> d_ic_flag_;
+    bool ic_factor_valid_{false};
     DevBatch db_{};
     int last_method_{1};
 
@@ -168,6 +171,10 @@ void launch_pack_branch_sym(int tw, DevStructure const& s, DevBatch const& b, De
                             void* out, cudaStream_t st);
 void launch_pack_appliance_sym(int tw, DevStructure const& s, DevBatch const& b, DevModelTables const& m, int force_const_y,
                                int first, int count, double const* src_res, void* out, cudaStream_t st);
+void launch_linear_sym(int tw, DevStructure const& s, DevBatch const& b, int n_slot, cudaStream_t st);
+void launch_ic_factor(DevStructure const& s, double* factor, int* flag, cudaStream_t st);
+void launch_ic_iterate_sym(int tw, DevStructure const& s, DevBatch const& b, SolveOptions const& opt, double const* factor,
+                           int const* flag, int n_slot, cudaStream_t st);
 void launch_to_tile(int tile_width, double const* src, double* dst, int64_t n_scn, int n_item, int n_comp, int shared_src,
                     cudaStream_t st);
 void launch_from_tile(int tile_width, double const* src, double* dst, int64_t n_scn, int n_item, int n_comp,

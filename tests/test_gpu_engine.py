@@ -109,3 +109,48 @@ def test_staged_solve_is_idempotent_and_timed():
     b = eng.fetch()
     assert ms1 > 0 and ms2 > 0
     assert np.array_equal(a["u"], b["u"]) and np.array_equal(a["n_iter"], b["n_iter"])
+
+
+@pytest.mark.parametrize("method", ["iterative_current", "linear", "linear_current"])
+def test_three_bus_other_methods(method):
+    grid, expected = three_bus_grid(True)
+    eng = pgm_b200.Engine.from_grid(grid)
+    out = eng.run(grid.s_injection[None], grid.source_u_ref, method=method, err_tol=1e-12, max_iter=100)
+    ref = orc.math_pf(grid, method, 1e-12, 100)
+    assert out["status"][0] == 0 and ref["status"] == 0
+    assert out["n_iter"][0] == ref["num_iter"]
+    for key in KEYS:
+        assert np.max(np.abs(out[key][0] - ref[key])) < 1e-12, key
+        if method == "iterative_current":
+            assert np.max(np.abs(out[key][0] - expected[key])) < 1e-11, key
+
+
+def test_three_bus_const_z_is_forced_linear():
+    grid, expected = three_bus_grid(True, const_z=True)
+    grid.load_gen_type[:] = 1
+    eng = pgm_b200.Engine.from_grid(grid)
+    out = eng.run(grid.s_injection[None], grid.source_u_ref, method="newton_raphson")
+    for key in KEYS:
+        assert np.max(np.abs(out[key][0] - expected[key])) < 1e-8, key
+
+
+@pytest.mark.parametrize("method", ["iterative_current", "linear", "linear_current"])
+@pytest.mark.parametrize("n_node,extra,seed,n_scn", [(250, 0, 2, 37), (300, 45, 4, 70)])
+def test_random_grids_other_methods(method, n_node, extra, seed, n_scn):
+    grid = random_grid(n_node, extra, seed, n_source=2 if seed % 2 == 0 else 1)
+    s, u_ref = random_scenarios(grid, n_scn, seed)
+    eng = pgm_b200.Engine.from_grid(grid)
+    out = eng.run(s, u_ref, method=method, max_iter=100)
+    compare(out, oracle_batch(grid, s, u_ref, method=method, max_iter=100))
+    assert (out["status"] == 0).all()
+
+
+@pytest.mark.parametrize("method", ["iterative_current", "linear"])
+def test_singular_and_diverge_other_methods(method):
+    grid, _ = three_bus_grid(True, singular=True)
+    out = pgm_b200.Engine.from_grid(grid).run(grid.s_injection[None], grid.source_u_ref, method=method, err_tol=1e-12)
+    assert out["status"][0] == 2
+    if method == "iterative_current":
+        grid, _ = three_bus_grid(True, diverge=True)
+        out = pgm_b200.Engine.from_grid(grid).run(grid.s_injection[None], grid.source_u_ref, method=method, err_tol=1e-12, max_iter=20)
+        assert out["status"][0] == 1 and out["n_iter"][0] == 20

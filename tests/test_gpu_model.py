@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 CASES = vc.load_cases()
 # methods / symmetries the GPU engine implements so far
-GPU_METHODS = {"newton_raphson"}
+GPU_METHODS = {"newton_raphson", "iterative_current", "linear", "linear_current"}
 GPU_SYM = {True}
 RUNS = [(n, s, m, b) for n, c in sorted(CASES.items()) for s, m, b in vc.case_runs(c) if m in GPU_METHODS and s in GPU_SYM]
 
@@ -28,8 +28,6 @@ def _is_forced_linear(case):
 @pytest.mark.parametrize("name,sym,method,is_batch", RUNS, ids=[f"{n}-{'sym' if s else 'asym'}-{m}-{'batch' if b else 'single'}" for n, s, m, b in RUNS])
 def test_reference_validation_case(name, sym, method, is_batch):
     case = CASES[name]
-    if _is_forced_linear(case):
-        pytest.skip("forced linear method (all const_y loads): not on the GPU yet")
     params = case["params"]
     model = pgm_b200.PowerGridModel(vc.to_numpy(case["input"], "input"))
     kind = "sym_output" if sym else "asym_output"
