@@ -170,7 +170,8 @@ void Engine::choose_tiling(int64_t n_scn) {
     }
     tile_width_ = env_int("PGMB_TILE", t);
     if (tile_width_ != 4 && tile_width_ != 8 && tile_width_ != 16 && tile_width_ != 32) tile_width_ = t;
-    n_slot_ = env_int("PGMB_SLOTS", 512 / tile_width_);
+    // generic-block kernel (asymmetric): a thread holds several 6 x 6 blocks, fewer threads per block keep them in L1
+    n_slot_ = env_int("PGMB_SLOTS", (symmetric_ ? 512 : 128) / tile_width_);
     if (n_slot_ < 1) n_slot_ = 1;
     if (n_slot_ * tile_width_ > 1024) n_slot_ = 1024 / tile_width_;
 }
@@ -178,7 +179,6 @@ void Engine::choose_tiling(int64_t n_scn) {
 void Engine::allocate_batch(int64_t n) {
     if (device_ < 0) throw CudaError("engine was created without a CUDA device (symbolic only): pgm_b200 has no CPU fallback");
     if (!param_set_) throw InvalidArgument("pgmb_engine_set_param must be called before running");
-    if (!symmetric_) throw InvalidArgument("asymmetric calculation is not implemented on the GPU yet");
     PGMB_CUDA(cudaSetDevice(device_));
     choose_tiling(n);
     int const T = tile_width_;
@@ -189,7 +189,7 @@ void Engine::allocate_batch(int64_t n) {
     d_xvec_.ensure(n_tile * nb * N * T);
     d_pol_.ensure(n_tile * nb * N * T);
     d_u_.ensure(n_tile * nb * N * T);
-    d_perm_.ensure(n_tile * nb * T * (B_ == 1 ? 1 : 2 * N));
+    d_perm_.ensure(n_tile * nb * T * 2 * N);
     d_sinj_.ensure(static_cast<size_t>(n_tile) * topo_.n_load_gen() * 2 * B_ * T + 1);
     d_lg_status_.ensure(static_cast<size_t>(n_tile) * topo_.n_load_gen() * T + 1);
     d_usrc_.ensure(static_cast<size_t>(n_tile) * topo_.n_source() * 2 * T + 1);
@@ -268,9 +268,15 @@ float Engine::solve_staged(SolveOptions const& opt_in) {
     last_method_ = opt.method;
     if (db_.phase_cycles != nullptr) PGMB_CUDA(cudaMemsetAsync(db_.phase_cycles, 0, sizeof(unsigned long long) * db_.n_tile * 16, stream_));
     PGMB_CUDA(cudaEventRecord(ev0_, stream_));
+    if (!symmetric_ && opt.method != 1) {
+        throw InvalidArgument("asymmetric calculation on the GPU supports newton_raphson only (method " + std::to_string(opt.method) +
+                              " requested" + (all_const_y ? ", forced to linear because all loads are const_y" : "") + ")");
+    }
     switch (opt.method) {
     case 1:
-        if (env_int("PGMB_KERNEL", 2) == 1) {
+        if (!symmetric_ || env_int("PGMB_KERNEL", 2) == 0) {
+            launch_nr_block(B_, tile_width_, ds_, db_, opt, n_slot_, stream_);
+        } else if (env_int("PGMB_KERNEL", 2) == 1) {
             launch_nr_sym(tile_width_, ds_, db_, opt, n_slot_, stream_);
         } else {
             launch_nr_sym_v2(tile_width_, ds_, db_, opt, n_slot_, stream_);
@@ -334,7 +340,11 @@ void Engine::fetch(SolverOutputView const& out) {
     double* const dsrc = want(out.source, d_out_source_, topo_.n_source() * 2 * c2);
     double* const dsh = want(out.shunt, d_out_shunt_, topo_.n_shunt() * 2 * c2);
     double* const dlg = want(out.load_gen, d_out_lg_, topo_.n_load_gen() * 2 * c2);
-    launch_math_result_sym(tile_width_, ds_, db_, last_method_ == 0 ? 1 : 0, du, di, dbr, dsrc, dsh, dlg, stream_);
+    if (symmetric_) {
+        launch_math_result_sym(tile_width_, ds_, db_, last_method_ == 0 ? 1 : 0, du, di, dbr, dsrc, dsh, dlg, stream_);
+    } else {
+        launch_math_result_asym(tile_width_, ds_, db_, last_method_ == 0 ? 1 : 0, du, di, dbr, dsrc, dsh, dlg, stream_);
+    }
     PGMB_CUDA(cudaGetLastError());
     auto back = [&](void* host, void const* dev, size_t bytes) {
         if (host != nullptr && bytes != 0) PGMB_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, stream_));

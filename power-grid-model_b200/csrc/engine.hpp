@@ -171,6 +171,11 @@ void launch_pack_branch_sym(int tw, DevStructure const& s, DevBatch const& b, De
                             void* out, cudaStream_t st);
 void launch_pack_appliance_sym(int tw, DevStructure const& s, DevBatch const& b, DevModelTables const& m, int force_const_y,
                                int first, int count, double const* src_res, void* out, cudaStream_t st);
+void launch_nr_block(int phases, int tile_width, DevStructure const& s, DevBatch const& b, SolveOptions const& opt, int n_slot,
+                     cudaStream_t st);
+void launch_math_result_asym(int tile_width, DevStructure const& s, DevBatch const& b, int force_const_y, double* out_u,
+                             double* out_inj, double* out_branch, double* out_source, double* out_shunt, double* out_lg,
+                             cudaStream_t st);
 void launch_linear_sym(int tw, DevStructure const& s, DevBatch const& b, int n_slot, cudaStream_t st);
 void launch_ic_factor(DevStructure const& s, double* factor, int* flag, cudaStream_t st);
 void launch_ic_iterate_sym(int tw, DevStructure const& s, DevBatch const& b, SolveOptions const& opt, double const* factor,

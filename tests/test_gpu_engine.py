@@ -45,6 +45,36 @@ def test_three_bus_known_answer():
     assert out["n_iter"][0] == ref["num_iter"]
 
 
+def test_three_bus_asymmetric_known_answer():
+    """reference test_math_solver_pf_nr 'Test asymmetric' closed form, three-phase 6 x 6 block kernel"""
+    grid, expected = three_bus_grid(False)
+    eng = pgm_b200.Engine.from_grid(grid)
+    s = np.repeat(grid.s_injection[None], 9, axis=0)
+    out = eng.run(s, grid.source_u_ref, err_tol=1e-12, max_iter=20)
+    ref = orc.math_pf(grid, "newton_raphson", 1e-12, 20)
+    assert (out["status"] == 0).all() and (out["n_iter"] == ref["num_iter"]).all()
+    for key in KEYS:
+        for k in (0, 8):
+            assert np.max(np.abs(out[key][k] - expected[key])) < 1e-12, key
+            assert np.max(np.abs(out[key][k] - ref[key])) < 1e-13, key
+    grid, _ = three_bus_grid(False, diverge=True)
+    out = pgm_b200.Engine.from_grid(grid).run(grid.s_injection[None], grid.source_u_ref, err_tol=1e-12, max_iter=20)
+    assert out["status"][0] == 1 and out["n_iter"][0] == 20
+    grid, _ = three_bus_grid(False, singular=True)
+    out = pgm_b200.Engine.from_grid(grid).run(grid.s_injection[None], grid.source_u_ref, err_tol=1e-12, max_iter=20)
+    assert out["status"][0] == 2
+
+
+def test_generic_block_kernel_equals_symmetric_kernel(monkeypatch):
+    """the generic (2B x 2B) kernel instantiated for B = 1 must reproduce the specialised symmetric kernel bit for bit"""
+    grid = random_grid(120, 15, 9, n_source=2)
+    s, u_ref = random_scenarios(grid, 21, 9)
+    a = pgm_b200.Engine.from_grid(grid).run(s, u_ref)
+    monkeypatch.setenv("PGMB_KERNEL", "0")
+    b = pgm_b200.Engine.from_grid(grid).run(s, u_ref)
+    assert np.array_equal(a["n_iter"], b["n_iter"]) and np.array_equal(a["u"], b["u"])
+
+
 def test_three_bus_diverge_and_singular_status():
     grid, _ = three_bus_grid(True, diverge=True)
     eng = pgm_b200.Engine.from_grid(grid)
