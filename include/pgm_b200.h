@@ -194,8 +194,9 @@ PGMB_API int64_t pgmb_model_n_math_groups(pgmb_model* model);
  * source_u_ref [n_scenarios][n_source] complex; caller-allocated. Only valid for batches that change loads / sources. */
 PGMB_API int pgmb_model_batch_pf_input(pgmb_model* model, const pgmb_update_data* update, int32_t symmetric,
                                        int64_t math_group, double* s_injection, double* source_u_ref);
-/* timing of the last calculate call, milliseconds: [0] host prepare, [1] H2D, [2] solve kernels (CUDA events),
- * [3] output kernels, [4] D2H, [5] total wall */
+/* timing of the last calculate call, milliseconds: [0] host prepare (tables, source references), [1] host time to
+ * enqueue the chunk pipeline (H2D, kernels, D2H of every chunk), [2] solver kernels (CUDA events, summed over the chunks,
+ * which overlap), [3] unused on the pipelined path, [4] wait for the pipeline to drain + status read-back, [5] total wall */
 PGMB_API int pgmb_model_last_timing(pgmb_model* model, double* ms6);
 
 /* ------------------------------------------------------------------------------------------------------------

@@ -256,54 +256,90 @@ void Engine::fetch_status(int32_t* status, int32_t* n_iter) {
     PGMB_CUDA(cudaStreamSynchronize(stream_));
 }
 
-float Engine::solve_staged(SolveOptions const& opt_in) {
+DevBatch Engine::batch_view(int64_t tile_begin, int64_t tile_end) const {
+    DevBatch v = db_;
+    int64_t const T = tile_width_;
+    int64_t const N = 2 * B_;
+    size_t const nb = static_cast<size_t>(topo_.n_bus);
+    int64_t const scn_begin = tile_begin * T;
+    v.n_tile = static_cast<int32_t>(tile_end - tile_begin);
+    v.n_scn = std::min<int64_t>(db_.n_scn, tile_end * T) - scn_begin;
+    // per-tile strides are those of allocate_batch(); a kernel that uses a smaller stride stays inside its view's range
+    v.jac += static_cast<size_t>(tile_begin) * pattern_.nnz_lu * N * N * T;
+    v.xvec += tile_begin * nb * N * T;
+    v.pol += tile_begin * nb * N * T;
+    v.u += tile_begin * nb * N * T;
+    v.perm += tile_begin * nb * T * 2 * N;
+    v.sinj += static_cast<size_t>(tile_begin) * topo_.n_load_gen() * 2 * B_ * T;
+    v.lg_status += static_cast<size_t>(tile_begin) * topo_.n_load_gen() * T;
+    v.usrc += static_cast<size_t>(tile_begin) * topo_.n_source() * 2 * T;
+    v.status += scn_begin;
+    v.n_iter += scn_begin;
+    v.max_dev += scn_begin;
+    if (v.phase_cycles != nullptr) v.phase_cycles += tile_begin * 16;
+    return v;
+}
+
+SolveOptions Engine::prepare_solve(SolveOptions const& opt_in) {
     if (device_ < 0) throw CudaError("engine was created without a CUDA device (symbolic only)");
     PGMB_CUDA(cudaSetDevice(device_));
-    if (db_.n_scn == 0) return 0.0f;
     SolveOptions opt = opt_in;
     // all loads const_y => the reference forces the linear method (math_solver.hpp:36-37, 48)
     bool const all_const_y = std::all_of(topo_.load_gen_type.begin(), topo_.load_gen_type.end(), [](int8_t t) { return t == 1; });
     if (all_const_y) opt.method = 0;
     if (opt.method == -128) opt.method = 1;
-    last_method_ = opt.method;
-    if (db_.phase_cycles != nullptr) PGMB_CUDA(cudaMemsetAsync(db_.phase_cycles, 0, sizeof(unsigned long long) * db_.n_tile * 16, stream_));
-    PGMB_CUDA(cudaEventRecord(ev0_, stream_));
+    if (opt.method != 0 && opt.method != 1 && opt.method != 3 && opt.method != 4) {
+        throw InvalidArgument("calculation method " + std::to_string(opt.method) + " is not a power-flow method");
+    }
     if (!symmetric_ && opt.method != 1) {
         throw InvalidArgument("asymmetric calculation on the GPU supports newton_raphson only (method " + std::to_string(opt.method) +
                               " requested" + (all_const_y ? ", forced to linear because all loads are const_y" : "") + ")");
     }
+    last_method_ = opt.method;
+    if ((opt.method == 3 || opt.method == 4) && !ic_factor_valid_) {
+        d_ic_factor_.ensure(static_cast<size_t>(pattern_.nnz_lu) * 2);
+        d_ic_flag_.ensure(1);
+        launch_ic_factor(ds_, d_ic_factor_.get(), reinterpret_cast<int*>(d_ic_flag_.get()), stream_);
+        PGMB_CUDA(cudaGetLastError());
+        ic_factor_valid_ = true;
+    }
+    if (opt.method == 4) { // linear_current = one iteration, no tolerance (math_solver.hpp:151-156)
+        opt.err_tol = INFINITY;
+        opt.max_iter = 1;
+    }
+    return opt;
+}
+
+void Engine::launch_solve(DevBatch const& b, SolveOptions const& opt, cudaStream_t st) {
+    if (b.n_scn == 0) return;
     switch (opt.method) {
     case 1:
         if (!symmetric_ || env_int("PGMB_KERNEL", 2) == 0) {
-            launch_nr_block(B_, tile_width_, ds_, db_, opt, n_slot_, stream_);
+            launch_nr_block(B_, tile_width_, ds_, b, opt, n_slot_, st);
         } else if (env_int("PGMB_KERNEL", 2) == 1) {
-            launch_nr_sym(tile_width_, ds_, db_, opt, n_slot_, stream_);
+            launch_nr_sym(tile_width_, ds_, b, opt, n_slot_, st);
         } else {
-            launch_nr_sym_v2(tile_width_, ds_, db_, opt, n_slot_, stream_);
+            launch_nr_sym_v2(tile_width_, ds_, b, opt, n_slot_, st);
         }
         break;
     case 0:
-        launch_linear_sym(tile_width_, ds_, db_, n_slot_, stream_);
+        launch_linear_sym(tile_width_, ds_, b, n_slot_, st);
         break;
-    case 3:
-    case 4: {
-        if (!ic_factor_valid_) {
-            d_ic_factor_.ensure(static_cast<size_t>(pattern_.nnz_lu) * 2);
-            d_ic_flag_.ensure(1);
-            launch_ic_factor(ds_, d_ic_factor_.get(), reinterpret_cast<int*>(d_ic_flag_.get()), stream_);
-            ic_factor_valid_ = true;
-        }
-        SolveOptions ic = opt;
-        if (opt.method == 4) { // linear_current = one iteration, no tolerance (math_solver.hpp:151-156)
-            ic.err_tol = INFINITY;
-            ic.max_iter = 1;
-        }
-        launch_ic_iterate_sym(tile_width_, ds_, db_, ic, d_ic_factor_.get(), reinterpret_cast<int const*>(d_ic_flag_.get()), n_slot_, stream_);
-        break;
-    }
     default:
-        throw InvalidArgument("calculation method " + std::to_string(opt.method) + " is not a power-flow method");
+        launch_ic_iterate_sym(tile_width_, ds_, b, opt, d_ic_factor_.get(), reinterpret_cast<int const*>(d_ic_flag_.get()), n_slot_, st);
+        break;
     }
+    PGMB_CUDA(cudaGetLastError());
+}
+
+float Engine::solve_staged(SolveOptions const& opt_in) {
+    if (device_ < 0) throw CudaError("engine was created without a CUDA device (symbolic only)");
+    PGMB_CUDA(cudaSetDevice(device_));
+    if (db_.n_scn == 0) return 0.0f;
+    SolveOptions const opt = prepare_solve(opt_in);
+    if (db_.phase_cycles != nullptr) PGMB_CUDA(cudaMemsetAsync(db_.phase_cycles, 0, sizeof(unsigned long long) * db_.n_tile * 16, stream_));
+    PGMB_CUDA(cudaEventRecord(ev0_, stream_));
+    launch_solve(db_, opt, stream_);
     PGMB_CUDA(cudaGetLastError());
     PGMB_CUDA(cudaEventRecord(ev1_, stream_));
     PGMB_CUDA(cudaEventSynchronize(ev1_));

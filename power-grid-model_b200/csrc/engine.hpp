@@ -101,6 +101,12 @@ class Engine {
     void apply_load_updates(DevModelTables const& m, DevUpdateBuffers const& ub);
     void fetch_status(int32_t* status, int32_t* n_iter);
     float solve_staged(SolveOptions const& opt);            // kernels only; returns solver-kernel milliseconds
+    // pipelined use (model device path): a view of the staged batch restricted to tiles [tile_begin, tile_end), and the solver
+    // launch on a caller-chosen stream without synchronisation.  prepare_solve() resolves the method and builds what all
+    // chunks share (the iterative-current factor) on the engine's own stream.
+    DevBatch batch_view(int64_t tile_begin, int64_t tile_end) const;
+    SolveOptions prepare_solve(SolveOptions const& opt);
+    void launch_solve(DevBatch const& view, SolveOptions const& resolved, cudaStream_t st);
     void fetch(SolverOutputView const& out);                // result extraction + D2H
     int run(SolveOptions const& opt, PfInputView const& in, SolverOutputView const& out); // returns #failed
 

@@ -91,6 +91,7 @@ struct DevModelTables {
     int8_t const* lg_phases;      // 1 (sym component) or 3 (asym component)
     int8_t const* lg_upd_buf;     // update buffer 0..3 (sym_gen, asym_gen, sym_load, asym_load) or -1 = never updated
     int32_t const* lg_upd_pos;    // element position inside one scenario of that buffer
+    int32_t const* lg_upd_id;     // raw id found at that position in scenario 0 (every scenario must repeat it)
     double const* lg_base_s;      // [n_lg][3][2] per-unit specified power of the permanent state
     uint8_t const* lg_base_status;
     double const* lg_scale;       // direction / base_power of the component
@@ -99,7 +100,7 @@ struct DevModelTables {
 struct DevUpdateBuffers {
     void const* data[4];          // device copies of the scenario-major update rows
     int64_t n_per_scenario[4];
-    int64_t first_scenario;       // scenario offset of this chunk inside the caller's buffers
+    int32_t* id_mismatch;         // set to 1 when a scenario's row carries another id than scenario 0 (dependent batch)
 };
 
 struct SolveOptions {

@@ -6,6 +6,8 @@
 // restore loop of the reference (job_dispatch.hpp:88-138, job_adapter.hpp:127-139).
 #include "model.hpp"
 
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace pgmb {
@@ -30,6 +32,7 @@ struct Model::DeviceSide {
     DevBuf<double> node_u_rated, branch_base_i, branch_rating, app_base_i, app_dir, lg_base_s, lg_scale;
     DevBuf<uint8_t> branch_energized, app_status, lg_base_status;
     DevBuf<int8_t> app_kind, lg_phases, lg_upd_buf;
+    DevBuf<int32_t> lg_upd_id;
     DevModelTables t{};
     Idx n_app_first[6]{}; // first appliance index of shunt, source, sym_gen, asym_gen, sym_load, asym_load
     // per-batch buffers
@@ -40,8 +43,27 @@ struct Model::DeviceSide {
     // pinned staging for pageable caller buffers
     unsigned char* pinned{nullptr};
     size_t pinned_size{0};
+    // chunk pipeline: one stream per chunk in flight, fork event on the engine stream, solve brackets per chunk
+    static constexpr int kMaxChunk = 8;
+    cudaStream_t cs[kMaxChunk]{};
+    cudaEvent_t fork{}, ev_a[kMaxChunk]{}, ev_b[kMaxChunk]{};
+    bool streams_ready{false};
+    void ensure_streams() {
+        if (streams_ready) return;
+        for (auto& q : cs) PGMB_CUDA(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
+        PGMB_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+        for (auto& ev : ev_a) PGMB_CUDA(cudaEventCreate(&ev));
+        for (auto& ev : ev_b) PGMB_CUDA(cudaEventCreate(&ev));
+        streams_ready = true;
+    }
     ~DeviceSide() {
         if (pinned != nullptr) cudaFreeHost(pinned);
+        if (streams_ready) {
+            for (auto& q : cs) cudaStreamDestroy(q);
+            cudaEventDestroy(fork);
+            for (auto& ev : ev_a) cudaEventDestroy(ev);
+            for (auto& ev : ev_b) cudaEventDestroy(ev);
+        }
     }
     unsigned char* staging(size_t bytes) {
         if (bytes > pinned_size) {
@@ -151,7 +173,7 @@ int64_t Model::run_batch_device(ModelOptions const& opt, UpdateData const& updat
         }
         // load update mapping from the ids of scenario 0 (an independent batch repeats them in every scenario)
         std::vector<int8_t> lg_phases(n_lg_math, 1), lg_buf(n_lg_math, -1);
-        std::vector<int32_t> lg_pos(n_lg_math, 0);
+        std::vector<int32_t> lg_pos(n_lg_math, 0), lg_id(n_lg_math, 0);
         std::vector<double> lg_base(n_lg_math * 6, 0.0), lg_scale(n_lg_math, 0.0);
         std::vector<uint8_t> lg_st(n_lg_math, 0);
         for (size_t i = 0; i != lg_.size(); ++i) {
@@ -192,6 +214,7 @@ int64_t Model::run_batch_device(ModelOptions const& opt, UpdateData const& updat
                 if (c.group != 0) continue;
                 lg_buf[c.pos] = static_cast<int8_t>(bfr);
                 lg_pos[c.pos] = static_cast<int32_t>(kpos);
+                lg_id[c.pos] = id;
             }
         }
         d.node_id.upload(node_id, st);
@@ -213,6 +236,7 @@ int64_t Model::run_batch_device(ModelOptions const& opt, UpdateData const& updat
         d.lg_phases.upload(lg_phases, st);
         d.lg_upd_buf.upload(lg_buf, st);
         d.lg_upd_pos.upload(lg_pos, st);
+        d.lg_upd_id.upload(lg_id, st);
         d.lg_base_s.upload(lg_base, st);
         d.lg_base_status.upload(lg_st, st);
         d.lg_scale.upload(lg_scale, st);
@@ -221,27 +245,10 @@ int64_t Model::run_batch_device(ModelOptions const& opt, UpdateData const& updat
                              d.node_id.get(), d.node_u_rated.get(), d.node_bus.get(), d.node_app_ptr.get(), d.node_app.get(),
                              d.branch_id.get(), d.branch_math.get(), d.branch_base_i.get(), d.branch_rating.get(),
                              d.branch_energized.get(), d.app_id.get(), d.app_math.get(), d.app_kind.get(), d.app_base_i.get(),
-                             d.app_dir.get(), d.app_status.get(), d.lg_phases.get(), d.lg_upd_buf.get(), d.lg_upd_pos.get(),
+                             d.app_dir.get(), d.app_status.get(), d.lg_phases.get(), d.lg_upd_buf.get(), d.lg_upd_pos.get(), d.lg_upd_id.get(),
                              d.lg_base_s.get(), d.lg_base_status.get(), d.lg_scale.get()};
     }
 
-    // ---- ids must repeat in every scenario (independent batch, main_core/update.hpp:58-83) ----
-    {
-        ComponentBuffer const* bufs[4] = {&update.sym_gen, &update.asym_gen, &update.sym_load, &update.asym_load};
-        size_t const row_size[4] = {sizeof(SymLoadGenUpdate), sizeof(AsymLoadGenUpdate), sizeof(SymLoadGenUpdate), sizeof(AsymLoadGenUpdate)};
-        for (int bfr = 0; bfr != 4; ++bfr) {
-            if (bufs[bfr]->data == nullptr) continue;
-            auto const* base = static_cast<unsigned char const*>(bufs[bfr]->data);
-            Idx const n = bufs[bfr]->n;
-            size_t const rs = row_size[bfr];
-            for (Idx s = 1; s < n_scn; ++s) {
-                unsigned char const* row = base + s * n * rs;
-                for (Idx kpos = 0; kpos != n; ++kpos) {
-                    if (std::memcmp(row + kpos * rs, base + kpos * rs, sizeof(ID)) != 0) return -1;
-                }
-            }
-        }
-    }
     // per-scenario source references (u_ref / u_ref_angle updates are allowed on this path)
     std::vector<double> uref;
     bool uref_shared = true;
@@ -278,37 +285,27 @@ int64_t Model::run_batch_device(ModelOptions const& opt, UpdateData const& updat
     }
     timing[0] += ms_since(t0);
 
-    // ---- H2D: raw update rows ----
+    // ---- chunk pipeline: H2D of the raw update rows -> apply -> solve -> output structs -> D2H, one stream per chunk, so the
+    //      PCIe transfers of one chunk overlap the kernels of the others (both copy engines + the SMs busy at once) ----
     t0 = Clock::now();
     e.stage_device(n_scn, uref.data(), uref_shared);
-    DevUpdateBuffers ub{};
-    {
-        ComponentBuffer const* bufs[4] = {&update.sym_gen, &update.asym_gen, &update.sym_load, &update.asym_load};
-        size_t const row_size[4] = {sizeof(SymLoadGenUpdate), sizeof(AsymLoadGenUpdate), sizeof(SymLoadGenUpdate), sizeof(AsymLoadGenUpdate)};
-        for (int bfr = 0; bfr != 4; ++bfr) {
-            if (bufs[bfr]->data == nullptr || bufs[bfr]->n == 0) continue;
-            size_t const bytes = static_cast<size_t>(n_scn) * bufs[bfr]->n * row_size[bfr];
-            d.upd[bfr].ensure(bytes);
-            PGMB_CUDA(cudaMemcpyAsync(d.upd[bfr].get(), bufs[bfr]->data, bytes, cudaMemcpyHostToDevice, st));
-            ub.data[bfr] = d.upd[bfr].get();
-            ub.n_per_scenario[bfr] = bufs[bfr]->n;
-        }
-    }
-    e.apply_load_updates(d.t, ub);
-    PGMB_CUDA(cudaStreamSynchronize(st));
-    timing[1] += ms_since(t0);
-
-    // ---- solve ----
-    timing[2] += e.solve_staged({opt.method, opt.err_tol, static_cast<int32_t>(opt.max_iter)});
-
-    // ---- output structs on the device, then one DMA per requested component ----
-    t0 = Clock::now();
+    SolveOptions const sopt = e.prepare_solve({opt.method, opt.err_tol, static_cast<int32_t>(opt.max_iter)});
+    d.ensure_streams();
+    d.flag.ensure(1);
+    PGMB_CUDA(cudaMemsetAsync(d.flag.get(), 0, sizeof(int32_t), st));
     int const tw = e.tile_width();
     DevStructure const& ds = e.dev_structure();
-    DevBatch const& db = e.dev_batch();
     int const force_const_y = e.last_method() == 0 ? 1 : 0;
-    d.src_res.ensure(static_cast<size_t>(n_scn) * m.n_source() * 4 + 1);
-    launch_source_result_sym(tw, ds, db, force_const_y, d.src_res.get(), st);
+    int64_t const n_tile = e.dev_batch().n_tile;
+    int n_chunk = static_cast<int>(std::min<int64_t>(DeviceSide::kMaxChunk, std::max<int64_t>(1, n_tile / 16)));
+    if (char const* env = std::getenv("PGMB_CHUNKS")) n_chunk = std::max(1, std::min<int>(DeviceSide::kMaxChunk, std::atoi(env)));
+    n_chunk = static_cast<int>(std::min<int64_t>(n_chunk, n_tile));
+
+    ComponentBuffer const* ubufs[4] = {&update.sym_gen, &update.asym_gen, &update.sym_load, &update.asym_load};
+    size_t const urow[4] = {sizeof(SymLoadGenUpdate), sizeof(AsymLoadGenUpdate), sizeof(SymLoadGenUpdate), sizeof(AsymLoadGenUpdate)};
+    for (int bfr = 0; bfr != 4; ++bfr) {
+        if (ubufs[bfr]->data != nullptr && ubufs[bfr]->n != 0) d.upd[bfr].ensure(static_cast<size_t>(n_scn) * ubufs[bfr]->n * urow[bfr]);
+    }
     struct Req {
         void* host;
         int slot;
@@ -327,32 +324,71 @@ int64_t Model::run_batch_device(ModelOptions const& opt, UpdateData const& updat
         {out.asym_load, 8, sizeof(ApplianceOutput<1>), n_asym_load_},
     };
     for (Req const& r : reqs) {
-        if (r.host == nullptr || r.count == 0) continue;
-        d.out[r.slot].ensure(static_cast<size_t>(n_scn) * r.count * r.row);
-        void* dst = d.out[r.slot].get();
-        switch (r.slot) {
-        case 0: launch_pack_node_sym(tw, ds, db, d.t, force_const_y, d.src_res.get(), dst, st); break;
-        case 1: launch_pack_branch_sym(tw, ds, db, d.t, 0, static_cast<int>(n_line()), dst, st); break;
-        case 2: launch_pack_branch_sym(tw, ds, db, d.t, static_cast<int>(n_line()), static_cast<int>(n_trafo()), dst, st); break;
-        default:
-            launch_pack_appliance_sym(tw, ds, db, d.t, force_const_y, static_cast<int>(d.n_app_first[r.slot - 3]),
-                                      static_cast<int>(r.count), d.src_res.get(), dst, st);
+        if (r.host != nullptr && r.count != 0) d.out[r.slot].ensure(static_cast<size_t>(n_scn) * r.count * r.row);
+    }
+    d.src_res.ensure(static_cast<size_t>(n_scn) * m.n_source() * 4 + 1);
+    PGMB_CUDA(cudaEventRecord(d.fork, st));
+
+    for (int c = 0; c != n_chunk; ++c) {
+        cudaStream_t const q = d.cs[c];
+        int64_t const tile_b = n_tile * c / n_chunk, tile_e = n_tile * (c + 1) / n_chunk;
+        DevBatch const view = e.batch_view(tile_b, tile_e);
+        int64_t const s0 = tile_b * tw, ns = view.n_scn;
+        PGMB_CUDA(cudaStreamWaitEvent(q, d.fork, 0));
+        DevUpdateBuffers ub{};
+        ub.id_mismatch = d.flag.get();
+        for (int bfr = 0; bfr != 4; ++bfr) {
+            if (ubufs[bfr]->data == nullptr || ubufs[bfr]->n == 0) continue;
+            size_t const per = static_cast<size_t>(ubufs[bfr]->n) * urow[bfr];
+            PGMB_CUDA(cudaMemcpyAsync(d.upd[bfr].get() + s0 * per, static_cast<unsigned char const*>(ubufs[bfr]->data) + s0 * per,
+                                      ns * per, cudaMemcpyHostToDevice, q));
+            ub.data[bfr] = d.upd[bfr].get() + s0 * per;
+            ub.n_per_scenario[bfr] = ubufs[bfr]->n;
+        }
+        launch_apply_load_update_sym(tw, ds, view, d.t, ub, q);
+        PGMB_CUDA(cudaEventRecord(d.ev_a[c], q));
+        e.launch_solve(view, sopt, q);
+        PGMB_CUDA(cudaEventRecord(d.ev_b[c], q));
+        double* const src_res = d.src_res.get() + s0 * m.n_source() * 4;
+        launch_source_result_sym(tw, ds, view, force_const_y, src_res, q);
+        for (Req const& r : reqs) {
+            if (r.host == nullptr || r.count == 0) continue;
+            void* const dst = d.out[r.slot].get() + static_cast<size_t>(s0) * r.count * r.row;
+            switch (r.slot) {
+            case 0: launch_pack_node_sym(tw, ds, view, d.t, force_const_y, src_res, dst, q); break;
+            case 1: launch_pack_branch_sym(tw, ds, view, d.t, 0, static_cast<int>(n_line()), dst, q); break;
+            case 2: launch_pack_branch_sym(tw, ds, view, d.t, static_cast<int>(n_line()), static_cast<int>(n_trafo()), dst, q); break;
+            default:
+                launch_pack_appliance_sym(tw, ds, view, d.t, force_const_y, static_cast<int>(d.n_app_first[r.slot - 3]),
+                                          static_cast<int>(r.count), src_res, dst, q);
+            }
+        }
+        PGMB_CUDA(cudaGetLastError());
+        for (Req const& r : reqs) {
+            if (r.host == nullptr || r.count == 0) continue;
+            size_t const off = static_cast<size_t>(s0) * r.count * r.row;
+            PGMB_CUDA(cudaMemcpyAsync(static_cast<unsigned char*>(r.host) + off, d.out[r.slot].get() + off,
+                                      static_cast<size_t>(ns) * r.count * r.row, cudaMemcpyDeviceToHost, q));
         }
     }
-    PGMB_CUDA(cudaGetLastError());
-    PGMB_CUDA(cudaStreamSynchronize(st));
-    timing[3] += ms_since(t0);
+    timing[1] += ms_since(t0);
 
     t0 = Clock::now();
-    for (Req const& r : reqs) {
-        if (r.host == nullptr || r.count == 0) continue;
-        size_t const bytes = static_cast<size_t>(n_scn) * r.count * r.row;
-        PGMB_CUDA(cudaMemcpyAsync(r.host, d.out[r.slot].get(), bytes, cudaMemcpyDeviceToHost, st));
+    for (int c = 0; c != n_chunk; ++c) PGMB_CUDA(cudaStreamSynchronize(d.cs[c]));
+    for (int c = 0; c != n_chunk; ++c) {
+        float ms = 0.0f;
+        PGMB_CUDA(cudaEventElapsedTime(&ms, d.ev_a[c], d.ev_b[c]));
+        timing[2] += ms; // solver time per chunk; chunks overlap, so the sum can exceed the wall time
     }
+    int32_t mismatch = 0;
+    PGMB_CUDA(cudaMemcpyAsync(&mismatch, d.flag.get(), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     std::vector<int32_t> st_local(n_scn), it_local(n_scn);
     e.fetch_status(st_local.data(), it_local.data());
     PGMB_CUDA(cudaStreamSynchronize(st));
     timing[4] += ms_since(t0);
+    // ids must repeat in every scenario (independent batch, main_core/update.hpp:58-83); checked by the apply kernel on the
+    // rows it reads.  A dependent batch is recomputed by the caller on the per-scenario host path.
+    if (mismatch != 0) return -1;
 
     int64_t failed = 0;
     for (Idx s = 0; s != n_scn; ++s) {

@@ -53,12 +53,14 @@ __global__ void apply_load_update_sym_kernel(DevStructure s, DevBatch b, DevMode
             int64_t const row = (scn * ub.n_per_scenario[buf] + m.lg_upd_pos[lg]);
             if (phases == 1) {
                 SymLoadGenUpdateRow const u = static_cast<SymLoadGenUpdateRow const*>(ub.data[buf])[row];
+                if (u.id != m.lg_upd_id[lg]) *ub.id_mismatch = 1;
                 if (u.status != kNaIntS) status = u.status != 0;
                 if (!isnan(u.p_specified)) sr[0] = scale * u.p_specified;
                 if (!isnan(u.q_specified)) si[0] = scale * u.q_specified;
             } else {
                 AsymLoadGenUpdateRow const* u = static_cast<AsymLoadGenUpdateRow const*>(ub.data[buf]) + row;
                 int8_t const st = u->status;
+                if (u->id != m.lg_upd_id[lg]) *ub.id_mismatch = 1;
                 if (st != kNaIntS) status = st != 0;
                 for (int p = 0; p < 3; ++p) {
                     double const pp = u->p_specified[p], qq = u->q_specified[p];

@@ -128,10 +128,11 @@ class PowerGridModel:
         return result
 
     def timing(self):
-        """milliseconds of the last calculate: host prepare, H2D+stage, solve kernels, output, D2H+fetch, total"""
+        """milliseconds of the last calculate: host prepare, pipeline enqueue, solver kernels (sum over overlapping chunks),
+        unused, pipeline drain + status, total (include/pgm_b200.h: pgmb_model_last_timing)"""
         t = (C.c_double * 6)()
         check(lib().pgmb_model_last_timing(self._h, t))
-        return dict(zip(("prepare", "stage", "solve_kernel", "output", "fetch", "total"), list(t)))
+        return dict(zip(("prepare", "enqueue", "solve_kernel", "output", "drain", "total"), list(t)))
 
     def batch_pf_input(self, update_data, symmetric=True, group=0):
         """PowerFlowInput of every scenario for one math group: (s_injection (n_scn, n_load_gen, B), u_ref (n_scn, n_source))"""
