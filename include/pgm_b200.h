@@ -55,6 +55,8 @@ enum {
 PGMB_API const char* pgmb_last_error(void);
 PGMB_API int pgmb_device_count(void);
 PGMB_API const char* pgmb_version(void);
+/* number of CUDA kernels this library has launched since it was loaded (evidence that the GPU path ran) */
+PGMB_API uint64_t pgmb_kernel_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------------------
  * ENGINE level

@@ -38,6 +38,7 @@ def lib():
         l = C.CDLL(LIB_PATH)
         l.pgmb_last_error.restype = C.c_char_p
         l.pgmb_version.restype = C.c_char_p
+        l.pgmb_kernel_launch_count.restype = C.c_uint64
         l.pgmb_model_n_math_groups.restype = C.c_int64
         _lib = l
     return _lib

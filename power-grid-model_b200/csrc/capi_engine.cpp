@@ -48,6 +48,7 @@ extern "C" {
 
 const char* pgmb_last_error(void) { return g_last_error.c_str(); }
 const char* pgmb_version(void) { return "pgm_b200 0.1 (reference power-grid-model 1.13 semantics)"; }
+uint64_t pgmb_kernel_launch_count(void) { return pgmb::kernel_launch_count(); }
 int pgmb_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) {

@@ -283,6 +283,7 @@ __global__ void ic_iterate_sym_kernel(DevStructure s, DevBatch b, SolveOptions o
 } // namespace
 
 void launch_linear_sym(int tw, DevStructure const& s, DevBatch const& b, int n_slot, cudaStream_t st) {
+    count_kernel_launch();
     switch (tw) {
     case 4: linear_sym_kernel<4><<<b.n_tile, 4 * n_slot, 0, st>>>(s, b); break;
     case 8: linear_sym_kernel<8><<<b.n_tile, 8 * n_slot, 0, st>>>(s, b); break;
@@ -291,11 +292,13 @@ void launch_linear_sym(int tw, DevStructure const& s, DevBatch const& b, int n_s
     }
 }
 void launch_ic_factor(DevStructure const& s, double* factor, int* flag, cudaStream_t st) {
+    count_kernel_launch();
     cudaMemsetAsync(flag, 0, sizeof(int), st);
     ic_factor_kernel<<<1, 256, 0, st>>>(s, factor, flag);
 }
 void launch_ic_iterate_sym(int tw, DevStructure const& s, DevBatch const& b, SolveOptions const& opt, double const* factor,
                            int const* flag, int n_slot, cudaStream_t st) {
+    count_kernel_launch();
     switch (tw) {
     case 4: ic_iterate_sym_kernel<4><<<b.n_tile, 4 * n_slot, 0, st>>>(s, b, opt, factor, flag); break;
     case 8: ic_iterate_sym_kernel<8><<<b.n_tile, 8 * n_slot, 0, st>>>(s, b, opt, factor, flag); break;

@@ -1,5 +1,6 @@
 #include "engine.hpp"
 
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -13,11 +14,16 @@ template <class To, class From> std::vector<To> narrow_vec(std::vector<From> con
     for (size_t i = 0; i != v.size(); ++i) out[i] = static_cast<To>(v[i]);
     return out;
 }
+std::atomic<uint64_t> g_kernel_launches{0};
+
 int env_int(char const* name, int fallback) {
     char const* v = std::getenv(name);
     return (v != nullptr && *v != '\0') ? std::atoi(v) : fallback;
 }
 } // namespace
+
+void count_kernel_launch() { g_kernel_launches.fetch_add(1, std::memory_order_relaxed); }
+uint64_t kernel_launch_count() { return g_kernel_launches.load(std::memory_order_relaxed); }
 
 Engine::Engine(MathTopology topo, bool symmetric, int device)
     : topo_{std::move(topo)}, symmetric_{symmetric}, B_{symmetric ? 1 : 3}, device_{device}, pattern_{topo_}, schedule_{pattern_}, program_{pattern_, schedule_, topo_} {

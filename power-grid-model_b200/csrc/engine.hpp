@@ -163,6 +163,8 @@ class Engine {
     void allocate_batch(int64_t n_scn);
 };
 
+uint64_t kernel_launch_count(); // kernels launched by this library since it was loaded
+
 // kernel launchers (nr_sym.cu, result_sym.cu)
 void launch_nr_sym(int tile_width, DevStructure const& s, DevBatch const& b, SolveOptions const& opt, int n_slot,
                    cudaStream_t st);

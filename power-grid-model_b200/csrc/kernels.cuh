@@ -103,6 +103,9 @@ struct DevUpdateBuffers {
     int32_t* id_mismatch;         // set to 1 when a scenario's row carries another id than scenario 0 (dependent batch)
 };
 
+// every launcher reports here; pgmb_kernel_launch_count() exposes the total (bench.py: gpu_launches)
+void count_kernel_launch();
+
 struct SolveOptions {
     int32_t method;
     double err_tol;

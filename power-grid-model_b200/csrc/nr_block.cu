@@ -586,6 +586,7 @@ static void launch_nr_block_b(int tw, DevStructure const& s, DevBatch const& b, 
 
 void launch_nr_block(int phases, int tw, DevStructure const& s, DevBatch const& b, SolveOptions const& opt, int n_slot,
                      cudaStream_t st) {
+    count_kernel_launch();
     if (phases == 1) {
         launch_nr_block_b<1>(tw, s, b, opt, n_slot, st);
     } else {

@@ -179,6 +179,7 @@ static void launch_nr_sym_t(DevStructure const& s, DevBatch const& b, SolveOptio
 
 void launch_nr_sym(int tile_width, DevStructure const& s, DevBatch const& b, SolveOptions const& opt, int n_slot,
                    cudaStream_t st) {
+    count_kernel_launch();
     switch (tile_width) {
     case 4: launch_nr_sym_t<4>(s, b, opt, n_slot, st); break;
     case 8: launch_nr_sym_t<8>(s, b, opt, n_slot, st); break;
@@ -189,6 +190,7 @@ void launch_nr_sym(int tile_width, DevStructure const& s, DevBatch const& b, Sol
 
 void launch_to_tile(int tile_width, double const* src, double* dst, int64_t n_scn, int n_item, int n_comp, int shared_src,
                     cudaStream_t st) {
+    count_kernel_launch();
     int64_t const n_tile = (n_scn + tile_width - 1) / tile_width;
     int64_t const total = n_tile * n_item * n_comp * tile_width;
     if (total == 0) return;
@@ -204,6 +206,7 @@ void launch_to_tile(int tile_width, double const* src, double* dst, int64_t n_sc
 
 void launch_from_tile(int tile_width, double const* src, double* dst, int64_t n_scn, int n_item, int n_comp,
                       cudaStream_t st) {
+    count_kernel_launch();
     int64_t const total = n_scn * n_item * n_comp;
     if (total == 0) return;
     int const block = 256;

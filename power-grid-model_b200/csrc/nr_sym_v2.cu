@@ -441,6 +441,7 @@ static void launch_v2_t(DevStructure const& s, DevBatch const& b, SolveOptions c
 
 void launch_nr_sym_v2(int tile_width, DevStructure const& s, DevBatch const& b, SolveOptions const& opt, int n_slot,
                       cudaStream_t st) {
+    count_kernel_launch();
     switch (tile_width) {
     case 4: launch_v2_t<4>(s, b, opt, n_slot, st); break;
     case 8: launch_v2_t<8>(s, b, opt, n_slot, st); break;

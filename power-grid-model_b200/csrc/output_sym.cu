@@ -250,29 +250,34 @@ inline unsigned grid_for(int64_t total, int block) { return (unsigned)((total + 
 
 void launch_apply_load_update_sym(int tw, DevStructure const& s, DevBatch const& b, DevModelTables const& m,
                                   DevUpdateBuffers const& ub, cudaStream_t st) {
+    count_kernel_launch();
     int64_t const total = (int64_t)b.n_tile * s.n_load_gen * tw;
     if (total == 0) return;
     PGMB_DISPATCH_T(tw, apply_load_update_sym_kernel, grid_for(total, 256), 256, st, s, b, m, ub);
 }
 void launch_source_result_sym(int tw, DevStructure const& s, DevBatch const& b, int force_const_y, double* out, cudaStream_t st) {
+    count_kernel_launch();
     int64_t const total = b.n_scn * s.n_source;
     if (total == 0) return;
     PGMB_DISPATCH_T(tw, source_result_sym_kernel, grid_for(total, 128), 128, st, s, b, force_const_y, out);
 }
 void launch_pack_node_sym(int tw, DevStructure const& s, DevBatch const& b, DevModelTables const& m, int force_const_y,
                           double const* src_res, void* out, cudaStream_t st) {
+    count_kernel_launch();
     int64_t const total = b.n_scn * m.n_node;
     if (total == 0) return;
     PGMB_DISPATCH_T(tw, pack_node_sym_kernel, grid_for(total, 256), 256, st, s, b, m, force_const_y, src_res, static_cast<double*>(out));
 }
 void launch_pack_branch_sym(int tw, DevStructure const& s, DevBatch const& b, DevModelTables const& m, int first, int count,
                             void* out, cudaStream_t st) {
+    count_kernel_launch();
     int64_t const total = b.n_scn * count;
     if (total == 0) return;
     PGMB_DISPATCH_T(tw, pack_branch_sym_kernel, grid_for(total, 256), 256, st, s, b, m, first, count, static_cast<double*>(out));
 }
 void launch_pack_appliance_sym(int tw, DevStructure const& s, DevBatch const& b, DevModelTables const& m, int force_const_y,
                                int first, int count, double const* src_res, void* out, cudaStream_t st) {
+    count_kernel_launch();
     int64_t const total = b.n_scn * count;
     if (total == 0) return;
     PGMB_DISPATCH_T(tw, pack_appliance_sym_kernel, grid_for(total, 256), 256, st, s, b, m, force_const_y, first, count, src_res,

@@ -210,6 +210,7 @@ __global__ void math_result_asym_kernel(DevStructure s, DevBatch b, int force_co
 void launch_math_result_asym(int tile_width, DevStructure const& s, DevBatch const& b, int force_const_y, double* out_u,
                              double* out_inj, double* out_branch, double* out_source, double* out_shunt, double* out_lg,
                              cudaStream_t st) {
+    count_kernel_launch();
     int64_t const per_scn = (int64_t)s.n_bus * 2 + s.n_branch + s.n_shunt + s.n_load_gen + s.n_source;
     int64_t const total = per_scn * b.n_scn;
     if (total == 0) return;
