@@ -251,7 +251,7 @@ def main():
                     "gpu_launches": e2e_launches},
             "gpu_launches": gpu_launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_kind": peak_kind, "kernel": "nr_sym_v2_kernel",
+                         "traffic": None, "peak_kind": peak_kind, "kernel": "nr_sym_v3_kernel (radial path kernel; nr_sym_v2_kernel for wide tiles / meshed grids)",
                          "algorithmic_bytes_per_launch": bytes_per_launch, "launch_ms": 1e3 * launch_s},
             "cpu_baseline": {"value": cpu_value, "unit": "scenarios/s", "cores": cores, "kind": "port",
                              "sample": f"{sample} of the {N_SCN} scenarios x {reps} repeats, all {cores} host threads (reference threading=0)"},

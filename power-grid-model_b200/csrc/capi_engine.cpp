@@ -96,6 +96,8 @@ int pgmb_engine_get_index(pgmb_engine* engine, const char* name, const int64_t**
             else if (key == "y_bus_entry_indptr") v = p.y_bus_entry_indptr;
             else if (key == "level_ptr") v = widen(s.level_ptr);
             else if (key == "level_rows") v = widen(s.level_rows);
+            else if (key == "row_program") v = widen(engine->engine->program().words);
+            else if (key == "path_program") v = widen(engine->engine->path_program().words); // empty: not a radial grid
             else throw InvalidArgument("unknown index array: " + key);
             it = engine->index_cache.emplace(key, std::move(v)).first;
         }

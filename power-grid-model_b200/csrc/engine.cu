@@ -26,7 +26,8 @@ void count_kernel_launch() { g_kernel_launches.fetch_add(1, std::memory_order_re
 uint64_t kernel_launch_count() { return g_kernel_launches.load(std::memory_order_relaxed); }
 
 Engine::Engine(MathTopology topo, bool symmetric, int device)
-    : topo_{std::move(topo)}, symmetric_{symmetric}, B_{symmetric ? 1 : 3}, device_{device}, pattern_{topo_}, schedule_{pattern_}, program_{pattern_, schedule_, topo_} {
+    : topo_{std::move(topo)}, symmetric_{symmetric}, B_{symmetric ? 1 : 3}, device_{device}, pattern_{topo_}, schedule_{pattern_}, program_{pattern_, schedule_, topo_},
+      path_program_{pattern_, schedule_, topo_, program_} {
     if (device < 0) return; // symbolic-only engine (structure introspection on hosts without a GPU); it cannot run
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
@@ -63,6 +64,7 @@ void Engine::upload_structure() {
     d_lg_ptr_.upload(narrow_vec<int32_t>(topo_.load_gens_per_bus), stream_);
     d_src_ptr_.upload(narrow_vec<int32_t>(topo_.sources_per_bus), stream_);
     d_prog_.upload(program_.words, stream_);
+    if (path_program_.valid) d_path_prog_.upload(path_program_.words, stream_);
     d_lg_type_.upload(topo_.load_gen_type, stream_);
     d_y_row_ptr_.upload(narrow_vec<int32_t>(pattern_.row_indptr), stream_);
     d_y_col_idx_.upload(narrow_vec<int32_t>(pattern_.col_indices), stream_);
@@ -108,6 +110,8 @@ void Engine::upload_structure() {
     ds_.phase_shift = d_phase_shift_.get();
     ds_.prog = d_prog_.get();
     ds_.prog_words = static_cast<int32_t>(program_.words.size());
+    ds_.path_prog = path_program_.valid ? d_path_prog_.get() : nullptr;
+    ds_.path_prog_words = path_program_.valid ? static_cast<int32_t>(path_program_.words.size()) : 0;
 }
 
 // YBus::update_admittance_entries (y_bus.hpp:400-431): sum of the contributions of each entry, in element order
@@ -195,6 +199,7 @@ void Engine::allocate_batch(int64_t n) {
     d_xvec_.ensure(n_tile * nb * N * T);
     d_pol_.ensure(n_tile * nb * N * T);
     d_u_.ensure(n_tile * nb * N * T);
+    if (symmetric_ && path_program_.valid) d_side_.ensure(n_tile * nb * N * T);
     d_perm_.ensure(n_tile * nb * T * 2 * N);
     d_sinj_.ensure(static_cast<size_t>(n_tile) * topo_.n_load_gen() * 2 * B_ * T + 1);
     d_lg_status_.ensure(static_cast<size_t>(n_tile) * topo_.n_load_gen() * T + 1);
@@ -208,6 +213,7 @@ void Engine::allocate_batch(int64_t n) {
     db_.xvec = d_xvec_.get();
     db_.pol = d_pol_.get();
     db_.u = d_u_.get();
+    db_.side = d_side_.get();
     db_.perm = d_perm_.get();
     db_.sinj = d_sinj_.get();
     db_.usrc = d_usrc_.get();
@@ -275,6 +281,7 @@ DevBatch Engine::batch_view(int64_t tile_begin, int64_t tile_end) const {
     v.xvec += tile_begin * nb * N * T;
     v.pol += tile_begin * nb * N * T;
     v.u += tile_begin * nb * N * T;
+    if (v.side != nullptr) v.side += tile_begin * nb * N * T;
     v.perm += tile_begin * nb * T * 2 * N;
     v.sinj += static_cast<size_t>(tile_begin) * topo_.n_load_gen() * 2 * B_ * T;
     v.lg_status += static_cast<size_t>(tile_begin) * topo_.n_load_gen() * T;
@@ -320,10 +327,14 @@ void Engine::launch_solve(DevBatch const& b, SolveOptions const& opt, cudaStream
     if (b.n_scn == 0) return;
     switch (opt.method) {
     case 1:
-        if (!symmetric_ || env_int("PGMB_KERNEL", 2) == 0) {
+        if (!symmetric_ || env_int("PGMB_KERNEL", 3) == 0) {
             launch_nr_block(B_, tile_width_, ds_, b, opt, n_slot_, st);
-        } else if (env_int("PGMB_KERNEL", 2) == 1) {
+        } else if (env_int("PGMB_KERNEL", 3) == 1) {
             launch_nr_sym(tile_width_, ds_, b, opt, n_slot_, st);
+        } else if (path_program_.valid && (env_int("PGMB_KERNEL", 0) == 3 || (env_int("PGMB_KERNEL", 3) == 3 && tile_width_ <= 8))) {
+            // radial grid, few scenarios per SM: the path kernel shortens the dependent chain (measured: 1000 scenarios
+            // 2.09 ms vs 2.39 ms); with wide tiles the level kernel has less work per row and wins (8000: 10.7 vs 11.5 ms)
+            launch_nr_sym_v3(tile_width_, ds_, b, opt, n_slot_, st);
         } else {
             launch_nr_sym_v2(tile_width_, ds_, b, opt, n_slot_, st);
         }
@@ -357,10 +368,11 @@ float Engine::solve_staged(SolveOptions const& opt_in) {
         double avg[16] = {};
         for (int t = 0; t != db_.n_tile; ++t)
             for (int k = 0; k != 16; ++k) avg[k] += static_cast<double>(h[t * 16 + k]) / db_.n_tile;
-        std::fprintf(stderr, "[pgmb row profile, kcycles/tile, thread 0 tree rows of narrow levels] pass1 %.0f diag+upper %.0f loads/src %.0f pass2 %.0f factor %.0f finish %.0f\n",
-                     avg[8] / 1e3, avg[9] / 1e3, avg[10] / 1e3, avg[11] / 1e3, avg[12] / 1e3, avg[13] / 1e3);
-        std::fprintf(stderr, "[pgmb phases, kcycles/tile] init: up0 %.0f up_rest %.0f down_rest %.0f down0 %.0f | iter: up0 %.0f up_rest %.0f down_rest %.0f down0 %.0f\n",
-                     avg[0] / 1e3, avg[1] / 1e3, avg[2] / 1e3, avg[3] / 1e3, avg[4] / 1e3, avg[5] / 1e3, avg[6] / 1e3, avg[7] / 1e3);
+        // level kernels (v1 / v2): init up0 up_rest down_rest down0 ... | newton (+4); path kernel (v3): init leaf-build
+        // inner-build up-chains down-chains down-leaves ... | newton (+8)
+        std::fprintf(stderr, "[pgmb phases, kcycles/tile]");
+        for (int k = 0; k != 16; ++k) std::fprintf(stderr, " %s%.0f", k == 8 ? "| " : "", avg[k] / 1e3);
+        std::fprintf(stderr, "\n");
     }
     return ms;
 }

@@ -114,6 +114,7 @@ class Engine {
     LuPattern const& pattern() const { return pattern_; }
     EliminationSchedule const& schedule() const { return schedule_; }
     RowProgram const& program() const { return program_; }
+    PathProgram const& path_program() const { return path_program_; }
     std::vector<double> const& admittance() const { return admittance_; } // [nnz][B][B] complex
     int device() const { return device_; }
     int phases() const { return B_; }
@@ -131,6 +132,7 @@ class Engine {
     LuPattern pattern_;
     EliminationSchedule schedule_;
     RowProgram program_;
+    PathProgram path_program_;
     std::vector<double> admittance_;
     std::vector<double> branch_param_, shunt_param_, source_param_;
     bool param_set_{false};
@@ -139,7 +141,7 @@ class Engine {
 
     // device structure
     DevBuf<int32_t> d_row_ptr_, d_col_idx_, d_diag_, d_map_y_, d_level_ptr_, d_level_rows_, d_upd_ptr_, d_upd_u_, d_upd_a_,
-        d_lg_ptr_, d_src_ptr_, d_prog_, d_y_row_ptr_, d_y_col_idx_, d_branch_bus_, d_shunt_bus_, d_lg_bus_, d_src_bus_;
+        d_lg_ptr_, d_src_ptr_, d_prog_, d_path_prog_, d_y_row_ptr_, d_y_col_idx_, d_branch_bus_, d_shunt_bus_, d_lg_bus_, d_src_bus_;
     DevBuf<int8_t> d_lg_type_;
     DevBuf<double> d_ydata_, d_src_yref_, d_src_y1y0_, d_branch_param_, d_shunt_param_, d_phase_shift_;
     DevStructure ds_{};
@@ -147,6 +149,7 @@ class Engine {
     // batch buffers
     int tile_width_{8};
     int n_slot_{64};
+    DevBuf<double> d_side_;
     DevBuf<double> d_jac_, d_xvec_, d_pol_, d_u_, d_sinj_, d_usrc_, d_max_dev_, d_in_sinj_, d_in_usrc_;
     DevBuf<double> d_out_u_, d_out_inj_, d_out_branch_, d_out_source_, d_out_shunt_, d_out_lg_;
     DevBuf<uint8_t> d_perm_, d_lg_status_;
@@ -169,6 +172,8 @@ uint64_t kernel_launch_count(); // kernels launched by this library since it was
 void launch_nr_sym(int tile_width, DevStructure const& s, DevBatch const& b, SolveOptions const& opt, int n_slot,
                    cudaStream_t st);
 void launch_nr_sym_v2(int tile_width, DevStructure const& s, DevBatch const& b, SolveOptions const& opt, int n_slot,
+                      cudaStream_t st);
+void launch_nr_sym_v3(int tile_width, DevStructure const& s, DevBatch const& b, SolveOptions const& opt, int n_slot,
                       cudaStream_t st);
 void launch_apply_load_update_sym(int tw, DevStructure const& s, DevBatch const& b, DevModelTables const& m,
                                   DevUpdateBuffers const& ub, cudaStream_t st);

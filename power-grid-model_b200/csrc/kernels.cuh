@@ -45,6 +45,9 @@ struct DevStructure {
     // row programs (symbolic.hpp RowProgram): level_ptr | task_off | records
     int32_t const* prog;
     int32_t prog_words;
+    // path programs (symbolic.hpp PathProgram) for radial grids; null when the grid has a cyclic core
+    int32_t const* path_prog;
+    int32_t path_prog_words;
 };
 
 // per-batch device buffers, tile layout (see above); B = phases, N = 2B
@@ -61,6 +64,7 @@ struct DevBatch {
     int32_t* status; // [n_scn]
     int32_t* n_iter; // [n_scn]
     double* max_dev; // [n_scn]
+    double* side;    // [tile][n_bus][2][T]      precomputed leaf update terms of the path kernel (nr_sym_v3.cu)
     uint8_t* lg_status; // [tile][n_load_gen][T] per-scenario status of each load_gen (device update path), may be null
     unsigned long long* phase_cycles; // optional [n_tile][8] clock64 totals per phase (PGMB_DEBUG_PHASES), may be null
 };

@@ -244,4 +244,196 @@ struct RowProgram {
     }
 };
 
+// Path programs (radial grids: every row is a tree row).  The elimination tree is cut into PATHS: maximal chains
+// child -> parent in which the parent continues the chain of exactly one non-leaf child (its "carry" child).  One thread
+// walks a whole path with the carried child's factor, U block, permutation and right-hand side in registers, so the
+// dependent chain of a feeder needs neither block barriers nor global round trips between consecutive rows.  Paths are
+// grouped in STAGES: a path may start once every other (non-carried) child of its rows is complete; leaves are stage 0.
+//   blob = header[8] | leaf records (8 words) | rec_off[n_rec] | stage_ptr[n_stage + 1] | paths (first_rec, n_rows) | records
+//   header (12 words): n_leaf, n_rec, n_stage, off_leaf, off_rec_off, off_stage_ptr, off_path, n_path, off_chain, 0, 0, 0
+//   chain record (8 words per non-leaf row, same index as rec_off): row, k_d, k_u, k_a (block towards the carry child or
+//                 -1), k_s (precomputed leaf term or -1), pattern, record offset, parent row
+//   pattern: 1 nothing left to eliminate in the chain, 2 carry child only, 3 carry child then the precomputed leaf term,
+//            0 anything else (generic loop over the row record)
+//   leaf record : row, k_d, ky_d, k_u, j, ky_u, lg0 | n_lg << 24, s0 | n_src << 24            (k_u = -1: no parent)
+//   row record  : same 8 words, then n_lower | carry_e << 12 | post_e << 20 (0xff = none), then per lower entry
+//                 c, ky, k_diag(c), k_U(c,row) | kind << 28
+//   kind: 0 leaf child eliminated when the row is built, 1 carry child (registers), 2 leaf child whose update term is
+//         precomputed when the row is built and subtracted in the chain (keeps the reference's order of subtractions),
+//         3 any other child: eliminated in the chain from global memory.
+// Records of a path are consecutive, bottom row first; stage s (>= 1) owns paths [stage_ptr[s-1], stage_ptr[s]).
+struct PathProgram {
+    std::vector<int32_t> words;
+    bool valid{false};
+    int32_t n_stage{};
+    int32_t n_path{};
+    int32_t max_path_rows{};
+
+    PathProgram(LuPattern const& p, EliminationSchedule const& sch, MathTopology const& topo, RowProgram const& rows) {
+        Idx const n = p.n_bus;
+        if (n == 0 || rows.n_tree_rows != n || p.nnz_lu >= (Idx{1} << 28)) return;
+        auto n_lower_of = [&](Idx r) { return p.diag_lu[r] - p.row_indptr_lu[r]; };
+        std::vector<int32_t> stage(n, 0), path_of(n, -1);
+        std::vector<std::vector<Idx>> paths;   // rows bottom-up
+        std::vector<int32_t> path_stage;
+        std::vector<Idx> carry(n, -1);
+        for (Idx r = 0; r != n; ++r) {
+            if (n_lower_of(r) == 0) continue;
+            Idx cc = -1;
+            for (Idx e = p.row_indptr_lu[r]; e != p.diag_lu[r]; ++e) {
+                Idx const c = p.col_indices_lu[e];
+                if (n_lower_of(c) == 0) continue;
+                if (cc < 0 || stage[c] > stage[cc] || (stage[c] == stage[cc] && sch.row_level[c] > sch.row_level[cc])) cc = c;
+            }
+            int32_t s_side = 1;
+            for (Idx e = p.row_indptr_lu[r]; e != p.diag_lu[r]; ++e) {
+                Idx const c = p.col_indices_lu[e];
+                if (n_lower_of(c) == 0 || c == cc) continue;
+                s_side = std::max(s_side, stage[c] + 1);
+            }
+            Idx const carry_e = cc < 0 ? -1 : (std::lower_bound(p.col_indices_lu.begin() + p.row_indptr_lu[r],
+                                                                 p.col_indices_lu.begin() + p.diag_lu[r], cc) -
+                                               (p.col_indices_lu.begin() + p.row_indptr_lu[r]));
+            if (cc >= 0 && s_side <= stage[cc] && carry_e < 255) {
+                stage[r] = stage[cc];
+                carry[r] = cc;
+                path_of[r] = path_of[cc];
+                paths[path_of[r]].push_back(r);
+            } else {
+                stage[r] = cc >= 0 ? std::max(s_side, stage[cc] + 1) : s_side;
+                path_of[r] = static_cast<int32_t>(paths.size());
+                paths.push_back({r});
+                path_stage.push_back(stage[r]);
+            }
+        }
+        n_stage = 1;
+        for (int32_t s : path_stage) n_stage = std::max(n_stage, s + 1);
+        n_path = static_cast<int32_t>(paths.size());
+        // order paths by stage, longest first inside a stage (the longest chains start first on the slots)
+        std::vector<int32_t> order(paths.size());
+        for (size_t i = 0; i != order.size(); ++i) order[i] = static_cast<int32_t>(i);
+        std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+            if (path_stage[a] != path_stage[b]) return path_stage[a] < path_stage[b];
+            return paths[a].size() > paths[b].size();
+        });
+        std::vector<Idx> leaves;
+        for (Idx r = 0; r != n; ++r)
+            if (n_lower_of(r) == 0) leaves.push_back(r);
+        Idx const n_rec = n - static_cast<Idx>(leaves.size());
+
+        auto head = [&](Idx row) {
+            Idx const dg = p.diag_lu[row], re = p.row_indptr_lu[row + 1];
+            Idx const lg0 = topo.load_gens_per_bus[row], n_lg = topo.load_gens_per_bus[row + 1] - lg0;
+            Idx const s0 = topo.sources_per_bus[row], n_src = topo.sources_per_bus[row + 1] - s0;
+            bool const has_u = re - dg - 1 == 1;
+            words.push_back(static_cast<int32_t>(row));
+            words.push_back(static_cast<int32_t>(dg));
+            words.push_back(static_cast<int32_t>(p.map_lu_y_bus[dg]));
+            words.push_back(has_u ? static_cast<int32_t>(dg + 1) : -1);
+            words.push_back(has_u ? static_cast<int32_t>(p.col_indices_lu[dg + 1]) : -1);
+            words.push_back(has_u ? static_cast<int32_t>(p.map_lu_y_bus[dg + 1]) : -1);
+            words.push_back(static_cast<int32_t>(lg0 | (n_lg << 24)));
+            words.push_back(static_cast<int32_t>(s0 | (n_src << 24)));
+        };
+        words.assign(12, 0);
+        Idx const off_leaf = static_cast<Idx>(words.size());
+        for (Idx r : leaves) head(r);
+        Idx const off_rec_off = static_cast<Idx>(words.size());
+        words.resize(words.size() + n_rec, 0);
+        Idx const off_stage_ptr = static_cast<Idx>(words.size());
+        words.resize(words.size() + n_stage + 1, 0);
+        Idx const off_path = static_cast<Idx>(words.size());
+        words.resize(words.size() + 2 * paths.size(), 0);
+        while (words.size() % 4 != 0) words.push_back(0); // chain records are read as 16-byte vectors
+        Idx const off_chain = static_cast<Idx>(words.size());
+        words.resize(words.size() + 8 * n_rec, 0);
+        Idx rec_idx = 0;
+        for (size_t oi = 0; oi != order.size(); ++oi) {
+            auto const& rows_of_path = paths[order[oi]];
+            words[off_stage_ptr + path_stage[order[oi]]] += 1; // counts per stage (stage >= 1), prefix-summed below
+            words[off_path + 2 * oi] = static_cast<int32_t>(rec_idx);
+            words[off_path + 2 * oi + 1] = static_cast<int32_t>(rows_of_path.size());
+            max_path_rows = std::max<int32_t>(max_path_rows, static_cast<int32_t>(rows_of_path.size()));
+            for (Idx r : rows_of_path) {
+                Idx const this_rec = rec_idx;
+                words[off_rec_off + rec_idx++] = static_cast<int32_t>(words.size());
+                int32_t const this_off = static_cast<int32_t>(words.size());
+                head(r);
+                Idx const rb = p.row_indptr_lu[r], dg = p.diag_lu[r];
+                size_t const w_n = words.size();
+                words.push_back(0);
+                int32_t carry_e = 0xff, post_e = 0xff;
+                bool seen_nonleaf = false;
+                for (Idx e = rb; e != dg; ++e) {
+                    Idx const c = p.col_indices_lu[e];
+                    int32_t kind;
+                    if (n_lower_of(c) == 0) {
+                        if (!seen_nonleaf) {
+                            kind = 0;
+                        } else if (post_e == 0xff && e - rb < 255) {
+                            kind = 2;
+                            post_e = static_cast<int32_t>(e - rb);
+                        } else {
+                            kind = 3;
+                        }
+                    } else {
+                        seen_nonleaf = true;
+                        if (c == carry[r]) {
+                            kind = 1;
+                            carry_e = static_cast<int32_t>(e - rb);
+                        } else {
+                            kind = 3;
+                        }
+                    }
+                    words.push_back(static_cast<int32_t>(c));
+                    words.push_back(static_cast<int32_t>(p.map_lu_y_bus[e]));
+                    words.push_back(static_cast<int32_t>(p.diag_lu[c]));
+                    words.push_back(static_cast<int32_t>(sch.upd_u[sch.upd_ptr[e]] | (kind << 28)));
+                }
+                words[w_n] = static_cast<int32_t>((dg - rb) | (carry_e << 12) | (post_e << 20));
+                // chain record
+                std::vector<int32_t> seq; // kinds left for the chain, in entry order
+                for (Idx e = rb; e != dg; ++e) {
+                    int32_t const kind = (words[w_n + 1 + 4 * (e - rb) + 3] >> 28) & 3;
+                    if (kind != 0) seq.push_back(kind);
+                }
+                int32_t pattern = 0;
+                if (seq.empty()) pattern = 1;
+                else if (seq.size() == 1 && seq[0] == 1) pattern = 2;
+                else if (seq.size() == 2 && seq[0] == 1 && seq[1] == 2) pattern = 3;
+                Idx const re = p.row_indptr_lu[r + 1];
+                bool const has_u = re - dg - 1 == 1;
+                int32_t* cr = &words[off_chain + 8 * this_rec];
+                cr[0] = static_cast<int32_t>(r);
+                cr[1] = static_cast<int32_t>(dg);
+                cr[2] = has_u ? static_cast<int32_t>(dg + 1) : -1;
+                cr[3] = carry_e != 0xff ? static_cast<int32_t>(rb + carry_e) : -1;
+                cr[4] = post_e != 0xff ? static_cast<int32_t>(rb + post_e) : -1;
+                cr[5] = pattern;
+                cr[6] = this_off;
+                cr[7] = has_u ? static_cast<int32_t>(p.col_indices_lu[dg + 1]) : -1;
+            }
+        }
+        // stage_ptr: stage s (>= 1) owns paths [stage_ptr[s - 1], stage_ptr[s]) ; entry 0 counts nothing
+        {
+            int32_t run = 0;
+            for (int32_t s = 0; s <= n_stage; ++s) {
+                run += words[off_stage_ptr + s];
+                words[off_stage_ptr + s] = run;
+            }
+        }
+        words[0] = static_cast<int32_t>(leaves.size());
+        words[1] = static_cast<int32_t>(n_rec);
+        words[2] = n_stage;
+        words[3] = static_cast<int32_t>(off_leaf);
+        words[4] = static_cast<int32_t>(off_rec_off);
+        words[5] = static_cast<int32_t>(off_stage_ptr);
+        words[6] = static_cast<int32_t>(off_path);
+        words[7] = n_path;
+        words[8] = static_cast<int32_t>(off_chain);
+        while (words.size() % 4 != 0) words.push_back(0);
+        valid = true;
+    }
+};
+
 } // namespace pgmb

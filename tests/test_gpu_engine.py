@@ -75,6 +75,22 @@ def test_generic_block_kernel_equals_symmetric_kernel(monkeypatch):
     assert np.array_equal(a["n_iter"], b["n_iter"]) and np.array_equal(a["u"], b["u"])
 
 
+@pytest.mark.parametrize("n_node,seed,n_scn", [(60, 11, 9), (400, 12, 33), (1500, 13, 40)])
+def test_path_kernel_equals_level_kernel_on_radial_grids(monkeypatch, n_node, seed, n_scn):
+    """radial grids run the path kernel (nr_sym_v3.cu); it must reproduce the level-scheduled kernel bit for bit"""
+    grid = random_grid(n_node, 0, seed, n_source=1)
+    s, u_ref = random_scenarios(grid, n_scn, seed)
+    eng = pgm_b200.Engine.from_grid(grid)
+    assert eng.index("path_program").size > 0
+    a = eng.run(s, u_ref)
+    monkeypatch.setenv("PGMB_KERNEL", "2")
+    b = pgm_b200.Engine.from_grid(grid).run(s, u_ref)
+    assert np.array_equal(a["n_iter"], b["n_iter"]) and np.array_equal(a["status"], b["status"])
+    for key in KEYS:
+        assert np.array_equal(a[key], b[key]), key
+    compare(a, oracle_batch(grid, s, u_ref))
+
+
 def test_three_bus_diverge_and_singular_status():
     grid, _ = three_bus_grid(True, diverge=True)
     eng = pgm_b200.Engine.from_grid(grid)
