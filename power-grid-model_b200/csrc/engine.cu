@@ -304,15 +304,16 @@ SolveOptions Engine::prepare_solve(SolveOptions const& opt_in) {
     if (opt.method != 0 && opt.method != 1 && opt.method != 3 && opt.method != 4) {
         throw InvalidArgument("calculation method " + std::to_string(opt.method) + " is not a power-flow method");
     }
-    if (!symmetric_ && opt.method != 1) {
-        throw InvalidArgument("asymmetric calculation on the GPU supports newton_raphson only (method " + std::to_string(opt.method) +
-                              " requested" + (all_const_y ? ", forced to linear because all loads are const_y" : "") + ")");
-    }
     last_method_ = opt.method;
     if ((opt.method == 3 || opt.method == 4) && !ic_factor_valid_) {
-        d_ic_factor_.ensure(static_cast<size_t>(pattern_.nnz_lu) * 2);
+        d_ic_factor_.ensure(static_cast<size_t>(pattern_.nnz_lu) * 2 * B_ * B_);
         d_ic_flag_.ensure(1);
-        launch_ic_factor(ds_, d_ic_factor_.get(), reinterpret_cast<int*>(d_ic_flag_.get()), stream_);
+        if (symmetric_) {
+            launch_ic_factor(ds_, d_ic_factor_.get(), reinterpret_cast<int*>(d_ic_flag_.get()), stream_);
+        } else {
+            d_ic_perm_.ensure(static_cast<size_t>(topo_.n_bus) * 2 * B_ + 1);
+            launch_ic_factor_asym(ds_, d_ic_factor_.get(), d_ic_perm_.get(), reinterpret_cast<int*>(d_ic_flag_.get()), stream_);
+        }
         PGMB_CUDA(cudaGetLastError());
         ic_factor_valid_ = true;
     }
@@ -340,10 +341,19 @@ void Engine::launch_solve(DevBatch const& b, SolveOptions const& opt, cudaStream
         }
         break;
     case 0:
-        launch_linear_sym(tile_width_, ds_, b, n_slot_, st);
+        if (symmetric_) {
+            launch_linear_sym(tile_width_, ds_, b, n_slot_, st);
+        } else {
+            launch_linear_asym(tile_width_, ds_, b, n_slot_, st);
+        }
         break;
     default:
-        launch_ic_iterate_sym(tile_width_, ds_, b, opt, d_ic_factor_.get(), reinterpret_cast<int const*>(d_ic_flag_.get()), n_slot_, st);
+        if (symmetric_) {
+            launch_ic_iterate_sym(tile_width_, ds_, b, opt, d_ic_factor_.get(), reinterpret_cast<int const*>(d_ic_flag_.get()), n_slot_, st);
+        } else {
+            launch_ic_iterate_asym(tile_width_, ds_, b, opt, d_ic_factor_.get(), d_ic_perm_.get(),
+                                   reinterpret_cast<int const*>(d_ic_flag_.get()), n_slot_, st);
+        }
         break;
     }
     PGMB_CUDA(cudaGetLastError());

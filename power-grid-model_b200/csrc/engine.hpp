@@ -157,6 +157,7 @@ class Engine {
     DevBuf<unsigned long long> d_phase_;
     DevBuf<double> d_ic_factor_; // shared iterative-current factor [nnz_lu][2]
     DevBuf<int32_t> d_ic_flag_;
+    DevBuf<uint8_t> d_ic_perm_;  // block permutations of the shared factor (asymmetric)
     bool ic_factor_valid_{false};
     DevBatch db_{};
     int last_method_{1};
@@ -189,6 +190,10 @@ void launch_nr_block(int phases, int tile_width, DevStructure const& s, DevBatch
 void launch_math_result_asym(int tile_width, DevStructure const& s, DevBatch const& b, int force_const_y, double* out_u,
                              double* out_inj, double* out_branch, double* out_source, double* out_shunt, double* out_lg,
                              cudaStream_t st);
+void launch_linear_asym(int tw, DevStructure const& s, DevBatch const& b, int n_slot, cudaStream_t st);
+void launch_ic_factor_asym(DevStructure const& s, double* factor, uint8_t* perm, int* flag, cudaStream_t st);
+void launch_ic_iterate_asym(int tw, DevStructure const& s, DevBatch const& b, SolveOptions const& opt, double* factor,
+                            uint8_t* perm, int const* flag, int n_slot, cudaStream_t st);
 void launch_linear_sym(int tw, DevStructure const& s, DevBatch const& b, int n_slot, cudaStream_t st);
 void launch_ic_factor(DevStructure const& s, double* factor, int* flag, cudaStream_t st);
 void launch_ic_iterate_sym(int tw, DevStructure const& s, DevBatch const& b, SolveOptions const& opt, double const* factor,

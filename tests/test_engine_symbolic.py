@@ -70,3 +70,53 @@ def test_three_bus_structure():
     eng = pgm_b200.Engine.from_grid(grid, device=-1)
     assert eng.index("row_indptr_lu").tolist() == [0, 2, 5, 7]
     assert eng.index("level_ptr").tolist() == [0, 1, 2, 3]
+
+
+@pytest.mark.parametrize("n_node,seed", [(2, 1), (40, 2), (300, 3), (1500, 4)])
+def test_path_program_covers_a_radial_grid(n_node, seed):
+    """PathProgram (symbolic.hpp): every non-leaf row sits in exactly one path, a path is a child -> parent chain, and every
+    child that is not carried in registers belongs to an earlier stage (or is a leaf)."""
+    grid = random_grid(n_node, 0, seed)
+    eng = pgm_b200.Engine.from_grid(grid, device=-1)
+    w = eng.index("path_program")
+    assert w.size > 0
+    rp, ci, dg = eng.index("row_indptr_lu"), eng.index("col_indices_lu"), eng.index("diag_lu")
+    n = len(rp) - 1
+    n_leaf, n_rec, n_stage, off_leaf, off_ro, off_sp, off_path, n_path, off_chain = (int(x) for x in w[:9])
+    leaves = [int(w[off_leaf + 8 * i]) for i in range(n_leaf)]
+    assert sorted(leaves) == [r for r in range(n) if dg[r] == rp[r]]
+    sp = w[off_sp:off_sp + n_stage + 1]
+    assert sp[0] == 0 and sp[n_stage] == n_path
+    stage_of = {r: 0 for r in leaves}
+    seen = set()
+    for st in range(1, n_stage + 1):
+        for p in range(sp[st - 1], sp[st]):
+            first, n_rows = int(w[off_path + 2 * p]), int(w[off_path + 2 * p + 1])
+            rows = [int(w[off_chain + 8 * (first + i)]) for i in range(n_rows)]
+            for i, r in enumerate(rows):
+                assert r not in seen
+                seen.add(r)
+                stage_of[r] = st
+                cr = w[off_chain + 8 * (first + i):off_chain + 8 * (first + i) + 8]
+                assert cr[1] == dg[r]
+                parent = int(ci[dg[r] + 1]) if rp[r + 1] - dg[r] == 2 else -1
+                assert cr[7] == parent and (i + 1 == n_rows or rows[i + 1] == parent)
+                rec = int(w[off_ro + first + i])
+                assert rec == cr[6] and w[rec] == r
+                n_lower = int(w[rec + 8]) & 0xfff
+                assert n_lower == dg[r] - rp[r]
+                for e in range(n_lower):
+                    c, kind = int(w[rec + 9 + 4 * e]), (int(w[rec + 9 + 4 * e + 3]) >> 28) & 3
+                    assert c == ci[rp[r] + e]
+                    if kind == 1:
+                        assert i > 0 and rows[i - 1] == c and cr[3] == rp[r] + e
+                    elif kind in (0, 2):
+                        assert stage_of[c] == 0
+                    else:
+                        assert stage_of[c] < st
+    assert len(seen) == n_rec == n - n_leaf
+
+
+def test_path_program_absent_on_meshed_grid():
+    grid = random_grid(60, 10, 5)
+    assert pgm_b200.Engine.from_grid(grid, device=-1).index("path_program").size == 0

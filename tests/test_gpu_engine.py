@@ -65,6 +65,22 @@ def test_three_bus_asymmetric_known_answer():
     assert out["status"][0] == 2
 
 
+@pytest.mark.parametrize("method", ["iterative_current", "linear", "linear_current"])
+def test_three_bus_asymmetric_other_methods(method):
+    """three-phase complex 3 x 3 block kernels (cplx_block.cu) against the oracle; the linear method against the
+    closed form of the const-impedance variant (test_math_solver_pf_linear 'Test asymmetric')"""
+    grid, expected = three_bus_grid(False, const_z=(method == "linear"))
+    eng = pgm_b200.Engine.from_grid(grid)
+    s = np.repeat(grid.s_injection[None], 5, axis=0)
+    out = eng.run(s, grid.source_u_ref, method=method, err_tol=1e-12, max_iter=100)
+    ref = orc.math_pf(grid, method, 1e-12, 100)
+    assert (out["status"] == 0).all() and (out["n_iter"] == ref["num_iter"]).all()
+    for key in KEYS:
+        assert np.max(np.abs(out[key][4] - ref[key])) < 1e-12, key
+        if method == "linear":
+            assert np.max(np.abs(out[key][0] - expected[key])) < 1e-11, key
+
+
 def test_generic_block_kernel_equals_symmetric_kernel(monkeypatch):
     """the generic (2B x 2B) kernel instantiated for B = 1 must reproduce the specialised symmetric kernel bit for bit"""
     grid = random_grid(120, 15, 9, n_source=2)

@@ -14,23 +14,7 @@ pytestmark = pytest.mark.gpu
 CASES = vc.load_cases()
 # methods / symmetries the GPU engine implements so far
 GPU_METHODS = {"newton_raphson", "iterative_current", "linear", "linear_current"}
-# asymmetric (three-phase) calculations run newton_raphson on the GPU; the other asymmetric methods are not built yet
-
-
-def _is_forced_linear(case):
-    """all loads const_y => the reference switches to the linear solver"""
-    inp = case["input"]["data"]
-    types = [row.get("type", 0) for c in ("sym_load", "sym_gen", "asym_load", "asym_gen") for row in inp.get(c, []) if isinstance(row, dict)]
-    return all(t == 1 for t in types)
-
-
-def _on_gpu(case, sym, method):
-    if method not in GPU_METHODS:
-        return False
-    return sym or (method == "newton_raphson" and not _is_forced_linear(case))
-
-
-RUNS = [(n, s, m, b) for n, c in sorted(CASES.items()) for s, m, b in vc.case_runs(c) if _on_gpu(c, s, m)]
+RUNS = [(n, s, m, b) for n, c in sorted(CASES.items()) for s, m, b in vc.case_runs(c) if m in GPU_METHODS]
 
 
 @pytest.mark.parametrize("name,sym,method,is_batch", RUNS, ids=[f"{n}-{'sym' if s else 'asym'}-{m}-{'batch' if b else 'single'}" for n, s, m, b in RUNS])
@@ -111,11 +95,18 @@ def test_asymmetric_benchmark_grid_batch_matches_oracle():
     _compare_with_oracle({k: v[None] for k, v in single.items()}, ref1, 1)
 
 
-def test_asymmetric_other_methods_fail_loudly():
-    grid = pgm_b200.FictionalGrid(seed=0, n_node_total_specified=60, n_connection_per_lv_feeder=3, n_lv_feeder=2, n_node_per_mv_feeder=3, n_mv_feeder=2)
+@pytest.mark.parametrize("method", ["iterative_current", "linear", "linear_current"])
+def test_asymmetric_other_methods_match_oracle(method):
+    grid = pgm_b200.FictionalGrid(seed=0, n_node_total_specified=300, n_connection_per_lv_feeder=5, n_lv_feeder=4, n_node_per_mv_feeder=5,
+                                  n_mv_feeder=3, has_mv_ring=True, has_lv_ring=True)
+    n_scn = 9
+    update = grid.batch_update(n_scn, seed=2)
     model = pgm_b200.PowerGridModel(grid.input_data)
-    with pytest.raises(pgm_b200.PgmB200Error, match="newton_raphson only"):
-        model.calculate_power_flow(symmetric=False, calculation_method="iterative_current")
+    res = model.calculate_power_flow(symmetric=False, update_data=update, calculation_method=method)
+    ref = orc.Model(grid.input_data).calculate(sym=False, update=update, threading=0, method=method)
+    assert ref["n_failed"] == 0
+    assert np.array_equal(model.n_iter, ref["n_iter"]), (model.n_iter, ref["n_iter"])
+    _compare_with_oracle(res, ref, n_scn)
 
 
 def test_batch_properties_at_full_size():
