@@ -36,6 +36,14 @@ def measured_peak_hbm():
         return 6650.0, "fallback"
 
 
+def measured_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the solver kernel from the committed ncu --set full capture"""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -251,7 +259,7 @@ def main():
                     "gpu_launches": e2e_launches},
             "gpu_launches": gpu_launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_kind": peak_kind, "kernel": "nr_sym_v3_kernel (radial path kernel; nr_sym_v2_kernel for wide tiles / meshed grids)",
+                         "traffic": measured_traffic(), "peak_kind": peak_kind, "kernel": "nr_sym_v3_kernel (radial path kernel; nr_sym_v2_kernel for wide tiles / meshed grids)",
                          "algorithmic_bytes_per_launch": bytes_per_launch, "launch_ms": 1e3 * launch_s},
             "cpu_baseline": {"value": cpu_value, "unit": "scenarios/s", "cores": cores, "kind": "port",
                              "sample": f"{sample} of the {N_SCN} scenarios x {reps} repeats, all {cores} host threads (reference threading=0)"},
