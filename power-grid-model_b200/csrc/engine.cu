@@ -180,8 +180,8 @@ void Engine::choose_tiling(int64_t n_scn) {
     }
     tile_width_ = env_int("PGMB_TILE", t);
     if (tile_width_ != 4 && tile_width_ != 8 && tile_width_ != 16 && tile_width_ != 32) tile_width_ = t;
-    // generic-block kernel (asymmetric): a thread holds several 6 x 6 blocks, fewer threads per block keep them in L1
-    n_slot_ = env_int("PGMB_SLOTS", (symmetric_ ? 512 : 128) / tile_width_);
+    // generic-block kernel (asymmetric): 255 registers per thread, at most 256 threads per block (measured best)
+    n_slot_ = env_int("PGMB_SLOTS", (symmetric_ ? 512 : 256) / tile_width_);
     if (n_slot_ < 1) n_slot_ = 1;
     if (n_slot_ * tile_width_ > 1024) n_slot_ = 1024 / tile_width_;
 }

@@ -11,6 +11,7 @@ n_scn = int(os.environ.get("N_SCN", "1000"))
 reps = int(os.environ.get("REPS", "3"))
 rings = os.environ.get("RINGS", "0") == "1"
 sym = os.environ.get("ASYM", "0") != "1"
+method = os.environ.get("METHOD", "newton_raphson")
 grid = pgm_b200.FictionalGrid(seed=0, has_mv_ring=rings, has_lv_ring=rings, **pgm_b200.BENCHMARK_OPTION)
 update = grid.batch_update(n_scn, seed=0)
 model = pgm_b200.PowerGridModel(grid.input_data)
@@ -22,7 +23,7 @@ eng.set_param(model.math_real(0, sym, "branch_param").view(np.complex128), model
               model.math_real(0, sym, "source_param").view(np.complex128))
 s_inj, u_ref = model.batch_pf_input(update, symmetric=sym)
 eng.stage(s_inj, u_ref)
-ms = [eng.solve_staged() for _ in range(reps)]
+ms = [eng.solve_staged(method=method) for _ in range(reps)]
 out = eng.fetch()
 print("solve ms:", ms, "mean iter", out["n_iter"].mean(), "levels", len(eng.index("level_ptr")) - 1,
-      "tile", os.environ.get("PGMB_TILE", "auto"), "slots", os.environ.get("PGMB_SLOTS", "auto"))
+      "method", method, "n_scn", n_scn, "tile", os.environ.get("PGMB_TILE", "auto"), "slots", os.environ.get("PGMB_SLOTS", "auto"))
