@@ -27,7 +27,8 @@ uint64_t kernel_launch_count() { return g_kernel_launches.load(std::memory_order
 
 Engine::Engine(MathTopology topo, bool symmetric, int device)
     : topo_{std::move(topo)}, symmetric_{symmetric}, B_{symmetric ? 1 : 3}, device_{device}, pattern_{topo_}, schedule_{pattern_}, program_{pattern_, schedule_, topo_},
-      path_program_{pattern_, schedule_, topo_, program_} {
+      path_program_{pattern_, schedule_, topo_, program_},
+      wide_plan_{pattern_, schedule_} {
     if (device < 0) return; // symbolic-only engine (structure introspection on hosts without a GPU); it cannot run
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
@@ -65,6 +66,10 @@ void Engine::upload_structure() {
     d_src_ptr_.upload(narrow_vec<int32_t>(topo_.sources_per_bus), stream_);
     d_prog_.upload(program_.words, stream_);
     if (path_program_.valid) d_path_prog_.upload(path_program_.words, stream_);
+    d_wide_level_ptr_.upload(wide_plan_.level_ptr, stream_);
+    d_wide_table_.upload(wide_plan_.table, stream_);
+    d_wide_data_.upload(wide_plan_.data, stream_);
+    d_row_is_wide_.upload(wide_plan_.is_wide, stream_);
     d_lg_type_.upload(topo_.load_gen_type, stream_);
     d_y_row_ptr_.upload(narrow_vec<int32_t>(pattern_.row_indptr), stream_);
     d_y_col_idx_.upload(narrow_vec<int32_t>(pattern_.col_indices), stream_);
@@ -110,6 +115,14 @@ void Engine::upload_structure() {
     ds_.phase_shift = d_phase_shift_.get();
     ds_.prog = d_prog_.get();
     ds_.prog_words = static_cast<int32_t>(program_.words.size());
+    ds_.wide_level_ptr = d_wide_level_ptr_.get();
+    ds_.wide_table = d_wide_table_.get();
+    ds_.wide_data = d_wide_data_.get();
+    ds_.row_is_wide = d_row_is_wide_.get();
+    ds_.n_wide = env_int("PGMB_WIDE", 1) != 0 ? wide_plan_.n_wide() : 0; // PGMB_WIDE=0: every row by one thread (cross-check)
+    ds_.wide_max_upd = wide_plan_.max_upd;
+    ds_.wide_max_lower = wide_plan_.max_lower;
+    ds_.wide_max_entries = wide_plan_.max_entries;
     ds_.path_prog = path_program_.valid ? d_path_prog_.get() : nullptr;
     ds_.path_prog_words = path_program_.valid ? static_cast<int32_t>(path_program_.words.size()) : 0;
 }
@@ -200,6 +213,11 @@ void Engine::allocate_batch(int64_t n) {
     d_pol_.ensure(n_tile * nb * N * T);
     d_u_.ensure(n_tile * nb * N * T);
     if (symmetric_ && path_program_.valid) d_side_.ensure(n_tile * nb * N * T);
+    if (wide_plan_.n_wide() != 0) {
+        d_wide_terms_.ensure(static_cast<size_t>(n_tile) * wide_plan_.max_upd * N * N * T + 1);
+        d_wide_rhs_.ensure(static_cast<size_t>(n_tile) * wide_plan_.max_lower * N * T + 1);
+        d_wide_sum_.ensure(static_cast<size_t>(n_tile) * wide_plan_.max_entries * N * T + 1);
+    }
     d_perm_.ensure(n_tile * nb * T * 2 * N);
     d_sinj_.ensure(static_cast<size_t>(n_tile) * topo_.n_load_gen() * 2 * B_ * T + 1);
     d_lg_status_.ensure(static_cast<size_t>(n_tile) * topo_.n_load_gen() * T + 1);
@@ -214,6 +232,9 @@ void Engine::allocate_batch(int64_t n) {
     db_.pol = d_pol_.get();
     db_.u = d_u_.get();
     db_.side = d_side_.get();
+    db_.wide_terms = d_wide_terms_.get();
+    db_.wide_rhs = d_wide_rhs_.get();
+    db_.wide_sum = d_wide_sum_.get();
     db_.perm = d_perm_.get();
     db_.sinj = d_sinj_.get();
     db_.usrc = d_usrc_.get();
@@ -282,6 +303,11 @@ DevBatch Engine::batch_view(int64_t tile_begin, int64_t tile_end) const {
     v.pol += tile_begin * nb * N * T;
     v.u += tile_begin * nb * N * T;
     if (v.side != nullptr) v.side += tile_begin * nb * N * T;
+    if (v.wide_terms != nullptr) {
+        v.wide_terms += static_cast<size_t>(tile_begin) * wide_plan_.max_upd * N * N * T;
+        v.wide_rhs += static_cast<size_t>(tile_begin) * wide_plan_.max_lower * N * T;
+        v.wide_sum += static_cast<size_t>(tile_begin) * wide_plan_.max_entries * N * T;
+    }
     v.perm += tile_begin * nb * T * 2 * N;
     v.sinj += static_cast<size_t>(tile_begin) * topo_.n_load_gen() * 2 * B_ * T;
     v.lg_status += static_cast<size_t>(tile_begin) * topo_.n_load_gen() * T;

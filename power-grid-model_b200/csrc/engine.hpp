@@ -115,6 +115,7 @@ class Engine {
     EliminationSchedule const& schedule() const { return schedule_; }
     RowProgram const& program() const { return program_; }
     PathProgram const& path_program() const { return path_program_; }
+    WideRowPlan const& wide_plan() const { return wide_plan_; }
     std::vector<double> const& admittance() const { return admittance_; } // [nnz][B][B] complex
     int device() const { return device_; }
     int phases() const { return B_; }
@@ -133,6 +134,7 @@ class Engine {
     EliminationSchedule schedule_;
     RowProgram program_;
     PathProgram path_program_;
+    WideRowPlan wide_plan_;
     std::vector<double> admittance_;
     std::vector<double> branch_param_, shunt_param_, source_param_;
     bool param_set_{false};
@@ -141,7 +143,7 @@ class Engine {
 
     // device structure
     DevBuf<int32_t> d_row_ptr_, d_col_idx_, d_diag_, d_map_y_, d_level_ptr_, d_level_rows_, d_upd_ptr_, d_upd_u_, d_upd_a_,
-        d_lg_ptr_, d_src_ptr_, d_prog_, d_path_prog_, d_y_row_ptr_, d_y_col_idx_, d_branch_bus_, d_shunt_bus_, d_lg_bus_, d_src_bus_;
+        d_lg_ptr_, d_src_ptr_, d_prog_, d_path_prog_, d_wide_level_ptr_, d_wide_table_, d_wide_data_, d_y_row_ptr_, d_y_col_idx_, d_branch_bus_, d_shunt_bus_, d_lg_bus_, d_src_bus_;
     DevBuf<int8_t> d_lg_type_;
     DevBuf<double> d_ydata_, d_src_yref_, d_src_y1y0_, d_branch_param_, d_shunt_param_, d_phase_shift_;
     DevStructure ds_{};
@@ -149,7 +151,8 @@ class Engine {
     // batch buffers
     int tile_width_{8};
     int n_slot_{64};
-    DevBuf<double> d_side_;
+    DevBuf<double> d_side_, d_wide_terms_, d_wide_rhs_, d_wide_sum_;
+    DevBuf<uint8_t> d_row_is_wide_;
     DevBuf<double> d_jac_, d_xvec_, d_pol_, d_u_, d_sinj_, d_usrc_, d_max_dev_, d_in_sinj_, d_in_usrc_;
     DevBuf<double> d_out_u_, d_out_inj_, d_out_branch_, d_out_source_, d_out_shunt_, d_out_lg_;
     DevBuf<uint8_t> d_perm_, d_lg_status_;

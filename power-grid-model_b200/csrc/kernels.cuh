@@ -45,6 +45,12 @@ struct DevStructure {
     // row programs (symbolic.hpp RowProgram): level_ptr | task_off | records
     int32_t const* prog;
     int32_t prog_words;
+    // wide rows (symbolic.hpp WideRowPlan): rows eliminated by the whole thread block together
+    int32_t const* wide_level_ptr; // [n_level + 1]
+    int32_t const* wide_table;     // 8 words per wide row
+    int32_t const* wide_data;
+    uint8_t const* row_is_wide;    // [n_bus]
+    int32_t n_wide, wide_max_upd, wide_max_lower, wide_max_entries;
     // path programs (symbolic.hpp PathProgram) for radial grids; null when the grid has a cyclic core
     int32_t const* path_prog;
     int32_t path_prog_words;
@@ -65,6 +71,9 @@ struct DevBatch {
     int32_t* n_iter; // [n_scn]
     double* max_dev; // [n_scn]
     double* side;    // [tile][n_bus][2][T]      precomputed leaf update terms of the path kernel (nr_sym_v3.cu)
+    double* wide_terms; // [tile][wide_max_upd][N*N][T]   update terms of the wide row in flight
+    double* wide_rhs;   // [tile][wide_max_lower][N][T]
+    double* wide_sum;   // [tile][wide_max_entries][N][T]
     uint8_t* lg_status; // [tile][n_load_gen][T] per-scenario status of each load_gen (device update path), may be null
     unsigned long long* phase_cycles; // optional [n_tile][8] clock64 totals per phase (PGMB_DEBUG_PHASES), may be null
 };

@@ -10,478 +10,11 @@
 // dynamically.  U blocks are stored with the row permutation / L^-1 applied but WITHOUT the later column permutation Q_j;
 // the backward substitution sums the products in the permuted order instead, so every rounding equals the reference's.
 #include "kernels.cuh"
-
-#include <cfloat>
-#include <cmath>
-#include <cuda_runtime.h>
+#include "block_common.cuh"
 
 namespace pgmb {
+using namespace blk;
 namespace {
-
-constexpr int kStatusOk = 0, kStatusDiverged = 1, kStatusSingular = 2;
-enum class Mode { linear_init, newton };
-
-__device__ __forceinline__ bool not_normal(double x) { return !(fabs(x) >= DBL_MIN) || isinf(x); }
-
-template <int T, int B> struct TileB {
-    static constexpr int N = 2 * B, NN = N * N;
-    double* jac;
-    double* xvec;
-    double* pol;
-    double* u;
-    uint8_t* perm;
-    double const* sinj;
-    double const* usrc;
-    __device__ __forceinline__ void load_blk(int k, double* a) const {
-        double const* p = jac + (size_t)k * NN * T;
-#pragma unroll
-        for (int i = 0; i < NN; ++i) a[i] = p[(size_t)i * T];
-    }
-    __device__ __forceinline__ void store_blk(int k, double const* a) const {
-        double* p = jac + (size_t)k * NN * T;
-#pragma unroll
-        for (int i = 0; i < NN; ++i) p[(size_t)i * T] = a[i];
-    }
-    // voltages: component 2p = re, 2p + 1 = im of phase p
-    __device__ __forceinline__ void load_u(int bus, double* ur, double* ui) const {
-#pragma unroll
-        for (int p = 0; p < B; ++p) {
-            ur[p] = u[(size_t)(bus * N + 2 * p) * T];
-            ui[p] = u[(size_t)(bus * N + 2 * p + 1) * T];
-        }
-    }
-};
-
-// element (r, c) of sub-block (br, bc), column-major N x N
-template <int B> __device__ __forceinline__ int el(int br, int bc, int r, int c) { return (bc * B + c) * (2 * B) + (br * B + r); }
-
-// block = hnml(y, ui, uj): power_flow[r][c] = (ui[r] * conj(uj[c])) * conj(y[r][c]); H = L = imag, N = -M = real
-template <int B>
-__device__ __forceinline__ void hnml(double* blk, double const* y /*[B*B][2] row-major*/, double sign, double const* uir,
-                                     double const* uii, double const* ujr, double const* uji) {
-#pragma unroll
-    for (int r = 0; r < B; ++r)
-#pragma unroll
-        for (int c = 0; c < B; ++c) {
-            double const yr = sign * y[2 * (r * B + c)], yi = sign * y[2 * (r * B + c) + 1];
-            double const cr = ujr[c], ci = -uji[c];
-            double const ar = uir[r] * cr - uii[r] * ci;
-            double const ai = uir[r] * ci + uii[r] * cr;
-            double const dr = yr, di = -yi;
-            double const n = ar * dr - ai * di;
-            double const h = ar * di + ai * dr;
-            blk[el<B>(0, 0, r, c)] = h;
-            blk[el<B>(0, 1, r, c)] = n;
-            blk[el<B>(1, 0, r, c)] = -n;
-            blk[el<B>(1, 1, r, c)] = h;
-        }
-}
-template <int B> __device__ __forceinline__ void linear_block(double* blk, double const* y) {
-#pragma unroll
-    for (int r = 0; r < B; ++r)
-#pragma unroll
-        for (int c = 0; c < B; ++c) {
-            double const g = y[2 * (r * B + c)], b = y[2 * (r * B + c) + 1];
-            blk[el<B>(0, 1, r, c)] = -b;
-            blk[el<B>(0, 0, r, c)] = g;
-            blk[el<B>(1, 1, r, c)] = g;
-            blk[el<B>(1, 0, r, c)] = b;
-        }
-}
-
-// DenseLUFactor::factorize_block_in_place for an N x N real block; p / q are the accumulated permutation index vectors
-template <int N> __device__ bool factorize_block(double* m, uint8_t* p, uint8_t* q) {
-    int rt[N], ct[N];
-    double max_pivot = 0.0;
-    bool stopped = false;
-    for (int pivot = 0; pivot < N; ++pivot) {
-        int rb = pivot, cb = pivot;
-        double best = m[pivot * N + pivot] * m[pivot * N + pivot];
-        for (int c = pivot; c < N; ++c)
-            for (int r = pivot; r < N; ++r) {
-                double const sc = m[c * N + r] * m[c * N + r];
-                if (sc > best) {
-                    best = sc;
-                    rb = r;
-                    cb = c;
-                }
-            }
-        if (best == 0.0) {
-            for (int k = pivot; k < N; ++k) {
-                rt[k] = k;
-                ct[k] = k;
-            }
-            stopped = true;
-            break;
-        }
-        max_pivot = fmax(max_pivot, sqrt(best));
-        rt[pivot] = rb;
-        ct[pivot] = cb;
-        if (rb != pivot)
-            for (int c = 0; c < N; ++c) {
-                double const x = m[c * N + pivot];
-                m[c * N + pivot] = m[c * N + rb];
-                m[c * N + rb] = x;
-            }
-        if (cb != pivot)
-            for (int r = 0; r < N; ++r) {
-                double const x = m[pivot * N + r];
-                m[pivot * N + r] = m[cb * N + r];
-                m[cb * N + r] = x;
-            }
-        if (pivot < N - 1) {
-            for (int r = pivot + 1; r < N; ++r) m[pivot * N + r] /= m[pivot * N + pivot];
-            for (int c = pivot + 1; c < N; ++c)
-                for (int r = pivot + 1; r < N; ++r) m[c * N + r] -= m[pivot * N + r] * m[c * N + pivot];
-        }
-    }
-    (void)stopped;
-    for (int i = 0; i < N; ++i) {
-        p[i] = (uint8_t)i;
-        q[i] = (uint8_t)i;
-    }
-    for (int pivot = N - 1; pivot >= 0; --pivot) {
-        uint8_t const x = p[pivot];
-        p[pivot] = p[rt[pivot]];
-        p[rt[pivot]] = x;
-    }
-    for (int pivot = 0; pivot < N; ++pivot) {
-        uint8_t const x = q[pivot];
-        q[pivot] = q[ct[pivot]];
-        q[ct[pivot]] = x;
-    }
-    double const threshold = DBL_EPSILON * max_pivot;
-    bool singular = false;
-    for (int pivot = 0; pivot < N; ++pivot) {
-        double const d = m[pivot * N + pivot];
-        singular = singular || fabs(d) < threshold || not_normal(d);
-    }
-    return singular;
-}
-
-template <int T, int B, Mode mode>
-__device__ bool up_row(DevStructure const& s, TileB<T, B> const& t, int row) {
-    constexpr int N = 2 * B, NN = N * N, BB2 = B * B * 2;
-    int const rb = __ldg(s.row_ptr + row), re = __ldg(s.row_ptr + row + 1), dg = __ldg(s.diag + row);
-    double uir[B], uii[B];
-    t.load_u(row, uir, uii);
-    double acc[N]; // NR: -P[B], -Q[B] then mismatch ; linear: rhs real[B], imag[B]
-#pragma unroll
-    for (int i = 0; i < N; ++i) acc[i] = 0.0;
-    double d[NN];
-#pragma unroll
-    for (int i = 0; i < NN; ++i) d[i] = 0.0;
-
-    // 1. build the row
-    for (int k = rb; k < re; ++k) {
-        int const ky = __ldg(s.map_y + k);
-        double blk[NN];
-#pragma unroll
-        for (int i = 0; i < NN; ++i) blk[i] = 0.0;
-        if (ky >= 0) {
-            double y[BB2];
-#pragma unroll
-            for (int i = 0; i < BB2; ++i) y[i] = __ldg(s.ydata + (size_t)ky * BB2 + i);
-            if constexpr (mode == Mode::newton) {
-                int const j = __ldg(s.col_idx + k);
-                double ujr[B], uji[B];
-                t.load_u(j, ujr, uji);
-                hnml<B>(blk, y, 1.0, uir, uii, ujr, uji);
-#pragma unroll
-                for (int r = 0; r < B; ++r) {
-                    double sn = blk[el<B>(0, 1, r, 0)], sh = blk[el<B>(0, 0, r, 0)];
-#pragma unroll
-                    for (int c = 1; c < B; ++c) {
-                        sn += blk[el<B>(0, 1, r, c)];
-                        sh += blk[el<B>(0, 0, r, c)];
-                    }
-                    acc[r] -= sn;
-                    acc[B + r] -= sh;
-                }
-            } else {
-                linear_block<B>(blk, y);
-            }
-        }
-        if (k == dg) {
-#pragma unroll
-            for (int i = 0; i < NN; ++i) d[i] = blk[i];
-        } else {
-            t.store_blk(k, blk);
-        }
-    }
-    if constexpr (mode == Mode::newton) {
-#pragma unroll
-        for (int p = 0; p < B; ++p) {
-            d[el<B>(0, 0, p, p)] += acc[B + p];
-            d[el<B>(0, 1, p, p)] += -acc[p];
-            d[el<B>(1, 0, p, p)] += -acc[p];
-            d[el<B>(1, 1, p, p)] += -acc[B + p];
-        }
-    }
-    // loads
-    for (int lg = __ldg(s.lg_ptr + row), lge = __ldg(s.lg_ptr + row + 1); lg < lge; ++lg) {
-        int const type = __ldg(s.lg_type + lg);
-#pragma unroll
-        for (int p = 0; p < B; ++p) {
-            double const ps = t.sinj[(size_t)(lg * N + 2 * p) * T], qs = t.sinj[(size_t)(lg * N + 2 * p + 1) * T];
-            if constexpr (mode == Mode::newton) {
-                double const v = t.pol[(size_t)(row * N + B + p) * T];
-                if (type == 0) {
-                    acc[p] += ps;
-                    acc[B + p] += qs;
-                } else if (type == 1) {
-                    acc[p] += ps * v * v;
-                    acc[B + p] += qs * v * v;
-                    d[el<B>(0, 1, p, p)] += -ps * 2.0 * v * v;
-                    d[el<B>(1, 1, p, p)] += -qs * 2.0 * v * v;
-                } else {
-                    acc[p] += ps * v;
-                    acc[B + p] += qs * v;
-                    d[el<B>(0, 1, p, p)] += -ps * v;
-                    d[el<B>(1, 1, p, p)] += -qs * v;
-                }
-            } else {
-                double const ylr = -ps, yli = qs; // y_load = -conj(s)
-                d[el<B>(0, 1, p, p)] += -yli;
-                d[el<B>(0, 0, p, p)] += ylr;
-                d[el<B>(1, 1, p, p)] += ylr;
-                d[el<B>(1, 0, p, p)] += yli;
-            }
-        }
-    }
-    // sources
-    for (int sr = __ldg(s.src_ptr + row), sre = __ldg(s.src_ptr + row + 1); sr < sre; ++sr) {
-        double y[BB2];
-#pragma unroll
-        for (int i = 0; i < BB2; ++i) y[i] = __ldg(s.src_yref + (size_t)sr * BB2 + i);
-        double const u0r = t.usrc[(size_t)(sr * 2) * T], u0i = t.usrc[(size_t)(sr * 2 + 1) * T];
-        double usr[B], usi[B];
-        usr[0] = u0r;
-        usi[0] = u0i;
-        if constexpr (B == 3) { // ComplexValue<asym>{u} = (u, u a^2, u a)   (three_phase_tensor.hpp:47-53)
-            double const a2r = -0.5, a2i = -0.8660254037844386 /* -sqrt3/2 */, ar = -0.5, ai = 0.8660254037844386;
-            usr[1] = u0r * a2r - u0i * a2i;
-            usi[1] = u0r * a2i + u0i * a2r;
-            usr[2] = u0r * ar - u0i * ai;
-            usi[2] = u0r * ai + u0i * ar;
-        }
-        if constexpr (mode == Mode::newton) {
-            double mm[NN], ms[NN];
-            hnml<B>(mm, y, 1.0, uir, uii, uir, uii);
-            hnml<B>(ms, y, -1.0, uir, uii, usr, usi);
-            double p_cal[B], q_cal[B];
-#pragma unroll
-            for (int r = 0; r < B; ++r) {
-                double sn = mm[el<B>(0, 1, r, 0)] + ms[el<B>(0, 1, r, 0)];
-                double sh = mm[el<B>(0, 0, r, 0)] + ms[el<B>(0, 0, r, 0)];
-#pragma unroll
-                for (int c = 1; c < B; ++c) {
-                    sn += mm[el<B>(0, 1, r, c)] + ms[el<B>(0, 1, r, c)];
-                    sh += mm[el<B>(0, 0, r, c)] + ms[el<B>(0, 0, r, c)];
-                }
-                p_cal[r] = sn;
-                q_cal[r] = sh;
-            }
-#pragma unroll
-            for (int p = 0; p < B; ++p) {
-                mm[el<B>(0, 0, p, p)] += -q_cal[p];
-                mm[el<B>(0, 1, p, p)] += p_cal[p];
-                mm[el<B>(1, 0, p, p)] += p_cal[p];
-                mm[el<B>(1, 1, p, p)] += q_cal[p];
-                acc[p] -= p_cal[p];
-                acc[B + p] -= q_cal[p];
-            }
-#pragma unroll
-            for (int i = 0; i < NN; ++i) d[i] += mm[i];
-        } else {
-#pragma unroll
-            for (int r = 0; r < B; ++r) {
-#pragma unroll
-                for (int c = 0; c < B; ++c) {
-                    double const yr = y[2 * (r * B + c)], yi = y[2 * (r * B + c) + 1];
-                    d[el<B>(0, 1, r, c)] -= yi;
-                    d[el<B>(0, 0, r, c)] += yr;
-                    d[el<B>(1, 1, r, c)] += yr;
-                    d[el<B>(1, 0, r, c)] += yi;
-                }
-                // rhs += dot(y_source, u_source): sequential sum over the phases
-                double sr_ = y[2 * (r * B)] * usr[0] - y[2 * (r * B) + 1] * usi[0];
-                double si_ = y[2 * (r * B)] * usi[0] + y[2 * (r * B) + 1] * usr[0];
-#pragma unroll
-                for (int c = 1; c < B; ++c) {
-                    sr_ += y[2 * (r * B + c)] * usr[c] - y[2 * (r * B + c) + 1] * usi[c];
-                    si_ += y[2 * (r * B + c)] * usi[c] + y[2 * (r * B + c) + 1] * usr[c];
-                }
-                acc[r] += sr_;
-                acc[B + r] += si_;
-            }
-        }
-    }
-
-    // 2. eliminate against finished rows (L block in local memory only)
-    for (int e = rb; e < dg; ++e) {
-        int const c = __ldg(s.col_idx + e);
-        int const dc = __ldg(s.diag + c);
-        double a[NN], piv[NN], l[NN];
-        t.load_blk(e, a);
-        t.load_blk(dc, piv);
-        uint8_t qc[N];
-#pragma unroll
-        for (int i = 0; i < N; ++i) qc[i] = t.perm[(size_t)(c * 2 * N + N + i) * T];
-        // l = (a Q_c): column i of l = column q[i] of a ; then right / upper triangular solve
-#pragma unroll
-        for (int i = 0; i < N; ++i)
-#pragma unroll
-            for (int r = 0; r < N; ++r) l[i * N + r] = a[qc[i] * N + r];
-        for (int idx = 0; idx < N; ++idx) {
-            for (int prev = 0; prev < idx; ++prev) {
-                double const uv = piv[idx * N + prev];
-#pragma unroll
-                for (int r = 0; r < N; ++r) l[idx * N + r] -= uv * l[prev * N + r];
-            }
-            double const dd = piv[idx * N + idx];
-#pragma unroll
-            for (int r = 0; r < N; ++r) l[idx * N + r] /= dd;
-        }
-        for (int q = __ldg(s.upd_ptr + e), qe = __ldg(s.upd_ptr + e + 1); q < qe; ++q) {
-            int const ui = __ldg(s.upd_u + q), ai = __ldg(s.upd_a + q);
-            double ub[NN];
-            t.load_blk(ui, ub);
-            double* tgt = d;
-            double tb[NN];
-            if (ai != dg) {
-                t.load_blk(ai, tb);
-                tgt = tb;
-            }
-            for (int cc = 0; cc < N; ++cc)
-#pragma unroll
-                for (int r = 0; r < N; ++r) {
-                    double sum = l[0 * N + r] * ub[cc * N + 0];
-#pragma unroll
-                    for (int k = 1; k < N; ++k) sum += l[k * N + r] * ub[cc * N + k];
-                    tgt[cc * N + r] -= sum;
-                }
-            if (ai != dg) t.store_blk(ai, tb);
-        }
-        double yc[N];
-#pragma unroll
-        for (int i = 0; i < N; ++i) yc[i] = t.xvec[(size_t)(c * N + i) * T];
-#pragma unroll
-        for (int r = 0; r < N; ++r) {
-            double sum = l[0 * N + r] * yc[0];
-#pragma unroll
-            for (int k = 1; k < N; ++k) sum += l[k * N + r] * yc[k];
-            acc[r] -= sum;
-        }
-    }
-
-    // 3. factorise the diagonal block
-    uint8_t p[N], q[N];
-    bool const singular = factorize_block<N>(d, p, q);
-    t.store_blk(dg, d);
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-        t.perm[(size_t)(row * 2 * N + i) * T] = p[i];
-        t.perm[(size_t)(row * 2 * N + N + i) * T] = q[i];
-    }
-    // 4. U blocks: L_pp^-1 (P A)   (P A: row p[i] of the result = row i of A)
-    for (int e = dg + 1; e < re; ++e) {
-        double a[NN], ub[NN];
-        t.load_blk(e, a);
-#pragma unroll
-        for (int cc = 0; cc < N; ++cc)
-#pragma unroll
-            for (int i = 0; i < N; ++i) ub[cc * N + p[i]] = a[cc * N + i];
-        for (int idx = 0; idx < N; ++idx)
-            for (int prev = 0; prev < idx; ++prev) {
-                double const lv = d[prev * N + idx];
-#pragma unroll
-                for (int cc = 0; cc < N; ++cc) ub[cc * N + idx] -= lv * ub[cc * N + prev];
-            }
-        t.store_blk(e, ub);
-    }
-    // 5. forward substitution inside the block: x = L_pp^-1 (P t)
-    double xr[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) xr[p[i]] = acc[i];
-    for (int idx = 0; idx < N; ++idx)
-        for (int prev = 0; prev < idx; ++prev) xr[idx] -= d[prev * N + idx] * xr[prev];
-#pragma unroll
-    for (int i = 0; i < N; ++i) t.xvec[(size_t)(row * N + i) * T] = xr[i];
-    return singular;
-}
-
-template <int T, int B, Mode mode> __device__ double down_row(DevStructure const& s, TileB<T, B> const& t, int row) {
-    constexpr int N = 2 * B, NN = N * N;
-    int const re = __ldg(s.row_ptr + row + 1), dg = __ldg(s.diag + row);
-    double y[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) y[i] = t.xvec[(size_t)(row * N + i) * T];
-    for (int e = re - 1; e > dg; --e) {
-        int const j = __ldg(s.col_idx + e);
-        double ub[NN], xj[N];
-        uint8_t qj[N];
-        t.load_blk(e, ub);
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            xj[i] = t.xvec[(size_t)(j * N + i) * T]; // final solution of row j (column permutation already applied)
-            qj[i] = t.perm[(size_t)(j * 2 * N + N + i) * T];
-        }
-        // reference: x_row -= (U Q_j) x'_j with x_j[q[i]] = x'_j[i]  =>  sum over i of U[:, q[i]] * x_j[q[i]], in that order
-#pragma unroll
-        for (int r = 0; r < N; ++r) {
-            double sum = ub[qj[0] * N + r] * xj[qj[0]];
-#pragma unroll
-            for (int i = 1; i < N; ++i) sum += ub[qj[i] * N + r] * xj[qj[i]];
-            y[r] -= sum;
-        }
-    }
-    double d[NN];
-    t.load_blk(dg, d);
-    for (int step = 0; step < N; ++step) { // left / upper solve, backward traversal
-        int const idx = N - 1 - step;
-        for (int ps = 0; ps < step; ++ps) {
-            int const prev = N - 1 - ps;
-            y[idx] -= d[prev * N + idx] * y[prev];
-        }
-        y[idx] /= d[idx * N + idx];
-    }
-    double x[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) x[t.perm[(size_t)(row * 2 * N + N + i) * T]] = y[i];
-#pragma unroll
-    for (int i = 0; i < N; ++i) t.xvec[(size_t)(row * N + i) * T] = x[i];
-    double dev = 0.0;
-#pragma unroll
-    for (int p = 0; p < B; ++p) {
-        double* const pth = t.pol + (size_t)(row * N + p) * T;
-        double* const pv = t.pol + (size_t)(row * N + B + p) * T;
-        double* const pur = t.u + (size_t)(row * N + 2 * p) * T;
-        double* const pui = t.u + (size_t)(row * N + 2 * p + 1) * T;
-        if constexpr (mode == Mode::newton) {
-            double theta = *pth, v = *pv;
-            theta += x[p];
-            v += v * x[B + p];
-            double sn, cs;
-            sincos(theta, &sn, &cs);
-            double const nr = v * cs, ni = v * sn;
-            double const dr = nr - *pur, di = ni - *pui;
-            *pth = theta;
-            *pv = v;
-            *pur = nr;
-            *pui = ni;
-            double const dp = sqrt(dr * dr + di * di);
-            dev = p == 0 ? dp : fmax(dev, dp);
-        } else {
-            double const xr = x[p], xi = x[B + p]; // linear start: real part in the P rows, imaginary part in the Q rows
-            *pur = xr;
-            *pui = xi;
-            *pv = sqrt(xr * xr + xi * xi);
-            *pth = atan2(xi, xr);
-        }
-    }
-    return dev;
-}
 
 template <int T, int B, Mode mode>
 __device__ void sweeps(DevStructure const& s, TileB<T, B> const& t, int slot, int n_slot, bool active, bool& singular,
@@ -489,8 +22,15 @@ __device__ void sweeps(DevStructure const& s, TileB<T, B> const& t, int slot, in
     for (int lv = 0; lv < s.n_level; ++lv) {
         int const b = __ldg(s.level_ptr + lv), e = __ldg(s.level_ptr + lv + 1);
         if (active)
-            for (int i = b + slot; i < e; i += n_slot) singular |= up_row<T, B, mode>(s, t, __ldg(s.level_rows + i));
+            for (int i = b + slot; i < e; i += n_slot) {
+                int const row = __ldg(s.level_rows + i);
+                if (s.n_wide != 0 && __ldg(s.row_is_wide + row)) continue; // eliminated below by the whole block
+                singular |= up_row<T, B, mode>(s, t, row);
+            }
         __syncthreads();
+        if (s.n_wide != 0)
+            for (int w = __ldg(s.wide_level_ptr + lv); w < __ldg(s.wide_level_ptr + lv + 1); ++w)
+                wide_up_row<T, B, mode, false>(s, t, w, slot, n_slot, active, singular);
     }
     for (int lv = s.n_level - 1; lv >= 0; --lv) {
         int const b = __ldg(s.level_ptr + lv), e = __ldg(s.level_ptr + lv + 1);
@@ -515,6 +55,9 @@ template <int T, int B> __global__ void nr_block_kernel(DevStructure s, DevBatch
     t.perm = b.perm + (size_t)tile * s.n_bus * 2 * N * T + lane;
     t.sinj = b.sinj + (size_t)tile * s.n_load_gen * N * T + lane;
     t.usrc = b.usrc + (size_t)tile * s.n_source * 2 * T + lane;
+    t.wide_terms = b.wide_terms ? b.wide_terms + (size_t)tile * s.wide_max_upd * N * N * T + lane : nullptr;
+    t.wide_rhs = b.wide_rhs ? b.wide_rhs + (size_t)tile * s.wide_max_lower * N * T + lane : nullptr;
+    t.wide_sum = b.wide_sum ? b.wide_sum + (size_t)tile * s.wide_max_entries * N * T + lane : nullptr;
     if (threadIdx.x < T) {
         sh_dev[threadIdx.x] = 0ull;
         sh_singular[threadIdx.x] = 0;

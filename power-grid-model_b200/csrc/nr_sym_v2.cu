@@ -5,6 +5,7 @@
 //     to the scratch matrix, only the factorised diagonal block, the U block towards the parent and the forward-substituted
 //     right-hand side leave the thread; every global load of a row task is issued before its first store.
 // Rows that are not tree rows (the cyclic core of a meshed grid) run the generic row task of nr_sym_common.cuh.
+#include "block_common.cuh"
 #include "nr_sym_common.cuh"
 
 #include <cuda_runtime.h>
@@ -292,9 +293,10 @@ __device__ __forceinline__ double down_tree_row(TileR<T> const& t, int32_t const
 }
 
 template <int T, Mode mode>
-__device__ __forceinline__ void sweeps_v2(DevStructure const& s, Tile<T> const& tg, TileR<T> const& t, int32_t const* prog,
-                                          int slot, int n_slot, bool active, bool& singular, double& dev,
-                                          unsigned long long* phase) {
+__device__ __forceinline__ void sweeps_v2(DevStructure const& s, Tile<T> const& tg, TileR<T> const& t,
+                                          blk::TileB<T, 1, true> const& tw, int32_t const* prog, int slot, int n_slot,
+                                          bool active, bool& singular, double& dev, unsigned long long* phase) {
+    constexpr blk::Mode wmode = mode == Mode::newton ? blk::Mode::newton : blk::Mode::linear_init;
     int32_t const* level_ptr = prog;
     int32_t const* task_off = prog + s.n_level + 1;
     long long t0 = clock64();
@@ -303,6 +305,7 @@ __device__ __forceinline__ void sweeps_v2(DevStructure const& s, Tile<T> const& 
         if (active) {
             for (int i = b + slot; i < e; i += n_slot) {
                 int32_t const* rec = prog + task_off[i];
+                if (s.n_wide != 0 && __ldg(s.row_is_wide + rec[0])) continue; // eliminated below by the whole block
                 if (rec[3] >> 24) {
                     singular |= up_tree_row<T, mode>(s, t, rec);
                 } else {
@@ -311,6 +314,9 @@ __device__ __forceinline__ void sweeps_v2(DevStructure const& s, Tile<T> const& 
             }
         }
         __syncthreads();
+        if (s.n_wide != 0)
+            for (int w = __ldg(s.wide_level_ptr + lv); w < __ldg(s.wide_level_ptr + lv + 1); ++w)
+                blk::wide_up_row<T, 1, wmode, true>(s, tw, w, slot, n_slot, active, singular);
         if (phase != nullptr && threadIdx.x == 0) {
             long long const t1 = clock64();
             phase[lv == 0 ? 0 : 1] += (unsigned long long)(t1 - t0);
@@ -367,6 +373,17 @@ template <int T> __global__ void nr_sym_v2_kernel(DevStructure s, DevBatch b, So
     tg.sinj = b.sinj + (size_t)tile * s.n_load_gen * 2 * T + lane;
     tg.usrc = b.usrc + (size_t)tile * s.n_source * 2 * T + lane;
     TileR<T> const t{tg.jac, tg.xvec, tg.pol, tg.u, tg.perm, tg.sinj, tg.usrc};
+    blk::TileB<T, 1, true> tw;
+    tw.jac = tg.jac;
+    tw.xvec = tg.xvec;
+    tw.pol = tg.pol;
+    tw.u = tg.u;
+    tw.perm = tg.perm;
+    tw.sinj = tg.sinj;
+    tw.usrc = tg.usrc;
+    tw.wide_terms = b.wide_terms ? b.wide_terms + (size_t)tile * s.wide_max_upd * 4 * T + lane : nullptr;
+    tw.wide_rhs = b.wide_rhs ? b.wide_rhs + (size_t)tile * s.wide_max_lower * 2 * T + lane : nullptr;
+    tw.wide_sum = b.wide_sum ? b.wide_sum + (size_t)tile * s.wide_max_entries * 2 * T + lane : nullptr;
 
     if (threadIdx.x < T) {
         sh_dev[threadIdx.x] = 0ull;
@@ -382,7 +399,7 @@ template <int T> __global__ void nr_sym_v2_kernel(DevStructure s, DevBatch b, So
     {
         bool singular = false;
         double dev = 0.0;
-        sweeps_v2<T, Mode::linear_init>(s, tg, t, prog, slot, n_slot, !done, singular, dev, phase);
+        sweeps_v2<T, Mode::linear_init>(s, tg, t, tw, prog, slot, n_slot, !done, singular, dev, phase);
         if (singular) sh_singular[lane] = 1;
         __syncthreads();
         if (!done && sh_singular[lane]) {
@@ -402,7 +419,7 @@ template <int T> __global__ void nr_sym_v2_kernel(DevStructure s, DevBatch b, So
         if (!__syncthreads_or(!done)) break;
         bool singular = false;
         double dev = 0.0;
-        sweeps_v2<T, Mode::newton>(s, tg, t, prog, slot, n_slot, !done, singular, dev, phase ? phase + 4 : nullptr);
+        sweeps_v2<T, Mode::newton>(s, tg, t, tw, prog, slot, n_slot, !done, singular, dev, phase ? phase + 4 : nullptr);
         if (!done) {
             if (singular) sh_singular[lane] = 1;
             atomicMax(&sh_dev[lane], (unsigned long long)__double_as_longlong(dev));

@@ -244,6 +244,91 @@ struct RowProgram {
     }
 };
 
+// Wide rows: a row with many lower entries (a hub of a meshed grid: the ring-closing / feeding nodes collect hundreds of
+// children) is a long sequential elimination when one thread owns the row.  For such rows the children are eliminated by all
+// threads of the block together: the L block of every child and its update terms are computed in parallel, and each target
+// entry then subtracts its terms in ascending child order -- the same operations on the same numbers as the row-by-row loop.
+// Children whose own block receives terms from earlier children (fill-in inside the row) are ordered in sub-levels.
+//   table (8 words per wide row): row, n_sub, off_sub_ptr, off_order, off_in_ptr, off_in_idx, n_upd, 0   (offsets into data)
+//   order:   lower-entry positions (entry - row begin) sorted by sub-level; sub_ptr[n_sub + 1] indexes it
+//   in_ptr[n_entries + 1], in_idx: for every entry of the row the indices (update number - first update of the row) of the
+//   terms it receives, ascending (= ascending child)
+struct WideRowPlan {
+    static constexpr Idx min_lower = 24;
+    std::vector<int32_t> level_ptr;  // wide rows per dependency level: [n_level + 1] into table rows
+    std::vector<int32_t> table;      // 8 words per wide row
+    std::vector<int32_t> data;
+    std::vector<uint8_t> is_wide;    // per row
+    int32_t max_upd{}, max_lower{}, max_entries{};
+
+    WideRowPlan(LuPattern const& p, EliminationSchedule const& sch) {
+        Idx const n = p.n_bus;
+        int32_t const n_level = sch.n_level();
+        is_wide.assign(n, 0);
+        level_ptr.assign(n_level + 1, 0);
+        for (int32_t lv = 0; lv != n_level; ++lv) {
+            int32_t const n_rows = sch.level_ptr[lv + 1] - sch.level_ptr[lv];
+            for (int32_t i = sch.level_ptr[lv]; i != sch.level_ptr[lv + 1]; ++i) {
+                Idx const row = sch.level_rows[i];
+                Idx const rb = p.row_indptr_lu[row], re = p.row_indptr_lu[row + 1], dg = p.diag_lu[row];
+                Idx const n_lower = dg - rb;
+                bool const wide = n_lower >= min_lower && (n_rows <= 8 || n_lower >= 128);
+                if (!wide) continue;
+                is_wide[row] = 1;
+                int32_t const upd_base = sch.upd_ptr[rb];
+                int32_t const n_upd = sch.upd_ptr[dg] - upd_base;
+                Idx const n_entries = re - rb;
+                // incoming terms per entry
+                std::vector<std::vector<int32_t>> incoming(n_entries);
+                std::vector<int32_t> src_child(n_upd);
+                for (Idx e = rb; e != dg; ++e)
+                    for (int32_t q = sch.upd_ptr[e]; q != sch.upd_ptr[e + 1]; ++q) {
+                        incoming[sch.upd_a[q] - rb].push_back(q - upd_base);
+                        src_child[q - upd_base] = static_cast<int32_t>(e - rb);
+                    }
+                // sub-levels of the lower entries
+                std::vector<int32_t> depth(n_lower, 0);
+                int32_t n_sub = 1;
+                for (Idx j = 0; j != n_lower; ++j) {
+                    for (int32_t q : incoming[j]) depth[j] = std::max(depth[j], depth[src_child[q]] + 1);
+                    n_sub = std::max(n_sub, depth[j] + 1);
+                }
+                std::vector<int32_t> sub_ptr(n_sub + 1, 0), order(n_lower);
+                for (Idx j = 0; j != n_lower; ++j) ++sub_ptr[depth[j] + 1];
+                for (int32_t d = 0; d != n_sub; ++d) sub_ptr[d + 1] += sub_ptr[d];
+                {
+                    std::vector<int32_t> cursor(sub_ptr.begin(), sub_ptr.end() - 1);
+                    for (Idx j = 0; j != n_lower; ++j) order[cursor[depth[j]]++] = static_cast<int32_t>(j);
+                }
+                table.push_back(static_cast<int32_t>(row));
+                table.push_back(n_sub);
+                table.push_back(static_cast<int32_t>(data.size()));
+                data.insert(data.end(), sub_ptr.begin(), sub_ptr.end());
+                table.push_back(static_cast<int32_t>(data.size()));
+                data.insert(data.end(), order.begin(), order.end());
+                table.push_back(static_cast<int32_t>(data.size()));
+                int32_t run = 0;
+                for (Idx k = 0; k != n_entries; ++k) {
+                    data.push_back(run);
+                    run += static_cast<int32_t>(incoming[k].size());
+                }
+                data.push_back(run);
+                table.push_back(static_cast<int32_t>(data.size()));
+                for (Idx k = 0; k != n_entries; ++k) data.insert(data.end(), incoming[k].begin(), incoming[k].end());
+                table.push_back(n_upd);
+                table.push_back(0);
+                max_upd = std::max(max_upd, n_upd);
+                max_lower = std::max<int32_t>(max_lower, static_cast<int32_t>(n_lower));
+                max_entries = std::max<int32_t>(max_entries, static_cast<int32_t>(n_entries));
+                ++level_ptr[lv + 1];
+            }
+        }
+        for (int32_t lv = 0; lv != n_level; ++lv) level_ptr[lv + 1] += level_ptr[lv];
+        if (data.empty()) data.push_back(0);
+    }
+    int32_t n_wide() const { return static_cast<int32_t>(table.size() / 8); }
+};
+
 // Path programs (radial grids: every row is a tree row).  The elimination tree is cut into PATHS: maximal chains
 // child -> parent in which the parent continues the chain of exactly one non-leaf child (its "carry" child).  One thread
 // walks a whole path with the carried child's factor, U block, permutation and right-hand side in registers, so the

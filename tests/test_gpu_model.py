@@ -109,6 +109,26 @@ def test_asymmetric_other_methods_match_oracle(method):
     _compare_with_oracle(res, ref, n_scn)
 
 
+@pytest.mark.parametrize("sym", [True, False])
+def test_wide_rows_of_the_ringed_benchmark_grid(monkeypatch, sym):
+    """the ringed 1804-bus grid has hub rows with ~400 lower entries that the whole thread block eliminates together
+    (symbolic.hpp WideRowPlan); results must equal the one-thread-per-row elimination bit for bit, and the oracle"""
+    grid = pgm_b200.FictionalGrid(seed=0, has_mv_ring=True, has_lv_ring=True, **pgm_b200.BENCHMARK_OPTION)
+    n_scn = 6
+    update = grid.batch_update(n_scn, seed=3)
+    model = pgm_b200.PowerGridModel(grid.input_data)
+    res = model.calculate_power_flow(symmetric=sym, update_data=update)
+    n_iter = model.n_iter.copy()
+    ref = orc.Model(grid.input_data).calculate(sym=sym, update=update, threading=0)
+    assert ref["n_failed"] == 0 and np.array_equal(n_iter, ref["n_iter"])
+    _compare_with_oracle(res, ref, n_scn)
+    monkeypatch.setenv("PGMB_WIDE", "0")
+    plain = pgm_b200.PowerGridModel(grid.input_data).calculate_power_flow(symmetric=sym, update_data=update)
+    for comp in res:
+        for name in res[comp].dtype.names:
+            assert np.array_equal(res[comp][name], plain[comp][name], equal_nan=True), (comp, name)
+
+
 def test_batch_properties_at_full_size():
     """config 2 at its full size (1000 scenarios): properties that need no oracle run per scenario:
     power balance (sum of node injections == losses), all scenarios converge, scenario order independence."""
