@@ -55,6 +55,11 @@ enum {
 PGMB_API const char* pgmb_last_error(void);
 PGMB_API int pgmb_device_count(void);
 PGMB_API const char* pgmb_version(void);
+/* page-locked host memory for update / output buffers (cudaHostAlloc): with such buffers the model-level batch call overlaps
+ * its transfers with the solver; pageable buffers work too but serialise.  No reference counterpart: the reference's
+ * buffers are plain host memory owned by the caller (dataset.h:173-206) and stay caller-owned here. */
+PGMB_API int pgmb_host_alloc(uint64_t bytes, void** ptr);
+PGMB_API int pgmb_host_free(void* ptr);
 /* number of CUDA kernels this library has launched since it was loaded (evidence that the GPU path ran) */
 PGMB_API uint64_t pgmb_kernel_launch_count(void);
 

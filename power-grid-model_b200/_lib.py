@@ -39,6 +39,8 @@ def lib():
         l.pgmb_last_error.restype = C.c_char_p
         l.pgmb_version.restype = C.c_char_p
         l.pgmb_kernel_launch_count.restype = C.c_uint64
+        l.pgmb_host_alloc.argtypes = [C.c_uint64, C.POINTER(C.c_void_p)]
+        l.pgmb_host_free.argtypes = [C.c_void_p]
         l.pgmb_model_n_math_groups.restype = C.c_int64
         _lib = l
     return _lib
@@ -102,3 +104,32 @@ class OptionsC(C.Structure):
 class GridOptionC(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("n_node_total_specified", "n_mv_feeder", "n_node_per_mv_feeder", "n_lv_feeder",
                                          "n_connection_per_lv_feeder")] + [("has_mv_ring", C.c_int32), ("has_lv_ring", C.c_int32)]
+
+
+class _PinnedBlock:
+    """owner of one cudaHostAlloc block, exposed through the array interface: numpy views keep it alive, the block is
+    released when the last view is garbage-collected"""
+
+    def __init__(self, nbytes):
+        self.ptr = C.c_void_p()
+        check(lib().pgmb_host_alloc(C.c_uint64(nbytes), C.byref(self.ptr)))
+        self.__array_interface__ = {"data": (self.ptr.value, False), "shape": (nbytes,), "typestr": "|u1", "version": 3}
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                lib().pgmb_host_free(self.ptr)
+        except Exception:  # interpreter shutdown
+            pass
+
+
+def pinned_empty(shape, dtype):
+    """numpy array in page-locked host memory (pgmb_host_alloc): update / output buffers of this kind let the batch
+    calculation overlap its PCIe transfers with the solver kernels"""
+    import numpy as np
+
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    if n == 0:
+        return np.empty(shape, dtype)
+    return np.asarray(_PinnedBlock(n)).view(dtype).reshape(shape)

@@ -48,6 +48,22 @@ extern "C" {
 
 const char* pgmb_last_error(void) { return g_last_error.c_str(); }
 const char* pgmb_version(void) { return "pgm_b200 0.1 (reference power-grid-model 1.13 semantics)"; }
+int pgmb_host_alloc(uint64_t bytes, void** ptr) {
+    return guarded([&] {
+        if (ptr == nullptr) throw InvalidArgument("null argument");
+        *ptr = nullptr;
+        if (bytes == 0) return;
+        cudaError_t const e = cudaHostAlloc(ptr, bytes, cudaHostAllocDefault);
+        if (e != cudaSuccess) throw CudaError(std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+    });
+}
+int pgmb_host_free(void* ptr) {
+    return guarded([&] {
+        if (ptr == nullptr) return;
+        cudaError_t const e = cudaFreeHost(ptr);
+        if (e != cudaSuccess) throw CudaError(std::string("cudaFreeHost: ") + cudaGetErrorString(e));
+    });
+}
 uint64_t pgmb_kernel_launch_count(void) { return pgmb::kernel_launch_count(); }
 int pgmb_device_count(void) {
     int n = 0;

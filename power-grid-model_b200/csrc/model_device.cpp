@@ -327,6 +327,16 @@ int64_t Model::run_batch_device(ModelOptions const& opt, UpdateData const& updat
         if (r.host != nullptr && r.count != 0) d.out[r.slot].ensure(static_cast<size_t>(n_scn) * r.count * r.row);
     }
     d.src_res.ensure(static_cast<size_t>(n_scn) * m.n_source() * 4 + 1);
+    // The chunks only overlap when the caller's buffers are page-locked: a copy from / to pageable memory blocks the host
+    // until the chunk's kernels are done, which would run the chunks one after another, each paying the solver's latency.
+    {
+        bool pinned = true;
+        for (Req const& r : reqs)
+            if (r.host != nullptr && r.count != 0) pinned = pinned && is_device_accessible_host(r.host);
+        for (int bfr = 0; bfr != 4; ++bfr)
+            if (ubufs[bfr]->data != nullptr && ubufs[bfr]->n != 0) pinned = pinned && is_device_accessible_host(ubufs[bfr]->data);
+        if (!pinned && std::getenv("PGMB_CHUNKS") == nullptr) n_chunk = 1;
+    }
     PGMB_CUDA(cudaEventRecord(d.fork, st));
 
     for (int c = 0; c != n_chunk; ++c) {
@@ -401,7 +411,6 @@ int64_t Model::run_batch_device(ModelOptions const& opt, UpdateData const& updat
                                                : "Sparse matrix error, possibly singular matrix!") + "\n";
         }
     }
-    (void)is_device_accessible_host;
     return failed;
 }
 

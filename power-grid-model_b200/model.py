@@ -16,6 +16,7 @@ def _buffer(arr):
 class PowerGridModel:
     def __init__(self, input_data: dict, system_frequency: float = 50.0):
         self._keep = {}
+        self._pinned_out = {}
         inp = _lib.InputDataC()
         self._counts = {}
         for c in structs.COMPONENT_ORDER:
@@ -81,10 +82,14 @@ class PowerGridModel:
     # -- calculation ------------------------------------------------------------------------------------------------
     def calculate_power_flow(self, *, symmetric=True, error_tolerance=1e-8, max_iterations=20,
                              calculation_method="newton_raphson", update_data=None, threading=-1,
-                             output_component_types=None, continue_on_batch_error=False, device=0, output_buffers=None):
+                             output_component_types=None, continue_on_batch_error=False, device=0, output_buffers=None,
+                             reuse_output_buffers=False):
         """Same contract as the reference: without ``update_data`` a single calculation returning 1-D arrays, with it a
         batch returning (n_scenarios, n_elements) arrays.  ``threading`` is accepted for signature compatibility; the
-        scenario loop runs on the GPU."""
+        scenario loop runs on the GPU.  ``output_buffers``: caller-owned arrays per component (like the C API; use
+        ``pgm_b200.pinned_empty`` for page-locked ones).  ``reuse_output_buffers=True``: results are written into page-locked
+        arrays owned by the model and reused by the next call with the same shapes (no page faults, transfers overlap the
+        solver) -- copy what must outlive the next calculation."""
         del threading
         if isinstance(calculation_method, str):
             calculation_method = _lib.METHODS[calculation_method]
@@ -106,6 +111,11 @@ class PowerGridModel:
             if output_buffers is not None and c in output_buffers:  # caller-owned (e.g. pinned) buffers, like the C API
                 arr = output_buffers[c]
                 assert arr.dtype == table[c] and arr.shape == (n_scn, self._counts[c]) and arr.flags.c_contiguous
+            elif reuse_output_buffers:
+                key = (c, n_scn, bool(symmetric))
+                if key not in self._pinned_out:
+                    self._pinned_out[key] = _lib.pinned_empty((n_scn, self._counts[c]), table[c])
+                arr = self._pinned_out[key]
             else:
                 arr = np.empty((n_scn, self._counts[c]), dtype=table[c])
             result[c] = arr

@@ -162,3 +162,22 @@ def test_failed_scenarios_are_isolated():
     assert model.status[7] != 0 and (np.delete(model.status, 7) == 0).all()
     keep = np.arange(20) != 7
     assert np.array_equal(res["node"]["u_pu"][keep], good["node"]["u_pu"][keep])
+
+
+def test_pinned_buffers_and_reused_outputs():
+    """page-locked update buffers + model-owned page-locked outputs (the overlapped pipeline) give the same bytes as plain
+    numpy buffers (single chunk)"""
+    grid = pgm_b200.FictionalGrid(seed=0, **pgm_b200.BENCHMARK_OPTION)
+    update = grid.batch_update(300, seed=5)
+    model = pgm_b200.PowerGridModel(grid.input_data)
+    plain = model.calculate_power_flow(update_data=update)
+    pinned = {}
+    for k, v in update.items():
+        pinned[k] = pgm_b200.pinned_empty(v.shape, v.dtype)
+        pinned[k][...] = v
+    first = model.calculate_power_flow(update_data=pinned, reuse_output_buffers=True)
+    for comp in plain:
+        for name in plain[comp].dtype.names:
+            assert np.array_equal(plain[comp][name], first[comp][name], equal_nan=True), (comp, name)
+    again = model.calculate_power_flow(update_data=pinned, reuse_output_buffers=True)
+    assert all(again[c] is first[c] or again[c].ctypes.data == first[c].ctypes.data for c in first)
