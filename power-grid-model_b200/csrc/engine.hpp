@@ -188,6 +188,15 @@ void launch_pack_branch_sym(int tw, DevStructure const& s, DevBatch const& b, De
                             void* out, cudaStream_t st);
 void launch_pack_appliance_sym(int tw, DevStructure const& s, DevBatch const& b, DevModelTables const& m, int force_const_y,
                                int first, int count, double const* src_res, void* out, cudaStream_t st);
+void launch_apply_load_update_asym(int tw, DevStructure const& s, DevBatch const& b, DevModelTables const& m,
+                                   DevUpdateBuffers const& ub, cudaStream_t st);
+void launch_source_result_asym(int tw, DevStructure const& s, DevBatch const& b, int force_const_y, double* out, cudaStream_t st);
+void launch_pack_node_asym(int tw, DevStructure const& s, DevBatch const& b, DevModelTables const& m, int force_const_y,
+                           double const* src_res, void* out, cudaStream_t st);
+void launch_pack_branch_asym(int tw, DevStructure const& s, DevBatch const& b, DevModelTables const& m, int first, int count,
+                             void* out, cudaStream_t st);
+void launch_pack_appliance_asym(int tw, DevStructure const& s, DevBatch const& b, DevModelTables const& m, int force_const_y,
+                                int first, int count, double const* src_res, void* out, cudaStream_t st);
 void launch_nr_block(int phases, int tile_width, DevStructure const& s, DevBatch const& b, SolveOptions const& opt, int n_slot,
                      cudaStream_t st);
 void launch_math_result_asym(int tile_width, DevStructure const& s, DevBatch const& b, int force_const_y, double* out_u,

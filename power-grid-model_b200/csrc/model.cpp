@@ -577,17 +577,15 @@ int64_t Model::calculate_impl(ModelOptions const& opt, UpdateData const* update,
             }
         }
         bool device_done = false;
-        if constexpr (B == 1) {
-            if (!structural && !source_param_change && device_path_eligible(*update)) {
-                prepare_engines<B>();
-                timing[0] += ms_since(t0);
-                int64_t const r = run_batch_device(opt, *update, out, n_iter, status);
-                if (r >= 0) {
-                    failed = r;
-                    device_done = true;
-                }
-                t0 = Clock::now();
+        if (!structural && !source_param_change) prepare_engines<B>(); // the eligibility test looks at the math topology
+        if (!structural && !source_param_change && device_path_eligible(*update)) {
+            timing[0] += ms_since(t0);
+            int64_t const r = run_batch_device(opt, B, *update, out, n_iter, status);
+            if (r >= 0) {
+                failed = r;
+                device_done = true;
             }
+            t0 = Clock::now();
         }
         if (device_done) {
             // results written by the device path

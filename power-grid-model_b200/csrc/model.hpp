@@ -138,7 +138,7 @@ class Model {
     struct DeviceSide;
     std::shared_ptr<DeviceSide> dev_;
     bool device_path_eligible(UpdateData const& update) const;
-    int64_t run_batch_device(ModelOptions const& opt, UpdateData const& update, OutputData const& out, int32_t* n_iter,
+    int64_t run_batch_device(ModelOptions const& opt, int phases, UpdateData const& update, OutputData const& out, int32_t* n_iter,
                              int32_t* status);
     template <int B>
     void write_output(Idx n_scn, Idx first_scenario, OutputData const& out,

@@ -86,10 +86,11 @@ bool Model::device_path_eligible(UpdateData const& u) const {
 }
 
 // returns number of failed scenarios, or -1 when the batch turned out not to be uniform (caller falls back to the host path)
-int64_t Model::run_batch_device(ModelOptions const& opt, UpdateData const& update, OutputData const& out, int32_t* n_iter,
+int64_t Model::run_batch_device(ModelOptions const& opt, int phases, UpdateData const& update, OutputData const& out, int32_t* n_iter,
                                 int32_t* status) {
     auto t0 = Clock::now();
-    Engine& e = *engines_[0].engine[0];
+    bool const sym = phases == 1;
+    Engine& e = *engines_[0].engine[sym ? 0 : 1];
     cudaStream_t const st = e.stream();
     MathTopology const& m = topo_.math[0];
     Idx const n_scn = update.n_scenarios;
@@ -313,20 +314,21 @@ int64_t Model::run_batch_device(ModelOptions const& opt, UpdateData const& updat
         Idx count;
     };
     Req const reqs[9] = {
-        {out.node, 0, sizeof(NodeOutput<1>), nn},
-        {out.line, 1, sizeof(BranchOutput<1>), n_line()},
-        {out.transformer, 2, sizeof(BranchOutput<1>), n_trafo()},
-        {out.shunt, 3, sizeof(ApplianceOutput<1>), static_cast<Idx>(shunt_in_.size())},
-        {out.source, 4, sizeof(ApplianceOutput<1>), static_cast<Idx>(source_in_.size())},
-        {out.sym_gen, 5, sizeof(ApplianceOutput<1>), n_sym_gen_},
-        {out.asym_gen, 6, sizeof(ApplianceOutput<1>), n_asym_gen_},
-        {out.sym_load, 7, sizeof(ApplianceOutput<1>), n_sym_load_},
-        {out.asym_load, 8, sizeof(ApplianceOutput<1>), n_asym_load_},
+        {out.node, 0, sym ? sizeof(NodeOutput<1>) : sizeof(NodeOutput<3>), nn},
+        {out.line, 1, sym ? sizeof(BranchOutput<1>) : sizeof(BranchOutput<3>), n_line()},
+        {out.transformer, 2, sym ? sizeof(BranchOutput<1>) : sizeof(BranchOutput<3>), n_trafo()},
+        {out.shunt, 3, sym ? sizeof(ApplianceOutput<1>) : sizeof(ApplianceOutput<3>), static_cast<Idx>(shunt_in_.size())},
+        {out.source, 4, sym ? sizeof(ApplianceOutput<1>) : sizeof(ApplianceOutput<3>), static_cast<Idx>(source_in_.size())},
+        {out.sym_gen, 5, sym ? sizeof(ApplianceOutput<1>) : sizeof(ApplianceOutput<3>), n_sym_gen_},
+        {out.asym_gen, 6, sym ? sizeof(ApplianceOutput<1>) : sizeof(ApplianceOutput<3>), n_asym_gen_},
+        {out.sym_load, 7, sym ? sizeof(ApplianceOutput<1>) : sizeof(ApplianceOutput<3>), n_sym_load_},
+        {out.asym_load, 8, sym ? sizeof(ApplianceOutput<1>) : sizeof(ApplianceOutput<3>), n_asym_load_},
     };
     for (Req const& r : reqs) {
         if (r.host != nullptr && r.count != 0) d.out[r.slot].ensure(static_cast<size_t>(n_scn) * r.count * r.row);
     }
-    d.src_res.ensure(static_cast<size_t>(n_scn) * m.n_source() * 4 + 1);
+    size_t const src_row = sym ? 4 : 12; // doubles per source result
+    d.src_res.ensure(static_cast<size_t>(n_scn) * m.n_source() * src_row + 1);
     // The chunks only overlap when the caller's buffers are page-locked: a copy from / to pageable memory blocks the host
     // until the chunk's kernels are done, which would run the chunks one after another, each paying the solver's latency.
     {
@@ -355,22 +357,39 @@ int64_t Model::run_batch_device(ModelOptions const& opt, UpdateData const& updat
             ub.data[bfr] = d.upd[bfr].get() + s0 * per;
             ub.n_per_scenario[bfr] = ubufs[bfr]->n;
         }
-        launch_apply_load_update_sym(tw, ds, view, d.t, ub, q);
+        if (sym) {
+            launch_apply_load_update_sym(tw, ds, view, d.t, ub, q);
+        } else {
+            launch_apply_load_update_asym(tw, ds, view, d.t, ub, q);
+        }
         PGMB_CUDA(cudaEventRecord(d.ev_a[c], q));
         e.launch_solve(view, sopt, q);
         PGMB_CUDA(cudaEventRecord(d.ev_b[c], q));
-        double* const src_res = d.src_res.get() + s0 * m.n_source() * 4;
-        launch_source_result_sym(tw, ds, view, force_const_y, src_res, q);
+        double* const src_res = d.src_res.get() + s0 * m.n_source() * src_row;
+        if (sym) {
+            launch_source_result_sym(tw, ds, view, force_const_y, src_res, q);
+        } else {
+            launch_source_result_asym(tw, ds, view, force_const_y, src_res, q);
+        }
         for (Req const& r : reqs) {
             if (r.host == nullptr || r.count == 0) continue;
             void* const dst = d.out[r.slot].get() + static_cast<size_t>(s0) * r.count * r.row;
-            switch (r.slot) {
-            case 0: launch_pack_node_sym(tw, ds, view, d.t, force_const_y, src_res, dst, q); break;
-            case 1: launch_pack_branch_sym(tw, ds, view, d.t, 0, static_cast<int>(n_line()), dst, q); break;
-            case 2: launch_pack_branch_sym(tw, ds, view, d.t, static_cast<int>(n_line()), static_cast<int>(n_trafo()), dst, q); break;
-            default:
-                launch_pack_appliance_sym(tw, ds, view, d.t, force_const_y, static_cast<int>(d.n_app_first[r.slot - 3]),
-                                          static_cast<int>(r.count), src_res, dst, q);
+            int const nl = static_cast<int>(n_line()), nt = static_cast<int>(n_trafo());
+            int const app_first = r.slot >= 3 ? static_cast<int>(d.n_app_first[r.slot - 3]) : 0;
+            if (sym) {
+                switch (r.slot) {
+                case 0: launch_pack_node_sym(tw, ds, view, d.t, force_const_y, src_res, dst, q); break;
+                case 1: launch_pack_branch_sym(tw, ds, view, d.t, 0, nl, dst, q); break;
+                case 2: launch_pack_branch_sym(tw, ds, view, d.t, nl, nt, dst, q); break;
+                default: launch_pack_appliance_sym(tw, ds, view, d.t, force_const_y, app_first, static_cast<int>(r.count), src_res, dst, q);
+                }
+            } else {
+                switch (r.slot) {
+                case 0: launch_pack_node_asym(tw, ds, view, d.t, force_const_y, src_res, dst, q); break;
+                case 1: launch_pack_branch_asym(tw, ds, view, d.t, 0, nl, dst, q); break;
+                case 2: launch_pack_branch_asym(tw, ds, view, d.t, nl, nt, dst, q); break;
+                default: launch_pack_appliance_asym(tw, ds, view, d.t, force_const_y, app_first, static_cast<int>(r.count), src_res, dst, q);
+                }
             }
         }
         PGMB_CUDA(cudaGetLastError());
