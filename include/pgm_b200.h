@@ -176,6 +176,9 @@ typedef struct pgmb_options {
     int64_t max_iter;
     int32_t n_devices;          /* GPUs of this process to shard scenarios over; 0 = all visible */
     int32_t first_device;
+    int32_t threading;          /* host threads for batches whose scenarios change topology / parameters (each thread owns a
+                                 * model copy, job_dispatch.hpp:88-160): -1 or 0 = all cores, n > 0 = n threads, 1 = sequential */
+    int32_t reserved;
 } pgmb_options;
 
 typedef struct pgmb_model pgmb_model;

@@ -98,7 +98,8 @@ class OutputDataC(C.Structure):
 
 class OptionsC(C.Structure):
     _fields_ = [("calculation_method", C.c_int32), ("symmetric", C.c_int32), ("err_tol", C.c_double),
-                ("max_iter", C.c_int64), ("n_devices", C.c_int32), ("first_device", C.c_int32)]
+                ("max_iter", C.c_int64), ("n_devices", C.c_int32), ("first_device", C.c_int32), ("threading", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class GridOptionC(C.Structure):

@@ -45,7 +45,7 @@ int pgmb_model_calculate(pgmb_model* model, const pgmb_options* opt, const pgmb_
     int const rc = guarded([&] {
         if (model == nullptr || opt == nullptr || output == nullptr) throw InvalidArgument("null argument");
         if (opt->max_iter < 0 || opt->max_iter > (int64_t{1} << 30)) throw InvalidArgument("max_iter out of range");
-        ModelOptions const mo{opt->calculation_method, opt->symmetric != 0, opt->err_tol, opt->max_iter, opt->first_device};
+        ModelOptions const mo{opt->calculation_method, opt->symmetric != 0, opt->err_tol, opt->max_iter, opt->first_device, opt->threading};
         OutputData const od{output->node, output->line, output->transformer, output->shunt, output->source,
                             output->sym_gen, output->asym_gen, output->sym_load, output->asym_load};
         if (update != nullptr) {

@@ -1,6 +1,8 @@
 #include "engine.hpp"
 
 #include <atomic>
+#include <map>
+#include <mutex>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -21,6 +23,70 @@ int env_int(char const* name, int fallback) {
     return (v != nullptr && *v != '\0') ? std::atoi(v) : fallback;
 }
 } // namespace
+
+namespace {
+struct PoolState {
+    std::mutex mutex;
+    std::map<std::pair<int, size_t>, std::vector<void*>> free_blocks; // (device, size class) -> blocks
+    size_t free_bytes{0};
+};
+PoolState& pool() {
+    static PoolState* p = new PoolState; // never destroyed: buffers may be released during static destruction
+    return *p;
+}
+constexpr size_t kPoolKeepBytes = size_t{8} << 30;
+} // namespace
+
+void* DevPool::alloc(size_t bytes) {
+    size_t const cls = size_class(bytes);
+    int dev = 0;
+    PGMB_CUDA(cudaGetDevice(&dev));
+    {
+        std::lock_guard<std::mutex> lock(pool().mutex);
+        auto it = pool().free_blocks.find({dev, cls});
+        if (it != pool().free_blocks.end() && !it->second.empty()) {
+            void* p = it->second.back();
+            it->second.pop_back();
+            pool().free_bytes -= cls;
+            return p;
+        }
+    }
+    void* p = nullptr;
+    cudaError_t err = cudaMalloc(&p, cls);
+    if (err != cudaSuccess) {
+        cudaGetLastError();
+        trim();
+        err = cudaMalloc(&p, cls);
+    }
+    if (err != cudaSuccess) throw CudaError(std::string("cudaMalloc of ") + std::to_string(cls) + " bytes failed: " + cudaGetErrorString(err));
+    return p;
+}
+
+void DevPool::release(void* p, size_t bytes) {
+    size_t const cls = size_class(bytes);
+    cudaPointerAttributes attr{};
+    int dev = 0;
+    if (cudaPointerGetAttributes(&attr, p) == cudaSuccess) dev = attr.device;
+    bool too_much = false;
+    {
+        std::lock_guard<std::mutex> lock(pool().mutex);
+        pool().free_blocks[{dev, cls}].push_back(p);
+        pool().free_bytes += cls;
+        too_much = pool().free_bytes > kPoolKeepBytes;
+    }
+    if (too_much) trim();
+}
+
+void DevPool::trim() {
+    std::map<std::pair<int, size_t>, std::vector<void*>> blocks;
+    {
+        std::lock_guard<std::mutex> lock(pool().mutex);
+        blocks.swap(pool().free_blocks);
+        pool().free_bytes = 0;
+    }
+    for (auto& [key, list] : blocks)
+        for (void* p : list) cudaFree(p);
+}
 
 void count_kernel_launch() { g_kernel_launches.fetch_add(1, std::memory_order_relaxed); }
 uint64_t kernel_launch_count() { return g_kernel_launches.load(std::memory_order_relaxed); }
@@ -46,6 +112,7 @@ Engine::Engine(MathTopology topo, bool symmetric, int device)
 Engine::~Engine() {
     if (device_ < 0) return;
     cudaSetDevice(device_);
+    if (stream_ != nullptr) cudaStreamSynchronize(stream_); // the buffers go back to the pool: nothing may still use them
     if (ev0_ != nullptr) cudaEventDestroy(ev0_);
     if (ev1_ != nullptr) cudaEventDestroy(ev1_);
     if (stream_ != nullptr) cudaStreamDestroy(stream_);

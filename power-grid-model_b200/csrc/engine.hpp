@@ -30,6 +30,22 @@ struct InvalidArgument : std::runtime_error {
         }                                                                                                            \
     } while (0)
 
+// Device memory pool: cudaMalloc / cudaFree serialise the whole process (and cudaFree synchronises the device), which hurts
+// when engines are rebuilt per scenario (topology-changing batches, one engine per host thread).  Released blocks are kept in
+// power-of-two size classes and handed out again; the pool is trimmed when it holds too much or an allocation fails.
+// A block must only be released when no work that uses it is in flight (~Engine synchronises its stream first).
+class DevPool {
+  public:
+    static void* alloc(size_t bytes);
+    static void release(void* p, size_t bytes);
+    static void trim();
+    static size_t size_class(size_t bytes) {
+        size_t c = 256;
+        while (c < bytes) c <<= 1;
+        return c;
+    }
+};
+
 // owning device buffer
 template <class T> class DevBuf {
   public:
@@ -52,7 +68,7 @@ template <class T> class DevBuf {
         if (n <= n_) return;
         release();
         if (n == 0) return;
-        PGMB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p_), n * sizeof(T)));
+        p_ = static_cast<T*>(DevPool::alloc(n * sizeof(T)));
         n_ = n;
     }
     void upload(std::vector<T> const& h, cudaStream_t st) {
@@ -64,7 +80,7 @@ template <class T> class DevBuf {
 
   private:
     void release() {
-        if (p_ != nullptr) cudaFree(p_);
+        if (p_ != nullptr) DevPool::release(p_, n_ * sizeof(T));
         p_ = nullptr;
         n_ = 0;
     }

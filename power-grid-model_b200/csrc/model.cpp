@@ -1,5 +1,8 @@
 #include "model.hpp"
 
+#include <exception>
+#include <thread>
+
 #include <cstring>
 
 namespace pgmb {
@@ -602,25 +605,59 @@ int64_t Model::calculate_impl(ModelOptions const& opt, UpdateData const* update,
             timing[0] += ms_since(t0);
             if (n != 0) failed = run_block<B>(opt, n, sinj, uref, out, 0, n_iter, status);
         } else {
-            // general path: scenario by scenario (topology / parameters may change), still on the GPU
-            for (Idx s = 0; s != n; ++s) {
-                Saved saved;
+            // general path: scenario by scenario (topology / parameters may change), still on the GPU.  Like the reference's
+            // job dispatch (job_dispatch.hpp:88-160) the scenarios are spread over host threads, thread t taking scenarios
+            // t, t + n_threads, ...; every thread works on its own copy of the model, whose engines own their CUDA streams,
+            // so the symbolic stage of one scenario overlaps the kernels of the others.
+            Idx n_threads = opt.threading > 0 ? opt.threading : static_cast<Idx>(std::thread::hardware_concurrency());
+            n_threads = std::max<Idx>(1, std::min<Idx>({n_threads, n, Idx{32}}));
+            std::vector<std::string> messages(n);
+            std::vector<int64_t> failed_per_thread(n_threads, 0);
+            std::vector<std::exception_ptr> fatal(n_threads);
+            auto worker = [&](Model& model, Idx t) {
                 try {
-                    apply_scenario(*update, s, &saved);
-                    prepare_engines<B>();
-                    std::vector<std::vector<double>> sinj(topo_.math.size()), uref(topo_.math.size());
-                    gather_pf_input<B>(sinj, uref);
-                    failed += run_block<B>(opt, 1, sinj, uref, out, s, n_iter, status);
-                } catch (CudaError const&) {
-                    restore(saved);
-                    throw;
-                } catch (std::exception const& ex) {
-                    ++failed;
-                    if (status != nullptr) status[s] = 3;
-                    batch_message += "Error in batch #" + std::to_string(s) + ": " + ex.what() + "\n";
+                    for (Idx s = t; s < n; s += n_threads) {
+                        Saved saved;
+                        try {
+                            model.apply_scenario(*update, s, &saved);
+                            model.template prepare_engines<B>();
+                            std::vector<std::vector<double>> sinj(model.topo_.math.size()), uref(model.topo_.math.size());
+                            model.template gather_pf_input<B>(sinj, uref);
+                            failed_per_thread[t] += model.template run_block<B>(opt, 1, sinj, uref, out, s, n_iter, status);
+                            messages[s] = std::move(model.batch_message);
+                            model.batch_message.clear();
+                        } catch (CudaError const&) {
+                            model.restore(saved);
+                            throw;
+                        } catch (std::exception const& ex) {
+                            ++failed_per_thread[t];
+                            if (status != nullptr) status[s] = 3;
+                            messages[s] = "Error in batch #" + std::to_string(s) + ": " + ex.what() + "\n";
+                            model.batch_message.clear();
+                        }
+                        model.restore(saved);
+                    }
+                } catch (...) {
+                    fatal[t] = std::current_exception();
                 }
-                restore(saved);
+            };
+            if (n_threads == 1) {
+                worker(*this, 0);
+            } else {
+                std::vector<std::unique_ptr<Model>> copies;
+                for (Idx t = 0; t != n_threads; ++t) {
+                    copies.push_back(std::make_unique<Model>(*this));
+                    copies.back()->dev_.reset();
+                    copies.back()->batch_message.clear();
+                }
+                std::vector<std::thread> pool;
+                for (Idx t = 0; t != n_threads; ++t) pool.emplace_back(worker, std::ref(*copies[t]), t);
+                for (auto& th : pool) th.join();
             }
+            for (auto const& ex : fatal)
+                if (ex) std::rethrow_exception(ex);
+            for (Idx t = 0; t != n_threads; ++t) failed += failed_per_thread[t];
+            for (Idx s = 0; s != n; ++s) batch_message += messages[s];
         }
     }
     timing[5] = ms_since(t_all);

@@ -40,6 +40,7 @@ struct ModelOptions {
     double err_tol;
     int64_t max_iter;
     int32_t device;
+    int32_t threading{-1}; // structural batches: -1 / 0 = all cores, n > 0 = n host threads
 };
 
 struct BatchFailure : std::runtime_error {
@@ -98,8 +99,17 @@ class Model {
     bool topo_valid_{false};
     bool param_valid_[2]{false, false};
     TopologyResult topo_;
-    struct GroupEngines {
-        std::unique_ptr<Engine> engine[2]; // [sym, asym]
+    struct GroupEngines { // [sym, asym]; a copy of the model starts without engines and builds its own (own CUDA stream)
+        std::unique_ptr<Engine> engine[2];
+        GroupEngines() = default;
+        GroupEngines(GroupEngines const&) {}
+        GroupEngines& operator=(GroupEngines const&) {
+            engine[0].reset();
+            engine[1].reset();
+            return *this;
+        }
+        GroupEngines(GroupEngines&&) = default;
+        GroupEngines& operator=(GroupEngines&&) = default;
     };
     std::vector<GroupEngines> engines_;
     int device_{0};

@@ -59,6 +59,7 @@ struct Model::DeviceSide {
     ~DeviceSide() {
         if (pinned != nullptr) cudaFreeHost(pinned);
         if (streams_ready) {
+            for (auto& q : cs) cudaStreamSynchronize(q); // the buffers go back to the pool: nothing may still use them
             for (auto& q : cs) cudaStreamDestroy(q);
             cudaEventDestroy(fork);
             for (auto& ev : ev_a) cudaEventDestroy(ev);

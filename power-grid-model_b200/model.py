@@ -86,15 +86,16 @@ class PowerGridModel:
                              reuse_output_buffers=False):
         """Same contract as the reference: without ``update_data`` a single calculation returning 1-D arrays, with it a
         batch returning (n_scenarios, n_elements) arrays.  ``threading`` is accepted for signature compatibility; the
-        scenario loop runs on the GPU.  ``output_buffers``: caller-owned arrays per component (like the C API; use
+        scenario loop of load / source-reference batches runs on the GPU whatever ``threading`` says; batches that switch
+        branches or change parameters are dispatched over host threads with one model copy each (``threading``: -1 / 0 = all
+        cores, n = n threads), every copy driving its own GPU stream.  ``output_buffers``: caller-owned arrays per component (like the C API; use
         ``pgm_b200.pinned_empty`` for page-locked ones).  ``reuse_output_buffers=True``: results are written into page-locked
         arrays owned by the model and reused by the next call with the same shapes (no page faults, transfers overlap the
         solver) -- copy what must outlive the next calculation."""
-        del threading
         if isinstance(calculation_method, str):
             calculation_method = _lib.METHODS[calculation_method]
         opt = _lib.OptionsC(int(calculation_method), int(bool(symmetric)), float(error_tolerance), int(max_iterations), 1,
-                            int(device))
+                            int(device), int(threading), 0)
         upd = None
         n_scn = 1
         keep = None

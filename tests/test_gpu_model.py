@@ -181,3 +181,26 @@ def test_pinned_buffers_and_reused_outputs():
             assert np.array_equal(plain[comp][name], first[comp][name], equal_nan=True), (comp, name)
     again = model.calculate_power_flow(update_data=pinned, reuse_output_buffers=True)
     assert all(again[c] is first[c] or again[c].ctypes.data == first[c].ctypes.data for c in first)
+
+
+@pytest.mark.parametrize("threads", [1, 4])
+def test_branch_switching_batch_on_host_threads(threads):
+    """N-1 style batch (config 5 shape): every scenario switches another line off, so every scenario has its own topology.
+    The scenarios are dispatched over host threads with one model copy each (job_dispatch.hpp:88-160); results and
+    per-scenario errors must not depend on the thread count and must equal the oracle's."""
+    grid = pgm_b200.FictionalGrid(seed=0, n_node_total_specified=300, n_connection_per_lv_feeder=5, n_lv_feeder=4, n_node_per_mv_feeder=5,
+                                  n_mv_feeder=3, has_mv_ring=True, has_lv_ring=True)
+    lines = grid.input_data["line"]
+    n_scn = 12
+    upd = pgm_b200.structs.initialize_array("update", "line", (n_scn, 1))
+    upd["id"][:, 0] = lines["id"][np.arange(n_scn) * 7 % len(lines)]
+    upd["from_status"][:, 0] = 0
+    upd["to_status"][:, 0] = 0
+    model = pgm_b200.PowerGridModel(grid.input_data)
+    res = model.calculate_power_flow(update_data={"line": upd}, threading=threads)
+    ref = orc.Model(grid.input_data).calculate(sym=True, update={"line": upd}, threading=0)
+    assert ref["n_failed"] == 0 and np.array_equal(model.n_iter, ref["n_iter"])
+    _compare_with_oracle(res, ref, n_scn)
+    base = model.calculate_power_flow()  # the model itself is untouched by the batch
+    ref0 = orc.Model(grid.input_data).calculate(sym=True)
+    _compare_with_oracle({k: v[None] for k, v in base.items()}, ref0, 1)

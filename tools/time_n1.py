@@ -1,0 +1,41 @@
+"""N-1 batch (one line switched off per scenario): wall time of pgm_b200 against the oracle port (config 5 shape)."""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import pgm_b200
+
+n_scn = int(os.environ.get("N_SCN", "64"))
+sym = os.environ.get("ASYM", "0") != "1"
+nodes = int(os.environ.get("NODES", "1500"))
+opt = dict(pgm_b200.BENCHMARK_OPTION)
+opt["n_node_total_specified"] = nodes
+grid = pgm_b200.FictionalGrid(seed=0, has_mv_ring=True, has_lv_ring=True, **opt)
+lines = grid.input_data["line"]
+rng = np.random.default_rng(0)
+pick = rng.choice(len(lines), n_scn, replace=False)
+upd = pgm_b200.structs.initialize_array("update", "line", (n_scn, 1))
+upd["id"][:, 0] = lines["id"][pick]
+upd["from_status"][:, 0] = 0
+upd["to_status"][:, 0] = 0
+update = {"line": upd}
+model = pgm_b200.PowerGridModel(grid.input_data)
+model.calculate_power_flow(symmetric=sym)
+t0 = time.perf_counter()
+res = model.calculate_power_flow(symmetric=sym, update_data=update, output_component_types=["node"], continue_on_batch_error=True, threading=int(os.environ.get("THREADS", "-1")))
+dt = time.perf_counter() - t0
+print(f"pgm_b200: {n_scn} N-1 scenarios on {len(grid.input_data['node'])} nodes sym={sym}: {1e3 * dt / n_scn:.1f} ms/scenario, failed {int((model.status != 0).sum())}")
+if os.environ.get("ORACLE", "1") == "1":
+    import oracle_lib as orc
+    om = orc.Model(grid.input_data)
+    t0 = time.perf_counter()
+    ref = om.calculate(sym=sym, update=update, threading=0, output_components=["node"])
+    dt = time.perf_counter() - t0
+    print(f"oracle (all cores): {1e3 * dt / n_scn:.1f} ms/scenario; n_iter equal {np.array_equal(ref['n_iter'], model.n_iter)}")
+    ok = model.status == 0
+    print("max |du_pu|", float(np.max(np.abs(res["node"]["u_pu"][ok] - ref["node"]["u_pu"][ok]))))
