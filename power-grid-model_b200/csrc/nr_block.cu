@@ -18,7 +18,15 @@ namespace {
 
 template <int T, int B, Mode mode>
 __device__ void sweeps(DevStructure const& s, TileB<T, B> const& t, int slot, int n_slot, bool active, bool& singular,
-                       double& dev) {
+                       double& dev, unsigned long long* phase) {
+    long long t0 = clock64();
+    auto lap = [&](int k) { // PGMB_DEBUG_PHASES: up level 0 | up wide rows | up other levels | down levels >= 1 | down level 0
+        if (phase != nullptr && threadIdx.x == 0) {
+            long long const t1 = clock64();
+            phase[k] += (unsigned long long)(t1 - t0);
+            t0 = t1;
+        }
+    };
     for (int lv = 0; lv < s.n_level; ++lv) {
         int const b = __ldg(s.level_ptr + lv), e = __ldg(s.level_ptr + lv + 1);
         if (active)
@@ -28,15 +36,18 @@ __device__ void sweeps(DevStructure const& s, TileB<T, B> const& t, int slot, in
                 singular |= up_row<T, B, mode>(s, t, row);
             }
         __syncthreads();
+        lap(lv == 0 ? 0 : 2);
         if (s.n_wide != 0)
             for (int w = __ldg(s.wide_level_ptr + lv); w < __ldg(s.wide_level_ptr + lv + 1); ++w)
                 wide_up_row<T, B, mode, false>(s, t, w, slot, n_slot, active, singular);
+        lap(1);
     }
     for (int lv = s.n_level - 1; lv >= 0; --lv) {
         int const b = __ldg(s.level_ptr + lv), e = __ldg(s.level_ptr + lv + 1);
         if (active)
             for (int i = b + slot; i < e; i += n_slot) dev = fmax(dev, down_row<T, B, mode>(s, t, __ldg(s.level_rows + i)));
         __syncthreads();
+        lap(lv == 0 ? 4 : 3);
     }
 }
 
@@ -63,13 +74,14 @@ template <int T, int B> __global__ void nr_block_kernel(DevStructure s, DevBatch
         sh_singular[threadIdx.x] = 0;
     }
     __syncthreads();
+    unsigned long long* const phase = b.phase_cycles ? b.phase_cycles + tile * 16 : nullptr;
     bool done = !valid;
     int status = kStatusOk, num_iter = 0;
     double max_dev = INFINITY;
     {
         bool singular = false;
         double dev = 0.0;
-        sweeps<T, B, Mode::linear_init>(s, t, slot, n_slot, !done, singular, dev);
+        sweeps<T, B, Mode::linear_init>(s, t, slot, n_slot, !done, singular, dev, phase);
         if (singular) sh_singular[lane] = 1;
         __syncthreads();
         if (!done && sh_singular[lane]) {
@@ -89,7 +101,7 @@ template <int T, int B> __global__ void nr_block_kernel(DevStructure s, DevBatch
         if (!__syncthreads_or(!done)) break;
         bool singular = false;
         double dev = 0.0;
-        sweeps<T, B, Mode::newton>(s, t, slot, n_slot, !done, singular, dev);
+        sweeps<T, B, Mode::newton>(s, t, slot, n_slot, !done, singular, dev, phase ? phase + 8 : nullptr);
         if (!done) {
             if (singular) sh_singular[lane] = 1;
             atomicMax(&sh_dev[lane], (unsigned long long)__double_as_longlong(dev));
