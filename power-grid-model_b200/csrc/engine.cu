@@ -342,12 +342,6 @@ void Engine::stage_device(int64_t n, double const* source_u_ref, bool source_is_
     PGMB_CUDA(cudaStreamSynchronize(stream_)); // source_u_ref may be a temporary of the caller
 }
 
-void Engine::apply_load_updates(DevModelTables const& m, DevUpdateBuffers const& ub) {
-    PGMB_CUDA(cudaSetDevice(device_));
-    launch_apply_load_update_sym(tile_width_, ds_, db_, m, ub, stream_);
-    PGMB_CUDA(cudaGetLastError());
-}
-
 void Engine::fetch_status(int32_t* status, int32_t* n_iter) {
     PGMB_CUDA(cudaSetDevice(device_));
     if (db_.n_scn == 0) return;

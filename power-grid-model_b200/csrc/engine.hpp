@@ -112,9 +112,8 @@ class Engine {
 
     void stage(PfInputView const& in);                      // H2D + layout conversion
     // device path of the model level: allocate the batch, upload per-scenario source references; load injections are then
-    // produced on the device by apply_load_updates()
+    // produced on the device by the apply_load_update kernels (model_device.cpp)
     void stage_device(int64_t n_scn, double const* source_u_ref, bool source_is_shared);
-    void apply_load_updates(DevModelTables const& m, DevUpdateBuffers const& ub);
     void fetch_status(int32_t* status, int32_t* n_iter);
     float solve_staged(SolveOptions const& opt);            // kernels only; returns solver-kernel milliseconds
     // pipelined use (model device path): a view of the staged batch restricted to tiles [tile_begin, tile_end), and the solver
@@ -228,8 +227,6 @@ void launch_ic_iterate_sym(int tw, DevStructure const& s, DevBatch const& b, Sol
                            int const* flag, int n_slot, cudaStream_t st);
 void launch_to_tile(int tile_width, double const* src, double* dst, int64_t n_scn, int n_item, int n_comp, int shared_src,
                     cudaStream_t st);
-void launch_from_tile(int tile_width, double const* src, double* dst, int64_t n_scn, int n_item, int n_comp,
-                      cudaStream_t st);
 void launch_math_result_sym(int tile_width, DevStructure const& s, DevBatch const& b, int force_const_y, double* out_u,
                             double* out_inj, double* out_branch, double* out_source, double* out_shunt, double* out_lg,
                             cudaStream_t st);

@@ -158,18 +158,6 @@ __global__ void to_tile_kernel(double const* __restrict__ src, double* __restric
 }
 
 // [tile][item][comp][T] -> [scn][item][comp]
-template <int T>
-__global__ void from_tile_kernel(double const* __restrict__ src, double* __restrict__ dst, int64_t n_scn, int n_item,
-                                 int n_comp) {
-    int64_t const idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; // over host-layout elements
-    int64_t const per_scn = (int64_t)n_item * n_comp;
-    if (idx >= per_scn * n_scn) return;
-    int64_t const scn = idx / per_scn;
-    int64_t const ic = idx % per_scn;
-    int64_t const tile = scn / T;
-    int const lane = scn % T;
-    dst[idx] = src[(tile * per_scn + ic) * T + lane];
-}
 
 // ---- host launchers ----------------------------------------------------------------------------------------------
 template <int T>
@@ -204,19 +192,5 @@ void launch_to_tile(int tile_width, double const* src, double* dst, int64_t n_sc
     }
 }
 
-void launch_from_tile(int tile_width, double const* src, double* dst, int64_t n_scn, int n_item, int n_comp,
-                      cudaStream_t st) {
-    count_kernel_launch();
-    int64_t const total = n_scn * n_item * n_comp;
-    if (total == 0) return;
-    int const block = 256;
-    unsigned const grid = (unsigned)((total + block - 1) / block);
-    switch (tile_width) {
-    case 4: from_tile_kernel<4><<<grid, block, 0, st>>>(src, dst, n_scn, n_item, n_comp); break;
-    case 8: from_tile_kernel<8><<<grid, block, 0, st>>>(src, dst, n_scn, n_item, n_comp); break;
-    case 16: from_tile_kernel<16><<<grid, block, 0, st>>>(src, dst, n_scn, n_item, n_comp); break;
-    default: from_tile_kernel<32><<<grid, block, 0, st>>>(src, dst, n_scn, n_item, n_comp); break;
-    }
-}
 
 } // namespace pgmb

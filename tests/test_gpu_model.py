@@ -204,3 +204,46 @@ def test_branch_switching_batch_on_host_threads(threads):
     base = model.calculate_power_flow()  # the model itself is untouched by the batch
     ref0 = orc.Model(grid.input_data).calculate(sym=True)
     _compare_with_oracle({k: v[None] for k, v in base.items()}, ref0, 1)
+
+
+def test_config3_properties_at_full_size():
+    """BASELINE config 3 at its full size (ringed grid, asymmetric NR, 1000 scenarios): every scenario converges, the
+    three-phase power balance closes (sum of node injections = branch losses + shunt consumption per phase), a sample of
+    scenarios equals the oracle, and the reversed batch gives the reversed results bit for bit."""
+    grid = pgm_b200.FictionalGrid(seed=0, has_mv_ring=True, has_lv_ring=True, **pgm_b200.BENCHMARK_OPTION)
+    update = grid.batch_update(1000, seed=0)
+    model = pgm_b200.PowerGridModel(grid.input_data)
+    res = model.calculate_power_flow(symmetric=False, update_data=update)
+    assert (model.status == 0).all() and 1 <= model.n_iter.min() and model.n_iter.max() <= 20
+    loss = sum(res[c][k].sum(1) for c in ("line", "transformer") for k in ("p_from", "p_to"))  # (n_scn, 3)
+    assert (loss.sum(1) > 0).all()
+    balance = res["node"]["p"].sum(1) - loss - res["shunt"]["p"].sum(1)
+    assert np.max(np.abs(balance)) / np.max(np.abs(res["source"]["p"])) < 1e-6
+    pick = [0, 333, 999]
+    sample = {k: np.ascontiguousarray(v[pick]) for k, v in update.items()}
+    ref = orc.Model(grid.input_data).calculate(sym=False, update=sample, threading=0)
+    assert np.array_equal(model.n_iter[pick], ref["n_iter"])
+    _compare_with_oracle({k: v[pick] for k, v in res.items()}, ref, len(pick))
+    rev = {k: np.ascontiguousarray(v[::-1]) for k, v in update.items()}
+    res_rev = model.calculate_power_flow(symmetric=False, update_data=rev, output_component_types=["node"])
+    assert np.array_equal(res_rev["node"]["u_pu"][::-1], res["node"]["u_pu"])
+
+
+@pytest.mark.parametrize("method", ["iterative_current", "linear"])
+def test_config4_properties_at_large_batch(method):
+    """BASELINE config 4 shape (radial grid, iterative current / linear, a large time series): all scenarios converge, a
+    sample equals the oracle (iteration counts included), chunked and unchunked execution agree bit for bit"""
+    grid = pgm_b200.FictionalGrid(seed=0, **pgm_b200.BENCHMARK_OPTION)
+    n_scn = 4000
+    update = grid.batch_update(n_scn, seed=4)
+    model = pgm_b200.PowerGridModel(grid.input_data)
+    res = model.calculate_power_flow(update_data=update, calculation_method=method, output_component_types=["node", "source"])
+    assert (model.status == 0).all()
+    pick = [0, 1777, 3999]
+    sample = {k: np.ascontiguousarray(v[pick]) for k, v in update.items()}
+    ref = orc.Model(grid.input_data).calculate(sym=True, update=sample, threading=0, method=method, output_components=["node", "source"])
+    assert np.array_equal(model.n_iter[pick], ref["n_iter"])
+    _compare_with_oracle({k: v[pick] for k, v in res.items()}, ref, len(pick))
+    head = {k: np.ascontiguousarray(v[:500]) for k, v in update.items()}
+    part = model.calculate_power_flow(update_data=head, calculation_method=method, output_component_types=["node"])
+    assert np.array_equal(part["node"]["u_pu"], res["node"]["u_pu"][:500])
