@@ -247,3 +247,21 @@ def test_config4_properties_at_large_batch(method):
     head = {k: np.ascontiguousarray(v[:500]) for k, v in update.items()}
     part = model.calculate_power_flow(update_data=head, calculation_method=method, output_component_types=["node"])
     assert np.array_equal(part["node"]["u_pu"], res["node"]["u_pu"][:500])
+
+
+@pytest.mark.parametrize("sym,n_scn", [(True, 16), (False, 4)])
+def test_50k_node_ringed_grid_matches_oracle(sym, n_scn):
+    """the grid of BASELINE config 5 (53 068 nodes, MV and LV rings, 26 628 fill-ins, wide hub rows): load-profile batch
+    against the oracle -- index arithmetic and scratch sizing at scale"""
+    opt = dict(pgm_b200.BENCHMARK_OPTION)
+    opt["n_node_total_specified"] = 50000
+    grid = pgm_b200.FictionalGrid(seed=0, has_mv_ring=True, has_lv_ring=True, **opt)
+    update = grid.batch_update(n_scn, seed=1)
+    model = pgm_b200.PowerGridModel(grid.input_data)
+    res = model.calculate_power_flow(symmetric=sym, update_data=update, output_component_types=["node", "line", "source"])
+    assert (model.status == 0).all()
+    pick = [0, n_scn - 1]
+    sample = {k: np.ascontiguousarray(v[pick]) for k, v in update.items()}
+    ref = orc.Model(grid.input_data).calculate(sym=sym, update=sample, threading=0, output_components=["node", "line", "source"])
+    assert np.array_equal(model.n_iter[pick], ref["n_iter"])
+    _compare_with_oracle({k: v[pick] for k, v in res.items()}, ref, len(pick))
