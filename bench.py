@@ -245,7 +245,7 @@ def main():
         cpu_model.calculate(sym=True, update=cpu_update, threading=0)
         reps = 0
         t0 = time.perf_counter()
-        while time.perf_counter() - t0 < 10.0 and reps < 50:
+        while time.perf_counter() - t0 < 10.0 and reps < 1000:
             cpu_model.calculate(sym=True, update=cpu_update, threading=0, err_tol=ERR_TOL, max_iter=MAX_ITER)
             reps += 1
         cpu_value = sample * reps / (time.perf_counter() - t0)
