@@ -150,6 +150,8 @@ class Model {
     bool device_path_eligible(UpdateData const& update) const;
     int64_t run_batch_device(ModelOptions const& opt, int phases, UpdateData const& update, OutputData const& out, int32_t* n_iter,
                              int32_t* status);
+    int64_t run_batch_device_part(ModelOptions const& opt, int phases, UpdateData const& update, OutputData const& out,
+                                  int32_t* n_iter, int32_t* status, Idx first_scenario);
     template <int B>
     void write_output(Idx n_scn, Idx first_scenario, OutputData const& out,
                       std::vector<std::vector<double>> const (&so)[6]) const;

@@ -87,8 +87,76 @@ bool Model::device_path_eligible(UpdateData const& u) const {
 }
 
 // returns number of failed scenarios, or -1 when the batch turned out not to be uniform (caller falls back to the host path)
+// A batch whose working set would not fit the device is cut into parts that are run one after another; the parts see
+// offset views of the caller's update / output buffers.
 int64_t Model::run_batch_device(ModelOptions const& opt, int phases, UpdateData const& update, OutputData const& out, int32_t* n_iter,
                                 int32_t* status) {
+    bool const sym = phases == 1;
+    Engine& e = *engines_[0].engine[sym ? 0 : 1];
+    MathTopology const& m = topo_.math[0];
+    size_t const N = 2 * static_cast<size_t>(phases);
+    size_t const row_node = sym ? sizeof(NodeOutput<1>) : sizeof(NodeOutput<3>);
+    size_t const row_branch = sym ? sizeof(BranchOutput<1>) : sizeof(BranchOutput<3>);
+    size_t const row_app = sym ? sizeof(ApplianceOutput<1>) : sizeof(ApplianceOutput<3>);
+    struct Part {
+        void* const* host;
+        size_t row;
+        Idx count;
+    };
+    Part const outs[9] = {{&out.node, row_node, static_cast<Idx>(node_.size())},
+                          {&out.line, row_branch, n_line()},
+                          {&out.transformer, row_branch, n_trafo()},
+                          {&out.shunt, row_app, static_cast<Idx>(shunt_in_.size())},
+                          {&out.source, row_app, static_cast<Idx>(source_in_.size())},
+                          {&out.sym_gen, row_app, n_sym_gen_},
+                          {&out.asym_gen, row_app, n_asym_gen_},
+                          {&out.sym_load, row_app, n_sym_load_},
+                          {&out.asym_load, row_app, n_asym_load_}};
+    ComponentBuffer const* ubufs[4] = {&update.sym_gen, &update.asym_gen, &update.sym_load, &update.asym_load};
+    size_t const urow[4] = {sizeof(SymLoadGenUpdate), sizeof(AsymLoadGenUpdate), sizeof(SymLoadGenUpdate), sizeof(AsymLoadGenUpdate)};
+    size_t per_scn = static_cast<size_t>(e.pattern().nnz_lu) * N * N * 8 + 6 * static_cast<size_t>(m.n_bus) * N * 8 +
+                     static_cast<size_t>(m.n_load_gen()) * (N * 8 + 1) +
+                     (static_cast<size_t>(e.wide_plan().max_upd) * N * N + static_cast<size_t>(e.wide_plan().max_lower + e.wide_plan().max_entries) * N) * 8;
+    for (Part const& o : outs)
+        if (*o.host != nullptr) per_scn += o.row * static_cast<size_t>(o.count);
+    for (int b = 0; b != 4; ++b)
+        if (ubufs[b]->data != nullptr) per_scn += urow[b] * static_cast<size_t>(ubufs[b]->n);
+    size_t free_b = 0, total_b = 0;
+    PGMB_CUDA(cudaSetDevice(e.device()));
+    PGMB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    size_t budget = total_b / 10 * 6; // the pool may hold freed blocks, so the total is the better yardstick
+    if (char const* env = std::getenv("PGMB_MAX_BATCH_BYTES")) budget = static_cast<size_t>(std::atoll(env));
+    Idx const n_scn = update.n_scenarios;
+    Idx max_scn = static_cast<Idx>(std::max<size_t>(32, budget / per_scn / 32 * 32));
+    if (n_scn <= max_scn) return run_batch_device_part(opt, phases, update, out, n_iter, status, 0);
+    int64_t failed = 0;
+    for (Idx s0 = 0; s0 < n_scn; s0 += max_scn) {
+        Idx const ns = std::min(max_scn, n_scn - s0);
+        UpdateData u = update;
+        u.n_scenarios = ns;
+        ComponentBuffer* ub[4] = {&u.sym_gen, &u.asym_gen, &u.sym_load, &u.asym_load};
+        for (int b = 0; b != 4; ++b)
+            if (ub[b]->data != nullptr) ub[b]->data = static_cast<unsigned char const*>(ub[b]->data) + static_cast<size_t>(s0) * ub[b]->n * urow[b];
+        if (u.source.data != nullptr) {
+            if (u.source.indptr != nullptr) {
+                u.source.indptr += s0; // sparse: scenario s of the part is scenario s0 + s of the caller's index pointer
+            } else {
+                u.source.data = static_cast<unsigned char const*>(u.source.data) + static_cast<size_t>(s0) * u.source.n * sizeof(SourceUpdate);
+            }
+        }
+        OutputData o = out;
+        void** ohost[9] = {&o.node, &o.line, &o.transformer, &o.shunt, &o.source, &o.sym_gen, &o.asym_gen, &o.sym_load, &o.asym_load};
+        for (int k = 0; k != 9; ++k)
+            if (*ohost[k] != nullptr) *ohost[k] = static_cast<unsigned char*>(*ohost[k]) + static_cast<size_t>(s0) * outs[k].count * outs[k].row;
+        int64_t const r = run_batch_device_part(opt, phases, u, o, n_iter ? n_iter + s0 : nullptr, status ? status + s0 : nullptr, s0);
+        if (r < 0) return -1;
+        failed += r;
+    }
+    return failed;
+}
+
+int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, UpdateData const& update, OutputData const& out,
+                                     int32_t* n_iter, int32_t* status, Idx first_scenario) {
     auto t0 = Clock::now();
     bool const sym = phases == 1;
     Engine& e = *engines_[0].engine[sym ? 0 : 1];
@@ -426,7 +494,7 @@ int64_t Model::run_batch_device(ModelOptions const& opt, int phases, UpdateData 
         if (status != nullptr) status[s] = st_local[s];
         if (st_local[s] != 0) {
             ++failed;
-            batch_message += "Error in batch #" + std::to_string(s) + ": " +
+            batch_message += "Error in batch #" + std::to_string(first_scenario + s) + ": " +
                              (st_local[s] == 1 ? "Iteration failed to converge after " + std::to_string(opt.max_iter) + " iterations!"
                                                : "Sparse matrix error, possibly singular matrix!") + "\n";
         }

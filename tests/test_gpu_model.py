@@ -265,3 +265,27 @@ def test_50k_node_ringed_grid_matches_oracle(sym, n_scn):
     ref = orc.Model(grid.input_data).calculate(sym=sym, update=sample, threading=0, output_components=["node", "line", "source"])
     assert np.array_equal(model.n_iter[pick], ref["n_iter"])
     _compare_with_oracle({k: v[pick] for k, v in res.items()}, ref, len(pick))
+
+
+def test_batch_larger_than_the_memory_budget_is_split(monkeypatch):
+    """a batch whose working set exceeds the device budget runs in parts over offset views of the caller's buffers"""
+    grid = pgm_b200.FictionalGrid(seed=0, n_node_total_specified=300, n_connection_per_lv_feeder=5, n_lv_feeder=4, n_node_per_mv_feeder=5,
+                                  n_mv_feeder=3)
+    update = grid.batch_update(150, seed=6)
+    src = pgm_b200.structs.initialize_array("update", "source", (150, 1))
+    src["id"][:, 0] = grid.input_data["source"]["id"][0]
+    src["u_ref"][:, 0] = 1.0 + 0.0002 * np.arange(150)
+    update["source"] = src
+    model = pgm_b200.PowerGridModel(grid.input_data)
+    whole = model.calculate_power_flow(update_data=update)
+    monkeypatch.setenv("PGMB_MAX_BATCH_BYTES", "4000000")  # ~ 64 scenarios per part
+    model2 = pgm_b200.PowerGridModel(grid.input_data)
+    parts = model2.calculate_power_flow(update_data=update)
+    assert np.array_equal(model.n_iter, model2.n_iter)
+    for comp in whole:
+        for name in whole[comp].dtype.names:
+            assert np.array_equal(whole[comp][name], parts[comp][name], equal_nan=True), (comp, name)
+    update["sym_load"]["p_specified"][101] *= 1e6  # the failing scenario keeps its batch position in the message
+    with pytest.raises(pgm_b200.BatchError) as e:
+        model2.calculate_power_flow(update_data=update)
+    assert "Error in batch #101" in str(e.value)
