@@ -174,8 +174,9 @@ typedef struct pgmb_options {
     int32_t symmetric;          /* 1 symmetric, 0 asymmetric */
     double err_tol;
     int64_t max_iter;
-    int32_t n_devices;          /* GPUs of this process to shard scenarios over; 0 = all visible */
-    int32_t first_device;
+    int32_t n_devices;          /* reserved, 0 or 1: a process drives ONE device; scenarios are sharded over GPUs by running
+                                 * one process per GPU (bench.py under torchrun, pgm_b200.distributed) */
+    int32_t first_device;       /* CUDA device ordinal of this process */
     int32_t threading;          /* host threads for batches whose scenarios change topology / parameters (each thread owns a
                                  * model copy, job_dispatch.hpp:88-160): -1 or 0 = all cores, n > 0 = n threads, 1 = sequential */
     int32_t reserved;
