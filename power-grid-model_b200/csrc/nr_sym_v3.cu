@@ -524,13 +524,51 @@ __device__ __forceinline__ void sweeps_v3(DevStructure const& s, TileP<T> const&
             t0 = t1;
         }
     };
+    // the voltages / loads of the row this thread builds next are pulled into L1 while the current row is computed
+    auto prefetch_row_inputs = [&](int32_t const* rec, int n_lower, int32_t const* lower) {
+        int const row = rec[0];
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(t.u + (size_t)(row * 2) * T));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(t.u + (size_t)(row * 2 + 1) * T));
+        if constexpr (mode == Mode::newton) asm volatile("prefetch.global.L1 [%0];" ::"l"(t.pol + (size_t)(row * 2 + 1) * T));
+        if (rec[4] >= 0) {
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(t.u + (size_t)(rec[4] * 2) * T));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(t.u + (size_t)(rec[4] * 2 + 1) * T));
+        }
+        int const lg0 = rec[6] & 0xffffff, n_lg = (rec[6] >> 24) & 0x7f;
+        for (int lg = lg0; lg < lg0 + n_lg; ++lg) {
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(t.sinj + (size_t)(lg * 2) * T));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(t.sinj + (size_t)(lg * 2 + 1) * T));
+        }
+        for (int e = 0; e < n_lower; ++e) {
+            int const c = lower[4 * e];
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(t.u + (size_t)(c * 2) * T));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(t.u + (size_t)(c * 2 + 1) * T));
+            int const kind = (lower[4 * e + 3] >> 28) & 3;
+            if (kind == 0 || kind == 2) { // leaf child: its factor, U block, permutation and rhs are read when the row is built
+                prefetch_blk<T>(t.jac, lower[4 * e + 2]);
+                prefetch_blk<T>(t.jac, lower[4 * e + 3] & 0x0fffffff);
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(t.perm + (size_t)c * T));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(t.xvec + (size_t)(c * 2) * T));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(t.xvec + (size_t)(c * 2 + 1) * T));
+            }
+        }
+    };
     if (active) {
-        for (int i = slot; i < n_leaf; i += n_slot) singular |= build_leaf<T, mode>(s, t, leaf + 8 * i);
+        for (int i = slot; i < n_leaf; i += n_slot) {
+            if (i + n_slot < n_leaf) prefetch_row_inputs(leaf + 8 * (i + n_slot), 0, nullptr);
+            singular |= build_leaf<T, mode>(s, t, leaf + 8 * i);
+        }
     }
     __syncthreads();
     lap(0);
     if (active) {
-        for (int i = slot; i < n_rec; i += n_slot) build_inner<T, mode>(s, t, prog + rec_off[i]);
+        for (int i = slot; i < n_rec; i += n_slot) {
+            if (i + n_slot < n_rec) {
+                int32_t const* nx = prog + rec_off[i + n_slot];
+                prefetch_row_inputs(nx, nx[8] & 0xfff, nx + 9);
+            }
+            build_inner<T, mode>(s, t, prog + rec_off[i]);
+        }
     }
     __syncthreads();
     lap(1);
@@ -555,6 +593,14 @@ __device__ __forceinline__ void sweeps_v3(DevStructure const& s, TileP<T> const&
     if (active) {
         for (int i = slot; i < n_leaf; i += n_slot) {
             int32_t const* rec = leaf + 8 * i;
+            if (i + n_slot < n_leaf) {
+                int32_t const* nx = leaf + 8 * (i + n_slot);
+                prefetch_down<T, mode>(t, make_int4(nx[0], nx[1], nx[3], 0));
+                if (nx[3] >= 0) {
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(t.xvec + (size_t)(nx[4] * 2) * T));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(t.xvec + (size_t)(nx[4] * 2 + 1) * T));
+                }
+            }
             DownOperands const o = fetch_down<T, mode>(t, rec);
             double x0 = 0.0, x1 = 0.0;
             bool const has_parent = rec[3] >= 0;
