@@ -192,6 +192,7 @@ void Engine::upload_structure() {
     ds_.wide_max_entries = wide_plan_.max_entries;
     ds_.path_prog = path_program_.valid ? d_path_prog_.get() : nullptr;
     ds_.path_prog_words = path_program_.valid ? static_cast<int32_t>(path_program_.words.size()) : 0;
+    ds_.path_prog_smem_words = path_program_.valid ? path_program_.smem_words : 0;
 }
 
 // YBus::update_admittance_entries (y_bus.hpp:400-431): sum of the contributions of each entry, in element order

@@ -54,6 +54,7 @@ struct DevStructure {
     // path programs (symbolic.hpp PathProgram) for radial grids; null when the grid has a cyclic core
     int32_t const* path_prog;
     int32_t path_prog_words;
+    int32_t path_prog_smem_words; // prefix of the path program that the kernel stages in shared memory
 };
 
 // per-batch device buffers, tile layout (see above); B = phases, N = 2B

@@ -14,6 +14,9 @@
 
 #include <cuda_runtime.h>
 
+#ifndef V3_CHAIN_AHEAD
+#define V3_CHAIN_AHEAD 2
+#endif
 #ifndef V3_THREADS
 #define V3_THREADS 512
 #endif
@@ -23,6 +26,8 @@ namespace pgmb {
 using namespace nrsym;
 
 namespace {
+
+constexpr int kChainAhead = V3_CHAIN_AHEAD; // rows whose operands are pulled into L1 ahead of the chain step that uses them
 
 __device__ __forceinline__ uint32_t smem_u32(void const* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
@@ -345,7 +350,7 @@ __device__ __forceinline__ bool up_path(TileP<T> const& t, int32_t const* __rest
     int4 n0 = chain[2 * first_rec], n1 = chain[2 * first_rec + 1];
     Blk a_next = n0.w >= 0 ? t.load_blk(n0.w) : Blk{0.0, 0.0, 0.0, 0.0};
     Blk d_next = t.load_blk(n0.y);
-    if (n_rows > 1) prefetch_row<T>(t, chain[2 * first_rec + 2], chain[2 * first_rec + 3]);
+    for (int k = 1; k < kChainAhead && k < n_rows; ++k) prefetch_row<T>(t, chain[2 * (first_rec + k)], chain[2 * (first_rec + k) + 1]);
     for (int i = 0; i < n_rows; ++i) {
         int4 const c0 = n0, c1 = n1;
         Blk const a_carry = a_next;
@@ -366,7 +371,7 @@ __device__ __forceinline__ bool up_path(TileP<T> const& t, int32_t const* __rest
             n1 = chain[2 * (first_rec + i + 1) + 1];
             a_next = n0.w >= 0 ? t.load_blk(n0.w) : Blk{0.0, 0.0, 0.0, 0.0};
             d_next = t.load_blk(n0.y);
-            if (i + 2 < n_rows) prefetch_row<T>(t, chain[2 * (first_rec + i + 2)], chain[2 * (first_rec + i + 2) + 1]);
+            if (i + kChainAhead < n_rows) prefetch_row<T>(t, chain[2 * (first_rec + i + kChainAhead)], chain[2 * (first_rec + i + kChainAhead) + 1]);
         }
         if (pattern >= 2) { // carry child, then (pattern 3) the precomputed leaf term
             eliminate(d, acc0, acc1, a_carry, c_piv, c_uc, c_y0, c_y1, c_q);
@@ -492,14 +497,14 @@ __device__ __forceinline__ double down_path(TileP<T> const& t, int4 const* __res
         x0 = t.xvec[(size_t)(j_top * 2) * T];
         x1 = t.xvec[(size_t)(j_top * 2 + 1) * T];
     }
-    if (n_rows > 1) prefetch_down<T, mode>(t, chain[2 * (first_rec + n_rows - 2)]);
+    for (int k = 2; k <= kChainAhead && k <= n_rows; ++k) prefetch_down<T, mode>(t, chain[2 * (first_rec + n_rows - k)]);
     for (int i = n_rows - 1; i >= 0; --i) {
         DownOperands const o = next;
         int const row = c0.x;
         if (i > 0) {
             c0 = chain[2 * (first_rec + i - 1)];
             next = fetch_down_k<T, mode>(t, c0.x, c0.y, c0.z);
-            if (i > 1) prefetch_down<T, mode>(t, chain[2 * (first_rec + i - 2)]);
+            if (i >= kChainAhead) prefetch_down<T, mode>(t, chain[2 * (first_rec + i - kChainAhead)]);
         }
         dev = fmax(dev, down_step<T, mode>(t, row, has_parent, o, x0, x1));
         has_parent = true;
@@ -510,9 +515,10 @@ __device__ __forceinline__ double down_path(TileP<T> const& t, int4 const* __res
 template <int T, Mode mode>
 __device__ __forceinline__ void sweeps_v3(DevStructure const& s, TileP<T> const& t, int32_t const* __restrict__ prog, int slot,
                                           int n_slot, bool active, bool& singular, double& dev, unsigned long long* phase) {
+    int32_t const* __restrict__ const recs = s.path_prog; // leaf / row records: global memory
     int const n_leaf = prog[0], n_rec = prog[1], n_stage = prog[2];
-    int32_t const* __restrict__ leaf = prog + prog[3];
-    int32_t const* __restrict__ rec_off = prog + prog[4];
+    int32_t const* __restrict__ leaf = recs + prog[3];
+    int32_t const* __restrict__ rec_off = recs + prog[4];
     int32_t const* __restrict__ stage_ptr = prog + prog[5];
     int32_t const* __restrict__ path = prog + prog[6];
     int4 const* __restrict__ chain = reinterpret_cast<int4 const*>(prog + prog[8]);
@@ -564,10 +570,10 @@ __device__ __forceinline__ void sweeps_v3(DevStructure const& s, TileP<T> const&
     if (active) {
         for (int i = slot; i < n_rec; i += n_slot) {
             if (i + n_slot < n_rec) {
-                int32_t const* nx = prog + rec_off[i + n_slot];
+                int32_t const* nx = recs + rec_off[i + n_slot];
                 prefetch_row_inputs(nx, nx[8] & 0xfff, nx + 9);
             }
-            build_inner<T, mode>(s, t, prog + rec_off[i]);
+            build_inner<T, mode>(s, t, recs + rec_off[i]);
         }
     }
     __syncthreads();
@@ -575,7 +581,7 @@ __device__ __forceinline__ void sweeps_v3(DevStructure const& s, TileP<T> const&
     for (int st = 1; st < n_stage; ++st) {
         if (active) {
             for (int p = stage_ptr[st - 1] + slot; p < stage_ptr[st]; p += n_slot) {
-                singular |= up_path<T>(t, prog, chain, path[2 * p], path[2 * p + 1]);
+                singular |= up_path<T>(t, recs, chain, path[2 * p], path[2 * p + 1]);
             }
         }
         __syncthreads();
@@ -630,8 +636,9 @@ template <int T, bool SMEM> __global__ void __launch_bounds__(V3_THREADS, 1) nr_
     int64_t const scn = (int64_t)tile * T + lane;
     bool const valid = scn < b.n_scn;
 
-    if constexpr (SMEM) stage_program(reinterpret_cast<int32_t*>(smem_raw), s.path_prog, (uint32_t)s.path_prog_words * 4u, &sh_mbar);
-    // SMEM: the pointer is derived from the shared array in this scope, so every program read compiles to LDS
+    if constexpr (SMEM) stage_program(reinterpret_cast<int32_t*>(smem_raw), s.path_prog, (uint32_t)s.path_prog_smem_words * 4u, &sh_mbar);
+    // SMEM: the pointer is derived from the shared array in this scope, so every read of the staged prefix (header, stages,
+    // paths, chain records) compiles to LDS; leaf / row records stay in global memory (s.path_prog, read through L1)
     int32_t const* const prog = SMEM ? reinterpret_cast<int32_t const*>(smem_raw) : s.path_prog;
     TileP<T> t;
     t.jac = b.jac + (size_t)tile * s.nnz_lu * 4 * T + lane;
@@ -704,7 +711,7 @@ template <int T, bool SMEM> __global__ void __launch_bounds__(V3_THREADS, 1) nr_
 
 template <int T>
 static void launch_v3_t(DevStructure const& s, DevBatch const& b, SolveOptions const& opt, int n_slot, cudaStream_t st) {
-    size_t const prog_bytes = (size_t)s.path_prog_words * 4;
+    size_t const prog_bytes = (size_t)s.path_prog_smem_words * 4;
     int dev = 0, max_optin = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);

@@ -335,7 +335,8 @@ struct WideRowPlan {
 // dependent chain of a feeder needs neither block barriers nor global round trips between consecutive rows.  Paths are
 // grouped in STAGES: a path may start once every other (non-carried) child of its rows is complete; leaves are stage 0.
 //   blob = header[8] | leaf records (8 words) | rec_off[n_rec] | stage_ptr[n_stage + 1] | paths (first_rec, n_rows) | records
-//   header (12 words): n_leaf, n_rec, n_stage, off_leaf, off_rec_off, off_stage_ptr, off_path, n_path, off_chain, 0, 0, 0
+//   header (12 words): n_leaf, n_rec, n_stage, off_leaf, off_rec_off, off_stage_ptr, off_path, n_path, off_chain,
+//                      smem_words (prefix staged in shared memory), 0, 0
 //   chain record (8 words per non-leaf row, same index as rec_off): row, k_d, k_u, k_a (block towards the carry child or
 //                 -1), k_s (precomputed leaf term or -1), pattern, record offset, parent row
 //   pattern: 1 nothing left to eliminate in the chain, 2 carry child only, 3 carry child then the precomputed leaf term,
@@ -353,6 +354,7 @@ struct PathProgram {
     int32_t n_stage{};
     int32_t n_path{};
     int32_t max_path_rows{};
+    int32_t smem_words{}; // header + stages + paths + chain records
 
     PathProgram(LuPattern const& p, EliminationSchedule const& sch, MathTopology const& topo, RowProgram const& rows) {
         Idx const n = p.n_bus;
@@ -420,11 +422,9 @@ struct PathProgram {
             words.push_back(static_cast<int32_t>(lg0 | (n_lg << 24)));
             words.push_back(static_cast<int32_t>(s0 | (n_src << 24)));
         };
+        // the latency-critical part (header, stages, paths, chain records) comes first: only this prefix is staged in shared
+        // memory, the records of the parallel build passes are read through L1
         words.assign(12, 0);
-        Idx const off_leaf = static_cast<Idx>(words.size());
-        for (Idx r : leaves) head(r);
-        Idx const off_rec_off = static_cast<Idx>(words.size());
-        words.resize(words.size() + n_rec, 0);
         Idx const off_stage_ptr = static_cast<Idx>(words.size());
         words.resize(words.size() + n_stage + 1, 0);
         Idx const off_path = static_cast<Idx>(words.size());
@@ -432,6 +432,11 @@ struct PathProgram {
         while (words.size() % 4 != 0) words.push_back(0); // chain records are read as 16-byte vectors
         Idx const off_chain = static_cast<Idx>(words.size());
         words.resize(words.size() + 8 * n_rec, 0);
+        Idx const smem_words = static_cast<Idx>(words.size());
+        Idx const off_leaf = static_cast<Idx>(words.size());
+        for (Idx r : leaves) head(r);
+        Idx const off_rec_off = static_cast<Idx>(words.size());
+        words.resize(words.size() + n_rec, 0);
         Idx rec_idx = 0;
         for (size_t oi = 0; oi != order.size(); ++oi) {
             auto const& rows_of_path = paths[order[oi]];
@@ -516,6 +521,8 @@ struct PathProgram {
         words[6] = static_cast<int32_t>(off_path);
         words[7] = n_path;
         words[8] = static_cast<int32_t>(off_chain);
+        words[9] = static_cast<int32_t>(smem_words);
+        this->smem_words = static_cast<int32_t>(smem_words);
         while (words.size() % 4 != 0) words.push_back(0);
         valid = true;
     }
