@@ -420,9 +420,9 @@ void Engine::launch_solve(DevBatch const& b, SolveOptions const& opt, cudaStream
             launch_nr_block(B_, tile_width_, ds_, b, opt, n_slot_, st);
         } else if (env_int("PGMB_KERNEL", 3) == 1) {
             launch_nr_sym(tile_width_, ds_, b, opt, n_slot_, st);
-        } else if (path_program_.valid && (env_int("PGMB_KERNEL", 0) == 3 || (env_int("PGMB_KERNEL", 3) == 3 && tile_width_ <= 8))) {
-            // radial grid, few scenarios per SM: the path kernel shortens the dependent chain (measured: 1000 scenarios
-            // 2.09 ms vs 2.39 ms); with wide tiles the level kernel has less work per row and wins (8000: 10.7 vs 11.5 ms)
+        } else if (path_program_.valid && env_int("PGMB_KERNEL", 3) == 3) {
+            // radial grid: the path kernel (measured against the level kernel: 1000 scenarios 1.93 vs 2.39 ms, 8000 scenarios
+            // 10.5 vs 11.1 ms)
             launch_nr_sym_v3(tile_width_, ds_, b, opt, n_slot_, st);
         } else {
             launch_nr_sym_v2(tile_width_, ds_, b, opt, n_slot_, st);
