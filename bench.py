@@ -117,6 +117,35 @@ def run_reference(args, rank, world):
     }))
 
 
+def other_configs(pgm_b200, np, device):
+    """kernel milliseconds (CUDA events, second of two runs) of BASELINE configs 3 and 4 on one GPU; informational"""
+
+    def staged_engine(grid, sym, n_scn, seed):
+        model = pgm_b200.PowerGridModel(grid.input_data)
+        eng = pgm_b200.Engine(symmetric=sym, phase_shift=model.math_real(0, sym, "phase_shift"),
+                              branch_bus_idx=model.math_index(0, "branch_bus_idx"), sources_per_bus=model.math_index(0, "sources_per_bus"),
+                              shunts_per_bus=model.math_index(0, "shunts_per_bus"), load_gens_per_bus=model.math_index(0, "load_gens_per_bus"),
+                              load_gen_type=model.math_index(0, "load_gen_type"), fill_in=model.math_index(0, "fill_in"), device=device)
+        eng.set_param(model.math_real(0, sym, "branch_param").view(np.complex128), model.math_real(0, sym, "shunt_param").view(np.complex128),
+                      model.math_real(0, sym, "source_param").view(np.complex128))
+        s_inj, u_ref = model.batch_pf_input(grid.batch_update(n_scn, seed=seed), symmetric=sym)
+        eng.stage(s_inj, u_ref)
+        return eng
+
+    out = {}
+    ringed = pgm_b200.FictionalGrid(seed=0, has_mv_ring=True, has_lv_ring=True, **pgm_b200.BENCHMARK_OPTION)
+    eng = staged_engine(ringed, False, 1000, 0)
+    ms = [eng.solve_staged(err_tol=ERR_TOL, max_iter=MAX_ITER) for _ in range(2)][-1]
+    out["configs[2] ringed grid, asymmetric newton_raphson, 1000 scenarios"] = {"kernel_ms": ms, "scenarios_per_s": 1000 / ms * 1e3}
+    radial = pgm_b200.FictionalGrid(seed=0, **pgm_b200.BENCHMARK_OPTION)
+    eng = staged_engine(radial, True, 12500, 0)
+    for method in ("iterative_current", "linear"):
+        ms = [eng.solve_staged(method=method, err_tol=ERR_TOL, max_iter=MAX_ITER) for _ in range(2)][-1]
+        out[f"configs[3] radial grid, {method}, 12500 scenarios (one GPU's share of 100k over 8)"] = {
+            "kernel_ms": ms, "scenarios_per_s": 12500 / ms * 1e3}
+    return out
+
+
 def workload_config(n_scn_per_gpu):
     return {"workload": "configs[1]: fictional radial grid n_node_total_specified=1500 (seed 0: 2605 nodes, 2600 lines, "
                         "7 transformers, 197 sym_load, 1200 asym_load), symmetric newton_raphson, err_tol 1e-8, max_iter 20",
@@ -229,6 +258,12 @@ def main():
     h2d = sum(v.nbytes for v in update.values())
     d2h = sum(v.nbytes for v in res.values())
 
+    # ---- the other BASELINE configs, solver kernels only, rank 0 (reported beside the bench line, not part of it; after
+    #      every timed region so that they cannot disturb it) ----
+    other = None
+    if rank == 0 and os.environ.get("PGMB_BENCH_OTHER", "1") == "1":
+        other = other_configs(pgm_b200, np, local_rank)
+
     if rank == 0:
         peak, peak_kind = measured_peak_hbm()
         a_solve = algorithmic_bytes_per_solve(n_bus, nnz_lu, n_lg)
@@ -263,7 +298,7 @@ def main():
                          "algorithmic_bytes_per_launch": bytes_per_launch, "launch_ms": 1e3 * launch_s},
             "cpu_baseline": {"value": cpu_value, "unit": "scenarios/s", "cores": cores, "kind": "port",
                              "sample": f"{sample} of the {N_SCN} scenarios x {reps} repeats, all {cores} host threads (reference threading=0)"},
-            "clocks": clocks, "device_wall_ms_per_step": 1e3 * wall_dev / args.steps,
+            "clocks": clocks, "device_wall_ms_per_step": 1e3 * wall_dev / args.steps, "other_configs_kernel_only": other,
         }))
     if dist is not None:
         dist.destroy_process_group()

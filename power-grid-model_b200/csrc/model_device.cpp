@@ -121,10 +121,16 @@ int64_t Model::run_batch_device(ModelOptions const& opt, int phases, UpdateData 
         if (*o.host != nullptr) per_scn += o.row * static_cast<size_t>(o.count);
     for (int b = 0; b != 4; ++b)
         if (ubufs[b]->data != nullptr) per_scn += urow[b] * static_cast<size_t>(ubufs[b]->n);
-    size_t free_b = 0, total_b = 0;
-    PGMB_CUDA(cudaSetDevice(e.device()));
-    PGMB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    size_t budget = total_b / 10 * 6; // the pool may hold freed blocks, so the total is the better yardstick
+    // total memory of the device, queried once: cudaMemGetInfo costs milliseconds in a process with many allocations
+    static size_t total_cache[64] = {};
+    int const dev_slot = e.device() % 64;
+    if (total_cache[dev_slot] == 0) {
+        size_t free_b = 0, total_b = 0;
+        PGMB_CUDA(cudaSetDevice(e.device()));
+        PGMB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        total_cache[dev_slot] = total_b;
+    }
+    size_t budget = total_cache[dev_slot] / 10 * 6; // the pool may hold freed blocks, so the total is the yardstick
     if (char const* env = std::getenv("PGMB_MAX_BATCH_BYTES")) budget = static_cast<size_t>(std::atoll(env));
     Idx const n_scn = update.n_scenarios;
     Idx max_scn = static_cast<Idx>(std::max<size_t>(32, budget / per_scn / 32 * 32));
