@@ -113,7 +113,7 @@ template <int T> __device__ __forceinline__ C backward_row(DevStructure const& s
 }
 
 // ---- linear ----------------------------------------------------------------------------------------------------------
-template <int T> __global__ void linear_sym_kernel(DevStructure s, DevBatch b) {
+template <int T> __global__ void __launch_bounds__(512, 2) linear_sym_kernel(DevStructure s, DevBatch b) {
     __shared__ int sh_singular[T];
     int const lane = threadIdx.x % T, slot = threadIdx.x / T, n_slot = blockDim.x / T, tile = blockIdx.x;
     int64_t const scn = (int64_t)tile * T + lane;
@@ -161,7 +161,7 @@ __global__ void ic_factor_kernel(DevStructure s, double* factor, int* flag) {
 }
 
 template <int T>
-__global__ void ic_iterate_sym_kernel(DevStructure s, DevBatch b, SolveOptions opt, double const* __restrict__ factor,
+__global__ void __launch_bounds__(512, 2) ic_iterate_sym_kernel(DevStructure s, DevBatch b, SolveOptions opt, double const* __restrict__ factor,
                                       int const* __restrict__ factor_flag) {
     __shared__ unsigned long long sh_dev[T];
     int const lane = threadIdx.x % T, slot = threadIdx.x / T, n_slot = blockDim.x / T, tile = blockIdx.x;
@@ -221,8 +221,18 @@ __global__ void ic_iterate_sym_kernel(DevStructure s, DevBatch b, SolveOptions o
         // up-sweep: injected current of the bus, then forward substitution with the shared L
         for (int lv = 0; lv < s.n_level; ++lv) {
             if (!done) {
-                for (int i = __ldg(s.level_ptr + lv) + slot; i < __ldg(s.level_ptr + lv + 1); i += n_slot) {
+                int const lv_end = __ldg(s.level_ptr + lv + 1);
+                for (int i = __ldg(s.level_ptr + lv) + slot; i < lv_end; i += n_slot) {
                     int const row = __ldg(s.level_rows + i);
+                    if (i + n_slot < lv_end) { // pull the voltage and the loads of this thread's next bus into L1
+                        int const nx = __ldg(s.level_rows + i + n_slot);
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(u + (size_t)(nx * 2) * T));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(u + (size_t)(nx * 2 + 1) * T));
+                        for (int lg = __ldg(s.lg_ptr + nx), lge = __ldg(s.lg_ptr + nx + 1); lg < lge; ++lg) {
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(sinj + (size_t)(lg * 2) * T));
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(sinj + (size_t)(lg * 2 + 1) * T));
+                        }
+                    }
                     C const ui = ldu(row);
                     C rhs{0.0, 0.0};
                     for (int lg = __ldg(s.lg_ptr + row), lge = __ldg(s.lg_ptr + row + 1); lg < lge; ++lg) {
