@@ -31,9 +31,9 @@ MAX_ITER = 20
 
 def measured_peak_hbm():
     try:
-        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "measured"
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs: burst copy figure, the only HBM figure there)"
     except Exception:
-        return 6650.0, "fallback"
+        return 6650.0, "fallback (B200_PROFILING.md)"
 
 
 def measured_traffic():
@@ -294,7 +294,7 @@ def main():
                     "gpu_launches": e2e_launches},
             "gpu_launches": gpu_launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": measured_traffic(), "peak_kind": peak_kind, "kernel": "nr_sym_v3_kernel (radial path kernel; nr_sym_v2_kernel for wide tiles / meshed grids)",
+                         "traffic": measured_traffic(), "peak_kind": peak_kind, "kernel": "nr_sym_v3_kernel (path kernel of radial grids; the whole NR loop of a launch)",
                          "algorithmic_bytes_per_launch": bytes_per_launch, "launch_ms": 1e3 * launch_s},
             "cpu_baseline": {"value": cpu_value, "unit": "scenarios/s", "cores": cores, "kind": "port",
                              "sample": f"{sample} of the {N_SCN} scenarios x {reps} repeats, all {cores} host threads (reference threading=0)"},
