@@ -114,6 +114,11 @@ int pgmb_engine_get_index(pgmb_engine* engine, const char* name, const int64_t**
             else if (key == "level_rows") v = widen(s.level_rows);
             else if (key == "row_program") v = widen(engine->engine->program().words);
             else if (key == "path_program") v = widen(engine->engine->path_program().words); // empty: not a radial grid
+            else if (key == "wide_level_ptr") v = widen(engine->engine->wide_plan().level_ptr);
+            else if (key == "wide_table") v = widen(engine->engine->wide_plan().table);
+            else if (key == "wide_data") v = widen(engine->engine->wide_plan().data);
+            else if (key == "upd_ptr") v = widen(s.upd_ptr);
+            else if (key == "upd_a") v = widen(s.upd_a);
             else throw InvalidArgument("unknown index array: " + key);
             it = engine->index_cache.emplace(key, std::move(v)).first;
         }

@@ -120,3 +120,46 @@ def test_path_program_covers_a_radial_grid(n_node, seed):
 def test_path_program_absent_on_meshed_grid():
     grid = random_grid(60, 10, 5)
     assert pgm_b200.Engine.from_grid(grid, device=-1).index("path_program").size == 0
+
+
+def test_wide_row_plan_of_a_hub_grid():
+    """WideRowPlan (symbolic.hpp): a star-of-rings grid has a hub row with many lower entries; its children are ordered in
+    sub-levels that respect the updates between them, and every entry lists the terms it receives in ascending child order"""
+    rng = np.random.default_rng(5)
+    n_spoke, ring = 30, 4
+    edges, n = [], 1
+    for s in range(n_spoke):  # hub 0 -- a -- b -- c -- d -- hub: rings through the hub
+        nodes = list(range(n, n + ring))
+        n += ring
+        edges += [(0, nodes[0])] + [(nodes[i], nodes[i + 1]) for i in range(ring - 1)] + [(nodes[-1], 0)]
+    bag = orc.topology(n, edges, [[1, 1]] * len(edges), [0.0] * len(edges), [0], [1])
+    assert bag.i64("n_math")[0] == 1
+    bb = bag.i64("g0.branch_bus_idx").reshape(-1, 2)
+    fill = bag.i64("g0.fill_in").reshape(-1, 2)
+    eng = _engine(n, bb, fill, np.zeros(n + 1, np.int64))
+    table = eng.index("wide_table").reshape(-1, 8)
+    assert len(table) >= 1
+    data, rp, ci, dg = eng.index("wide_data"), eng.index("row_indptr_lu"), eng.index("col_indices_lu"), eng.index("diag_lu")
+    upd_ptr, upd_a = eng.index("upd_ptr"), eng.index("upd_a")
+    for row, n_sub, off_sub, off_order, off_in_ptr, off_in_idx, n_upd, _ in table:
+        rb, re_, d = rp[row], rp[row + 1], dg[row]
+        n_lower, n_entries = d - rb, re_ - rb
+        assert n_lower >= 24 and n_upd == upd_ptr[d] - upd_ptr[rb]
+        sub_ptr = data[off_sub:off_sub + n_sub + 1]
+        order = data[off_order:off_order + n_lower]
+        assert sorted(order.tolist()) == list(range(n_lower)) and sub_ptr[0] == 0 and sub_ptr[-1] == n_lower
+        depth = np.empty(n_lower, int)
+        for sl in range(n_sub):
+            depth[order[sub_ptr[sl]:sub_ptr[sl + 1]]] = sl
+        in_ptr = data[off_in_ptr:off_in_ptr + n_entries + 1]
+        in_idx = data[off_in_idx:off_in_idx + in_ptr[-1]]
+        assert in_ptr[-1] == n_upd
+        src_child = np.empty(n_upd, int)
+        for e in range(rb, d):
+            src_child[upd_ptr[e] - upd_ptr[rb]:upd_ptr[e + 1] - upd_ptr[rb]] = e - rb
+        for pos in range(n_entries):
+            terms = in_idx[in_ptr[pos]:in_ptr[pos + 1]]
+            assert (np.diff(terms) > 0).all()                       # ascending update number = ascending child
+            assert all(upd_a[upd_ptr[rb] + q] == rb + pos for q in terms)
+            if pos < n_lower:                                        # a child only receives terms from earlier sub-levels
+                assert all(depth[src_child[q]] < depth[pos] for q in terms)
