@@ -289,3 +289,31 @@ def test_batch_larger_than_the_memory_budget_is_split(monkeypatch):
     with pytest.raises(pgm_b200.BatchError) as e:
         model2.calculate_power_flow(update_data=update)
     assert "Error in batch #101" in str(e.value)
+
+
+def test_edge_batches():
+    """empty batch, single-scenario batch, partial updates (a subset of the loads, status-only rows, NaN = keep)"""
+    grid = pgm_b200.FictionalGrid(seed=0, n_node_total_specified=60, n_connection_per_lv_feeder=3, n_lv_feeder=2, n_node_per_mv_feeder=3,
+                                  n_mv_feeder=2)
+    inp = grid.input_data
+    model = pgm_b200.PowerGridModel(inp)
+    base = model.calculate_power_flow()
+    full = grid.batch_update(4, seed=9)
+    empty = {k: v[:0] for k, v in full.items()}
+    res0 = model.calculate_power_flow(update_data=empty)
+    assert all(a.shape[0] == 0 for a in res0.values())
+    one = {k: np.ascontiguousarray(v[:1]) for k, v in full.items()}
+    ref = orc.Model(inp).calculate(sym=True, update=one)
+    _compare_with_oracle(model.calculate_power_flow(update_data=one), ref, 1)
+    # partial: two sym loads only; scenario 0 switches one off, scenario 1 keeps p (NaN) and changes q, scenario 2 all NaN
+    ids = inp["sym_load"]["id"][:2]
+    upd = pgm_b200.structs.initialize_array("update", "sym_load", (3, 2))
+    upd["id"][:] = ids
+    upd["status"][0, 0] = 0
+    upd["q_specified"][1, 1] = 1234.5
+    ref = orc.Model(inp).calculate(sym=True, update={"sym_load": upd})
+    res = model.calculate_power_flow(update_data={"sym_load": upd})
+    assert np.array_equal(model.n_iter, ref["n_iter"])
+    _compare_with_oracle(res, ref, 3)
+    assert np.array_equal(res["node"]["u_pu"][2], base["node"]["u_pu"])  # all-NaN scenario = the base state
+    assert res["sym_load"]["energized"][0, 0] == 0 and res["sym_load"]["p"][0, 0] == 0.0
