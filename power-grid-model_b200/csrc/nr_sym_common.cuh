@@ -54,7 +54,6 @@ __device__ __forceinline__ bool factor_diag(Blk& d, int& pr, int& pcq) {
         pcq = 1;
     }
     bool singular = (best == 0.0);
-    double max_pivot = sqrt(best);
     if (pr) {
         double x = d.a00;
         d.a00 = d.a10;
@@ -73,7 +72,9 @@ __device__ __forceinline__ bool factor_diag(Blk& d, int& pr, int& pcq) {
     }
     d.a10 /= d.a00;
     d.a11 -= d.a10 * d.a01;
-    max_pivot = fmax(max_pivot, sqrt(d.a11 * d.a11)); // sqrt(|x|^2) like the reference, not |x|
+    // reference: max(sqrt(best), sqrt(|d11|^2)); sqrt is monotone and correctly rounded, so one square root of the larger
+    // argument gives the same bits
+    double const max_pivot = sqrt(fmax(best, d.a11 * d.a11));
     double const threshold = DBL_EPSILON * max_pivot;
     singular = singular || fabs(d.a00) < threshold || not_normal(d.a00) || fabs(d.a11) < threshold || not_normal(d.a11);
     return singular;
