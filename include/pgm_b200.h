@@ -41,7 +41,13 @@ enum {
 
 /* per-scenario status (the reference throws IterationDiverge / SparseMatrixError per scenario,
  * common/exception.hpp:89-110; job_dispatch.hpp:181-224 collects them) */
-enum { PGMB_SCN_OK = 0, PGMB_SCN_DIVERGED = 1, PGMB_SCN_SINGULAR = 2, PGMB_SCN_ERROR = 3 };
+enum {
+    PGMB_SCN_OK = 0,
+    PGMB_SCN_DIVERGED = 1,
+    PGMB_SCN_SINGULAR = 2,
+    PGMB_SCN_ERROR = 3,
+    PGMB_SCN_UNALLOCATED_Q = 4 /* "Unallocated Q remains after distribution" (common_solver_functions.hpp:373-376) */
+};
 
 /* CalculationMethod, common/enum.hpp:33-41 */
 enum {
@@ -79,6 +85,10 @@ typedef struct pgmb_math_topology {
     const int64_t* shunts_per_bus;    /* indptr [n_bus + 1] */
     const int64_t* load_gens_per_bus; /* indptr [n_bus + 1] */
     const int8_t* load_gen_type;      /* [n_load_gen] LoadGenType: 0 const_pq, 1 const_y, 2 const_i */
+    /* voltage regulators grouped by the load_gen they regulate (calculation_parameters.hpp:176, topology.hpp:594-600):
+     * indptr [n_load_gen + 1], or NULL when the grid has none.  At most one regulator per load_gen (main_core/input.hpp:216-241
+     * enforces that for every model). */
+    const int64_t* voltage_regulators_per_load_gen;
 } pgmb_math_topology;
 
 /* MathModelParam<sym> (calculation_parameters.hpp:240-255) */
@@ -100,6 +110,11 @@ typedef struct pgmb_pf_input {
     const double* source_u_ref; /* [n_scenarios][n_source] complex; or [n_source] when source_is_shared != 0 */
     int32_t source_is_shared;
     const double* s_injection;  /* [n_scenarios][n_load_gen][B] complex, per-unit, injection direction */
+    /* grids with voltage regulators only (NULL otherwise): VoltageRegulatorCalcParam (calculation_parameters.hpp:228-236)
+     * as [n_regulator][4] = status, u_ref, q_min, q_max (per unit, NaN = no limit), shared by the scenarios of the call, and
+     * the status of each load_gen per scenario (PowerFlowInput::load_gen_status), NULL = all on */
+    const double* voltage_regulator;
+    const int8_t* load_gen_status; /* [n_scenarios][n_load_gen] */
 } pgmb_pf_input;
 
 /* SolverOutput<sym> for n_scenarios scenarios (calculation_parameters.hpp:338-350); any pointer may be NULL */
@@ -113,6 +128,8 @@ typedef struct pgmb_solver_output {
     int32_t* status;       /* [n_scenarios] PGMB_SCN_* */
     int32_t* n_iter;       /* [n_scenarios] iterations used (the reference only logs it, iterative_pf_solver.hpp:87) */
     double* max_dev;       /* [n_scenarios] last max |dU| */
+    int8_t* voltage_regulator; /* [n_scenarios][n_regulator][2] = limit_violated (0 none, 1 lower, 2 upper), generator_status
+                                * (VoltageRegulatorSolverOutput, calculation_parameters.hpp:94-100) */
 } pgmb_solver_output;
 
 typedef struct pgmb_engine pgmb_engine;
@@ -155,17 +172,20 @@ typedef struct pgmb_component_buffer {
 /* order = component storage order of the reference (all_components.hpp:36-39), PF subset */
 typedef struct pgmb_input_data {
     pgmb_component_buffer node, line, transformer, shunt, source, sym_gen, asym_gen, sym_load, asym_load;
+    pgmb_component_buffer voltage_regulator; /* VoltageRegulatorInput (auxiliary/input.hpp:492-498) */
 } pgmb_input_data;
 
 typedef struct pgmb_update_data {
     int64_t n_scenarios;
     pgmb_component_buffer line, transformer, shunt, source, sym_gen, asym_gen, sym_load, asym_load;
+    pgmb_component_buffer voltage_regulator; /* VoltageRegulatorUpdate (auxiliary/update.hpp:213-219) */
 } pgmb_update_data;
 
 /* caller-owned output buffers [n_scenarios][n_component]; NULL = component not requested
  * (only components present in the output dataset are produced, main_model_impl.hpp:450-460) */
 typedef struct pgmb_output_data {
     void *node, *line, *transformer, *shunt, *source, *sym_gen, *asym_gen, *sym_load, *asym_load;
+    void* voltage_regulator; /* VoltageRegulatorOutput (auxiliary/output.hpp:239-243) */
 } pgmb_output_data;
 
 /* PGM_Options (power_grid_model_c/src/options.hpp:16-27), PF subset */

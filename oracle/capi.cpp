@@ -287,6 +287,7 @@ static void store_topology(Bag& b, std::vector<MathTopology> const& math, Compon
         b.i[p + "load_gens_per_bus"] = m.load_gens_per_bus;
         auto& lt = b.i[p + "load_gen_type"];
         for (auto t : m.load_gen_type) lt.push_back(static_cast<int64_t>(t));
+        b.i[p + "voltage_regulators_per_load_gen"] = m.voltage_regulators_per_load_gen;
     }
     auto put = [&b](std::string const& name, std::vector<Idx2D> const& v) {
         auto& o = b.i[name];
@@ -300,6 +301,7 @@ static void store_topology(Bag& b, std::vector<MathTopology> const& math, Compon
     put("coup.shunt", coup.shunt);
     put("coup.load_gen", coup.load_gen);
     put("coup.source", coup.source);
+    put("coup.voltage_regulator", coup.voltage_regulator);
     auto& b3 = b.i["coup.branch3"];
     for (auto const& [g, pos] : coup.branch3) {
         b3.push_back(g);

@@ -101,6 +101,23 @@ template <int B> struct ApplianceOutput {
     IntS energized;
     double p[B], q[B], i[B], s[B], pf[B];
 };
+// voltage regulator (auxiliary/input.hpp:492-498, update.hpp:213-219, output.hpp:239-243)
+struct VoltageRegulatorInput {
+    ID id, regulated_object;
+    IntS status;
+    double u_ref, q_min, q_max;
+};
+struct VoltageRegulatorUpdate {
+    ID id;
+    IntS status;
+    double u_ref, q_min, q_max;
+};
+struct VoltageRegulatorOutput {
+    ID id;
+    IntS energized;
+    IntS limit_violated;
+};
+static_assert(sizeof(VoltageRegulatorInput) == 40 && sizeof(VoltageRegulatorUpdate) == 32 && sizeof(VoltageRegulatorOutput) == 8);
 static_assert(sizeof(LineInput) == 88 && sizeof(TransformerInput) == 168 && sizeof(SourceInput) == 56);
 static_assert(sizeof(SymLoadGenUpdate) == 24 && sizeof(AsymLoadGenUpdate) == 56);
 static_assert(sizeof(NodeOutput<1>) == 48 && sizeof(NodeOutput<3>) == 128);
@@ -535,6 +552,29 @@ struct LoadGen : ApplianceBase {
             return r;
         }
     }
+};
+
+// component/voltage_regulator.hpp:22-101, component/regulator.hpp
+struct VoltageRegulator {
+    ID id{};
+    ID regulated_object{};
+    bool status{};
+    double u_ref{}, q_min{}, q_max{};
+    explicit VoltageRegulator(VoltageRegulatorInput const& in)
+        : id{in.id}, regulated_object{in.regulated_object}, status{in.status != 0}, u_ref{in.u_ref}, q_min{in.q_min}, q_max{in.q_max} {}
+    void update(VoltageRegulatorUpdate const& u) {
+        if (u.status != na_IntS) status = u.status != 0;
+        if (!is_nan(u.u_ref)) u_ref = u.u_ref;
+        if (!is_nan(u.q_min)) q_min = u.q_min;
+        if (!is_nan(u.q_max)) q_max = u.q_max;
+    }
+    VoltageRegulatorCalcParam calc_param() const {
+        return {static_cast<IntS>(status), cplx{u_ref, 0.0}, q_min / base_power_3p, q_max / base_power_3p, regulated_object};
+    }
+    VoltageRegulatorOutput get_output(VoltageRegulatorSolverOutput const& so) const {
+        return {id, static_cast<IntS>(status && so.generator_status != 0), static_cast<IntS>(so.limit_violated)};
+    }
+    VoltageRegulatorOutput get_null_output() const { return {id, 0, 0}; }
 };
 
 } // namespace pgm_oracle

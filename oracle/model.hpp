@@ -16,6 +16,7 @@
 #include "pf_solvers.hpp"
 #include "topology.hpp"
 
+#include <set>
 #include <thread>
 #include <unordered_map>
 
@@ -40,6 +41,8 @@ struct ModelInput {
     SymLoadGenInput const* sym_load;
     Idx n_asym_load;
     AsymLoadGenInput const* asym_load;
+    Idx n_voltage_regulator;
+    VoltageRegulatorInput const* voltage_regulator;
 };
 
 // one buffer of a batch update dataset: uniform (indptr == nullptr, n_per_scenario elements each) or sparse
@@ -63,6 +66,7 @@ struct BatchUpdate {
     UpdateBuffer<AsymLoadGenUpdate> asym_gen;
     UpdateBuffer<SymLoadGenUpdate> sym_load;
     UpdateBuffer<AsymLoadGenUpdate> asym_load;
+    UpdateBuffer<VoltageRegulatorUpdate> voltage_regulator;
 };
 // output buffers, each [n_scenarios][n_component] or nullptr when the caller does not want that component
 template <int B> struct BatchOutput {
@@ -75,6 +79,7 @@ template <int B> struct BatchOutput {
     ApplianceOutput<B>* asym_gen;
     ApplianceOutput<B>* sym_load;
     ApplianceOutput<B>* asym_load;
+    VoltageRegulatorOutput* voltage_regulator;
 };
 
 struct CalcOptions {
@@ -143,13 +148,68 @@ class Model {
         for (size_t i = 0; i != shunts_.size(); ++i) shunt_idx_[shunts_[i].id] = static_cast<Idx>(i);
         for (size_t i = 0; i != sources_.size(); ++i) source_idx_[sources_[i].id] = static_cast<Idx>(i);
         for (size_t i = 0; i != load_gens_.size(); ++i) load_gen_idx_[load_gens_[i].id] = static_cast<Idx>(i);
+        // voltage regulators (main_core/input.hpp:216-241): the regulated object must be a load / generator, at most one
+        // regulator per object
+        std::set<ID> regulated;
+        for (Idx i = 0; i != in.n_voltage_regulator; ++i) {
+            add_id(in.voltage_regulator[i].id);
+            auto it = load_gen_idx_.find(in.voltage_regulator[i].regulated_object);
+            if (it == load_gen_idx_.end()) {
+                throw PgmError{"voltage_regulator has invalid regulated object " + std::to_string(in.voltage_regulator[i].regulated_object)};
+            }
+            if (!regulated.insert(in.voltage_regulator[i].regulated_object).second) {
+                throw PgmError{"There are objects regulated by more than one regulator. Maximum one regulator is allowed."};
+            }
+            regulators_.emplace_back(in.voltage_regulator[i]);
+            regulator_idx_[in.voltage_regulator[i].id] = i;
+        }
     }
 
     Idx n_node() const { return static_cast<Idx>(nodes_.size()); }
     Idx n_branch() const { return static_cast<Idx>(lines_.size() + transformers_.size()); }
 
     // ---- single calculation ----
-    template <int B> void calculate(CalcOptions const& opt, BatchOutput<B> const& out, Idx scenario) {
+    // calculation_preparation.hpp:163-225 check_state_validity + main_model_impl.hpp:362-366, 400-420
+    template <int B> void check_regulators(CalcOptions const& opt) const {
+        if (regulators_.empty()) return;
+        if (opt.method != CalculationMethod::newton_raphson && opt.method != CalculationMethod::default_method) {
+            throw PgmError{"The calculation method is invalid for this calculation!"};
+        }
+        std::unordered_map<ID, std::pair<ID, double>> node_ref; // node -> (regulator id, u_ref)
+        for (auto const& r : regulators_) {
+            if (!r.status) continue;
+            auto const& lg = load_gens_[load_gen_idx_.at(r.regulated_object)];
+            auto it = node_ref.find(lg.node);
+            if (it != node_ref.end()) {
+                if (it->second.second != r.u_ref) {
+                    throw PgmError{"Voltage regulators with different u_ref on the same node: " + std::to_string(it->second.first) + ", " +
+                                   std::to_string(r.id)};
+                }
+            } else {
+                node_ref[lg.node] = {r.id, r.u_ref};
+            }
+        }
+        for (auto const& r : regulators_) {
+            if (!r.status) continue;
+            if (load_gens_[load_gen_idx_.at(r.regulated_object)].type != LoadGenType::const_pq) {
+                throw PgmError{"Voltage regulator " + std::to_string(r.id) + " regulates a load/generator of unsupported type"};
+            }
+        }
+        for (auto const& src : sources_) {
+            if (src.status && node_ref.count(src.node) != 0) {
+                throw PgmError{"Unsupported combination of source and voltage regulator at node " + std::to_string(src.node)};
+            }
+        }
+        if constexpr (B == 3) {
+            for (auto const& r : regulators_)
+                if (!is_nan(r.q_min) || !is_nan(r.q_max)) {
+                    throw PgmError{"Voltage Regulator with Qmin/Qmax limits for asymmetric calculations is an experimental feature"};
+                }
+        }
+    }
+
+    template <int B> void calculate(CalcOptions const& opt, BatchOutput<B> const& out, Idx scenario, bool cache_run = false) {
+        check_regulators<B>(opt);
         prepare_solvers<B>();
         auto const pf_input = prepare_power_flow_input<B>();
         auto& ys = y_bus<B>();
@@ -158,7 +218,7 @@ class Model {
         last_num_iter_ = 0;
         for (size_t g = 0; g != ys.size(); ++g) {
             so.push_back(solvers[g].run_power_flow(pf_input[g], opt.err_tol, opt.max_iter, opt.method, ys[g],
-                                                   opt.reuse_ic_factorization));
+                                                   opt.reuse_ic_factorization, cache_run));
             last_num_iter_ = std::max(last_num_iter_, so.back().num_iter);
         }
         output_result<B>(so, out, scenario);
@@ -179,7 +239,7 @@ class Model {
             CalcOptions cache_opt = opt;
             cache_opt.err_tol = std::numeric_limits<double>::max();
             cache_opt.max_iter = 1;
-            calculate<B>(cache_opt, none, 0);
+            calculate<B>(cache_opt, none, 0, true);
         } catch (SparseMatrixError const&) {
         } catch (IterationDiverge const&) {
         }
@@ -237,6 +297,8 @@ class Model {
     std::vector<Shunt> shunts_;
     std::vector<Source> sources_;
     std::vector<LoadGen> load_gens_; // sym_gen, asym_gen, sym_load, asym_load
+    std::vector<VoltageRegulator> regulators_;
+    std::unordered_map<ID, Idx> regulator_idx_;
     Idx n_sym_gen_{}, n_asym_gen_{}, n_sym_load_{}, n_asym_load_{};
     std::unordered_map<ID, Idx> all_ids_, node_idx_, line_idx_, transformer_idx_, shunt_idx_, source_idx_, load_gen_idx_;
 
@@ -293,6 +355,7 @@ class Model {
             comp_topo_.load_gen_node_idx.push_back(node_idx_.at(lg.node));
             comp_topo_.load_gen_type.push_back(lg.type);
         }
+        for (auto const& r : regulators_) comp_topo_.regulated_load_gen_idx.push_back(load_gen_idx_.at(r.regulated_object));
         Topology topology{comp_topo_, conn};
         auto [math, coup] = topology.build_topology();
         math_topo_.clear();
@@ -376,6 +439,20 @@ class Model {
         for (size_t i = 0; i != load_gens_.size(); ++i) {
             Idx2D const m = coup_.load_gen[i];
             if (m.group != -1) in[m.group].s_injection[m.pos] = load_gens_[i].calc_param<B>();
+        }
+        if (!regulators_.empty()) {
+            for (size_t g = 0; g != math_topo_.size(); ++g) {
+                in[g].voltage_regulator.resize(math_topo_[g]->n_voltage_regulator());
+                in[g].load_gen_status.resize(math_topo_[g]->n_load_gen());
+            }
+            for (size_t i = 0; i != regulators_.size(); ++i) {
+                Idx2D const m = coup_.voltage_regulator[i];
+                if (m.group != -1) in[m.group].voltage_regulator[m.pos] = regulators_[i].calc_param();
+            }
+            for (size_t i = 0; i != load_gens_.size(); ++i) {
+                Idx2D const m = coup_.load_gen[i];
+                if (m.group != -1) in[m.group].load_gen_status[m.pos] = static_cast<IntS>(load_gens_[i].status);
+            }
         }
         return in;
     }
@@ -501,6 +578,14 @@ class Model {
         lg_out(out.asym_gen, n_sym_gen_, n_asym_gen_);
         lg_out(out.sym_load, n_sym_gen_ + n_asym_gen_, n_sym_load_);
         lg_out(out.asym_load, n_sym_gen_ + n_asym_gen_ + n_sym_load_, n_asym_load_);
+        if (out.voltage_regulator != nullptr) { // main_core/output.hpp:407-421
+            Idx const n = static_cast<Idx>(regulators_.size());
+            for (Idx i = 0; i != n; ++i) {
+                Idx2D const m = coup_.voltage_regulator[i];
+                out.voltage_regulator[scenario * n + i] =
+                    m.group == -1 ? regulators_[i].get_null_output() : regulators_[i].get_output(so[m.group].voltage_regulator[m.pos]);
+            }
+        }
     }
 
     // ---- update / restore ----
@@ -510,6 +595,7 @@ class Model {
         std::vector<std::pair<Idx, Shunt>> shunts;
         std::vector<std::pair<Idx, Source>> sources;
         std::vector<std::pair<Idx, LoadGen>> load_gens;
+        std::vector<std::pair<Idx, VoltageRegulator>> regulators;
         bool topo{false}, param{false};
     };
     void mark(bool topo, bool param, Saved& saved) {
@@ -605,6 +691,14 @@ class Model {
         upd_lg(upd.asym_gen, n_sym_gen_, n_asym_gen_);
         upd_lg(upd.sym_load, n_sym_gen_ + n_asym_gen_, n_sym_load_);
         upd_lg(upd.asym_load, n_sym_gen_ + n_asym_gen_ + n_sym_load_, n_asym_load_);
+        {
+            auto [b, e] = upd.voltage_regulator.scenario(s);
+            for (auto p = b; p != e; ++p) {
+                Idx const i = find_seq(*p, p - b, e - b, static_cast<Idx>(regulators_.size()), regulator_idx_, 0);
+                saved.regulators.emplace_back(i, regulators_[i]);
+                regulators_[i].update(*p); // UpdateChange{false, false} (voltage_regulator.hpp:35-41)
+            }
+        }
     }
     void restore(Saved const& saved) {
         // restore in reverse order so repeated updates of one component end at the original value
@@ -614,6 +708,7 @@ class Model {
         for (auto it = saved.shunts.rbegin(); it != saved.shunts.rend(); ++it) shunts_[it->first] = it->second;
         for (auto it = saved.sources.rbegin(); it != saved.sources.rend(); ++it) sources_[it->first] = it->second;
         for (auto it = saved.load_gens.rbegin(); it != saved.load_gens.rend(); ++it) load_gens_[it->first] = it->second;
+        for (auto it = saved.regulators.rbegin(); it != saved.regulators.rend(); ++it) regulators_[it->first] = it->second;
         if (saved.topo) topo_valid_ = false;
         if (saved.param) param_valid_[0] = param_valid_[1] = false;
     }

@@ -69,6 +69,129 @@ inline void calculate_multiple_source_result(Idx s_begin, Idx s_end, YBus<B> con
     }
 }
 
+// ---- reactive power of the regulated generators (common_solver_functions.hpp:162-381) ----------------------------------
+template <int B> struct RegulatorQState {
+    Idx regulator_idx;
+    Idx load_gen_idx;
+    bool has_available_capacity{false};
+    double q_allocated[B]{};
+};
+template <int B> inline double total_q(double const* q) {
+    if constexpr (B == 1) {
+        return q[0];
+    } else {
+        return q[0] + q[1] + q[2];
+    }
+}
+// distribute_q :223-238: keep the per-phase proportions of the base distribution, or split equally when it is ~0
+template <int B> inline void distribute_q(double q_scalar, double const* base, double* out) {
+    if constexpr (B == 1) {
+        (void)base;
+        out[0] = q_scalar;
+    } else {
+        double const base_total = total_q<3>(base);
+        if (std::abs(base_total) > numerical_tolerance) {
+            double const scale = q_scalar / base_total;
+            for (int p = 0; p < 3; ++p) out[p] = base[p] * scale;
+        } else {
+            for (int p = 0; p < 3; ++p) out[p] = q_scalar / 3.0;
+        }
+    }
+}
+
+template <int B>
+inline void calculate_voltage_regulator_result(Idx bus, Idx lg_begin, Idx lg_end, MathTopology const& topo,
+                                               PowerFlowInput<B> const& input, SolverOutput<B>& output) {
+    if (lg_begin == lg_end) return;
+    auto const& vr = topo.voltage_regulators_per_load_gen;
+    // 1. regulator outputs + the set of regulating generators (:170-216)
+    std::vector<RegulatorQState<B>> state;
+    CVec<B> s_load_gen_bus{};
+    int num_regulating = 0;
+    for (Idx lg = lg_begin; lg != lg_end; ++lg) {
+        if (vr[lg] == vr[lg + 1]) {
+            s_load_gen_bus += output.load_gen[lg].s;
+            continue;
+        }
+        Idx const regulator = vr[lg]; // std::map::insert keeps the first regulator of the load_gen (:434-438)
+        auto& out_reg = output.voltage_regulator[regulator];
+        out_reg.generator_id = input.voltage_regulator[regulator].generator_id;
+        out_reg.generator_status = input.load_gen_status[lg];
+        out_reg.limit_violated = LimitViolation::none;
+        bool const is_regulating = input.load_gen_status[lg] != 0 && input.voltage_regulator[regulator].status != 0;
+        if (!is_regulating) {
+            s_load_gen_bus += output.load_gen[lg].s;
+            continue;
+        }
+        ++num_regulating;
+        RegulatorQState<B> st{};
+        st.regulator_idx = regulator;
+        st.load_gen_idx = lg;
+        state.push_back(st);
+    }
+    if (num_regulating == 0) return;
+    // 2. distribution under the regulator limits (:254-270)
+    double q_remaining[B];
+    for (int p = 0; p < B; ++p) q_remaining[p] = (output.bus_injection[bus].v[p] - s_load_gen_bus.v[p]).imag();
+    LimitViolation const bus_limit_violated =
+        output.bus_q_limit_violated.empty() ? LimitViolation::none : output.bus_q_limit_violated[bus];
+    if (bus_limit_violated == LimitViolation::none) {
+        // allocate_q_iterative_distribution (:321-381)
+        for (auto& st : state) st.has_available_capacity = true;
+        int n_active = num_regulating;
+        while (std::abs(total_q<B>(q_remaining)) > numerical_tolerance && n_active > 0) {
+            double q_per_regulator[B], q_unallocated[B] = {};
+            for (int p = 0; p < B; ++p) q_per_regulator[p] = q_remaining[p] / n_active;
+            for (auto& st : state) {
+                if (!st.has_available_capacity) continue;
+                auto const& in_reg = input.voltage_regulator[st.regulator_idx];
+                double q_prev[B], q_next[B];
+                for (int p = 0; p < B; ++p) {
+                    q_prev[p] = st.q_allocated[p];
+                    q_next[p] = q_prev[p] + q_per_regulator[p];
+                }
+                double const q_next_scalar = total_q<B>(q_next);
+                bool const hit_upper = !std::isnan(in_reg.q_max) && q_next_scalar > in_reg.q_max + numerical_tolerance;
+                bool const hit_lower =
+                    !hit_upper && !std::isnan(in_reg.q_min) && q_next_scalar < in_reg.q_min - numerical_tolerance;
+                if (hit_upper || hit_lower) {
+                    distribute_q<B>(hit_upper ? in_reg.q_max : in_reg.q_min, q_next, st.q_allocated);
+                    st.has_available_capacity = false;
+                    for (int p = 0; p < B; ++p) q_unallocated[p] += q_per_regulator[p] - (st.q_allocated[p] - q_prev[p]);
+                    n_active -= 1;
+                } else {
+                    for (int p = 0; p < B; ++p) st.q_allocated[p] = q_next[p];
+                }
+                output.voltage_regulator[st.regulator_idx].limit_violated = LimitViolation::none;
+            }
+            double diff[B];
+            for (int p = 0; p < B; ++p) diff[p] = q_remaining[p] - q_unallocated[p];
+            if (std::abs(total_q<B>(diff)) < numerical_tolerance) {
+                throw PgmError{"Unallocated Q remains after distribution on"};
+            }
+            for (int p = 0; p < B; ++p) q_remaining[p] = q_unallocated[p];
+        }
+    } else {
+        // allocate_q_bus_limit_violated (:293-318)
+        for (auto& st : state) {
+            auto const& in_reg = input.voltage_regulator[st.regulator_idx];
+            output.voltage_regulator[st.regulator_idx].limit_violated = bus_limit_violated;
+            double const limit_value = bus_limit_violated == LimitViolation::upper ? in_reg.q_max : in_reg.q_min;
+            double const q_limit_scalar = std::isnan(limit_value) ? 0.0 : limit_value;
+            double base_q[B];
+            for (int p = 0; p < B; ++p) base_q[p] = output.load_gen[st.load_gen_idx].s.v[p].imag();
+            distribute_q<B>(q_limit_scalar, base_q, st.q_allocated);
+            st.has_available_capacity = false;
+        }
+    }
+    // 3. apply to the generators (:272-289)
+    for (auto const& st : state) {
+        auto& lg_out = output.load_gen[st.load_gen_idx];
+        for (int p = 0; p < B; ++p) lg_out.s.v[p] = cplx{lg_out.s.v[p].real(), st.q_allocated[p]};
+        lg_out.i = conj(lg_out.s / output.u[bus]);
+    }
+}
+
 template <int B, class LoadGenFunc>
 inline void calculate_pf_result(YBus<B> const& y_bus, PowerFlowInput<B> const& input, SolverOutput<B>& output,
                                 LoadGenFunc load_gen_func) {
@@ -79,6 +202,7 @@ inline void calculate_pf_result(YBus<B> const& y_bus, PowerFlowInput<B> const& i
     output.load_gen.assign(topo.n_load_gen(), {});
     output.bus_injection.resize(topo.n_bus());
     for (Idx bus = 0; bus != topo.n_bus(); ++bus) output.bus_injection[bus] = y_bus.calculate_injection(output.u, bus);
+    output.voltage_regulator.assign(topo.n_voltage_regulator(), {});
 
     for (Idx bus = 0; bus != topo.n_bus(); ++bus) {
         Idx const lg_begin = topo.load_gens_per_bus[bus], lg_end = topo.load_gens_per_bus[bus + 1];
@@ -98,6 +222,9 @@ inline void calculate_pf_result(YBus<B> const& y_bus, PowerFlowInput<B> const& i
                 throw PgmError{"unknown load_gen type"};
             }
             output.load_gen[lg].i = conj(output.load_gen[lg].s / output.u[bus]);
+        }
+        if (!topo.voltage_regulators_per_load_gen.empty()) {
+            calculate_voltage_regulator_result<B>(bus, lg_begin, lg_end, topo, input, output);
         }
         if (s_begin == s_end) continue;
         CVec<B> i_load_gen_bus{};
@@ -126,9 +253,11 @@ template <int B> class NewtonRaphsonPFSolver {
           x_(n_bus_ * N),
           del_x_pq_(n_bus_ * N),
           solver_{y_bus.structure().row_indptr_lu, y_bus.structure().col_indices_lu, y_bus.structure().diag_lu},
-          perm_(n_bus_) {}
+          perm_(n_bus_),
+          bus_control_(n_bus_) {}
 
-    SolverOutput<B> run_power_flow(YBus<B> const& y_bus, PowerFlowInput<B> const& input, double err_tol, Idx max_iter) {
+    SolverOutput<B> run_power_flow(YBus<B> const& y_bus, PowerFlowInput<B> const& input, double err_tol, Idx max_iter,
+                                   bool cache_run = false) {
         SolverOutput<B> output;
         output.u.resize(n_bus_);
         double max_dev = std::numeric_limits<double>::infinity();
@@ -138,11 +267,19 @@ template <int B> class NewtonRaphsonPFSolver {
             if (num_iter++ == max_iter) {
                 throw IterationDiverge{max_iter, max_dev, err_tol};
             }
-            build_jacobian_and_rhs(y_bus, input, output.u);
+            // prepare_matrix_and_rhs (:306-319)
+            build_jacobian_and_rhs(y_bus, input, output.u, false);
+            if (limit_check_countdown_ > 0) --limit_check_countdown_;
+            bool const buses_switched = (limit_check_countdown_ == 0) && enforce_q_limits(y_bus, input);
+            if (buses_switched) build_jacobian_and_rhs(y_bus, input, output.u, true);
+            apply_pv_constraints(y_bus);
             solver_.prefactorize_and_solve(data_jac_, perm_, del_x_pq_, del_x_pq_);
-            max_dev = iterate_unknown(output.u);
+            max_dev = iterate_unknown(output.u, err_tol, cache_run);
         }
         output.num_iter = num_iter;
+        // finalize_result (:351-360)
+        output.bus_q_limit_violated.resize(n_bus_);
+        for (Idx i = 0; i != n_bus_; ++i) output.bus_q_limit_violated[i] = bus_control_[i].limit_violated;
         auto const& lgt = y_bus.topo().load_gen_type;
         calculate_pf_result<B>(y_bus, input, output, [&lgt](Idx i) { return lgt[i]; });
         return output;
@@ -158,6 +295,136 @@ template <int B> class NewtonRaphsonPFSolver {
     std::vector<double> del_x_pq_; // per bus: p[B], q[B]
     Solver solver_;
     typename Solver::PermArray perm_;
+    // PV buses / Q limits (:374-397)
+    struct BusControlState {
+        BusType type{BusType::pq};
+        cplx u_ref{};
+        bool has_q_limits{false};
+        bool recalc_after_limit_violation{false};
+        LimitViolation limit_violated{LimitViolation::none};
+        double bus_q_min{0.0};
+        double bus_q_max{0.0};
+    };
+    std::vector<BusControlState> bus_control_;
+    Idx limit_check_countdown_{-1}; // -1 no check, 0 check now, > 0 iterations to wait
+    std::vector<std::array<double, B>> clamped_q_; // per load_gen, NaN = not clamped
+
+    static bool regulates(YBus<B> const& y_bus, PowerFlowInput<B> const& input, Idx lg, Idx reg) {
+        (void)y_bus;
+        return input.voltage_regulator[reg].status != 0 && input.load_gen_status[lg] != 0;
+    }
+
+    // set_bus_types_and_q_limits (:400-444)
+    bool set_bus_types_and_q_limits(YBus<B> const& y_bus, PowerFlowInput<B> const& input) {
+        auto const& topo = y_bus.topo();
+        bool has_usable_q_limits = false;
+        if (topo.voltage_regulators_per_load_gen.empty()) {
+            for (Idx bus = 0; bus != n_bus_; ++bus)
+                if (topo.sources_per_bus[bus] != topo.sources_per_bus[bus + 1]) bus_control_[bus].type = BusType::slack;
+            return false;
+        }
+        for (Idx bus = 0; bus != n_bus_; ++bus) {
+            auto& bc = bus_control_[bus];
+            if (topo.sources_per_bus[bus] != topo.sources_per_bus[bus + 1]) {
+                bc.type = BusType::slack;
+                continue;
+            }
+            for (Idx lg = topo.load_gens_per_bus[bus]; lg != topo.load_gens_per_bus[bus + 1]; ++lg) {
+                if (input.load_gen_status.empty() || input.load_gen_status[lg] == 0) continue;
+                for (Idx reg = topo.voltage_regulators_per_load_gen[lg]; reg != topo.voltage_regulators_per_load_gen[lg + 1]; ++reg) {
+                    auto const& regulator = input.voltage_regulator[reg];
+                    if (regulator.status != 0) {
+                        bc.type = BusType::pv;
+                        bc.u_ref = regulator.u_ref;
+                        bc.bus_q_min += regulator.q_min;
+                        bc.bus_q_max += regulator.q_max;
+                    }
+                }
+            }
+            if (bc.type == BusType::pv) {
+                bc.has_q_limits = !std::isnan(bc.bus_q_min) || !std::isnan(bc.bus_q_max);
+                if (bc.has_q_limits) has_usable_q_limits = true;
+            }
+        }
+        return has_usable_q_limits;
+    }
+
+    // apply_pv_constraints (:549-587): M row zero, L row zero except diag = V, q mismatch = 0
+    void apply_pv_constraints(YBus<B> const& y_bus) {
+        auto const& s = y_bus.structure();
+        for (Idx row = 0; row != n_bus_; ++row) {
+            if (bus_control_[row].type != BusType::pv) continue;
+            for (Idx k = s.row_indptr_lu[row]; k != s.row_indptr_lu[row + 1]; ++k) {
+                for (int r = 0; r < B; ++r)
+                    for (int c = 0; c < B; ++c) {
+                        el(k, 1, 0, r, c) = 0.0;
+                        el(k, 1, 1, r, c) = 0.0;
+                    }
+                if (s.col_indices_lu[k] == row)
+                    for (int p = 0; p < B; ++p) el(k, 1, 1, p, p) = v(row, p);
+            }
+            for (int p = 0; p < B; ++p) dq(row, p) = 0.0;
+        }
+    }
+
+    // enforce_q_limits (:605-704)
+    bool enforce_q_limits(YBus<B> const& y_bus, PowerFlowInput<B> const& input) {
+        auto const& topo = y_bus.topo();
+        bool switched = false;
+        for (Idx bus = 0; bus != n_bus_; ++bus) {
+            auto& bc = bus_control_[bus];
+            if (bc.type != BusType::pv || !bc.has_q_limits) continue;
+            double specified_regulating_q[B] = {};
+            for (Idx lg = topo.load_gens_per_bus[bus]; lg != topo.load_gens_per_bus[bus + 1]; ++lg) {
+                if (input.load_gen_status[lg] == 0) continue;
+                for (Idx reg = topo.voltage_regulators_per_load_gen[lg]; reg != topo.voltage_regulators_per_load_gen[lg + 1]; ++reg) {
+                    if (input.voltage_regulator[reg].status != 0) {
+                        if (topo.load_gen_type[lg] != LoadGenType::const_pq) {
+                            throw PgmError{"Voltage regulator(s) " + std::to_string(reg) + " regulate(s) a load/generator with unsupported type"};
+                        }
+                        for (int p = 0; p < B; ++p) specified_regulating_q[p] += input.s_injection[lg].v[p].imag();
+                    }
+                }
+            }
+            double q_total = 0.0;
+            for (int p = 0; p < B; ++p) {
+                double const q_required = specified_regulating_q[p] - dq(bus, p);
+                q_total = p == 0 ? q_required : q_total + q_required;
+            }
+            LimitViolation limit = LimitViolation::none;
+            if (!std::isnan(bc.bus_q_max) && q_total > bc.bus_q_max + numerical_tolerance) {
+                limit = LimitViolation::upper;
+            } else if (!std::isnan(bc.bus_q_min) && q_total < bc.bus_q_min - numerical_tolerance) {
+                limit = LimitViolation::lower;
+            }
+            if (limit == LimitViolation::none) continue;
+            for (Idx lg = topo.load_gens_per_bus[bus]; lg != topo.load_gens_per_bus[bus + 1]; ++lg) {
+                for (Idx reg = topo.voltage_regulators_per_load_gen[lg]; reg != topo.voltage_regulators_per_load_gen[lg + 1]; ++reg) {
+                    if (input.load_gen_status[lg] == 0 || input.voltage_regulator[reg].status == 0) continue;
+                    double const q_limit_scalar =
+                        limit == LimitViolation::upper ? input.voltage_regulator[reg].q_max : input.voltage_regulator[reg].q_min;
+                    if constexpr (B == 1) {
+                        clamped_q_[lg][0] = q_limit_scalar;
+                    } else {
+                        double base_q[3];
+                        for (int p = 0; p < 3; ++p) base_q[p] = input.s_injection[lg].v[p].imag();
+                        double const base_q_total = base_q[0] + base_q[1] + base_q[2];
+                        if (std::abs(base_q_total) > numerical_tolerance) {
+                            double const scale = q_limit_scalar / base_q_total;
+                            for (int p = 0; p < 3; ++p) clamped_q_[lg][p] = base_q[p] * scale;
+                        } else {
+                            for (int p = 0; p < 3; ++p) clamped_q_[lg][p] = q_limit_scalar / 3.0;
+                        }
+                    }
+                }
+            }
+            bc.limit_violated = limit;
+            bc.recalc_after_limit_violation = true;
+            bc.type = BusType::pq;
+            switched = true;
+        }
+        return switched;
+    }
 
     double* blk(Idx k) { return &data_jac_[k * NN]; }
     // element (r, c) of sub-block (br, bc) of block k
@@ -172,6 +439,13 @@ template <int B> class NewtonRaphsonPFSolver {
         auto const& topo = y_bus.topo();
         std::fill(data_jac_.begin(), data_jac_.end(), 0.0);
         std::fill(del_x_pq_.begin(), del_x_pq_.end(), 0.0);
+        bus_control_.assign(n_bus_, BusControlState{});
+        std::array<double, B> nan_q;
+        nan_q.fill(std::numeric_limits<double>::quiet_NaN());
+        clamped_q_.assign(topo.n_load_gen(), nan_q);
+        bool const has_usable_limits = set_bus_types_and_q_limits(y_bus, input);
+        limit_check_countdown_ = has_usable_limits ? 2 : -1; // limit_check_at_iteration / no_limit_check (:169-171)
+        bool const has_regulators = !topo.voltage_regulators_per_load_gen.empty();
         auto const& ydata = y_bus.admittance();
         for (Idx k = 0; k != y_bus.nnz_lu(); ++k) {
             Idx const ky = s.map_lu_y_bus[k];
@@ -190,9 +464,17 @@ template <int B> class NewtonRaphsonPFSolver {
         for (Idx bus = 0; bus != n_bus_; ++bus) {
             Idx const d = s.diag_lu[bus];
             for (Idx lg = topo.load_gens_per_bus[bus]; lg != topo.load_gens_per_bus[bus + 1]; ++lg) {
-                // y_load = -conj(s)
+                // y_load = -conj(s); the specified Q of a regulated load_gen is ignored (:706-742)
+                bool is_regulated = false;
+                if (has_regulators)
+                    for (Idx reg = topo.voltage_regulators_per_load_gen[lg]; reg != topo.voltage_regulators_per_load_gen[lg + 1]; ++reg)
+                        if (regulates(y_bus, input, lg, reg)) {
+                            is_regulated = true;
+                            break;
+                        }
                 for (int p = 0; p < B; ++p) {
-                    cplx const y_load = -std::conj(input.s_injection[lg].v[p]);
+                    cplx const s_in = is_regulated ? cplx{input.s_injection[lg].v[p].real(), 0.0} : input.s_injection[lg].v[p];
+                    cplx const y_load = -std::conj(s_in);
                     el(d, 0, 1, p, p) += -y_load.imag();
                     el(d, 0, 0, p, p) += y_load.real();
                     el(d, 1, 1, p, p) += y_load.real();
@@ -220,6 +502,8 @@ template <int B> class NewtonRaphsonPFSolver {
         for (Idx i = 0; i != n_bus_; ++i) {
             for (int p = 0; p < B; ++p) {
                 output.u[i].v[p] = cplx{dp(i, p), dq(i, p)};
+                // set_reference_voltage_for_pv_buses (:446-452)
+                if (bus_control_[i].type == BusType::pv) output.u[i].v[p] = bus_control_[i].u_ref * phase_shift(output.u[i].v[p]);
                 v(i, p) = cabs(output.u[i].v[p]);
                 theta(i, p) = std::arg(output.u[i].v[p]);
             }
@@ -242,11 +526,14 @@ template <int B> class NewtonRaphsonPFSolver {
     static double bh(double const* b, int r, int c) { return b[(0 * B + c) * N + r]; }
     static double bn(double const* b, int r, int c) { return b[(1 * B + c) * N + r]; }
 
-    void build_jacobian_and_rhs(YBus<B> const& y_bus, PowerFlowInput<B> const& input, std::vector<CVec<B>> const& u) {
+    void build_jacobian_and_rhs(YBus<B> const& y_bus, PowerFlowInput<B> const& input, std::vector<CVec<B>> const& u,
+                                bool partial_rebuild) {
         auto const& s = y_bus.structure();
         auto const& topo = y_bus.topo();
         auto const& ydata = y_bus.admittance();
         for (Idx row = 0; row != n_bus_; ++row) {
+            // only the rows of buses that switched from PV to PQ are rebuilt (:477-482)
+            if (partial_rebuild && !bus_control_[row].recalc_after_limit_violation) continue;
             for (int p = 0; p < B; ++p) {
                 dp(row, p) = 0.0;
                 dq(row, p) = 0.0;
@@ -279,8 +566,19 @@ template <int B> class NewtonRaphsonPFSolver {
             }
         }
         for (Idx bus = 0; bus != n_bus_; ++bus) {
+            if (partial_rebuild) {
+                if (!bus_control_[bus].recalc_after_limit_violation) continue;
+                bus_control_[bus].recalc_after_limit_violation = false;
+            }
             Idx const d = s.diag_lu[bus];
             for (Idx lg = topo.load_gens_per_bus[bus]; lg != topo.load_gens_per_bus[bus + 1]; ++lg) {
+                if (!std::isnan(clamped_q_[lg][0])) { // the load_gen hit a Q limit: use the clamped value (:768-776)
+                    for (int p = 0; p < B; ++p) {
+                        dp(bus, p) += input.s_injection[lg].v[p].real();
+                        dq(bus, p) += clamped_q_[lg][p];
+                    }
+                    continue;
+                }
                 for (int p = 0; p < B; ++p) {
                     double const ps = input.s_injection[lg].v[p].real();
                     double const qs = input.s_injection[lg].v[p].imag();
@@ -337,7 +635,7 @@ template <int B> class NewtonRaphsonPFSolver {
         }
     }
 
-    double iterate_unknown(std::vector<CVec<B>>& u) {
+    double iterate_unknown(std::vector<CVec<B>>& u, double err_tol, bool cache_run) {
         double max_dev = 0.0;
         for (Idx i = 0; i != n_bus_; ++i) {
             double dev_bus = 0.0;
@@ -350,6 +648,11 @@ template <int B> class NewtonRaphsonPFSolver {
                 u[i].v[p] = u_tmp;
             }
             max_dev = std::max(dev_bus, max_dev);
+        }
+        if (max_dev <= err_tol && limit_check_countdown_ > 0 && !cache_run) {
+            // converged before the limit check happened: force the check in one more iteration (:343-347)
+            limit_check_countdown_ = 0;
+            return std::numeric_limits<double>::infinity();
         }
         return max_dev;
     }
@@ -523,13 +826,14 @@ template <int B> class MathSolver {
                                    [](LoadGenType x) { return x == LoadGenType::const_y; })} {}
 
     SolverOutput<B> run_power_flow(PowerFlowInput<B> const& input, double err_tol, Idx max_iter,
-                                   CalculationMethod method, YBus<B> const& y_bus, bool reuse_ic_factorization = false) {
+                                   CalculationMethod method, YBus<B> const& y_bus, bool reuse_ic_factorization = false,
+                                   bool cache_run = false) {
         method = all_const_y_ ? CalculationMethod::linear : method;
         switch (method) {
         case CalculationMethod::default_method:
         case CalculationMethod::newton_raphson:
             if (!nr_) nr_.emplace(y_bus);
-            return nr_->run_power_flow(y_bus, input, err_tol, max_iter);
+            return nr_->run_power_flow(y_bus, input, err_tol, max_iter, cache_run);
         case CalculationMethod::linear:
             if (!lin_) lin_.emplace(y_bus);
             return lin_->run_power_flow(y_bus, input);

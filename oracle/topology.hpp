@@ -32,6 +32,7 @@ struct ComponentTopology {
     IdxVector source_node_idx;
     IdxVector load_gen_node_idx;
     std::vector<LoadGenType> load_gen_type;
+    IdxVector regulated_load_gen_idx; // per voltage regulator: sequence index of the regulated load_gen
     Idx n_node_total() const { return n_node + static_cast<Idx>(branch3_node_idx.size()); }
 };
 struct ComponentConnections {
@@ -42,7 +43,7 @@ struct ComponentConnections {
     std::vector<IntS> source_connected;
 };
 struct ComponentToMathCoupling {
-    std::vector<Idx2D> node, branch, shunt, load_gen, source;
+    std::vector<Idx2D> node, branch, shunt, load_gen, source, voltage_regulator;
     std::vector<std::pair<Idx, Branch3Idx>> branch3; // group, pos[3]
 };
 
@@ -415,6 +416,30 @@ class Topology {
         }
         couple_objects(ct_.source_node_idx, &MathTopology::sources_per_bus, coup_.source,
                        [this](Idx i) { return cc_.source_connected[i] != 0; });
+        couple_voltage_regulators();
+    }
+
+    // topology.hpp:594-600: regulators grouped by the math load_gen they regulate (stable counting sort)
+    void couple_voltage_regulators() {
+        coup_.voltage_regulator.assign(ct_.regulated_load_gen_idx.size(), Idx2D{-1, -1});
+        Idx const n_math = static_cast<Idx>(math_.size());
+        std::vector<IdxVector> obj(n_math), comp(n_math);
+        for (size_t r = 0; r != ct_.regulated_load_gen_idx.size(); ++r) {
+            Idx2D const m = coup_.load_gen[ct_.regulated_load_gen_idx[r]];
+            if (m.group >= 0) {
+                obj[m.group].push_back(m.pos);
+                comp[m.group].push_back(static_cast<Idx>(r));
+            }
+        }
+        for (Idx g = 0; g != n_math; ++g) {
+            Idx const n_lg = math_[g].n_load_gen();
+            IdxVector& indptr = math_[g].voltage_regulators_per_load_gen;
+            indptr.assign(n_lg + 1, 0);
+            for (Idx const lg : obj[g]) ++indptr[lg + 1];
+            for (Idx i = 0; i != n_lg; ++i) indptr[i + 1] += indptr[i];
+            IdxVector cursor(indptr.begin(), indptr.end() - 1);
+            for (size_t k = 0; k != obj[g].size(); ++k) coup_.voltage_regulator[comp[g][k]] = {g, cursor[obj[g][k]]++};
+        }
     }
 };
 

@@ -30,12 +30,14 @@ struct MathTopology {
     IdxVector shunts_per_bus;    // indptr
     IdxVector load_gens_per_bus; // indptr
     std::vector<LoadGenType> load_gen_type;
+    IdxVector voltage_regulators_per_load_gen; // indptr over the load_gens (empty = no regulators), topology.hpp:594-600
 
     Idx n_bus() const { return static_cast<Idx>(phase_shift.size()); }
     Idx n_branch() const { return static_cast<Idx>(branch_bus_idx.size()); }
     Idx n_source() const { return sources_per_bus.empty() ? 0 : sources_per_bus.back(); }
     Idx n_shunt() const { return shunts_per_bus.empty() ? 0 : shunts_per_bus.back(); }
     Idx n_load_gen() const { return load_gens_per_bus.empty() ? 0 : load_gens_per_bus.back(); }
+    Idx n_voltage_regulator() const { return voltage_regulators_per_load_gen.empty() ? 0 : voltage_regulators_per_load_gen.back(); }
 };
 
 struct SourceCalcParam {
@@ -60,9 +62,25 @@ template <int B> struct MathParam {
     std::vector<SourceCalcParam> source_param;
 };
 
+enum class BusType : IntS { pq = 0, pv = 1, slack = 2 };
+enum class LimitViolation : IntS { none = 0, lower = 1, upper = 2 };
+struct VoltageRegulatorCalcParam { // calculation_parameters.hpp:228-236
+    IntS status{};
+    cplx u_ref{};
+    double q_min{};
+    double q_max{};
+    ID generator_id{};
+};
+struct VoltageRegulatorSolverOutput { // calculation_parameters.hpp:94-100
+    LimitViolation limit_violated{};
+    ID generator_id{};
+    IntS generator_status{};
+};
 template <int B> struct PowerFlowInput {
     std::vector<cplx> source;         // u_ref of each source
     std::vector<CVec<B>> s_injection; // specified power of each load_gen
+    std::vector<VoltageRegulatorCalcParam> voltage_regulator; // math order (grouped by load_gen)
+    std::vector<IntS> load_gen_status;                        // only filled when the grid has voltage regulators
 };
 
 template <int B> struct BranchSolverOutput {
@@ -78,6 +96,8 @@ template <int B> struct SolverOutput {
     std::vector<ApplianceSolverOutput<B>> source;
     std::vector<ApplianceSolverOutput<B>> shunt;
     std::vector<ApplianceSolverOutput<B>> load_gen;
+    std::vector<LimitViolation> bus_q_limit_violated; // BusSolverOutput (calculation_parameters.hpp:46-49)
+    std::vector<VoltageRegulatorSolverOutput> voltage_regulator;
     Idx num_iter{}; // the reference only logs this (iterative_pf_solver.hpp:87)
 };
 

@@ -57,6 +57,7 @@ class MathTopologyC(C.Structure):
         ("n_bus", C.c_int64), ("phase_shift", C.c_void_p), ("n_branch", C.c_int64), ("branch_bus_idx", C.c_void_p),
         ("n_fill_in", C.c_int64), ("fill_in", C.c_void_p), ("sources_per_bus", C.c_void_p),
         ("shunts_per_bus", C.c_void_p), ("load_gens_per_bus", C.c_void_p), ("load_gen_type", C.c_void_p),
+        ("voltage_regulators_per_load_gen", C.c_void_p),
     ]
 
 
@@ -70,18 +71,19 @@ class RunOptionsC(C.Structure):
 
 class PfInputC(C.Structure):
     _fields_ = [("n_scenarios", C.c_int64), ("source_u_ref", C.c_void_p), ("source_is_shared", C.c_int32),
-                ("s_injection", C.c_void_p)]
+                ("s_injection", C.c_void_p), ("voltage_regulator", C.c_void_p), ("load_gen_status", C.c_void_p)]
 
 
 class SolverOutputC(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("u", "bus_injection", "branch", "source", "shunt", "load_gen", "status", "n_iter", "max_dev")]
+    _fields_ = [(n, C.c_void_p) for n in ("u", "bus_injection", "branch", "source", "shunt", "load_gen", "status", "n_iter", "max_dev",
+                                               "voltage_regulator")]
 
 
 class ComponentBufferC(C.Structure):
     _fields_ = [("n", C.c_int64), ("indptr", C.c_void_p), ("data", C.c_void_p)]
 
 
-_COMPS = ("node", "line", "transformer", "shunt", "source", "sym_gen", "asym_gen", "sym_load", "asym_load")
+_COMPS = ("node", "line", "transformer", "shunt", "source", "sym_gen", "asym_gen", "sym_load", "asym_load", "voltage_regulator")
 
 
 class InputDataC(C.Structure):

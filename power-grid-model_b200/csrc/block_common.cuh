@@ -35,6 +35,9 @@ template <int T, int B, bool SymPerm = false> struct TileB {
     double* wide_terms; // [max_upd][NN][T]
     double* wide_rhs;   // [max_lower][N][T]
     double* wide_sum;   // [max_entries][N][T]
+    // PV buses (only read by the REG instantiations)
+    uint8_t const* lg_status; // [n_load_gen][T]
+    uint8_t* qviol;           // [n_bus][T]
     __device__ __forceinline__ void get_q(int bus, uint8_t* q) const {
         if constexpr (SymPerm) {
             static_assert(!SymPerm || B == 1, "byte-packed permutation is a 2 x 2 layout");
@@ -194,6 +197,104 @@ template <int N> __device__ bool factorize_block(double* m, uint8_t* p, uint8_t*
     return singular;
 }
 
+// ---- PV buses / reactive-power limits of voltage regulators -------------------------------------------------------------
+//   newton_raphson_pf_solver.hpp:400-444 (bus types and limits), 446-452 (reference voltage after the linear start),
+//   549-587 (PV rows of the Jacobian), 605-704 (limit check, PV -> PQ switch with clamped Q), 706-742 (linear start ignores
+//   the Q of a regulating generator).  Every decision is local to the bus; the only per-scenario state is the iteration
+//   number (the check runs from iteration 2 on) and DevBatch.qviol.
+constexpr double kNumTol = 1e-8;
+struct BusControl {
+    bool regulated;  // a regulating (status on, generator on) regulator sits on this non-slack bus
+    bool has_limits;
+    double u_ref, q_min, q_max;
+};
+template <int T, int B, bool SP>
+__device__ __forceinline__ bool lg_regulating(DevStructure const& s, TileB<T, B, SP> const& t, int lg, int& reg) {
+    reg = __ldg(s.lg_reg + lg);
+    return reg >= 0 && __ldg(s.reg_param + 4 * reg) != 0.0 && t.lg_status[(size_t)lg * T] != 0;
+}
+template <int T, int B, bool SP>
+__device__ BusControl bus_control(DevStructure const& s, TileB<T, B, SP> const& t, int row) {
+    BusControl c{false, false, 0.0, 0.0, 0.0};
+    if (__ldg(s.src_ptr + row) != __ldg(s.src_ptr + row + 1)) return c; // slack bus
+    for (int lg = __ldg(s.lg_ptr + row), lge = __ldg(s.lg_ptr + row + 1); lg < lge; ++lg) {
+        int reg;
+        if (lg_regulating<T, B, SP>(s, t, lg, reg)) {
+            c.regulated = true;
+            c.u_ref = __ldg(s.reg_param + 4 * reg + 1);
+            c.q_min += __ldg(s.reg_param + 4 * reg + 2);
+            c.q_max += __ldg(s.reg_param + 4 * reg + 3);
+        }
+    }
+    c.has_limits = c.regulated && (!isnan(c.q_min) || !isnan(c.q_max));
+    return c;
+}
+// Q of a regulating generator whose bus ran into limit `viol` (1 lower, 2 upper): the regulator's limit, spread over the
+// phases in proportion to the specified Q (equally when that is ~0)
+template <int T, int B, bool SP>
+__device__ __forceinline__ void clamped_q(DevStructure const& s, TileB<T, B, SP> const& t, int lg, int reg, int viol, double* out) {
+    constexpr int N = 2 * B;
+    double const lim = __ldg(s.reg_param + 4 * reg + (viol == 2 ? 3 : 2));
+    if constexpr (B == 1) {
+        out[0] = lim;
+    } else {
+        double base[B];
+#pragma unroll
+        for (int p = 0; p < B; ++p) base[p] = t.sinj[(size_t)(lg * N + 2 * p + 1) * T];
+        double const total = base[0] + base[1] + base[2];
+        if (fabs(total) > kNumTol) {
+            double const scale = lim / total;
+#pragma unroll
+            for (int p = 0; p < B; ++p) out[p] = base[p] * scale;
+        } else {
+#pragma unroll
+            for (int p = 0; p < B; ++p) out[p] = lim / 3.0;
+        }
+    }
+}
+// enforce_q_limits for one PV bus; acc = mismatch of the freshly built row.  Returns the violated limit (0 = none).
+template <int T, int B, bool SP>
+__device__ int check_q_limit(DevStructure const& s, TileB<T, B, SP> const& t, int row, BusControl const& c, double const* acc) {
+    constexpr int N = 2 * B;
+    double spec[B];
+#pragma unroll
+    for (int p = 0; p < B; ++p) spec[p] = 0.0;
+    for (int lg = __ldg(s.lg_ptr + row), lge = __ldg(s.lg_ptr + row + 1); lg < lge; ++lg) {
+        int reg;
+        if (!lg_regulating<T, B, SP>(s, t, lg, reg)) continue;
+#pragma unroll
+        for (int p = 0; p < B; ++p) spec[p] += t.sinj[(size_t)(lg * N + 2 * p + 1) * T];
+    }
+    double q_total = spec[0] - acc[B];
+#pragma unroll
+    for (int p = 1; p < B; ++p) q_total += spec[p] - acc[B + p];
+    if (!isnan(c.q_max) && q_total > c.q_max + kNumTol) return 2;
+    if (!isnan(c.q_min) && q_total < c.q_min - kNumTol) return 1;
+    return 0;
+}
+// apply_pv_constraints on the diagonal block and the mismatch of a PV row (the other blocks: zero_pv_rows)
+template <int T, int B, bool SP>
+__device__ __forceinline__ void pv_diag(TileB<T, B, SP> const& t, int row, double* d, double* acc) {
+    constexpr int N = 2 * B;
+#pragma unroll
+    for (int c = 0; c < N; ++c)
+#pragma unroll
+        for (int r = B; r < N; ++r) d[c * N + r] = 0.0;
+#pragma unroll
+    for (int p = 0; p < B; ++p) {
+        d[el<B>(1, 1, p, p)] = t.pol[(size_t)(row * N + B + p) * T];
+        acc[B + p] = 0.0;
+    }
+}
+template <int T, int B, bool SP> __device__ __forceinline__ void zero_pv_rows(TileB<T, B, SP> const& t, int k) {
+    constexpr int N = 2 * B, NN = N * N;
+    double* p = t.jac + (size_t)k * NN * T;
+#pragma unroll
+    for (int c = 0; c < N; ++c)
+#pragma unroll
+        for (int r = B; r < N; ++r) p[(size_t)(c * N + r) * T] = 0.0;
+}
+
 // block of LU entry k of row `row` (zero for a fill-in) and, for the Newton step, its contribution to the row sums
 // (contrib[r] = sum_c N[r][c], contrib[B + r] = sum_c H[r][c])
 template <int T, int B, Mode mode, bool SP>
@@ -232,9 +333,10 @@ __device__ __forceinline__ void build_entry(DevStructure const& s, TileB<T, B, S
 }
 
 // diagonal corrections from the row sums, loads and sources of the bus (acc = row sums on entry, mismatch / rhs on exit)
-template <int T, int B, Mode mode, bool SP>
+// REG: the grid has voltage regulators; viol = limit the bus ran into (its regulating generators then inject the clamped Q)
+template <int T, int B, Mode mode, bool SP, bool REG = false>
 __device__ __forceinline__ void finish_diag(DevStructure const& s, TileB<T, B, SP> const& t, int row, double const* uir,
-                                            double const* uii, double* acc, double* d) {
+                                            double const* uii, double* acc, double* d, int viol = 0) {
     constexpr int N = 2 * B, NN = N * N, BB2 = B * B * 2;
     if constexpr (mode == Mode::newton) {
 #pragma unroll
@@ -248,9 +350,22 @@ __device__ __forceinline__ void finish_diag(DevStructure const& s, TileB<T, B, S
     // loads
     for (int lg = __ldg(s.lg_ptr + row), lge = __ldg(s.lg_ptr + row + 1); lg < lge; ++lg) {
         int const type = __ldg(s.lg_type + lg);
+        [[maybe_unused]] double qclamp[B];
+        [[maybe_unused]] bool regulating = false;
+        if constexpr (REG) {
+            int reg;
+            regulating = lg_regulating<T, B, SP>(s, t, lg, reg);
+            if (mode == Mode::newton && regulating && viol != 0) clamped_q<T, B, SP>(s, t, lg, reg, viol, qclamp);
+        }
 #pragma unroll
         for (int p = 0; p < B; ++p) {
-            double const ps = t.sinj[(size_t)(lg * N + 2 * p) * T], qs = t.sinj[(size_t)(lg * N + 2 * p + 1) * T];
+            double const ps = t.sinj[(size_t)(lg * N + 2 * p) * T];
+            double qs = t.sinj[(size_t)(lg * N + 2 * p + 1) * T];
+            if constexpr (REG) {
+                // linear start: the specified Q of a regulating generator is ignored; Newton: clamped once the bus hit a limit
+                if (regulating && mode == Mode::linear_init) qs = 0.0;
+                if (regulating && mode == Mode::newton && viol != 0) qs = qclamp[p];
+            }
             if constexpr (mode == Mode::newton) {
                 double const v = t.pol[(size_t)(row * N + B + p) * T];
                 if (type == 0) {
@@ -346,35 +461,61 @@ __device__ __forceinline__ void finish_diag(DevStructure const& s, TileB<T, B, S
     }
 }
 
-template <int T, int B, Mode mode, bool SP = false>
-__device__ bool up_row(DevStructure const& s, TileB<T, B, SP> const& t, int row) {
+template <int T, int B, Mode mode, bool SP = false, bool REG = false>
+__device__ bool up_row(DevStructure const& s, TileB<T, B, SP> const& t, int row, bool check_now = false) {
     constexpr int N = 2 * B, NN = N * N;
     int const rb = __ldg(s.row_ptr + row), re = __ldg(s.row_ptr + row + 1), dg = __ldg(s.diag + row);
     double uir[B], uii[B];
     t.load_u(row, uir, uii);
     double acc[N]; // NR: -P[B], -Q[B] then mismatch ; linear: rhs real[B], imag[B]
-#pragma unroll
-    for (int i = 0; i < N; ++i) acc[i] = 0.0;
     double d[NN];
+    [[maybe_unused]] BusControl ctl{};
+    [[maybe_unused]] int viol = 0;
+    if constexpr (REG && mode == Mode::newton) {
+        ctl = bus_control<T, B, SP>(s, t, row);
+        viol = t.qviol[(size_t)row * T];
+    }
+    constexpr int n_pass = (REG && mode == Mode::newton) ? 2 : 1;
+#pragma unroll 1
+    for (int pass = 0; pass < n_pass; ++pass) { // a second pass only for a PV bus that has just run into a Q limit
 #pragma unroll
-    for (int i = 0; i < NN; ++i) d[i] = 0.0;
-
-    // 1. build the row
-    for (int k = rb; k < re; ++k) {
-        double blk[NN], contrib[N];
-        build_entry<T, B, mode, SP>(s, t, uir, uii, k, blk, contrib);
-        if (__ldg(s.map_y + k) >= 0) {
+        for (int i = 0; i < N; ++i) acc[i] = 0.0;
 #pragma unroll
-            for (int i = 0; i < N; ++i) acc[i] -= contrib[i];
+        for (int i = 0; i < NN; ++i) d[i] = 0.0;
+        // 1. build the row
+        for (int k = rb; k < re; ++k) {
+            double blk[NN], contrib[N];
+            build_entry<T, B, mode, SP>(s, t, uir, uii, k, blk, contrib);
+            if (__ldg(s.map_y + k) >= 0) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) acc[i] -= contrib[i];
+            }
+            if (k == dg) {
+#pragma unroll
+                for (int i = 0; i < NN; ++i) d[i] = blk[i];
+            } else {
+                t.store_blk(k, blk);
+            }
         }
-        if (k == dg) {
-#pragma unroll
-            for (int i = 0; i < NN; ++i) d[i] = blk[i];
-        } else {
-            t.store_blk(k, blk);
+        finish_diag<T, B, mode, SP, REG>(s, t, row, uir, uii, acc, d, viol);
+        if constexpr (REG && mode == Mode::newton) {
+            if (pass == 0 && check_now && ctl.has_limits && viol == 0) {
+                viol = check_q_limit<T, B, SP>(s, t, row, ctl, acc);
+                if (viol != 0) {
+                    t.qviol[(size_t)row * T] = (uint8_t)viol;
+                    continue; // the bus is PQ from now on: rebuild its row with the clamped generators
+                }
+            }
+        }
+        break;
+    }
+    if constexpr (REG && mode == Mode::newton) {
+        if (ctl.regulated && viol == 0) { // PV row
+            pv_diag<T, B, SP>(t, row, d, acc);
+            for (int k = rb; k < re; ++k)
+                if (k != dg) zero_pv_rows<T, B, SP>(t, k);
         }
     }
-    finish_diag<T, B, mode, SP>(s, t, row, uir, uii, acc, d);
 
     // 2. eliminate against finished rows (L block in local memory only)
     for (int e = rb; e < dg; ++e) {
@@ -464,7 +605,7 @@ __device__ bool up_row(DevStructure const& s, TileB<T, B, SP> const& t, int row)
     return singular;
 }
 
-template <int T, int B, Mode mode, bool SP = false>
+template <int T, int B, Mode mode, bool SP = false, bool REG = false>
 __device__ double down_row(DevStructure const& s, TileB<T, B, SP> const& t, int row) {
     constexpr int N = 2 * B, NN = N * N;
     int const re = __ldg(s.row_ptr + row + 1), dg = __ldg(s.diag + row);
@@ -506,6 +647,8 @@ __device__ double down_row(DevStructure const& s, TileB<T, B, SP> const& t, int 
 #pragma unroll
     for (int i = 0; i < N; ++i) t.xvec[(size_t)(row * N + i) * T] = x[i];
     double dev = 0.0;
+    [[maybe_unused]] BusControl ctl{};
+    if constexpr (REG && mode == Mode::linear_init) ctl = bus_control<T, B, SP>(s, t, row);
 #pragma unroll
     for (int p = 0; p < B; ++p) {
         double* const pth = t.pol + (size_t)(row * N + p) * T;
@@ -527,7 +670,19 @@ __device__ double down_row(DevStructure const& s, TileB<T, B, SP> const& t, int 
             double const dp = sqrt(dr * dr + di * di);
             dev = p == 0 ? dp : fmax(dev, dp);
         } else {
-            double const xr = x[p], xi = x[B + p]; // linear start: real part in the P rows, imaginary part in the Q rows
+            double xr = x[p], xi = x[B + p]; // linear start: real part in the P rows, imaginary part in the Q rows
+            if constexpr (REG) { // a PV bus starts at its reference magnitude: u = u_ref * u / |u|
+                if (ctl.regulated) {
+                    double const ax = sqrt(xr * xr + xi * xi);
+                    double sr = 1.0, si = 0.0;
+                    if (ax > 0.0) {
+                        sr = xr / ax;
+                        si = xi / ax;
+                    }
+                    xr = ctl.u_ref * sr - 0.0 * si;
+                    xi = ctl.u_ref * si + 0.0 * sr;
+                }
+            }
             *pur = xr;
             *pui = xi;
             *pv = sqrt(xr * xr + xi * xi);
@@ -545,9 +700,9 @@ __device__ double down_row(DevStructure const& s, TileB<T, B, SP> const& t, int 
 //      L = (A Q_c) U_c^-1, update terms L * U(c, j) and L * x_c to scratch
 //   4  diagonal / upper entries in parallel subtract their terms in ascending child order; slot 0 subtracts the L * x_c terms
 //   5  slot 0 factorises the diagonal block and forward-substitutes; 6  U blocks in parallel
-template <int T, int B, Mode mode, bool SP>
+template <int T, int B, Mode mode, bool SP, bool REG = false>
 __device__ void wide_up_row(DevStructure const& s, TileB<T, B, SP> const& t, int w, int slot, int n_slot, bool active,
-                            bool& singular) {
+                            bool& singular, bool check_now = false) {
     constexpr int N = 2 * B, NN = N * N;
     int32_t const* const tab = s.wide_table + 8 * w;
     int const row = __ldg(tab), n_sub = __ldg(tab + 1);
@@ -583,20 +738,48 @@ __device__ void wide_up_row(DevStructure const& s, TileB<T, B, SP> const& t, int
         double uir[B], uii[B];
         t.load_u(row, uir, uii);
         double acc[N], d[NN];
-#pragma unroll
-        for (int i = 0; i < N; ++i) acc[i] = 0.0;
-        for (int idx = 0; idx < n_entries; ++idx) {
-            if (__ldg(s.map_y + rb + idx) < 0) continue;
-#pragma unroll
-            for (int i = 0; i < N; ++i) acc[i] -= t.wide_sum[(size_t)(idx * N + i) * T];
+        [[maybe_unused]] BusControl ctl{};
+        [[maybe_unused]] int viol = 0;
+        if constexpr (REG && mode == Mode::newton) {
+            ctl = bus_control<T, B, SP>(s, t, row);
+            viol = t.qviol[(size_t)row * T];
         }
-        t.load_blk(dg, d);
-        finish_diag<T, B, mode, SP>(s, t, row, uir, uii, acc, d);
+        constexpr int n_pass = (REG && mode == Mode::newton) ? 2 : 1;
+#pragma unroll 1
+        for (int pass = 0; pass < n_pass; ++pass) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) acc[i] = 0.0;
+            for (int idx = 0; idx < n_entries; ++idx) {
+                if (__ldg(s.map_y + rb + idx) < 0) continue;
+#pragma unroll
+                for (int i = 0; i < N; ++i) acc[i] -= t.wide_sum[(size_t)(idx * N + i) * T];
+            }
+            t.load_blk(dg, d);
+            finish_diag<T, B, mode, SP, REG>(s, t, row, uir, uii, acc, d, viol);
+            if constexpr (REG && mode == Mode::newton) {
+                if (pass == 0 && check_now && ctl.has_limits && viol == 0) {
+                    viol = check_q_limit<T, B, SP>(s, t, row, ctl, acc);
+                    if (viol != 0) {
+                        t.qviol[(size_t)row * T] = (uint8_t)viol;
+                        continue;
+                    }
+                }
+            }
+            break;
+        }
+        if constexpr (REG && mode == Mode::newton) {
+            if (ctl.regulated && viol == 0) { // PV row: the built blocks of the row lose their Q rows before phase 3 reads them
+                pv_diag<T, B, SP>(t, row, d, acc);
+                for (int k = rb; k < re; ++k)
+                    if (k != dg) zero_pv_rows<T, B, SP>(t, k);
+            }
+        }
         t.store_blk(dg, d);
 #pragma unroll
         for (int i = 0; i < N; ++i) t.xvec[(size_t)(row * N + i) * T] = acc[i];
     }
-    // 3 (the diagonal block is not touched here, so phase 2 needs no barrier of its own)
+    if constexpr (REG && mode == Mode::newton) __syncthreads(); // phase 2 may have rewritten blocks that phase 3 loads
+    // 3 (without regulators the diagonal block is the only thing phase 2 writes, so it needs no barrier of its own)
     for (int sl = 0; sl < n_sub; ++sl) {
         if (active) {
             for (int oi = __ldg(sub_ptr + sl) + slot; oi < __ldg(sub_ptr + sl + 1); oi += n_slot) {

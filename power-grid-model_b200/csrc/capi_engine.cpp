@@ -26,16 +26,24 @@ MathTopology topology_from_view(pgmb_math_topology const& t) {
     m.shunts_per_bus.assign(t.shunts_per_bus, t.shunts_per_bus + t.n_bus + 1);
     m.load_gens_per_bus.assign(t.load_gens_per_bus, t.load_gens_per_bus + t.n_bus + 1);
     if (m.n_load_gen() > 0) m.load_gen_type.assign(t.load_gen_type, t.load_gen_type + m.n_load_gen());
+    if (t.voltage_regulators_per_load_gen != nullptr) {
+        m.load_gen_regulator.assign(m.n_load_gen(), -1);
+        for (Idx lg = 0; lg != m.n_load_gen(); ++lg) {
+            int64_t const b = t.voltage_regulators_per_load_gen[lg], e = t.voltage_regulators_per_load_gen[lg + 1];
+            if (e - b > 1) throw InvalidArgument("There are objects regulated by more than one regulator. Maximum one regulator is allowed.");
+            if (e - b == 1) m.load_gen_regulator[lg] = b;
+        }
+    }
     return m;
 }
 } // namespace pgmb
 
 namespace {
 PfInputView view_of(pgmb_pf_input const& in) {
-    return {in.n_scenarios, in.source_u_ref, in.source_is_shared != 0, in.s_injection};
+    return {in.n_scenarios, in.source_u_ref, in.source_is_shared != 0, in.s_injection, in.voltage_regulator, in.load_gen_status};
 }
 SolverOutputView view_of(pgmb_solver_output const& o) {
-    return {o.u, o.bus_injection, o.branch, o.source, o.shunt, o.load_gen, o.status, o.n_iter, o.max_dev};
+    return {o.u, o.bus_injection, o.branch, o.source, o.shunt, o.load_gen, o.status, o.n_iter, o.max_dev, o.voltage_regulator};
 }
 SolveOptions options_of(pgmb_run_options const& o) {
     if (o.max_iter < 0 || o.max_iter > (int64_t{1} << 30)) throw InvalidArgument("max_iter out of range");

@@ -100,6 +100,23 @@ struct AsymLoadGenUpdate {
     IntS status;
     double p_specified[3], q_specified[3];
 };
+// voltage regulator (auxiliary/input.hpp:492-498, update.hpp:213-219, output.hpp:239-243)
+struct VoltageRegulatorInput {
+    ID id, regulated_object;
+    IntS status;
+    double u_ref, q_min, q_max;
+};
+struct VoltageRegulatorUpdate {
+    ID id;
+    IntS status;
+    double u_ref, q_min, q_max;
+};
+struct VoltageRegulatorOutput {
+    ID id;
+    IntS energized;
+    IntS limit_violated;
+};
+static_assert(sizeof(VoltageRegulatorInput) == 40 && sizeof(VoltageRegulatorUpdate) == 32 && sizeof(VoltageRegulatorOutput) == 8);
 template <int B> struct NodeOutput {
     ID id;
     IntS energized;
@@ -141,6 +158,10 @@ struct ShuntState {
 struct LoadGenState {
     bool status;
     cplx s[3]; // per-unit specified power in injection direction; [0] only for symmetric loads
+};
+struct RegulatorState { // component/voltage_regulator.hpp:22-101
+    bool status;
+    double u_ref, q_min, q_max; // q in VAr (3-phase), divided by the base power in calc_param
 };
 
 // write a B x B complex tensor (row-major, interleaved) --------------------------------------------------------------

@@ -151,6 +151,21 @@ void Engine::upload_structure() {
     d_lg_bus_.upload(group_of(topo_.load_gens_per_bus), stream_);
     d_src_bus_.upload(group_of(topo_.sources_per_bus), stream_);
     d_phase_shift_.upload(topo_.phase_shift, stream_);
+    std::vector<int32_t> reg_bus;
+    if (has_regulators()) {
+        if (static_cast<Idx>(topo_.load_gen_regulator.size()) != topo_.n_load_gen()) {
+            throw InvalidArgument("load_gen_regulator must have one entry per load_gen");
+        }
+        d_lg_reg_.upload(narrow_vec<int32_t>(topo_.load_gen_regulator), stream_);
+        for (Idx b = 0; b != n_bus; ++b) {
+            int n_reg = 0;
+            for (Idx k = topo_.load_gens_per_bus[b]; k != topo_.load_gens_per_bus[b + 1]; ++k) n_reg += topo_.load_gen_regulator[k] >= 0 ? 1 : 0;
+            if (n_reg > 16) throw InvalidArgument("more than 16 regulated generators on one bus are not supported");
+            if (n_reg != 0) reg_bus.push_back(static_cast<int32_t>(b));
+        }
+        d_reg_bus_.upload(reg_bus, stream_);
+        n_reg_bus_ = static_cast<int>(reg_bus.size());
+    }
     PGMB_CUDA(cudaStreamSynchronize(stream_)); // temporaries above must outlive the copies
 
     ds_.n_bus = static_cast<int32_t>(n_bus);
@@ -193,6 +208,31 @@ void Engine::upload_structure() {
     ds_.path_prog = path_program_.valid ? d_path_prog_.get() : nullptr;
     ds_.path_prog_words = path_program_.valid ? static_cast<int32_t>(path_program_.words.size()) : 0;
     ds_.path_prog_smem_words = path_program_.valid ? path_program_.smem_words : 0;
+    ds_.n_regulator = static_cast<int32_t>(topo_.n_voltage_regulator());
+    ds_.lg_reg = has_regulators() ? d_lg_reg_.get() : nullptr;
+    ds_.reg_param = nullptr;
+}
+
+// VoltageRegulatorCalcParam of every regulator (calculation_parameters.hpp:228-236).  A regulating regulator needs a
+// const_pq generator (newton_raphson_pf_solver.hpp:621-625; the reference throws when it reaches the limit check).
+void Engine::set_regulators(double const* param) {
+    if (!has_regulators()) throw InvalidArgument("the math topology has no voltage regulators");
+    if (param == nullptr) throw InvalidArgument("voltage regulator parameters are required for a grid with regulators");
+    Idx const n_reg = topo_.n_voltage_regulator();
+    reg_param_.assign(param, param + 4 * n_reg);
+    for (Idx lg = 0; lg != topo_.n_load_gen(); ++lg) {
+        Idx const r = topo_.load_gen_regulator[lg];
+        if (r >= 0 && reg_param_[4 * r] != 0.0 && topo_.load_gen_type[lg] != 0) {
+            throw InvalidArgument("Voltage regulator(s) " + std::to_string(r) + " regulate(s) a load/generator with unsupported type");
+        }
+    }
+    reg_param_set_ = true;
+    if (device_ < 0) return;
+    PGMB_CUDA(cudaSetDevice(device_));
+    d_reg_param_.ensure(reg_param_.size() + 1);
+    PGMB_CUDA(cudaMemcpyAsync(d_reg_param_.get(), reg_param_.data(), reg_param_.size() * sizeof(double), cudaMemcpyHostToDevice, stream_));
+    PGMB_CUDA(cudaStreamSynchronize(stream_));
+    ds_.reg_param = d_reg_param_.get();
 }
 
 // YBus::update_admittance_entries (y_bus.hpp:400-431): sum of the contributions of each entry, in element order
@@ -290,6 +330,7 @@ void Engine::allocate_batch(int64_t n) {
     d_sinj_.ensure(static_cast<size_t>(n_tile) * topo_.n_load_gen() * 2 * B_ * T + 1);
     d_lg_status_.ensure(static_cast<size_t>(n_tile) * topo_.n_load_gen() * T + 1);
     d_usrc_.ensure(static_cast<size_t>(n_tile) * topo_.n_source() * 2 * T + 1);
+    if (has_regulators()) d_qviol_.ensure(n_tile * nb * T + 1);
     d_status_.ensure(n + 1);
     d_n_iter_.ensure(n + 1);
     d_max_dev_.ensure(n + 1);
@@ -310,6 +351,7 @@ void Engine::allocate_batch(int64_t n) {
     db_.n_iter = d_n_iter_.get();
     db_.max_dev = d_max_dev_.get();
     db_.lg_status = d_lg_status_.get();
+    db_.qviol = has_regulators() ? d_qviol_.get() : nullptr;
     db_.phase_cycles = nullptr;
     if (env_int("PGMB_DEBUG_PHASES", 0) != 0) {
         d_phase_.ensure(static_cast<size_t>(n_tile) * 16);
@@ -331,6 +373,15 @@ void Engine::stage(PfInputView const& in) {
     launch_to_tile(T, d_in_sinj_.get(), d_sinj_.get(), n, static_cast<int>(topo_.n_load_gen()), 2 * B_, 0, stream_);
     launch_to_tile(T, d_in_usrc_.get(), d_usrc_.get(), n, static_cast<int>(topo_.n_source()), 2, in.source_is_shared ? 1 : 0, stream_);
     PGMB_CUDA(cudaMemsetAsync(d_lg_status_.get(), 1, d_lg_status_.size(), stream_));
+    if (has_regulators()) {
+        set_regulators(in.voltage_regulator);
+        if (in.load_gen_status != nullptr && n * topo_.n_load_gen() != 0) {
+            size_t const bytes = static_cast<size_t>(n) * topo_.n_load_gen();
+            d_in_lg_status_.ensure(bytes);
+            PGMB_CUDA(cudaMemcpyAsync(d_in_lg_status_.get(), in.load_gen_status, bytes, cudaMemcpyHostToDevice, stream_));
+            launch_status_to_tile(T, d_in_lg_status_.get(), d_lg_status_.get(), n, static_cast<int>(topo_.n_load_gen()), stream_);
+        }
+    }
     PGMB_CUDA(cudaStreamSynchronize(stream_));
 }
 
@@ -373,6 +424,7 @@ DevBatch Engine::batch_view(int64_t tile_begin, int64_t tile_end) const {
     v.perm += tile_begin * nb * T * 2 * N;
     v.sinj += static_cast<size_t>(tile_begin) * topo_.n_load_gen() * 2 * B_ * T;
     v.lg_status += static_cast<size_t>(tile_begin) * topo_.n_load_gen() * T;
+    if (v.qviol != nullptr) v.qviol += tile_begin * nb * T;
     v.usrc += static_cast<size_t>(tile_begin) * topo_.n_source() * 2 * T;
     v.status += scn_begin;
     v.n_iter += scn_begin;
@@ -391,6 +443,10 @@ SolveOptions Engine::prepare_solve(SolveOptions const& opt_in) {
     if (opt.method == -128) opt.method = 1;
     if (opt.method != 0 && opt.method != 1 && opt.method != 3 && opt.method != 4) {
         throw InvalidArgument("calculation method " + std::to_string(opt.method) + " is not a power-flow method");
+    }
+    if (has_regulators()) { // calculation_preparation.hpp:163-225: regulators exist only in the Newton-Raphson formulation
+        if (opt_in.method != 1 && opt_in.method != -128) throw InvalidArgument("The calculation method is invalid for this calculation!");
+        if (!reg_param_set_) throw InvalidArgument("voltage regulator parameters have not been set");
     }
     last_method_ = opt.method;
     if ((opt.method == 3 || opt.method == 4) && !ic_factor_valid_) {
@@ -414,9 +470,13 @@ SolveOptions Engine::prepare_solve(SolveOptions const& opt_in) {
 
 void Engine::launch_solve(DevBatch const& b, SolveOptions const& opt, cudaStream_t st) {
     if (b.n_scn == 0) return;
+    if (b.qviol != nullptr) {
+        PGMB_CUDA(cudaMemsetAsync(b.qviol, 0, static_cast<size_t>(b.n_tile) * topo_.n_bus * tile_width_, st));
+    }
     switch (opt.method) {
     case 1:
-        if (!symmetric_ || env_int("PGMB_KERNEL", 3) == 0) {
+        // grids with voltage regulators (PV buses): the generic block kernel carries that logic for B = 1 and B = 3
+        if (!symmetric_ || has_regulators() || env_int("PGMB_KERNEL", 3) == 0) {
             launch_nr_block(B_, tile_width_, ds_, b, opt, n_slot_, st);
         } else if (env_int("PGMB_KERNEL", 3) == 1) {
             launch_nr_sym(tile_width_, ds_, b, opt, n_slot_, st);
@@ -486,16 +546,23 @@ void Engine::fetch(SolverOutputView const& out) {
         buf.ensure(static_cast<size_t>(n) * per_scn + 1);
         return buf.get();
     };
-    double* const du = want(out.u, d_out_u_, topo_.n_bus * c2);
-    double* const di = want(out.bus_injection, d_out_inj_, topo_.n_bus * c2);
+    bool const reg = has_regulators();
+    double dummy = 0.0; // the regulator step reads u, the bus injection and the load_gen results on the device
+    double* const du = want(reg ? &dummy : out.u, d_out_u_, topo_.n_bus * c2);
+    double* const di = want(reg ? &dummy : out.bus_injection, d_out_inj_, topo_.n_bus * c2);
     double* const dbr = want(out.branch, d_out_branch_, topo_.n_branch() * 4 * c2);
     double* const dsrc = want(out.source, d_out_source_, topo_.n_source() * 2 * c2);
     double* const dsh = want(out.shunt, d_out_shunt_, topo_.n_shunt() * 2 * c2);
-    double* const dlg = want(out.load_gen, d_out_lg_, topo_.n_load_gen() * 2 * c2);
+    double* const dlg = want(reg ? &dummy : out.load_gen, d_out_lg_, topo_.n_load_gen() * 2 * c2);
+    if (reg) d_out_reg_.ensure(static_cast<size_t>(n) * ds_.n_regulator * 2 + 1);
     if (symmetric_) {
         launch_math_result_sym(tile_width_, ds_, db_, last_method_ == 0 ? 1 : 0, du, di, dbr, dsrc, dsh, dlg, stream_);
     } else {
         launch_math_result_asym(tile_width_, ds_, db_, last_method_ == 0 ? 1 : 0, du, di, dbr, dsrc, dsh, dlg, stream_);
+    }
+    if (reg) {
+        // sources sit on slack buses, which never regulate: the source results above do not depend on this step
+        launch_regulator_result(B_, tile_width_, ds_, db_, d_reg_bus_.get(), n_reg_bus_, du, di, dlg, d_out_reg_.get(), stream_);
     }
     PGMB_CUDA(cudaGetLastError());
     auto back = [&](void* host, void const* dev, size_t bytes) {
@@ -510,6 +577,7 @@ void Engine::fetch(SolverOutputView const& out) {
     back(out.status, d_status_.get(), sizeof(int32_t) * n);
     back(out.n_iter, d_n_iter_.get(), sizeof(int32_t) * n);
     back(out.max_dev, d_max_dev_.get(), sizeof(double) * n);
+    if (reg) back(out.voltage_regulator, d_out_reg_.get(), static_cast<size_t>(n) * ds_.n_regulator * 2);
     PGMB_CUDA(cudaStreamSynchronize(stream_));
 }
 

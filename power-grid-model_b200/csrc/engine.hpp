@@ -93,11 +93,14 @@ struct PfInputView {
     double const* source_u_ref;
     bool source_is_shared;
     double const* s_injection;
+    double const* voltage_regulator{nullptr}; // [n_regulator][4] status, u_ref, q_min, q_max (shared by the scenarios)
+    int8_t const* load_gen_status{nullptr};   // [n_scenarios][n_load_gen], null = all on
 };
 struct SolverOutputView {
     double *u, *bus_injection, *branch, *source, *shunt, *load_gen;
     int32_t *status, *n_iter;
     double* max_dev;
+    int8_t* voltage_regulator{nullptr}; // [n_scenarios][n_regulator][2] limit_violated, generator_status
 };
 
 class Engine {
@@ -110,6 +113,9 @@ class Engine {
     // branch_param [n_branch][4][B][B], shunt_param [n_shunt][B][B], source_param [n_source][2] (all complex)
     void set_param(double const* branch_param, double const* shunt_param, double const* source_param);
 
+    // voltage regulator parameters of the next solves: [n_regulator][4] status, u_ref, q_min, q_max
+    void set_regulators(double const* param);
+    bool has_regulators() const { return !topo_.load_gen_regulator.empty(); }
     void stage(PfInputView const& in);                      // H2D + layout conversion
     // device path of the model level: allocate the batch, upload per-scenario source references; load injections are then
     // produced on the device by the apply_load_update kernels (model_device.cpp)
@@ -170,7 +176,13 @@ class Engine {
     DevBuf<uint8_t> d_row_is_wide_;
     DevBuf<double> d_jac_, d_xvec_, d_pol_, d_u_, d_sinj_, d_usrc_, d_max_dev_, d_in_sinj_, d_in_usrc_;
     DevBuf<double> d_out_u_, d_out_inj_, d_out_branch_, d_out_source_, d_out_shunt_, d_out_lg_;
-    DevBuf<uint8_t> d_perm_, d_lg_status_;
+    DevBuf<uint8_t> d_perm_, d_lg_status_, d_qviol_, d_in_lg_status_;
+    DevBuf<int32_t> d_lg_reg_, d_reg_bus_;
+    DevBuf<double> d_reg_param_;
+    DevBuf<int8_t> d_out_reg_;
+    std::vector<double> reg_param_;
+    int n_reg_bus_{0};
+    bool reg_param_set_{false};
     DevBuf<int32_t> d_status_, d_n_iter_;
     DevBuf<unsigned long long> d_phase_;
     DevBuf<double> d_ic_factor_; // shared iterative-current factor [nnz_lu][2]
@@ -212,6 +224,10 @@ void launch_pack_branch_asym(int tw, DevStructure const& s, DevBatch const& b, D
                              void* out, cudaStream_t st);
 void launch_pack_appliance_asym(int tw, DevStructure const& s, DevBatch const& b, DevModelTables const& m, int force_const_y,
                                 int first, int count, double const* src_res, void* out, cudaStream_t st);
+void launch_regulator_result(int phases, int tile_width, DevStructure const& s, DevBatch const& b, int32_t const* reg_bus,
+                             int n_reg_bus, double const* out_u, double const* out_inj, double* out_lg, int8_t* out_reg,
+                             cudaStream_t st);
+void launch_status_to_tile(int tile_width, uint8_t const* src, uint8_t* dst, int64_t n_scn, int n_item, cudaStream_t st);
 void launch_nr_block(int phases, int tile_width, DevStructure const& s, DevBatch const& b, SolveOptions const& opt, int n_slot,
                      cudaStream_t st);
 void launch_math_result_asym(int tile_width, DevStructure const& s, DevBatch const& b, int force_const_y, double* out_u,

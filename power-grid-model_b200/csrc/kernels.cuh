@@ -55,6 +55,10 @@ struct DevStructure {
     int32_t const* path_prog;
     int32_t path_prog_words;
     int32_t path_prog_smem_words; // prefix of the path program that the kernel stages in shared memory
+    // voltage regulators (PV buses, newton_raphson_pf_solver.hpp:374-453); lg_reg == nullptr when the grid has none
+    int32_t n_regulator;
+    int32_t const* lg_reg;    // [n_load_gen] regulator of the load_gen or -1 (at most one regulator per load_gen)
+    double const* reg_param;  // [n_regulator][4] status, u_ref, q_min, q_max (per unit; NaN = no limit)
 };
 
 // per-batch device buffers, tile layout (see above); B = phases, N = 2B
@@ -76,6 +80,7 @@ struct DevBatch {
     double* wide_rhs;   // [tile][wide_max_lower][N][T]
     double* wide_sum;   // [tile][wide_max_entries][N][T]
     uint8_t* lg_status; // [tile][n_load_gen][T] per-scenario status of each load_gen (device update path), may be null
+    uint8_t* qviol;     // [tile][n_bus][T] reactive-power limit a PV bus ran into: 0 none, 1 lower, 2 upper; null = no regulators
     unsigned long long* phase_cycles; // optional [n_tile][8] clock64 totals per phase (PGMB_DEBUG_PHASES), may be null
 };
 

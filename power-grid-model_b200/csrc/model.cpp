@@ -100,6 +100,61 @@ Model::Model(double system_frequency, InputData const& in) : freq_{system_freque
     add_lg(static_cast<AsymLoadGenInput const*>(in.asym_gen.data), in.asym_gen.n, 3, 1.0);
     add_lg(static_cast<SymLoadGenInput const*>(in.sym_load.data), in.sym_load.n, 1, -1.0);
     add_lg(static_cast<AsymLoadGenInput const*>(in.asym_load.data), in.asym_load.n, 3, -1.0);
+    // voltage regulators (main_core/input.hpp:216-241): the regulated object is a load / generator, one regulator per object
+    auto const* regs = static_cast<VoltageRegulatorInput const*>(in.voltage_regulator.data);
+    std::unordered_map<ID, int> regulated;
+    for (Idx i = 0; i != in.voltage_regulator.n; ++i) {
+        VoltageRegulatorInput const& r = regs[i];
+        add_id(r.id);
+        auto it = lg_idx_.find(r.regulated_object);
+        if (it == lg_idx_.end()) {
+            throw InvalidArgument("Wrong type for object with id " + std::to_string(r.regulated_object) + "\n");
+        }
+        if (!regulated.emplace(r.regulated_object, 0).second) {
+            throw InvalidArgument("There are objects regulated by more than one regulator. Maximum one regulator is allowed.\n");
+        }
+        reg_idx_[r.id] = i;
+        reg_in_.push_back(r);
+        reg_lg_.push_back(it->second);
+        reg_st_.push_back({r.status != 0, r.u_ref, r.q_min, r.q_max});
+    }
+}
+
+// check_state_validity (main_core/calculation_preparation.hpp:163-225) + the method restriction of the regulator
+// (main_model_impl.hpp:362-366, 400-420)
+template <int B> void Model::check_regulators(ModelOptions const& opt) const {
+    if (reg_in_.empty()) return;
+    if (opt.method != 1 && opt.method != -128) throw InvalidArgument("The calculation method is invalid for this calculation!\n");
+    std::unordered_map<Idx, std::pair<ID, double>> node_ref; // node -> (regulator id, u_ref)
+    for (size_t r = 0; r != reg_in_.size(); ++r) {
+        if (!reg_st_[r].status) continue;
+        Idx const node = lg_[reg_lg_[r]].node;
+        auto it = node_ref.find(node);
+        if (it != node_ref.end()) {
+            if (it->second.second != reg_st_[r].u_ref) {
+                throw InvalidArgument("Voltage regulators with different u_ref on the same node: " + std::to_string(it->second.first) + ", " +
+                                      std::to_string(reg_in_[r].id) + "\n");
+            }
+        } else {
+            node_ref[node] = {reg_in_[r].id, reg_st_[r].u_ref};
+        }
+    }
+    for (size_t r = 0; r != reg_in_.size(); ++r) {
+        if (reg_st_[r].status && lg_[reg_lg_[r]].type != 0) {
+            throw InvalidArgument("Voltage regulator " + std::to_string(reg_in_[r].id) + " regulates a load/generator of unsupported type\n");
+        }
+    }
+    for (size_t i = 0; i != source_in_.size(); ++i) {
+        if (source_st_[i].status && node_ref.count(node_idx_.at(source_in_[i].node)) != 0) {
+            throw InvalidArgument("Unsupported combination of source and voltage regulator at node " + std::to_string(source_in_[i].node) + "\n");
+        }
+    }
+    if constexpr (B == 3) {
+        for (auto const& st : reg_st_)
+            if (!std::isnan(st.q_min) || !std::isnan(st.q_max)) {
+                throw InvalidArgument("Voltage Regulator with Qmin/Qmax limits for asymmetric calculations is an experimental feature\n");
+            }
+    }
 }
 
 Idx Model::node_seq(ID id) const {
@@ -143,6 +198,7 @@ void Model::prepare_topology() {
         g.load_gen_node.push_back(l.node);
         g.load_gen_type.push_back(l.type);
     }
+    g.regulated_load_gen = reg_lg_;
     topo_ = build_topology(g);
     dev_.reset();
     engines_.clear();
@@ -196,7 +252,31 @@ template <int B> void Model::prepare_engines() {
 
 // PowerFlowInput of the current state: sinj[g] = [n_lg][B] complex, uref[g] = [n_src] complex (appended)
 template <int B>
-void Model::gather_pf_input(std::vector<std::vector<double>>& sinj, std::vector<std::vector<double>>& uref) const {
+void Model::gather_pf_input(std::vector<std::vector<double>>& sinj, std::vector<std::vector<double>>& uref,
+                            RegulatorInput* reg) const {
+    if (reg != nullptr) { // load_gen status per scenario: also what the output step reports as `energized`
+        reg->param.resize(topo_.math.size());
+        reg->lg_status.resize(topo_.math.size());
+        std::vector<size_t> base(topo_.math.size());
+        for (size_t g = 0; g != topo_.math.size(); ++g) {
+            reg->param[g].assign(topo_.math[g].n_voltage_regulator() * 4, 0.0);
+            base[g] = reg->lg_status[g].size();
+            reg->lg_status[g].resize(base[g] + topo_.math[g].n_load_gen(), 0);
+        }
+        for (size_t r = 0; r != reg_in_.size(); ++r) { // VoltageRegulator::calc_param (voltage_regulator.hpp:83-91)
+            Coupling const c = topo_.voltage_regulator[r];
+            if (c.group == -1) continue;
+            double* o = &reg->param[c.group][c.pos * 4];
+            o[0] = reg_st_[r].status ? 1.0 : 0.0;
+            o[1] = reg_st_[r].u_ref;
+            o[2] = reg_st_[r].q_min / kBasePower3p;
+            o[3] = reg_st_[r].q_max / kBasePower3p;
+        }
+        for (size_t i = 0; i != lg_.size(); ++i) {
+            Coupling const c = topo_.load_gen[i];
+            if (c.group != -1) reg->lg_status[c.group][base[c.group] + c.pos] = lg_st_[i].status ? 1 : 0;
+        }
+    }
     for (size_t g = 0; g != topo_.math.size(); ++g) {
         size_t const off_s = sinj[g].size(), off_u = uref[g].size();
         sinj[g].resize(off_s + topo_.math[g].n_load_gen() * B * 2, 0.0);
@@ -327,6 +407,18 @@ void Model::apply_scenario(UpdateData const& u, Idx s, Saved* saved) {
     upd_lg(AsymLoadGenUpdate{}, u.asym_gen, n_sym_gen_, n_asym_gen_);
     upd_lg(SymLoadGenUpdate{}, u.sym_load, n_sym_gen_ + n_asym_gen_, n_sym_load_);
     upd_lg(AsymLoadGenUpdate{}, u.asym_load, n_sym_gen_ + n_asym_gen_ + n_sym_load_, n_asym_load_);
+    {
+        // VoltageRegulator::update (voltage_regulator.hpp:35-41): neither topology nor parameters change
+        auto [b, e] = scenario_span<VoltageRegulatorUpdate>(u.voltage_regulator, s);
+        for (auto p = b; p != e; ++p) {
+            Idx const i = find(*p, p - b, e - b, static_cast<Idx>(reg_in_.size()), reg_idx_, 0);
+            if (saved != nullptr) saved->reg.emplace_back(i, reg_st_[i]);
+            set_status(reg_st_[i].status, p->status);
+            if (!std::isnan(p->u_ref)) reg_st_[i].u_ref = p->u_ref;
+            if (!std::isnan(p->q_min)) reg_st_[i].q_min = p->q_min;
+            if (!std::isnan(p->q_max)) reg_st_[i].q_max = p->q_max;
+        }
+    }
 }
 
 void Model::restore(Saved const& s) {
@@ -335,6 +427,7 @@ void Model::restore(Saved const& s) {
     for (auto it = s.source.rbegin(); it != s.source.rend(); ++it) source_st_[it->first] = it->second;
     for (auto it = s.shunt.rbegin(); it != s.shunt.rend(); ++it) shunt_st_[it->first] = it->second;
     for (auto it = s.lg.rbegin(); it != s.lg.rend(); ++it) lg_st_[it->first] = it->second;
+    for (auto it = s.reg.rbegin(); it != s.reg.rend(); ++it) reg_st_[it->first] = it->second;
     if (s.topo) topo_valid_ = false;
     if (s.param) param_valid_[0] = param_valid_[1] = false;
 }
@@ -366,7 +459,9 @@ void Model::batch_pf_input(UpdateData const& update, bool symmetric, Idx group, 
 // ---- output conversion (host, v1) ------------------------------------------------------------------------------------
 // so[0..5] = u, bus_injection(unused), branch, source, shunt, load_gen per group, scenario-major
 template <int B>
-void Model::write_output(Idx n_scn, Idx first, OutputData const& out, std::vector<std::vector<double>> const (&so)[6]) const {
+void Model::write_output(Idx n_scn, Idx first, OutputData const& out, std::vector<std::vector<double>> const (&so)[6],
+                         std::vector<std::vector<int8_t>> const& reg_out,
+                         std::vector<std::vector<int8_t>> const* lg_status) const {
     constexpr int c2 = 2 * B;
     constexpr double base_power = B == 1 ? kBasePower3p : kBasePower1p;
     constexpr double u_scale = B == 1 ? 1.0 : 1.0 / kSqrt3;
@@ -491,24 +586,42 @@ void Model::write_output(Idx n_scn, Idx first, OutputData const& out, std::vecto
             auto* dst = static_cast<ApplianceOutput<B>*>(base) + os * count;
             for (Idx k = 0; k != count; ++k) {
                 Idx const i = begin + k;
-                dst[k] = appliance(topo_.load_gen[i], 5, lg_[i].base_i, lg_[i].direction, lg_[i].id, lg_st_[i].status);
+                Coupling const c = topo_.load_gen[i];
+                bool status = lg_st_[i].status;
+                if (lg_status != nullptr && c.group != -1) status = (*lg_status)[c.group][s * topo_.math[c.group].n_load_gen() + c.pos] != 0;
+                dst[k] = appliance(c, 5, lg_[i].base_i, lg_[i].direction, lg_[i].id, status);
             }
         };
         lg_out(out.sym_gen, 0, n_sym_gen_);
         lg_out(out.asym_gen, n_sym_gen_, n_asym_gen_);
         lg_out(out.sym_load, n_sym_gen_ + n_asym_gen_, n_sym_load_);
         lg_out(out.asym_load, n_sym_gen_ + n_asym_gen_ + n_sym_load_, n_asym_load_);
+        if (out.voltage_regulator != nullptr) { // main_core/output.hpp:407-421, VoltageRegulator::get_output
+            Idx const n = static_cast<Idx>(reg_in_.size());
+            auto* dst = static_cast<VoltageRegulatorOutput*>(out.voltage_regulator) + os * n;
+            for (Idx i = 0; i != n; ++i) {
+                Coupling const c = topo_.voltage_regulator[i];
+                VoltageRegulatorOutput o{reg_in_[i].id, 0, 0};
+                if (c.group != -1) {
+                    int8_t const* v = &reg_out[c.group][(s * topo_.math[c.group].n_voltage_regulator() + c.pos) * 2];
+                    o.energized = (reg_st_[i].status && v[1] != 0) ? 1 : 0;
+                    o.limit_violated = v[0];
+                }
+                dst[i] = o;
+            }
+        }
     }
 }
 
 template <int B>
 int64_t Model::run_block(ModelOptions const& opt, Idx n_scn, std::vector<std::vector<double>> const& sinj,
                          std::vector<std::vector<double>> const& uref, OutputData const& out, Idx first, int32_t* n_iter,
-                         int32_t* status) {
+                         int32_t* status, RegulatorInput const* reg) {
     constexpr int si = B == 1 ? 0 : 1;
     constexpr int c2 = 2 * B;
     std::vector<std::vector<double>> so[6];
     for (auto& v : so) v.resize(topo_.math.size());
+    std::vector<std::vector<int8_t>> reg_out(topo_.math.size());
     std::vector<int32_t> st_all(n_scn, 0), it_all(n_scn, 0);
     for (size_t g = 0; g != topo_.math.size(); ++g) {
         auto const& m = topo_.math[g];
@@ -521,8 +634,16 @@ int64_t Model::run_block(ModelOptions const& opt, Idx n_scn, std::vector<std::ve
         std::vector<int32_t> st(n_scn), it(n_scn);
         SolverOutputView view{so[0][g].data(), nullptr, so[2][g].data(), so[3][g].data(), so[4][g].data(), so[5][g].data(),
                               st.data(), it.data(), nullptr};
+        PfInputView in_view{n_scn, uref[g].data(), false, sinj[g].data()};
+        if (e.has_regulators()) {
+            if (reg == nullptr) throw InvalidArgument("internal: regulator input missing");
+            reg_out[g].resize(n_scn * m.n_voltage_regulator() * 2);
+            view.voltage_regulator = reg_out[g].data();
+            in_view.voltage_regulator = reg->param[g].data();
+            in_view.load_gen_status = reg->lg_status[g].data();
+        }
         auto t0 = Clock::now();
-        e.stage({n_scn, uref[g].data(), false, sinj[g].data()});
+        e.stage(in_view);
         timing[1] += ms_since(t0);
         timing[2] += e.solve_staged({opt.method, opt.err_tol, static_cast<int32_t>(opt.max_iter)});
         t0 = Clock::now();
@@ -534,7 +655,7 @@ int64_t Model::run_block(ModelOptions const& opt, Idx n_scn, std::vector<std::ve
         }
     }
     auto t0 = Clock::now();
-    write_output<B>(n_scn, first, out, so);
+    write_output<B>(n_scn, first, out, so, reg_out, reg != nullptr ? &reg->lg_status : nullptr);
     timing[3] += ms_since(t0);
     int64_t failed = 0;
     for (Idx s = 0; s != n_scn; ++s) {
@@ -543,8 +664,9 @@ int64_t Model::run_block(ModelOptions const& opt, Idx n_scn, std::vector<std::ve
         if (st_all[s] != 0) {
             ++failed;
             batch_message += "Error in batch #" + std::to_string(first + s) + ": " +
-                             (st_all[s] == 1 ? "Iteration failed to converge after " + std::to_string(opt.max_iter) + " iterations!"
-                                             : "Sparse matrix error, possibly singular matrix!") + "\n";
+                             (st_all[s] == 1   ? "Iteration failed to converge after " + std::to_string(opt.max_iter) + " iterations!"
+                              : st_all[s] == 4 ? std::string("Unallocated Q remains after distribution on a regulated bus")
+                                               : std::string("Sparse matrix error, possibly singular matrix!")) + "\n";
         }
     }
     return failed;
@@ -559,17 +681,21 @@ int64_t Model::calculate_impl(ModelOptions const& opt, UpdateData const* update,
     device_ = opt.device;
     int64_t failed = 0;
     auto t0 = Clock::now();
+    bool const has_reg = !reg_in_.empty();
     if (update == nullptr) {
+        check_regulators<B>(opt);
         prepare_engines<B>();
         std::vector<std::vector<double>> sinj(topo_.math.size()), uref(topo_.math.size());
-        gather_pf_input<B>(sinj, uref);
+        RegulatorInput reg;
+        gather_pf_input<B>(sinj, uref, &reg);
         timing[0] += ms_since(t0);
-        failed = run_block<B>(opt, 1, sinj, uref, out, 0, n_iter, status);
+        failed = run_block<B>(opt, 1, sinj, uref, out, 0, n_iter, status, &reg);
     } else {
         Idx const n = update->n_scenarios;
         // does any scenario touch something other than loads / generators / source references?
+        // (regulator updates change the parameters every scenario of one engine call shares: scenario by scenario as well)
         bool const structural = update->line.data != nullptr || update->transformer.data != nullptr ||
-                                update->shunt.data != nullptr;
+                                update->shunt.data != nullptr || (has_reg && update->voltage_regulator.data != nullptr);
         bool source_param_change = false;
         if (update->source.data != nullptr) {
             for (Idx s = 0; s != n && !source_param_change; ++s) {
@@ -581,7 +707,9 @@ int64_t Model::calculate_impl(ModelOptions const& opt, UpdateData const* update,
         }
         bool device_done = false;
         if (!structural && !source_param_change) prepare_engines<B>(); // the eligibility test looks at the math topology
-        if (!structural && !source_param_change && device_path_eligible(*update)) {
+        if (!structural && !source_param_change && has_reg) check_regulators<B>(opt);
+        // grids with voltage regulators: host-staged engine call (the device update / output kernels do not carry them yet)
+        if (!structural && !source_param_change && !has_reg && device_path_eligible(*update)) {
             timing[0] += ms_since(t0);
             int64_t const r = run_batch_device(opt, B, *update, out, n_iter, status);
             if (r >= 0) {
@@ -596,14 +724,15 @@ int64_t Model::calculate_impl(ModelOptions const& opt, UpdateData const* update,
             // fast path: one engine call for the whole batch
             prepare_engines<B>();
             std::vector<std::vector<double>> sinj(topo_.math.size()), uref(topo_.math.size());
+            RegulatorInput reg;
             for (Idx s = 0; s != n; ++s) {
                 Saved saved;
                 apply_scenario(*update, s, &saved);
-                gather_pf_input<B>(sinj, uref);
+                gather_pf_input<B>(sinj, uref, &reg);
                 restore(saved);
             }
             timing[0] += ms_since(t0);
-            if (n != 0) failed = run_block<B>(opt, n, sinj, uref, out, 0, n_iter, status);
+            if (n != 0) failed = run_block<B>(opt, n, sinj, uref, out, 0, n_iter, status, &reg);
         } else {
             // general path: scenario by scenario (topology / parameters may change), still on the GPU.  Like the reference's
             // job dispatch (job_dispatch.hpp:88-160) the scenarios are spread over host threads, thread t taking scenarios
@@ -620,10 +749,12 @@ int64_t Model::calculate_impl(ModelOptions const& opt, UpdateData const* update,
                         Saved saved;
                         try {
                             model.apply_scenario(*update, s, &saved);
+                            model.template check_regulators<B>(opt);
                             model.template prepare_engines<B>();
                             std::vector<std::vector<double>> sinj(model.topo_.math.size()), uref(model.topo_.math.size());
-                            model.template gather_pf_input<B>(sinj, uref);
-                            failed_per_thread[t] += model.template run_block<B>(opt, 1, sinj, uref, out, s, n_iter, status);
+                            RegulatorInput reg;
+                            model.template gather_pf_input<B>(sinj, uref, &reg);
+                            failed_per_thread[t] += model.template run_block<B>(opt, 1, sinj, uref, out, s, n_iter, status, &reg);
                             messages[s] = std::move(model.batch_message);
                             model.batch_message.clear();
                         } catch (CudaError const&) {
@@ -695,6 +826,7 @@ std::vector<int64_t> const& Model::get_index(Idx group, std::string const& name)
     else if (name == "coup.shunt") v = coupling(topo_.shunt);
     else if (name == "coup.load_gen") v = coupling(topo_.load_gen);
     else if (name == "coup.source") v = coupling(topo_.source);
+    else if (name == "coup.voltage_regulator") v = coupling(topo_.voltage_regulator);
     else {
         if (group < 0 || group >= static_cast<Idx>(topo_.math.size())) throw InvalidArgument("math group out of range");
         auto const& m = topo_.math[group];
@@ -706,6 +838,10 @@ std::vector<int64_t> const& Model::get_index(Idx group, std::string const& name)
         else if (name == "shunts_per_bus") v = m.shunts_per_bus;
         else if (name == "load_gens_per_bus") v = m.load_gens_per_bus;
         else if (name == "load_gen_type") v.assign(m.load_gen_type.begin(), m.load_gen_type.end());
+        else if (name == "voltage_regulators_per_load_gen") { // indptr form of the reference
+            v.assign(m.n_load_gen() + 1, 0);
+            for (size_t i = 0; i != m.load_gen_regulator.size(); ++i) v[i + 1] = v[i] + (m.load_gen_regulator[i] >= 0 ? 1 : 0);
+        }
         else {
             LuPattern const p{m};
             if (name == "row_indptr") v = p.row_indptr;

@@ -25,14 +25,14 @@ struct ComponentBuffer {
     void const* data;
 };
 struct InputData {
-    ComponentBuffer node, line, transformer, shunt, source, sym_gen, asym_gen, sym_load, asym_load;
+    ComponentBuffer node, line, transformer, shunt, source, sym_gen, asym_gen, sym_load, asym_load, voltage_regulator;
 };
 struct UpdateData {
     int64_t n_scenarios;
-    ComponentBuffer line, transformer, shunt, source, sym_gen, asym_gen, sym_load, asym_load;
+    ComponentBuffer line, transformer, shunt, source, sym_gen, asym_gen, sym_load, asym_load, voltage_regulator;
 };
 struct OutputData {
-    void *node, *line, *transformer, *shunt, *source, *sym_gen, *asym_gen, *sym_load, *asym_load;
+    void *node, *line, *transformer, *shunt, *source, *sym_gen, *asym_gen, *sym_load, *asym_load, *voltage_regulator;
 };
 struct ModelOptions {
     int32_t method;
@@ -91,8 +91,12 @@ class Model {
     std::vector<SourceState> source_st_;
     std::vector<ShuntState> shunt_st_;
     std::vector<LoadGenState> lg_st_;
+    // voltage regulators (component/voltage_regulator.hpp): static part, regulated load_gen (index into lg_), state
+    std::vector<VoltageRegulatorInput> reg_in_;
+    std::vector<Idx> reg_lg_;
+    std::vector<RegulatorState> reg_st_;
     // id lookup
-    std::unordered_map<ID, Idx> node_idx_, line_idx_, trafo_idx_, shunt_idx_, source_idx_, lg_idx_;
+    std::unordered_map<ID, Idx> node_idx_, line_idx_, trafo_idx_, shunt_idx_, source_idx_, lg_idx_, reg_idx_;
     std::unordered_map<ID, int> all_ids_;
 
     // caches
@@ -122,7 +126,16 @@ class Model {
     void prepare_topology();
     template <int B> void prepare_engines();
     template <int B> void param_arrays(Idx group, std::vector<double>& bp, std::vector<double>& sp, std::vector<double>& srcp) const;
-    template <int B> void gather_pf_input(std::vector<std::vector<double>>& sinj, std::vector<std::vector<double>>& uref) const;
+    // per-scenario inputs of the grids with voltage regulators: regulator parameters of the current state (per group, shared
+    // by the scenarios of one engine call) and the status of every load_gen (appended per scenario)
+    struct RegulatorInput {
+        std::vector<std::vector<double>> param;     // [group][n_reg][4]
+        std::vector<std::vector<int8_t>> lg_status; // [group][n_scn][n_lg]
+    };
+    template <int B>
+    void gather_pf_input(std::vector<std::vector<double>>& sinj, std::vector<std::vector<double>>& uref,
+                         RegulatorInput* reg = nullptr) const;
+    template <int B> void check_regulators(ModelOptions const& opt) const;
 
     struct Saved {
         std::vector<std::pair<Idx, BranchState>> branch;
@@ -130,6 +143,7 @@ class Model {
         std::vector<std::pair<Idx, SourceState>> source;
         std::vector<std::pair<Idx, ShuntState>> shunt;
         std::vector<std::pair<Idx, LoadGenState>> lg;
+        std::vector<std::pair<Idx, RegulatorState>> reg;
         bool topo{false}, param{false};
     };
     void apply_scenario(UpdateData const& u, Idx s, Saved* saved);
@@ -143,7 +157,7 @@ class Model {
     template <int B>
     int64_t run_block(ModelOptions const& opt, Idx n_scn, std::vector<std::vector<double>> const& sinj,
                       std::vector<std::vector<double>> const& uref, OutputData const& out, Idx first_scenario,
-                      int32_t* n_iter, int32_t* status);
+                      int32_t* n_iter, int32_t* status, RegulatorInput const* reg = nullptr);
     // ---- device path (model_device.cpp): updates applied and output structs written by CUDA kernels ----
     struct DeviceSide;
     std::shared_ptr<DeviceSide> dev_;
@@ -154,7 +168,8 @@ class Model {
                                   int32_t* n_iter, int32_t* status, Idx first_scenario);
     template <int B>
     void write_output(Idx n_scn, Idx first_scenario, OutputData const& out,
-                      std::vector<std::vector<double>> const (&so)[6]) const;
+                      std::vector<std::vector<double>> const (&so)[6], std::vector<std::vector<int8_t>> const& reg_out,
+                      std::vector<std::vector<int8_t>> const* lg_status) const;
 };
 
 } // namespace pgmb

@@ -16,9 +16,9 @@ namespace pgmb {
 using namespace blk;
 namespace {
 
-template <int T, int B, Mode mode>
+template <int T, int B, Mode mode, bool REG>
 __device__ void sweeps(DevStructure const& s, TileB<T, B> const& t, int slot, int n_slot, bool active, bool& singular,
-                       double& dev, unsigned long long* phase) {
+                       double& dev, unsigned long long* phase, bool check_now) {
     long long t0 = clock64();
     auto lap = [&](int k) { // PGMB_DEBUG_PHASES: up level 0 | up wide rows | up other levels | down levels >= 1 | down level 0
         if (phase != nullptr && threadIdx.x == 0) {
@@ -33,28 +33,30 @@ __device__ void sweeps(DevStructure const& s, TileB<T, B> const& t, int slot, in
             for (int i = b + slot; i < e; i += n_slot) {
                 int const row = __ldg(s.level_rows + i);
                 if (s.n_wide != 0 && __ldg(s.row_is_wide + row)) continue; // eliminated below by the whole block
-                singular |= up_row<T, B, mode>(s, t, row);
+                singular |= up_row<T, B, mode, false, REG>(s, t, row, check_now);
             }
         __syncthreads();
         lap(lv == 0 ? 0 : 2);
         if (s.n_wide != 0)
             for (int w = __ldg(s.wide_level_ptr + lv); w < __ldg(s.wide_level_ptr + lv + 1); ++w)
-                wide_up_row<T, B, mode, false>(s, t, w, slot, n_slot, active, singular);
+                wide_up_row<T, B, mode, false, REG>(s, t, w, slot, n_slot, active, singular, check_now);
         lap(1);
     }
     for (int lv = s.n_level - 1; lv >= 0; --lv) {
         int const b = __ldg(s.level_ptr + lv), e = __ldg(s.level_ptr + lv + 1);
         if (active)
-            for (int i = b + slot; i < e; i += n_slot) dev = fmax(dev, down_row<T, B, mode>(s, t, __ldg(s.level_rows + i)));
+            for (int i = b + slot; i < e; i += n_slot) dev = fmax(dev, down_row<T, B, mode, false, REG>(s, t, __ldg(s.level_rows + i)));
         __syncthreads();
         lap(lv == 0 ? 4 : 3);
     }
 }
 
-template <int T, int B> __global__ void nr_block_kernel(DevStructure s, DevBatch b, SolveOptions opt) {
+// REG: grids with voltage regulators (PV buses, Q limits); the plain instantiation carries none of that code
+template <int T, int B, bool REG> __global__ void nr_block_kernel(DevStructure s, DevBatch b, SolveOptions opt) {
     constexpr int N = 2 * B;
     __shared__ unsigned long long sh_dev[T];
     __shared__ int sh_singular[T];
+    __shared__ int sh_has_limits[T]; // REG: the scenario has a PV bus with a usable Q limit (limit check at iteration 2)
     int const lane = threadIdx.x % T, slot = threadIdx.x / T, n_slot = blockDim.x / T, tile = blockIdx.x;
     int64_t const scn = (int64_t)tile * T + lane;
     bool const valid = scn < b.n_scn;
@@ -69,11 +71,23 @@ template <int T, int B> __global__ void nr_block_kernel(DevStructure s, DevBatch
     t.wide_terms = b.wide_terms ? b.wide_terms + (size_t)tile * s.wide_max_upd * N * N * T + lane : nullptr;
     t.wide_rhs = b.wide_rhs ? b.wide_rhs + (size_t)tile * s.wide_max_lower * N * T + lane : nullptr;
     t.wide_sum = b.wide_sum ? b.wide_sum + (size_t)tile * s.wide_max_entries * N * T + lane : nullptr;
+    t.lg_status = b.lg_status ? b.lg_status + (size_t)tile * s.n_load_gen * T + lane : nullptr;
+    t.qviol = b.qviol ? b.qviol + (size_t)tile * s.n_bus * T + lane : nullptr;
     if (threadIdx.x < T) {
         sh_dev[threadIdx.x] = 0ull;
         sh_singular[threadIdx.x] = 0;
+        sh_has_limits[threadIdx.x] = 0;
     }
     __syncthreads();
+    if constexpr (REG) { // set_bus_types_and_q_limits (newton_raphson_pf_solver.hpp:400-444); no limit has been hit yet
+        if (valid)
+            for (int row = slot; row < s.n_bus; row += n_slot) {
+                t.qviol[(size_t)row * T] = 0;
+                if (__ldg(s.lg_ptr + row) != __ldg(s.lg_ptr + row + 1) && bus_control<T, B, false>(s, t, row).has_limits)
+                    sh_has_limits[lane] = 1;
+            }
+        __syncthreads();
+    }
     unsigned long long* const phase = b.phase_cycles ? b.phase_cycles + tile * 16 : nullptr;
     bool done = !valid;
     int status = kStatusOk, num_iter = 0;
@@ -81,7 +95,7 @@ template <int T, int B> __global__ void nr_block_kernel(DevStructure s, DevBatch
     {
         bool singular = false;
         double dev = 0.0;
-        sweeps<T, B, Mode::linear_init>(s, t, slot, n_slot, !done, singular, dev, phase);
+        sweeps<T, B, Mode::linear_init, REG>(s, t, slot, n_slot, !done, singular, dev, phase, false);
         if (singular) sh_singular[lane] = 1;
         __syncthreads();
         if (!done && sh_singular[lane]) {
@@ -101,7 +115,7 @@ template <int T, int B> __global__ void nr_block_kernel(DevStructure s, DevBatch
         if (!__syncthreads_or(!done)) break;
         bool singular = false;
         double dev = 0.0;
-        sweeps<T, B, Mode::newton>(s, t, slot, n_slot, !done, singular, dev, phase ? phase + 8 : nullptr);
+        sweeps<T, B, Mode::newton, REG>(s, t, slot, n_slot, !done, singular, dev, phase ? phase + 8 : nullptr, REG && num_iter >= 2);
         if (!done) {
             if (singular) sh_singular[lane] = 1;
             atomicMax(&sh_dev[lane], (unsigned long long)__double_as_longlong(dev));
@@ -113,7 +127,13 @@ template <int T, int B> __global__ void nr_block_kernel(DevStructure s, DevBatch
                 done = true;
             } else {
                 max_dev = __longlong_as_double((long long)sh_dev[lane]);
-                if (!(max_dev > opt.err_tol)) done = true;
+                if (!(max_dev > opt.err_tol)) {
+                    if (REG && sh_has_limits[lane] && num_iter < 2) {
+                        max_dev = INFINITY; // converged before the limit check: one more iteration (:343-347)
+                    } else {
+                        done = true;
+                    }
+                }
             }
         }
         __syncthreads();
@@ -128,24 +148,26 @@ template <int T, int B> __global__ void nr_block_kernel(DevStructure s, DevBatch
 
 } // namespace
 
-template <int B>
+template <int B, bool REG>
 static void launch_nr_block_b(int tw, DevStructure const& s, DevBatch const& b, SolveOptions const& opt, int n_slot,
                               cudaStream_t st) {
     switch (tw) {
-    case 4: nr_block_kernel<4, B><<<b.n_tile, 4 * n_slot, 0, st>>>(s, b, opt); break;
-    case 8: nr_block_kernel<8, B><<<b.n_tile, 8 * n_slot, 0, st>>>(s, b, opt); break;
-    case 16: nr_block_kernel<16, B><<<b.n_tile, 16 * n_slot, 0, st>>>(s, b, opt); break;
-    default: nr_block_kernel<32, B><<<b.n_tile, 32 * n_slot, 0, st>>>(s, b, opt); break;
+    case 4: nr_block_kernel<4, B, REG><<<b.n_tile, 4 * n_slot, 0, st>>>(s, b, opt); break;
+    case 8: nr_block_kernel<8, B, REG><<<b.n_tile, 8 * n_slot, 0, st>>>(s, b, opt); break;
+    case 16: nr_block_kernel<16, B, REG><<<b.n_tile, 16 * n_slot, 0, st>>>(s, b, opt); break;
+    default: nr_block_kernel<32, B, REG><<<b.n_tile, 32 * n_slot, 0, st>>>(s, b, opt); break;
     }
 }
 
 void launch_nr_block(int phases, int tw, DevStructure const& s, DevBatch const& b, SolveOptions const& opt, int n_slot,
                      cudaStream_t st) {
     count_kernel_launch();
+    bool const reg = s.lg_reg != nullptr;
+    if (reg && (b.qviol == nullptr || b.lg_status == nullptr)) return; // never: the engine allocates both with the regulators
     if (phases == 1) {
-        launch_nr_block_b<1>(tw, s, b, opt, n_slot, st);
+        reg ? launch_nr_block_b<1, true>(tw, s, b, opt, n_slot, st) : launch_nr_block_b<1, false>(tw, s, b, opt, n_slot, st);
     } else {
-        launch_nr_block_b<3>(tw, s, b, opt, n_slot, st);
+        reg ? launch_nr_block_b<3, true>(tw, s, b, opt, n_slot, st) : launch_nr_block_b<3, false>(tw, s, b, opt, n_slot, st);
     }
 }
 

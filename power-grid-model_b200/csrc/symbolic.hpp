@@ -30,6 +30,9 @@ struct MathTopology {
     std::vector<Idx> fill_in;        // [n_fill][2]
     std::vector<Idx> sources_per_bus, shunts_per_bus, load_gens_per_bus; // indptr
     std::vector<int8_t> load_gen_type;
+    // voltage regulator of each load_gen or -1 (at most one, main_core/input.hpp:216-241); empty = grid without regulators.
+    // Regulators are numbered in load_gen order = the reference's grouping by regulated object (topology.hpp:594-600).
+    std::vector<Idx> load_gen_regulator;
     Idx slack_bus{};
     bool is_radial{};
 
@@ -38,6 +41,11 @@ struct MathTopology {
     Idx n_source() const { return sources_per_bus.empty() ? 0 : sources_per_bus.back(); }
     Idx n_shunt() const { return shunts_per_bus.empty() ? 0 : shunts_per_bus.back(); }
     Idx n_load_gen() const { return load_gens_per_bus.empty() ? 0 : load_gens_per_bus.back(); }
+    Idx n_voltage_regulator() const {
+        Idx n = 0;
+        for (Idx const r : load_gen_regulator) n += r >= 0 ? 1 : 0;
+        return n;
+    }
 };
 
 // element kinds follow YBusElementType (common/enum.hpp:79-87): 0..3 = branch ff/ft/tf/tt, 4 = shunt

@@ -27,6 +27,7 @@ struct GridGraph {                      // component-level connectivity, compone
     std::vector<Idx> shunt_node;
     std::vector<Idx> load_gen_node;
     std::vector<int8_t> load_gen_type;
+    std::vector<Idx> regulated_load_gen;           // per voltage regulator: sequence number of its load_gen
 };
 
 struct Coupling {
@@ -36,7 +37,7 @@ struct Coupling {
 
 struct TopologyResult {
     std::vector<MathTopology> math;
-    std::vector<Coupling> node, branch, shunt, load_gen, source;
+    std::vector<Coupling> node, branch, shunt, load_gen, source, voltage_regulator;
 };
 
 namespace detail {
@@ -313,6 +314,24 @@ inline TopologyResult build_topology(GridGraph const& g) {
     for (size_t c = 0; c != g.load_gen_node.size(); ++c)
         if (res.load_gen[c].group != -1) res.math[res.load_gen[c].group].load_gen_type[res.load_gen[c].pos] = g.load_gen_type[c];
     group_by_bus(g.source_node, res.source, &MathTopology::sources_per_bus, [&](size_t c) { return g.source_status[c] != 0; });
+    // voltage regulators grouped by the math load_gen they regulate (topology.hpp:594-600); one regulator per load_gen at
+    // most, so the position of a regulator is the rank of its load_gen among the regulated ones
+    res.voltage_regulator.assign(g.regulated_load_gen.size(), {});
+    if (!g.regulated_load_gen.empty()) {
+        for (auto& m : res.math) m.load_gen_regulator.assign(m.n_load_gen(), -1);
+        for (size_t r = 0; r != g.regulated_load_gen.size(); ++r) {
+            Coupling const c = res.load_gen[g.regulated_load_gen[r]];
+            if (c.group != -1) res.math[c.group].load_gen_regulator[c.pos] = static_cast<Idx>(r); // component index for now
+        }
+        for (auto& m : res.math) {
+            Idx pos = 0;
+            for (Idx& r : m.load_gen_regulator)
+                if (r >= 0) {
+                    res.voltage_regulator[r] = {static_cast<Idx>(&m - res.math.data()), pos};
+                    r = pos++;
+                }
+        }
+    }
     return res;
 }
 

@@ -20,7 +20,7 @@ def _cplx_flat(a):
 
 class Engine:
     def __init__(self, *, symmetric, phase_shift, branch_bus_idx, sources_per_bus, shunts_per_bus, load_gens_per_bus,
-                 load_gen_type, fill_in=(), device=0):
+                 load_gen_type, fill_in=(), device=0, voltage_regulators_per_load_gen=None):
         self.symmetric = bool(symmetric)
         self.B = 1 if symmetric else 3
         self._keep = [
@@ -34,8 +34,16 @@ class Engine:
         self.n_source = int(spb[-1])
         self.n_shunt = int(shb[-1])
         self.n_load_gen = int(lgb[-1])
+        self.n_regulator = 0
+        vr_ptr = None
+        if voltage_regulators_per_load_gen is not None and len(voltage_regulators_per_load_gen):
+            vr = _arr(voltage_regulators_per_load_gen, np.int64)
+            assert len(vr) == self.n_load_gen + 1
+            self._keep.append(vr)
+            self.n_regulator = int(vr[-1])
+            vr_ptr = vr.ctypes.data
         topo = _lib.MathTopologyC(self.n_bus, ps.ctypes.data, self.n_branch, bb.ctypes.data, len(fi) // 2, fi.ctypes.data,
-                                  spb.ctypes.data, shb.ctypes.data, lgb.ctypes.data, lgt.ctypes.data)
+                                  spb.ctypes.data, shb.ctypes.data, lgb.ctypes.data, lgt.ctypes.data, vr_ptr)
         self._h = C.c_void_p()
         check(lib().pgmb_engine_create(C.byref(topo), C.c_int32(int(symmetric)), C.c_int32(device), C.byref(self._h)))
 
@@ -45,7 +53,7 @@ class Engine:
         eng = cls(symmetric=grid.sym, phase_shift=grid.phase_shift, branch_bus_idx=grid.branch_bus_idx,
                   sources_per_bus=grid.sources_per_bus, shunts_per_bus=grid.shunts_per_bus,
                   load_gens_per_bus=grid.load_gens_per_bus, load_gen_type=grid.load_gen_type, fill_in=grid.fill_in,
-                  device=device)
+                  device=device, voltage_regulators_per_load_gen=getattr(grid, "voltage_regulators_per_load_gen", None))
         eng.set_param(grid.branch_param, grid.shunt_param, grid.source_param)
         return eng
 
@@ -73,7 +81,7 @@ class Engine:
         return np.ctypeslib.as_array(ptr, shape=(n.value,)).copy().view(np.complex128).reshape(-1, self.B, self.B)
 
     # -- running ---------------------------------------------------------------------------------------------------
-    def _input(self, s_injection, source_u_ref):
+    def _input(self, s_injection, source_u_ref, voltage_regulator=None, load_gen_status=None):
         s = np.ascontiguousarray(np.asarray(s_injection, dtype=np.complex128))
         if s.ndim == 2 and self.B == 1:
             s = s.reshape(s.shape[0], s.shape[1], 1)
@@ -82,8 +90,15 @@ class Engine:
         u = np.ascontiguousarray(np.asarray(source_u_ref, dtype=np.complex128))
         shared = u.ndim == 1
         assert u.shape[-1] == self.n_source
-        self._in_keep = (s, u)
-        return _lib.PfInputC(n_scn, u.ctypes.data, int(shared), s.ctypes.data), n_scn
+        vr = ls = None
+        if self.n_regulator:
+            # (n_regulator, 4): status, u_ref, q_min, q_max per unit -- shared by the scenarios of the call
+            vr = np.ascontiguousarray(np.asarray(voltage_regulator, dtype=np.float64).reshape(self.n_regulator, 4))
+            if load_gen_status is not None:
+                ls = np.ascontiguousarray(np.asarray(load_gen_status, dtype=np.int8).reshape(n_scn, self.n_load_gen))
+        self._in_keep = (s, u, vr, ls)
+        return _lib.PfInputC(n_scn, u.ctypes.data, int(shared), s.ctypes.data, vr.ctypes.data if vr is not None else None,
+                             ls.ctypes.data if ls is not None else None), n_scn
 
     def _output(self, n_scn, full=True):
         B = self.B
@@ -99,21 +114,25 @@ class Engine:
                 "shunt": np.zeros((n_scn, self.n_shunt, 2, B), np.complex128),
                 "load_gen": np.zeros((n_scn, self.n_load_gen, 2, B), np.complex128),
             })
+        if self.n_regulator:
+            o["voltage_regulator"] = np.zeros((n_scn, self.n_regulator, 2), np.int8)  # limit_violated, generator_status
         c = _lib.SolverOutputC(*[o[k].ctypes.data if k in o and o[k].size else None for k in
-                                 ("u", "bus_injection", "branch", "source", "shunt", "load_gen", "status", "n_iter", "max_dev")])
+                                 ("u", "bus_injection", "branch", "source", "shunt", "load_gen", "status", "n_iter", "max_dev",
+                                  "voltage_regulator")])
         return o, c
 
-    def run(self, s_injection, source_u_ref, method="newton_raphson", err_tol=1e-8, max_iter=20, full_output=True):
+    def run(self, s_injection, source_u_ref, method="newton_raphson", err_tol=1e-8, max_iter=20, full_output=True,
+            voltage_regulator=None, load_gen_status=None):
         """s_injection: (n_scn, n_load_gen[, B]) complex; source_u_ref: (n_source,) shared or (n_scn, n_source).
         Returns dict of arrays; failed scenarios are flagged in out['status'] (no exception)."""
-        inp, n_scn = self._input(s_injection, source_u_ref)
+        inp, n_scn = self._input(s_injection, source_u_ref, voltage_regulator, load_gen_status)
         out, outc = self._output(n_scn, full_output)
         opt = _lib.RunOptionsC(_lib.METHODS[method], err_tol, max_iter)
         check(lib().pgmb_engine_run(self._h, C.byref(opt), C.byref(inp), C.byref(outc)), allow_batch=True)
         return out
 
-    def stage(self, s_injection, source_u_ref):
-        inp, n_scn = self._input(s_injection, source_u_ref)
+    def stage(self, s_injection, source_u_ref, voltage_regulator=None, load_gen_status=None):
+        inp, n_scn = self._input(s_injection, source_u_ref, voltage_regulator, load_gen_status)
         check(lib().pgmb_engine_stage(self._h, C.byref(inp)))
         self._n_staged = n_scn
 

@@ -38,6 +38,9 @@ INPUT = {
     "sym_load": _dt(_appliance_head + [("type", "i1"), ("p_specified", "f8"), ("q_specified", "f8")]),
     "asym_load": _dt(_appliance_head + [("type", "i1"), ("p_specified", "f8", (3,)), ("q_specified", "f8", (3,))]),
 }
+# voltage_regulator (PV buses with reactive-power limits, Newton-Raphson only)
+INPUT["voltage_regulator"] = _dt([("id", "i4"), ("regulated_object", "i4"), ("status", "i1"), ("u_ref", "f8"), ("q_min", "f8"),
+                                  ("q_max", "f8")])
 INPUT["sym_gen"] = INPUT["sym_load"]
 INPUT["asym_gen"] = INPUT["asym_load"]
 
@@ -49,6 +52,7 @@ UPDATE = {
     "sym_load": _dt([("id", "i4"), ("status", "i1"), ("p_specified", "f8"), ("q_specified", "f8")]),
     "asym_load": _dt([("id", "i4"), ("status", "i1"), ("p_specified", "f8", (3,)), ("q_specified", "f8", (3,))]),
 }
+UPDATE["voltage_regulator"] = _dt([("id", "i4"), ("status", "i1"), ("u_ref", "f8"), ("q_min", "f8"), ("q_max", "f8")])
 UPDATE["sym_gen"] = UPDATE["sym_load"]
 UPDATE["asym_gen"] = UPDATE["asym_load"]
 
@@ -68,6 +72,7 @@ def output_dtypes(sym: bool):
     return {
         "node": node, "line": branch, "transformer": branch, "shunt": appliance, "source": appliance,
         "sym_gen": appliance, "asym_gen": appliance, "sym_load": appliance, "asym_load": appliance,
+        "voltage_regulator": _dt([("id", "i4"), ("energized", "i1"), ("limit_violated", "i1")]),
     }
 
 
@@ -75,8 +80,9 @@ SYM_OUTPUT = output_dtypes(True)
 ASYM_OUTPUT = output_dtypes(False)
 
 # component storage order of the reference (all_components.hpp:36-39), PF subset
-COMPONENT_ORDER = ("node", "line", "transformer", "shunt", "source", "sym_gen", "asym_gen", "sym_load", "asym_load")
-UPDATABLE = ("line", "transformer", "shunt", "source", "sym_gen", "asym_gen", "sym_load", "asym_load")
+COMPONENT_ORDER = ("node", "line", "transformer", "shunt", "source", "sym_gen", "asym_gen", "sym_load", "asym_load",
+                   "voltage_regulator")
+UPDATABLE = ("line", "transformer", "shunt", "source", "sym_gen", "asym_gen", "sym_load", "asym_load", "voltage_regulator")
 
 
 def initialize_array(kind: str, component: str, shape, sym: bool = True):
@@ -94,6 +100,8 @@ def initialize_array(kind: str, component: str, shape, sym: bool = True):
     return arr
 
 
+assert INPUT["voltage_regulator"].itemsize == 40 and UPDATE["voltage_regulator"].itemsize == 32
+assert SYM_OUTPUT["voltage_regulator"].itemsize == 8
 assert INPUT["line"].itemsize == 88 and INPUT["transformer"].itemsize == 168 and INPUT["source"].itemsize == 56
 assert UPDATE["sym_load"].itemsize == 24 and UPDATE["asym_load"].itemsize == 56
 assert SYM_OUTPUT["node"].itemsize == 48 and ASYM_OUTPUT["node"].itemsize == 128

@@ -157,3 +157,47 @@ def random_scenarios(grid, n_scn, seed=0, scale=0.6):
     s = np.where(gen, -0.5 * (p + 1j * q), p + 1j * q)
     u_ref = rng.uniform(0.98, 1.06, (n_scn, len(grid.source_u_ref))) * np.exp(1j * rng.uniform(-0.05, 0.05, (n_scn, 1)))
     return s, u_ref
+
+
+def regulated_benchmark_grid(rings, n_gen=12, seed=3, q_lim=None, option=None, n_scn=8):
+    """Fictional benchmark grid plus `n_gen` const_pq generators under voltage regulators (PV buses): two buses carry two
+    regulated generators each (shared u_ref), some regulators have one-sided limits; the batch switches generators off in some
+    scenarios and varies one generator's P on top of the load profile.  Returns (FictionalGrid, input_data, update_data)."""
+    import pgm_b200
+    from pgm_b200 import structs
+
+    option = option or pgm_b200.BENCHMARK_OPTION
+    grid = pgm_b200.FictionalGrid(seed=0, has_mv_ring=rings, has_lv_ring=rings, **option)
+    inp = dict(grid.input_data)
+    rng = np.random.default_rng(seed)
+    nodes = rng.choice(inp["sym_load"]["node"], size=n_gen, replace=False)
+    nodes[-2:] = nodes[:2]
+    max_id = max(int(a["id"].max()) for a in inp.values() if len(a))
+    gen = structs.initialize_array("input", "sym_gen", n_gen)
+    gen["id"] = max_id + 1 + np.arange(n_gen)
+    gen["node"] = nodes
+    gen["status"] = 1
+    gen["type"] = 0
+    gen["p_specified"] = rng.uniform(2e3, 2e4, n_gen)
+    gen["q_specified"] = rng.uniform(-5e3, 5e3, n_gen)
+    reg = structs.initialize_array("input", "voltage_regulator", n_gen)
+    reg["id"] = max_id + 1 + n_gen + np.arange(n_gen)
+    reg["regulated_object"] = gen["id"]
+    reg["status"] = 1
+    reg["u_ref"] = rng.uniform(0.99, 1.03, n_gen)
+    reg["u_ref"][-2:] = reg["u_ref"][:2]
+    if q_lim is not None:
+        reg["q_min"] = -q_lim * rng.uniform(0.5, 1.5, n_gen)
+        reg["q_max"] = q_lim * rng.uniform(0.5, 1.5, n_gen)
+        reg["q_max"][2] = np.nan
+        reg["q_min"][3] = np.nan
+    inp["sym_gen"] = gen
+    inp["voltage_regulator"] = reg
+    upd = grid.batch_update(n_scn, seed=0)
+    g = structs.initialize_array("update", "sym_gen", (n_scn, n_gen))
+    g["id"] = gen["id"]
+    g["status"][1::3, 4] = 0
+    g["status"][2::4, -1] = 0
+    g["p_specified"][:, 5] = rng.uniform(1e3, 3e4, n_scn)
+    upd["sym_gen"] = g
+    return grid, inp, upd

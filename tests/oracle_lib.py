@@ -192,9 +192,12 @@ def math_pf(grid: MathGrid, method="newton_raphson", err_tol=1e-8, max_iter=20):
 
 
 # ---- component-level model -------------------------------------------------------------------------------------
+ORACLE_COMPONENT_ORDER = structs.COMPONENT_ORDER
+ORACLE_UPDATABLE = structs.UPDATABLE
+
+
 class _ModelInput(C.Structure):
-    _fields_ = [(f, t) for c in ("node", "line", "transformer", "shunt", "source", "sym_gen", "asym_gen", "sym_load", "asym_load")
-                for f, t in ((f"n_{c}", C.c_int64), (c, C.c_void_p))]
+    _fields_ = [(f, t) for c in ORACLE_COMPONENT_ORDER for f, t in ((f"n_{c}", C.c_int64), (c, C.c_void_p))]
 
 
 class _UpdateBuffer(C.Structure):
@@ -202,11 +205,11 @@ class _UpdateBuffer(C.Structure):
 
 
 class _BatchUpdate(C.Structure):
-    _fields_ = [("n_scenarios", C.c_int64)] + [(c, _UpdateBuffer) for c in structs.UPDATABLE]
+    _fields_ = [("n_scenarios", C.c_int64)] + [(c, _UpdateBuffer) for c in ORACLE_UPDATABLE]
 
 
 class _BatchOutput(C.Structure):
-    _fields_ = [(c, C.c_void_p) for c in structs.COMPONENT_ORDER]
+    _fields_ = [(c, C.c_void_p) for c in ORACLE_COMPONENT_ORDER]
 
 
 class Model:
@@ -216,7 +219,7 @@ class Model:
         self._keep = {}
         mi = _ModelInput()
         self.counts = {}
-        for c in structs.COMPONENT_ORDER:
+        for c in ORACLE_COMPONENT_ORDER:
             arr = input_data.get(c)
             n = 0 if arr is None else len(arr)
             self.counts[c] = n
@@ -270,7 +273,7 @@ class Model:
                 setattr(bu, c, buf)
             bu.n_scenarios = n_scn
         table = structs.SYM_OUTPUT if sym else structs.ASYM_OUTPUT
-        comps = output_components if output_components is not None else [c for c in structs.COMPONENT_ORDER if self.counts[c]]
+        comps = output_components if output_components is not None else [c for c in ORACLE_COMPONENT_ORDER if self.counts[c]]
         bo = _BatchOutput()
         result = {}
         for c in comps:

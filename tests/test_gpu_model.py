@@ -95,6 +95,64 @@ def test_asymmetric_benchmark_grid_batch_matches_oracle():
     _compare_with_oracle({k: v[None] for k, v in single.items()}, ref1, 1)
 
 
+@pytest.mark.parametrize("rings", [False, True])
+@pytest.mark.parametrize("q_lim", [None, 6e6])
+def test_voltage_regulators_on_the_benchmark_grid_match_oracle(rings, q_lim):
+    """PV buses: 12 regulated generators on the 1500-node grid, with and without reactive-power limits
+    (with limits some buses switch PV -> PQ at the iteration-2 check, lower and upper), generators switched off per scenario,
+    two generators sharing a bus.  Iteration counts, limit flags and the allocated Q must equal the oracle's."""
+    import grids
+
+    n_scn = 24
+    _, inp, update = grids.regulated_benchmark_grid(rings, q_lim=q_lim, n_scn=n_scn)
+    model = pgm_b200.PowerGridModel(inp)
+    res = model.calculate_power_flow(symmetric=True, update_data=update)
+    ref = orc.Model(inp).calculate(sym=True, update=update, threading=0)
+    assert ref["n_failed"] == 0
+    assert np.array_equal(model.n_iter, ref["n_iter"]), (model.n_iter, ref["n_iter"])
+    if q_lim is not None:
+        assert {0, 1, 2} <= set(np.unique(ref["voltage_regulator"]["limit_violated"]).tolist())
+    _compare_with_oracle(res, ref, n_scn)
+    # single calculation on the permanent state (diverges for the radial grid with limits -- in the oracle as well)
+    ref1 = orc.Model(inp).calculate(sym=True)
+    if ref1["n_failed"] == 0:
+        single = model.calculate_power_flow(symmetric=True)
+        assert model.n_iter[0] == ref1["n_iter"][0]
+        _compare_with_oracle({k: v[None] for k, v in single.items()}, ref1, 1)
+    else:
+        with pytest.raises(pgm_b200.BatchError, match="Iteration failed to converge"):
+            model.calculate_power_flow(symmetric=True)
+    # a regulator update in the batch (u_ref, status): scenario-by-scenario route
+    upd2 = {"voltage_regulator": pgm_b200.structs.initialize_array("update", "voltage_regulator", (4, 2))}
+    upd2["voltage_regulator"]["id"] = inp["voltage_regulator"]["id"][[2, 3]]
+    upd2["voltage_regulator"]["u_ref"][:, 0] = [1.0, 1.01, 1.02, np.nan]
+    upd2["voltage_regulator"]["status"][:, 1] = [0, 1, 0, -128]
+    res2 = model.calculate_power_flow(symmetric=True, update_data=upd2, continue_on_batch_error=True)
+    ref2 = orc.Model(inp).calculate(sym=True, update=upd2, threading=0)
+    ok = ref2["status"] == 0 if "status" in ref2 else np.ones(4, bool)
+    assert np.array_equal(model.status == 0, ok)
+    assert np.array_equal(model.n_iter[ok], ref2["n_iter"][ok])
+    if ok.any():
+        _compare_with_oracle({k: v[ok] for k, v in res2.items()}, {k: v[ok] for k, v in ref2.items() if k in res2}, int(ok.sum()))
+    assert ok.any() or q_lim is not None  # without limits the regulator-update scenarios converge
+    with pytest.raises(pgm_b200.PgmB200Error):
+        model.calculate_power_flow(symmetric=True, calculation_method="iterative_current")
+
+
+def test_voltage_regulators_asymmetric_match_oracle():
+    import grids
+
+    option = dict(n_node_total_specified=300, n_connection_per_lv_feeder=5, n_lv_feeder=4, n_node_per_mv_feeder=5, n_mv_feeder=3)
+    n_scn = 6
+    _, inp, update = grids.regulated_benchmark_grid(True, n_gen=6, option=option, n_scn=n_scn)
+    model = pgm_b200.PowerGridModel(inp)
+    res = model.calculate_power_flow(symmetric=False, update_data=update)
+    ref = orc.Model(inp).calculate(sym=False, update=update, threading=0)
+    assert ref["n_failed"] == 0
+    assert np.array_equal(model.n_iter, ref["n_iter"]), (model.n_iter, ref["n_iter"])
+    _compare_with_oracle(res, ref, n_scn)
+
+
 @pytest.mark.parametrize("method", ["iterative_current", "linear", "linear_current"])
 def test_asymmetric_other_methods_match_oracle(method):
     grid = pgm_b200.FictionalGrid(seed=0, n_node_total_specified=300, n_connection_per_lv_feeder=5, n_lv_feeder=4, n_node_per_mv_feeder=5,

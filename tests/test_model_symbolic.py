@@ -13,9 +13,9 @@ import validation_cases as vc
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 INDEX_NAMES = ("slack_bus", "is_radial", "branch_bus_idx", "fill_in", "sources_per_bus", "shunts_per_bus",
-               "load_gens_per_bus", "load_gen_type", "row_indptr", "col_indices", "bus_entry", "row_indptr_lu",
+               "load_gens_per_bus", "load_gen_type", "voltage_regulators_per_load_gen", "row_indptr", "col_indices", "bus_entry", "row_indptr_lu",
                "col_indices_lu", "diag_lu", "map_lu_y_bus", "lu_transpose_entry")
-COUPLING = ("coup.node", "coup.branch", "coup.shunt", "coup.load_gen", "coup.source")
+COUPLING = ("coup.node", "coup.branch", "coup.shunt", "coup.load_gen", "coup.source", "coup.voltage_regulator")
 REAL_NAMES = ("branch_param", "shunt_param", "source_param", "s_injection", "source_u_ref")
 
 
