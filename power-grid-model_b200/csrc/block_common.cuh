@@ -38,6 +38,10 @@ template <int T, int B, bool SymPerm = false> struct TileB {
     // PV buses (only read by the REG instantiations)
     uint8_t const* lg_status; // [n_load_gen][T]
     uint8_t* qviol;           // [n_bus][T]
+    // branch-outage overlay of this lane's scenario (DevOverlay), null = none
+    int32_t const* ovr_entry{nullptr}; // [4]
+    double const* ovr_y{nullptr};      // [4][B*B][2]
+    uint8_t const* dead{nullptr};      // [n_bus] buses without supply in this scenario: identity rows, voltage 0
     __device__ __forceinline__ void get_q(int bus, uint8_t* q) const {
         if constexpr (SymPerm) {
             static_assert(!SymPerm || B == 1, "byte-packed permutation is a 2 x 2 layout");
@@ -299,17 +303,24 @@ template <int T, int B, bool SP> __device__ __forceinline__ void zero_pv_rows(Ti
 // (contrib[r] = sum_c N[r][c], contrib[B + r] = sum_c H[r][c])
 template <int T, int B, Mode mode, bool SP>
 __device__ __forceinline__ void build_entry(DevStructure const& s, TileB<T, B, SP> const& t, double const* uir, double const* uii,
-                                            int k, double* blk, double* contrib) {
+                                            int k, double* blk, double* contrib, int row = -1) {
     constexpr int N = 2 * B, NN = N * N, BB2 = B * B * 2;
-    int const ky = __ldg(s.map_y + k);
+    int ky = __ldg(s.map_y + k);
+    if (t.dead != nullptr && ky >= 0 && (t.dead[row] != 0 || t.dead[__ldg(s.col_idx + k)] != 0)) ky = -1; // no coupling
 #pragma unroll
     for (int i = 0; i < NN; ++i) blk[i] = 0.0;
 #pragma unroll
     for (int i = 0; i < N; ++i) contrib[i] = 0.0;
     if (ky >= 0) {
         double y[BB2];
+        double const* ysrc = s.ydata + (size_t)ky * BB2;
+        if (t.ovr_entry != nullptr) { // this scenario replaces the entries of its switched branch
 #pragma unroll
-        for (int i = 0; i < BB2; ++i) y[i] = __ldg(s.ydata + (size_t)ky * BB2 + i);
+            for (int j = 0; j < 4; ++j)
+                if (t.ovr_entry[j] == ky) ysrc = t.ovr_y + j * BB2;
+        }
+#pragma unroll
+        for (int i = 0; i < BB2; ++i) y[i] = __ldg(ysrc + i);
         if constexpr (mode == Mode::newton) {
             int const j = __ldg(s.col_idx + k);
             double ujr[B], uji[B];
@@ -338,6 +349,16 @@ template <int T, int B, Mode mode, bool SP, bool REG = false>
 __device__ __forceinline__ void finish_diag(DevStructure const& s, TileB<T, B, SP> const& t, int row, double const* uir,
                                             double const* uii, double* acc, double* d, int viol = 0) {
     constexpr int N = 2 * B, NN = N * N, BB2 = B * B * 2;
+    if (t.dead != nullptr && t.dead[row] != 0) { // bus without supply: identity row, zero right-hand side -> u stays 0
+#pragma unroll
+        for (int i = 0; i < NN; ++i) d[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            d[i * N + i] = 1.0;
+            acc[i] = 0.0;
+        }
+        return;
+    }
     if constexpr (mode == Mode::newton) {
 #pragma unroll
         for (int p = 0; p < B; ++p) {
@@ -485,7 +506,7 @@ __device__ bool up_row(DevStructure const& s, TileB<T, B, SP> const& t, int row,
         // 1. build the row
         for (int k = rb; k < re; ++k) {
             double blk[NN], contrib[N];
-            build_entry<T, B, mode, SP>(s, t, uir, uii, k, blk, contrib);
+            build_entry<T, B, mode, SP>(s, t, uir, uii, k, blk, contrib, row);
             if (__ldg(s.map_y + k) >= 0) {
 #pragma unroll
                 for (int i = 0; i < N; ++i) acc[i] -= contrib[i];
@@ -726,7 +747,7 @@ __device__ void wide_up_row(DevStructure const& s, TileB<T, B, SP> const& t, int
         t.load_u(row, uir, uii);
         for (int idx = slot; idx < n_entries; idx += n_slot) {
             double blk[NN], contrib[N];
-            build_entry<T, B, mode, SP>(s, t, uir, uii, rb + idx, blk, contrib);
+            build_entry<T, B, mode, SP>(s, t, uir, uii, rb + idx, blk, contrib, row);
             t.store_blk(rb + idx, blk);
 #pragma unroll
             for (int i = 0; i < N; ++i) t.wide_sum[(size_t)(idx * N + i) * T] = contrib[i];

@@ -352,6 +352,7 @@ void Engine::allocate_batch(int64_t n) {
     db_.max_dev = d_max_dev_.get();
     db_.lg_status = d_lg_status_.get();
     db_.qviol = has_regulators() ? d_qviol_.get() : nullptr;
+    db_.ovl = DevOverlay{};
     db_.phase_cycles = nullptr;
     if (env_int("PGMB_DEBUG_PHASES", 0) != 0) {
         d_phase_.ensure(static_cast<size_t>(n_tile) * 16);
@@ -394,6 +395,63 @@ void Engine::stage_device(int64_t n, double const* source_u_ref, bool source_is_
     PGMB_CUDA(cudaStreamSynchronize(stream_)); // source_u_ref may be a temporary of the caller
 }
 
+void Engine::set_overlay(int64_t n_scn, int64_t const* math_branch, double const* bparam, int32_t const* comp,
+                         uint8_t const* energized, int32_t const* dead_off, uint8_t const* dead, size_t dead_bytes) {
+    if (device_ < 0) throw CudaError("engine was created without a CUDA device (symbolic only)");
+    if (n_scn != db_.n_scn) throw InvalidArgument("overlay size differs from the staged batch");
+    PGMB_CUDA(cudaSetDevice(device_));
+    size_t const bb2 = static_cast<size_t>(B_) * B_ * 2;
+    if (branch_entries_.empty()) {
+        branch_entries_.assign(topo_.n_branch(), {-1, -1, -1, -1});
+        for (Idx entry = 0; entry != pattern_.nnz; ++entry)
+            for (Idx e = pattern_.y_bus_entry_indptr[entry]; e != pattern_.y_bus_entry_indptr[entry + 1]; ++e)
+                if (pattern_.element_type[e] < 4) branch_entries_[pattern_.element_idx[e]][pattern_.element_type[e]] = static_cast<int32_t>(entry);
+    }
+    std::vector<int32_t> entry(n_scn * 4, -1), branch(n_scn, -1);
+    std::vector<double> y(n_scn * 4 * bb2, 0.0);
+    for (int64_t s = 0; s != n_scn; ++s) {
+        Idx const br = math_branch[s];
+        if (br < 0) continue;
+        if (br >= topo_.n_branch()) throw InvalidArgument("overlay branch out of range");
+        branch[s] = static_cast<int32_t>(br);
+        double const* np = bparam + s * 4 * bb2;
+        for (int k = 0; k != 4; ++k) {
+            int32_t const en = branch_entries_[br][k];
+            entry[s * 4 + k] = en;
+            if (en < 0) continue;
+            // the same sum as Engine::set_param, with this branch's contributions replaced
+            double* yo = &y[(s * 4 + k) * bb2];
+            for (Idx e = pattern_.y_bus_entry_indptr[en]; e != pattern_.y_bus_entry_indptr[en + 1]; ++e) {
+                int const kind = pattern_.element_type[e];
+                Idx const idx = pattern_.element_idx[e];
+                double const* src = kind == 4 ? &shunt_param_[idx * bb2] : (idx == br ? np + kind * bb2 : &branch_param_[(idx * 4 + kind) * bb2]);
+                for (size_t i = 0; i != bb2; ++i) yo[i] += src[i];
+            }
+        }
+    }
+    d_ovl_entry_.upload(entry, stream_);
+    d_ovl_branch_.upload(branch, stream_);
+    d_ovl_y_.upload(y, stream_);
+    d_ovl_bparam_.ensure(n_scn * 4 * bb2 + 1);
+    d_ovl_comp_.ensure(n_scn + 1);
+    d_ovl_energized_.ensure(n_scn + 1);
+    if (n_scn != 0) {
+        PGMB_CUDA(cudaMemcpyAsync(d_ovl_bparam_.get(), bparam, n_scn * 4 * bb2 * sizeof(double), cudaMemcpyHostToDevice, stream_));
+        PGMB_CUDA(cudaMemcpyAsync(d_ovl_comp_.get(), comp, n_scn * sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
+        PGMB_CUDA(cudaMemcpyAsync(d_ovl_energized_.get(), energized, n_scn, cudaMemcpyHostToDevice, stream_));
+    }
+    bool const any_dead = dead_off != nullptr && dead != nullptr && dead_bytes != 0;
+    if (any_dead) {
+        d_ovl_dead_off_.ensure(n_scn + 1);
+        d_ovl_dead_.ensure(dead_bytes);
+        PGMB_CUDA(cudaMemcpyAsync(d_ovl_dead_off_.get(), dead_off, n_scn * sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
+        PGMB_CUDA(cudaMemcpyAsync(d_ovl_dead_.get(), dead, dead_bytes, cudaMemcpyHostToDevice, stream_));
+    }
+    PGMB_CUDA(cudaStreamSynchronize(stream_));
+    db_.ovl = DevOverlay{d_ovl_entry_.get(), d_ovl_y_.get(), d_ovl_branch_.get(), d_ovl_bparam_.get(), d_ovl_comp_.get(), d_ovl_energized_.get(),
+                         any_dead ? d_ovl_dead_off_.get() : nullptr, any_dead ? d_ovl_dead_.get() : nullptr};
+}
+
 void Engine::fetch_status(int32_t* status, int32_t* n_iter) {
     PGMB_CUDA(cudaSetDevice(device_));
     if (db_.n_scn == 0) return;
@@ -429,6 +487,16 @@ DevBatch Engine::batch_view(int64_t tile_begin, int64_t tile_end) const {
     v.status += scn_begin;
     v.n_iter += scn_begin;
     v.max_dev += scn_begin;
+    if (v.ovl.entry != nullptr) {
+        size_t const bb2 = static_cast<size_t>(B_) * B_ * 2;
+        v.ovl.entry += scn_begin * 4;
+        v.ovl.y += scn_begin * 4 * bb2;
+        v.ovl.branch += scn_begin;
+        v.ovl.bparam += scn_begin * 4 * bb2;
+        v.ovl.comp += scn_begin;
+        v.ovl.energized += scn_begin;
+        if (v.ovl.dead_off != nullptr) v.ovl.dead_off += scn_begin;
+    }
     if (v.phase_cycles != nullptr) v.phase_cycles += tile_begin * 16;
     return v;
 }
@@ -473,10 +541,11 @@ void Engine::launch_solve(DevBatch const& b, SolveOptions const& opt, cudaStream
     if (b.qviol != nullptr) {
         PGMB_CUDA(cudaMemsetAsync(b.qviol, 0, static_cast<size_t>(b.n_tile) * topo_.n_bus * tile_width_, st));
     }
+    if (b.ovl.entry != nullptr && opt.method != 1) throw InvalidArgument("a branch-outage overlay needs the Newton-Raphson method");
     switch (opt.method) {
     case 1:
         // grids with voltage regulators (PV buses): the generic block kernel carries that logic for B = 1 and B = 3
-        if (!symmetric_ || has_regulators() || env_int("PGMB_KERNEL", 3) == 0) {
+        if (!symmetric_ || has_regulators() || b.ovl.entry != nullptr || env_int("PGMB_KERNEL", 3) == 0) {
             launch_nr_block(B_, tile_width_, ds_, b, opt, n_slot_, st);
         } else if (env_int("PGMB_KERNEL", 3) == 1) {
             launch_nr_sym(tile_width_, ds_, b, opt, n_slot_, st);

@@ -8,6 +8,7 @@
 
 #include <cuda_runtime.h>
 
+#include <array>
 #include <complex>
 #include <memory>
 #include <string>
@@ -120,6 +121,14 @@ class Engine {
     // device path of the model level: allocate the batch, upload per-scenario source references; load injections are then
     // produced on the device by the apply_load_update kernels (model_device.cpp)
     void stage_device(int64_t n_scn, double const* source_u_ref, bool source_is_shared);
+    // Branch-outage overlay for the staged batch (call after stage / stage_device): scenario s replaces the parameters of math
+    // branch `math_branch[s]` (-1 = none) by bparam[s] ([4][B][B] complex) -- the engine derives the replaced Y-bus entries, summing
+    // each entry's elements in the assembly order (y_bus.hpp:400-431).  comp / energized: the branch component's index and
+    // `energized` flag for the output kernels.  Only the Newton-Raphson block kernel and the result kernels read the overlay.
+    // dead_off / dead: per scenario the index of its mask of buses without supply ([n_mask][n_bus] bytes), -1 = none.
+    void set_overlay(int64_t n_scn, int64_t const* math_branch, double const* bparam, int32_t const* comp, uint8_t const* energized,
+                     int32_t const* dead_off = nullptr, uint8_t const* dead = nullptr, size_t dead_bytes = 0);
+    bool has_overlay() const { return db_.ovl.entry != nullptr; }
     void fetch_status(int32_t* status, int32_t* n_iter);
     float solve_staged(SolveOptions const& opt);            // kernels only; returns solver-kernel milliseconds
     // pipelined use (model device path): a view of the staged batch restricted to tiles [tile_begin, tile_end), and the solver
@@ -180,6 +189,11 @@ class Engine {
     DevBuf<int32_t> d_lg_reg_, d_reg_bus_;
     DevBuf<double> d_reg_param_;
     DevBuf<int8_t> d_out_reg_;
+    DevBuf<int32_t> d_ovl_entry_, d_ovl_branch_, d_ovl_comp_;
+    DevBuf<double> d_ovl_y_, d_ovl_bparam_;
+    DevBuf<uint8_t> d_ovl_energized_, d_ovl_dead_;
+    DevBuf<int32_t> d_ovl_dead_off_;
+    std::vector<std::array<int32_t, 4>> branch_entries_; // Y-bus entries (ff, ft, tf, tt) of each math branch, -1 = none
     std::vector<double> reg_param_;
     int n_reg_bus_{0};
     bool reg_param_set_{false};

@@ -61,6 +61,22 @@ struct DevStructure {
     double const* reg_param;  // [n_regulator][4] status, u_ref, q_min, q_max (per unit; NaN = no limit)
 };
 
+// Branch-outage overlay of a batch whose scenarios each switch one branch of the shared topology (N-1 studies): the symbolic
+// pattern stays the base grid's; a scenario replaces the values of the (at most four) Y-bus entries its branch contributes to and
+// the parameters of that branch.  Scenario-major arrays; entry == nullptr when the batch has no overlay.
+struct DevOverlay {
+    int32_t const* entry;     // [n_scn][4] Y-bus entries (ff, ft, tf, tt) with replaced values, -1 = unused slot
+    double const* y;          // [n_scn][4][B*B][2] replacement values
+    int32_t const* branch;    // [n_scn] math branch with replaced parameters, -1 = none
+    double const* bparam;     // [n_scn][4][B*B][2]
+    int32_t const* comp;      // [n_scn] component index of that branch (lines then transformers), -1 = none
+    uint8_t const* energized; // [n_scn] its `energized` flag in this scenario
+    // buses that lose their supply in a scenario (the switched branch was a bridge): their rows become identity rows, their
+    // voltage stays 0 and everything on them is reported as not energized
+    int32_t const* dead_off;  // [n_scn] index of the scenario's mask in `dead`, -1 = no bus is lost
+    uint8_t const* dead;      // [n_mask][n_bus]
+};
+
 // per-batch device buffers, tile layout (see above); B = phases, N = 2B
 struct DevBatch {
     int64_t n_scn;
@@ -81,6 +97,7 @@ struct DevBatch {
     double* wide_sum;   // [tile][wide_max_entries][N][T]
     uint8_t* lg_status; // [tile][n_load_gen][T] per-scenario status of each load_gen (device update path), may be null
     uint8_t* qviol;     // [tile][n_bus][T] reactive-power limit a PV bus ran into: 0 none, 1 lower, 2 upper; null = no regulators
+    DevOverlay ovl;     // branch-outage overlay (all null when unused)
     unsigned long long* phase_cycles; // optional [n_tile][8] clock64 totals per phase (PGMB_DEBUG_PHASES), may be null
 };
 

@@ -3,6 +3,7 @@
 #include <exception>
 #include <thread>
 
+#include <cstdio>
 #include <cstring>
 
 namespace pgmb {
@@ -672,6 +673,211 @@ int64_t Model::run_block(ModelOptions const& opt, Idx n_scn, std::vector<std::ve
     return failed;
 }
 
+// bridges of the graph of fully connected branches (iterative Tarjan; parallel branches are told apart by their edge id)
+Model::BridgeInfo Model::bridge_analysis() const {
+    Idx const n = static_cast<Idx>(node_.size());
+    Idx const nb = n_line() + n_trafo();
+    auto ends = [&](Idx b) -> std::pair<Idx, Idx> {
+        return b < n_line() ? std::pair<Idx, Idx>{node_seq(line_in_[b].from_node), node_seq(line_in_[b].to_node)}
+                            : std::pair<Idx, Idx>{node_seq(trafo_in_[b - n_line()].from_node), node_seq(trafo_in_[b - n_line()].to_node)};
+    };
+    std::vector<Idx> ptr(n + 1, 0);
+    std::vector<std::pair<Idx, Idx>> e(nb);
+    for (Idx b = 0; b != nb; ++b) {
+        e[b] = ends(b);
+        if (!branch_st_[b].from_status || !branch_st_[b].to_status || e[b].first == e[b].second) continue;
+        ++ptr[e[b].first + 1];
+        ++ptr[e[b].second + 1];
+    }
+    for (Idx i = 0; i != n; ++i) ptr[i + 1] += ptr[i];
+    std::vector<Idx> adj_node(ptr[n]), adj_edge(ptr[n]), cur(ptr.begin(), ptr.end() - 1);
+    for (Idx b = 0; b != nb; ++b) {
+        if (!branch_st_[b].from_status || !branch_st_[b].to_status || e[b].first == e[b].second) continue;
+        adj_node[cur[e[b].first]] = e[b].second;
+        adj_edge[cur[e[b].first]++] = b;
+        adj_node[cur[e[b].second]] = e[b].first;
+        adj_edge[cur[e[b].second]++] = b;
+    }
+    BridgeInfo info;
+    info.bridge.assign(nb, 0);
+    info.child.assign(nb, -1);
+    info.size.assign(n, 1);
+    info.n_source.assign(n, 0);
+    info.root.assign(n, -1);
+    info.order.assign(n, -1);
+    for (size_t i = 0; i != source_in_.size(); ++i)
+        if (source_st_[i].status) ++info.n_source[node_idx_.at(source_in_[i].node)];
+    std::vector<char>& bridge = info.bridge;
+    std::vector<Idx>& disc = info.disc;
+    disc.assign(n, -1);
+    std::vector<Idx> low(n, 0), parent_edge(n, -1), it(ptr.begin(), ptr.end() - 1), stack;
+    Idx timer = 0;
+    for (Idx root = 0; root != n; ++root) {
+        if (disc[root] != -1) continue;
+        info.order[timer] = root;
+        disc[root] = low[root] = timer++;
+        info.root[root] = root;
+        stack.push_back(root);
+        while (!stack.empty()) {
+            Idx const v = stack.back();
+            if (it[v] != ptr[v + 1]) {
+                Idx const w = adj_node[it[v]], eid = adj_edge[it[v]];
+                ++it[v];
+                if (eid == parent_edge[v]) continue;
+                if (disc[w] == -1) {
+                    info.order[timer] = w;
+                    disc[w] = low[w] = timer++;
+                    info.root[w] = root;
+                    parent_edge[w] = eid;
+                    stack.push_back(w);
+                } else {
+                    low[v] = std::min(low[v], disc[w]);
+                }
+            } else {
+                stack.pop_back();
+                if (!stack.empty()) {
+                    Idx const p = stack.back();
+                    low[p] = std::min(low[p], low[v]);
+                    info.size[p] += info.size[v];
+                    info.n_source[p] += info.n_source[v];
+                    if (low[v] > disc[p]) {
+                        bridge[parent_edge[v]] = 1;
+                        info.child[parent_edge[v]] = v;
+                    }
+                }
+            }
+        }
+    }
+    return info;
+}
+
+template <int B> bool Model::plan_outage_batch(UpdateData const& u, OutagePlan& plan) const {
+    if (u.shunt.data != nullptr || u.source.data != nullptr || u.sym_gen.data != nullptr || u.asym_gen.data != nullptr ||
+        u.sym_load.data != nullptr || u.asym_load.data != nullptr || u.voltage_regulator.data != nullptr) {
+        return false;
+    }
+    if (topo_.math.size() != 1 || u.n_scenarios <= 0) return false;
+    MathTopology const& m = topo_.math[0];
+    if (std::all_of(m.load_gen_type.begin(), m.load_gen_type.end(), [](int8_t t) { return t == 1; })) return false; // linear method
+    constexpr size_t bb2 = static_cast<size_t>(B) * B * 2;
+    Idx const n = u.n_scenarios;
+    BridgeInfo const info = bridge_analysis();
+    std::vector<char> const& bridge = info.bridge;
+    std::unordered_map<Idx, int32_t> mask_of_branch; // bridge -> its mask in plan.dead
+    plan.dead_off.assign(n, -1);
+    plan.dead.clear();
+    plan.math_branch.assign(n, -1);
+    plan.bparam.assign(n * 4 * bb2, 0.0);
+    plan.comp.assign(n, -1);
+    plan.energized.assign(n, 0);
+    plan.exact.clear();
+    auto lookup = [](ID id, Idx pos, Idx n_in_scenario, Idx n_comp, std::unordered_map<ID, Idx> const& map) -> Idx {
+        if (id == kNaID) {
+            if (n_in_scenario != n_comp) throw InvalidArgument("update without ids must cover every element of the component");
+            return pos;
+        }
+        auto it = map.find(id);
+        if (it == map.end()) throw InvalidArgument("The id cannot be found: " + std::to_string(id) + "\n");
+        return it->second;
+    };
+    struct Change {
+        Idx branch;
+        bool from, to;
+    };
+    std::vector<Change> changes;
+    for (Idx s = 0; s != n; ++s) {
+        changes.clear();
+        bool exact = false;
+        auto note = [&](Idx bi, IntS from, IntS to) {
+            auto it = std::find_if(changes.begin(), changes.end(), [bi](Change const& c) { return c.branch == bi; });
+            if (it == changes.end()) {
+                changes.push_back({bi, branch_st_[bi].from_status, branch_st_[bi].to_status});
+                it = changes.end() - 1;
+            }
+            if (from != kNaIntS) it->from = from != 0;
+            if (to != kNaIntS) it->to = to != 0;
+        };
+        {
+            auto [b, e] = scenario_span<BranchUpdate>(u.line, s);
+            for (auto p = b; p != e; ++p) note(lookup(p->id, p - b, e - b, n_line(), line_idx_), p->from_status, p->to_status);
+        }
+        {
+            auto [b, e] = scenario_span<TransformerUpdate>(u.transformer, s);
+            for (auto p = b; p != e; ++p) {
+                Idx const i = lookup(p->id, p - b, e - b, n_trafo(), trafo_idx_);
+                if (p->tap_pos != kNaIntS && p->tap_pos != trafo_st_[i].tap_pos) exact = true;
+                note(n_line() + i, p->from_status, p->to_status);
+            }
+        }
+        std::erase_if(changes, [this](Change const& c) { return c.from == branch_st_[c.branch].from_status && c.to == branch_st_[c.branch].to_status; });
+        if (!exact && changes.size() == 1) {
+            Change const& c = changes[0];
+            Coupling const cp = topo_.branch[c.branch];
+            bool const base_closed = branch_st_[c.branch].from_status && branch_st_[c.branch].to_status && cp.group == 0 &&
+                                     m.branch_bus_idx[2 * cp.pos] >= 0 && m.branch_bus_idx[2 * cp.pos + 1] >= 0 &&
+                                     m.branch_bus_idx[2 * cp.pos] != m.branch_bus_idx[2 * cp.pos + 1];
+            // a bridge cuts a subtree of the DFS off: fine when exactly one side keeps a source (the other side goes dark)
+            bool shared_pattern = base_closed;
+            if (base_closed && bridge[c.branch]) {
+                Idx const v = info.child[c.branch];
+                Idx const inside = info.n_source[v], outside = info.n_source[info.root[v]] - inside;
+                if ((inside == 0) == (outside == 0)) {
+                    shared_pattern = false; // two supplied islands (two math models), or an island that was dark already
+                } else {
+                    auto it = mask_of_branch.find(c.branch);
+                    if (it == mask_of_branch.end()) {
+                        int32_t const k = static_cast<int32_t>(plan.dead.size() / m.n_bus);
+                        plan.dead.resize(plan.dead.size() + m.n_bus, 0);
+                        uint8_t* mask = &plan.dead[static_cast<size_t>(k) * m.n_bus];
+                        Idx const r = info.root[v];
+                        auto mark = [&](Idx t0, Idx t1) {
+                            for (Idx t = t0; t != t1; ++t) {
+                                Coupling const nc = topo_.node[info.order[t]];
+                                if (nc.group == 0) mask[nc.pos] = 1;
+                            }
+                        };
+                        if (inside == 0) {
+                            mark(info.disc[v], info.disc[v] + info.size[v]);
+                        } else {
+                            mark(info.disc[r], info.disc[v]);
+                            mark(info.disc[v] + info.size[v], info.disc[r] + info.size[r]);
+                        }
+                        it = mask_of_branch.emplace(c.branch, k).first;
+                    }
+                    plan.dead_off[s] = it->second;
+                }
+            }
+            if (shared_pattern) {
+                plan.math_branch[s] = cp.pos;
+                plan.comp[s] = static_cast<int32_t>(c.branch);
+                plan.energized[s] = (c.from || c.to) ? 1 : 0;
+                BranchState const st{c.from, c.to};
+                if (c.branch < n_line()) {
+                    line_param<B>(line_c_[c.branch], st, &plan.bparam[s * 4 * bb2]);
+                } else {
+                    Idx const i = c.branch - n_line();
+                    transformer_param<B>(trafo_c_[i], st, trafo_st_[i].tap_pos, &plan.bparam[s * 4 * bb2]);
+                }
+                if (plan.dead_off[s] >= 0) { // still connected to a supplied bus?  otherwise the branch itself goes dark
+                    uint8_t const* mask = &plan.dead[static_cast<size_t>(plan.dead_off[s]) * m.n_bus];
+                    bool const from_live = c.from && mask[m.branch_bus_idx[2 * cp.pos]] == 0;
+                    bool const to_live = c.to && mask[m.branch_bus_idx[2 * cp.pos + 1]] == 0;
+                    if (!from_live && !to_live) {
+                        std::fill_n(&plan.bparam[s * 4 * bb2], 4 * bb2, 0.0);
+                        plan.energized[s] = 0;
+                    }
+                }
+            } else {
+                exact = true;
+            }
+        } else if (!changes.empty()) {
+            exact = true;
+        }
+        if (exact) plan.exact.push_back(s);
+    }
+    return true;
+}
+
 template <int B>
 int64_t Model::calculate_impl(ModelOptions const& opt, UpdateData const* update, OutputData const& out, int32_t* n_iter,
                               int32_t* status) {
@@ -706,6 +912,62 @@ int64_t Model::calculate_impl(ModelOptions const& opt, UpdateData const* update,
             }
         }
         bool device_done = false;
+        // branch-switching batches (N-1): scenarios that keep the grid connected run together on the base pattern; `todo` is
+        // what remains for the exact per-scenario route below
+        std::vector<Idx> todo;
+        bool todo_is_subset = false;
+        std::vector<int32_t> status_local;
+        if (structural && !source_param_change && !has_reg && (opt.method == 1 || opt.method == -128) && n > 0 &&
+            (update->line.data != nullptr || update->transformer.data != nullptr) && std::getenv("PGMB_N1_EXACT") == nullptr) {
+            prepare_engines<B>();
+            OutagePlan plan;
+            bool const planned = plan_outage_batch<B>(*update, plan);
+            if (std::getenv("PGMB_DEBUG_N1") != nullptr) {
+                std::fprintf(stderr, "[pgmb n-1] planned=%d scenarios=%lld exact=%zu plan_ms=%.2f\n", planned ? 1 : 0,
+                             static_cast<long long>(n), plan.exact.size(), ms_since(t0));
+            }
+            if (planned && 2 * plan.exact.size() <= static_cast<size_t>(n)) {
+                if (status == nullptr) {
+                    status_local.assign(n, 0);
+                    status = status_local.data();
+                }
+                UpdateData none{};
+                none.n_scenarios = n;
+                outage_plan_ = &plan;
+                timing[0] += ms_since(t0);
+                int64_t r = -1;
+                try {
+                    r = run_batch_device(opt, B, none, out, n_iter, status);
+                } catch (...) {
+                    outage_plan_ = nullptr;
+                    throw;
+                }
+                outage_plan_ = nullptr;
+                t0 = Clock::now();
+                if (r >= 0) {
+                    failed = r;
+                    for (Idx const s : plan.exact) // placeholders of the scenarios that are recomputed below
+                        if (status[s] != 0) --failed;
+                    todo = std::move(plan.exact);
+                    todo_is_subset = true;
+                    if (!todo.empty()) { // drop the placeholder messages
+                        std::string kept;
+                        size_t pos = 0;
+                        while (pos < batch_message.size()) {
+                            size_t const end = batch_message.find('\n', pos);
+                            std::string const line = batch_message.substr(pos, end == std::string::npos ? std::string::npos : end - pos + 1);
+                            bool drop = false;
+                            for (Idx const s : todo)
+                                if (line.rfind("Error in batch #" + std::to_string(s) + ":", 0) == 0) drop = true;
+                            if (!drop) kept += line;
+                            if (end == std::string::npos) break;
+                            pos = end + 1;
+                        }
+                        batch_message = std::move(kept);
+                    }
+                }
+            }
+        }
         if (!structural && !source_param_change) prepare_engines<B>(); // the eligibility test looks at the math topology
         if (!structural && !source_param_change && has_reg) check_regulators<B>(opt);
         // grids with voltage regulators: host-staged engine call (the device update / output kernels do not carry them yet)
@@ -718,7 +980,7 @@ int64_t Model::calculate_impl(ModelOptions const& opt, UpdateData const* update,
             }
             t0 = Clock::now();
         }
-        if (device_done) {
+        if (device_done || (todo_is_subset && todo.empty())) {
             // results written by the device path
         } else if (!structural && !source_param_change) {
             // fast path: one engine call for the whole batch
@@ -738,14 +1000,20 @@ int64_t Model::calculate_impl(ModelOptions const& opt, UpdateData const* update,
             // job dispatch (job_dispatch.hpp:88-160) the scenarios are spread over host threads, thread t taking scenarios
             // t, t + n_threads, ...; every thread works on its own copy of the model, whose engines own their CUDA streams,
             // so the symbolic stage of one scenario overlaps the kernels of the others.
+            if (!todo_is_subset) {
+                todo.resize(n);
+                for (Idx s = 0; s != n; ++s) todo[s] = s;
+            }
+            Idx const n_todo = static_cast<Idx>(todo.size());
             Idx n_threads = opt.threading > 0 ? opt.threading : static_cast<Idx>(std::thread::hardware_concurrency());
-            n_threads = std::max<Idx>(1, std::min<Idx>({n_threads, n, Idx{32}}));
+            n_threads = std::max<Idx>(1, std::min<Idx>({n_threads, n_todo, Idx{32}}));
             std::vector<std::string> messages(n);
             std::vector<int64_t> failed_per_thread(n_threads, 0);
             std::vector<std::exception_ptr> fatal(n_threads);
             auto worker = [&](Model& model, Idx t) {
                 try {
-                    for (Idx s = t; s < n; s += n_threads) {
+                    for (Idx k = t; k < n_todo; k += n_threads) {
+                        Idx const s = todo[k];
                         Saved saved;
                         try {
                             model.apply_scenario(*update, s, &saved);
@@ -788,7 +1056,7 @@ int64_t Model::calculate_impl(ModelOptions const& opt, UpdateData const* update,
             for (auto const& ex : fatal)
                 if (ex) std::rethrow_exception(ex);
             for (Idx t = 0; t != n_threads; ++t) failed += failed_per_thread[t];
-            for (Idx s = 0; s != n; ++s) batch_message += messages[s];
+            for (Idx const s : todo) batch_message += messages[s];
         }
     }
     timing[5] = ms_since(t_all);

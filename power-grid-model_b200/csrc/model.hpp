@@ -158,6 +158,30 @@ class Model {
     int64_t run_block(ModelOptions const& opt, Idx n_scn, std::vector<std::vector<double>> const& sinj,
                       std::vector<std::vector<double>> const& uref, OutputData const& out, Idx first_scenario,
                       int32_t* n_iter, int32_t* status, RegulatorInput const* reg = nullptr);
+    // ---- branch-outage batches on the shared symbolic pattern (N-1 studies) ----
+    // A scenario that switches ONE fully connected branch which is not a bridge of the grid keeps every node energized: it is
+    // solved on the base topology's pattern with the branch's admittance contributions replaced (Engine::set_overlay) instead of
+    // rebuilding topology, ordering and pattern for it as the reference does (main_model_impl.hpp:139-160 -> rebuild_topology).
+    // Same equations in another elimination order: results agree to rounding, not bit for bit.  Other scenarios (bridges,
+    // several branches, tap changes, branches that are open in the base state) take the exact per-scenario route.
+    struct OutagePlan {
+        std::vector<int64_t> math_branch;
+        std::vector<double> bparam;
+        std::vector<int32_t> comp;
+        std::vector<uint8_t> energized;
+        std::vector<int32_t> dead_off; // per scenario: mask of the buses that lose their supply (bridge outages), -1 = none
+        std::vector<uint8_t> dead;     // [n_mask][n_bus]
+        std::vector<Idx> exact;
+    };
+    // DFS over the fully connected branches: bridges and, for each bridge, the subtree it cuts off
+    struct BridgeInfo {
+        std::vector<char> bridge;     // per branch
+        std::vector<Idx> child;       // per branch: the DFS child end of a bridge
+        std::vector<Idx> disc, size, n_source, root, order; // per node: discovery time, subtree size / active sources, DFS root; node by time
+    };
+    BridgeInfo bridge_analysis() const;
+    OutagePlan const* outage_plan_{nullptr};
+    template <int B> bool plan_outage_batch(UpdateData const& update, OutagePlan& plan) const;
     // ---- device path (model_device.cpp): updates applied and output structs written by CUDA kernels ----
     struct DeviceSide;
     std::shared_ptr<DeviceSide> dev_;

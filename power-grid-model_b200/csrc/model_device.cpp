@@ -365,6 +365,13 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
     //      PCIe transfers of one chunk overlap the kernels of the others (both copy engines + the SMs busy at once) ----
     t0 = Clock::now();
     e.stage_device(n_scn, uref.data(), uref_shared);
+    if (outage_plan_ != nullptr) { // branch-outage overlay of this part's scenarios (model.hpp: OutagePlan)
+        OutagePlan const& plan = *outage_plan_;
+        size_t const bb2 = static_cast<size_t>(phases) * phases * 2;
+        e.set_overlay(n_scn, plan.math_branch.data() + first_scenario, plan.bparam.data() + first_scenario * 4 * bb2,
+                      plan.comp.data() + first_scenario, plan.energized.data() + first_scenario,
+                      plan.dead_off.data() + first_scenario, plan.dead.data(), plan.dead.size());
+    }
     SolveOptions const sopt = e.prepare_solve({opt.method, opt.err_tol, static_cast<int32_t>(opt.max_iter)});
     d.ensure_streams();
     d.flag.ensure(1);

@@ -124,7 +124,7 @@ __global__ void pack_node_asym_kernel(DevStructure s, DevBatch b, DevModelTables
     int const bus = __ldg(m.node_bus + node);
     double* o = out + idx * 16;
     int32_t const id = __ldg(m.node_id + node);
-    if (bus < 0) {
+    if (bus < 0 || bus_is_dead(b.ovl, scn, bus, s.n_bus)) {
         o[0] = head_word(id, 0);
         for (int k = 1; k < 16; ++k) o[k] = 0.0;
         return;
@@ -165,7 +165,12 @@ __global__ void pack_branch_asym_kernel(DevStructure s, DevBatch b, DevModelTabl
     int const mb = __ldg(m.branch_math + comp);
     double* o = out + idx * 26;
     int32_t const id = __ldg(m.branch_id + comp);
-    if (mb < 0) {
+    bool all_dead = false;
+    if (mb >= 0 && b.ovl.dead_off != nullptr) { // a branch whose connected sides all sit on buses that lost their supply
+        int const bf = __ldg(s.branch_bus + 2 * mb), bt = __ldg(s.branch_bus + 2 * mb + 1);
+        all_dead = (bf < 0 || bus_is_dead(b.ovl, scn, bf, s.n_bus)) && (bt < 0 || bus_is_dead(b.ovl, scn, bt, s.n_bus));
+    }
+    if (mb < 0 || all_dead) {
         o[0] = head_word(id, 0);
         for (int k = 1; k < 26; ++k) o[k] = 0.0;
         return;
@@ -174,7 +179,7 @@ __global__ void pack_branch_asym_kernel(DevStructure s, DevBatch b, DevModelTabl
     int const f = __ldg(s.branch_bus + 2 * mb), t = __ldg(s.branch_bus + 2 * mb + 1);
     V3 const uf = f >= 0 ? uv.get(scn, f) : V3{};
     V3 const ut = t >= 0 ? uv.get(scn, t) : V3{};
-    double const* bp = s.branch_param + (size_t)mb * 4 * 18;
+    double const* bp = branch_param_of(s, b.ovl, scn, mb, 18);
     V3 const i_f = vadd(mat_vec(bp, uf), mat_vec(bp + 18, ut));
     V3 const i_t = vadd(mat_vec(bp + 36, uf), mat_vec(bp + 54, ut));
     V3 const s_f = vmul(uf, vconj(i_f));
@@ -200,7 +205,9 @@ __global__ void pack_branch_asym_kernel(DevStructure s, DevBatch b, DevModelTabl
         max_it = ph == 0 ? i_to : fmax(max_it, i_to);
     }
     double const rating = __ldg(m.branch_rating + comp);
-    o[0] = head_word(id, __ldg(m.branch_energized + comp));
+    int energized = __ldg(m.branch_energized + comp);
+    if (b.ovl.comp != nullptr && __ldg(b.ovl.comp + scn) == comp) energized = __ldg(b.ovl.energized + scn);
+    o[0] = head_word(id, energized);
     o[1] = rating > 0.0 ? fmax(sum_sf, sum_st) / rating : fmax(max_if, max_it) / (-rating);
 }
 
@@ -216,7 +223,12 @@ __global__ void pack_appliance_asym_kernel(DevStructure s, DevBatch b, DevModelT
     int const kind = __ldg(m.app_kind + comp);
     double* o = out + idx * 16;
     int32_t const id = __ldg(m.app_id + comp);
-    if (a < 0) {
+    bool dead = false;
+    if (a >= 0 && b.ovl.dead_off != nullptr) {
+        int const bus = kind == 0 ? __ldg(s.shunt_bus + a) : (kind == 1 ? __ldg(s.src_bus + a) : __ldg(s.lg_bus + a));
+        dead = bus_is_dead(b.ovl, scn, bus, s.n_bus);
+    }
+    if (a < 0 || dead) {
         o[0] = head_word(id, 0);
         for (int k = 1; k < 16; ++k) o[k] = 0.0;
         return;

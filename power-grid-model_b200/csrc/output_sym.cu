@@ -121,7 +121,7 @@ __global__ void pack_node_sym_kernel(DevStructure s, DevBatch b, DevModelTables 
     int const bus = __ldg(m.node_bus + node);
     double* o = out + idx * 6;
     int32_t const id = __ldg(m.node_id + node);
-    if (bus < 0) {
+    if (bus < 0 || bus_is_dead(b.ovl, scn, bus, s.n_bus)) {
         o[0] = head_word(id, 0);
         o[1] = o[2] = o[3] = o[4] = o[5] = 0.0;
         return;
@@ -158,7 +158,12 @@ __global__ void pack_branch_sym_kernel(DevStructure s, DevBatch b, DevModelTable
     int const mb = __ldg(m.branch_math + comp);
     double* o = out + idx * 10;
     int32_t const id = __ldg(m.branch_id + comp);
-    if (mb < 0) {
+    bool all_dead = false;
+    if (mb >= 0 && b.ovl.dead_off != nullptr) { // a branch whose connected sides all sit on buses that lost their supply
+        int const bf = __ldg(s.branch_bus + 2 * mb), bt = __ldg(s.branch_bus + 2 * mb + 1);
+        all_dead = (bf < 0 || bus_is_dead(b.ovl, scn, bf, s.n_bus)) && (bt < 0 || bus_is_dead(b.ovl, scn, bt, s.n_bus));
+    }
+    if (mb < 0 || all_dead) {
         o[0] = head_word(id, 0);
         for (int k = 1; k < 10; ++k) o[k] = 0.0;
         return;
@@ -167,8 +172,9 @@ __global__ void pack_branch_sym_kernel(DevStructure s, DevBatch b, DevModelTable
     int const f = __ldg(s.branch_bus + 2 * mb), t = __ldg(s.branch_bus + 2 * mb + 1);
     C const uf = f >= 0 ? uv.get(scn, f) : C{0.0, 0.0};
     C const ut = t >= 0 ? uv.get(scn, t) : C{0.0, 0.0};
-    C const i_f = cadd(cmul(ldc(s.branch_param, mb * 4 + 0), uf), cmul(ldc(s.branch_param, mb * 4 + 1), ut));
-    C const i_t = cadd(cmul(ldc(s.branch_param, mb * 4 + 2), uf), cmul(ldc(s.branch_param, mb * 4 + 3), ut));
+    double const* bp = branch_param_of(s, b.ovl, scn, mb, 2);
+    C const i_f = cadd(cmul(ldc(bp, 0), uf), cmul(ldc(bp, 1), ut));
+    C const i_t = cadd(cmul(ldc(bp, 2), uf), cmul(ldc(bp, 3), ut));
     C const s_f = cmul(uf, conj(i_f));
     C const s_t = cmul(ut, conj(i_t));
     double const i_from = __ldg(m.branch_base_i + 2 * comp) * cabs_(i_f);
@@ -176,7 +182,9 @@ __global__ void pack_branch_sym_kernel(DevStructure s, DevBatch b, DevModelTable
     double const s_from = kBasePower * cabs_(s_f);
     double const s_to = kBasePower * cabs_(s_t);
     double const rating = __ldg(m.branch_rating + comp);
-    o[0] = head_word(id, __ldg(m.branch_energized + comp));
+    int energized = __ldg(m.branch_energized + comp);
+    if (b.ovl.comp != nullptr && __ldg(b.ovl.comp + scn) == comp) energized = __ldg(b.ovl.energized + scn);
+    o[0] = head_word(id, energized);
     o[1] = rating > 0.0 ? fmax(s_from, s_to) / rating : fmax(i_from, i_to) / (-rating);
     o[2] = kBasePower * s_f.r;
     o[3] = kBasePower * s_f.i;
@@ -200,7 +208,12 @@ __global__ void pack_appliance_sym_kernel(DevStructure s, DevBatch b, DevModelTa
     int const kind = __ldg(m.app_kind + comp);
     double* o = out + idx * 6;
     int32_t const id = __ldg(m.app_id + comp);
-    if (a < 0) {
+    bool dead = false;
+    if (a >= 0 && b.ovl.dead_off != nullptr) {
+        int const bus = kind == 0 ? __ldg(s.shunt_bus + a) : (kind == 1 ? __ldg(s.src_bus + a) : __ldg(s.lg_bus + a));
+        dead = bus_is_dead(b.ovl, scn, bus, s.n_bus);
+    }
+    if (a < 0 || dead) {
         o[0] = head_word(id, 0);
         o[1] = o[2] = o[3] = o[4] = o[5] = 0.0;
         return;

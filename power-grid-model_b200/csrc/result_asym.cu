@@ -24,7 +24,7 @@ __global__ void math_result_asym_kernel(DevStructure s, DevBatch b, int force_co
     }
     r -= s.n_bus;
     if (r < s.n_bus) {
-        if (out_inj != nullptr) store3(out_inj + (scn * s.n_bus + r) * 6, bus_injection3<T>(s, uv, scn, (int)r));
+        if (out_inj != nullptr) store3(out_inj + (scn * s.n_bus + r) * 6, bus_injection3<T>(s, uv, scn, (int)r, b.ovl));
         return;
     }
     r -= s.n_bus;
@@ -33,7 +33,7 @@ __global__ void math_result_asym_kernel(DevStructure s, DevBatch b, int force_co
             int const f = __ldg(s.branch_bus + 2 * r), t = __ldg(s.branch_bus + 2 * r + 1);
             V3 const uf = f >= 0 ? uv.get(scn, f) : V3{};
             V3 const ut = t >= 0 ? uv.get(scn, t) : V3{};
-            double const* bp = s.branch_param + (size_t)r * 4 * 18;
+            double const* bp = branch_param_of(s, b.ovl, scn, r, 18);
             V3 const i_f = vadd(mat_vec(bp, uf), mat_vec(bp + 18, ut));
             V3 const i_t = vadd(mat_vec(bp + 36, uf), mat_vec(bp + 54, ut));
             double* o = out_branch + (scn * s.n_branch + r) * 24;

@@ -66,10 +66,11 @@ template <int T> struct UView3 {
     }
 };
 
-template <int T> __device__ V3 bus_injection3(DevStructure const& s, UView3<T> const& uv, int64_t scn, int bus) {
+template <int T>
+__device__ V3 bus_injection3(DevStructure const& s, UView3<T> const& uv, int64_t scn, int bus, DevOverlay const& ovl) {
     V3 i_inj{};
     for (int k = __ldg(s.y_row_ptr + bus), ke = __ldg(s.y_row_ptr + bus + 1); k < ke; ++k) {
-        i_inj = vadd(i_inj, mat_vec(s.ydata + (size_t)k * 18, uv.get(scn, __ldg(s.y_col_idx + k))));
+        i_inj = vadd(i_inj, mat_vec(y_entry(s, ovl, scn, k, 18), uv.get(scn, __ldg(s.y_col_idx + k))));
     }
     return vmul(vconj(i_inj), uv.get(scn, bus));
 }
@@ -111,7 +112,7 @@ __device__ void source_result3(DevStructure const& s, DevBatch const& b, UView3<
         V3 const sv = load_gen_s3<T>(s, b.sinj, scn, lg, u, force_const_y ? 1 : __ldg(s.lg_type + lg));
         i_lg = vadd(i_lg, vconj(vdiv(sv, u)));
     }
-    V3 const i_inj_t = vsub(vconj(vdiv(bus_injection3<T>(s, uv, scn, bus), u)), i_lg);
+    V3 const i_inj_t = vsub(vconj(vdiv(bus_injection3<T>(s, uv, scn, bus, b.ovl), u)), i_lg);
     int const sb = __ldg(s.src_ptr + bus), se = __ldg(s.src_ptr + bus + 1);
     V3 i_src;
     if (se - sb == 1) {

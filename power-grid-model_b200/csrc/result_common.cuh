@@ -47,10 +47,30 @@ template <int T> struct UView {
     }
 };
 
-template <int T> __device__ __forceinline__ C bus_injection(DevStructure const& s, UView<T> const& uv, int64_t scn, int bus) {
+// value block of Y-bus entry k for scenario scn: the shared admittance or the scenario's branch-outage replacement
+__device__ __forceinline__ double const* y_entry(DevStructure const& s, DevOverlay const& o, int64_t scn, int k, int bb2) {
+    if (o.entry != nullptr) {
+        for (int j = 0; j < 4; ++j)
+            if (__ldg(o.entry + scn * 4 + j) == k) return o.y + (scn * 4 + j) * bb2;
+    }
+    return s.ydata + (size_t)k * bb2;
+}
+__device__ __forceinline__ bool bus_is_dead(DevOverlay const& o, int64_t scn, int bus, int n_bus) {
+    if (o.dead_off == nullptr) return false;
+    int32_t const off = __ldg(o.dead_off + scn);
+    return off >= 0 && __ldg(o.dead + (size_t)off * n_bus + bus) != 0;
+}
+// parameters of math branch r for scenario scn
+__device__ __forceinline__ double const* branch_param_of(DevStructure const& s, DevOverlay const& o, int64_t scn, int64_t r, int bb2) {
+    if (o.branch != nullptr && __ldg(o.branch + scn) == r) return o.bparam + scn * 4 * bb2;
+    return s.branch_param + (size_t)r * 4 * bb2;
+}
+
+template <int T>
+__device__ __forceinline__ C bus_injection(DevStructure const& s, UView<T> const& uv, int64_t scn, int bus, DevOverlay const& ovl) {
     C i_inj{0.0, 0.0};
     for (int k = __ldg(s.y_row_ptr + bus), ke = __ldg(s.y_row_ptr + bus + 1); k < ke; ++k) {
-        i_inj = cadd(i_inj, cmul(ldc(s.ydata, k), uv.get(scn, __ldg(s.y_col_idx + k))));
+        i_inj = cadd(i_inj, cmul(ldc(y_entry(s, ovl, scn, k, 2), 0), uv.get(scn, __ldg(s.y_col_idx + k))));
     }
     return cmul(conj(i_inj), uv.get(scn, bus));
 }
@@ -78,7 +98,7 @@ __device__ __forceinline__ void source_result(DevStructure const& s, DevBatch co
         C const sv = load_gen_s<T>(s, b.sinj, scn, lg, u, force_const_y ? 1 : __ldg(s.lg_type + lg));
         i_lg = cadd(i_lg, conj(cdiv(sv, u)));
     }
-    C const i_inj_t = csub(conj(cdiv(bus_injection<T>(s, uv, scn, bus), u)), i_lg);
+    C const i_inj_t = csub(conj(cdiv(bus_injection<T>(s, uv, scn, bus, b.ovl), u)), i_lg);
     int const sb = __ldg(s.src_ptr + bus), se = __ldg(s.src_ptr + bus + 1);
     C i_src;
     if (se - sb == 1) {

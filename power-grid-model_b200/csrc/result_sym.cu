@@ -30,7 +30,7 @@ __global__ void math_result_sym_kernel(DevStructure s, DevBatch b, int force_con
     r -= s.n_bus;
     if (r < s.n_bus) { // bus injection
         if (out_inj != nullptr) {
-            C const v = bus_injection<T>(s, uv, scn, (int)r);
+            C const v = bus_injection<T>(s, uv, scn, (int)r, b.ovl);
             out_inj[(scn * s.n_bus + r) * 2] = v.r;
             out_inj[(scn * s.n_bus + r) * 2 + 1] = v.i;
         }
@@ -42,8 +42,9 @@ __global__ void math_result_sym_kernel(DevStructure s, DevBatch b, int force_con
             int const f = __ldg(s.branch_bus + 2 * r), t = __ldg(s.branch_bus + 2 * r + 1);
             C const uf = f >= 0 ? uv.get(scn, f) : C{0.0, 0.0};
             C const ut = t >= 0 ? uv.get(scn, t) : C{0.0, 0.0};
-            C const i_f = cadd(cmul(ldc(s.branch_param, r * 4 + 0), uf), cmul(ldc(s.branch_param, r * 4 + 1), ut));
-            C const i_t = cadd(cmul(ldc(s.branch_param, r * 4 + 2), uf), cmul(ldc(s.branch_param, r * 4 + 3), ut));
+            double const* bp = branch_param_of(s, b.ovl, scn, r, 2);
+            C const i_f = cadd(cmul(ldc(bp, 0), uf), cmul(ldc(bp, 1), ut));
+            C const i_t = cadd(cmul(ldc(bp, 2), uf), cmul(ldc(bp, 3), ut));
             C const s_f = cmul(uf, conj(i_f));
             C const s_t = cmul(ut, conj(i_t));
             double* o = out_branch + (scn * s.n_branch + r) * 8;

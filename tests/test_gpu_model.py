@@ -241,11 +241,50 @@ def test_pinned_buffers_and_reused_outputs():
     assert all(again[c] is first[c] or again[c].ctypes.data == first[c].ctypes.data for c in first)
 
 
+def test_mixed_outage_batch_matches_oracle():
+    """Shared-pattern outages mixed with scenarios that need their own topology: a transformer outage that de-energises a
+    whole LV grid (bridge), two lines at once, a tap change together with a switched line -- asymmetric and symmetric."""
+    grid = pgm_b200.FictionalGrid(seed=0, n_node_total_specified=300, n_connection_per_lv_feeder=5, n_lv_feeder=4, n_node_per_mv_feeder=5,
+                                  n_mv_feeder=3, has_mv_ring=True, has_lv_ring=True)
+    lines, trafos = grid.input_data["line"], grid.input_data["transformer"]
+    n_scn = 10
+    line_rows, trafo_rows = [], []
+    for s in range(n_scn):
+        lu = pgm_b200.structs.initialize_array("update", "line", 2 if s == 4 else 1)
+        lu["id"] = lines["id"][[(11 * s + 3) % len(lines), (11 * s + 17) % len(lines)][: len(lu)]]
+        lu["from_status"] = 0
+        lu["to_status"] = 0
+        tu = pgm_b200.structs.initialize_array("update", "transformer", 1 if s in (2, 6) else 0)
+        if s == 2:  # bridge: the source transformer -- everything behind it loses its supply
+            tu["id"] = trafos["id"][0]
+            tu["from_status"] = 0
+            tu["to_status"] = 0
+            lu = lu[:0]
+        if s == 6:
+            tu["id"] = trafos["id"][0]
+            tu["tap_pos"] = trafos["tap_pos"][0] + 1
+        line_rows.append(lu)
+        trafo_rows.append(tu)
+    update = {"line": {"data": np.concatenate(line_rows), "indptr": np.cumsum([0] + [len(x) for x in line_rows])},
+              "transformer": {"data": np.concatenate(trafo_rows), "indptr": np.cumsum([0] + [len(x) for x in trafo_rows])}}
+    for sym in (True, False):
+        model = pgm_b200.PowerGridModel(grid.input_data)
+        res = model.calculate_power_flow(symmetric=sym, update_data=update)
+        ref = orc.Model(grid.input_data).calculate(sym=sym, update=update, threading=0)
+        assert ref["n_failed"] == 0 and np.array_equal(model.n_iter, ref["n_iter"]), (model.n_iter, ref["n_iter"])
+        assert (ref["node"]["energized"][2] == 0).any() and (res["node"]["energized"][2] == ref["node"]["energized"][2]).all()
+        _compare_with_oracle(res, ref, n_scn)
+
+
+@pytest.mark.parametrize("exact", [False, True])
 @pytest.mark.parametrize("threads", [1, 4])
-def test_branch_switching_batch_on_host_threads(threads):
-    """N-1 style batch (config 5 shape): every scenario switches another line off, so every scenario has its own topology.
-    The scenarios are dispatched over host threads with one model copy each (job_dispatch.hpp:88-160); results and
-    per-scenario errors must not depend on the thread count and must equal the oracle's."""
+def test_branch_switching_batch_on_host_threads(threads, exact, monkeypatch):
+    """N-1 style batch (config 5 shape): every scenario switches another line off.  exact=True (PGMB_N1_EXACT): every scenario
+    gets its own topology like in the reference, dispatched over host threads with one model copy each
+    (job_dispatch.hpp:88-160).  exact=False (default): scenarios whose branch is not a bridge share the base pattern (branch
+    outage overlay), the others take the exact route.  Either way results and per-scenario errors must equal the oracle's."""
+    if exact:
+        monkeypatch.setenv("PGMB_N1_EXACT", "1")
     grid = pgm_b200.FictionalGrid(seed=0, n_node_total_specified=300, n_connection_per_lv_feeder=5, n_lv_feeder=4, n_node_per_mv_feeder=5,
                                   n_mv_feeder=3, has_mv_ring=True, has_lv_ring=True)
     lines = grid.input_data["line"]
@@ -254,11 +293,19 @@ def test_branch_switching_batch_on_host_threads(threads):
     upd["id"][:, 0] = lines["id"][np.arange(n_scn) * 7 % len(lines)]
     upd["from_status"][:, 0] = 0
     upd["to_status"][:, 0] = 0
+    upd["to_status"][3, 0] = 1      # one side stays connected
+    upd["from_status"][5, 0] = -128  # only the to side opens
+    upd["from_status"][7, 0] = 1     # no change at all
+    upd["to_status"][7, 0] = 1
     model = pgm_b200.PowerGridModel(grid.input_data)
+    launches0 = int(pgm_b200.lib().pgmb_kernel_launch_count())
     res = model.calculate_power_flow(update_data={"line": upd}, threading=threads)
+    launches = int(pgm_b200.lib().pgmb_kernel_launch_count()) - launches0
     ref = orc.Model(grid.input_data).calculate(sym=True, update={"line": upd}, threading=0)
     assert ref["n_failed"] == 0 and np.array_equal(model.n_iter, ref["n_iter"])
     _compare_with_oracle(res, ref, n_scn)
+    if not exact:
+        assert launches < 4 * n_scn, launches  # one shared-pattern batch, not a solver launch per scenario
     base = model.calculate_power_flow()  # the model itself is untouched by the batch
     ref0 = orc.Model(grid.input_data).calculate(sym=True)
     _compare_with_oracle({k: v[None] for k, v in base.items()}, ref0, 1)

@@ -39,3 +39,4 @@ if os.environ.get("ORACLE", "1") == "1":
     print(f"oracle (all cores): {1e3 * dt / n_scn:.1f} ms/scenario; n_iter equal {np.array_equal(ref['n_iter'], model.n_iter)}")
     ok = model.status == 0
     print("max |du_pu|", float(np.max(np.abs(res["node"]["u_pu"][ok] - ref["node"]["u_pu"][ok]))))
+print("timing", {k: round(v, 2) for k, v in model.timing().items()})
