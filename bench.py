@@ -143,6 +143,23 @@ def other_configs(pgm_b200, np, device):
         ms = [eng.solve_staged(method=method, err_tol=ERR_TOL, max_iter=MAX_ITER) for _ in range(2)][-1]
         out[f"configs[3] radial grid, {method}, 12500 scenarios (one GPU's share of 100k over 8)"] = {
             "kernel_ms": ms, "scenarios_per_s": 12500 / ms * 1e3}
+    # configs[4] shape at the 1500-node size: asymmetric N-1 batch (one line switched off per scenario) through the public
+    # API; scenarios share the base grid's symbolic pattern (branch-outage overlay), node output only; second of two calls
+    n1 = 1000
+    lines = ringed.input_data["line"]
+    upd = pgm_b200.structs.initialize_array("update", "line", (n1, 1))
+    upd["id"][:, 0] = lines["id"][np.random.default_rng(0).choice(len(lines), n1, replace=False)]
+    upd["from_status"][:, 0] = 0
+    upd["to_status"][:, 0] = 0
+    model = pgm_b200.PowerGridModel(ringed.input_data)
+    for _ in range(2):
+        t0 = time.perf_counter()
+        model.calculate_power_flow(symmetric=False, update_data={"line": upd}, output_component_types=["node"],
+                                   reuse_output_buffers=True, device=device)
+        wall = 1e3 * (time.perf_counter() - t0)
+    out["configs[4] shape, ringed 1804-node grid, asymmetric N-1 (1000 single-line outages, shared pattern), public API"] = {
+        "wall_ms": wall, "kernel_ms": model.timing()["solve_kernel"], "scenarios_per_s": n1 / wall * 1e3,
+        "failed": int((model.status != 0).sum())}
     return out
 
 

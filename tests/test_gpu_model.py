@@ -372,6 +372,43 @@ def test_50k_node_ringed_grid_matches_oracle(sym, n_scn):
     _compare_with_oracle({k: v[pick] for k, v in res.items()}, ref, len(pick))
 
 
+def test_config5_n1_batch_on_the_50k_node_grid():
+    """BASELINE config 5 shape: asymmetric N-1 batch on the 53 068-node ringed grid.  All scenarios share the base grid's
+    symbolic pattern (branch-outage overlay, bridge outages with masked buses).  Checked: (1) a sample of scenarios against
+    the oracle, which rebuilds the topology per scenario like the reference (iteration counts identical, results within the
+    north_star tolerances); (2) at full batch size the properties of an outage: the switched line carries nothing and is not
+    energised, every scenario converges, one kernel batch instead of a solver launch per scenario."""
+    opt = dict(pgm_b200.BENCHMARK_OPTION)
+    opt["n_node_total_specified"] = 50000
+    grid = pgm_b200.FictionalGrid(seed=0, has_mv_ring=True, has_lv_ring=True, **opt)
+    lines = grid.input_data["line"]
+    n_scn = 96
+    pick_lines = np.random.default_rng(5).choice(len(lines), n_scn, replace=False)
+    upd = pgm_b200.structs.initialize_array("update", "line", (n_scn, 1))
+    upd["id"][:, 0] = lines["id"][pick_lines]
+    upd["from_status"][:, 0] = 0
+    upd["to_status"][:, 0] = 0
+    model = pgm_b200.PowerGridModel(grid.input_data)
+    launches0 = int(pgm_b200.lib().pgmb_kernel_launch_count())
+    res = model.calculate_power_flow(symmetric=False, update_data={"line": upd}, output_component_types=["node", "line", "asym_load"])
+    launches = int(pgm_b200.lib().pgmb_kernel_launch_count()) - launches0
+    assert (model.status == 0).all()
+    assert launches < n_scn, launches
+    rows = np.arange(n_scn)
+    switched = res["line"][rows, pick_lines]
+    assert (switched["energized"] == 0).all()
+    for name in ("p_from", "q_from", "i_from", "s_from", "p_to", "q_to", "i_to", "s_to", "loading"):
+        assert np.all(switched[name] == 0.0), name
+    dark = res["node"]["energized"] == 0
+    assert dark.any() and not dark.all(axis=1).any()  # some outages are bridges; no scenario loses the whole grid
+    assert np.all(res["node"]["u_pu"][dark] == 0.0) and np.all(res["node"]["u_pu"][~dark] > 0.5)
+    pick = [0, 17, int(np.argmax(dark.sum(axis=1)))]  # the last one is the bridge that darkens most nodes
+    sample = {"line": np.ascontiguousarray(upd[pick])}
+    ref = orc.Model(grid.input_data).calculate(sym=False, update=sample, threading=0, output_components=["node", "line", "asym_load"])
+    assert ref["n_failed"] == 0 and np.array_equal(model.n_iter[pick], ref["n_iter"])
+    _compare_with_oracle({k: v[pick] for k, v in res.items()}, ref, len(pick))
+
+
 def test_batch_larger_than_the_memory_budget_is_split(monkeypatch):
     """a batch whose working set exceeds the device budget runs in parts over offset views of the caller's buffers"""
     grid = pgm_b200.FictionalGrid(seed=0, n_node_total_specified=300, n_connection_per_lv_feeder=5, n_lv_feeder=4, n_node_per_mv_feeder=5,
