@@ -395,6 +395,12 @@ void Engine::stage_device(int64_t n, double const* source_u_ref, bool source_is_
     PGMB_CUDA(cudaStreamSynchronize(stream_)); // source_u_ref may be a temporary of the caller
 }
 
+void Engine::launch_regulator_apply(DevBatch const& view, int8_t* out_reg, cudaStream_t st) {
+    if (!has_regulators() || view.n_scn == 0) return;
+    pgmb::launch_regulator_apply(B_, tile_width_, ds_, view, d_reg_bus_.get(), n_reg_bus_, out_reg, st);
+    PGMB_CUDA(cudaGetLastError());
+}
+
 void Engine::set_overlay(int64_t n_scn, int64_t const* math_branch, double const* bparam, int32_t const* comp,
                          uint8_t const* energized, int32_t const* dead_off, uint8_t const* dead, size_t dead_bytes) {
     if (device_ < 0) throw CudaError("engine was created without a CUDA device (symbolic only)");

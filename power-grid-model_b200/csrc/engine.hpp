@@ -117,6 +117,9 @@ class Engine {
     // voltage regulator parameters of the next solves: [n_regulator][4] status, u_ref, q_min, q_max
     void set_regulators(double const* param);
     bool has_regulators() const { return !topo_.load_gen_regulator.empty(); }
+    // device pipeline: Q allocation of the regulated generators of a solved chunk (rewrites their Q in the injection buffer) and
+    // the per-regulator flags [n_scn][n_regulator][2] for the output kernel
+    void launch_regulator_apply(DevBatch const& view, int8_t* out_reg, cudaStream_t st);
     void stage(PfInputView const& in);                      // H2D + layout conversion
     // device path of the model level: allocate the batch, upload per-scenario source references; load injections are then
     // produced on the device by the apply_load_update kernels (model_device.cpp)
@@ -241,6 +244,10 @@ void launch_pack_appliance_asym(int tw, DevStructure const& s, DevBatch const& b
 void launch_regulator_result(int phases, int tile_width, DevStructure const& s, DevBatch const& b, int32_t const* reg_bus,
                              int n_reg_bus, double const* out_u, double const* out_inj, double* out_lg, int8_t* out_reg,
                              cudaStream_t st);
+void launch_regulator_apply(int phases, int tile_width, DevStructure const& s, DevBatch const& b, int32_t const* reg_bus,
+                            int n_reg_bus, int8_t* out_reg, cudaStream_t st);
+void launch_pack_regulator(int64_t n_scn, int n_comp, int n_regulator, int32_t const* id, int32_t const* math, uint8_t const* status,
+                           int8_t const* reg_out, void* out, cudaStream_t st);
 void launch_status_to_tile(int tile_width, uint8_t const* src, uint8_t* dst, int64_t n_scn, int n_item, cudaStream_t st);
 void launch_nr_block(int phases, int tile_width, DevStructure const& s, DevBatch const& b, SolveOptions const& opt, int n_slot,
                      cudaStream_t st);

@@ -970,8 +970,7 @@ int64_t Model::calculate_impl(ModelOptions const& opt, UpdateData const* update,
         }
         if (!structural && !source_param_change) prepare_engines<B>(); // the eligibility test looks at the math topology
         if (!structural && !source_param_change && has_reg) check_regulators<B>(opt);
-        // grids with voltage regulators: host-staged engine call (the device update / output kernels do not carry them yet)
-        if (!structural && !source_param_change && !has_reg && device_path_eligible(*update)) {
+        if (!structural && !source_param_change && device_path_eligible(*update)) {
             timing[0] += ms_since(t0);
             int64_t const r = run_batch_device(opt, B, *update, out, n_iter, status);
             if (r >= 0) {

@@ -37,8 +37,12 @@ struct Model::DeviceSide {
     Idx n_app_first[6]{}; // first appliance index of shunt, source, sym_gen, asym_gen, sym_load, asym_load
     // per-batch buffers
     DevBuf<unsigned char> upd[4];
-    DevBuf<unsigned char> out[9];
+    DevBuf<unsigned char> out[10];
     DevBuf<double> src_res;
+    // voltage regulators: component tables and the per-scenario flags of the math regulators
+    DevBuf<int32_t> reg_id, reg_math;
+    DevBuf<uint8_t> reg_status;
+    DevBuf<int8_t> reg_flags;
     DevBuf<int32_t> flag;
     // pinned staging for pageable caller buffers
     unsigned char* pinned{nullptr};
@@ -103,7 +107,7 @@ int64_t Model::run_batch_device(ModelOptions const& opt, int phases, UpdateData 
         size_t row;
         Idx count;
     };
-    Part const outs[9] = {{&out.node, row_node, static_cast<Idx>(node_.size())},
+    Part const outs[10] = {{&out.node, row_node, static_cast<Idx>(node_.size())},
                           {&out.line, row_branch, n_line()},
                           {&out.transformer, row_branch, n_trafo()},
                           {&out.shunt, row_app, static_cast<Idx>(shunt_in_.size())},
@@ -111,7 +115,8 @@ int64_t Model::run_batch_device(ModelOptions const& opt, int phases, UpdateData 
                           {&out.sym_gen, row_app, n_sym_gen_},
                           {&out.asym_gen, row_app, n_asym_gen_},
                           {&out.sym_load, row_app, n_sym_load_},
-                          {&out.asym_load, row_app, n_asym_load_}};
+                          {&out.asym_load, row_app, n_asym_load_},
+                          {&out.voltage_regulator, sizeof(VoltageRegulatorOutput), static_cast<Idx>(reg_in_.size())}};
     ComponentBuffer const* ubufs[4] = {&update.sym_gen, &update.asym_gen, &update.sym_load, &update.asym_load};
     size_t const urow[4] = {sizeof(SymLoadGenUpdate), sizeof(AsymLoadGenUpdate), sizeof(SymLoadGenUpdate), sizeof(AsymLoadGenUpdate)};
     size_t per_scn = static_cast<size_t>(e.pattern().nnz_lu) * N * N * 8 + 6 * static_cast<size_t>(m.n_bus) * N * 8 +
@@ -151,8 +156,9 @@ int64_t Model::run_batch_device(ModelOptions const& opt, int phases, UpdateData 
             }
         }
         OutputData o = out;
-        void** ohost[9] = {&o.node, &o.line, &o.transformer, &o.shunt, &o.source, &o.sym_gen, &o.asym_gen, &o.sym_load, &o.asym_load};
-        for (int k = 0; k != 9; ++k)
+        void** ohost[10] = {&o.node, &o.line, &o.transformer, &o.shunt, &o.source, &o.sym_gen, &o.asym_gen, &o.sym_load, &o.asym_load,
+                            &o.voltage_regulator};
+        for (int k = 0; k != 10; ++k)
             if (*ohost[k] != nullptr) *ohost[k] = static_cast<unsigned char*>(*ohost[k]) + static_cast<size_t>(s0) * outs[k].count * outs[k].row;
         int64_t const r = run_batch_device_part(opt, phases, u, o, n_iter ? n_iter + s0 : nullptr, status ? status + s0 : nullptr, s0);
         if (r < 0) return -1;
@@ -316,6 +322,16 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
         d.lg_base_s.upload(lg_base, st);
         d.lg_base_status.upload(lg_st, st);
         d.lg_scale.upload(lg_scale, st);
+        std::vector<int32_t> r_id(reg_in_.size()), r_math(reg_in_.size());
+        std::vector<uint8_t> r_status(reg_in_.size());
+        for (size_t i = 0; i != reg_in_.size(); ++i) {
+            r_id[i] = reg_in_[i].id;
+            r_math[i] = topo_.voltage_regulator[i].group == 0 ? static_cast<int32_t>(topo_.voltage_regulator[i].pos) : -1;
+            r_status[i] = reg_st_[i].status ? 1 : 0;
+        }
+        d.reg_id.upload(r_id, st);
+        d.reg_math.upload(r_math, st);
+        d.reg_status.upload(r_status, st);
         PGMB_CUDA(cudaStreamSynchronize(st)); // host vectors die at the end of this scope
         d.t = DevModelTables{static_cast<int32_t>(nn), static_cast<int32_t>(nb), static_cast<int32_t>(n_app),
                              d.node_id.get(), d.node_u_rated.get(), d.node_bus.get(), d.node_app_ptr.get(), d.node_app.get(),
@@ -365,6 +381,19 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
     //      PCIe transfers of one chunk overlap the kernels of the others (both copy engines + the SMs busy at once) ----
     t0 = Clock::now();
     e.stage_device(n_scn, uref.data(), uref_shared);
+    if (e.has_regulators()) { // VoltageRegulator::calc_param of the permanent state (regulator updates take the host route)
+        std::vector<double> rp(m.n_voltage_regulator() * 4, 0.0);
+        for (size_t r = 0; r != reg_in_.size(); ++r) {
+            Coupling const c = topo_.voltage_regulator[r];
+            if (c.group != 0) continue;
+            rp[c.pos * 4] = reg_st_[r].status ? 1.0 : 0.0;
+            rp[c.pos * 4 + 1] = reg_st_[r].u_ref;
+            rp[c.pos * 4 + 2] = reg_st_[r].q_min / kBasePower3p;
+            rp[c.pos * 4 + 3] = reg_st_[r].q_max / kBasePower3p;
+        }
+        e.set_regulators(rp.data());
+        d.reg_flags.ensure(static_cast<size_t>(n_scn) * m.n_voltage_regulator() * 2 + 1);
+    }
     if (outage_plan_ != nullptr) { // branch-outage overlay of this part's scenarios (model.hpp: OutagePlan)
         OutagePlan const& plan = *outage_plan_;
         size_t const bb2 = static_cast<size_t>(phases) * phases * 2;
@@ -395,7 +424,7 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
         size_t row;
         Idx count;
     };
-    Req const reqs[9] = {
+    Req const reqs[10] = {
         {out.node, 0, sym ? sizeof(NodeOutput<1>) : sizeof(NodeOutput<3>), nn},
         {out.line, 1, sym ? sizeof(BranchOutput<1>) : sizeof(BranchOutput<3>), n_line()},
         {out.transformer, 2, sym ? sizeof(BranchOutput<1>) : sizeof(BranchOutput<3>), n_trafo()},
@@ -405,6 +434,7 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
         {out.asym_gen, 6, sym ? sizeof(ApplianceOutput<1>) : sizeof(ApplianceOutput<3>), n_asym_gen_},
         {out.sym_load, 7, sym ? sizeof(ApplianceOutput<1>) : sizeof(ApplianceOutput<3>), n_sym_load_},
         {out.asym_load, 8, sym ? sizeof(ApplianceOutput<1>) : sizeof(ApplianceOutput<3>), n_asym_load_},
+        {out.voltage_regulator, 9, sizeof(VoltageRegulatorOutput), static_cast<Idx>(reg_in_.size())},
     };
     for (Req const& r : reqs) {
         if (r.host != nullptr && r.count != 0) d.out[r.slot].ensure(static_cast<size_t>(n_scn) * r.count * r.row);
@@ -447,6 +477,8 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
         PGMB_CUDA(cudaEventRecord(d.ev_a[c], q));
         e.launch_solve(view, sopt, q);
         PGMB_CUDA(cudaEventRecord(d.ev_b[c], q));
+        int8_t* const reg_flags = e.has_regulators() ? d.reg_flags.get() + s0 * m.n_voltage_regulator() * 2 : nullptr;
+        e.launch_regulator_apply(view, reg_flags, q); // before every kernel that reads the generators' power
         double* const src_res = d.src_res.get() + s0 * m.n_source() * src_row;
         if (sym) {
             launch_source_result_sym(tw, ds, view, force_const_y, src_res, q);
@@ -457,12 +489,16 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
             if (r.host == nullptr || r.count == 0) continue;
             void* const dst = d.out[r.slot].get() + static_cast<size_t>(s0) * r.count * r.row;
             int const nl = static_cast<int>(n_line()), nt = static_cast<int>(n_trafo());
-            int const app_first = r.slot >= 3 ? static_cast<int>(d.n_app_first[r.slot - 3]) : 0;
+            int const app_first = (r.slot >= 3 && r.slot < 9) ? static_cast<int>(d.n_app_first[r.slot - 3]) : 0;
             if (sym) {
                 switch (r.slot) {
                 case 0: launch_pack_node_sym(tw, ds, view, d.t, force_const_y, src_res, dst, q); break;
                 case 1: launch_pack_branch_sym(tw, ds, view, d.t, 0, nl, dst, q); break;
                 case 2: launch_pack_branch_sym(tw, ds, view, d.t, nl, nt, dst, q); break;
+                case 9:
+                    launch_pack_regulator(ns, static_cast<int>(r.count), static_cast<int>(m.n_voltage_regulator()), d.reg_id.get(),
+                                          d.reg_math.get(), d.reg_status.get(), reg_flags, dst, q);
+                    break;
                 default: launch_pack_appliance_sym(tw, ds, view, d.t, force_const_y, app_first, static_cast<int>(r.count), src_res, dst, q);
                 }
             } else {
@@ -470,6 +506,10 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
                 case 0: launch_pack_node_asym(tw, ds, view, d.t, force_const_y, src_res, dst, q); break;
                 case 1: launch_pack_branch_asym(tw, ds, view, d.t, 0, nl, dst, q); break;
                 case 2: launch_pack_branch_asym(tw, ds, view, d.t, nl, nt, dst, q); break;
+                case 9:
+                    launch_pack_regulator(ns, static_cast<int>(r.count), static_cast<int>(m.n_voltage_regulator()), d.reg_id.get(),
+                                          d.reg_math.get(), d.reg_status.get(), reg_flags, dst, q);
+                    break;
                 default: launch_pack_appliance_asym(tw, ds, view, d.t, force_const_y, app_first, static_cast<int>(r.count), src_res, dst, q);
                 }
             }
@@ -508,8 +548,9 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
         if (st_local[s] != 0) {
             ++failed;
             batch_message += "Error in batch #" + std::to_string(first_scenario + s) + ": " +
-                             (st_local[s] == 1 ? "Iteration failed to converge after " + std::to_string(opt.max_iter) + " iterations!"
-                                               : "Sparse matrix error, possibly singular matrix!") + "\n";
+                             (st_local[s] == 1   ? "Iteration failed to converge after " + std::to_string(opt.max_iter) + " iterations!"
+                              : st_local[s] == 4 ? std::string("Unallocated Q remains after distribution on a regulated bus")
+                                                 : std::string("Sparse matrix error, possibly singular matrix!")) + "\n";
         }
     }
     return failed;
