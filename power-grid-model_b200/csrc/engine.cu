@@ -551,11 +551,12 @@ void Engine::launch_solve(DevBatch const& b, SolveOptions const& opt, cudaStream
     switch (opt.method) {
     case 1:
         // grids with voltage regulators (PV buses): the generic block kernel carries that logic for B = 1 and B = 3
-        if (!symmetric_ || has_regulators() || b.ovl.entry != nullptr || env_int("PGMB_KERNEL", 3) == 0) {
+        // (a branch-outage overlay is read by the block kernel and the symmetric level kernel)
+        if (!symmetric_ || has_regulators() || env_int("PGMB_KERNEL", 3) == 0) {
             launch_nr_block(B_, tile_width_, ds_, b, opt, n_slot_, st);
-        } else if (env_int("PGMB_KERNEL", 3) == 1) {
+        } else if (env_int("PGMB_KERNEL", 3) == 1 && b.ovl.entry == nullptr) {
             launch_nr_sym(tile_width_, ds_, b, opt, n_slot_, st);
-        } else if (path_program_.valid && env_int("PGMB_KERNEL", 3) == 3) {
+        } else if (path_program_.valid && env_int("PGMB_KERNEL", 3) == 3 && b.ovl.entry == nullptr) {
             // radial grid: the path kernel (measured against the level kernel: 1000 scenarios 1.93 vs 2.39 ms, 8000 scenarios
             // 10.5 vs 11.1 ms)
             launch_nr_sym_v3(tile_width_, ds_, b, opt, n_slot_, st);

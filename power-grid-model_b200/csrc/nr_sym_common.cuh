@@ -106,6 +106,24 @@ __device__ __forceinline__ double polar_update(double* pol, double* u, double x0
     }
 }
 
+// Branch-outage overlay of a lane's scenario (kernels.cuh: DevOverlay): replaced Y-bus entry values and the buses that lost
+// their supply.  All null for ordinary batches.
+// OVL is a compile-time switch: the ordinary instantiations carry none of this code.
+template <bool OVL, class TileT>
+__device__ __forceinline__ void load_y(DevStructure const& s, TileT const& t, int ky, double& yr, double& yi) {
+    double const* p = s.ydata + 2 * ky;
+    if (OVL && t.ovr_entry != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (t.ovr_entry[j] == ky) p = t.ovr_y + 2 * j;
+    }
+    yr = __ldg(p);
+    yi = __ldg(p + 1);
+}
+template <bool OVL, class TileT> __device__ __forceinline__ bool is_dead(TileT const& t, int bus) {
+    return OVL && t.dead != nullptr && t.dead[bus] != 0;
+}
+
 template <int T> struct Tile {
     double* jac;
     double* xvec;
@@ -114,6 +132,9 @@ template <int T> struct Tile {
     uint8_t* perm;
     double const* sinj;
     double const* usrc;
+    int32_t const* ovr_entry{nullptr}; // [4]
+    double const* ovr_y{nullptr};      // [4][2]
+    uint8_t const* dead{nullptr};      // [n_bus]
 
     __device__ __forceinline__ Blk load_blk(int k) const {
         double const* p = jac + (size_t)k * 4 * T;
@@ -129,7 +150,7 @@ template <int T> struct Tile {
 };
 
 // ---- up-sweep row task -------------------------------------------------------------------------------------------
-template <int T, Mode mode>
+template <int T, Mode mode, bool OVL = false>
 __device__ __forceinline__ bool up_row(DevStructure const& s, Tile<T> const& t, int row) {
     int const rb = __ldg(s.row_ptr + row), re = __ldg(s.row_ptr + row + 1), dg = __ldg(s.diag + row);
     double const uir = t.u[(size_t)(row * 2) * T], uii = t.u[(size_t)(row * 2 + 1) * T];
@@ -138,10 +159,12 @@ __device__ __forceinline__ bool up_row(DevStructure const& s, Tile<T> const& t, 
 
     // 1. build the row
     for (int k = rb; k < re; ++k) {
-        int const ky = __ldg(s.map_y + k);
+        int ky = __ldg(s.map_y + k);
+        if (OVL && t.dead != nullptr && ky >= 0 && (t.dead[row] != 0 || t.dead[__ldg(s.col_idx + k)] != 0)) ky = -1; // no coupling
         Blk b{0.0, 0.0, 0.0, 0.0};
         if (ky >= 0) {
-            double const yr = __ldg(s.ydata + 2 * ky), yi = __ldg(s.ydata + 2 * ky + 1);
+            double yr, yi;
+            load_y<OVL>(s, t, ky, yr, yi);
             if constexpr (mode == Mode::newton) {
                 int const j = __ldg(s.col_idx + k);
                 double ujr = uir, uji = uii;
@@ -229,6 +252,12 @@ __device__ __forceinline__ bool up_row(DevStructure const& s, Tile<T> const& t, 
             acc0 += yr * usr - yi * usi;
             acc1 += yr * usi + yi * usr;
         }
+    }
+
+    if (is_dead<OVL>(t, row)) { // bus without supply (branch-outage overlay): identity row, zero right-hand side -> u stays 0
+        d = {1.0, 0.0, 0.0, 1.0};
+        acc0 = 0.0;
+        acc1 = 0.0;
     }
 
     // 2. eliminate against finished rows; L block lives in registers only

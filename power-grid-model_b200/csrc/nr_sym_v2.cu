@@ -56,6 +56,9 @@ template <int T> struct TileR { // restrict-qualified view: the arrays never ali
     uint8_t* __restrict__ perm;
     double const* __restrict__ sinj;
     double const* __restrict__ usrc;
+    int32_t const* ovr_entry{nullptr}; // branch-outage overlay of the lane's scenario (nr_sym_common.cuh: load_y / is_dead)
+    double const* ovr_y{nullptr};
+    uint8_t const* dead{nullptr};
     __device__ __forceinline__ Blk load_blk(int k) const {
         double const* p = jac + (size_t)k * 4 * T;
         return {p[0], p[T], p[2 * T], p[3 * T]};
@@ -69,7 +72,7 @@ template <int T> struct TileR { // restrict-qualified view: the arrays never ali
     }
 };
 
-template <int T, Mode mode>
+template <int T, Mode mode, bool OVL>
 __device__ __forceinline__ bool up_tree_row(DevStructure const& s, TileR<T> const& t, int32_t const* __restrict__ rec) {
     int const row = rec[0], k_d = rec[1], ky_d = rec[2];
     int const n_lower = rec[3] & 0xfff, n_upper = (rec[3] >> 12) & 0xfff;
@@ -87,9 +90,10 @@ __device__ __forceinline__ bool up_tree_row(DevStructure const& s, TileR<T> cons
 #pragma unroll 2
         for (int e = 0; e < n_lower; ++e) {
             int const c = lower[4 * e], ky = lower[4 * e + 1];
-            if (ky >= 0) {
-                double h, n;
-                hnml(__ldg(s.ydata + 2 * ky), __ldg(s.ydata + 2 * ky + 1), uir, uii, t.u[(size_t)(c * 2) * T],
+            if (ky >= 0 && !(OVL && t.dead != nullptr && (t.dead[row] != 0 || t.dead[c] != 0))) {
+                double h, n, yr, yi;
+                load_y<OVL>(s, t, ky, yr, yi);
+                hnml(yr, yi, uir, uii, t.u[(size_t)(c * 2) * T],
                      t.u[(size_t)(c * 2 + 1) * T], h, n);
                 acc0 -= n;
                 acc1 -= h;
@@ -97,7 +101,8 @@ __device__ __forceinline__ bool up_tree_row(DevStructure const& s, TileR<T> cons
         }
     }
     {
-        double const yr = __ldg(s.ydata + 2 * ky_d), yi = __ldg(s.ydata + 2 * ky_d + 1);
+        double yr, yi;
+        load_y<OVL>(s, t, ky_d, yr, yi);
         if constexpr (mode == Mode::newton) {
             double h, n;
             hnml(yr, yi, uir, uii, uir, uii, h, n);
@@ -112,8 +117,9 @@ __device__ __forceinline__ bool up_tree_row(DevStructure const& s, TileR<T> cons
     if (n_upper != 0) {
         k_u = upper[0];
         int const j = upper[1], ky = upper[2];
-        if (ky >= 0) {
-            double const yr = __ldg(s.ydata + 2 * ky), yi = __ldg(s.ydata + 2 * ky + 1);
+        if (ky >= 0 && !(OVL && t.dead != nullptr && (t.dead[row] != 0 || t.dead[j] != 0))) {
+            double yr, yi;
+            load_y<OVL>(s, t, ky, yr, yi);
             if constexpr (mode == Mode::newton) {
                 double h, n;
                 hnml(yr, yi, uir, uii, t.u[(size_t)(j * 2) * T], t.u[(size_t)(j * 2 + 1) * T], h, n);
@@ -189,13 +195,19 @@ __device__ __forceinline__ bool up_tree_row(DevStructure const& s, TileR<T> cons
         }
     }
 
+    if (is_dead<OVL>(t, row)) { // bus without supply: identity row, zero right-hand side (its entries were skipped above)
+        d = {1.0, 0.0, 0.0, 1.0};
+        acc0 = 0.0;
+        acc1 = 0.0;
+    }
     // pass 2: eliminate against the children; the lower block is rebuilt in registers (never stored)
 #pragma unroll 2
     for (int e = 0; e < n_lower; ++e) {
         int const c = lower[4 * e], ky = lower[4 * e + 1], kd_c = lower[4 * e + 2], k_uc = lower[4 * e + 3];
         Blk a{0.0, 0.0, 0.0, 0.0};
-        if (ky >= 0) {
-            double const yr = __ldg(s.ydata + 2 * ky), yi = __ldg(s.ydata + 2 * ky + 1);
+        if (ky >= 0 && !(OVL && t.dead != nullptr && (t.dead[row] != 0 || t.dead[c] != 0))) {
+            double yr, yi;
+            load_y<OVL>(s, t, ky, yr, yi);
             if constexpr (mode == Mode::newton) {
                 double h, n;
                 hnml(yr, yi, uir, uii, t.u[(size_t)(c * 2) * T], t.u[(size_t)(c * 2 + 1) * T], h, n);
@@ -292,7 +304,7 @@ __device__ __forceinline__ double down_tree_row(TileR<T> const& t, int32_t const
     return polar_update<T, mode>(t.pol + (size_t)(row * 2) * T, t.u + (size_t)(row * 2) * T, y0, y1, th, v, our, oui);
 }
 
-template <int T, Mode mode>
+template <int T, Mode mode, bool OVL>
 __device__ __forceinline__ void sweeps_v2(DevStructure const& s, Tile<T> const& tg, TileR<T> const& t,
                                           blk::TileB<T, 1, true> const& tw, int32_t const* prog, int slot, int n_slot,
                                           bool active, bool& singular, double& dev, unsigned long long* phase) {
@@ -307,9 +319,9 @@ __device__ __forceinline__ void sweeps_v2(DevStructure const& s, Tile<T> const& 
                 int32_t const* rec = prog + task_off[i];
                 if (s.n_wide != 0 && __ldg(s.row_is_wide + rec[0])) continue; // eliminated below by the whole block
                 if (rec[3] >> 24) {
-                    singular |= up_tree_row<T, mode>(s, t, rec);
+                    singular |= up_tree_row<T, mode, OVL>(s, t, rec);
                 } else {
-                    singular |= up_row<T, mode>(s, tg, rec[0]);
+                    singular |= up_row<T, mode, OVL>(s, tg, rec[0]);
                 }
             }
         }
@@ -346,7 +358,8 @@ __device__ __forceinline__ void sweeps_v2(DevStructure const& s, Tile<T> const& 
 
 } // namespace
 
-template <int T> __global__ void nr_sym_v2_kernel(DevStructure s, DevBatch b, SolveOptions opt, int prog_in_smem) {
+// OVL: batches with a branch-outage overlay (kernels.cuh: DevOverlay); capped at 128 registers like the plain kernel uses
+template <int T, bool OVL> __global__ void __launch_bounds__(512, 1) nr_sym_v2_kernel(DevStructure s, DevBatch b, SolveOptions opt, int prog_in_smem) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ unsigned long long sh_dev[T];
     __shared__ int sh_singular[T];
@@ -372,8 +385,16 @@ template <int T> __global__ void nr_sym_v2_kernel(DevStructure s, DevBatch b, So
     tg.perm = b.perm + (size_t)tile * s.n_bus * T + lane;
     tg.sinj = b.sinj + (size_t)tile * s.n_load_gen * 2 * T + lane;
     tg.usrc = b.usrc + (size_t)tile * s.n_source * 2 * T + lane;
-    TileR<T> const t{tg.jac, tg.xvec, tg.pol, tg.u, tg.perm, tg.sinj, tg.usrc};
+    if (OVL && b.ovl.entry != nullptr && valid) { // branch-outage overlay of this lane's scenario
+        tg.ovr_entry = b.ovl.entry + scn * 4;
+        tg.ovr_y = b.ovl.y + scn * 4 * 2;
+        if (b.ovl.dead_off != nullptr && b.ovl.dead_off[scn] >= 0) tg.dead = b.ovl.dead + (size_t)b.ovl.dead_off[scn] * s.n_bus;
+    }
+    TileR<T> const t{tg.jac, tg.xvec, tg.pol, tg.u, tg.perm, tg.sinj, tg.usrc, tg.ovr_entry, tg.ovr_y, tg.dead};
     blk::TileB<T, 1, true> tw;
+    tw.ovr_entry = tg.ovr_entry;
+    tw.ovr_y = tg.ovr_y;
+    tw.dead = tg.dead;
     tw.jac = tg.jac;
     tw.xvec = tg.xvec;
     tw.pol = tg.pol;
@@ -399,7 +420,7 @@ template <int T> __global__ void nr_sym_v2_kernel(DevStructure s, DevBatch b, So
     {
         bool singular = false;
         double dev = 0.0;
-        sweeps_v2<T, Mode::linear_init>(s, tg, t, tw, prog, slot, n_slot, !done, singular, dev, phase);
+        sweeps_v2<T, Mode::linear_init, OVL>(s, tg, t, tw, prog, slot, n_slot, !done, singular, dev, phase);
         if (singular) sh_singular[lane] = 1;
         __syncthreads();
         if (!done && sh_singular[lane]) {
@@ -419,7 +440,7 @@ template <int T> __global__ void nr_sym_v2_kernel(DevStructure s, DevBatch b, So
         if (!__syncthreads_or(!done)) break;
         bool singular = false;
         double dev = 0.0;
-        sweeps_v2<T, Mode::newton>(s, tg, t, tw, prog, slot, n_slot, !done, singular, dev, phase ? phase + 4 : nullptr);
+        sweeps_v2<T, Mode::newton, OVL>(s, tg, t, tw, prog, slot, n_slot, !done, singular, dev, phase ? phase + 4 : nullptr);
         if (!done) {
             if (singular) sh_singular[lane] = 1;
             atomicMax(&sh_dev[lane], (unsigned long long)__double_as_longlong(dev));
@@ -452,8 +473,13 @@ static void launch_v2_t(DevStructure const& s, DevBatch const& b, SolveOptions c
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     bool const in_smem = prog_bytes + 1024 <= (size_t)max_optin;
     size_t const dyn = in_smem ? prog_bytes : 0;
-    cudaFuncSetAttribute(nr_sym_v2_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-    nr_sym_v2_kernel<T><<<b.n_tile, T * n_slot, dyn, st>>>(s, b, opt, in_smem ? 1 : 0);
+    if (b.ovl.entry != nullptr) {
+        cudaFuncSetAttribute(nr_sym_v2_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        nr_sym_v2_kernel<T, true><<<b.n_tile, T * n_slot, dyn, st>>>(s, b, opt, in_smem ? 1 : 0);
+    } else {
+        cudaFuncSetAttribute(nr_sym_v2_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        nr_sym_v2_kernel<T, false><<<b.n_tile, T * n_slot, dyn, st>>>(s, b, opt, in_smem ? 1 : 0);
+    }
 }
 
 void launch_nr_sym_v2(int tile_width, DevStructure const& s, DevBatch const& b, SolveOptions const& opt, int n_slot,
