@@ -1094,6 +1094,14 @@ std::vector<int64_t> const& Model::get_index(Idx group, std::string const& name)
     else if (name == "coup.load_gen") v = coupling(topo_.load_gen);
     else if (name == "coup.source") v = coupling(topo_.source);
     else if (name == "coup.voltage_regulator") v = coupling(topo_.voltage_regulator);
+    else if (name == "branch_is_bridge" || name == "bridge_cut_size") {
+        // host logic of the shared-pattern N-1 route (plan_outage_batch): per branch component (lines then transformers)
+        // whether it is a bridge of the closed-branch graph, and how many nodes its DFS subtree holds
+        BridgeInfo const info = bridge_analysis();
+        for (size_t b = 0; b != info.bridge.size(); ++b) {
+            v.push_back(name == "branch_is_bridge" ? info.bridge[b] : (info.bridge[b] ? info.size[info.child[b]] : 0));
+        }
+    }
     else {
         if (group < 0 || group >= static_cast<Idx>(topo_.math.size())) throw InvalidArgument("math group out of range");
         auto const& m = topo_.math[group];

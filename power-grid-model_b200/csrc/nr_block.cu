@@ -10,6 +10,8 @@
 // dynamically.  U blocks are stored with the row permutation / L^-1 applied but WITHOUT the later column permutation Q_j;
 // the backward substitution sums the products in the permuted order instead, so every rounding equals the reference's.
 #include "kernels.cuh"
+
+#include <stdexcept>
 #include "block_common.cuh"
 
 namespace pgmb {
@@ -166,7 +168,9 @@ void launch_nr_block(int phases, int tw, DevStructure const& s, DevBatch const& 
                      cudaStream_t st) {
     count_kernel_launch();
     bool const reg = s.lg_reg != nullptr;
-    if (reg && (b.qviol == nullptr || b.lg_status == nullptr)) return; // never: the engine allocates both with the regulators
+    if (reg && (b.qviol == nullptr || b.lg_status == nullptr)) {
+        throw std::logic_error("nr_block: a grid with voltage regulators needs the qviol / lg_status buffers of the batch");
+    }
     if (phases == 1) {
         reg ? launch_nr_block_b<1, true>(tw, s, b, opt, n_slot, st) : launch_nr_block_b<1, false>(tw, s, b, opt, n_slot, st);
     } else {

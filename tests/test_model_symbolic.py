@@ -111,3 +111,36 @@ def test_invalid_input_is_reported_not_thrown():
     with pytest.raises(pgm_b200.PgmB200Error) as e:
         pgm_b200.PowerGridModel({"node": node})
     assert "Conflicting id" in str(e.value)
+
+
+@pytest.mark.parametrize("rings", [False, True])
+def test_bridge_analysis_of_the_n1_route(rings):
+    """Host logic of the shared-pattern N-1 route: a branch is a bridge iff removing it splits its connected component, and the
+    subtree size the DFS reports for it is the size of one of the two parts (checked by brute force with scipy)."""
+    import scipy.sparse as sp
+    from scipy.sparse.csgraph import connected_components
+
+    grid = pgm_b200.FictionalGrid(seed=2, n_node_total_specified=120, n_mv_feeder=3, n_node_per_mv_feeder=4, n_lv_feeder=3,
+                                  n_connection_per_lv_feeder=6, has_mv_ring=rings, has_lv_ring=rings)
+    inp = grid.input_data
+    model = pgm_b200.PowerGridModel(inp)
+    is_bridge = model.math_index(0, "branch_is_bridge")
+    cut = model.math_index(0, "bridge_cut_size")
+    node_pos = {int(i): k for k, i in enumerate(inp["node"]["id"])}
+    ends = [(node_pos[int(b["from_node"])], node_pos[int(b["to_node"])]) for comp in ("line", "transformer") for b in inp[comp]]
+    n = len(node_pos)
+    assert len(is_bridge) == len(ends)
+
+    def components(skip):
+        rows = [f for k, (f, t) in enumerate(ends) if k != skip]
+        cols = [t for k, (f, t) in enumerate(ends) if k != skip]
+        return connected_components(sp.coo_matrix((np.ones(len(rows)), (rows, cols)), shape=(n, n)), directed=False)
+
+    n0, _ = components(-1)
+    assert n0 == 1
+    for k in range(len(ends)):
+        nc, labels = components(k)
+        assert bool(is_bridge[k]) == (nc == 2), k
+        if nc == 2:
+            assert cut[k] in (int((labels == 0).sum()), int((labels == 1).sum())), k
+    assert is_bridge.all() if not rings else (0 < is_bridge.sum() < len(ends))
