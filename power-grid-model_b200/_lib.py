@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpgm_b200.so")
+LIB_PATH = os.environ.get("PGMB_LIB", os.path.join(_HERE, "libpgm_b200.so"))  # PGMB_LIB: experiment builds
 
 PGMB_OK, PGMB_ERR_INVALID, PGMB_ERR_CUDA, PGMB_ERR_BATCH, PGMB_ERR_INTERNAL = range(5)
 METHODS = {"default_method": -128, "linear": 0, "newton_raphson": 1, "iterative_current": 3, "linear_current": 4}

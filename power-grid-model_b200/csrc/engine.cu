@@ -552,7 +552,10 @@ void Engine::launch_solve(DevBatch const& b, SolveOptions const& opt, cudaStream
     case 1:
         // grids with voltage regulators (PV buses): the generic block kernel carries that logic for B = 1 and B = 3
         // (a branch-outage overlay is read by the block kernel and the symmetric level kernel)
-        if (!symmetric_ || has_regulators() || env_int("PGMB_KERNEL", 3) == 0) {
+        if (!symmetric_ && !has_regulators() && env_int("PGMB_BLOCK6", 0) != 0) {
+            // row-split kernel: six threads per (bus row, scenario); see nr_block6.cu
+            launch_nr_block6(tile_width_, ds_, b, opt, env_int("PGMB_BLOCK6_THREADS", 512), st);
+        } else if (!symmetric_ || has_regulators() || env_int("PGMB_KERNEL", 3) == 0) {
             launch_nr_block(B_, tile_width_, ds_, b, opt, n_slot_, st);
         } else if (env_int("PGMB_KERNEL", 3) == 1 && b.ovl.entry == nullptr) {
             launch_nr_sym(tile_width_, ds_, b, opt, n_slot_, st);

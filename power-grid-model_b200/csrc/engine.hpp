@@ -241,6 +241,7 @@ void launch_pack_branch_asym(int tw, DevStructure const& s, DevBatch const& b, D
                              void* out, cudaStream_t st);
 void launch_pack_appliance_asym(int tw, DevStructure const& s, DevBatch const& b, DevModelTables const& m, int force_const_y,
                                 int first, int count, double const* src_res, void* out, cudaStream_t st);
+void launch_nr_block6(int tile_width, DevStructure const& s, DevBatch const& b, SolveOptions const& opt, int threads, cudaStream_t st);
 void launch_regulator_result(int phases, int tile_width, DevStructure const& s, DevBatch const& b, int32_t const* reg_bus,
                              int n_reg_bus, double const* out_u, double const* out_inj, double* out_lg, int8_t* out_reg,
                              cudaStream_t st);

@@ -1,0 +1,650 @@
+// Asymmetric (three-phase) Newton-Raphson with the row task of a bus SPLIT OVER SIX THREADS: thread r owns block row r of every
+// 6 x 6 block of the bus row (and element r of its right-hand side).  nr_block.cu gives one thread the whole row task -- ~5000
+// dependent FP64 operations, ~130 k cycles -- and the elimination tree of a meshed grid has 60 levels with ~20 rows each, so
+// that kernel walks a critical path of row latencies with most of the SM idle.  Here the L row, the Schur-update row and the
+// right-hand-side element are thread-local, the full-pivot search / row swaps / pivot-row broadcasts of the 6 x 6 factorisation
+// are warp shuffles, and the U blocks are finished column-wise.  Per matrix element the floating-point operations and their
+// order are exactly those of nr_block.cu (and of the reference), so the results are bit-identical.
+//   newton_raphson_pf_solver.hpp:255-303, 462-547, 764-852, 325-349 ; sparse_lu_solver.hpp:86-165, 171-200, 346-495, 769-827
+// Warp layout: lane = r * 4 + sc, r = 0..7 (rows 6, 7 idle: they mirror rows 0, 1 without storing), sc = scenario within a group
+// of four; a tile of T scenarios is T / 4 such groups; one warp = one row task for one group.  Hub rows (WideRowPlan) still run
+// the cooperative code of block_common.cuh with its one-thread-per-(slot, scenario) mapping.
+#include "kernels.cuh"
+#include "block_common.cuh"
+
+#include <type_traits>
+
+namespace pgmb {
+using namespace blk;
+namespace {
+
+#ifndef B6_THREADS
+#define B6_THREADS 512
+#endif
+constexpr int kB = 3, kN = 6, kNN = 36, kBB2 = 18;
+constexpr unsigned kFull = 0xffffffffu;
+
+template <int T> struct Tile6 {
+    double* jac;
+    double* xvec;
+    double* pol;
+    double* u;
+    uint8_t* perm;
+    double const* sinj;
+    double const* usrc;
+    int32_t const* ovr_entry;
+    double const* ovr_y;
+    uint8_t const* dead;
+    int r;    // block row of this thread (0..5; the idle lanes carry 0 / 1)
+    int sc;   // scenario within the group of four = lane & 3
+    bool real; // lane carries a real block row (not one of the two idle mirrors)
+    bool act; // this thread stores results (real row, valid and unfinished scenario)
+};
+
+__device__ __forceinline__ double shfl_row(double v, int row, int sc) { return __shfl_sync(kFull, v, row * 4 + sc); }
+__device__ __forceinline__ double sel6(double const* d, int c) {
+    double x = d[0];
+#pragma unroll
+    for (int i = 1; i < kN; ++i) x = (c == i) ? d[i] : x;
+    return x;
+}
+__device__ __forceinline__ int nib(uint32_t packed, int i) { return (packed >> (4 * i)) & 15; }
+__device__ __forceinline__ uint32_t nib_swap(uint32_t packed, int i, int j) {
+    uint32_t const a = nib(packed, i), b = nib(packed, j);
+    packed &= ~((15u << (4 * i)) | (15u << (4 * j)));
+    return packed | (b << (4 * i)) | (a << (4 * j));
+}
+constexpr uint32_t kIdentityPerm = 0x543210u;
+
+// power-flow term of hnml for one element: h = imag, n = real of (ui * conj(uj)) * conj(y)
+__device__ __forceinline__ void pf_term(double yr, double yi, double uir, double uii, double ujr, double uji, double& h, double& n) {
+    double const cr = ujr, ci = -uji;
+    double const ar = uir * cr - uii * ci;
+    double const ai = uir * ci + uii * cr;
+    double const dr = yr, di = -yi;
+    n = ar * dr - ai * di;
+    h = ar * di + ai * dr;
+}
+
+// ---- full-pivot LU of the 6 x 6 diagonal block, row r in d[6] of thread r (DenseLUFactor::factorize_block_in_place) --------
+// p / q come back nibble-packed (uniform over the threads of a scenario); returns the singular flag (uniform as well)
+__device__ bool factorize6(double* d, int r, int sc, bool real_row, uint32_t& p_out, uint32_t& q_out) {
+    int rt[kN], ct[kN];
+    double max_pivot = 0.0;
+    bool stopped = false;
+#pragma unroll
+    for (int pivot = 0; pivot < kN; ++pivot) {
+        // candidate of my row: first maximum over the columns >= pivot; NaN never wins except at (pivot, pivot), which the
+        // reference keeps as its initial best whatever follows
+        double bv = -1.0;
+        int bc = pivot, br = real_row ? r : 6 + r;
+        if (real_row && r >= pivot) {
+#pragma unroll
+            for (int c = pivot; c < kN; ++c) {
+                double const v = d[c] * d[c];
+                double const key = isnan(v) ? ((r == pivot && c == pivot) ? INFINITY : -1.0) : v;
+                if (c == pivot || key > bv) {
+                    bv = key;
+                    bc = c;
+                }
+            }
+        }
+#pragma unroll
+        for (int off = 4; off <= 16; off <<= 1) {
+            double const ov = __shfl_xor_sync(kFull, bv, off);
+            int const oc = __shfl_xor_sync(kFull, bc, off), orr = __shfl_xor_sync(kFull, br, off);
+            bool const better = ov > bv || (ov == bv && (oc < bc || (oc == bc && orr < br)));
+            if (better) {
+                bv = ov;
+                bc = oc;
+                br = orr;
+            }
+        }
+        int rb = br, cb = bc;
+        double const x = shfl_row(sel6(d, cb), rb < kN ? rb : 0, sc);
+        double const best = x * x;
+        if (stopped || best == 0.0) { // the reference stops here: the remaining transpositions are identities
+            stopped = true;
+            rb = pivot;
+            cb = pivot;
+        } else {
+            max_pivot = fmax(max_pivot, sqrt(best));
+        }
+        rt[pivot] = rb;
+        ct[pivot] = cb;
+        // row swap pivot <-> rb
+        int const partner = (r == pivot) ? rb : ((r == rb) ? pivot : r);
+#pragma unroll
+        for (int c = 0; c < kN; ++c) d[c] = shfl_row(d[c], partner, sc);
+        // column swap pivot <-> cb (inside my row)
+        {
+            double const a = d[pivot], b = sel6(d, cb);
+            d[pivot] = b;
+#pragma unroll
+            for (int c = pivot + 1; c < kN; ++c) d[c] = (c == cb) ? a : d[c];
+        }
+        if (pivot < kN - 1) {
+            double const pv = shfl_row(d[pivot], pivot, sc);
+            bool const below = !stopped && r > pivot;
+            if (below) d[pivot] /= pv;
+#pragma unroll
+            for (int c = pivot + 1; c < kN; ++c) {
+                double const prc = shfl_row(d[c], pivot, sc);
+                if (below) d[c] -= d[pivot] * prc;
+            }
+        }
+    }
+    uint32_t p = kIdentityPerm, q = kIdentityPerm;
+#pragma unroll
+    for (int pivot = kN - 1; pivot >= 0; --pivot) p = nib_swap(p, pivot, rt[pivot]);
+#pragma unroll
+    for (int pivot = 0; pivot < kN; ++pivot) q = nib_swap(q, pivot, ct[pivot]);
+    p_out = p;
+    q_out = q;
+    double const threshold = DBL_EPSILON * max_pivot;
+    double const dd = sel6(d, r);
+    int bad = (real_row && (fabs(dd) < threshold || not_normal(dd))) ? 1 : 0;
+#pragma unroll
+    for (int off = 4; off <= 16; off <<= 1) bad |= __shfl_xor_sync(kFull, bad, off);
+    return bad != 0;
+}
+
+// ---- up-sweep row task (build + eliminate + factorise + U blocks + forward substitution) ------------------------------------
+template <int T, Mode mode> __device__ bool up_row6(DevStructure const& s, Tile6<T> const& t, int row) {
+    int const r = t.r, sc = t.sc, p = r % kB;
+    bool const top = r < kB;
+    int const rb = __ldg(s.row_ptr + row), re = __ldg(s.row_ptr + row + 1), dg = __ldg(s.diag + row);
+    bool const dead_row = t.dead != nullptr && t.dead[row] != 0;
+    double uir[kB], uii[kB];
+#pragma unroll
+    for (int c = 0; c < kB; ++c) {
+        uir[c] = t.u[(size_t)(row * kN + 2 * c) * T];
+        uii[c] = t.u[(size_t)(row * kN + 2 * c + 1) * T];
+    }
+    double acc_p = 0.0, acc_q = 0.0; // NR: -P / -Q of phase p then mismatch ; linear: rhs real / imag
+    double d[kN];
+#pragma unroll
+    for (int i = 0; i < kN; ++i) d[i] = 0.0;
+
+    // 1. build my block row of every entry
+    for (int k = rb; k < re; ++k) {
+        int ky = __ldg(s.map_y + k);
+        int const j = __ldg(s.col_idx + k);
+        if (t.dead != nullptr && ky >= 0 && (dead_row || t.dead[j] != 0)) ky = -1;
+        double bl[kN];
+#pragma unroll
+        for (int i = 0; i < kN; ++i) bl[i] = 0.0;
+        if (ky >= 0) {
+            double const* ysrc = s.ydata + (size_t)ky * kBB2;
+            if (t.ovr_entry != nullptr) {
+#pragma unroll
+                for (int o = 0; o < 4; ++o)
+                    if (t.ovr_entry[o] == ky) ysrc = t.ovr_y + o * kBB2;
+            }
+            double sn = 0.0, sh = 0.0;
+#pragma unroll
+            for (int c = 0; c < kB; ++c) {
+                double const yr = __ldg(ysrc + 2 * (p * kB + c)), yi = __ldg(ysrc + 2 * (p * kB + c) + 1);
+                if constexpr (mode == Mode::newton) {
+                    double const ujr = t.u[(size_t)(j * kN + 2 * c) * T], uji = t.u[(size_t)(j * kN + 2 * c + 1) * T];
+                    double h, n;
+                    pf_term(yr, yi, uir[p], uii[p], ujr, uji, h, n);
+                    bl[c] = top ? h : -n;
+                    bl[kB + c] = top ? n : h;
+                    sn = c == 0 ? n : sn + n;
+                    sh = c == 0 ? h : sh + h;
+                } else {
+                    bl[c] = top ? yr : yi;
+                    bl[kB + c] = top ? -yi : yr;
+                }
+            }
+            if constexpr (mode == Mode::newton) {
+                acc_p -= sn;
+                acc_q -= sh;
+            }
+        }
+        if (k == dg) {
+#pragma unroll
+            for (int i = 0; i < kN; ++i) d[i] = bl[i];
+        } else if (t.act) {
+            double* bp = t.jac + (size_t)k * kNN * T;
+#pragma unroll
+            for (int c = 0; c < kN; ++c) bp[(size_t)(c * kN + r) * T] = bl[c];
+        }
+    }
+    // diagonal corrections, loads, sources (finish_diag of block_common.cuh, row r)
+    if (dead_row) {
+#pragma unroll
+        for (int c = 0; c < kN; ++c) d[c] = (c == r) ? 1.0 : 0.0;
+        acc_p = 0.0;
+        acc_q = 0.0;
+    } else {
+        double dpp = sel6(d, p), dp3 = sel6(d, kB + p); // the two entries of my row that the corrections touch: columns p, 3 + p
+        if constexpr (mode == Mode::newton) {
+            if (top) {
+                dpp += acc_q;
+                dp3 += -acc_p;
+            } else {
+                dpp += -acc_p;
+                dp3 += -acc_q;
+            }
+        }
+        for (int lg = __ldg(s.lg_ptr + row), lge = __ldg(s.lg_ptr + row + 1); lg < lge; ++lg) {
+            int const type = __ldg(s.lg_type + lg);
+            double const ps = t.sinj[(size_t)(lg * kN + 2 * p) * T], qs = t.sinj[(size_t)(lg * kN + 2 * p + 1) * T];
+            if constexpr (mode == Mode::newton) {
+                double const v = t.pol[(size_t)(row * kN + kB + p) * T];
+                if (type == 0) {
+                    acc_p += ps;
+                    acc_q += qs;
+                } else if (type == 1) {
+                    acc_p += ps * v * v;
+                    acc_q += qs * v * v;
+                    dp3 += top ? -ps * 2.0 * v * v : -qs * 2.0 * v * v;
+                } else {
+                    acc_p += ps * v;
+                    acc_q += qs * v;
+                    dp3 += top ? -ps * v : -qs * v;
+                }
+            } else {
+                double const ylr = -ps, yli = qs;
+                if (top) {
+                    dp3 += -yli;
+                    dpp += ylr;
+                } else {
+                    dp3 += ylr;
+                    dpp += yli;
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < kN; ++c) d[c] = (c == p) ? dpp : ((c == kB + p) ? dp3 : d[c]);
+        for (int sr = __ldg(s.src_ptr + row), sre = __ldg(s.src_ptr + row + 1); sr < sre; ++sr) {
+            double const* y = s.src_yref + (size_t)sr * kBB2;
+            double const u0r = t.usrc[(size_t)(sr * 2) * T], u0i = t.usrc[(size_t)(sr * 2 + 1) * T];
+            double usr[kB], usi[kB];
+            double const a2r = -0.5, a2i = -0.8660254037844386, ar = -0.5, ai = 0.8660254037844386;
+            usr[0] = u0r;
+            usi[0] = u0i;
+            usr[1] = u0r * a2r - u0i * a2i;
+            usi[1] = u0r * a2i + u0i * a2r;
+            usr[2] = u0r * ar - u0i * ai;
+            usi[2] = u0r * ai + u0i * ar;
+            if constexpr (mode == Mode::newton) {
+                double mm[kN];
+                double p_cal = 0.0, q_cal = 0.0;
+#pragma unroll
+                for (int c = 0; c < kB; ++c) {
+                    double const yr = __ldg(y + 2 * (p * kB + c)), yi = __ldg(y + 2 * (p * kB + c) + 1);
+                    double hmm, nmm, hms, nms;
+                    pf_term(1.0 * yr, 1.0 * yi, uir[p], uii[p], uir[c], uii[c], hmm, nmm);
+                    pf_term(-1.0 * yr, -1.0 * yi, uir[p], uii[p], usr[c], usi[c], hms, nms);
+                    mm[c] = top ? hmm : -nmm;
+                    mm[kB + c] = top ? nmm : hmm;
+                    p_cal = c == 0 ? nmm + nms : p_cal + (nmm + nms);
+                    q_cal = c == 0 ? hmm + hms : q_cal + (hmm + hms);
+                }
+#pragma unroll
+                for (int c = 0; c < kN; ++c) {
+                    double add = 0.0;
+                    bool hit = false;
+                    if (c == p) {
+                        add = top ? -q_cal : p_cal;
+                        hit = true;
+                    }
+                    if (c == kB + p) {
+                        add = top ? p_cal : q_cal;
+                        hit = true;
+                    }
+                    if (hit) mm[c] += add;
+                }
+                acc_p -= p_cal;
+                acc_q -= q_cal;
+#pragma unroll
+                for (int c = 0; c < kN; ++c) d[c] += mm[c];
+            } else {
+                double sr_ = 0.0, si_ = 0.0;
+#pragma unroll
+                for (int c = 0; c < kB; ++c) {
+                    double const yr = __ldg(y + 2 * (p * kB + c)), yi = __ldg(y + 2 * (p * kB + c) + 1);
+                    if (top) {
+                        d[kB + c] -= yi;
+                        d[c] += yr;
+                    } else {
+                        d[kB + c] += yr;
+                        d[c] += yi;
+                    }
+                    sr_ = c == 0 ? yr * usr[0] - yi * usi[0] : sr_ + (yr * usr[c] - yi * usi[c]);
+                    si_ = c == 0 ? yr * usi[0] + yi * usr[0] : si_ + (yr * usi[c] + yi * usr[c]);
+                }
+                acc_p += sr_;
+                acc_q += si_;
+            }
+        }
+    }
+    double a_r = top ? acc_p : acc_q; // my element of the right-hand side
+
+    // 2. eliminate against finished rows: my row of L, of every update and of the rhs are thread-local
+    for (int e = rb; e < dg; ++e) {
+        int const c = __ldg(s.col_idx + e);
+        double const* ap = t.jac + (size_t)e * kNN * T;
+        double const* pp = t.jac + (size_t)__ldg(s.diag + c) * kNN * T;
+        uint8_t const* qp = t.perm + (size_t)(c * 2 * kN + kN) * T;
+        double l[kN];
+#pragma unroll
+        for (int i = 0; i < kN; ++i) l[i] = ap[(size_t)((int)qp[(size_t)i * T] * kN + r) * T];
+#pragma unroll
+        for (int idx = 0; idx < kN; ++idx) {
+#pragma unroll
+            for (int prev = 0; prev < idx; ++prev) l[idx] -= pp[(size_t)(idx * kN + prev) * T] * l[prev];
+            l[idx] /= pp[(size_t)(idx * kN + idx) * T];
+        }
+        for (int q = __ldg(s.upd_ptr + e), qe = __ldg(s.upd_ptr + e + 1); q < qe; ++q) {
+            int const ui = __ldg(s.upd_u + q), ai = __ldg(s.upd_a + q);
+            double const* ubp = t.jac + (size_t)ui * kNN * T;
+            double* tp = t.jac + (size_t)ai * kNN * T;
+#pragma unroll
+            for (int cc = 0; cc < kN; ++cc) {
+                double sum = l[0] * ubp[(size_t)(cc * kN) * T];
+#pragma unroll
+                for (int k = 1; k < kN; ++k) sum += l[k] * ubp[(size_t)(cc * kN + k) * T];
+                if (ai == dg) {
+                    d[cc] -= sum;
+                } else if (t.act) {
+                    tp[(size_t)(cc * kN + r) * T] -= sum;
+                }
+            }
+        }
+        double sum = l[0] * t.xvec[(size_t)(c * kN) * T];
+#pragma unroll
+        for (int k = 1; k < kN; ++k) sum += l[k] * t.xvec[(size_t)(c * kN + k) * T];
+        a_r -= sum;
+    }
+
+    // 3. factorise the diagonal block across the six row threads
+    uint32_t pk, qk;
+    bool const singular = factorize6(d, r, sc, t.real, pk, qk);
+    if (t.act) {
+        double* dp = t.jac + (size_t)dg * kNN * T;
+#pragma unroll
+        for (int c = 0; c < kN; ++c) dp[(size_t)(c * kN + r) * T] = d[c];
+        t.perm[(size_t)(row * 2 * kN + r) * T] = (uint8_t)nib(pk, r);
+        t.perm[(size_t)(row * 2 * kN + kN + r) * T] = (uint8_t)nib(qk, r);
+    }
+    __syncwarp();
+    // 4. U blocks, column r of each: L_pp^-1 (P A) with the row permutation folded into the load addresses
+    uint32_t pinv = 0;
+#pragma unroll
+    for (int i = 0; i < kN; ++i) pinv |= (uint32_t)i << (4 * nib(pk, i));
+    double lo[kNN]; // unit-lower factors lo[prev * 6 + idx], prev < idx (uniform loads of the block just stored)
+    {
+        double const* dp = t.jac + (size_t)dg * kNN * T;
+#pragma unroll
+        for (int idx = 0; idx < kN; ++idx)
+#pragma unroll
+            for (int prev = 0; prev < idx; ++prev) lo[prev * kN + idx] = dp[(size_t)(prev * kN + idx) * T];
+    }
+    for (int e = dg + 1; e < re; ++e) {
+        double* ap = t.jac + (size_t)e * kNN * T;
+        double col[kN];
+#pragma unroll
+        for (int jj = 0; jj < kN; ++jj) col[jj] = ap[(size_t)(r * kN + nib(pinv, jj)) * T];
+#pragma unroll
+        for (int idx = 0; idx < kN; ++idx)
+#pragma unroll
+            for (int prev = 0; prev < idx; ++prev) col[idx] -= lo[prev * kN + idx] * col[prev];
+        if (t.act) {
+#pragma unroll
+            for (int jj = 0; jj < kN; ++jj) ap[(size_t)(r * kN + jj) * T] = col[jj];
+        }
+    }
+    // 5. forward substitution inside the block: x = L_pp^-1 (P t), every thread computes all six, stores its own
+    double av[kN], xr[kN];
+#pragma unroll
+    for (int i = 0; i < kN; ++i) av[i] = shfl_row(a_r, i, sc);
+#pragma unroll
+    for (int jj = 0; jj < kN; ++jj) xr[jj] = sel6(av, nib(pinv, jj));
+#pragma unroll
+    for (int idx = 0; idx < kN; ++idx)
+#pragma unroll
+        for (int prev = 0; prev < idx; ++prev) xr[idx] -= lo[prev * kN + idx] * xr[prev];
+    if (t.act) t.xvec[(size_t)(row * kN + r) * T] = sel6(xr, r);
+    return singular;
+}
+
+// ---- down-sweep row task ----------------------------------------------------------------------------------------------------
+template <int T, Mode mode> __device__ double down_row6(DevStructure const& s, Tile6<T> const& t, int row) {
+    int const r = t.r, sc = t.sc;
+    int const re = __ldg(s.row_ptr + row + 1), dg = __ldg(s.diag + row);
+    double y_r = t.xvec[(size_t)(row * kN + r) * T];
+    for (int e = re - 1; e > dg; --e) {
+        int const j = __ldg(s.col_idx + e);
+        uint8_t const* qp = t.perm + (size_t)(j * 2 * kN + kN) * T;
+        double const* up = t.jac + (size_t)e * kNN * T;
+        int const q0 = qp[0];
+        double sum = up[(size_t)(q0 * kN + r) * T] * t.xvec[(size_t)(j * kN + q0) * T];
+#pragma unroll
+        for (int i = 1; i < kN; ++i) {
+            int const qi = qp[(size_t)i * T];
+            sum += up[(size_t)(qi * kN + r) * T] * t.xvec[(size_t)(j * kN + qi) * T];
+        }
+        y_r -= sum;
+    }
+    double y[kN];
+#pragma unroll
+    for (int i = 0; i < kN; ++i) y[i] = shfl_row(y_r, i, sc);
+    double const* dp = t.jac + (size_t)dg * kNN * T;
+#pragma unroll
+    for (int step = 0; step < kN; ++step) {
+        int const idx = kN - 1 - step;
+#pragma unroll
+        for (int ps = 0; ps < step; ++ps) {
+            int const prev = kN - 1 - ps;
+            y[idx] -= dp[(size_t)(prev * kN + idx) * T] * y[prev];
+        }
+        y[idx] /= dp[(size_t)(idx * kN + idx) * T];
+    }
+    // x[q[i]] = y[i]
+    uint8_t const* qr = t.perm + (size_t)(row * 2 * kN + kN) * T;
+    double x[kN];
+#pragma unroll
+    for (int jj = 0; jj < kN; ++jj) x[jj] = 0.0;
+#pragma unroll
+    for (int i = 0; i < kN; ++i) {
+        int const qi = qr[(size_t)i * T];
+#pragma unroll
+        for (int jj = 0; jj < kN; ++jj) x[jj] = (qi == jj) ? y[i] : x[jj];
+    }
+    if (t.act) t.xvec[(size_t)(row * kN + r) * T] = sel6(x, r);
+    double dev = 0.0;
+    if (r < kB && t.act) { // thread p updates phase p
+        int const p = r;
+        double const xa = sel6(x, p), xb = sel6(x, kB + p);
+        double* const pth = t.pol + (size_t)(row * kN + p) * T;
+        double* const pv = t.pol + (size_t)(row * kN + kB + p) * T;
+        double* const pur = t.u + (size_t)(row * kN + 2 * p) * T;
+        double* const pui = t.u + (size_t)(row * kN + 2 * p + 1) * T;
+        if constexpr (mode == Mode::newton) {
+            double theta = *pth, v = *pv;
+            theta += xa;
+            v += v * xb;
+            double sn, cs;
+            sincos(theta, &sn, &cs);
+            double const nr = v * cs, ni = v * sn;
+            double const dr = nr - *pur, di = ni - *pui;
+            *pth = theta;
+            *pv = v;
+            *pur = nr;
+            *pui = ni;
+            dev = sqrt(dr * dr + di * di);
+        } else {
+            *pur = xa;
+            *pui = xb;
+            *pv = sqrt(xa * xa + xb * xb);
+            *pth = atan2(xb, xa);
+        }
+    }
+    return dev;
+}
+
+template <int T, Mode mode>
+__device__ void sweeps6(DevStructure const& s, Tile6<T>& t6, TileB<T, kB> const& tw, int slot6, int n_slot6, int slot_o, int n_slot_o,
+                        bool active_o, bool& singular6, bool& singular_o, double& dev, unsigned long long* phase) {
+    long long t0 = clock64();
+    auto lap = [&](int k) { // PGMB_DEBUG_PHASES: up level 0 | up wide rows | up other levels | down levels >= 1 | down level 0
+        if (phase != nullptr && threadIdx.x == 0) {
+            long long const t1 = clock64();
+            phase[k] += (unsigned long long)(t1 - t0);
+            t0 = t1;
+        }
+    };
+    bool const warp_active = __any_sync(kFull, t6.act); // a warp whose four scenarios are all finished skips its row tasks
+    for (int lv = 0; lv < s.n_level; ++lv) {
+        int const b = __ldg(s.level_ptr + lv), e = __ldg(s.level_ptr + lv + 1);
+        if (warp_active)
+            for (int i = b + slot6; i < e; i += n_slot6) {
+                int const row = __ldg(s.level_rows + i);
+                if (s.n_wide != 0 && __ldg(s.row_is_wide + row)) continue;
+                singular6 |= up_row6<T, mode>(s, t6, row);
+            }
+        __syncthreads();
+        lap(lv == 0 ? 0 : 2);
+        if (s.n_wide != 0)
+            for (int w = __ldg(s.wide_level_ptr + lv); w < __ldg(s.wide_level_ptr + lv + 1); ++w)
+                wide_up_row<T, kB, mode, false, false>(s, tw, w, slot_o, n_slot_o, active_o, singular_o);
+        lap(1);
+    }
+    for (int lv = s.n_level - 1; lv >= 0; --lv) {
+        int const b = __ldg(s.level_ptr + lv), e = __ldg(s.level_ptr + lv + 1);
+        if (warp_active)
+            for (int i = b + slot6; i < e; i += n_slot6) dev = fmax(dev, down_row6<T, mode>(s, t6, __ldg(s.level_rows + i)));
+        __syncthreads();
+        lap(lv == 0 ? 4 : 3);
+    }
+}
+
+template <int T> __global__ void __launch_bounds__(B6_THREADS, 1) nr_block6_kernel(DevStructure s, DevBatch b, SolveOptions opt) {
+    constexpr int TS = T / 4; // groups of four scenarios per tile
+    __shared__ unsigned long long sh_dev[T];
+    __shared__ int sh_singular[T], sh_done[T], sh_status[T], sh_iter[T];
+    __shared__ double sh_max_dev[T];
+    int const tile = blockIdx.x;
+    int const warp = threadIdx.x / 32, wl = threadIdx.x % 32;
+    int const n_warp = blockDim.x / 32;
+    // row-split mapping
+    int const st = warp % TS, slot6 = warp / TS, n_slot6 = n_warp / TS;
+    int const r8 = wl >> 2, sc = wl & 3;
+    int const ln6 = st * 4 + sc; // my scenario lane within the tile
+    // one-thread-per-(slot, scenario) mapping of the cooperative wide rows
+    int const lane_o = threadIdx.x % T, slot_o = threadIdx.x / T, n_slot_o = blockDim.x / T;
+    auto tile_ptrs = [&](int lane, auto& t) {
+        t.jac = b.jac + (size_t)tile * s.nnz_lu * kNN * T + lane;
+        t.xvec = b.xvec + (size_t)tile * s.n_bus * kN * T + lane;
+        t.pol = b.pol + (size_t)tile * s.n_bus * kN * T + lane;
+        t.u = b.u + (size_t)tile * s.n_bus * kN * T + lane;
+        t.perm = b.perm + (size_t)tile * s.n_bus * 2 * kN * T + lane;
+        t.sinj = b.sinj + (size_t)tile * s.n_load_gen * kN * T + lane;
+        t.usrc = b.usrc + (size_t)tile * s.n_source * 2 * T + lane;
+        int64_t const scn = (int64_t)tile * T + lane;
+        bool const valid = scn < b.n_scn;
+        t.ovr_entry = (b.ovl.entry != nullptr && valid) ? b.ovl.entry + scn * 4 : nullptr;
+        t.ovr_y = (b.ovl.entry != nullptr && valid) ? b.ovl.y + scn * 4 * kBB2 : nullptr;
+        t.dead = (b.ovl.dead_off != nullptr && valid && b.ovl.dead_off[scn] >= 0) ? b.ovl.dead + (size_t)b.ovl.dead_off[scn] * s.n_bus
+                                                                                   : nullptr;
+    };
+    Tile6<T> t6;
+    tile_ptrs(ln6, t6);
+    t6.r = r8 < kN ? r8 : r8 - kN;
+    t6.sc = sc;
+    t6.real = r8 < kN;
+    TileB<T, kB> tw;
+    tile_ptrs(lane_o, tw);
+    tw.wide_terms = b.wide_terms ? b.wide_terms + (size_t)tile * s.wide_max_upd * kNN * T + lane_o : nullptr;
+    tw.wide_rhs = b.wide_rhs ? b.wide_rhs + (size_t)tile * s.wide_max_lower * kN * T + lane_o : nullptr;
+    tw.wide_sum = b.wide_sum ? b.wide_sum + (size_t)tile * s.wide_max_entries * kN * T + lane_o : nullptr;
+    tw.lg_status = nullptr;
+    tw.qviol = nullptr;
+    if (threadIdx.x < T) {
+        int64_t const scn = (int64_t)tile * T + threadIdx.x;
+        sh_dev[threadIdx.x] = 0ull;
+        sh_singular[threadIdx.x] = 0;
+        sh_done[threadIdx.x] = scn < b.n_scn ? 0 : 1;
+        sh_status[threadIdx.x] = kStatusOk;
+        sh_iter[threadIdx.x] = 0;
+        sh_max_dev[threadIdx.x] = INFINITY;
+    }
+    __syncthreads();
+    auto run = [&](auto mode_tag) {
+        constexpr Mode mode = decltype(mode_tag)::value;
+        bool const done6 = sh_done[ln6] != 0;
+        bool const active_o = sh_done[lane_o] == 0;
+        t6.act = !done6 && r8 < kN;
+        bool singular6 = false, singular_o = false;
+        double dev = 0.0;
+        unsigned long long* const phase = b.phase_cycles ? b.phase_cycles + tile * 16 + (mode == Mode::newton ? 8 : 0) : nullptr;
+        sweeps6<T, mode>(s, t6, tw, slot6, n_slot6, slot_o, n_slot_o, active_o, singular6, singular_o, dev, phase);
+        if (!done6 && singular6) sh_singular[ln6] = 1;
+        if (active_o && singular_o) sh_singular[lane_o] = 1;
+        if (t6.act && mode == Mode::newton) atomicMax(&sh_dev[ln6], (unsigned long long)__double_as_longlong(dev));
+        __syncthreads();
+    };
+    using LinTag = std::integral_constant<Mode, Mode::linear_init>;
+    using NrTag = std::integral_constant<Mode, Mode::newton>;
+    run(LinTag{});
+    if (threadIdx.x < T && !sh_done[threadIdx.x] && sh_singular[threadIdx.x]) {
+        sh_status[threadIdx.x] = kStatusSingular;
+        sh_done[threadIdx.x] = 1;
+    }
+    __syncthreads();
+    while (true) {
+        if (threadIdx.x < T && !sh_done[threadIdx.x]) {
+            if (sh_iter[threadIdx.x] == opt.max_iter) {
+                sh_status[threadIdx.x] = kStatusDiverged;
+                sh_done[threadIdx.x] = 1;
+            } else {
+                ++sh_iter[threadIdx.x];
+            }
+        }
+        __syncthreads();
+        bool any = false;
+#pragma unroll
+        for (int i = 0; i < T; ++i) any |= sh_done[i] == 0;
+        if (!any) break;
+        run(NrTag{});
+        if (threadIdx.x < T && !sh_done[threadIdx.x]) {
+            if (sh_singular[threadIdx.x]) {
+                sh_status[threadIdx.x] = kStatusSingular;
+                sh_done[threadIdx.x] = 1;
+            } else {
+                double const md = __longlong_as_double((long long)sh_dev[threadIdx.x]);
+                sh_max_dev[threadIdx.x] = md;
+                if (!(md > opt.err_tol)) sh_done[threadIdx.x] = 1;
+            }
+        }
+        if (threadIdx.x < T) sh_dev[threadIdx.x] = 0ull;
+        __syncthreads();
+    }
+    if (threadIdx.x < T) {
+        int64_t const scn = (int64_t)tile * T + threadIdx.x;
+        if (scn < b.n_scn) {
+            b.status[scn] = sh_status[threadIdx.x];
+            b.n_iter[scn] = sh_iter[threadIdx.x];
+            b.max_dev[scn] = sh_max_dev[threadIdx.x];
+        }
+    }
+}
+
+} // namespace
+
+// threads: a multiple of 32 * (T / 4); every warp runs one row task for four scenarios
+void launch_nr_block6(int tw, DevStructure const& s, DevBatch const& b, SolveOptions const& opt, int threads, cudaStream_t st) {
+    count_kernel_launch();
+    switch (tw) {
+    case 4: nr_block6_kernel<4><<<b.n_tile, threads, 0, st>>>(s, b, opt); break;
+    case 8: nr_block6_kernel<8><<<b.n_tile, threads, 0, st>>>(s, b, opt); break;
+    case 16: nr_block6_kernel<16><<<b.n_tile, threads, 0, st>>>(s, b, opt); break;
+    default: nr_block6_kernel<32><<<b.n_tile, threads, 0, st>>>(s, b, opt); break;
+    }
+}
+
+} // namespace pgmb

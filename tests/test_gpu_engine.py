@@ -91,6 +91,25 @@ def test_generic_block_kernel_equals_symmetric_kernel(monkeypatch):
     assert np.array_equal(a["n_iter"], b["n_iter"]) and np.array_equal(a["u"], b["u"])
 
 
+@pytest.mark.parametrize("rings", [True, False])
+def test_row_split_block_kernel_equals_block_kernel(monkeypatch, rings):
+    """the opt-in asymmetric kernel with the row task split over six threads (nr_block6.cu, PGMB_BLOCK6=1: block row per thread,
+    6 x 6 full-pivot factorisation by warp shuffles, hub rows on the cooperative code) must reproduce the one-thread-per-row
+    kernel bit for bit -- every output value of every component, and the iteration counts"""
+    grid = pgm_b200.FictionalGrid(seed=0, n_node_total_specified=300, n_connection_per_lv_feeder=5, n_lv_feeder=4, n_node_per_mv_feeder=5,
+                                  n_mv_feeder=3, has_mv_ring=rings, has_lv_ring=rings)
+    update = grid.batch_update(21, seed=3)
+    model = pgm_b200.PowerGridModel(grid.input_data)
+    a = model.calculate_power_flow(symmetric=False, update_data=update)
+    it_a = model.n_iter.copy()
+    monkeypatch.setenv("PGMB_BLOCK6", "1")
+    b = model.calculate_power_flow(symmetric=False, update_data=update)
+    assert np.array_equal(it_a, model.n_iter) and (model.status == 0).all()
+    for comp in a:
+        for name in a[comp].dtype.names:
+            assert np.array_equal(a[comp][name], b[comp][name], equal_nan=True), (comp, name)
+
+
 @pytest.mark.parametrize("n_node,seed,n_scn", [(60, 11, 9), (400, 12, 33), (1500, 13, 40)])
 def test_path_kernel_equals_level_kernel_on_radial_grids(monkeypatch, n_node, seed, n_scn):
     """radial grids run the path kernel (nr_sym_v3.cu); it must reproduce the level-scheduled kernel bit for bit"""
