@@ -173,12 +173,17 @@ typedef struct pgmb_component_buffer {
 typedef struct pgmb_input_data {
     pgmb_component_buffer node, line, transformer, shunt, source, sym_gen, asym_gen, sym_load, asym_load;
     pgmb_component_buffer voltage_regulator; /* VoltageRegulatorInput (auxiliary/input.hpp:492-498) */
+    /* further branch components; in the branch sequence of the model they sit between `line` and `transformer` like in the
+     * reference's component list (all_components.hpp:36-39): line, asym_line, generic_branch, transformer */
+    pgmb_component_buffer asym_line;      /* AsymLineInput (auxiliary/input.hpp:99-142) */
+    pgmb_component_buffer generic_branch; /* GenericBranchInput (auxiliary/input.hpp:144-165); symmetric calculations only */
 } pgmb_input_data;
 
 typedef struct pgmb_update_data {
     int64_t n_scenarios;
     pgmb_component_buffer line, transformer, shunt, source, sym_gen, asym_gen, sym_load, asym_load;
     pgmb_component_buffer voltage_regulator; /* VoltageRegulatorUpdate (auxiliary/update.hpp:213-219) */
+    pgmb_component_buffer asym_line, generic_branch; /* BranchUpdate */
 } pgmb_update_data;
 
 /* caller-owned output buffers [n_scenarios][n_component]; NULL = component not requested
@@ -186,6 +191,7 @@ typedef struct pgmb_update_data {
 typedef struct pgmb_output_data {
     void *node, *line, *transformer, *shunt, *source, *sym_gen, *asym_gen, *sym_load, *asym_load;
     void* voltage_regulator; /* VoltageRegulatorOutput (auxiliary/output.hpp:239-243) */
+    void *asym_line, *generic_branch; /* BranchOutput */
 } pgmb_output_data;
 
 /* PGM_Options (power_grid_model_c/src/options.hpp:16-27), PF subset */

@@ -29,6 +29,19 @@ struct LineInput {
     IntS from_status, to_status;
     double r1, x1, c1, tan1, r0, x0, c0, tan0, i_n;
 };
+struct AsymLineInput { // auxiliary/input.hpp:99-142
+    ID id, from_node, to_node;
+    IntS from_status, to_status;
+    double r_aa, r_ba, r_bb, r_ca, r_cb, r_cc, r_na, r_nb, r_nc, r_nn;
+    double x_aa, x_ba, x_bb, x_ca, x_cb, x_cc, x_na, x_nb, x_nc, x_nn;
+    double c_aa, c_ba, c_bb, c_ca, c_cb, c_cc, c0, c1, i_n;
+};
+struct GenericBranchInput { // auxiliary/input.hpp:144-165
+    ID id, from_node, to_node;
+    IntS from_status, to_status;
+    double r1, x1, g1, b1, k, theta, sn;
+};
+static_assert(sizeof(AsymLineInput) == 248 && sizeof(GenericBranchInput) == 72);
 struct TransformerInput {
     ID id, from_node, to_node;
     IntS from_status, to_status;
@@ -214,6 +227,152 @@ struct Line : BranchBase {
             return calc_param_y_sym(y1_series, y1_shunt, 1.0);
         } else {
             return calc_param_y_asym(y1_series, y1_shunt, y0_series, y0_shunt, 1.0);
+        }
+    }
+};
+
+// component/generic_branch.hpp:37-93: pi model behind a complex ratio k e^{j theta}; no asymmetric parameters
+struct GenericBranch : BranchBase {
+    double sn{}, theta{};
+    cplx y1_series, y1_shunt, ratio;
+    GenericBranch(GenericBranchInput const& in, double u1, double u2) {
+        id = in.id;
+        from_node = in.from_node;
+        to_node = in.to_node;
+        from_status = in.from_status != 0;
+        to_status = in.to_status != 0;
+        sn = in.sn;
+        double const k = is_nan(in.k) ? 1.0 : in.k;
+        theta = is_nan(in.theta) ? 0.0 : std::fmod(in.theta, 2 * pi);
+        base_i_from = base_power_3p / u1 / sqrt3;
+        base_i_to = base_power_3p / u2 / sqrt3;
+        double const base_y = base_i_to / (u2 / sqrt3);
+        cplx const j{0.0, 1.0};
+        y1_series = 1.0 / (in.r1 + j * in.x1) / base_y;
+        y1_shunt = (in.g1 + j * in.b1) / base_y;
+        ratio = k * std::exp(j * theta);
+    }
+    double phase_shift() const { return theta; }
+    double loading_sn() const { return is_nan(sn) ? std::numeric_limits<double>::infinity() : sn; } // NaN sn: loading 0
+    template <int B> BranchCalcParam<B> calc_param() const {
+        if constexpr (B == 1) {
+            if (!(from_status || to_status)) return BranchCalcParam<1>{};
+            return calc_param_y_sym(y1_series, y1_shunt, ratio);
+        } else {
+            throw PgmError{"Function not yet implemented: generic_branch in an asymmetric calculation"};
+        }
+    }
+};
+
+// component/asym_line.hpp:26-127 (+ component/line_utils.hpp kron_reduction, common/matrix_utils.hpp averages)
+struct AsymLine : BranchBase {
+    double i_n{};
+    CMat<3> y_series, y_shunt;
+    static CMat<3> sym3(cplx s1, cplx s2, cplx s3, cplx m12, cplx m13, cplx m23) {
+        CMat<3> r;
+        r.m[0][0] = s1, r.m[1][1] = s2, r.m[2][2] = s3;
+        r.m[0][1] = r.m[1][0] = m12;
+        r.m[0][2] = r.m[2][0] = m13;
+        r.m[1][2] = r.m[2][1] = m23;
+        return r;
+    }
+    // fixed-size 3 x 3 inverse by cofactors: inv(i, j) = cofactor(j, i) / det, det expanded along the first column
+    static CMat<3> inv3(CMat<3> const& a) {
+        auto cof = [&a](int i, int j) {
+            int const i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+            return a.m[i1][j1] * a.m[i2][j2] - a.m[i1][j2] * a.m[i2][j1];
+        };
+        cplx const c0 = cof(0, 0), c1 = cof(1, 0), c2 = cof(2, 0);
+        cplx const det = c0 * a.m[0][0] + c1 * a.m[1][0] + c2 * a.m[2][0];
+        cplx const invdet = 1.0 / det;
+        CMat<3> r;
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) r.m[i][j] = cof(j, i) * invdet;
+        return r;
+    }
+    AsymLine(AsymLineInput const& in, double system_frequency, double u1, double u2) {
+        id = in.id;
+        from_node = in.from_node;
+        to_node = in.to_node;
+        from_status = in.from_status != 0;
+        to_status = in.to_status != 0;
+        i_n = in.i_n;
+        double const base_i = base_power_3p / u1 / sqrt3;
+        base_i_from = base_i_to = base_i;
+        if (cabs(u1 - u2) > numerical_tolerance) throw PgmError{"Conflicting voltage for line " + std::to_string(id)};
+        cplx const j{0.0, 1.0};
+        CMat<3> z;
+        if (is_nan(in.r_na) && is_nan(in.x_na)) {
+            CMat<3> const r = sym3(in.r_aa, in.r_bb, in.r_cc, in.r_ba, in.r_ca, in.r_cb);
+            CMat<3> const x = sym3(in.x_aa, in.x_bb, in.x_cc, in.x_ba, in.x_ca, in.x_cb);
+            for (int a = 0; a < 3; ++a)
+                for (int b = 0; b < 3; ++b) z.m[a][b] = r.m[a][b] + j * x.m[a][b];
+        } else {
+            auto zz = [&j](double r, double x) { return cplx{r} + j * cplx{x}; };
+            CMat<3> const z_pp = sym3(zz(in.r_aa, in.x_aa), zz(in.r_bb, in.x_bb), zz(in.r_cc, in.x_cc), zz(in.r_ba, in.x_ba),
+                                      zz(in.r_ca, in.x_ca), zz(in.r_cb, in.x_cb));
+            cplx const z_pn[3] = {zz(in.r_na, in.x_na), zz(in.r_nb, in.x_nb), zz(in.r_nc, in.x_nc)};
+            cplx const z_nn_inv = 1.0 / zz(in.r_nn, in.x_nn);
+            for (int a = 0; a < 3; ++a)
+                for (int b = 0; b < 3; ++b) z.m[a][b] = z_pp.m[a][b] - (z_pn[a] * z_pn[b]) * z_nn_inv;
+        }
+        CMat<3> cm;
+        if (!is_nan(in.c0) && !is_nan(in.c1)) {
+            cplx const sdiag = (2.0 * in.c1 + in.c0) / 3.0, moff = (in.c0 - in.c1) / 3.0;
+            cm = sym3(sdiag, sdiag, sdiag, moff, moff, moff);
+        } else {
+            cm = sym3(in.c_aa, in.c_bb, in.c_cc, in.c_ba, in.c_ca, in.c_cb);
+        }
+        double const base_y = base_i / (u1 / sqrt3);
+        double const inv_base_y = 1 / base_y;
+        CMat<3> const zi = inv3(z);
+        cplx const w = 2.0 * j * pi * system_frequency;
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) {
+                y_series.m[a][b] = inv_base_y * zi.m[a][b];
+                y_shunt.m[a][b] = inv_base_y * (w * cm.m[a][b]);
+            }
+    }
+    double phase_shift() const { return 0.0; }
+    template <int B> BranchCalcParam<B> calc_param() const {
+        if constexpr (B == 1) {
+            if (!(from_status || to_status)) return BranchCalcParam<1>{};
+            auto avg_diag = [](CMat<3> const& a) { return (a.m[0][0] + a.m[1][1] + a.m[2][2]) / 3.0; };
+            // matrix_utils.hpp:16-18 as written: (1,2) counted twice, (0,2) not at all
+            auto avg_off = [](CMat<3> const& a) { return (a.m[0][1] + a.m[1][2] + a.m[1][0] + a.m[1][2] + a.m[2][0] + a.m[2][1]) / 6.0; };
+            return calc_param_y_sym(avg_diag(y_series) - avg_off(y_series), avg_diag(y_shunt) - avg_off(y_shunt), 1.0);
+        } else {
+            BranchCalcParam<3> param{};
+            auto scaled = [](CMat<3> const& a, double f) {
+                CMat<3> r;
+                for (int i = 0; i < 3; ++i)
+                    for (int k = 0; k < 3; ++k) r.m[i][k] = f * a.m[i][k];
+                return r;
+            };
+            auto added = [](CMat<3> const& a, CMat<3> const& b) {
+                CMat<3> r;
+                for (int i = 0; i < 3; ++i)
+                    for (int k = 0; k < 3; ++k) r.m[i][k] = a.m[i][k] + b.m[i][k];
+                return r;
+            };
+            if (!branch_status()) {
+                if (from_status || to_status) {
+                    CMat<3> branch_shunt{};
+                    bool all_above = true;
+                    for (int i = 0; i < 3; ++i)
+                        for (int k = 0; k < 3; ++k) all_above = all_above && cabs(y_shunt.m[i][k]) >= numerical_tolerance;
+                    if (all_above) branch_shunt = added(scaled(y_shunt, 0.5), inv3(added(inv3(y_series), scaled(inv3(y_shunt), 2.0))));
+                    if (from_status) param.value[0] = branch_shunt;
+                    if (to_status) param.value[3] = branch_shunt;
+                }
+            } else {
+                param.value[3] = added(y_series, scaled(y_shunt, 0.5));
+                param.value[0] = param.value[3];
+                for (int i = 0; i < 3; ++i)
+                    for (int k = 0; k < 3; ++k) param.value[1].m[i][k] = -y_series.m[i][k];
+                param.value[2] = param.value[1];
+            }
+            return param;
         }
     }
 };

@@ -43,6 +43,10 @@ struct ModelInput {
     AsymLoadGenInput const* asym_load;
     Idx n_voltage_regulator;
     VoltageRegulatorInput const* voltage_regulator;
+    Idx n_asym_line;
+    AsymLineInput const* asym_line;
+    Idx n_generic_branch;
+    GenericBranchInput const* generic_branch;
 };
 
 // one buffer of a batch update dataset: uniform (indptr == nullptr, n_per_scenario elements each) or sparse
@@ -67,6 +71,8 @@ struct BatchUpdate {
     UpdateBuffer<SymLoadGenUpdate> sym_load;
     UpdateBuffer<AsymLoadGenUpdate> asym_load;
     UpdateBuffer<VoltageRegulatorUpdate> voltage_regulator;
+    UpdateBuffer<BranchUpdate> asym_line;
+    UpdateBuffer<BranchUpdate> generic_branch;
 };
 // output buffers, each [n_scenarios][n_component] or nullptr when the caller does not want that component
 template <int B> struct BatchOutput {
@@ -80,6 +86,8 @@ template <int B> struct BatchOutput {
     ApplianceOutput<B>* sym_load;
     ApplianceOutput<B>* asym_load;
     VoltageRegulatorOutput* voltage_regulator;
+    BranchOutput<B>* asym_line;
+    BranchOutput<B>* generic_branch;
 };
 
 struct CalcOptions {
@@ -106,6 +114,16 @@ class Model {
         for (Idx i = 0; i != in.n_line; ++i) {
             add_id(in.line[i].id);
             lines_.emplace_back(in.line[i], system_frequency_, u_rated(in.line[i].from_node), u_rated(in.line[i].to_node));
+        }
+        for (Idx i = 0; i != in.n_asym_line; ++i) {
+            add_id(in.asym_line[i].id);
+            asym_lines_.emplace_back(in.asym_line[i], system_frequency_, u_rated(in.asym_line[i].from_node),
+                                     u_rated(in.asym_line[i].to_node));
+        }
+        for (Idx i = 0; i != in.n_generic_branch; ++i) {
+            add_id(in.generic_branch[i].id);
+            generic_branches_.emplace_back(in.generic_branch[i], u_rated(in.generic_branch[i].from_node),
+                                           u_rated(in.generic_branch[i].to_node));
         }
         for (Idx i = 0; i != in.n_transformer; ++i) {
             add_id(in.transformer[i].id);
@@ -145,6 +163,8 @@ class Model {
         // id -> sequence index within each updatable type
         for (size_t i = 0; i != lines_.size(); ++i) line_idx_[lines_[i].id] = static_cast<Idx>(i);
         for (size_t i = 0; i != transformers_.size(); ++i) transformer_idx_[transformers_[i].id] = static_cast<Idx>(i);
+        for (size_t i = 0; i != asym_lines_.size(); ++i) asym_line_idx_[asym_lines_[i].id] = static_cast<Idx>(i);
+        for (size_t i = 0; i != generic_branches_.size(); ++i) generic_branch_idx_[generic_branches_[i].id] = static_cast<Idx>(i);
         for (size_t i = 0; i != shunts_.size(); ++i) shunt_idx_[shunts_[i].id] = static_cast<Idx>(i);
         for (size_t i = 0; i != sources_.size(); ++i) source_idx_[sources_[i].id] = static_cast<Idx>(i);
         for (size_t i = 0; i != load_gens_.size(); ++i) load_gen_idx_[load_gens_[i].id] = static_cast<Idx>(i);
@@ -166,7 +186,9 @@ class Model {
     }
 
     Idx n_node() const { return static_cast<Idx>(nodes_.size()); }
-    Idx n_branch() const { return static_cast<Idx>(lines_.size() + transformers_.size()); }
+    Idx n_branch() const {
+        return static_cast<Idx>(lines_.size() + asym_lines_.size() + generic_branches_.size() + transformers_.size());
+    }
 
     // ---- single calculation ----
     // calculation_preparation.hpp:163-225 check_state_validity + main_model_impl.hpp:362-366, 400-420
@@ -293,7 +315,10 @@ class Model {
     double system_frequency_;
     std::vector<NodeInput> nodes_;
     std::vector<Line> lines_;
+    std::vector<AsymLine> asym_lines_;
+    std::vector<GenericBranch> generic_branches_;
     std::vector<Transformer> transformers_;
+    std::unordered_map<ID, Idx> asym_line_idx_, generic_branch_idx_;
     std::vector<Shunt> shunts_;
     std::vector<Source> sources_;
     std::vector<LoadGen> load_gens_; // sym_gen, asym_gen, sym_load, asym_load
@@ -332,7 +357,13 @@ class Model {
         }
     }
     Idx branch_seq_line(Idx i) const { return i; }
-    Idx branch_seq_transformer(Idx i) const { return static_cast<Idx>(lines_.size()) + i; }
+    // branch sequence = component order of the reference (all_components.hpp:36-39): line, asym_line, (link), generic_branch,
+    // transformer
+    Idx branch_seq_asym_line(Idx i) const { return static_cast<Idx>(lines_.size()) + i; }
+    Idx branch_seq_generic_branch(Idx i) const { return static_cast<Idx>(lines_.size() + asym_lines_.size()) + i; }
+    Idx branch_seq_transformer(Idx i) const {
+        return static_cast<Idx>(lines_.size() + asym_lines_.size() + generic_branches_.size()) + i;
+    }
 
     void prepare_topology() {
         if (topo_valid_) return;
@@ -345,6 +376,8 @@ class Model {
             conn.branch_phase_shift.push_back(shift);
         };
         for (auto const& l : lines_) add_branch(l, l.phase_shift());
+        for (auto const& l : asym_lines_) add_branch(l, l.phase_shift());
+        for (auto const& g : generic_branches_) add_branch(g, g.phase_shift());
         for (auto const& t : transformers_) add_branch(t, t.phase_shift());
         for (auto const& s : shunts_) comp_topo_.shunt_node_idx.push_back(node_idx_.at(s.node));
         for (auto const& s : sources_) {
@@ -379,6 +412,14 @@ class Model {
         for (size_t i = 0; i != lines_.size(); ++i) {
             Idx2D const m = coup_.branch[branch_seq_line(static_cast<Idx>(i))];
             if (m.group != -1) param[m.group].branch_param[m.pos] = lines_[i].calc_param<B>();
+        }
+        for (size_t i = 0; i != asym_lines_.size(); ++i) {
+            Idx2D const m = coup_.branch[branch_seq_asym_line(static_cast<Idx>(i))];
+            if (m.group != -1) param[m.group].branch_param[m.pos] = asym_lines_[i].calc_param<B>();
+        }
+        for (size_t i = 0; i != generic_branches_.size(); ++i) {
+            Idx2D const m = coup_.branch[branch_seq_generic_branch(static_cast<Idx>(i))];
+            if (m.group != -1) param[m.group].branch_param[m.pos] = generic_branches_[i].calc_param<B>();
         }
         for (size_t i = 0; i != transformers_.size(); ++i) {
             Idx2D const m = coup_.branch[branch_seq_transformer(static_cast<Idx>(i))];
@@ -540,6 +581,24 @@ class Model {
                                                  : branch_output<B>(lines_[i], so[m.group].branch[m.pos], -1.0, lines_[i].i_n);
             }
         }
+        if (out.asym_line != nullptr) {
+            Idx const n = static_cast<Idx>(asym_lines_.size());
+            for (Idx i = 0; i != n; ++i) {
+                Idx2D const m = coup_.branch[branch_seq_asym_line(i)];
+                out.asym_line[scenario * n + i] =
+                    m.group == -1 ? null_branch(asym_lines_[i])
+                                  : branch_output<B>(asym_lines_[i], so[m.group].branch[m.pos], -1.0, asym_lines_[i].i_n);
+            }
+        }
+        if (out.generic_branch != nullptr) {
+            Idx const n = static_cast<Idx>(generic_branches_.size());
+            for (Idx i = 0; i != n; ++i) {
+                Idx2D const m = coup_.branch[branch_seq_generic_branch(i)];
+                out.generic_branch[scenario * n + i] =
+                    m.group == -1 ? null_branch(generic_branches_[i])
+                                  : branch_output<B>(generic_branches_[i], so[m.group].branch[m.pos], generic_branches_[i].loading_sn(), 0.0);
+            }
+        }
         if (out.transformer != nullptr) {
             Idx const n = static_cast<Idx>(transformers_.size());
             for (Idx i = 0; i != n; ++i) {
@@ -592,6 +651,8 @@ class Model {
     struct Saved {
         std::vector<std::pair<Idx, Line>> lines;
         std::vector<std::pair<Idx, Transformer>> transformers;
+        std::vector<std::pair<Idx, AsymLine>> asym_lines;
+        std::vector<std::pair<Idx, GenericBranch>> generic_branches;
         std::vector<std::pair<Idx, Shunt>> shunts;
         std::vector<std::pair<Idx, Source>> sources;
         std::vector<std::pair<Idx, LoadGen>> load_gens;
@@ -625,6 +686,24 @@ class Model {
                 Idx const i = find_seq(*p, p - b, e - b, static_cast<Idx>(lines_.size()), line_idx_, 0);
                 saved.lines.emplace_back(i, lines_[i]);
                 bool const changed = lines_[i].set_status(p->from_status, p->to_status);
+                mark(changed, changed, saved);
+            }
+        }
+        {
+            auto [b, e] = upd.asym_line.scenario(s);
+            for (auto p = b; p != e; ++p) {
+                Idx const i = find_seq(*p, p - b, e - b, static_cast<Idx>(asym_lines_.size()), asym_line_idx_, 0);
+                saved.asym_lines.emplace_back(i, asym_lines_[i]);
+                bool const changed = asym_lines_[i].set_status(p->from_status, p->to_status);
+                mark(changed, changed, saved);
+            }
+        }
+        {
+            auto [b, e] = upd.generic_branch.scenario(s);
+            for (auto p = b; p != e; ++p) {
+                Idx const i = find_seq(*p, p - b, e - b, static_cast<Idx>(generic_branches_.size()), generic_branch_idx_, 0);
+                saved.generic_branches.emplace_back(i, generic_branches_[i]);
+                bool const changed = generic_branches_[i].set_status(p->from_status, p->to_status);
                 mark(changed, changed, saved);
             }
         }
@@ -703,6 +782,9 @@ class Model {
     void restore(Saved const& saved) {
         // restore in reverse order so repeated updates of one component end at the original value
         for (auto it = saved.lines.rbegin(); it != saved.lines.rend(); ++it) lines_[it->first] = it->second;
+        for (auto it = saved.asym_lines.rbegin(); it != saved.asym_lines.rend(); ++it) asym_lines_[it->first] = it->second;
+        for (auto it = saved.generic_branches.rbegin(); it != saved.generic_branches.rend(); ++it)
+            generic_branches_[it->first] = it->second;
         for (auto it = saved.transformers.rbegin(); it != saved.transformers.rend(); ++it)
             transformers_[it->first] = it->second;
         for (auto it = saved.shunts.rbegin(); it != saved.shunts.rend(); ++it) shunts_[it->first] = it->second;

@@ -83,7 +83,8 @@ class ComponentBufferC(C.Structure):
     _fields_ = [("n", C.c_int64), ("indptr", C.c_void_p), ("data", C.c_void_p)]
 
 
-_COMPS = ("node", "line", "transformer", "shunt", "source", "sym_gen", "asym_gen", "sym_load", "asym_load", "voltage_regulator")
+_COMPS = ("node", "line", "transformer", "shunt", "source", "sym_gen", "asym_gen", "sym_load", "asym_load", "voltage_regulator",
+          "asym_line", "generic_branch")
 
 
 class InputDataC(C.Structure):

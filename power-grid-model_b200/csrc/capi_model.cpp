@@ -12,11 +12,11 @@ namespace {
 ComponentBuffer cb(pgmb_component_buffer const& b) { return {b.n, b.indptr, b.data}; }
 InputData input_of(pgmb_input_data const& in) {
     return {cb(in.node), cb(in.line), cb(in.transformer), cb(in.shunt), cb(in.source), cb(in.sym_gen), cb(in.asym_gen),
-            cb(in.sym_load), cb(in.asym_load), cb(in.voltage_regulator)};
+            cb(in.sym_load), cb(in.asym_load), cb(in.voltage_regulator), cb(in.asym_line), cb(in.generic_branch)};
 }
 UpdateData update_of(pgmb_update_data const& u) {
     return {u.n_scenarios, cb(u.line), cb(u.transformer), cb(u.shunt), cb(u.source), cb(u.sym_gen), cb(u.asym_gen),
-            cb(u.sym_load), cb(u.asym_load), cb(u.voltage_regulator)};
+            cb(u.sym_load), cb(u.asym_load), cb(u.voltage_regulator), cb(u.asym_line), cb(u.generic_branch)};
 }
 } // namespace
 
@@ -48,7 +48,7 @@ int pgmb_model_calculate(pgmb_model* model, const pgmb_options* opt, const pgmb_
         ModelOptions const mo{opt->calculation_method, opt->symmetric != 0, opt->err_tol, opt->max_iter, opt->first_device, opt->threading};
         OutputData const od{output->node, output->line, output->transformer, output->shunt, output->source,
                             output->sym_gen, output->asym_gen, output->sym_load, output->asym_load,
-                            output->voltage_regulator};
+                            output->voltage_regulator, output->asym_line, output->generic_branch};
         if (update != nullptr) {
             UpdateData const ud = update_of(*update);
             failed = model->model->calculate(mo, &ud, od, n_iter, status);

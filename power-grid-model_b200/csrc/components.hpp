@@ -100,6 +100,20 @@ struct AsymLoadGenUpdate {
     IntS status;
     double p_specified[3], q_specified[3];
 };
+// asym_line / generic_branch (auxiliary/input.hpp:99-165); both are updated with BranchUpdate and report BranchOutput
+struct AsymLineInput {
+    ID id, from_node, to_node;
+    IntS from_status, to_status;
+    double r_aa, r_ba, r_bb, r_ca, r_cb, r_cc, r_na, r_nb, r_nc, r_nn;
+    double x_aa, x_ba, x_bb, x_ca, x_cb, x_cc, x_na, x_nb, x_nc, x_nn;
+    double c_aa, c_ba, c_bb, c_ca, c_cb, c_cc, c0, c1, i_n;
+};
+struct GenericBranchInput {
+    ID id, from_node, to_node;
+    IntS from_status, to_status;
+    double r1, x1, g1, b1, k, theta, sn;
+};
+static_assert(sizeof(AsymLineInput) == 248 && sizeof(GenericBranchInput) == 72);
 // voltage regulator (auxiliary/input.hpp:492-498, update.hpp:213-219, output.hpp:239-243)
 struct VoltageRegulatorInput {
     ID id, regulated_object;
@@ -229,6 +243,148 @@ template <int B> inline void line_param(LineConst const& c, BranchState const& s
         SymBranchParam const p0 = branch_pi_model(st.from_status, st.to_status, c.y0_series, c.y0_shunt, 1.0);
         cplx const v0[4] = {p0.yff, p0.yft, p0.ytf, p0.ytt};
         for (int k = 0; k != 4; ++k) put_scalar_tensor<3>(out + 18 * k, (2.0 * v1[k] + v0[k]) / 3.0, (v0[k] - v1[k]) / 3.0);
+    }
+}
+
+// ---- generic branch (component/generic_branch.hpp:37-93): pi model with a complex ratio k e^{j theta}; symmetric only ----
+struct GenericBranchConst {
+    double base_i_from, base_i_to, sn, theta;
+    cplx y1_series, y1_shunt, ratio;
+};
+inline GenericBranchConst generic_branch_constants(GenericBranchInput const& in, double u1_rated, double u2_rated) {
+    GenericBranchConst c;
+    c.sn = in.sn;
+    double const k = std::isnan(in.k) ? 1.0 : in.k;
+    c.theta = std::isnan(in.theta) ? 0.0 : std::fmod(in.theta, 2 * kPi);
+    c.base_i_from = kBasePower3p / u1_rated / kSqrt3;
+    c.base_i_to = kBasePower3p / u2_rated / kSqrt3;
+    double const base_y = c.base_i_to / (u2_rated / kSqrt3);
+    cplx const j{0.0, 1.0};
+    c.y1_series = 1.0 / (in.r1 + j * in.x1) / base_y;
+    c.y1_shunt = (in.g1 + j * in.b1) / base_y;
+    c.ratio = k * std::exp(j * c.theta);
+    return c;
+}
+inline void generic_branch_param(GenericBranchConst const& c, BranchState const& st, double* out) { // [4] complex, B = 1
+    SymBranchParam const p = branch_pi_model(st.from_status, st.to_status, c.y1_series, c.y1_shunt, c.ratio);
+    cplx const v[4] = {p.yff, p.yft, p.ytf, p.ytt};
+    for (int k = 0; k != 4; ++k) put_scalar_tensor<1>(out + 2 * k, v[k], 0.0);
+}
+
+// ---- asymmetric line (component/asym_line.hpp:26-127, component/line_utils.hpp, common/matrix_utils.hpp) ---------------------
+struct Mat3 {
+    cplx m[3][3]{};
+};
+inline Mat3 mat3_sym(cplx s1, cplx s2, cplx s3, cplx m12, cplx m13, cplx m23) {
+    Mat3 r;
+    r.m[0][0] = s1, r.m[1][1] = s2, r.m[2][2] = s3;
+    r.m[0][1] = r.m[1][0] = m12;
+    r.m[0][2] = r.m[2][0] = m13;
+    r.m[1][2] = r.m[2][1] = m23;
+    return r;
+}
+template <class F> inline Mat3 mat3_map(Mat3 const& a, F f) {
+    Mat3 r;
+    for (int i = 0; i != 3; ++i)
+        for (int j = 0; j != 3; ++j) r.m[i][j] = f(a.m[i][j]);
+    return r;
+}
+inline Mat3 mat3_add(Mat3 const& a, Mat3 const& b) {
+    Mat3 r;
+    for (int i = 0; i != 3; ++i)
+        for (int j = 0; j != 3; ++j) r.m[i][j] = a.m[i][j] + b.m[i][j];
+    return r;
+}
+// inverse by cofactors (what a fixed-size 3 x 3 inverse does): inv(i, j) = cofactor(j, i) / det
+inline Mat3 mat3_inv(Mat3 const& a) {
+    auto cof = [&a](int i, int j) {
+        int const i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+        return a.m[i1][j1] * a.m[i2][j2] - a.m[i1][j2] * a.m[i2][j1];
+    };
+    cplx const c0 = cof(0, 0), c1 = cof(1, 0), c2 = cof(2, 0);
+    cplx const det = c0 * a.m[0][0] + c1 * a.m[1][0] + c2 * a.m[2][0];
+    cplx const invdet = 1.0 / det;
+    Mat3 r;
+    for (int i = 0; i != 3; ++i)
+        for (int j = 0; j != 3; ++j) r.m[i][j] = cof(j, i) * invdet;
+    return r;
+}
+struct AsymLineConst {
+    double base_i, i_n;
+    Mat3 y_series, y_shunt;
+};
+inline AsymLineConst asym_line_constants(AsymLineInput const& in, double system_frequency, double u_rated) {
+    AsymLineConst c;
+    c.i_n = in.i_n;
+    c.base_i = kBasePower3p / u_rated / kSqrt3;
+    cplx const j{0.0, 1.0};
+    Mat3 z;
+    if (std::isnan(in.r_na) && std::isnan(in.x_na)) {
+        Mat3 const r = mat3_sym(in.r_aa, in.r_bb, in.r_cc, in.r_ba, in.r_ca, in.r_cb);
+        Mat3 const x = mat3_sym(in.x_aa, in.x_bb, in.x_cc, in.x_ba, in.x_ca, in.x_cb);
+        for (int a = 0; a != 3; ++a)
+            for (int b = 0; b != 3; ++b) z.m[a][b] = r.m[a][b] + j * x.m[a][b];
+    } else { // neutral conductor given: Kron reduction of the 4 x 4 matrix
+        auto zz = [&j](double r, double x) { return cplx{r} + j * cplx{x}; };
+        Mat3 const z_pp = mat3_sym(zz(in.r_aa, in.x_aa), zz(in.r_bb, in.x_bb), zz(in.r_cc, in.x_cc), zz(in.r_ba, in.x_ba),
+                                   zz(in.r_ca, in.x_ca), zz(in.r_cb, in.x_cb));
+        cplx const z_pn[3] = {zz(in.r_na, in.x_na), zz(in.r_nb, in.x_nb), zz(in.r_nc, in.x_nc)};
+        cplx const z_nn_inv = 1.0 / zz(in.r_nn, in.x_nn);
+        for (int a = 0; a != 3; ++a)
+            for (int b = 0; b != 3; ++b) z.m[a][b] = z_pp.m[a][b] - (z_pn[a] * z_pn[b]) * z_nn_inv;
+    }
+    Mat3 cm;
+    if (!std::isnan(in.c0) && !std::isnan(in.c1)) {
+        cplx const sdiag = (2.0 * in.c1 + in.c0) / 3.0, moff = (in.c0 - in.c1) / 3.0;
+        cm = mat3_sym(sdiag, sdiag, sdiag, moff, moff, moff);
+    } else {
+        cm = mat3_sym(in.c_aa, in.c_bb, in.c_cc, in.c_ba, in.c_ca, in.c_cb);
+    }
+    double const base_y = c.base_i / (u_rated / kSqrt3);
+    double const inv_base_y = 1 / base_y;
+    c.y_series = mat3_map(mat3_inv(z), [inv_base_y](cplx v) { return inv_base_y * v; });
+    cplx const w = 2.0 * j * kPi * system_frequency;
+    c.y_shunt = mat3_map(cm, [inv_base_y, w](cplx v) { return inv_base_y * (w * v); });
+    return c;
+}
+template <int B> inline void asym_line_param(AsymLineConst const& c, BranchState const& st, double* out) { // [4][B][B] complex
+    if constexpr (B == 1) {
+        auto avg_diag = [](Mat3 const& a) { return (a.m[0][0] + a.m[1][1] + a.m[2][2]) / 3.0; };
+        // the reference's off-diagonal average as it is written (matrix_utils.hpp:16-18: (1,2) twice, (0,2) absent)
+        auto avg_off = [](Mat3 const& a) { return (a.m[0][1] + a.m[1][2] + a.m[1][0] + a.m[1][2] + a.m[2][0] + a.m[2][1]) / 6.0; };
+        cplx const y1_series = avg_diag(c.y_series) - avg_off(c.y_series);
+        cplx const y1_shunt = avg_diag(c.y_shunt) - avg_off(c.y_shunt);
+        SymBranchParam const p = branch_pi_model(st.from_status, st.to_status, y1_series, y1_shunt, 1.0);
+        cplx const v[4] = {p.yff, p.yft, p.ytf, p.ytt};
+        for (int k = 0; k != 4; ++k) put_scalar_tensor<1>(out + 2 * k, v[k], 0.0);
+    } else {
+        Mat3 yff, yft, ytf, ytt;
+        if (!(st.from_status && st.to_status)) {
+            if (st.from_status || st.to_status) {
+                Mat3 branch_shunt;
+                bool all_above = true;
+                for (int a = 0; a != 3; ++a)
+                    for (int b = 0; b != 3; ++b) all_above = all_above && std::sqrt(std::norm(c.y_shunt.m[a][b])) >= kNumTol;
+                if (all_above) {
+                    Mat3 const inner = mat3_add(mat3_inv(c.y_series), mat3_map(mat3_inv(c.y_shunt), [](cplx v) { return 2.0 * v; }));
+                    branch_shunt = mat3_add(mat3_map(c.y_shunt, [](cplx v) { return 0.5 * v; }), mat3_inv(inner));
+                }
+                if (st.from_status) yff = branch_shunt;
+                if (st.to_status) ytt = branch_shunt;
+            }
+        } else {
+            ytt = mat3_add(c.y_series, mat3_map(c.y_shunt, [](cplx v) { return 0.5 * v; }));
+            yff = ytt;
+            yft = mat3_map(c.y_series, [](cplx v) { return -v; });
+            ytf = yft;
+        }
+        Mat3 const* blocks[4] = {&yff, &yft, &ytf, &ytt};
+        for (int k = 0; k != 4; ++k)
+            for (int a = 0; a != 3; ++a)
+                for (int b = 0; b != 3; ++b) {
+                    out[18 * k + 2 * (a * 3 + b)] = blocks[k]->m[a][b].real();
+                    out[18 * k + 2 * (a * 3 + b) + 1] = blocks[k]->m[a][b].imag();
+                }
     }
 }
 

@@ -43,6 +43,26 @@ Model::Model(double system_frequency, InputData const& in) : freq_{system_freque
         line_c_.push_back(line_constants(l, freq_, u1));
         branch_st_.push_back({l.from_status != 0, l.to_status != 0});
     }
+    auto const* alines = static_cast<AsymLineInput const*>(in.asym_line.data);
+    for (Idx i = 0; i != in.asym_line.n; ++i) {
+        AsymLineInput const& l = alines[i];
+        add_id(l.id);
+        double const u1 = u_rated(l.from_node), u2 = u_rated(l.to_node);
+        if (std::abs(u1 - u2) > kNumTol) throw InvalidArgument("Conflicting voltage for line " + std::to_string(l.id) + "\n");
+        aline_idx_[l.id] = i;
+        aline_in_.push_back(l);
+        aline_c_.push_back(asym_line_constants(l, freq_, u1));
+        branch_st_.push_back({l.from_status != 0, l.to_status != 0});
+    }
+    auto const* gbs = static_cast<GenericBranchInput const*>(in.generic_branch.data);
+    for (Idx i = 0; i != in.generic_branch.n; ++i) {
+        GenericBranchInput const& g = gbs[i];
+        add_id(g.id);
+        gb_idx_[g.id] = i;
+        gb_in_.push_back(g);
+        gb_c_.push_back(generic_branch_constants(g, u_rated(g.from_node), u_rated(g.to_node)));
+        branch_st_.push_back({g.from_status != 0, g.to_status != 0});
+    }
     auto const* trafos = static_cast<TransformerInput const*>(in.transformer.data);
     for (Idx i = 0; i != in.transformer.n; ++i) {
         TransformerInput const& t = trafos[i];
@@ -158,6 +178,27 @@ template <int B> void Model::check_regulators(ModelOptions const& opt) const {
     }
 }
 
+Model::BranchInfo Model::branch_info(Idx b) const {
+    if (b < off_aline()) {
+        auto const& l = line_in_[b];
+        return {l.id, node_seq(l.from_node), node_seq(l.to_node), line_c_[b].base_i, line_c_[b].base_i, -l.i_n};
+    }
+    if (b < off_gb()) {
+        Idx const i = b - off_aline();
+        auto const& l = aline_in_[i];
+        return {l.id, node_seq(l.from_node), node_seq(l.to_node), aline_c_[i].base_i, aline_c_[i].base_i, -l.i_n};
+    }
+    if (b < off_trafo()) {
+        Idx const i = b - off_gb();
+        auto const& g = gb_in_[i];
+        return {g.id, node_seq(g.from_node), node_seq(g.to_node), gb_c_[i].base_i_from, gb_c_[i].base_i_to,
+                std::isnan(gb_c_[i].sn) ? std::numeric_limits<double>::infinity() : gb_c_[i].sn};
+    }
+    Idx const i = b - off_trafo();
+    auto const& t = trafo_in_[i];
+    return {t.id, node_seq(t.from_node), node_seq(t.to_node), trafo_c_[i].base_i_from, trafo_c_[i].base_i_to, trafo_c_[i].sn};
+}
+
 Idx Model::node_seq(ID id) const {
     auto it = node_idx_.find(id);
     if (it == node_idx_.end()) throw InvalidArgument("The id cannot be found: " + std::to_string(id) + "\n");
@@ -184,8 +225,14 @@ void Model::prepare_topology() {
         g.branch_status.push_back({static_cast<int8_t>(branch_st_[i].from_status), static_cast<int8_t>(branch_st_[i].to_status)});
         g.branch_shift.push_back(0.0);
     }
+    for (Idx b = off_aline(); b != off_trafo(); ++b) {
+        BranchInfo const info = branch_info(b);
+        g.branch_node.push_back({info.from, info.to});
+        g.branch_status.push_back({static_cast<int8_t>(branch_st_[b].from_status), static_cast<int8_t>(branch_st_[b].to_status)});
+        g.branch_shift.push_back(b < off_gb() ? 0.0 : gb_c_[b - off_gb()].theta);
+    }
     for (Idx i = 0; i != n_trafo(); ++i) {
-        auto const& st = branch_st_[n_line() + i];
+        auto const& st = branch_st_[off_trafo() + i];
         g.branch_node.push_back({node_seq(trafo_in_[i].from_node), node_seq(trafo_in_[i].to_node)});
         g.branch_status.push_back({static_cast<int8_t>(st.from_status), static_cast<int8_t>(st.to_status)});
         g.branch_shift.push_back(trafo_c_[i].clock * kDeg30);
@@ -221,9 +268,22 @@ void Model::param_arrays(Idx group, std::vector<double>& bp, std::vector<double>
         Coupling const c = topo_.branch[i];
         if (c.group == group) line_param<B>(line_c_[i], branch_st_[i], &bp[c.pos * 4 * bb2]);
     }
+    for (Idx i = 0; i != n_aline(); ++i) {
+        Coupling const c = topo_.branch[off_aline() + i];
+        if (c.group == group) asym_line_param<B>(aline_c_[i], branch_st_[off_aline() + i], &bp[c.pos * 4 * bb2]);
+    }
+    for (Idx i = 0; i != n_gb(); ++i) {
+        Coupling const c = topo_.branch[off_gb() + i];
+        if (c.group != group) continue;
+        if constexpr (B == 1) {
+            generic_branch_param(gb_c_[i], branch_st_[off_gb() + i], &bp[c.pos * 4 * bb2]);
+        } else { // GenericBranch::asym_calc_param throws NotImplementedError (generic_branch.hpp:91)
+            throw InvalidArgument("Function not yet implemented: generic_branch in an asymmetric calculation\n");
+        }
+    }
     for (Idx i = 0; i != n_trafo(); ++i) {
-        Coupling const c = topo_.branch[n_line() + i];
-        if (c.group == group) transformer_param<B>(trafo_c_[i], branch_st_[n_line() + i], trafo_st_[i].tap_pos, &bp[c.pos * 4 * bb2]);
+        Coupling const c = topo_.branch[off_trafo() + i];
+        if (c.group == group) transformer_param<B>(trafo_c_[i], branch_st_[off_trafo() + i], trafo_st_[i].tap_pos, &bp[c.pos * 4 * bb2]);
     }
     for (size_t i = 0; i != shunt_in_.size(); ++i) {
         Coupling const c = topo_.shunt[i];
@@ -344,11 +404,23 @@ void Model::apply_scenario(UpdateData const& u, Idx s, Saved* saved) {
             mark(changed, changed, saved);
         }
     }
+    auto upd_plain_branch = [&](ComponentBuffer const& buf, Idx count, std::unordered_map<ID, Idx> const& map, Idx offset) {
+        auto [b, e] = scenario_span<BranchUpdate>(buf, s);
+        for (auto p = b; p != e; ++p) {
+            Idx const i = offset + find(*p, p - b, e - b, count, map, 0);
+            if (saved != nullptr) saved->branch.emplace_back(i, branch_st_[i]);
+            bool changed = set_status(branch_st_[i].from_status, p->from_status);
+            changed = set_status(branch_st_[i].to_status, p->to_status) || changed;
+            mark(changed, changed, saved);
+        }
+    };
+    upd_plain_branch(u.asym_line, n_aline(), aline_idx_, off_aline());
+    upd_plain_branch(u.generic_branch, n_gb(), gb_idx_, off_gb());
     {
         auto [b, e] = scenario_span<TransformerUpdate>(u.transformer, s);
         for (auto p = b; p != e; ++p) {
             Idx const i = find(*p, p - b, e - b, n_trafo(), trafo_idx_, 0);
-            Idx const bi = n_line() + i;
+            Idx const bi = off_trafo() + i;
             if (saved != nullptr) {
                 saved->branch.emplace_back(bi, branch_st_[bi]);
                 saved->trafo.emplace_back(i, trafo_st_[i]);
@@ -561,11 +633,18 @@ void Model::write_output(Idx n_scn, Idx first, OutputData const& out, std::vecto
             auto* dst = static_cast<BranchOutput<B>*>(out.line) + os * n_line();
             for (Idx i = 0; i != n_line(); ++i) dst[i] = branch(i, line_in_[i].id, line_c_[i].base_i, line_c_[i].base_i, -1.0, line_in_[i].i_n);
         }
-        if (out.transformer != nullptr) {
-            auto* dst = static_cast<BranchOutput<B>*>(out.transformer) + os * n_trafo();
-            for (Idx i = 0; i != n_trafo(); ++i)
-                dst[i] = branch(n_line() + i, trafo_in_[i].id, trafo_c_[i].base_i_from, trafo_c_[i].base_i_to, trafo_c_[i].sn, 0.0);
-        }
+        auto branch_range = [&](void* base, Idx first_b, Idx count) {
+            if (base == nullptr) return;
+            auto* dst = static_cast<BranchOutput<B>*>(base) + os * count;
+            for (Idx i = 0; i != count; ++i) {
+                BranchInfo const info = branch_info(first_b + i);
+                dst[i] = branch(first_b + i, info.id, info.base_i_from, info.base_i_to, info.rating > 0.0 ? info.rating : -1.0,
+                                info.rating > 0.0 ? 0.0 : -info.rating);
+            }
+        };
+        branch_range(out.asym_line, off_aline(), n_aline());
+        branch_range(out.generic_branch, off_gb(), n_gb());
+        branch_range(out.transformer, off_trafo(), n_trafo());
         if (out.shunt != nullptr) {
             Idx const n = static_cast<Idx>(shunt_in_.size());
             auto* dst = static_cast<ApplianceOutput<B>*>(out.shunt) + os * n;
@@ -676,10 +755,10 @@ int64_t Model::run_block(ModelOptions const& opt, Idx n_scn, std::vector<std::ve
 // bridges of the graph of fully connected branches (iterative Tarjan; parallel branches are told apart by their edge id)
 Model::BridgeInfo Model::bridge_analysis() const {
     Idx const n = static_cast<Idx>(node_.size());
-    Idx const nb = n_line() + n_trafo();
+    Idx const nb = n_branch_comp();
     auto ends = [&](Idx b) -> std::pair<Idx, Idx> {
-        return b < n_line() ? std::pair<Idx, Idx>{node_seq(line_in_[b].from_node), node_seq(line_in_[b].to_node)}
-                            : std::pair<Idx, Idx>{node_seq(trafo_in_[b - n_line()].from_node), node_seq(trafo_in_[b - n_line()].to_node)};
+        BranchInfo const info = branch_info(b);
+        return {info.from, info.to};
     };
     std::vector<Idx> ptr(n + 1, 0);
     std::vector<std::pair<Idx, Idx>> e(nb);
@@ -753,7 +832,8 @@ Model::BridgeInfo Model::bridge_analysis() const {
 
 template <int B> bool Model::plan_outage_batch(UpdateData const& u, OutagePlan& plan) const {
     if (u.shunt.data != nullptr || u.source.data != nullptr || u.sym_gen.data != nullptr || u.asym_gen.data != nullptr ||
-        u.sym_load.data != nullptr || u.asym_load.data != nullptr || u.voltage_regulator.data != nullptr) {
+        u.sym_load.data != nullptr || u.asym_load.data != nullptr || u.voltage_regulator.data != nullptr ||
+        u.asym_line.data != nullptr || u.generic_branch.data != nullptr) {
         return false;
     }
     if (topo_.math.size() != 1 || u.n_scenarios <= 0) return false;
@@ -806,7 +886,7 @@ template <int B> bool Model::plan_outage_batch(UpdateData const& u, OutagePlan& 
             for (auto p = b; p != e; ++p) {
                 Idx const i = lookup(p->id, p - b, e - b, n_trafo(), trafo_idx_);
                 if (p->tap_pos != kNaIntS && p->tap_pos != trafo_st_[i].tap_pos) exact = true;
-                note(n_line() + i, p->from_status, p->to_status);
+                note(off_trafo() + i, p->from_status, p->to_status);
             }
         }
         std::erase_if(changes, [this](Change const& c) { return c.from == branch_st_[c.branch].from_status && c.to == branch_st_[c.branch].to_status; });
@@ -855,7 +935,7 @@ template <int B> bool Model::plan_outage_batch(UpdateData const& u, OutagePlan& 
                 if (c.branch < n_line()) {
                     line_param<B>(line_c_[c.branch], st, &plan.bparam[s * 4 * bb2]);
                 } else {
-                    Idx const i = c.branch - n_line();
+                    Idx const i = c.branch - off_trafo();
                     transformer_param<B>(trafo_c_[i], st, trafo_st_[i].tap_pos, &plan.bparam[s * 4 * bb2]);
                 }
                 if (plan.dead_off[s] >= 0) { // still connected to a supplied bus?  otherwise the branch itself goes dark
@@ -901,6 +981,7 @@ int64_t Model::calculate_impl(ModelOptions const& opt, UpdateData const* update,
         // does any scenario touch something other than loads / generators / source references?
         // (regulator updates change the parameters every scenario of one engine call shares: scenario by scenario as well)
         bool const structural = update->line.data != nullptr || update->transformer.data != nullptr ||
+                                update->asym_line.data != nullptr || update->generic_branch.data != nullptr ||
                                 update->shunt.data != nullptr || (has_reg && update->voltage_regulator.data != nullptr);
         bool source_param_change = false;
         if (update->source.data != nullptr) {

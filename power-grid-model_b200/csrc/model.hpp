@@ -25,14 +25,14 @@ struct ComponentBuffer {
     void const* data;
 };
 struct InputData {
-    ComponentBuffer node, line, transformer, shunt, source, sym_gen, asym_gen, sym_load, asym_load, voltage_regulator;
+    ComponentBuffer node, line, transformer, shunt, source, sym_gen, asym_gen, sym_load, asym_load, voltage_regulator, asym_line, generic_branch;
 };
 struct UpdateData {
     int64_t n_scenarios;
-    ComponentBuffer line, transformer, shunt, source, sym_gen, asym_gen, sym_load, asym_load, voltage_regulator;
+    ComponentBuffer line, transformer, shunt, source, sym_gen, asym_gen, sym_load, asym_load, voltage_regulator, asym_line, generic_branch;
 };
 struct OutputData {
-    void *node, *line, *transformer, *shunt, *source, *sym_gen, *asym_gen, *sym_load, *asym_load, *voltage_regulator;
+    void *node, *line, *transformer, *shunt, *source, *sym_gen, *asym_gen, *sym_load, *asym_load, *voltage_regulator, *asym_line, *generic_branch;
 };
 struct ModelOptions {
     int32_t method;
@@ -70,6 +70,10 @@ class Model {
     std::vector<NodeInput> node_;
     std::vector<LineInput> line_in_;
     std::vector<LineConst> line_c_;
+    std::vector<AsymLineInput> aline_in_;
+    std::vector<AsymLineConst> aline_c_;
+    std::vector<GenericBranchInput> gb_in_;
+    std::vector<GenericBranchConst> gb_c_;
     std::vector<TransformerInput> trafo_in_;
     std::vector<TransformerConst> trafo_c_;
     std::vector<SourceInput> source_in_;
@@ -86,7 +90,7 @@ class Model {
     std::vector<LoadGenStatic> lg_;
     Idx n_sym_gen_{}, n_asym_gen_{}, n_sym_load_{}, n_asym_load_{};
     // mutable state
-    std::vector<BranchState> branch_st_; // lines then transformers
+    std::vector<BranchState> branch_st_; // branch sequence of the reference: lines, asym_lines, generic_branches, transformers
     std::vector<TransformerState> trafo_st_;
     std::vector<SourceState> source_st_;
     std::vector<ShuntState> shunt_st_;
@@ -96,7 +100,7 @@ class Model {
     std::vector<Idx> reg_lg_;
     std::vector<RegulatorState> reg_st_;
     // id lookup
-    std::unordered_map<ID, Idx> node_idx_, line_idx_, trafo_idx_, shunt_idx_, source_idx_, lg_idx_, reg_idx_;
+    std::unordered_map<ID, Idx> node_idx_, line_idx_, trafo_idx_, shunt_idx_, source_idx_, lg_idx_, reg_idx_, aline_idx_, gb_idx_;
     std::unordered_map<ID, int> all_ids_;
 
     // caches
@@ -122,6 +126,20 @@ class Model {
 
     Idx n_line() const { return static_cast<Idx>(line_in_.size()); }
     Idx n_trafo() const { return static_cast<Idx>(trafo_in_.size()); }
+    Idx n_aline() const { return static_cast<Idx>(aline_in_.size()); }
+    Idx n_gb() const { return static_cast<Idx>(gb_in_.size()); }
+    Idx off_aline() const { return n_line(); }
+    Idx off_gb() const { return n_line() + n_aline(); }
+    Idx off_trafo() const { return n_line() + n_aline() + n_gb(); }
+    Idx n_branch_comp() const { return off_trafo() + n_trafo(); }
+    // per branch of the sequence: id, end nodes (sequence numbers), base currents, rating (> 0: sn, loading = max_s / sn;
+    // < 0: -i_n, loading = max_i / i_n; +inf: loading 0)
+    struct BranchInfo {
+        ID id;
+        Idx from, to;
+        double base_i_from, base_i_to, rating;
+    };
+    BranchInfo branch_info(Idx b) const;
     Idx node_seq(ID id) const;
     void prepare_topology();
     template <int B> void prepare_engines();

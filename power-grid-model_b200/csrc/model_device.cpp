@@ -37,7 +37,7 @@ struct Model::DeviceSide {
     Idx n_app_first[6]{}; // first appliance index of shunt, source, sym_gen, asym_gen, sym_load, asym_load
     // per-batch buffers
     DevBuf<unsigned char> upd[4];
-    DevBuf<unsigned char> out[10];
+    DevBuf<unsigned char> out[12];
     DevBuf<double> src_res;
     // voltage regulators: component tables and the per-scenario flags of the math regulators
     DevBuf<int32_t> reg_id, reg_math;
@@ -107,7 +107,7 @@ int64_t Model::run_batch_device(ModelOptions const& opt, int phases, UpdateData 
         size_t row;
         Idx count;
     };
-    Part const outs[10] = {{&out.node, row_node, static_cast<Idx>(node_.size())},
+    Part const outs[12] = {{&out.node, row_node, static_cast<Idx>(node_.size())},
                           {&out.line, row_branch, n_line()},
                           {&out.transformer, row_branch, n_trafo()},
                           {&out.shunt, row_app, static_cast<Idx>(shunt_in_.size())},
@@ -116,7 +116,9 @@ int64_t Model::run_batch_device(ModelOptions const& opt, int phases, UpdateData 
                           {&out.asym_gen, row_app, n_asym_gen_},
                           {&out.sym_load, row_app, n_sym_load_},
                           {&out.asym_load, row_app, n_asym_load_},
-                          {&out.voltage_regulator, sizeof(VoltageRegulatorOutput), static_cast<Idx>(reg_in_.size())}};
+                          {&out.voltage_regulator, sizeof(VoltageRegulatorOutput), static_cast<Idx>(reg_in_.size())},
+                          {&out.asym_line, row_branch, n_aline()},
+                          {&out.generic_branch, row_branch, n_gb()}};
     ComponentBuffer const* ubufs[4] = {&update.sym_gen, &update.asym_gen, &update.sym_load, &update.asym_load};
     size_t const urow[4] = {sizeof(SymLoadGenUpdate), sizeof(AsymLoadGenUpdate), sizeof(SymLoadGenUpdate), sizeof(AsymLoadGenUpdate)};
     size_t per_scn = static_cast<size_t>(e.pattern().nnz_lu) * N * N * 8 + 6 * static_cast<size_t>(m.n_bus) * N * 8 +
@@ -156,9 +158,9 @@ int64_t Model::run_batch_device(ModelOptions const& opt, int phases, UpdateData 
             }
         }
         OutputData o = out;
-        void** ohost[10] = {&o.node, &o.line, &o.transformer, &o.shunt, &o.source, &o.sym_gen, &o.asym_gen, &o.sym_load, &o.asym_load,
-                            &o.voltage_regulator};
-        for (int k = 0; k != 10; ++k)
+        void** ohost[12] = {&o.node, &o.line, &o.transformer, &o.shunt, &o.source, &o.sym_gen, &o.asym_gen, &o.sym_load, &o.asym_load,
+                            &o.voltage_regulator, &o.asym_line, &o.generic_branch};
+        for (int k = 0; k != 12; ++k)
             if (*ohost[k] != nullptr) *ohost[k] = static_cast<unsigned char*>(*ohost[k]) + static_cast<size_t>(s0) * outs[k].count * outs[k].row;
         int64_t const r = run_batch_device_part(opt, phases, u, o, n_iter ? n_iter + s0 : nullptr, status ? status + s0 : nullptr, s0);
         if (r < 0) return -1;
@@ -203,18 +205,17 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
             app.insert(app.end(), per_node[i].begin(), per_node[i].end());
             app_ptr[i + 1] = static_cast<int32_t>(app.size());
         }
-        Idx const nb = n_line() + n_trafo();
+        Idx const nb = n_branch_comp();
         std::vector<int32_t> b_id(nb), b_math(nb);
         std::vector<double> b_base(2 * nb), b_rating(nb);
         std::vector<uint8_t> b_en(nb);
         for (Idx i = 0; i != nb; ++i) {
-            bool const is_line = i < n_line();
-            Idx const k = is_line ? i : i - n_line();
-            b_id[i] = is_line ? line_in_[k].id : trafo_in_[k].id;
+            BranchInfo const info = branch_info(i);
+            b_id[i] = info.id;
             b_math[i] = topo_.branch[i].group == 0 ? static_cast<int32_t>(topo_.branch[i].pos) : -1;
-            b_base[2 * i] = is_line ? line_c_[k].base_i : trafo_c_[k].base_i_from;
-            b_base[2 * i + 1] = is_line ? line_c_[k].base_i : trafo_c_[k].base_i_to;
-            b_rating[i] = is_line ? -line_in_[k].i_n : trafo_c_[k].sn;
+            b_base[2 * i] = info.base_i_from;
+            b_base[2 * i + 1] = info.base_i_to;
+            b_rating[i] = info.rating; // > 0: sn ; < 0: -i_n ; +inf: loading 0
             b_en[i] = (branch_st_[i].from_status || branch_st_[i].to_status) ? 1 : 0;
         }
         Idx const n_app = static_cast<Idx>(shunt_in_.size() + source_in_.size() + lg_.size());
@@ -424,7 +425,7 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
         size_t row;
         Idx count;
     };
-    Req const reqs[10] = {
+    Req const reqs[12] = {
         {out.node, 0, sym ? sizeof(NodeOutput<1>) : sizeof(NodeOutput<3>), nn},
         {out.line, 1, sym ? sizeof(BranchOutput<1>) : sizeof(BranchOutput<3>), n_line()},
         {out.transformer, 2, sym ? sizeof(BranchOutput<1>) : sizeof(BranchOutput<3>), n_trafo()},
@@ -435,6 +436,8 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
         {out.sym_load, 7, sym ? sizeof(ApplianceOutput<1>) : sizeof(ApplianceOutput<3>), n_sym_load_},
         {out.asym_load, 8, sym ? sizeof(ApplianceOutput<1>) : sizeof(ApplianceOutput<3>), n_asym_load_},
         {out.voltage_regulator, 9, sizeof(VoltageRegulatorOutput), static_cast<Idx>(reg_in_.size())},
+        {out.asym_line, 10, sym ? sizeof(BranchOutput<1>) : sizeof(BranchOutput<3>), n_aline()},
+        {out.generic_branch, 11, sym ? sizeof(BranchOutput<1>) : sizeof(BranchOutput<3>), n_gb()},
     };
     for (Req const& r : reqs) {
         if (r.host != nullptr && r.count != 0) d.out[r.slot].ensure(static_cast<size_t>(n_scn) * r.count * r.row);
@@ -489,12 +492,16 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
             if (r.host == nullptr || r.count == 0) continue;
             void* const dst = d.out[r.slot].get() + static_cast<size_t>(s0) * r.count * r.row;
             int const nl = static_cast<int>(n_line()), nt = static_cast<int>(n_trafo());
+            int const o_al = static_cast<int>(off_aline()), n_al = static_cast<int>(n_aline()), o_gb = static_cast<int>(off_gb()),
+                      n_g = static_cast<int>(n_gb()), o_tr = static_cast<int>(off_trafo());
             int const app_first = (r.slot >= 3 && r.slot < 9) ? static_cast<int>(d.n_app_first[r.slot - 3]) : 0;
             if (sym) {
                 switch (r.slot) {
                 case 0: launch_pack_node_sym(tw, ds, view, d.t, force_const_y, src_res, dst, q); break;
                 case 1: launch_pack_branch_sym(tw, ds, view, d.t, 0, nl, dst, q); break;
-                case 2: launch_pack_branch_sym(tw, ds, view, d.t, nl, nt, dst, q); break;
+                case 2: launch_pack_branch_sym(tw, ds, view, d.t, o_tr, nt, dst, q); break;
+                case 10: launch_pack_branch_sym(tw, ds, view, d.t, o_al, n_al, dst, q); break;
+                case 11: launch_pack_branch_sym(tw, ds, view, d.t, o_gb, n_g, dst, q); break;
                 case 9:
                     launch_pack_regulator(ns, static_cast<int>(r.count), static_cast<int>(m.n_voltage_regulator()), d.reg_id.get(),
                                           d.reg_math.get(), d.reg_status.get(), reg_flags, dst, q);
@@ -505,7 +512,9 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
                 switch (r.slot) {
                 case 0: launch_pack_node_asym(tw, ds, view, d.t, force_const_y, src_res, dst, q); break;
                 case 1: launch_pack_branch_asym(tw, ds, view, d.t, 0, nl, dst, q); break;
-                case 2: launch_pack_branch_asym(tw, ds, view, d.t, nl, nt, dst, q); break;
+                case 2: launch_pack_branch_asym(tw, ds, view, d.t, o_tr, nt, dst, q); break;
+                case 10: launch_pack_branch_asym(tw, ds, view, d.t, o_al, n_al, dst, q); break;
+                case 11: launch_pack_branch_asym(tw, ds, view, d.t, o_gb, n_g, dst, q); break;
                 case 9:
                     launch_pack_regulator(ns, static_cast<int>(r.count), static_cast<int>(m.n_voltage_regulator()), d.reg_id.get(),
                                           d.reg_math.get(), d.reg_status.get(), reg_flags, dst, q);

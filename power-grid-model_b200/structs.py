@@ -43,6 +43,12 @@ INPUT["voltage_regulator"] = _dt([("id", "i4"), ("regulated_object", "i4"), ("st
                                   ("q_max", "f8")])
 INPUT["sym_gen"] = INPUT["sym_load"]
 INPUT["asym_gen"] = INPUT["asym_load"]
+# further branch components (auxiliary/input.hpp:99-165)
+INPUT["asym_line"] = _dt(_branch_head + [(n, "f8") for n in (
+    "r_aa", "r_ba", "r_bb", "r_ca", "r_cb", "r_cc", "r_na", "r_nb", "r_nc", "r_nn",
+    "x_aa", "x_ba", "x_bb", "x_ca", "x_cb", "x_cc", "x_na", "x_nb", "x_nc", "x_nn",
+    "c_aa", "c_ba", "c_bb", "c_ca", "c_cb", "c_cc", "c0", "c1", "i_n")])
+INPUT["generic_branch"] = _dt(_branch_head + [(n, "f8") for n in ("r1", "x1", "g1", "b1", "k", "theta", "sn")])
 
 UPDATE = {
     "line": _dt([("id", "i4"), ("from_status", "i1"), ("to_status", "i1")]),
@@ -55,6 +61,8 @@ UPDATE = {
 UPDATE["voltage_regulator"] = _dt([("id", "i4"), ("status", "i1"), ("u_ref", "f8"), ("q_min", "f8"), ("q_max", "f8")])
 UPDATE["sym_gen"] = UPDATE["sym_load"]
 UPDATE["asym_gen"] = UPDATE["asym_load"]
+UPDATE["asym_line"] = UPDATE["line"]
+UPDATE["generic_branch"] = UPDATE["line"]
 
 
 def _real(sym):
@@ -70,7 +78,8 @@ def output_dtypes(sym: bool):
     )
     appliance = _dt([("id", "i4"), ("energized", "i1")] + [(n, *r) for n in ("p", "q", "i", "s", "pf")])
     return {
-        "node": node, "line": branch, "transformer": branch, "shunt": appliance, "source": appliance,
+        "node": node, "line": branch, "transformer": branch, "asym_line": branch, "generic_branch": branch,
+        "shunt": appliance, "source": appliance,
         "sym_gen": appliance, "asym_gen": appliance, "sym_load": appliance, "asym_load": appliance,
         "voltage_regulator": _dt([("id", "i4"), ("energized", "i1"), ("limit_violated", "i1")]),
     }
@@ -81,8 +90,9 @@ ASYM_OUTPUT = output_dtypes(False)
 
 # component storage order of the reference (all_components.hpp:36-39), PF subset
 COMPONENT_ORDER = ("node", "line", "transformer", "shunt", "source", "sym_gen", "asym_gen", "sym_load", "asym_load",
-                   "voltage_regulator")
-UPDATABLE = ("line", "transformer", "shunt", "source", "sym_gen", "asym_gen", "sym_load", "asym_load", "voltage_regulator")
+                   "voltage_regulator", "asym_line", "generic_branch")
+UPDATABLE = ("line", "transformer", "shunt", "source", "sym_gen", "asym_gen", "sym_load", "asym_load", "voltage_regulator",
+             "asym_line", "generic_branch")
 
 
 def initialize_array(kind: str, component: str, shape, sym: bool = True):
@@ -100,6 +110,7 @@ def initialize_array(kind: str, component: str, shape, sym: bool = True):
     return arr
 
 
+assert INPUT["asym_line"].itemsize == 248 and INPUT["generic_branch"].itemsize == 72
 assert INPUT["voltage_regulator"].itemsize == 40 and UPDATE["voltage_regulator"].itemsize == 32
 assert SYM_OUTPUT["voltage_regulator"].itemsize == 8
 assert INPUT["line"].itemsize == 88 and INPUT["transformer"].itemsize == 168 and INPUT["source"].itemsize == 56
