@@ -831,9 +831,9 @@ Model::BridgeInfo Model::bridge_analysis() const {
 }
 
 template <int B> bool Model::plan_outage_batch(UpdateData const& u, OutagePlan& plan) const {
-    if (u.shunt.data != nullptr || u.source.data != nullptr || u.sym_gen.data != nullptr || u.asym_gen.data != nullptr ||
-        u.sym_load.data != nullptr || u.asym_load.data != nullptr || u.voltage_regulator.data != nullptr ||
-        u.asym_line.data != nullptr || u.generic_branch.data != nullptr) {
+    // load / generator updates may ride along (contingency x load profile): the device pipeline applies them as in any load batch
+    if (u.shunt.data != nullptr || u.source.data != nullptr || u.voltage_regulator.data != nullptr || u.asym_line.data != nullptr ||
+        u.generic_branch.data != nullptr) {
         return false;
     }
     if (topo_.math.size() != 1 || u.n_scenarios <= 0) return false;
@@ -1007,13 +1007,17 @@ int64_t Model::calculate_impl(ModelOptions const& opt, UpdateData const* update,
                 std::fprintf(stderr, "[pgmb n-1] planned=%d scenarios=%lld exact=%zu plan_ms=%.2f\n", planned ? 1 : 0,
                              static_cast<long long>(n), plan.exact.size(), ms_since(t0));
             }
-            if (planned && 2 * plan.exact.size() <= static_cast<size_t>(n)) {
+            if (planned && 2 * plan.exact.size() <= static_cast<size_t>(n) && device_path_eligible(*update)) {
                 if (status == nullptr) {
                     status_local.assign(n, 0);
                     status = status_local.data();
                 }
-                UpdateData none{};
+                UpdateData none{}; // the branch updates are in the plan; what remains are the load / generator updates
                 none.n_scenarios = n;
+                none.sym_gen = update->sym_gen;
+                none.asym_gen = update->asym_gen;
+                none.sym_load = update->sym_load;
+                none.asym_load = update->asym_load;
                 outage_plan_ = &plan;
                 timing[0] += ms_since(t0);
                 int64_t r = -1;

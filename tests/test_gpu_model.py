@@ -277,6 +277,29 @@ def test_mixed_outage_batch_matches_oracle():
         _compare_with_oracle(res, ref, n_scn)
 
 
+@pytest.mark.parametrize("sym", [True, False])
+def test_outages_with_a_load_profile_match_oracle(sym):
+    """contingency x load profile: every scenario switches a line AND carries its own loads; the outages share the base
+    pattern, the load updates are applied on the device like in any load batch"""
+    grid = pgm_b200.FictionalGrid(seed=0, n_node_total_specified=300, n_connection_per_lv_feeder=5, n_lv_feeder=4, n_node_per_mv_feeder=5,
+                                  n_mv_feeder=3, has_mv_ring=True, has_lv_ring=True)
+    n_scn = 14
+    update = grid.batch_update(n_scn, seed=4)
+    lines = grid.input_data["line"]
+    upd = pgm_b200.structs.initialize_array("update", "line", (n_scn, 1))
+    upd["id"][:, 0] = lines["id"][(np.arange(n_scn) * 9 + 2) % len(lines)]
+    upd["from_status"][:, 0] = 0
+    upd["to_status"][:, 0] = 0
+    update["line"] = upd
+    model = pgm_b200.PowerGridModel(grid.input_data)
+    launches0 = int(pgm_b200.lib().pgmb_kernel_launch_count())
+    res = model.calculate_power_flow(symmetric=sym, update_data=update)
+    assert int(pgm_b200.lib().pgmb_kernel_launch_count()) - launches0 < 4 * n_scn
+    ref = orc.Model(grid.input_data).calculate(sym=sym, update=update, threading=0)
+    assert ref["n_failed"] == 0 and np.array_equal(model.n_iter, ref["n_iter"])
+    _compare_with_oracle(res, ref, n_scn)
+
+
 @pytest.mark.parametrize("exact", [False, True])
 @pytest.mark.parametrize("threads", [1, 4])
 def test_branch_switching_batch_on_host_threads(threads, exact, monkeypatch):
