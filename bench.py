@@ -120,7 +120,7 @@ def run_reference(args, rank, world):
 def other_configs(pgm_b200, np, device):
     """kernel milliseconds (CUDA events, second of two runs) of BASELINE configs 3 and 4 on one GPU; informational"""
 
-    def staged_engine(grid, sym, n_scn, seed):
+    def staged_engine(grid, sym, n_scn, seed, method=None):
         model = pgm_b200.PowerGridModel(grid.input_data)
         eng = pgm_b200.Engine(symmetric=sym, phase_shift=model.math_real(0, sym, "phase_shift"),
                               branch_bus_idx=model.math_index(0, "branch_bus_idx"), sources_per_bus=model.math_index(0, "sources_per_bus"),
@@ -129,7 +129,7 @@ def other_configs(pgm_b200, np, device):
         eng.set_param(model.math_real(0, sym, "branch_param").view(np.complex128), model.math_real(0, sym, "shunt_param").view(np.complex128),
                       model.math_real(0, sym, "source_param").view(np.complex128))
         s_inj, u_ref = model.batch_pf_input(grid.batch_update(n_scn, seed=seed), symmetric=sym)
-        eng.stage(s_inj, u_ref)
+        eng.stage(s_inj, u_ref, method=method)
         return eng
 
     out = {}
@@ -138,8 +138,8 @@ def other_configs(pgm_b200, np, device):
     ms = [eng.solve_staged(err_tol=ERR_TOL, max_iter=MAX_ITER) for _ in range(2)][-1]
     out["configs[2] ringed grid, asymmetric newton_raphson, 1000 scenarios"] = {"kernel_ms": ms, "scenarios_per_s": 1000 / ms * 1e3}
     radial = pgm_b200.FictionalGrid(seed=0, **pgm_b200.BENCHMARK_OPTION)
-    eng = staged_engine(radial, True, 12500, 0)
     for method in ("iterative_current", "linear"):
+        eng = staged_engine(radial, True, 12500, 0, method)
         ms = [eng.solve_staged(method=method, err_tol=ERR_TOL, max_iter=MAX_ITER) for _ in range(2)][-1]
         out[f"configs[3] radial grid, {method}, 12500 scenarios (one GPU's share of 100k over 8)"] = {
             "kernel_ms": ms, "scenarios_per_s": 12500 / ms * 1e3}

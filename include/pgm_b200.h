@@ -115,6 +115,11 @@ typedef struct pgmb_pf_input {
      * the status of each load_gen per scenario (PowerFlowInput::load_gen_status), NULL = all on */
     const double* voltage_regulator;
     const int8_t* load_gen_status; /* [n_scenarios][n_load_gen] */
+    /* optional: the method the staged batch will be solved with (PGMB_METHOD_*).  The tile width of the device layout is chosen
+     * at staging time and iterative-current batches prefer another width than Newton-Raphson ones.  method_hint is only read
+     * when method_hint_valid != 0 (zero-initialised structs keep the default). */
+    int32_t method_hint;
+    int32_t method_hint_valid;
 } pgmb_pf_input;
 
 /* SolverOutput<sym> for n_scenarios scenarios (calculation_parameters.hpp:338-350); any pointer may be NULL */

@@ -71,7 +71,8 @@ class RunOptionsC(C.Structure):
 
 class PfInputC(C.Structure):
     _fields_ = [("n_scenarios", C.c_int64), ("source_u_ref", C.c_void_p), ("source_is_shared", C.c_int32),
-                ("s_injection", C.c_void_p), ("voltage_regulator", C.c_void_p), ("load_gen_status", C.c_void_p)]
+                ("s_injection", C.c_void_p), ("voltage_regulator", C.c_void_p), ("load_gen_status", C.c_void_p),
+                ("method_hint", C.c_int32), ("method_hint_valid", C.c_int32)]
 
 
 class SolverOutputC(C.Structure):

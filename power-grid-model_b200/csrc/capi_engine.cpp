@@ -40,7 +40,8 @@ MathTopology topology_from_view(pgmb_math_topology const& t) {
 
 namespace {
 PfInputView view_of(pgmb_pf_input const& in) {
-    return {in.n_scenarios, in.source_u_ref, in.source_is_shared != 0, in.s_injection, in.voltage_regulator, in.load_gen_status};
+    return {in.n_scenarios, in.source_u_ref, in.source_is_shared != 0, in.s_injection, in.voltage_regulator, in.load_gen_status,
+            in.method_hint_valid != 0 ? in.method_hint : -128};
 }
 SolverOutputView view_of(pgmb_solver_output const& o) {
     return {o.u, o.bus_injection, o.branch, o.source, o.shunt, o.load_gen, o.status, o.n_iter, o.max_dev, o.voltage_regulator};

@@ -96,6 +96,7 @@ struct PfInputView {
     double const* s_injection;
     double const* voltage_regulator{nullptr}; // [n_regulator][4] status, u_ref, q_min, q_max (shared by the scenarios)
     int8_t const* load_gen_status{nullptr};   // [n_scenarios][n_load_gen], null = all on
+    int32_t method_hint{-128};                // method the batch will be solved with (affects the tile width), -128 = unknown
 };
 struct SolverOutputView {
     double *u, *bus_injection, *branch, *source, *shunt, *load_gen;
@@ -117,6 +118,9 @@ class Engine {
     // voltage regulator parameters of the next solves: [n_regulator][4] status, u_ref, q_min, q_max
     void set_regulators(double const* param);
     bool has_regulators() const { return !topo_.load_gen_regulator.empty(); }
+    // calculation method the next staged batch will be solved with (PGMB_METHOD_*; 0 linear, 3 / 4 iterative current): the
+    // tile width is chosen when the batch is staged, and the iterative-current kernels run two thread blocks per SM
+    void set_method_hint(int method) { method_hint_ = method; }
     // device pipeline: Q allocation of the regulated generators of a solved chunk (rewrites their Q in the injection buffer) and
     // the per-regulator flags [n_scn][n_regulator][2] for the output kernel
     void launch_regulator_apply(DevBatch const& view, int8_t* out_reg, cudaStream_t st);
@@ -182,6 +186,7 @@ class Engine {
     DevStructure ds_{};
 
     // batch buffers
+    int method_hint_{1};
     int tile_width_{8};
     int n_slot_{64};
     DevBuf<double> d_side_, d_wide_terms_, d_wide_rhs_, d_wide_sum_;

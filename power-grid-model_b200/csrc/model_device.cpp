@@ -381,6 +381,7 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
     // ---- chunk pipeline: H2D of the raw update rows -> apply -> solve -> output structs -> D2H, one stream per chunk, so the
     //      PCIe transfers of one chunk overlap the kernels of the others (both copy engines + the SMs busy at once) ----
     t0 = Clock::now();
+    e.set_method_hint(opt.method);
     e.stage_device(n_scn, uref.data(), uref_shared);
     if (e.has_regulators()) { // VoltageRegulator::calc_param of the permanent state (regulator updates take the host route)
         std::vector<double> rp(m.n_voltage_regulator() * 4, 0.0);

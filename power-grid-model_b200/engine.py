@@ -81,7 +81,7 @@ class Engine:
         return np.ctypeslib.as_array(ptr, shape=(n.value,)).copy().view(np.complex128).reshape(-1, self.B, self.B)
 
     # -- running ---------------------------------------------------------------------------------------------------
-    def _input(self, s_injection, source_u_ref, voltage_regulator=None, load_gen_status=None):
+    def _input(self, s_injection, source_u_ref, voltage_regulator=None, load_gen_status=None, method=None):
         s = np.ascontiguousarray(np.asarray(s_injection, dtype=np.complex128))
         if s.ndim == 2 and self.B == 1:
             s = s.reshape(s.shape[0], s.shape[1], 1)
@@ -98,7 +98,8 @@ class Engine:
                 ls = np.ascontiguousarray(np.asarray(load_gen_status, dtype=np.int8).reshape(n_scn, self.n_load_gen))
         self._in_keep = (s, u, vr, ls)
         return _lib.PfInputC(n_scn, u.ctypes.data, int(shared), s.ctypes.data, vr.ctypes.data if vr is not None else None,
-                             ls.ctypes.data if ls is not None else None), n_scn
+                             ls.ctypes.data if ls is not None else None, _lib.METHODS[method] if method else 0,
+                             1 if method else 0), n_scn
 
     def _output(self, n_scn, full=True):
         B = self.B
@@ -125,14 +126,15 @@ class Engine:
             voltage_regulator=None, load_gen_status=None):
         """s_injection: (n_scn, n_load_gen[, B]) complex; source_u_ref: (n_source,) shared or (n_scn, n_source).
         Returns dict of arrays; failed scenarios are flagged in out['status'] (no exception)."""
-        inp, n_scn = self._input(s_injection, source_u_ref, voltage_regulator, load_gen_status)
+        inp, n_scn = self._input(s_injection, source_u_ref, voltage_regulator, load_gen_status, method)
         out, outc = self._output(n_scn, full_output)
         opt = _lib.RunOptionsC(_lib.METHODS[method], err_tol, max_iter)
         check(lib().pgmb_engine_run(self._h, C.byref(opt), C.byref(inp), C.byref(outc)), allow_batch=True)
         return out
 
-    def stage(self, s_injection, source_u_ref, voltage_regulator=None, load_gen_status=None):
-        inp, n_scn = self._input(s_injection, source_u_ref, voltage_regulator, load_gen_status)
+    def stage(self, s_injection, source_u_ref, voltage_regulator=None, load_gen_status=None, method=None):
+        """method: the method the staged batch will be solved with (optional hint for the tile width)"""
+        inp, n_scn = self._input(s_injection, source_u_ref, voltage_regulator, load_gen_status, method)
         check(lib().pgmb_engine_stage(self._h, C.byref(inp)))
         self._n_staged = n_scn
 
