@@ -1,0 +1,107 @@
+/* The reference's own C API names for the power-flow path, exported by libpgm_b200.so.
+ *
+ * A C client (or the reference's ctypes wrapper restricted to row-based buffers) that drives power flow through
+ * `PGM_create_handle / PGM_create_options / PGM_create_dataset_* / PGM_create_model / PGM_calculate` links against this library
+ * unchanged: same symbol names, argument meaning and error behaviour as
+ *   power_grid_model_c/include/power_grid_model_c/handle.h:32-115, options.h:38-138, dataset.h:140-320, model.h:33-125
+ * of the reference.  Scope = what the engine builds:
+ *   - calculation type power_flow; methods default / newton_raphson / linear / iterative_current / linear_current; symmetric and
+ *     asymmetric; single and batch (one batch dimension);
+ *   - row-based buffers ("attribute" / columnar buffers and cartesian-product batches are answered with PGM_regular_error);
+ *   - components: node, line, asym_line, generic_branch, transformer, shunt, source, sym_gen, asym_gen, sym_load, asym_load,
+ *     voltage_regulator; sensors and faults may be present in the input dataset and are ignored by power flow like in the
+ *     reference; any other component is PGM_regular_error at PGM_create_model;
+ *   - tap_changing_strategy: any valid value (the model cannot hold a transformer_tap_regulator, so it is the plain power flow).
+ * Everything else of the reference's C API (meta-data tables, serialization, writable datasets) is outside the hot path and not
+ * provided.  There is no CPU fallback: PGM_calculate on a host without a CUDA device reports PGM_regular_error.
+ */
+#ifndef PGM_B200_CAPI_H
+#define PGM_B200_CAPI_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PGM_API __attribute__((visibility("default")))
+
+typedef int64_t PGM_Idx;
+typedef int32_t PGM_ID;
+typedef struct PGM_Handle PGM_Handle;
+typedef struct PGM_Options PGM_Options;
+typedef struct PGM_ConstDataset PGM_ConstDataset;
+typedef struct PGM_MutableDataset PGM_MutableDataset;
+typedef struct PGM_PowerGridModel PGM_PowerGridModel;
+
+enum PGM_CalculationType { PGM_power_flow = 0, PGM_state_estimation = 1, PGM_short_circuit = 2 };
+enum PGM_CalculationMethod {
+    PGM_default_method = -128,
+    PGM_linear = 0,
+    PGM_newton_raphson = 1,
+    PGM_iterative_linear = 2,
+    PGM_iterative_current = 3,
+    PGM_linear_current = 4,
+    PGM_iec60909 = 5
+};
+enum PGM_SymmetryType { PGM_asymmetric = 0, PGM_symmetric = 1 };
+enum PGM_ErrorCode { PGM_no_error = 0, PGM_regular_error = 1, PGM_batch_error = 2, PGM_serialization_error = 3 };
+
+/* handle.h */
+PGM_API PGM_Handle* PGM_create_handle(void);
+PGM_API void PGM_destroy_handle(PGM_Handle* handle);
+PGM_API PGM_Idx PGM_error_code(PGM_Handle const* handle);
+PGM_API char const* PGM_error_message(PGM_Handle const* handle);
+PGM_API PGM_Idx PGM_n_failed_scenarios(PGM_Handle const* handle);
+PGM_API PGM_Idx const* PGM_failed_scenarios(PGM_Handle const* handle);
+PGM_API char const** PGM_batch_errors(PGM_Handle const* handle);
+PGM_API void PGM_clear_error(PGM_Handle* handle);
+PGM_API char const* PGM_version(void);
+
+/* options.h */
+PGM_API PGM_Options* PGM_create_options(PGM_Handle* handle);
+PGM_API void PGM_destroy_options(PGM_Options* opt);
+PGM_API void PGM_set_calculation_type(PGM_Handle* handle, PGM_Options* opt, PGM_Idx type);
+PGM_API void PGM_set_calculation_method(PGM_Handle* handle, PGM_Options* opt, PGM_Idx method);
+PGM_API void PGM_set_symmetric(PGM_Handle* handle, PGM_Options* opt, PGM_Idx sym);
+PGM_API void PGM_set_err_tol(PGM_Handle* handle, PGM_Options* opt, double err_tol);
+PGM_API void PGM_set_max_iter(PGM_Handle* handle, PGM_Options* opt, PGM_Idx max_iter);
+PGM_API void PGM_set_threading(PGM_Handle* handle, PGM_Options* opt, PGM_Idx threading);
+PGM_API void PGM_set_short_circuit_voltage_scaling(PGM_Handle* handle, PGM_Options* opt, PGM_Idx short_circuit_voltage_scaling);
+PGM_API void PGM_set_tap_changing_strategy(PGM_Handle* handle, PGM_Options* opt, PGM_Idx tap_changing_strategy);
+PGM_API void PGM_set_experimental_features(PGM_Handle* handle, PGM_Options* opt, PGM_Idx experimental_features);
+
+/* dataset.h (row-based buffers) */
+PGM_API PGM_ConstDataset* PGM_create_dataset_const(PGM_Handle* handle, char const* dataset, PGM_Idx is_batch, PGM_Idx batch_size);
+PGM_API PGM_ConstDataset* PGM_create_dataset_const_from_mutable(PGM_Handle* handle, PGM_MutableDataset const* mutable_dataset);
+PGM_API void PGM_destroy_dataset_const(PGM_ConstDataset* dataset);
+PGM_API void PGM_dataset_const_add_buffer(PGM_Handle* handle, PGM_ConstDataset* dataset, char const* component,
+                                          PGM_Idx elements_per_scenario, PGM_Idx total_elements, PGM_Idx const* indptr,
+                                          void const* data);
+PGM_API void PGM_dataset_const_add_attribute_buffer(PGM_Handle* handle, PGM_ConstDataset* dataset, char const* component,
+                                                    char const* attribute, void const* data);
+PGM_API void PGM_dataset_const_set_next_cartesian_product_dimension(PGM_Handle* handle, PGM_ConstDataset* dataset,
+                                                                    PGM_ConstDataset const* next_dataset);
+PGM_API PGM_MutableDataset* PGM_create_dataset_mutable(PGM_Handle* handle, char const* dataset, PGM_Idx is_batch,
+                                                       PGM_Idx batch_size);
+PGM_API void PGM_destroy_dataset_mutable(PGM_MutableDataset* dataset);
+PGM_API void PGM_dataset_mutable_add_buffer(PGM_Handle* handle, PGM_MutableDataset* dataset, char const* component,
+                                            PGM_Idx elements_per_scenario, PGM_Idx total_elements, PGM_Idx const* indptr,
+                                            void* data);
+PGM_API void PGM_dataset_mutable_add_attribute_buffer(PGM_Handle* handle, PGM_MutableDataset* dataset, char const* component,
+                                                      char const* attribute, void* data);
+
+/* model.h */
+PGM_API PGM_PowerGridModel* PGM_create_model(PGM_Handle* handle, double system_frequency, PGM_ConstDataset const* input_dataset);
+PGM_API void PGM_update_model(PGM_Handle* handle, PGM_PowerGridModel* model, PGM_ConstDataset const* update_dataset);
+PGM_API PGM_PowerGridModel* PGM_copy_model(PGM_Handle* handle, PGM_PowerGridModel const* model);
+PGM_API void PGM_get_indexer(PGM_Handle* handle, PGM_PowerGridModel const* model, char const* component, PGM_Idx size,
+                             PGM_ID const* ids, PGM_Idx* indexer);
+PGM_API void PGM_calculate(PGM_Handle* handle, PGM_PowerGridModel* model, PGM_Options const* opt,
+                           PGM_MutableDataset const* output_dataset, PGM_ConstDataset const* batch_dataset);
+PGM_API void PGM_destroy_model(PGM_PowerGridModel* model);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGM_B200_CAPI_H */

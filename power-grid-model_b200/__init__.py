@@ -5,3 +5,4 @@ from .engine import Engine  # noqa: F401
 from .fictional_grid import BENCHMARK_OPTION, FictionalGrid  # noqa: F401
 from .model import PowerGridModel  # noqa: F401
 from . import distributed  # noqa: F401,E402
+from . import pgm_core  # noqa: F401,E402

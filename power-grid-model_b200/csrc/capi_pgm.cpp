@@ -1,0 +1,465 @@
+// The reference's own C API names for the power-flow path (include/pgm_b200_capi.h): handle, options, row-based datasets,
+// model create / update / copy / get_indexer / calculate.  A thin adapter: every call lands in the same pgmb::Model the
+// pgmb_model_* seam drives, so PGM_calculate runs the CUDA pipeline and nothing else (no CPU fallback).
+//   handle    power_grid_model_c/src/handle.cpp:29-62, handle.hpp:20-82 (error code / message / failed scenarios, cleared by
+//             every call that takes the handle)
+//   options   power_grid_model_c/src/options.cpp, options.hpp:16-27 (defaults)
+//   datasets  power_grid_model_c/src/dataset.cpp:96-190 ; auxiliary/dataset.hpp:233-243, 587-625 (integrity checks, messages)
+//   model     power_grid_model_c/src/model.cpp:48-75, 188-204 (single batch dimension), 349-359
+#include "../../include/pgm_b200_capi.h"
+#include "capi_common.hpp"
+#include "model.hpp"
+
+#include <cstdlib>
+#include <cstring>
+
+using namespace pgmb;
+
+struct PGM_Handle {
+    PGM_Idx err_code{PGM_no_error};
+    std::string err_msg;
+    std::vector<PGM_Idx> failed_scenarios;
+    std::vector<std::string> batch_errs;
+    mutable std::vector<char const*> batch_errs_c_str;
+};
+
+struct PGM_Options {
+    PGM_Idx calculation_type{PGM_power_flow};
+    PGM_Idx calculation_method{PGM_default_method};
+    PGM_Idx symmetric{1};
+    double err_tol{1e-8};
+    PGM_Idx max_iter{20};
+    PGM_Idx threading{-1};
+    PGM_Idx short_circuit_voltage_scaling{1};
+    PGM_Idx tap_changing_strategy{0};
+    PGM_Idx experimental_features{0};
+};
+
+namespace {
+
+struct DatasetError : std::runtime_error {
+    explicit DatasetError(std::string const& msg) : std::runtime_error("Dataset error: " + msg) {}
+};
+struct CalculationError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+struct DatasetBuffer {
+    std::string component;
+    PGM_Idx elements_per_scenario;
+    PGM_Idx total_elements;
+    PGM_Idx const* indptr;
+    void* data;
+};
+
+struct Dataset {
+    std::string name;
+    bool is_batch;
+    PGM_Idx batch_size;
+    std::vector<DatasetBuffer> buffers;
+
+    Dataset(char const* dataset, PGM_Idx batch, PGM_Idx size) : is_batch{batch != 0}, batch_size{size} {
+        if (dataset == nullptr) throw InvalidArgument("null argument");
+        name = dataset;
+        if (name != "input" && name != "update" && name != "sym_output" && name != "asym_output" && name != "sc_output") {
+            throw std::out_of_range("Cannot find dataset with name: " + name + "!\n");
+        }
+        if (batch_size < 0) throw DatasetError("Batch size cannot be negative!\n");
+        if (!is_batch && batch_size != 1) throw DatasetError("For non-batch dataset, batch size should be one!\n");
+    }
+
+    DatasetBuffer const* find(std::string const& component) const {
+        for (auto const& b : buffers) {
+            if (b.component == component) return &b;
+        }
+        return nullptr;
+    }
+
+    void add_buffer(char const* component, PGM_Idx elements_per_scenario, PGM_Idx total_elements, PGM_Idx const* indptr,
+                    void* data, bool check_indptr) {
+        if (component == nullptr) throw InvalidArgument("null argument");
+        if (!known_component(component)) throw std::out_of_range("Cannot find component with name: " + std::string(component) + "!\n");
+        if (find(component) != nullptr) throw DatasetError("Cannot have duplicated components!\n");
+        if (elements_per_scenario >= 0 && elements_per_scenario * batch_size != total_elements) {
+            throw DatasetError("For a uniform buffer, total_elements should be equal to elements_per_scenario * batch_size!\n");
+        }
+        if (elements_per_scenario < 0) {
+            if (indptr == nullptr) throw DatasetError("For a non-uniform buffer, indptr should be supplied!\n");
+            if (check_indptr) {
+                if (indptr[0] != 0 || indptr[batch_size] != total_elements) {
+                    throw DatasetError("For a non-uniform buffer, indptr should begin with 0 and end with total_elements!\n");
+                }
+                for (PGM_Idx s = 0; s != batch_size; ++s) {
+                    if (indptr[s] > indptr[s + 1]) throw DatasetError("For a non-uniform buffer, indptr should be non-decreasing!\n");
+                }
+            }
+        } else if (indptr != nullptr) {
+            throw DatasetError("For a uniform buffer, indptr should be nullptr!\n");
+        }
+        buffers.push_back({component, elements_per_scenario, total_elements, indptr, data});
+    }
+
+    // every component of the reference's dataset definitions (all_components.hpp:36-39)
+    static bool known_component(std::string const& c) {
+        static char const* const names[] = {"node", "line", "asym_line", "link", "generic_branch", "transformer",
+                                            "three_winding_transformer", "shunt", "source", "sym_gen", "asym_gen", "sym_load",
+                                            "asym_load", "sym_power_sensor", "asym_power_sensor", "sym_voltage_sensor",
+                                            "asym_voltage_sensor", "sym_current_sensor", "asym_current_sensor", "fault",
+                                            "transformer_tap_regulator", "voltage_regulator"};
+        for (auto const* n : names) {
+            if (c == n) return true;
+        }
+        return false;
+    }
+};
+
+// power flow does not read these (sensors: state estimation; faults: short circuit); they may sit in the input dataset
+bool ignored_by_power_flow(std::string const& c) {
+    return c == "fault" || c.find("_sensor") != std::string::npos;
+}
+
+void clear(PGM_Handle* handle) {
+    if (handle != nullptr) *handle = PGM_Handle{};
+}
+
+// Lippincott wrapper like call_with_catch (handle.hpp:62-80): clear the handle, run, translate any exception
+template <class F> auto call(PGM_Handle* handle, F&& f) noexcept -> decltype(f()) {
+    using R = decltype(f());
+    try {
+        clear(handle);
+        return f();
+    } catch (std::exception const& e) {
+        if (handle != nullptr) {
+            handle->err_code = PGM_regular_error;
+            handle->err_msg = e.what();
+        }
+    } catch (...) {
+        if (handle != nullptr) {
+            handle->err_code = PGM_regular_error;
+            handle->err_msg = "Unknown error!\n";
+        }
+    }
+    if constexpr (!std::is_void_v<R>) return R{};
+}
+
+template <class T> T& deref(T* p) {
+    if (p == nullptr) throw InvalidArgument("Received null pointer where a valid pointer was expected.\n");
+    return *p;
+}
+
+ComponentBuffer buffer_of(DatasetBuffer const& b) {
+    if (b.elements_per_scenario < 0) return {-1, b.indptr, b.data};
+    return {b.elements_per_scenario, nullptr, b.data};
+}
+
+int device_ordinal() {
+    char const* env = std::getenv("PGMB_DEVICE");
+    return env != nullptr ? std::atoi(env) : 0;
+}
+
+UpdateData update_of(Dataset const& ds) {
+    if (ds.name != "update") throw DatasetError("An update dataset is expected, got '" + ds.name + "'!\n");
+    UpdateData u{};
+    u.n_scenarios = ds.batch_size;
+    for (auto const& b : ds.buffers) {
+        if (b.total_elements == 0) continue;
+        ComponentBuffer const cb = buffer_of(b);
+        if (b.component == "line") u.line = cb;
+        else if (b.component == "asym_line") u.asym_line = cb;
+        else if (b.component == "generic_branch") u.generic_branch = cb;
+        else if (b.component == "transformer") u.transformer = cb;
+        else if (b.component == "shunt") u.shunt = cb;
+        else if (b.component == "source") u.source = cb;
+        else if (b.component == "sym_gen") u.sym_gen = cb;
+        else if (b.component == "asym_gen") u.asym_gen = cb;
+        else if (b.component == "sym_load") u.sym_load = cb;
+        else if (b.component == "asym_load") u.asym_load = cb;
+        else if (b.component == "voltage_regulator") u.voltage_regulator = cb;
+        else if (ignored_by_power_flow(b.component)) continue;
+        else throw InvalidArgument("component '" + b.component + "' cannot be updated by pgm_b200\n");
+    }
+    return u;
+}
+
+} // namespace
+
+struct PGM_ConstDataset : Dataset {
+    using Dataset::Dataset;
+};
+struct PGM_MutableDataset : Dataset {
+    using Dataset::Dataset;
+};
+struct PGM_PowerGridModel {
+    std::unique_ptr<Model> model;
+};
+
+extern "C" {
+
+// ---- handle --------------------------------------------------------------------------------------------------------
+PGM_Handle* PGM_create_handle(void) {
+    try {
+        return new PGM_Handle{};
+    } catch (...) {
+        return nullptr;
+    }
+}
+void PGM_destroy_handle(PGM_Handle* handle) { delete handle; }
+PGM_Idx PGM_error_code(PGM_Handle const* handle) { return handle != nullptr ? handle->err_code : 0; }
+char const* PGM_error_message(PGM_Handle const* handle) { return handle != nullptr ? handle->err_msg.c_str() : nullptr; }
+PGM_Idx PGM_n_failed_scenarios(PGM_Handle const* handle) {
+    return handle != nullptr ? static_cast<PGM_Idx>(handle->failed_scenarios.size()) : 0;
+}
+PGM_Idx const* PGM_failed_scenarios(PGM_Handle const* handle) {
+    return handle != nullptr ? handle->failed_scenarios.data() : nullptr;
+}
+char const** PGM_batch_errors(PGM_Handle const* handle) {
+    if (handle == nullptr) return nullptr;
+    handle->batch_errs_c_str.clear();
+    for (auto const& s : handle->batch_errs) handle->batch_errs_c_str.push_back(s.c_str());
+    return handle->batch_errs_c_str.data();
+}
+void PGM_clear_error(PGM_Handle* handle) { clear(handle); }
+char const* PGM_version(void) { return "pgm_b200 0.1 (power-flow path of power-grid-model on sm_100a)"; }
+
+// ---- options -------------------------------------------------------------------------------------------------------
+PGM_Options* PGM_create_options(PGM_Handle* handle) {
+    return call(handle, [] { return new PGM_Options{}; });
+}
+void PGM_destroy_options(PGM_Options* opt) { delete opt; }
+void PGM_set_calculation_type(PGM_Handle* handle, PGM_Options* opt, PGM_Idx type) {
+    call(handle, [&] { deref(opt).calculation_type = type; });
+}
+void PGM_set_calculation_method(PGM_Handle* handle, PGM_Options* opt, PGM_Idx method) {
+    call(handle, [&] { deref(opt).calculation_method = method; });
+}
+void PGM_set_symmetric(PGM_Handle* handle, PGM_Options* opt, PGM_Idx sym) {
+    call(handle, [&] { deref(opt).symmetric = sym; });
+}
+void PGM_set_err_tol(PGM_Handle* handle, PGM_Options* opt, double err_tol) {
+    call(handle, [&] { deref(opt).err_tol = err_tol; });
+}
+void PGM_set_max_iter(PGM_Handle* handle, PGM_Options* opt, PGM_Idx max_iter) {
+    call(handle, [&] { deref(opt).max_iter = max_iter; });
+}
+void PGM_set_threading(PGM_Handle* handle, PGM_Options* opt, PGM_Idx threading) {
+    call(handle, [&] { deref(opt).threading = threading; });
+}
+void PGM_set_short_circuit_voltage_scaling(PGM_Handle* handle, PGM_Options* opt, PGM_Idx short_circuit_voltage_scaling) {
+    call(handle, [&] { deref(opt).short_circuit_voltage_scaling = short_circuit_voltage_scaling; });
+}
+void PGM_set_tap_changing_strategy(PGM_Handle* handle, PGM_Options* opt, PGM_Idx tap_changing_strategy) {
+    call(handle, [&] { deref(opt).tap_changing_strategy = tap_changing_strategy; });
+}
+void PGM_set_experimental_features(PGM_Handle* handle, PGM_Options* opt, PGM_Idx experimental_features) {
+    call(handle, [&] { deref(opt).experimental_features = experimental_features; });
+}
+
+// ---- datasets (row-based) ------------------------------------------------------------------------------------------
+PGM_ConstDataset* PGM_create_dataset_const(PGM_Handle* handle, char const* dataset, PGM_Idx is_batch, PGM_Idx batch_size) {
+    return call(handle, [&] { return new PGM_ConstDataset{dataset, is_batch, batch_size}; });
+}
+PGM_ConstDataset* PGM_create_dataset_const_from_mutable(PGM_Handle* handle, PGM_MutableDataset const* mutable_dataset) {
+    return call(handle, [&] {
+        Dataset const& src = deref(mutable_dataset);
+        auto* ds = new PGM_ConstDataset{src.name.c_str(), src.is_batch ? 1 : 0, src.batch_size};
+        ds->buffers = src.buffers;
+        return ds;
+    });
+}
+void PGM_destroy_dataset_const(PGM_ConstDataset* dataset) { delete dataset; }
+void PGM_dataset_const_add_buffer(PGM_Handle* handle, PGM_ConstDataset* dataset, char const* component,
+                                  PGM_Idx elements_per_scenario, PGM_Idx total_elements, PGM_Idx const* indptr,
+                                  void const* data) {
+    call(handle, [&] {
+        deref(dataset).add_buffer(component, elements_per_scenario, total_elements, indptr, const_cast<void*>(data), true);
+    });
+}
+void PGM_dataset_const_add_attribute_buffer(PGM_Handle* handle, PGM_ConstDataset*, char const*, char const*, void const*) {
+    call(handle, [] { throw DatasetError("pgm_b200 takes row-based buffers only (no attribute / columnar buffers)!\n"); });
+}
+void PGM_dataset_const_set_next_cartesian_product_dimension(PGM_Handle* handle, PGM_ConstDataset*, PGM_ConstDataset const*) {
+    call(handle, [] { throw DatasetError("pgm_b200 takes one batch dimension (no cartesian product of update datasets)!\n"); });
+}
+PGM_MutableDataset* PGM_create_dataset_mutable(PGM_Handle* handle, char const* dataset, PGM_Idx is_batch, PGM_Idx batch_size) {
+    return call(handle, [&] { return new PGM_MutableDataset{dataset, is_batch, batch_size}; });
+}
+void PGM_destroy_dataset_mutable(PGM_MutableDataset* dataset) { delete dataset; }
+void PGM_dataset_mutable_add_buffer(PGM_Handle* handle, PGM_MutableDataset* dataset, char const* component,
+                                    PGM_Idx elements_per_scenario, PGM_Idx total_elements, PGM_Idx const* indptr, void* data) {
+    call(handle, [&] { deref(dataset).add_buffer(component, elements_per_scenario, total_elements, indptr, data, false); });
+}
+void PGM_dataset_mutable_add_attribute_buffer(PGM_Handle* handle, PGM_MutableDataset*, char const*, char const*, void*) {
+    call(handle, [] { throw DatasetError("pgm_b200 takes row-based buffers only (no attribute / columnar buffers)!\n"); });
+}
+
+// ---- model ---------------------------------------------------------------------------------------------------------
+PGM_PowerGridModel* PGM_create_model(PGM_Handle* handle, double system_frequency, PGM_ConstDataset const* input_dataset) {
+    return call(handle, [&] {
+        Dataset const& ds = deref(input_dataset);
+        if (ds.name != "input" || ds.is_batch) throw DatasetError("PGM_create_model takes a single (non-batch) input dataset!\n");
+        InputData in{};
+        for (auto const& b : ds.buffers) {
+            if (b.total_elements == 0 || ignored_by_power_flow(b.component)) continue;
+            if (b.data == nullptr) throw InvalidArgument("Received null pointer where a valid pointer was expected.\n");
+            ComponentBuffer const cb{b.total_elements, nullptr, b.data};
+            if (b.component == "node") in.node = cb;
+            else if (b.component == "line") in.line = cb;
+            else if (b.component == "asym_line") in.asym_line = cb;
+            else if (b.component == "generic_branch") in.generic_branch = cb;
+            else if (b.component == "transformer") in.transformer = cb;
+            else if (b.component == "shunt") in.shunt = cb;
+            else if (b.component == "source") in.source = cb;
+            else if (b.component == "sym_gen") in.sym_gen = cb;
+            else if (b.component == "asym_gen") in.asym_gen = cb;
+            else if (b.component == "sym_load") in.sym_load = cb;
+            else if (b.component == "asym_load") in.asym_load = cb;
+            else if (b.component == "voltage_regulator") in.voltage_regulator = cb;
+            else throw InvalidArgument("component '" + b.component + "' is not built by pgm_b200 (power-flow path only)\n");
+        }
+        auto m = std::make_unique<PGM_PowerGridModel>();
+        m->model = std::make_unique<Model>(system_frequency, in);
+        return m.release();
+    });
+}
+
+void PGM_update_model(PGM_Handle* handle, PGM_PowerGridModel* model, PGM_ConstDataset const* update_dataset) {
+    call(handle, [&] {
+        Dataset const& ds = deref(update_dataset);
+        if (ds.is_batch) throw DatasetError("PGM_update_model takes a single (non-batch) update dataset!\n");
+        deref(model).model->update_permanent(update_of(ds));
+    });
+}
+
+PGM_PowerGridModel* PGM_copy_model(PGM_Handle* handle, PGM_PowerGridModel const* model) {
+    return call(handle, [&] {
+        auto m = std::make_unique<PGM_PowerGridModel>();
+        m->model = deref(model).model->clone();
+        return m.release();
+    });
+}
+
+void PGM_get_indexer(PGM_Handle* handle, PGM_PowerGridModel const* model, char const* component, PGM_Idx size,
+                     PGM_ID const* ids, PGM_Idx* indexer) {
+    call(handle, [&] {
+        if (component == nullptr || (size != 0 && (ids == nullptr || indexer == nullptr))) {
+            throw InvalidArgument("Received null pointer where a valid pointer was expected.\n");
+        }
+        deref(model).model->get_indexer(component, ids, size, indexer);
+    });
+}
+
+void PGM_calculate(PGM_Handle* handle, PGM_PowerGridModel* model, PGM_Options const* opt,
+                   PGM_MutableDataset const* output_dataset, PGM_ConstDataset const* batch_dataset) {
+    std::vector<int32_t> status;
+    bool batch_failed = false;
+    call(handle, [&] {
+        Model& m = *deref(model).model;
+        PGM_Options const& o = deref(opt);
+        Dataset const& out_ds = deref(output_dataset);
+        if (o.calculation_type < PGM_power_flow || o.calculation_type > PGM_short_circuit) {
+            throw InvalidArgument("CalculationType is not implemented for #" + std::to_string(o.calculation_type) + "!\n");
+        }
+        if (o.calculation_type != PGM_power_flow) {
+            throw CalculationError("pgm_b200 provides calculation type power_flow only (state estimation and short circuit are "
+                                   "outside the accelerated path)\n");
+        }
+        // automatic tap changing acts on transformer_tap_regulator components, which PGM_create_model of this library refuses:
+        // with none in the model every valid strategy is the plain power flow (optimizer/tap_position_optimizer.hpp)
+        if (o.tap_changing_strategy < 0 || o.tap_changing_strategy > 4) {
+            throw InvalidArgument("get_optimizer_type is not implemented for #" + std::to_string(o.tap_changing_strategy) + "!\n");
+        }
+        if (o.symmetric != PGM_symmetric && o.symmetric != PGM_asymmetric) throw InvalidArgument("get_calculation_symmetry is not implemented for this value\n");
+        int32_t method;
+        switch (o.calculation_method) {
+        case PGM_default_method:
+        case PGM_newton_raphson: method = PGMB_METHOD_NEWTON_RAPHSON; break;
+        case PGM_linear: method = PGMB_METHOD_LINEAR; break;
+        case PGM_iterative_current: method = PGMB_METHOD_ITERATIVE_CURRENT; break;
+        case PGM_linear_current: method = PGMB_METHOD_LINEAR_CURRENT; break;
+        default:
+            throw CalculationError("The calculation method is invalid for this calculation!\n"); // InvalidCalculationMethod
+        }
+        if (batch_dataset != nullptr && (!batch_dataset->is_batch || !out_ds.is_batch)) {
+            throw CalculationError("If batch_dataset is provided. Both batch_dataset and output_dataset should be a batch!\n");
+        }
+        bool const sym = o.symmetric == PGM_symmetric;
+        if (out_ds.name != (sym ? "sym_output" : "asym_output")) {
+            throw DatasetError("The output dataset '" + out_ds.name + "' does not match the calculation symmetry!\n");
+        }
+        PGM_Idx const n_scn = batch_dataset != nullptr ? batch_dataset->batch_size : 1;
+        if (out_ds.batch_size != n_scn) throw DatasetError("The batch sizes of the update and the output dataset differ!\n");
+        if (n_scn == 0) return; // empty batch: nothing to calculate (job_dispatch.hpp:43-46)
+
+        OutputData od{};
+        for (auto const& b : out_ds.buffers) {
+            if (b.total_elements == 0) continue;
+            Idx const count = m.component_count(b.component);
+            if (count < 0) throw InvalidArgument("component '" + b.component + "' has no power-flow output in pgm_b200\n");
+            if (b.elements_per_scenario != count) {
+                throw DatasetError("The output buffer of '" + b.component + "' must hold exactly the model's " + std::to_string(count) + " elements per scenario!\n");
+            }
+            if (b.data == nullptr) throw InvalidArgument("Received null pointer where a valid pointer was expected.\n");
+            if (b.component == "node") od.node = b.data;
+            else if (b.component == "line") od.line = b.data;
+            else if (b.component == "asym_line") od.asym_line = b.data;
+            else if (b.component == "generic_branch") od.generic_branch = b.data;
+            else if (b.component == "transformer") od.transformer = b.data;
+            else if (b.component == "shunt") od.shunt = b.data;
+            else if (b.component == "source") od.source = b.data;
+            else if (b.component == "sym_gen") od.sym_gen = b.data;
+            else if (b.component == "asym_gen") od.asym_gen = b.data;
+            else if (b.component == "sym_load") od.sym_load = b.data;
+            else if (b.component == "asym_load") od.asym_load = b.data;
+            else if (b.component == "voltage_regulator") od.voltage_regulator = b.data;
+        }
+        if (o.max_iter < 0 || o.max_iter > (PGM_Idx{1} << 30)) throw InvalidArgument("max_iter out of range\n");
+        ModelOptions const mo{method, sym, o.err_tol, o.max_iter, device_ordinal(), static_cast<int32_t>(o.threading)};
+        status.assign(static_cast<size_t>(n_scn), 0);
+        int64_t failed;
+        if (batch_dataset != nullptr) {
+            UpdateData const ud = update_of(*batch_dataset);
+            failed = m.calculate(mo, &ud, od, nullptr, status.data());
+        } else {
+            failed = m.calculate(mo, nullptr, od, nullptr, status.data());
+        }
+        if (failed == 0) return;
+        if (batch_dataset == nullptr) {
+            // a single calculation reports the solver's exception itself (PGM_regular_error)
+            std::string msg = m.batch_message;
+            auto const colon = msg.find(": ");
+            if (msg.rfind("Error in batch #", 0) == 0 && colon != std::string::npos) msg = msg.substr(colon + 2);
+            throw CalculationError(msg);
+        }
+        batch_failed = true;
+    });
+    if (!batch_failed || handle == nullptr) return;
+    // BatchCalculationError (job_dispatch.hpp:208-224): combined message, failed scenario numbers, one message per scenario
+    std::string const& all = model->model->batch_message;
+    handle->err_code = PGM_batch_error;
+    handle->err_msg = all;
+    std::string const tag = "Error in batch #";
+    size_t pos = all.find(tag);
+    while (pos != std::string::npos) {
+        size_t const next = all.find(tag, pos + tag.size());
+        std::string const entry = all.substr(pos, next == std::string::npos ? std::string::npos : next - pos);
+        size_t const colon = entry.find(": ");
+        PGM_Idx const scenario = std::strtoll(entry.c_str() + tag.size(), nullptr, 10);
+        std::string msg = colon == std::string::npos ? entry : entry.substr(colon + 2);
+        if (msg.size() >= 2 && msg.compare(msg.size() - 2, 2, "\n\n") == 0) msg.pop_back();
+        handle->failed_scenarios.push_back(scenario);
+        handle->batch_errs.push_back(std::move(msg));
+        pos = next;
+    }
+    if (handle->failed_scenarios.empty()) { // messages were not itemised: fall back on the status array
+        for (size_t s = 0; s != status.size(); ++s) {
+            if (status[s] != 0) {
+                handle->failed_scenarios.push_back(static_cast<PGM_Idx>(s));
+                handle->batch_errs.emplace_back("scenario failed\n");
+            }
+        }
+    }
+}
+
+void PGM_destroy_model(PGM_PowerGridModel* model) { delete model; }
+
+} // extern "C"

@@ -1153,6 +1153,60 @@ int64_t Model::calculate(ModelOptions const& opt, UpdateData const* update, Outp
                          : calculate_impl<3>(opt, update, out, n_iter, status);
 }
 
+// ---- copy / indexer (PGM_copy_model, PGM_get_indexer) -------------------------------------------------------------
+std::unique_ptr<Model> Model::clone() const {
+    auto copy = std::make_unique<Model>(*this);
+    copy->dev_.reset();
+    copy->outage_plan_ = nullptr;
+    copy->batch_message.clear();
+    return copy;
+}
+
+Idx Model::component_count(std::string const& c) const {
+    if (c == "node") return static_cast<Idx>(node_.size());
+    if (c == "line") return n_line();
+    if (c == "asym_line") return n_aline();
+    if (c == "generic_branch") return n_gb();
+    if (c == "transformer") return n_trafo();
+    if (c == "shunt") return static_cast<Idx>(shunt_in_.size());
+    if (c == "source") return static_cast<Idx>(source_in_.size());
+    if (c == "sym_gen") return n_sym_gen_;
+    if (c == "asym_gen") return n_asym_gen_;
+    if (c == "sym_load") return n_sym_load_;
+    if (c == "asym_load") return n_asym_load_;
+    if (c == "voltage_regulator") return static_cast<Idx>(reg_in_.size());
+    return -1;
+}
+
+void Model::get_indexer(std::string const& c, ID const* ids, Idx size, Idx* indexer) const {
+    // load_gen components share one sequence (sym_gen, asym_gen, sym_load, asym_load): position = index - offset of the type
+    std::unordered_map<ID, Idx> const* map = nullptr;
+    Idx offset = 0, count = 0;
+    if (c == "node") map = &node_idx_;
+    else if (c == "line") map = &line_idx_;
+    else if (c == "asym_line") map = &aline_idx_;
+    else if (c == "generic_branch") map = &gb_idx_;
+    else if (c == "transformer") map = &trafo_idx_;
+    else if (c == "shunt") map = &shunt_idx_;
+    else if (c == "source") map = &source_idx_;
+    else if (c == "voltage_regulator") map = &reg_idx_;
+    else if (c == "sym_gen") { map = &lg_idx_; offset = 0; count = n_sym_gen_; }
+    else if (c == "asym_gen") { map = &lg_idx_; offset = n_sym_gen_; count = n_asym_gen_; }
+    else if (c == "sym_load") { map = &lg_idx_; offset = n_sym_gen_ + n_asym_gen_; count = n_sym_load_; }
+    else if (c == "asym_load") { map = &lg_idx_; offset = n_sym_gen_ + n_asym_gen_ + n_sym_load_; count = n_asym_load_; }
+    else return; // the reference matches the name against its component list and does nothing when none matches
+    for (Idx i = 0; i != size; ++i) {
+        auto const it = map->find(ids[i]);
+        if (it == map->end()) {
+            if (all_ids_.count(ids[i]) != 0) throw InvalidArgument("Wrong type for object with id " + std::to_string(ids[i]) + "\n");
+            throw InvalidArgument("The id cannot be found: " + std::to_string(ids[i]) + "\n");
+        }
+        Idx const pos = it->second - offset;
+        if (map == &lg_idx_ && (pos < 0 || pos >= count)) throw InvalidArgument("Wrong type for object with id " + std::to_string(ids[i]) + "\n");
+        indexer[i] = pos;
+    }
+}
+
 // ---- introspection -----------------------------------------------------------------------------------------------
 Idx Model::n_math_groups() {
     prepare_topology();

@@ -64,6 +64,12 @@ class Model {
     double timing[6]{};
     std::string batch_message;
 
+    // PGM_copy_model / PGM_get_indexer (main_model_impl.hpp:218-228) and the element counts the output dataset is checked
+    // against; the copy shares no device state with the original (it builds its own engines on first use)
+    std::unique_ptr<Model> clone() const;
+    void get_indexer(std::string const& component, ID const* ids, Idx size, Idx* indexer) const;
+    Idx component_count(std::string const& component) const; // -1: not a component of this library
+
   private:
     double freq_;
     // static data

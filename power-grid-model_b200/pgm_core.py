@@ -1,0 +1,194 @@
+"""ctypes binding over the reference's own C API names (include/pgm_b200_capi.h), written the way the reference's Python
+wrapper drives its core library (src/power_grid_model/_core/power_grid_core.py: one handle, every call takes it first,
+errors read back from it; _core/power_grid_model.py: datasets built from numpy row buffers, PGM_calculate).
+It exists to show -- and to test -- that a client of `PGM_create_model / PGM_update_model / PGM_calculate` runs unchanged
+against libpgm_b200.so.  Row-based numpy buffers only."""
+import ctypes as C
+
+import numpy as np
+
+from . import structs
+from ._lib import LIB_PATH, lib
+
+PGM_NO_ERROR, PGM_REGULAR_ERROR, PGM_BATCH_ERROR, PGM_SERIALIZATION_ERROR = range(4)
+CALCULATION_METHOD = {"default_method": -128, "linear": 0, "newton_raphson": 1, "iterative_linear": 2,
+                      "iterative_current": 3, "linear_current": 4, "iec60909": 5}
+
+
+class PowerGridError(RuntimeError):
+    """PGM_regular_error"""
+
+
+class PowerGridBatchError(PowerGridError):
+    """PGM_batch_error: failed_scenarios / error_messages like the reference's PowerGridBatchError"""
+
+    def __init__(self, message, failed_scenarios, error_messages):
+        super().__init__(message)
+        self.failed_scenarios = failed_scenarios
+        self.error_messages = error_messages
+
+
+_core = None
+
+
+def core():
+    global _core
+    if _core is None:
+        lib()  # loud failure with the build hint when the library is missing
+        l = C.CDLL(LIB_PATH)
+        P, I, D, S = C.c_void_p, C.c_int64, C.c_double, C.c_char_p
+        sig = {
+            "PGM_create_handle": (P, []), "PGM_destroy_handle": (None, [P]), "PGM_error_code": (I, [P]),
+            "PGM_error_message": (S, [P]), "PGM_n_failed_scenarios": (I, [P]), "PGM_failed_scenarios": (C.POINTER(I), [P]),
+            "PGM_batch_errors": (C.POINTER(S), [P]), "PGM_clear_error": (None, [P]), "PGM_version": (S, []),
+            "PGM_create_options": (P, [P]), "PGM_destroy_options": (None, [P]),
+            "PGM_set_calculation_type": (None, [P, P, I]), "PGM_set_calculation_method": (None, [P, P, I]),
+            "PGM_set_symmetric": (None, [P, P, I]), "PGM_set_err_tol": (None, [P, P, D]), "PGM_set_max_iter": (None, [P, P, I]),
+            "PGM_set_threading": (None, [P, P, I]), "PGM_set_short_circuit_voltage_scaling": (None, [P, P, I]),
+            "PGM_set_tap_changing_strategy": (None, [P, P, I]), "PGM_set_experimental_features": (None, [P, P, I]),
+            "PGM_create_dataset_const": (P, [P, S, I, I]), "PGM_create_dataset_const_from_mutable": (P, [P, P]),
+            "PGM_destroy_dataset_const": (None, [P]), "PGM_dataset_const_add_buffer": (None, [P, P, S, I, I, P, P]),
+            "PGM_dataset_const_add_attribute_buffer": (None, [P, P, S, S, P]),
+            "PGM_dataset_const_set_next_cartesian_product_dimension": (None, [P, P, P]),
+            "PGM_create_dataset_mutable": (P, [P, S, I, I]), "PGM_destroy_dataset_mutable": (None, [P]),
+            "PGM_dataset_mutable_add_buffer": (None, [P, P, S, I, I, P, P]),
+            "PGM_dataset_mutable_add_attribute_buffer": (None, [P, P, S, S, P]),
+            "PGM_create_model": (P, [P, D, P]), "PGM_update_model": (None, [P, P, P]), "PGM_copy_model": (P, [P, P]),
+            "PGM_get_indexer": (None, [P, P, S, I, P, P]), "PGM_calculate": (None, [P, P, P, P, P]),
+            "PGM_destroy_model": (None, [P]),
+        }
+        for name, (res, args) in sig.items():
+            f = getattr(l, name)
+            f.restype, f.argtypes = res, args
+        _core = l
+    return _core
+
+
+class Handle:
+    def __init__(self):
+        self.h = core().PGM_create_handle()
+
+    def __del__(self):
+        if _core is not None and self.h:
+            _core.PGM_destroy_handle(self.h)
+            self.h = None
+
+    def check(self, batch_error_ok=False):
+        """assert_no_error of the reference's wrapper (_core/error_handling.py)"""
+        c = core()
+        code = c.PGM_error_code(self.h)
+        if code == PGM_NO_ERROR:
+            return None
+        msg = c.PGM_error_message(self.h).decode()
+        if code == PGM_BATCH_ERROR:
+            n = c.PGM_n_failed_scenarios(self.h)
+            failed = np.array([c.PGM_failed_scenarios(self.h)[i] for i in range(n)], dtype=np.int64)
+            errs = c.PGM_batch_errors(self.h)
+            err = PowerGridBatchError(msg, failed, [errs[i].decode() for i in range(n)])
+            c.PGM_clear_error(self.h)
+            if batch_error_ok:
+                return err
+            raise err
+        c.PGM_clear_error(self.h)
+        raise PowerGridError(msg)
+
+
+class _Dataset:
+    """Const (input / update) or mutable (output) dataset over numpy row buffers; keeps the arrays alive."""
+
+    def __init__(self, handle, name, data, *, mutable, is_batch, batch_size):
+        c = core()
+        self.handle, self.mutable, self.keep = handle, mutable, []
+        create = c.PGM_create_dataset_mutable if mutable else c.PGM_create_dataset_const
+        self.ptr = create(handle.h, name.encode(), int(is_batch), int(batch_size))
+        handle.check()
+        add = c.PGM_dataset_mutable_add_buffer if mutable else c.PGM_dataset_const_add_buffer
+        for comp, val in data.items():
+            if isinstance(val, dict):  # sparse batch buffer
+                arr = np.ascontiguousarray(val["data"])
+                indptr = np.ascontiguousarray(val["indptr"], dtype=np.int64)
+                self.keep += [arr, indptr]
+                add(handle.h, self.ptr, comp.encode(), -1, arr.size, indptr.ctypes.data, arr.ctypes.data)
+            else:
+                arr = val if mutable else np.ascontiguousarray(val)
+                assert arr.flags.c_contiguous
+                self.keep.append(arr)
+                per_scenario = arr.shape[-1] if arr.ndim else 1
+                add(handle.h, self.ptr, comp.encode(), per_scenario, arr.size, None, arr.ctypes.data)
+            handle.check()
+
+    def __del__(self):
+        if _core is not None and self.ptr:
+            (_core.PGM_destroy_dataset_mutable if self.mutable else _core.PGM_destroy_dataset_const)(self.ptr)
+            self.ptr = None
+
+
+class PowerGridModel:
+    """The reference's PowerGridModel surface for power flow, over PGM_* symbols."""
+
+    def __init__(self, input_data, system_frequency=50.0, _ptr=None, _counts=None):
+        self.handle = Handle()
+        if _ptr is not None:
+            self.ptr, self._counts = _ptr, _counts
+            return
+        ds = _Dataset(self.handle, "input", input_data, mutable=False, is_batch=False, batch_size=1)
+        self.ptr = core().PGM_create_model(self.handle.h, float(system_frequency), ds.ptr)
+        self.handle.check()
+        self._counts = {c: len(a) for c, a in input_data.items()}
+
+    def __del__(self):
+        if _core is not None and getattr(self, "ptr", None):
+            _core.PGM_destroy_model(self.ptr)
+            self.ptr = None
+
+    def copy(self):
+        h = Handle()
+        ptr = core().PGM_copy_model(h.h, self.ptr)
+        h.check()
+        return PowerGridModel(None, _ptr=ptr, _counts=dict(self._counts))
+
+    def update(self, *, update_data):
+        ds = _Dataset(self.handle, "update", update_data, mutable=False, is_batch=False, batch_size=1)
+        core().PGM_update_model(self.handle.h, self.ptr, ds.ptr)
+        self.handle.check()
+
+    def get_indexer(self, component_type, ids):
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        indexer = np.empty(ids.shape, dtype=np.int64)
+        core().PGM_get_indexer(self.handle.h, self.ptr, component_type.encode(), ids.size, ids.ctypes.data, indexer.ctypes.data)
+        self.handle.check()
+        return indexer
+
+    def calculate_power_flow(self, *, symmetric=True, error_tolerance=1e-8, max_iterations=20,
+                             calculation_method="newton_raphson", update_data=None, threading=-1,
+                             output_component_types=None, continue_on_batch_error=False, tap_changing_strategy=0,
+                             calculation_type=0):
+        c = core()
+        opt = c.PGM_create_options(self.handle.h)
+        try:
+            method = CALCULATION_METHOD[calculation_method] if isinstance(calculation_method, str) else int(calculation_method)
+            c.PGM_set_calculation_type(self.handle.h, opt, int(calculation_type))
+            c.PGM_set_calculation_method(self.handle.h, opt, method)
+            c.PGM_set_symmetric(self.handle.h, opt, int(bool(symmetric)))
+            c.PGM_set_err_tol(self.handle.h, opt, float(error_tolerance))
+            c.PGM_set_max_iter(self.handle.h, opt, int(max_iterations))
+            c.PGM_set_threading(self.handle.h, opt, int(threading))
+            c.PGM_set_tap_changing_strategy(self.handle.h, opt, int(tap_changing_strategy))
+            batch, n_scn, upd = update_data is not None, 1, None
+            if batch:
+                sizes = {(len(v["indptr"]) - 1) if isinstance(v, dict) else np.asarray(v).shape[0] for v in update_data.values()}
+                if len(sizes) > 1:
+                    raise PowerGridError("inconsistent batch sizes in update data")
+                n_scn = sizes.pop() if sizes else 0
+                upd = _Dataset(self.handle, "update", update_data, mutable=False, is_batch=True, batch_size=n_scn)
+            table = structs.SYM_OUTPUT if symmetric else structs.ASYM_OUTPUT
+            comps = output_component_types or [k for k in structs.COMPONENT_ORDER if self._counts.get(k)]
+            shape = (lambda k: (n_scn, self._counts.get(k, 0))) if batch else (lambda k: (self._counts.get(k, 0),))
+            result = {k: np.zeros(shape(k), dtype=table[k]) for k in comps}
+            out = _Dataset(self.handle, "sym_output" if symmetric else "asym_output", result, mutable=True, is_batch=batch,
+                           batch_size=n_scn)
+            c.PGM_calculate(self.handle.h, self.ptr, opt, out.ptr, upd.ptr if upd is not None else None)
+            self.batch_error = self.handle.check(batch_error_ok=continue_on_batch_error)
+            return result
+        finally:
+            c.PGM_destroy_options(opt)

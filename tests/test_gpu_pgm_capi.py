@@ -1,0 +1,133 @@
+"""GPU tests through the reference's own C API names (PGM_create_model / PGM_update_model / PGM_copy_model / PGM_calculate of
+libpgm_b200.so, driven by pgm_b200.pgm_core the way the reference's Python wrapper drives its core):
+ (a) the scenarios of the reference's tests/native_api_tests/test_api_model.cpp with their closed-form answers,
+ (b) the reference's power-flow validation cases (tests/golden/power_flow_cases.json) with the reference's tolerances,
+ (c) the 1000-scenario benchmark batch: the same bytes as the pgmb_model_* seam produces (one engine behind both)."""
+import numpy as np
+import pytest
+
+import pgm_b200
+import validation_cases as vc
+from pgm_b200 import pgm_core
+from pgm_b200.structs import initialize_array
+from test_pgm_capi import _api_model_input
+
+pytestmark = pytest.mark.gpu
+
+
+def _update(source_u_ref=None, q=None, line_status=((0, 1), (0, 0))):
+    upd = {}
+    if source_u_ref is not None:
+        s = initialize_array("update", "source", 1)
+        s["id"], s["u_ref"] = 1, source_u_ref
+        upd["source"] = s
+    if q is not None:
+        l = initialize_array("update", "sym_load", 1)
+        l["id"], l["q_specified"] = 2, q
+        upd["sym_load"] = l
+    ln = initialize_array("update", "line", 2)
+    ln["id"] = [5, 6]
+    ln["from_status"], ln["to_status"] = [line_status[0][0], line_status[1][0]], [line_status[0][1], line_status[1][1]]
+    upd["line"] = ln
+    return upd
+
+
+def _check_node(node, u0):
+    assert node["id"].tolist() == [0, 4] and node["energized"].tolist() == [1, 0]
+    assert node["u"][0] == pytest.approx(u0) and node["u_pu"][0] == pytest.approx(u0 / 100.0)
+    assert node["u_angle"][0] == pytest.approx(0.0, abs=1e-12)
+    assert node["u"][1] == 0.0 and node["u_pu"][1] == 0.0 and node["u_angle"][1] == 0.0
+
+
+def test_api_model_single_update_copy():
+    """test_api_model.cpp:225-253: 50 V; after the permanent update 40 V; a copy made before the update still gives 50 V"""
+    model = pgm_core.PowerGridModel(_api_model_input())
+    _check_node(model.calculate_power_flow(output_component_types=["node"])["node"], 50.0)
+    copy = model.copy()
+    model.update(update_data=_update(source_u_ref=0.5, q=100.0))
+    _check_node(model.calculate_power_flow(output_component_types=["node"])["node"], 40.0)
+    _check_node(copy.calculate_power_flow(output_component_types=["node"])["node"], 50.0)
+    # every valid tap changing strategy is the plain power flow on a model without tap regulators (test_api_model.cpp:462-465)
+    _check_node(copy.calculate_power_flow(output_component_types=["node"], tap_changing_strategy=3)["node"], 50.0)
+
+
+def test_api_model_batch():
+    """test_api_model.cpp:289-314: sparse source buffer (only scenario 0 updates it), dense load / line buffers"""
+    model = pgm_core.PowerGridModel(_api_model_input())
+    s0, s1 = _update(source_u_ref=0.5, q=100.0), _update(q=300.0, line_status=((0, 0), (0, 0)))
+    batch = {"source": {"data": s0["source"], "indptr": np.array([0, 1, 1])},
+             "sym_load": np.stack([s0["sym_load"], s1["sym_load"]]), "line": np.stack([s0["line"], s1["line"]])}
+    res = model.calculate_power_flow(update_data=batch, output_component_types=["node"])["node"]
+    assert res.shape == (2, 2)
+    _check_node(res[0], 40.0)
+    _check_node(res[1], 70.0)
+    _check_node(model.calculate_power_flow(output_component_types=["node"])["node"], 50.0)  # model restored
+
+
+def test_api_model_calculation_errors():
+    """test_api_model.cpp:468-546: a single calculation that does not converge is PGM_regular_error; a batch with a bad id in
+    scenario 1 is PGM_batch_error with that scenario listed and scenario 0 calculated"""
+    model = pgm_core.PowerGridModel(_api_model_input())
+    with pytest.raises(pgm_core.PowerGridError, match="Iteration failed to converge after") as e:
+        model.calculate_power_flow(max_iterations=1, error_tolerance=1e-100, symmetric=False, threading=1)
+    assert not isinstance(e.value, pgm_core.PowerGridBatchError)
+    s0, s1 = _update(source_u_ref=0.5, q=100.0), _update(q=300.0)
+    s1["line"]["id"] = [99, 6]
+    batch = {"source": {"data": s0["source"], "indptr": np.array([0, 1, 1])},
+             "sym_load": np.stack([s0["sym_load"], s1["sym_load"]]), "line": np.stack([s0["line"], s1["line"]])}
+    with pytest.raises(pgm_core.PowerGridBatchError, match="The id cannot be found:") as e:
+        model.calculate_power_flow(update_data=batch, output_component_types=["node"])
+    assert e.value.failed_scenarios.tolist() == [1] and "The id cannot be found:" in e.value.error_messages[0]
+    res = model.calculate_power_flow(update_data=batch, output_component_types=["node"], continue_on_batch_error=True)
+    assert model.batch_error.failed_scenarios.tolist() == [1]
+    _check_node(res["node"][0], 40.0)
+    # non-converging scenarios of a batch: all listed, with the solver's message
+    with pytest.raises(pgm_core.PowerGridBatchError) as e:
+        model.calculate_power_flow(update_data={"sym_load": np.stack([s0["sym_load"], s1["sym_load"]])}, max_iterations=1,
+                                   error_tolerance=1e-100)
+    assert e.value.failed_scenarios.tolist() == [0, 1]
+    assert all("Iteration failed to converge after" in m for m in e.value.error_messages)
+    # empty batch: nothing to do, no error
+    empty = model.calculate_power_flow(update_data={"sym_load": np.zeros((0, 1), dtype=s0["sym_load"].dtype)},
+                                       output_component_types=["node"])
+    assert empty["node"].shape == (0, 2)
+
+
+CASES = vc.load_cases()
+GPU_METHODS = {"newton_raphson", "iterative_current", "linear", "linear_current"}
+RUNS = [(n, s, m, b) for n, c in sorted(CASES.items()) for s, m, b in vc.case_runs(c) if m in GPU_METHODS]
+
+
+@pytest.mark.parametrize("name,sym,method,is_batch", RUNS, ids=[f"{n}-{'sym' if s else 'asym'}-{m}-{'batch' if b else 'single'}" for n, s, m, b in RUNS])
+def test_reference_validation_case_through_pgm_calculate(name, sym, method, is_batch):
+    case = CASES[name]
+    params = case["params"]
+    model = pgm_core.PowerGridModel(vc.to_numpy(case["input"], "input"))
+    kind = "sym_output" if sym else "asym_output"
+    if not is_batch:
+        res = model.calculate_power_flow(symmetric=sym, calculation_method=method)
+        vc.compare_result(res, vc.to_numpy(case[kind], kind), params["rtol"], params["atol"])
+    else:
+        updates = vc.to_numpy(case["update_batch"], "update")
+        expected = vc.to_numpy(case[kind + "_batch"], kind)
+        res = model.calculate_power_flow(symmetric=sym, calculation_method=method, update_data=vc.batch_update_arrays(updates))
+        for s, exp in enumerate(expected):
+            vc.compare_result({k: v[s] for k, v in res.items()}, exp, params["rtol"], params["atol"])
+        if kind in case:  # model unchanged after the batch
+            res = model.calculate_power_flow(symmetric=sym, calculation_method=method)
+            vc.compare_result(res, vc.to_numpy(case[kind], kind), params["rtol"], params["atol"])
+
+
+@pytest.mark.parametrize("sym", [True, False])
+def test_benchmark_batch_equals_the_model_seam(sym):
+    """BASELINE config 2 shape (and its asymmetric twin at 64 scenarios): PGM_calculate and pgmb_model_calculate are two doors
+    to one engine, so the output bytes are identical"""
+    grid = pgm_b200.FictionalGrid(seed=0, **pgm_b200.BENCHMARK_OPTION)
+    n_scn = 1000 if sym else 64
+    update = grid.batch_update(n_scn, seed=0)
+    a = pgm_core.PowerGridModel(grid.input_data).calculate_power_flow(symmetric=sym, update_data=update)
+    b = pgm_b200.PowerGridModel(grid.input_data).calculate_power_flow(symmetric=sym, update_data=update)
+    assert set(a) == set(b) and a["node"].shape == (n_scn, len(grid.input_data["node"]))
+    for comp in a:
+        assert a[comp].tobytes() == b[comp].tobytes(), comp
+    assert np.all(a["node"]["energized"] == 1) and np.all(np.abs(a["node"]["u_pu"] - 1.0) < 0.2)
