@@ -7,17 +7,21 @@
  * of the reference.  Scope = what the engine builds:
  *   - calculation type power_flow; methods default / newton_raphson / linear / iterative_current / linear_current; symmetric and
  *     asymmetric; single and batch (one batch dimension);
- *   - row-based buffers ("attribute" / columnar buffers and cartesian-product batches are answered with PGM_regular_error);
+ *   - row-based and columnar ("attribute") buffers, dense or sparse; a cartesian product of update datasets is answered with
+ *     PGM_regular_error;
+ *   - the meta-data tables (PGM_meta_*) of every dataset and component of the reference, PGM_create_buffer / PGM_buffer_* and
+ *     the dataset info calls, so a client sizes and fills its buffers the way the reference's wrapper does;
  *   - components: node, line, asym_line, generic_branch, transformer, shunt, source, sym_gen, asym_gen, sym_load, asym_load,
  *     voltage_regulator; sensors and faults may be present in the input dataset and are ignored by power flow like in the
  *     reference; any other component is PGM_regular_error at PGM_create_model;
  *   - tap_changing_strategy: any valid value (the model cannot hold a transformer_tap_regulator, so it is the plain power flow).
- * Everything else of the reference's C API (meta-data tables, serialization, writable datasets) is outside the hot path and not
+ * Everything else of the reference's C API (serialization, writable datasets, the PGM_def_* constants) is outside the hot path and not
  * provided.  There is no CPU fallback: PGM_calculate on a host without a CUDA device reports PGM_regular_error.
  */
 #ifndef PGM_B200_CAPI_H
 #define PGM_B200_CAPI_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -33,6 +37,10 @@ typedef struct PGM_Options PGM_Options;
 typedef struct PGM_ConstDataset PGM_ConstDataset;
 typedef struct PGM_MutableDataset PGM_MutableDataset;
 typedef struct PGM_PowerGridModel PGM_PowerGridModel;
+typedef struct PGM_MetaDataset PGM_MetaDataset;
+typedef struct PGM_MetaComponent PGM_MetaComponent;
+typedef struct PGM_MetaAttribute PGM_MetaAttribute;
+typedef struct PGM_DatasetInfo PGM_DatasetInfo;
 
 enum PGM_CalculationType { PGM_power_flow = 0, PGM_state_estimation = 1, PGM_short_circuit = 2 };
 enum PGM_CalculationMethod {
@@ -45,6 +53,7 @@ enum PGM_CalculationMethod {
     PGM_iec60909 = 5
 };
 enum PGM_SymmetryType { PGM_asymmetric = 0, PGM_symmetric = 1 };
+enum PGM_CType { PGM_int32 = 0, PGM_int8 = 1, PGM_double = 2, PGM_double3 = 3 };
 enum PGM_ErrorCode { PGM_no_error = 0, PGM_regular_error = 1, PGM_batch_error = 2, PGM_serialization_error = 3 };
 
 /* handle.h */
@@ -71,7 +80,53 @@ PGM_API void PGM_set_short_circuit_voltage_scaling(PGM_Handle* handle, PGM_Optio
 PGM_API void PGM_set_tap_changing_strategy(PGM_Handle* handle, PGM_Options* opt, PGM_Idx tap_changing_strategy);
 PGM_API void PGM_set_experimental_features(PGM_Handle* handle, PGM_Options* opt, PGM_Idx experimental_features);
 
-/* dataset.h (row-based buffers) */
+/* meta_data.h:32-190 -- datasets input / update / sym_output / asym_output / sc_output, every component of the reference, attribute
+ * names, ctypes and offsets generated from the reference's definition files (tools/gen_meta_table.py) */
+PGM_API PGM_Idx PGM_meta_n_datasets(PGM_Handle* handle);
+PGM_API PGM_MetaDataset const* PGM_meta_get_dataset_by_idx(PGM_Handle* handle, PGM_Idx idx);
+PGM_API PGM_MetaDataset const* PGM_meta_get_dataset_by_name(PGM_Handle* handle, char const* dataset);
+PGM_API char const* PGM_meta_dataset_name(PGM_Handle* handle, PGM_MetaDataset const* dataset);
+PGM_API PGM_Idx PGM_meta_n_components(PGM_Handle* handle, PGM_MetaDataset const* dataset);
+PGM_API PGM_MetaComponent const* PGM_meta_get_component_by_idx(PGM_Handle* handle, PGM_MetaDataset const* dataset, PGM_Idx idx);
+PGM_API PGM_MetaComponent const* PGM_meta_get_component_by_name(PGM_Handle* handle, char const* dataset, char const* component);
+PGM_API char const* PGM_meta_component_name(PGM_Handle* handle, PGM_MetaComponent const* component);
+PGM_API size_t PGM_meta_component_size(PGM_Handle* handle, PGM_MetaComponent const* component);
+PGM_API size_t PGM_meta_component_alignment(PGM_Handle* handle, PGM_MetaComponent const* component);
+PGM_API PGM_Idx PGM_meta_n_attributes(PGM_Handle* handle, PGM_MetaComponent const* component);
+PGM_API PGM_MetaAttribute const* PGM_meta_get_attribute_by_idx(PGM_Handle* handle, PGM_MetaComponent const* component, PGM_Idx idx);
+PGM_API PGM_MetaAttribute const* PGM_meta_get_attribute_by_name(PGM_Handle* handle, char const* dataset, char const* component,
+                                                                char const* attribute);
+PGM_API char const* PGM_meta_attribute_name(PGM_Handle* handle, PGM_MetaAttribute const* attribute);
+PGM_API PGM_Idx PGM_meta_attribute_ctype(PGM_Handle* handle, PGM_MetaAttribute const* attribute);
+PGM_API size_t PGM_meta_attribute_offset(PGM_Handle* handle, PGM_MetaAttribute const* attribute);
+PGM_API int PGM_is_little_endian(PGM_Handle* handle);
+
+/* buffer.h:40-108 */
+PGM_API void* PGM_create_buffer(PGM_Handle* handle, PGM_MetaComponent const* component, PGM_Idx size);
+PGM_API void PGM_destroy_buffer(void* ptr);
+PGM_API void PGM_buffer_set_nan(PGM_Handle* handle, PGM_MetaComponent const* component, void* ptr, PGM_Idx buffer_offset,
+                                PGM_Idx size);
+PGM_API void PGM_buffer_set_value(PGM_Handle* handle, PGM_MetaAttribute const* attribute, void* buffer_ptr, void const* src_ptr,
+                                  PGM_Idx buffer_offset, PGM_Idx size, PGM_Idx src_stride);
+PGM_API void PGM_buffer_get_value(PGM_Handle* handle, PGM_MetaAttribute const* attribute, void const* buffer_ptr, void* dest_ptr,
+                                  PGM_Idx buffer_offset, PGM_Idx size, PGM_Idx dest_stride);
+
+/* dataset.h:27-138 (info) */
+PGM_API char const* PGM_dataset_info_name(PGM_Handle* handle, PGM_DatasetInfo const* info);
+PGM_API PGM_Idx PGM_dataset_info_is_batch(PGM_Handle* handle, PGM_DatasetInfo const* info);
+PGM_API PGM_Idx PGM_dataset_info_batch_size(PGM_Handle* handle, PGM_DatasetInfo const* info);
+PGM_API PGM_Idx PGM_dataset_info_n_components(PGM_Handle* handle, PGM_DatasetInfo const* info);
+PGM_API char const* PGM_dataset_info_component_name(PGM_Handle* handle, PGM_DatasetInfo const* info, PGM_Idx component_idx);
+PGM_API PGM_Idx PGM_dataset_info_elements_per_scenario(PGM_Handle* handle, PGM_DatasetInfo const* info, PGM_Idx component_idx);
+PGM_API PGM_Idx PGM_dataset_info_total_elements(PGM_Handle* handle, PGM_DatasetInfo const* info, PGM_Idx component_idx);
+PGM_API PGM_Idx PGM_dataset_info_has_attribute_indications(PGM_Handle* handle, PGM_DatasetInfo const* info, PGM_Idx component_idx);
+PGM_API PGM_Idx PGM_dataset_info_n_attribute_indications(PGM_Handle* handle, PGM_DatasetInfo const* info, PGM_Idx component_idx);
+PGM_API char const* PGM_dataset_info_attribute_name(PGM_Handle* handle, PGM_DatasetInfo const* info, PGM_Idx component_idx,
+                                                    PGM_Idx attribute_idx);
+PGM_API PGM_DatasetInfo const* PGM_dataset_const_get_info(PGM_Handle* handle, PGM_ConstDataset const* dataset);
+PGM_API PGM_DatasetInfo const* PGM_dataset_mutable_get_info(PGM_Handle* handle, PGM_MutableDataset const* dataset);
+
+/* dataset.h:140-332 (row-based and columnar buffers, dense or sparse) */
 PGM_API PGM_ConstDataset* PGM_create_dataset_const(PGM_Handle* handle, char const* dataset, PGM_Idx is_batch, PGM_Idx batch_size);
 PGM_API PGM_ConstDataset* PGM_create_dataset_const_from_mutable(PGM_Handle* handle, PGM_MutableDataset const* mutable_dataset);
 PGM_API void PGM_destroy_dataset_const(PGM_ConstDataset* dataset);

@@ -8,20 +8,14 @@
 //   model     power_grid_model_c/src/model.cpp:48-75, 188-204 (single batch dimension), 349-359
 #include "../../include/pgm_b200_capi.h"
 #include "capi_common.hpp"
+#include "capi_pgm_common.hpp"
 #include "model.hpp"
 
 #include <cstdlib>
 #include <cstring>
 
 using namespace pgmb;
-
-struct PGM_Handle {
-    PGM_Idx err_code{PGM_no_error};
-    std::string err_msg;
-    std::vector<PGM_Idx> failed_scenarios;
-    std::vector<std::string> batch_errs;
-    mutable std::vector<char const*> batch_errs_c_str;
-};
+using namespace pgmb::capi;
 
 struct PGM_Options {
     PGM_Idx calculation_type{PGM_power_flow};
@@ -44,41 +38,55 @@ struct CalculationError : std::runtime_error {
     using std::runtime_error::runtime_error;
 };
 
+struct AttributeBuffer {
+    PGM_MetaAttribute const* attribute;
+    void* data;
+};
+
 struct DatasetBuffer {
     std::string component;
     PGM_Idx elements_per_scenario;
     PGM_Idx total_elements;
     PGM_Idx const* indptr;
-    void* data;
+    void* data; // row buffer; nullptr = columnar component, its attribute buffers are in `attributes`
+    PGM_MetaComponent const* meta;
+    std::vector<AttributeBuffer> attributes;
+    bool columnar() const { return data == nullptr; }
 };
 
 struct Dataset {
     std::string name;
     bool is_batch;
     PGM_Idx batch_size;
+    PGM_MetaDataset const* meta;
     std::vector<DatasetBuffer> buffers;
 
     Dataset(char const* dataset, PGM_Idx batch, PGM_Idx size) : is_batch{batch != 0}, batch_size{size} {
-        if (dataset == nullptr) throw InvalidArgument("null argument");
+        if (dataset == nullptr) throw InvalidArgument("Received null pointer where a valid pointer was expected.\n");
         name = dataset;
-        if (name != "input" && name != "update" && name != "sym_output" && name != "asym_output" && name != "sc_output") {
-            throw std::out_of_range("Cannot find dataset with name: " + name + "!\n");
-        }
+        meta = meta::find_dataset(name);
+        if (meta == nullptr) throw std::out_of_range("Cannot find dataset with name: " + name + "!\n");
         if (batch_size < 0) throw DatasetError("Batch size cannot be negative!\n");
         if (!is_batch && batch_size != 1) throw DatasetError("For non-batch dataset, batch size should be one!\n");
     }
 
-    DatasetBuffer const* find(std::string const& component) const {
-        for (auto const& b : buffers) {
+    DatasetBuffer* find(std::string const& component) {
+        for (auto& b : buffers) {
             if (b.component == component) return &b;
         }
         return nullptr;
     }
+    DatasetBuffer const& at(PGM_Idx idx) const {
+        if (idx < 0 || idx >= static_cast<PGM_Idx>(buffers.size())) throw std::out_of_range("Index out of range!\n");
+        return buffers[static_cast<size_t>(idx)];
+    }
 
+    // auxiliary/dataset.hpp:587-625
     void add_buffer(char const* component, PGM_Idx elements_per_scenario, PGM_Idx total_elements, PGM_Idx const* indptr,
                     void* data, bool check_indptr) {
-        if (component == nullptr) throw InvalidArgument("null argument");
-        if (!known_component(component)) throw std::out_of_range("Cannot find component with name: " + std::string(component) + "!\n");
+        if (component == nullptr) throw InvalidArgument("Received null pointer where a valid pointer was expected.\n");
+        PGM_MetaComponent const* mc = meta->find(component);
+        if (mc == nullptr) throw std::out_of_range("Cannot find component with name: " + std::string(component) + "!\n");
         if (find(component) != nullptr) throw DatasetError("Cannot have duplicated components!\n");
         if (elements_per_scenario >= 0 && elements_per_scenario * batch_size != total_elements) {
             throw DatasetError("For a uniform buffer, total_elements should be equal to elements_per_scenario * batch_size!\n");
@@ -96,20 +104,66 @@ struct Dataset {
         } else if (indptr != nullptr) {
             throw DatasetError("For a uniform buffer, indptr should be nullptr!\n");
         }
-        buffers.push_back({component, elements_per_scenario, total_elements, indptr, data});
+        buffers.push_back({component, elements_per_scenario, total_elements, indptr, data, mc, {}});
     }
 
-    // every component of the reference's dataset definitions (all_components.hpp:36-39)
-    static bool known_component(std::string const& c) {
-        static char const* const names[] = {"node", "line", "asym_line", "link", "generic_branch", "transformer",
-                                            "three_winding_transformer", "shunt", "source", "sym_gen", "asym_gen", "sym_load",
-                                            "asym_load", "sym_power_sensor", "asym_power_sensor", "sym_voltage_sensor",
-                                            "asym_voltage_sensor", "sym_current_sensor", "asym_current_sensor", "fault",
-                                            "transformer_tap_regulator", "voltage_regulator"};
-        for (auto const* n : names) {
-            if (c == n) return true;
+    // auxiliary/dataset.hpp:627-646: a component added with a null row pointer is columnar and takes one buffer per attribute
+    void add_attribute_buffer(char const* component, char const* attribute, void* data) {
+        if (component == nullptr || attribute == nullptr) throw InvalidArgument("Received null pointer where a valid pointer was expected.\n");
+        DatasetBuffer* b = find(component);
+        if (b == nullptr) throw DatasetError("Cannot find component '" + std::string(component) + "'!\n");
+        if (!b->columnar()) throw DatasetError("Cannot add attribute buffers to row-based dataset!\n");
+        PGM_MetaAttribute const* ma = b->meta->find(attribute);
+        if (ma == nullptr) throw std::out_of_range("Cannot find attribute with name: " + std::string(attribute) + "!\n");
+        for (auto const& a : b->attributes) {
+            if (a.attribute == ma) throw DatasetError("Cannot have duplicated attribute buffers!\n");
         }
-        return false;
+        if (data == nullptr && b->total_elements > 0) {
+            throw DatasetError("Attribute buffer data pointer cannot be null for non-empty component!\n");
+        }
+        b->attributes.push_back({ma, data});
+    }
+};
+
+// Row images of columnar components: the engine reads and writes packed rows, so a columnar input / update component is packed
+// into a scratch row buffer (absent attributes = the reference's null values, like ColumnarAttributeRange's proxy does), and a
+// columnar output component is computed into scratch rows whose requested attributes are copied out afterwards.
+struct RowScratch {
+    std::vector<std::unique_ptr<char[]>> store;
+    struct Pending {
+        DatasetBuffer const* buffer;
+        char const* rows;
+    };
+    std::vector<Pending> outputs;
+
+    void* rows_in(DatasetBuffer const& b) {
+        if (!b.columnar()) return b.data;
+        size_t const n = static_cast<size_t>(b.total_elements), size = b.meta->size;
+        store.push_back(std::make_unique<char[]>(std::max<size_t>(n * size, 1)));
+        char* rows = store.back().get();
+        b.meta->set_nan(rows, 0, b.total_elements);
+        for (auto const& a : b.attributes) {
+            size_t const w = a.attribute->size();
+            auto const* src = static_cast<char const*>(a.data);
+            for (size_t i = 0; i != n; ++i) std::memcpy(rows + i * size + a.attribute->offset, src + i * w, w);
+        }
+        return rows;
+    }
+    void* rows_out(DatasetBuffer const& b) {
+        if (!b.columnar()) return b.data;
+        store.push_back(std::make_unique<char[]>(std::max<size_t>(static_cast<size_t>(b.total_elements) * b.meta->size, 1)));
+        outputs.push_back({&b, store.back().get()});
+        return store.back().get();
+    }
+    void scatter_outputs() const {
+        for (auto const& p : outputs) {
+            size_t const n = static_cast<size_t>(p.buffer->total_elements), size = p.buffer->meta->size;
+            for (auto const& a : p.buffer->attributes) {
+                size_t const w = a.attribute->size();
+                auto* dst = static_cast<char*>(a.data);
+                for (size_t i = 0; i != n; ++i) std::memcpy(dst + i * w, p.rows + i * size + a.attribute->offset, w);
+            }
+        }
     }
 };
 
@@ -118,38 +172,9 @@ bool ignored_by_power_flow(std::string const& c) {
     return c == "fault" || c.find("_sensor") != std::string::npos;
 }
 
-void clear(PGM_Handle* handle) {
-    if (handle != nullptr) *handle = PGM_Handle{};
-}
-
-// Lippincott wrapper like call_with_catch (handle.hpp:62-80): clear the handle, run, translate any exception
-template <class F> auto call(PGM_Handle* handle, F&& f) noexcept -> decltype(f()) {
-    using R = decltype(f());
-    try {
-        clear(handle);
-        return f();
-    } catch (std::exception const& e) {
-        if (handle != nullptr) {
-            handle->err_code = PGM_regular_error;
-            handle->err_msg = e.what();
-        }
-    } catch (...) {
-        if (handle != nullptr) {
-            handle->err_code = PGM_regular_error;
-            handle->err_msg = "Unknown error!\n";
-        }
-    }
-    if constexpr (!std::is_void_v<R>) return R{};
-}
-
-template <class T> T& deref(T* p) {
-    if (p == nullptr) throw InvalidArgument("Received null pointer where a valid pointer was expected.\n");
-    return *p;
-}
-
-ComponentBuffer buffer_of(DatasetBuffer const& b) {
-    if (b.elements_per_scenario < 0) return {-1, b.indptr, b.data};
-    return {b.elements_per_scenario, nullptr, b.data};
+ComponentBuffer buffer_of(DatasetBuffer const& b, RowScratch& scratch) {
+    if (b.elements_per_scenario < 0) return {-1, b.indptr, scratch.rows_in(b)};
+    return {b.elements_per_scenario, nullptr, scratch.rows_in(b)};
 }
 
 int device_ordinal() {
@@ -157,13 +182,14 @@ int device_ordinal() {
     return env != nullptr ? std::atoi(env) : 0;
 }
 
-UpdateData update_of(Dataset const& ds) {
+UpdateData update_of(Dataset const& ds, RowScratch& scratch) {
     if (ds.name != "update") throw DatasetError("An update dataset is expected, got '" + ds.name + "'!\n");
     UpdateData u{};
     u.n_scenarios = ds.batch_size;
     for (auto const& b : ds.buffers) {
         if (b.total_elements == 0) continue;
-        ComponentBuffer const cb = buffer_of(b);
+        if (ignored_by_power_flow(b.component)) continue;
+        ComponentBuffer const cb = buffer_of(b, scratch);
         if (b.component == "line") u.line = cb;
         else if (b.component == "asym_line") u.asym_line = cb;
         else if (b.component == "generic_branch") u.generic_branch = cb;
@@ -274,8 +300,9 @@ void PGM_dataset_const_add_buffer(PGM_Handle* handle, PGM_ConstDataset* dataset,
         deref(dataset).add_buffer(component, elements_per_scenario, total_elements, indptr, const_cast<void*>(data), true);
     });
 }
-void PGM_dataset_const_add_attribute_buffer(PGM_Handle* handle, PGM_ConstDataset*, char const*, char const*, void const*) {
-    call(handle, [] { throw DatasetError("pgm_b200 takes row-based buffers only (no attribute / columnar buffers)!\n"); });
+void PGM_dataset_const_add_attribute_buffer(PGM_Handle* handle, PGM_ConstDataset* dataset, char const* component,
+                                            char const* attribute, void const* data) {
+    call(handle, [&] { deref(dataset).add_attribute_buffer(component, attribute, const_cast<void*>(data)); });
 }
 void PGM_dataset_const_set_next_cartesian_product_dimension(PGM_Handle* handle, PGM_ConstDataset*, PGM_ConstDataset const*) {
     call(handle, [] { throw DatasetError("pgm_b200 takes one batch dimension (no cartesian product of update datasets)!\n"); });
@@ -288,9 +315,55 @@ void PGM_dataset_mutable_add_buffer(PGM_Handle* handle, PGM_MutableDataset* data
                                     PGM_Idx elements_per_scenario, PGM_Idx total_elements, PGM_Idx const* indptr, void* data) {
     call(handle, [&] { deref(dataset).add_buffer(component, elements_per_scenario, total_elements, indptr, data, false); });
 }
-void PGM_dataset_mutable_add_attribute_buffer(PGM_Handle* handle, PGM_MutableDataset*, char const*, char const*, void*) {
-    call(handle, [] { throw DatasetError("pgm_b200 takes row-based buffers only (no attribute / columnar buffers)!\n"); });
+void PGM_dataset_mutable_add_attribute_buffer(PGM_Handle* handle, PGM_MutableDataset* dataset, char const* component,
+                                              char const* attribute, void* data) {
+    call(handle, [&] { deref(dataset).add_attribute_buffer(component, attribute, data); });
 }
+PGM_DatasetInfo const* PGM_dataset_const_get_info(PGM_Handle* handle, PGM_ConstDataset const* dataset) {
+    return call(handle, [&] { return reinterpret_cast<PGM_DatasetInfo const*>(static_cast<Dataset const*>(&deref(dataset))); });
+}
+PGM_DatasetInfo const* PGM_dataset_mutable_get_info(PGM_Handle* handle, PGM_MutableDataset const* dataset) {
+    return call(handle, [&] { return reinterpret_cast<PGM_DatasetInfo const*>(static_cast<Dataset const*>(&deref(dataset))); });
+}
+
+// ---- dataset info (dataset.h:27-138) -----------------------------------------------------------------------------
+#define PGMB_INFO(info) (*reinterpret_cast<Dataset const*>(&deref(info)))
+char const* PGM_dataset_info_name(PGM_Handle* handle, PGM_DatasetInfo const* info) {
+    return call(handle, [&] { return PGMB_INFO(info).name.c_str(); });
+}
+PGM_Idx PGM_dataset_info_is_batch(PGM_Handle* handle, PGM_DatasetInfo const* info) {
+    return call(handle, [&] { return static_cast<PGM_Idx>(PGMB_INFO(info).is_batch); });
+}
+PGM_Idx PGM_dataset_info_batch_size(PGM_Handle* handle, PGM_DatasetInfo const* info) {
+    return call(handle, [&] { return PGMB_INFO(info).batch_size; });
+}
+PGM_Idx PGM_dataset_info_n_components(PGM_Handle* handle, PGM_DatasetInfo const* info) {
+    return call(handle, [&] { return static_cast<PGM_Idx>(PGMB_INFO(info).buffers.size()); });
+}
+char const* PGM_dataset_info_component_name(PGM_Handle* handle, PGM_DatasetInfo const* info, PGM_Idx component_idx) {
+    return call(handle, [&] { return PGMB_INFO(info).at(component_idx).component.c_str(); });
+}
+PGM_Idx PGM_dataset_info_elements_per_scenario(PGM_Handle* handle, PGM_DatasetInfo const* info, PGM_Idx component_idx) {
+    return call(handle, [&] { return PGMB_INFO(info).at(component_idx).elements_per_scenario; });
+}
+PGM_Idx PGM_dataset_info_total_elements(PGM_Handle* handle, PGM_DatasetInfo const* info, PGM_Idx component_idx) {
+    return call(handle, [&] { return PGMB_INFO(info).at(component_idx).total_elements; });
+}
+PGM_Idx PGM_dataset_info_has_attribute_indications(PGM_Handle* handle, PGM_DatasetInfo const* info, PGM_Idx component_idx) {
+    return call(handle, [&] { return static_cast<PGM_Idx>(PGMB_INFO(info).at(component_idx).columnar()); });
+}
+PGM_Idx PGM_dataset_info_n_attribute_indications(PGM_Handle* handle, PGM_DatasetInfo const* info, PGM_Idx component_idx) {
+    return call(handle, [&] { return static_cast<PGM_Idx>(PGMB_INFO(info).at(component_idx).attributes.size()); });
+}
+char const* PGM_dataset_info_attribute_name(PGM_Handle* handle, PGM_DatasetInfo const* info, PGM_Idx component_idx,
+                                            PGM_Idx attribute_idx) {
+    return call(handle, [&] {
+        auto const& b = PGMB_INFO(info).at(component_idx);
+        if (attribute_idx < 0 || attribute_idx >= static_cast<PGM_Idx>(b.attributes.size())) throw std::out_of_range("Index out of range!\n");
+        return b.attributes[static_cast<size_t>(attribute_idx)].attribute->name;
+    });
+}
+#undef PGMB_INFO
 
 // ---- model ---------------------------------------------------------------------------------------------------------
 PGM_PowerGridModel* PGM_create_model(PGM_Handle* handle, double system_frequency, PGM_ConstDataset const* input_dataset) {
@@ -298,10 +371,10 @@ PGM_PowerGridModel* PGM_create_model(PGM_Handle* handle, double system_frequency
         Dataset const& ds = deref(input_dataset);
         if (ds.name != "input" || ds.is_batch) throw DatasetError("PGM_create_model takes a single (non-batch) input dataset!\n");
         InputData in{};
+        RowScratch scratch;
         for (auto const& b : ds.buffers) {
             if (b.total_elements == 0 || ignored_by_power_flow(b.component)) continue;
-            if (b.data == nullptr) throw InvalidArgument("Received null pointer where a valid pointer was expected.\n");
-            ComponentBuffer const cb{b.total_elements, nullptr, b.data};
+            ComponentBuffer const cb{b.total_elements, nullptr, scratch.rows_in(b)};
             if (b.component == "node") in.node = cb;
             else if (b.component == "line") in.line = cb;
             else if (b.component == "asym_line") in.asym_line = cb;
@@ -326,7 +399,8 @@ void PGM_update_model(PGM_Handle* handle, PGM_PowerGridModel* model, PGM_ConstDa
     call(handle, [&] {
         Dataset const& ds = deref(update_dataset);
         if (ds.is_batch) throw DatasetError("PGM_update_model takes a single (non-batch) update dataset!\n");
-        deref(model).model->update_permanent(update_of(ds));
+        RowScratch scratch;
+        deref(model).model->update_permanent(update_of(ds, scratch));
     });
 }
 
@@ -391,6 +465,7 @@ void PGM_calculate(PGM_Handle* handle, PGM_PowerGridModel* model, PGM_Options co
         if (n_scn == 0) return; // empty batch: nothing to calculate (job_dispatch.hpp:43-46)
 
         OutputData od{};
+        RowScratch scratch;
         for (auto const& b : out_ds.buffers) {
             if (b.total_elements == 0) continue;
             Idx const count = m.component_count(b.component);
@@ -398,30 +473,31 @@ void PGM_calculate(PGM_Handle* handle, PGM_PowerGridModel* model, PGM_Options co
             if (b.elements_per_scenario != count) {
                 throw DatasetError("The output buffer of '" + b.component + "' must hold exactly the model's " + std::to_string(count) + " elements per scenario!\n");
             }
-            if (b.data == nullptr) throw InvalidArgument("Received null pointer where a valid pointer was expected.\n");
-            if (b.component == "node") od.node = b.data;
-            else if (b.component == "line") od.line = b.data;
-            else if (b.component == "asym_line") od.asym_line = b.data;
-            else if (b.component == "generic_branch") od.generic_branch = b.data;
-            else if (b.component == "transformer") od.transformer = b.data;
-            else if (b.component == "shunt") od.shunt = b.data;
-            else if (b.component == "source") od.source = b.data;
-            else if (b.component == "sym_gen") od.sym_gen = b.data;
-            else if (b.component == "asym_gen") od.asym_gen = b.data;
-            else if (b.component == "sym_load") od.sym_load = b.data;
-            else if (b.component == "asym_load") od.asym_load = b.data;
-            else if (b.component == "voltage_regulator") od.voltage_regulator = b.data;
+            void* const rows = scratch.rows_out(b);
+            if (b.component == "node") od.node = rows;
+            else if (b.component == "line") od.line = rows;
+            else if (b.component == "asym_line") od.asym_line = rows;
+            else if (b.component == "generic_branch") od.generic_branch = rows;
+            else if (b.component == "transformer") od.transformer = rows;
+            else if (b.component == "shunt") od.shunt = rows;
+            else if (b.component == "source") od.source = rows;
+            else if (b.component == "sym_gen") od.sym_gen = rows;
+            else if (b.component == "asym_gen") od.asym_gen = rows;
+            else if (b.component == "sym_load") od.sym_load = rows;
+            else if (b.component == "asym_load") od.asym_load = rows;
+            else if (b.component == "voltage_regulator") od.voltage_regulator = rows;
         }
         if (o.max_iter < 0 || o.max_iter > (PGM_Idx{1} << 30)) throw InvalidArgument("max_iter out of range\n");
         ModelOptions const mo{method, sym, o.err_tol, o.max_iter, device_ordinal(), static_cast<int32_t>(o.threading)};
         status.assign(static_cast<size_t>(n_scn), 0);
         int64_t failed;
         if (batch_dataset != nullptr) {
-            UpdateData const ud = update_of(*batch_dataset);
+            UpdateData const ud = update_of(*batch_dataset, scratch);
             failed = m.calculate(mo, &ud, od, nullptr, status.data());
         } else {
             failed = m.calculate(mo, nullptr, od, nullptr, status.data());
         }
+        scratch.scatter_outputs();
         if (failed == 0) return;
         if (batch_dataset == nullptr) {
             // a single calculation reports the solver's exception itself (PGM_regular_error)

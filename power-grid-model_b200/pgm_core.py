@@ -53,6 +53,22 @@ def core():
             "PGM_create_dataset_mutable": (P, [P, S, I, I]), "PGM_destroy_dataset_mutable": (None, [P]),
             "PGM_dataset_mutable_add_buffer": (None, [P, P, S, I, I, P, P]),
             "PGM_dataset_mutable_add_attribute_buffer": (None, [P, P, S, S, P]),
+            "PGM_meta_n_datasets": (I, [P]), "PGM_meta_get_dataset_by_idx": (P, [P, I]), "PGM_meta_get_dataset_by_name": (P, [P, S]),
+            "PGM_meta_dataset_name": (S, [P, P]), "PGM_meta_n_components": (I, [P, P]),
+            "PGM_meta_get_component_by_idx": (P, [P, P, I]), "PGM_meta_get_component_by_name": (P, [P, S, S]),
+            "PGM_meta_component_name": (S, [P, P]), "PGM_meta_component_size": (C.c_size_t, [P, P]),
+            "PGM_meta_component_alignment": (C.c_size_t, [P, P]), "PGM_meta_n_attributes": (I, [P, P]),
+            "PGM_meta_get_attribute_by_idx": (P, [P, P, I]), "PGM_meta_get_attribute_by_name": (P, [P, S, S, S]),
+            "PGM_meta_attribute_name": (S, [P, P]), "PGM_meta_attribute_ctype": (I, [P, P]),
+            "PGM_meta_attribute_offset": (C.c_size_t, [P, P]), "PGM_is_little_endian": (C.c_int, [P]),
+            "PGM_create_buffer": (P, [P, P, I]), "PGM_destroy_buffer": (None, [P]), "PGM_buffer_set_nan": (None, [P, P, P, I, I]),
+            "PGM_buffer_set_value": (None, [P, P, P, P, I, I, I]), "PGM_buffer_get_value": (None, [P, P, P, P, I, I, I]),
+            "PGM_dataset_info_name": (S, [P, P]), "PGM_dataset_info_is_batch": (I, [P, P]), "PGM_dataset_info_batch_size": (I, [P, P]),
+            "PGM_dataset_info_n_components": (I, [P, P]), "PGM_dataset_info_component_name": (S, [P, P, I]),
+            "PGM_dataset_info_elements_per_scenario": (I, [P, P, I]), "PGM_dataset_info_total_elements": (I, [P, P, I]),
+            "PGM_dataset_info_has_attribute_indications": (I, [P, P, I]),
+            "PGM_dataset_info_n_attribute_indications": (I, [P, P, I]), "PGM_dataset_info_attribute_name": (S, [P, P, I, I]),
+            "PGM_dataset_const_get_info": (P, [P, P]), "PGM_dataset_mutable_get_info": (P, [P, P]),
             "PGM_create_model": (P, [P, D, P]), "PGM_update_model": (None, [P, P, P]), "PGM_copy_model": (P, [P, P]),
             "PGM_get_indexer": (None, [P, P, S, I, P, P]), "PGM_calculate": (None, [P, P, P, P, P]),
             "PGM_destroy_model": (None, [P]),
@@ -93,6 +109,38 @@ class Handle:
         raise PowerGridError(msg)
 
 
+_CTYPES = {0: "<i4", 1: "i1", 2: "<f8", 3: ("<f8", (3,))}
+_meta_cache = None
+
+
+def power_grid_meta_data():
+    """dataset -> component -> numpy dtype, read through PGM_meta_* the way the reference's wrapper does
+    (_core/power_grid_meta.py: names, formats, offsets, itemsize from the library, nothing hard-coded)"""
+    global _meta_cache
+    if _meta_cache is None:
+        c, h = core(), Handle()
+        meta = {}
+        for d in range(c.PGM_meta_n_datasets(h.h)):
+            ds = c.PGM_meta_get_dataset_by_idx(h.h, d)
+            comps = {}
+            for k in range(c.PGM_meta_n_components(h.h, ds)):
+                comp = c.PGM_meta_get_component_by_idx(h.h, ds, k)
+                attrs = [c.PGM_meta_get_attribute_by_idx(h.h, comp, a) for a in range(c.PGM_meta_n_attributes(h.h, comp))]
+                comps[c.PGM_meta_component_name(h.h, comp).decode()] = np.dtype({
+                    "names": [c.PGM_meta_attribute_name(h.h, a).decode() for a in attrs],
+                    "formats": [_CTYPES[c.PGM_meta_attribute_ctype(h.h, a)] for a in attrs],
+                    "offsets": [c.PGM_meta_attribute_offset(h.h, a) for a in attrs],
+                    "itemsize": c.PGM_meta_component_size(h.h, comp), "aligned": True})
+            meta[c.PGM_meta_dataset_name(h.h, ds).decode()] = comps
+        h.check()
+        _meta_cache = meta
+    return _meta_cache
+
+
+def _is_sparse(val):
+    return isinstance(val, dict) and set(val) == {"data", "indptr"}
+
+
 class _Dataset:
     """Const (input / update) or mutable (output) dataset over numpy row buffers; keeps the arrays alive."""
 
@@ -103,11 +151,33 @@ class _Dataset:
         self.ptr = create(handle.h, name.encode(), int(is_batch), int(batch_size))
         handle.check()
         add = c.PGM_dataset_mutable_add_buffer if mutable else c.PGM_dataset_const_add_buffer
+        add_attr = c.PGM_dataset_mutable_add_attribute_buffer if mutable else c.PGM_dataset_const_add_attribute_buffer
         for comp, val in data.items():
-            if isinstance(val, dict):  # sparse batch buffer
-                arr = np.ascontiguousarray(val["data"])
+            indptr = None
+            if _is_sparse(val):
                 indptr = np.ascontiguousarray(val["indptr"], dtype=np.int64)
-                self.keep += [arr, indptr]
+                self.keep.append(indptr)
+                val = val["data"]
+            if isinstance(val, dict):  # columnar: attribute -> array, dense (n_scenarios, n[, 3]) or the flat data of a sparse buffer
+                cols = {a: (v if mutable else np.ascontiguousarray(v)) for a, v in val.items()}
+                self.keep.append(cols)
+                first = next(iter(cols.values()))
+                if indptr is not None:
+                    per_scenario, total = -1, first.shape[0]
+                elif is_batch:
+                    per_scenario, total = first.shape[1], first.shape[0] * first.shape[1]
+                else:
+                    per_scenario, total = first.shape[0], first.shape[0]
+                add(handle.h, self.ptr, comp.encode(), per_scenario, total, None if indptr is None else indptr.ctypes.data, None)
+                handle.check()
+                for a, v in cols.items():
+                    assert v.flags.c_contiguous
+                    add_attr(handle.h, self.ptr, comp.encode(), a.encode(), v.ctypes.data)
+                    handle.check()
+                continue
+            if indptr is not None:  # sparse row buffer
+                arr = np.ascontiguousarray(val)
+                self.keep.append(arr)
                 add(handle.h, self.ptr, comp.encode(), -1, arr.size, indptr.ctypes.data, arr.ctypes.data)
             else:
                 arr = val if mutable else np.ascontiguousarray(val)
@@ -134,7 +204,7 @@ class PowerGridModel:
         ds = _Dataset(self.handle, "input", input_data, mutable=False, is_batch=False, batch_size=1)
         self.ptr = core().PGM_create_model(self.handle.h, float(system_frequency), ds.ptr)
         self.handle.check()
-        self._counts = {c: len(a) for c, a in input_data.items()}
+        self._counts = {c: len(next(iter(a.values())) if isinstance(a, dict) else a) for c, a in input_data.items()}
 
     def __del__(self):
         if _core is not None and getattr(self, "ptr", None):
@@ -176,7 +246,8 @@ class PowerGridModel:
             c.PGM_set_tap_changing_strategy(self.handle.h, opt, int(tap_changing_strategy))
             batch, n_scn, upd = update_data is not None, 1, None
             if batch:
-                sizes = {(len(v["indptr"]) - 1) if isinstance(v, dict) else np.asarray(v).shape[0] for v in update_data.values()}
+                sizes = {(len(v["indptr"]) - 1) if _is_sparse(v) else
+                         np.asarray(next(iter(v.values())) if isinstance(v, dict) else v).shape[0] for v in update_data.values()}
                 if len(sizes) > 1:
                     raise PowerGridError("inconsistent batch sizes in update data")
                 n_scn = sizes.pop() if sizes else 0
@@ -184,7 +255,12 @@ class PowerGridModel:
             table = structs.SYM_OUTPUT if symmetric else structs.ASYM_OUTPUT
             comps = output_component_types or [k for k in structs.COMPONENT_ORDER if self._counts.get(k)]
             shape = (lambda k: (n_scn, self._counts.get(k, 0))) if batch else (lambda k: (self._counts.get(k, 0),))
-            result = {k: np.zeros(shape(k), dtype=table[k]) for k in comps}
+            if isinstance(comps, dict):  # component -> attribute names (columnar output) or None (row output)
+                result = {k: (np.zeros(shape(k), dtype=table[k]) if attrs is None else
+                              {a: np.zeros(shape(k) + table[k][a].shape, dtype=table[k][a].base) for a in attrs})
+                          for k, attrs in comps.items()}
+            else:
+                result = {k: np.zeros(shape(k), dtype=table[k]) for k in comps}
             out = _Dataset(self.handle, "sym_output" if symmetric else "asym_output", result, mutable=True, is_batch=batch,
                            batch_size=n_scn)
             c.PGM_calculate(self.handle.h, self.ptr, opt, out.ptr, upd.ptr if upd is not None else None)

@@ -131,3 +131,65 @@ def test_benchmark_batch_equals_the_model_seam(sym):
     for comp in a:
         assert a[comp].tobytes() == b[comp].tobytes(), comp
     assert np.all(a["node"]["energized"] == 1) and np.all(np.abs(a["node"]["u_pu"] - 1.0) < 0.2)
+
+
+def _columns(arr):
+    """structured array -> attribute -> contiguous column (the reference's columnar data format)"""
+    return {name: np.ascontiguousarray(arr[name]) for name in arr.dtype.names}
+
+
+def test_columnar_buffers_equal_row_buffers():
+    """test_api_model.cpp:27-50 builds its datasets from a mix of row-based and columnar, dense and sparse buffers: columnar
+    input (node, line), columnar dense batch update (line), sparse row update (source), columnar output -- same answers."""
+    data = _api_model_input()
+    model = pgm_core.PowerGridModel({"node": _columns(data["node"]), "line": _columns(data["line"]), "source": data["source"],
+                                     "sym_load": data["sym_load"]})
+    s0, s1 = _update(source_u_ref=0.5, q=100.0), _update(q=300.0, line_status=((0, 0), (0, 0)))
+    line = np.stack([s0["line"], s1["line"]])
+    batch = {"source": {"data": s0["source"], "indptr": np.array([0, 1, 1])},
+             "sym_load": np.stack([s0["sym_load"], s1["sym_load"]]),
+             "line": {k: np.ascontiguousarray(line[k]) for k in ("id", "from_status", "to_status")}}
+    res = model.calculate_power_flow(update_data=batch, output_component_types={"node": ["id", "energized", "u", "u_pu", "u_angle"]})
+    node = res["node"]
+    assert node["id"].tolist() == [[0, 4], [0, 4]] and node["energized"].tolist() == [[1, 0], [1, 0]]
+    assert node["u"][:, 0] == pytest.approx([40.0, 70.0]) and node["u_pu"][:, 0] == pytest.approx([0.4, 0.7])
+    assert (node["u"][:, 1] == 0).all() and np.abs(node["u_angle"]).max() < 1e-12
+    # sparse columnar update: only scenario 0 carries a source row
+    batch["source"] = {"data": {"id": np.array([1], dtype=np.int32), "u_ref": np.array([0.5])}, "indptr": np.array([0, 1, 1])}
+    res2 = model.calculate_power_flow(update_data=batch, output_component_types=["node"])["node"]
+    assert res2["u"].tobytes() == node["u"].tobytes()
+
+
+def test_model_update_optional_id_row_and_columnar():
+    """test_api_model.cpp:549-650 ("Model update optional id"): a uniform update that covers every element may leave the ids
+    out -- as NaN ids in a row buffer or by not supplying the id column at all"""
+    node = initialize_array("input", "node", 1)
+    node["id"], node["u_rated"] = 0, 100.0
+    source = initialize_array("input", "source", 1)
+    source["id"], source["node"], source["status"], source["u_ref"], source["sk"], source["rx_ratio"] = 1, 0, 1, 1.0, 1000.0, 0.0
+    load = initialize_array("input", "sym_load", 1)
+    load["id"], load["node"], load["status"], load["type"], load["p_specified"], load["q_specified"] = 2, 0, 1, 2, 0.0, 500.0
+    inputs = {"node": node, "source": source, "sym_load": load}
+    q = np.array([[100.0], [300.0]])
+    row = initialize_array("update", "sym_load", (2, 1))
+    row["q_specified"] = q  # ids stay NaN
+    a = pgm_core.PowerGridModel(inputs).calculate_power_flow(update_data={"sym_load": row}, output_component_types=["node"])
+    b = pgm_core.PowerGridModel({k: _columns(v) for k, v in inputs.items()}).calculate_power_flow(
+        update_data={"sym_load": {"q_specified": q}}, output_component_types=["node"])
+    row["id"] = 2
+    c = pgm_core.PowerGridModel(inputs).calculate_power_flow(update_data={"sym_load": row}, output_component_types=["node"])
+    assert a["node"]["u"][:, 0] == pytest.approx([90.0, 70.0])
+    assert a["node"].tobytes() == b["node"].tobytes() == c["node"].tobytes()
+
+
+def test_benchmark_batch_columnar_output():
+    """columnar output of the benchmark batch (node voltages only -- the reference's advice for large batches,
+    docs/user_manual/performance-guide.md): the same numbers as the row buffers hold"""
+    grid = pgm_b200.FictionalGrid(seed=0, **pgm_b200.BENCHMARK_OPTION)
+    update = grid.batch_update(64, seed=0)
+    model = pgm_core.PowerGridModel(grid.input_data)
+    rows = model.calculate_power_flow(update_data=update, output_component_types=["node"])["node"]
+    cols = model.calculate_power_flow(update_data={k: _columns(v) for k, v in update.items()},
+                                      output_component_types={"node": ["u_pu", "u_angle"], "line": ["i_from"]})
+    assert cols["node"]["u_pu"].tobytes() == rows["u_pu"].tobytes() and cols["node"]["u_angle"].tobytes() == rows["u_angle"].tobytes()
+    assert cols["line"]["i_from"].shape == (64, len(grid.input_data["line"])) and (cols["line"]["i_from"] >= 0).all()

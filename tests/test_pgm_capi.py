@@ -19,7 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_library_exports_every_pgm_symbol():
     header = open(os.path.join(ROOT, "include", "pgm_b200_capi.h")).read()
     names = re.findall(r"PGM_API\s+[\w\s\*]+?\b(PGM_\w+)\s*\(", header)
-    assert len(names) == 36, len(names)
+    assert len(names) == 70, len(names)
     lib = C.CDLL(os.path.join(ROOT, "power-grid-model_b200", "libpgm_b200.so"))
     for n in names:
         assert hasattr(lib, n), n
@@ -75,7 +75,33 @@ def test_handle_is_cleared_by_every_call_and_reports_dataset_errors():
     add(h.h, ds, b"sym_load", 2, 6, None, buf.ctypes.data)
     assert b"Cannot have duplicated components" in c.PGM_error_message(h.h)
     c.PGM_dataset_const_add_attribute_buffer(h.h, ds, b"sym_load", b"id", buf.ctypes.data)
-    assert c.PGM_error_code(h.h) == pgm_core.PGM_REGULAR_ERROR and b"row-based" in c.PGM_error_message(h.h)
+    assert c.PGM_error_message(h.h) == b"Dataset error: Cannot add attribute buffers to row-based dataset!\n"
+    # columnar component: null row pointer, one buffer per attribute (auxiliary/dataset.hpp:627-646)
+    ids = np.zeros(6, dtype=np.int32)
+    add(h.h, ds, b"asym_load", 2, 6, None, None)
+    assert c.PGM_error_code(h.h) == 0
+    add_attr = c.PGM_dataset_const_add_attribute_buffer
+    add_attr(h.h, ds, b"asym_load", b"id", ids.ctypes.data)
+    assert c.PGM_error_code(h.h) == 0
+    add_attr(h.h, ds, b"asym_load", b"id", ids.ctypes.data)
+    assert b"Cannot have duplicated attribute buffers" in c.PGM_error_message(h.h)
+    add_attr(h.h, ds, b"asym_load", b"no_such_attribute", ids.ctypes.data)
+    assert b"Cannot find attribute with name: no_such_attribute" in c.PGM_error_message(h.h)
+    add_attr(h.h, ds, b"asym_load", b"p_specified", None)
+    assert b"Attribute buffer data pointer cannot be null for non-empty component" in c.PGM_error_message(h.h)
+    add_attr(h.h, ds, b"shunt", b"id", ids.ctypes.data)
+    assert b"Cannot find component 'shunt'" in c.PGM_error_message(h.h)
+    # dataset info (dataset.h:27-138)
+    info = c.PGM_dataset_const_get_info(h.h, ds)
+    assert c.PGM_dataset_info_name(h.h, info) == b"update" and c.PGM_dataset_info_is_batch(h.h, info) == 1
+    assert c.PGM_dataset_info_batch_size(h.h, info) == 3 and c.PGM_dataset_info_n_components(h.h, info) == 2
+    assert [c.PGM_dataset_info_component_name(h.h, info, i) for i in range(2)] == [b"sym_load", b"asym_load"]
+    assert [c.PGM_dataset_info_elements_per_scenario(h.h, info, i) for i in range(2)] == [-1, 2]
+    assert [c.PGM_dataset_info_total_elements(h.h, info, i) for i in range(2)] == [6, 6]
+    assert [c.PGM_dataset_info_has_attribute_indications(h.h, info, i) for i in range(2)] == [0, 1]
+    assert [c.PGM_dataset_info_n_attribute_indications(h.h, info, i) for i in range(2)] == [0, 1]
+    assert c.PGM_dataset_info_attribute_name(h.h, info, 1, 0) == b"id"
+    assert c.PGM_dataset_info_component_name(h.h, info, 2) is None and b"Index out of range" in c.PGM_error_message(h.h)
     c.PGM_clear_error(h.h)
     assert c.PGM_error_code(h.h) == 0 and c.PGM_error_message(h.h) == b""
     c.PGM_destroy_dataset_const(ds)
@@ -86,9 +112,8 @@ def test_handle_is_cleared_by_every_call_and_reports_dataset_errors():
 
 def test_get_indexer_and_construction_errors():
     """test_api_model.cpp:255-287 ("Test get indexer"), :319-343 ("Construction error"), :345-372 ("Update error")"""
-    node = initialize_array("input", "node", 3)
-    node["id"], node["u_rated"] = [1, 2, 3], 10e3
-    model = pgm_core.PowerGridModel({"node": node})
+    # the reference's test builds this model from columnar buffers (test_api_model.cpp:259-265)
+    model = pgm_core.PowerGridModel({"node": {"id": np.array([1, 2, 3], dtype=np.int32), "u_rated": np.full(3, 10e3)}})
     assert model.get_indexer("node", [2, 1, 3, 2]).tolist() == [1, 0, 2, 1]
     with pytest.raises(pgm_core.PowerGridError, match="The id cannot be found: 4"):
         model.get_indexer("node", [2, 1, 3, 4])
@@ -144,3 +169,70 @@ def test_pgm_calculate_has_no_cpu_fallback():
     model = pgm_core.PowerGridModel(_api_model_input())
     with pytest.raises(pgm_core.PowerGridError, match="no CPU fallback"):
         model.calculate_power_flow()
+
+
+def test_meta_data_tables_match_the_struct_layouts():
+    """PGM_meta_* (meta_data.h): the tables generated from the reference's definition files against the independently written
+    numpy dtypes of pgm_b200.structs (which the kernels' structs are static_asserted against) for every component the engine
+    builds, plus the shape of the whole table (datasets / components in the reference's order)."""
+    meta = pgm_core.power_grid_meta_data()
+    assert list(meta) == ["input", "update", "sym_output", "asym_output", "sc_output"]
+    comps = list(meta["input"])
+    assert len(comps) == 22 and comps[:6] == ["node", "line", "asym_line", "link", "generic_branch", "transformer"]
+    assert comps[-3:] == ["fault", "transformer_tap_regulator", "voltage_regulator"]
+    assert all(list(meta[d]) == comps for d in meta)
+    st = pgm_b200.structs
+    n_checked = 0
+    for ds, table in (("input", st.INPUT), ("update", st.UPDATE), ("sym_output", st.SYM_OUTPUT), ("asym_output", st.ASYM_OUTPUT)):
+        for comp, dt in table.items():
+            got = meta[ds][comp]
+            assert got.names == dt.names and got.itemsize == dt.itemsize, (ds, comp)
+            for name in dt.names:
+                assert got.fields[name][1] == dt.fields[name][1] and got.fields[name][0] == dt.fields[name][0], (ds, comp, name)
+            n_checked += 1
+    assert n_checked == 12 + 11 + 12 + 12
+    # sizes the reference states for components outside the engine (auxiliary/static_asserts, SURVEY appendix B conventions)
+    assert meta["input"]["link"].itemsize == 16 and meta["update"]["node"].itemsize == 4
+    assert meta["input"]["three_winding_transformer"].names[:4] == ("id", "node_1", "node_2", "node_3")
+    assert meta["sym_output"]["three_winding_transformer"].names[-4:] == ("p_3", "q_3", "i_3", "s_3")
+    assert meta["sc_output"]["node"].fields["u_pu"][0].shape == (3,)
+    c, h = pgm_core.core(), pgm_core.Handle()
+    assert c.PGM_is_little_endian(h.h) == 1
+    assert c.PGM_meta_get_dataset_by_name(h.h, b"nope") is None and b"Cannot find dataset with name: nope!" in c.PGM_error_message(h.h)
+    assert c.PGM_meta_get_component_by_name(h.h, b"input", b"nope") is None
+    assert b"Cannot find component with name: nope!" in c.PGM_error_message(h.h)
+    assert c.PGM_meta_get_attribute_by_name(h.h, b"input", b"node", b"nope") is None
+    assert b"Cannot find attribute with name: nope!" in c.PGM_error_message(h.h)
+    assert c.PGM_meta_get_dataset_by_idx(h.h, 5) is None and b"Index out of range!" in c.PGM_error_message(h.h)
+    node = c.PGM_meta_get_component_by_name(h.h, b"input", b"node")
+    assert c.PGM_meta_component_alignment(h.h, node) == 8 and c.PGM_meta_component_size(h.h, node) == 16
+    assert c.PGM_meta_get_attribute_by_idx(h.h, node, 2) is None and b"Index out of range!" in c.PGM_error_message(h.h)
+
+
+def test_buffer_create_set_nan_set_get_value():
+    """buffer.h: the calls test_api_buffer.cpp exercises -- NaN fill, strided set / get of one attribute"""
+    c, h = pgm_core.core(), pgm_core.Handle()
+    comp = c.PGM_meta_get_component_by_name(h.h, b"input", b"asym_load")
+    dt = pgm_core.power_grid_meta_data()["input"]["asym_load"]
+    ptr = c.PGM_create_buffer(h.h, comp, 4)
+    assert ptr and ptr % 8 == 0
+    view = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(4 * dt.itemsize,)).view(dt)
+    view.view(np.uint8)[:] = 0
+    c.PGM_buffer_set_nan(h.h, comp, ptr, 1, 2)
+    assert view["id"].tolist() == [0, -2**31, -2**31, 0] and view["status"].tolist() == [0, -128, -128, 0]
+    assert np.isnan(view["p_specified"][1:3]).all() and (view["p_specified"][[0, 3]] == 0).all()
+    attr_id = c.PGM_meta_get_attribute_by_name(h.h, b"input", b"asym_load", b"id")
+    attr_q = c.PGM_meta_get_attribute_by_name(h.h, b"input", b"asym_load", b"q_specified")
+    ids = np.array([10, 11, 12, 13], dtype=np.int32)
+    c.PGM_buffer_set_value(h.h, attr_id, ptr, ids.ctypes.data, 0, 4, -1)
+    q = np.arange(24, dtype=np.float64).reshape(4, 6)  # rows of 6 doubles, the attribute takes the first 3: stride 48
+    c.PGM_buffer_set_value(h.h, attr_q, ptr, q.ctypes.data, 1, 2, 48)
+    assert view["id"].tolist() == [10, 11, 12, 13]
+    assert view["q_specified"][1].tolist() == [6.0, 7.0, 8.0] and view["q_specified"][2].tolist() == [12.0, 13.0, 14.0]
+    assert (view["q_specified"][0] == 0).all()
+    back = np.full((4, 3), -1.0)
+    c.PGM_buffer_get_value(h.h, attr_q, ptr, back.ctypes.data, 1, 2, -1)
+    assert back[1].tolist() == [6.0, 7.0, 8.0] and back[2].tolist() == [12.0, 13.0, 14.0] and (back[[0, 3]] == -1).all()
+    c.PGM_buffer_set_value(h.h, attr_q, ptr, None, 0, 1, -1)
+    assert c.PGM_error_code(h.h) == pgm_core.PGM_REGULAR_ERROR
+    c.PGM_destroy_buffer(ptr)
