@@ -6,9 +6,10 @@
  *   power_grid_model_c/include/power_grid_model_c/handle.h:32-115, options.h:38-138, dataset.h:140-320, model.h:33-125
  * of the reference.  Scope = what the engine builds:
  *   - calculation type power_flow; methods default / newton_raphson / linear / iterative_current / linear_current; symmetric and
- *     asymmetric; single and batch (one batch dimension);
- *   - row-based and columnar ("attribute") buffers, dense or sparse; a cartesian product of update datasets is answered with
- *     PGM_regular_error;
+ *     asymmetric; single and batch;
+ *   - row-based and columnar ("attribute") buffers, dense or sparse; a cartesian product of update datasets
+ *     (PGM_dataset_const_set_next_cartesian_product_dimension): outer dimensions are applied as permanent updates to a model copy,
+ *     the innermost dimension is the batch one GPU call solves;
  *   - the meta-data tables (PGM_meta_*) of every dataset and component of the reference, PGM_create_buffer / PGM_buffer_* and
  *     the dataset info calls, so a client sizes and fills its buffers the way the reference's wrapper does;
  *   - components: node, line, asym_line, generic_branch, transformer, shunt, source, sym_gen, asym_gen, sym_load, asym_load,

@@ -60,6 +60,7 @@ struct Dataset {
     PGM_Idx batch_size;
     PGM_MetaDataset const* meta;
     std::vector<DatasetBuffer> buffers;
+    Dataset const* next{nullptr}; // next cartesian-product dimension
 
     Dataset(char const* dataset, PGM_Idx batch, PGM_Idx size) : is_batch{batch != 0}, batch_size{size} {
         if (dataset == nullptr) throw InvalidArgument("Received null pointer where a valid pointer was expected.\n");
@@ -105,6 +106,43 @@ struct Dataset {
             throw DatasetError("For a uniform buffer, indptr should be nullptr!\n");
         }
         buffers.push_back({component, elements_per_scenario, total_elements, indptr, data, mc, {}});
+    }
+
+    // auxiliary/dataset.hpp:563-574
+    void set_next(Dataset const* next_dataset) {
+        for (Dataset const* d = next_dataset; d != nullptr; d = d->next) {
+            if (d == this) throw DatasetError("Cannot create cyclic cartesian product dimension linked list!\n");
+        }
+        next = next_dataset;
+    }
+
+    // rows [begin, end) of a buffer as a buffer of its own (row pointer or every attribute pointer moved)
+    static DatasetBuffer sub_buffer(DatasetBuffer const& b, PGM_Idx begin, PGM_Idx end, PGM_Idx elements_per_scenario) {
+        DatasetBuffer r{b.component, elements_per_scenario, end - begin, nullptr, nullptr, b.meta, {}};
+        if (!b.columnar()) r.data = static_cast<char*>(b.data) + static_cast<size_t>(begin) * b.meta->size;
+        for (auto const& a : b.attributes) {
+            r.attributes.push_back({a.attribute, static_cast<char*>(a.data) + static_cast<size_t>(begin) * a.attribute->size()});
+        }
+        return r;
+    }
+    // get_individual_scenario (auxiliary/dataset.hpp:463-475): scenario i as a single (non-batch) dataset
+    Dataset individual_scenario(PGM_Idx i) const {
+        Dataset single{name.c_str(), 0, 1};
+        for (auto const& b : buffers) {
+            PGM_Idx const begin = b.elements_per_scenario < 0 ? b.indptr[i] : i * b.elements_per_scenario;
+            PGM_Idx const end = b.elements_per_scenario < 0 ? b.indptr[i + 1] : (i + 1) * b.elements_per_scenario;
+            single.buffers.push_back(sub_buffer(b, begin, end, end - begin));
+        }
+        return single;
+    }
+    // get_slice_scenario (auxiliary/dataset.hpp:476-499): scenarios [begin, end) of a batch dataset with uniform buffers
+    Dataset slice_scenarios(PGM_Idx begin, PGM_Idx end) const {
+        Dataset slice{name.c_str(), 1, end - begin};
+        for (auto const& b : buffers) {
+            if (b.elements_per_scenario < 0) throw DatasetError("Cannot export a single dataset with specified scenario\n");
+            slice.buffers.push_back(sub_buffer(b, begin * b.elements_per_scenario, end * b.elements_per_scenario, b.elements_per_scenario));
+        }
+        return slice;
     }
 
     // auxiliary/dataset.hpp:627-646: a component added with a null row pointer is columnar and takes one buffer per attribute
@@ -207,6 +245,130 @@ UpdateData update_of(Dataset const& ds, RowScratch& scratch) {
     return u;
 }
 
+
+// BatchCalculationError (job_dispatch.hpp:208-224): combined message, failed scenario numbers, one message per scenario
+struct ApiBatchFailure {
+    std::string message;
+    std::vector<PGM_Idx> scenarios;
+    std::vector<std::string> errors;
+};
+
+void set_output_slot(OutputData& od, std::string const& c, void* rows) {
+    if (c == "node") od.node = rows;
+    else if (c == "line") od.line = rows;
+    else if (c == "asym_line") od.asym_line = rows;
+    else if (c == "generic_branch") od.generic_branch = rows;
+    else if (c == "transformer") od.transformer = rows;
+    else if (c == "shunt") od.shunt = rows;
+    else if (c == "source") od.source = rows;
+    else if (c == "sym_gen") od.sym_gen = rows;
+    else if (c == "asym_gen") od.asym_gen = rows;
+    else if (c == "sym_load") od.sym_load = rows;
+    else if (c == "asym_load") od.asym_load = rows;
+    else if (c == "voltage_regulator") od.voltage_regulator = rows;
+}
+
+// calculate_single_batch_dimension_impl (power_grid_model_c/src/model.cpp:188-204): one engine call for the whole batch
+void calculate_single_dimension(Model& m, ModelOptions const& mo, Dataset const& out_ds, Dataset const* batch) {
+    if (batch != nullptr && (!batch->is_batch || !out_ds.is_batch)) {
+        throw CalculationError("If batch_dataset is provided. Both batch_dataset and output_dataset should be a batch!\n");
+    }
+    PGM_Idx const n_scn = batch != nullptr ? batch->batch_size : 1;
+    if (out_ds.batch_size != n_scn) throw DatasetError("The batch sizes of the update and the output dataset differ!\n");
+    if (n_scn == 0) return; // empty batch: nothing to calculate (job_dispatch.hpp:43-46)
+
+    OutputData od{};
+    RowScratch scratch;
+    for (auto const& b : out_ds.buffers) {
+        if (b.total_elements == 0) continue;
+        Idx const count = m.component_count(b.component);
+        if (count < 0) throw InvalidArgument("component '" + b.component + "' has no power-flow output in pgm_b200\n");
+        if (b.elements_per_scenario != count) {
+            throw DatasetError("The output buffer of '" + b.component + "' must hold exactly the model's " + std::to_string(count) + " elements per scenario!\n");
+        }
+        set_output_slot(od, b.component, scratch.rows_out(b));
+    }
+    std::vector<int32_t> status(static_cast<size_t>(n_scn), 0);
+    int64_t failed;
+    if (batch != nullptr) {
+        UpdateData const ud = update_of(*batch, scratch);
+        failed = m.calculate(mo, &ud, od, nullptr, status.data());
+    } else {
+        failed = m.calculate(mo, nullptr, od, nullptr, status.data());
+    }
+    scratch.scatter_outputs();
+    if (failed == 0) return;
+    std::string const& all = m.batch_message;
+    if (batch == nullptr) {
+        // a single calculation reports the solver's exception itself (PGM_regular_error)
+        std::string msg = all;
+        auto const colon = msg.find(": ");
+        if (msg.rfind("Error in batch #", 0) == 0 && colon != std::string::npos) msg = msg.substr(colon + 2);
+        throw CalculationError(msg);
+    }
+    ApiBatchFailure f;
+    f.message = all;
+    std::string const tag = "Error in batch #";
+    size_t pos = all.find(tag);
+    while (pos != std::string::npos) {
+        size_t const next = all.find(tag, pos + tag.size());
+        std::string const entry = all.substr(pos, next == std::string::npos ? std::string::npos : next - pos);
+        size_t const colon = entry.find(": ");
+        PGM_Idx const scenario = std::strtoll(entry.c_str() + tag.size(), nullptr, 10);
+        std::string msg = colon == std::string::npos ? entry : entry.substr(colon + 2);
+        if (msg.size() >= 2 && msg.compare(msg.size() - 2, 2, "\n\n") == 0) msg.pop_back();
+        f.scenarios.push_back(scenario);
+        f.errors.push_back(std::move(msg));
+        pos = next;
+    }
+    if (f.scenarios.empty()) { // messages were not itemised: fall back on the status array
+        for (size_t s = 0; s != status.size(); ++s) {
+            if (status[s] != 0) {
+                f.scenarios.push_back(static_cast<PGM_Idx>(s));
+                f.errors.emplace_back("scenario failed\n");
+            }
+        }
+    }
+    throw f;
+}
+
+// calculate_multi_dimensional_impl (model.cpp:290-334): a linked list of batch datasets is a cartesian product; every scenario of
+// an outer dimension is applied as a permanent update to a copy of the model, the inner dimensions run on the copy and write the
+// matching slice of the output.  The innermost dimension is the batch the GPU pipeline takes in one call.
+void calculate_multi_dimensional(Model& m, ModelOptions const& mo, Dataset const& out_ds, Dataset const* batch) {
+    if (batch == nullptr || batch->next == nullptr) {
+        calculate_single_dimension(m, mo, out_ds, batch);
+        return;
+    }
+    PGM_Idx stride = 1;
+    for (Dataset const* d = batch->next; d != nullptr; d = d->next) stride *= d->batch_size;
+    ApiBatchFailure all;
+    for (PGM_Idx i = 0; i != batch->batch_size; ++i) {
+        auto fail_all = [&](std::string const& what) { // a failure outside the inner batch fails every scenario of the slice
+            all.message = what;
+            for (PGM_Idx k = 0; k != stride; ++k) {
+                all.scenarios.push_back(i * stride + k); // the reference lists 0..stride-1 here (model.cpp:253); the slice's own
+                all.errors.push_back(what);              // scenario numbers are what the caller can act on
+            }
+        };
+        try {
+            Dataset const single = batch->individual_scenario(i);
+            Dataset const slice = out_ds.slice_scenarios(i * stride, (i + 1) * stride);
+            std::unique_ptr<Model> local = m.clone();
+            RowScratch scratch;
+            local->update_permanent(update_of(single, scratch));
+            calculate_multi_dimensional(*local, mo, slice, batch->next);
+        } catch (ApiBatchFailure const& f) {
+            all.message = f.message;
+            for (PGM_Idx s : f.scenarios) all.scenarios.push_back(s + i * stride);
+            all.errors.insert(all.errors.end(), f.errors.begin(), f.errors.end());
+        } catch (std::exception const& e) {
+            fail_all(e.what());
+        }
+    }
+    if (!all.scenarios.empty()) throw all;
+}
+
 } // namespace
 
 struct PGM_ConstDataset : Dataset {
@@ -304,8 +466,9 @@ void PGM_dataset_const_add_attribute_buffer(PGM_Handle* handle, PGM_ConstDataset
                                             char const* attribute, void const* data) {
     call(handle, [&] { deref(dataset).add_attribute_buffer(component, attribute, const_cast<void*>(data)); });
 }
-void PGM_dataset_const_set_next_cartesian_product_dimension(PGM_Handle* handle, PGM_ConstDataset*, PGM_ConstDataset const*) {
-    call(handle, [] { throw DatasetError("pgm_b200 takes one batch dimension (no cartesian product of update datasets)!\n"); });
+void PGM_dataset_const_set_next_cartesian_product_dimension(PGM_Handle* handle, PGM_ConstDataset* dataset,
+                                                            PGM_ConstDataset const* next_dataset) {
+    call(handle, [&] { deref(dataset).set_next(next_dataset); });
 }
 PGM_MutableDataset* PGM_create_dataset_mutable(PGM_Handle* handle, char const* dataset, PGM_Idx is_batch, PGM_Idx batch_size) {
     return call(handle, [&] { return new PGM_MutableDataset{dataset, is_batch, batch_size}; });
@@ -424,7 +587,7 @@ void PGM_get_indexer(PGM_Handle* handle, PGM_PowerGridModel const* model, char c
 
 void PGM_calculate(PGM_Handle* handle, PGM_PowerGridModel* model, PGM_Options const* opt,
                    PGM_MutableDataset const* output_dataset, PGM_ConstDataset const* batch_dataset) {
-    std::vector<int32_t> status;
+    ApiBatchFailure batch_failure;
     bool batch_failed = false;
     call(handle, [&] {
         Model& m = *deref(model).model;
@@ -453,87 +616,24 @@ void PGM_calculate(PGM_Handle* handle, PGM_PowerGridModel* model, PGM_Options co
         default:
             throw CalculationError("The calculation method is invalid for this calculation!\n"); // InvalidCalculationMethod
         }
-        if (batch_dataset != nullptr && (!batch_dataset->is_batch || !out_ds.is_batch)) {
-            throw CalculationError("If batch_dataset is provided. Both batch_dataset and output_dataset should be a batch!\n");
-        }
         bool const sym = o.symmetric == PGM_symmetric;
         if (out_ds.name != (sym ? "sym_output" : "asym_output")) {
             throw DatasetError("The output dataset '" + out_ds.name + "' does not match the calculation symmetry!\n");
         }
-        PGM_Idx const n_scn = batch_dataset != nullptr ? batch_dataset->batch_size : 1;
-        if (out_ds.batch_size != n_scn) throw DatasetError("The batch sizes of the update and the output dataset differ!\n");
-        if (n_scn == 0) return; // empty batch: nothing to calculate (job_dispatch.hpp:43-46)
-
-        OutputData od{};
-        RowScratch scratch;
-        for (auto const& b : out_ds.buffers) {
-            if (b.total_elements == 0) continue;
-            Idx const count = m.component_count(b.component);
-            if (count < 0) throw InvalidArgument("component '" + b.component + "' has no power-flow output in pgm_b200\n");
-            if (b.elements_per_scenario != count) {
-                throw DatasetError("The output buffer of '" + b.component + "' must hold exactly the model's " + std::to_string(count) + " elements per scenario!\n");
-            }
-            void* const rows = scratch.rows_out(b);
-            if (b.component == "node") od.node = rows;
-            else if (b.component == "line") od.line = rows;
-            else if (b.component == "asym_line") od.asym_line = rows;
-            else if (b.component == "generic_branch") od.generic_branch = rows;
-            else if (b.component == "transformer") od.transformer = rows;
-            else if (b.component == "shunt") od.shunt = rows;
-            else if (b.component == "source") od.source = rows;
-            else if (b.component == "sym_gen") od.sym_gen = rows;
-            else if (b.component == "asym_gen") od.asym_gen = rows;
-            else if (b.component == "sym_load") od.sym_load = rows;
-            else if (b.component == "asym_load") od.asym_load = rows;
-            else if (b.component == "voltage_regulator") od.voltage_regulator = rows;
-        }
         if (o.max_iter < 0 || o.max_iter > (PGM_Idx{1} << 30)) throw InvalidArgument("max_iter out of range\n");
         ModelOptions const mo{method, sym, o.err_tol, o.max_iter, device_ordinal(), static_cast<int32_t>(o.threading)};
-        status.assign(static_cast<size_t>(n_scn), 0);
-        int64_t failed;
-        if (batch_dataset != nullptr) {
-            UpdateData const ud = update_of(*batch_dataset, scratch);
-            failed = m.calculate(mo, &ud, od, nullptr, status.data());
-        } else {
-            failed = m.calculate(mo, nullptr, od, nullptr, status.data());
+        try {
+            calculate_multi_dimensional(m, mo, out_ds, batch_dataset);
+        } catch (ApiBatchFailure& f) {
+            batch_failure = std::move(f);
+            batch_failed = true;
         }
-        scratch.scatter_outputs();
-        if (failed == 0) return;
-        if (batch_dataset == nullptr) {
-            // a single calculation reports the solver's exception itself (PGM_regular_error)
-            std::string msg = m.batch_message;
-            auto const colon = msg.find(": ");
-            if (msg.rfind("Error in batch #", 0) == 0 && colon != std::string::npos) msg = msg.substr(colon + 2);
-            throw CalculationError(msg);
-        }
-        batch_failed = true;
     });
     if (!batch_failed || handle == nullptr) return;
-    // BatchCalculationError (job_dispatch.hpp:208-224): combined message, failed scenario numbers, one message per scenario
-    std::string const& all = model->model->batch_message;
     handle->err_code = PGM_batch_error;
-    handle->err_msg = all;
-    std::string const tag = "Error in batch #";
-    size_t pos = all.find(tag);
-    while (pos != std::string::npos) {
-        size_t const next = all.find(tag, pos + tag.size());
-        std::string const entry = all.substr(pos, next == std::string::npos ? std::string::npos : next - pos);
-        size_t const colon = entry.find(": ");
-        PGM_Idx const scenario = std::strtoll(entry.c_str() + tag.size(), nullptr, 10);
-        std::string msg = colon == std::string::npos ? entry : entry.substr(colon + 2);
-        if (msg.size() >= 2 && msg.compare(msg.size() - 2, 2, "\n\n") == 0) msg.pop_back();
-        handle->failed_scenarios.push_back(scenario);
-        handle->batch_errs.push_back(std::move(msg));
-        pos = next;
-    }
-    if (handle->failed_scenarios.empty()) { // messages were not itemised: fall back on the status array
-        for (size_t s = 0; s != status.size(); ++s) {
-            if (status[s] != 0) {
-                handle->failed_scenarios.push_back(static_cast<PGM_Idx>(s));
-                handle->batch_errs.emplace_back("scenario failed\n");
-            }
-        }
-    }
+    handle->err_msg = std::move(batch_failure.message);
+    handle->failed_scenarios = std::move(batch_failure.scenarios);
+    handle->batch_errs = std::move(batch_failure.errors);
 }
 
 void PGM_destroy_model(PGM_PowerGridModel* model) { delete model; }

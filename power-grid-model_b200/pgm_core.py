@@ -146,7 +146,7 @@ class _Dataset:
 
     def __init__(self, handle, name, data, *, mutable, is_batch, batch_size):
         c = core()
-        self.handle, self.mutable, self.keep = handle, mutable, []
+        self.handle, self.mutable, self.keep, self.batch_size = handle, mutable, [], batch_size
         create = c.PGM_create_dataset_mutable if mutable else c.PGM_create_dataset_const
         self.ptr = create(handle.h, name.encode(), int(is_batch), int(batch_size))
         handle.check()
@@ -245,7 +245,18 @@ class PowerGridModel:
             c.PGM_set_threading(self.handle.h, opt, int(threading))
             c.PGM_set_tap_changing_strategy(self.handle.h, opt, int(tap_changing_strategy))
             batch, n_scn, upd = update_data is not None, 1, None
-            if batch:
+            if isinstance(update_data, (list, tuple)):  # cartesian product of batch dimensions, outermost first
+                dims = []
+                for data in update_data:
+                    size = np.asarray(next(iter(next(iter(data.values())).values())) if isinstance(next(iter(data.values())), dict)
+                                      and not _is_sparse(next(iter(data.values()))) else next(iter(data.values()))).shape[0]
+                    dims.append(_Dataset(self.handle, "update", data, mutable=False, is_batch=True, batch_size=size))
+                for outer, inner in zip(dims, dims[1:]):
+                    c.PGM_dataset_const_set_next_cartesian_product_dimension(self.handle.h, outer.ptr, inner.ptr)
+                    self.handle.check()
+                upd, n_scn = dims[0], int(np.prod([d.batch_size for d in dims]))
+                self._dims = dims
+            elif batch:
                 sizes = {(len(v["indptr"]) - 1) if _is_sparse(v) else
                          np.asarray(next(iter(v.values())) if isinstance(v, dict) else v).shape[0] for v in update_data.values()}
                 if len(sizes) > 1:

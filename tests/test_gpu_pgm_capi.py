@@ -193,3 +193,29 @@ def test_benchmark_batch_columnar_output():
                                       output_component_types={"node": ["u_pu", "u_angle"], "line": ["i_from"]})
     assert cols["node"]["u_pu"].tobytes() == rows["u_pu"].tobytes() and cols["node"]["u_angle"].tobytes() == rows["u_angle"].tobytes()
     assert cols["line"]["i_from"].shape == (64, len(grid.input_data["line"])) and (cols["line"]["i_from"] >= 0).all()
+
+
+def test_api_model_multi_dimension():
+    """tests/native_api_tests/test_api_model_multi_dimension.cpp: u_ref x p_specified x q_specified as a cartesian product of three
+    columnar update datasets without ids; source current = |p + jq| / (sqrt3 u_rated u_ref) in the flattened (i, j, k) order"""
+    node = initialize_array("input", "node", 1)
+    node["id"], node["u_rated"] = 0, 10e3
+    source = initialize_array("input", "source", 1)
+    source["id"], source["node"], source["status"], source["u_ref"], source["sk"] = 1, 0, 1, 1.0, 1e20
+    load = initialize_array("input", "sym_load", 1)
+    load["id"], load["node"], load["status"], load["type"], load["p_specified"], load["q_specified"] = 2, 0, 1, 0, 0.0, 0.0
+    model = pgm_core.PowerGridModel({"node": node, "source": source, "sym_load": load})
+    u_ref, p, q = np.array([0.9, 1.0, 1.1]), np.array([1e6, 2e6, 3e6, 4e6]), np.array([0.1e6, 0.2e6, 0.3e6, 0.4e6, 0.5e6])
+    dims = [{"source": {"u_ref": u_ref.reshape(-1, 1)}}, {"sym_load": {"p_specified": p.reshape(-1, 1)}},
+            {"sym_load": {"q_specified": q.reshape(-1, 1)}}]
+    res = model.calculate_power_flow(update_data=dims, output_component_types={"source": ["i"]})
+    expected = np.abs(p[None, :, None] + 1j * q[None, None, :]) / (np.sqrt(3) * 10e3 * u_ref[:, None, None])
+    assert res["source"]["i"].shape == (60, 1)
+    assert res["source"]["i"][:, 0] == pytest.approx(expected.reshape(-1), rel=1e-6)
+    # the model itself is untouched by the outer dimensions
+    single = model.calculate_power_flow(output_component_types=["source"])
+    assert single["source"]["i"][0] == pytest.approx(0.0, abs=1e-6)
+    # failures keep their flattened scenario numbers: with max_iter 1 nothing converges to 1e-100
+    with pytest.raises(pgm_core.PowerGridBatchError) as e:
+        model.calculate_power_flow(update_data=dims, output_component_types={"source": ["i"]}, max_iterations=1, error_tolerance=1e-100)
+    assert e.value.failed_scenarios.tolist() == list(range(60)) and len(e.value.error_messages) == 60

@@ -102,6 +102,18 @@ def test_handle_is_cleared_by_every_call_and_reports_dataset_errors():
     assert [c.PGM_dataset_info_n_attribute_indications(h.h, info, i) for i in range(2)] == [0, 1]
     assert c.PGM_dataset_info_attribute_name(h.h, info, 1, 0) == b"id"
     assert c.PGM_dataset_info_component_name(h.h, info, 2) is None and b"Index out of range" in c.PGM_error_message(h.h)
+    # cartesian product linked list: no self reference, no cycle (test_api_model_multi_dimension.cpp:105-110)
+    ds2 = c.PGM_create_dataset_const(h.h, b"update", 1, 2)
+    link = c.PGM_dataset_const_set_next_cartesian_product_dimension
+    link(h.h, ds, ds)
+    assert b"Cannot create cyclic cartesian product dimension linked list" in c.PGM_error_message(h.h)
+    link(h.h, ds, ds2)
+    assert c.PGM_error_code(h.h) == 0
+    link(h.h, ds2, ds)
+    assert b"Cannot create cyclic cartesian product dimension linked list" in c.PGM_error_message(h.h)
+    link(h.h, ds, None)
+    assert c.PGM_error_code(h.h) == 0
+    c.PGM_destroy_dataset_const(ds2)
     c.PGM_clear_error(h.h)
     assert c.PGM_error_code(h.h) == 0 and c.PGM_error_message(h.h) == b""
     c.PGM_destroy_dataset_const(ds)
