@@ -16,7 +16,7 @@
  *     voltage_regulator; sensors and faults may be present in the input dataset and are ignored by power flow like in the
  *     reference; any other component is PGM_regular_error at PGM_create_model;
  *   - tap_changing_strategy: any valid value (the model cannot hold a transformer_tap_regulator, so it is the plain power flow).
- * Everything else of the reference's C API (serialization, writable datasets, the PGM_def_* constants) is outside the hot path and not
+ * Everything else of the reference's C API (working serialization / writable datasets, the PGM_def_* constants) is outside the hot path and not
  * provided.  There is no CPU fallback: PGM_calculate on a host without a CUDA device reports PGM_regular_error.
  */
 #ifndef PGM_B200_CAPI_H
@@ -42,6 +42,9 @@ typedef struct PGM_MetaDataset PGM_MetaDataset;
 typedef struct PGM_MetaComponent PGM_MetaComponent;
 typedef struct PGM_MetaAttribute PGM_MetaAttribute;
 typedef struct PGM_DatasetInfo PGM_DatasetInfo;
+typedef struct PGM_WritableDataset PGM_WritableDataset;
+typedef struct PGM_Serializer PGM_Serializer;
+typedef struct PGM_Deserializer PGM_Deserializer;
 
 enum PGM_CalculationType { PGM_power_flow = 0, PGM_state_estimation = 1, PGM_short_circuit = 2 };
 enum PGM_CalculationMethod {
@@ -156,6 +159,30 @@ PGM_API void PGM_get_indexer(PGM_Handle* handle, PGM_PowerGridModel const* model
 PGM_API void PGM_calculate(PGM_Handle* handle, PGM_PowerGridModel* model, PGM_Options const* opt,
                            PGM_MutableDataset const* output_dataset, PGM_ConstDataset const* batch_dataset);
 PGM_API void PGM_destroy_model(PGM_PowerGridModel* model);
+
+/* serialization.h:29-114 and the writable-dataset calls of dataset.h:241-269 -- NOT provided: JSON / msgpack (de)serialization is
+ * off the calculation path.  The symbols exist so that a client which resolves the whole C API when it loads the library (the
+ * reference's Python wrapper does, _core/power_grid_core.py:146-194) can load this one; every call answers
+ * PGM_serialization_error ("... not provided by libpgm_b200 ...") and returns NULL / nothing. */
+PGM_API PGM_Deserializer* PGM_create_deserializer_from_binary_buffer(PGM_Handle* handle, char const* data, PGM_Idx size,
+                                                                     PGM_Idx serialization_format);
+PGM_API PGM_Deserializer* PGM_create_deserializer_from_null_terminated_string(PGM_Handle* handle, char const* data_string,
+                                                                              PGM_Idx serialization_format);
+PGM_API PGM_WritableDataset* PGM_deserializer_get_dataset(PGM_Handle* handle, PGM_Deserializer* deserializer);
+PGM_API void PGM_deserializer_parse_to_buffer(PGM_Handle* handle, PGM_Deserializer* deserializer);
+PGM_API void PGM_destroy_deserializer(PGM_Deserializer* deserializer);
+PGM_API PGM_Serializer* PGM_create_serializer(PGM_Handle* handle, PGM_ConstDataset const* dataset, PGM_Idx serialization_format);
+PGM_API void PGM_serializer_get_to_binary_buffer(PGM_Handle* handle, PGM_Serializer* serializer, PGM_Idx use_compact_list,
+                                                 char const** data, PGM_Idx* size);
+PGM_API char const* PGM_serializer_get_to_zero_terminated_string(PGM_Handle* handle, PGM_Serializer* serializer,
+                                                                 PGM_Idx use_compact_list, PGM_Idx indent);
+PGM_API void PGM_destroy_serializer(PGM_Serializer* serializer);
+PGM_API PGM_ConstDataset* PGM_create_dataset_const_from_writable(PGM_Handle* handle, PGM_WritableDataset const* writable_dataset);
+PGM_API PGM_DatasetInfo const* PGM_dataset_writable_get_info(PGM_Handle* handle, PGM_WritableDataset const* dataset);
+PGM_API void PGM_dataset_writable_set_buffer(PGM_Handle* handle, PGM_WritableDataset* dataset, char const* component,
+                                             PGM_Idx* indptr, void* data);
+PGM_API void PGM_dataset_writable_set_attribute_buffer(PGM_Handle* handle, PGM_WritableDataset* dataset, char const* component,
+                                                       char const* attribute, void* data);
 
 #ifdef __cplusplus
 }

@@ -19,7 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_library_exports_every_pgm_symbol():
     header = open(os.path.join(ROOT, "include", "pgm_b200_capi.h")).read()
     names = re.findall(r"PGM_API\s+[\w\s\*]+?\b(PGM_\w+)\s*\(", header)
-    assert len(names) == 70, len(names)
+    assert len(names) == 83, len(names)  # the reference's whole function surface (83 functions)
     lib = C.CDLL(os.path.join(ROOT, "power-grid-model_b200", "libpgm_b200.so"))
     for n in names:
         assert hasattr(lib, n), n
@@ -248,3 +248,19 @@ def test_buffer_create_set_nan_set_get_value():
     c.PGM_buffer_set_value(h.h, attr_q, ptr, None, 0, 1, -1)
     assert c.PGM_error_code(h.h) == pgm_core.PGM_REGULAR_ERROR
     c.PGM_destroy_buffer(ptr)
+
+
+def test_serialization_calls_answer_serialization_error():
+    """(de)serialization is off the path: the symbols exist (the reference's wrapper binds them at import), every call reports
+    PGM_serialization_error and returns nothing"""
+    c, h = pgm_core.core(), pgm_core.Handle()
+    lib = C.CDLL(pgm_core.LIB_PATH)
+    lib.PGM_create_deserializer_from_null_terminated_string.restype = C.c_void_p
+    lib.PGM_create_deserializer_from_null_terminated_string.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
+    assert lib.PGM_create_deserializer_from_null_terminated_string(h.h, b"{}", 0) is None
+    assert c.PGM_error_code(h.h) == pgm_core.PGM_SERIALIZATION_ERROR and b"not provided by libpgm_b200" in c.PGM_error_message(h.h)
+    lib.PGM_create_serializer.restype = C.c_void_p
+    lib.PGM_create_serializer.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+    assert lib.PGM_create_serializer(h.h, None, 0) is None and c.PGM_error_code(h.h) == pgm_core.PGM_SERIALIZATION_ERROR
+    lib.PGM_destroy_serializer.argtypes = [C.c_void_p]
+    lib.PGM_destroy_serializer(None)
