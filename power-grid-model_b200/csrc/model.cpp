@@ -993,6 +993,7 @@ int64_t Model::calculate_impl(ModelOptions const& opt, UpdateData const* update,
             }
         }
         bool device_done = false;
+        bool scenario_errors = false; // some scenario of a load / source-reference batch cannot be applied
         // branch-switching batches (N-1): scenarios that keep the grid connected run together on the base pattern; `todo` is
         // what remains for the exact per-scenario route below
         std::vector<Idx> todo;
@@ -1067,18 +1068,30 @@ int64_t Model::calculate_impl(ModelOptions const& opt, UpdateData const* update,
         if (device_done || (todo_is_subset && todo.empty())) {
             // results written by the device path
         } else if (!structural && !source_param_change) {
-            // fast path: one engine call for the whole batch
+            // fast path: one engine call for the whole batch.  A scenario whose update cannot be applied (unknown id, ...) fails
+            // alone in the reference (job_dispatch.hpp:162-206): such a batch takes the scenario-by-scenario route below, which
+            // records the message of every failing scenario and calculates the others.
             prepare_engines<B>();
             std::vector<std::vector<double>> sinj(topo_.math.size()), uref(topo_.math.size());
             RegulatorInput reg;
-            for (Idx s = 0; s != n; ++s) {
+            for (Idx s = 0; s != n && !scenario_errors; ++s) {
                 Saved saved;
-                apply_scenario(*update, s, &saved);
-                gather_pf_input<B>(sinj, uref, &reg);
+                try {
+                    apply_scenario(*update, s, &saved);
+                    gather_pf_input<B>(sinj, uref, &reg);
+                } catch (CudaError const&) {
+                    restore(saved);
+                    throw;
+                } catch (std::exception const&) {
+                    scenario_errors = true;
+                }
                 restore(saved);
             }
             timing[0] += ms_since(t0);
-            if (n != 0) failed = run_block<B>(opt, n, sinj, uref, out, 0, n_iter, status, &reg);
+            if (n != 0 && !scenario_errors) failed = run_block<B>(opt, n, sinj, uref, out, 0, n_iter, status, &reg);
+        }
+        if (device_done || (todo_is_subset && todo.empty())) {
+        } else if (!structural && !source_param_change && !scenario_errors) {
         } else {
             // general path: scenario by scenario (topology / parameters may change), still on the GPU.  Like the reference's
             // job dispatch (job_dispatch.hpp:88-160) the scenarios are spread over host threads, thread t taking scenarios
