@@ -222,3 +222,33 @@ def test_api_model_multi_dimension():
     failed = e.value.failed_scenarios.tolist()
     assert failed == sorted(set(failed)) and set(range(20)) | set(range(40, 60)) <= set(failed) <= set(range(60))
     assert len(e.value.error_messages) == len(failed) and all("Iteration failed to converge" in m for m in e.value.error_messages)
+
+
+def test_model_copies_calculate_concurrently_from_two_threads():
+    """SURVEY 8b "Threading": one handle per thread, one model per thread (PGM_copy_model); ctypes releases the GIL, so the two
+    PGM_calculate calls overlap on the device (each model drives its own CUDA streams).  Same bytes as the serial run."""
+    import threading
+
+    grid = pgm_b200.FictionalGrid(seed=0, **pgm_b200.BENCHMARK_OPTION)
+    updates = [grid.batch_update(200, seed=s) for s in (0, 1)]
+    base = pgm_core.PowerGridModel(grid.input_data)
+    serial = [base.calculate_power_flow(update_data=u, output_component_types=["node", "line"]) for u in updates]
+    models = [base.copy(), base.copy()]
+    results, errors = [None, None], []
+
+    def work(k):
+        try:
+            for _ in range(4):
+                results[k] = models[k].calculate_power_flow(update_data=updates[k], output_component_types=["node", "line"])
+        except Exception as ex:  # noqa: BLE001
+            errors.append(ex)
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for k in range(2):
+        for comp in ("node", "line"):
+            assert results[k][comp].tobytes() == serial[k][comp].tobytes(), (k, comp)

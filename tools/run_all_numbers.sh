@@ -22,3 +22,5 @@ ORACLE=0 ASYM=1 NODES=50000 N_SCN=512 python tools/time_n1.py 2>&1 | head -1
 echo "== config 5 shape against the CPU port (16 host threads), 256 scenarios on the 1804-bus grid"
 NODES=1500 N_SCN=256 python tools/time_n1.py 2>&1 | head -3
 ASYM=1 NODES=1500 N_SCN=256 python tools/time_n1.py 2>&1 | head -3
+echo "== drop-in: config 2 through the reference's unchanged Python wrapper / PGM_calculate (pageable buffers) vs page-locked reused buffers"
+python tools/time_reference_wrapper.py 2>&1 | tail -4
