@@ -193,6 +193,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: pgm_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dist = None
+    cpu_binding = pgm_b200.distributed.bind_process_to_device_cpus(local_rank) if world > 1 else None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -305,7 +306,8 @@ def main():
             "metric": "batch power-flow scenarios/sec (NR, fp64)", "value": value, "unit": "scenarios/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dev_time / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dict(workload_config(N_SCN), mean_nr_iterations=mean_iter, tile_width=os.environ.get("PGMB_TILE", "auto")),
+            "config": dict(workload_config(N_SCN), mean_nr_iterations=mean_iter, tile_width=os.environ.get("PGMB_TILE", "auto"),
+                           **({"rank0_cpu_binding": f"{len(cpu_binding)} CPUs local to the GPU (NVML affinity)"} if cpu_binding else {})),
             "e2e": {"value": world * N_SCN * args.steps / e2e_time, "unit": "scenarios/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_time / args.steps, "last_step_breakdown_ms": timing,
                     "gpu_launches": e2e_launches},

@@ -62,3 +62,29 @@ def _run(model, update, **kwargs):
     kwargs.setdefault("continue_on_batch_error", True)
     result = model.calculate_power_flow(update_data=update, **kwargs)
     return result, model.status.copy(), model.n_iter.copy()
+
+
+def bind_process_to_device_cpus(device: int):
+    """One process per GPU: keep this process (and therefore the page-locked host buffers it allocates, first touch) on the CPUs
+    that are local to its GPU (NVML's affinity mask = the NUMA node the GPU's PCIe root hangs off).  With 8 ranks each delivering
+    hundreds of MB of output structs per step, buffers on the far socket put every transfer across the inter-socket link.
+    Returns the CPU list it bound to, or None when NVML gives no usable mask (single-socket hosts, VMs) -- then nothing changes."""
+    import os
+
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = int(visible.split(",")[device]) if visible and all(v.strip().isdigit() for v in visible.split(",")) else device
+        handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus or cpus == allowed:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:  # noqa: BLE001 -- binding is an optimisation, never a requirement
+        return None
