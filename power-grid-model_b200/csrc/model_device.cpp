@@ -6,6 +6,8 @@
 // restore loop of the reference (job_dispatch.hpp:88-138, job_adapter.hpp:127-139).
 #include "model.hpp"
 
+#include <thread>
+
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -447,14 +449,30 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
     d.src_res.ensure(static_cast<size_t>(n_scn) * m.n_source() * src_row + 1);
     // The chunks only overlap when the caller's buffers are page-locked: a copy from / to pageable memory blocks the host
     // until the chunk's kernels are done, which would run the chunks one after another, each paying the solver's latency.
+    // Pageable OUTPUT buffers (what a client of PGM_calculate that allocates with malloc / numpy hands over) are served through a
+    // page-locked staging area owned by the model: every chunk's results go device -> staging asynchronously, and host threads
+    // copy a finished chunk into the caller's memory (faulting its fresh pages in parallel) while the next chunks are still in
+    // flight.  A direct cudaMemcpy into unfaulted pageable memory runs at a few GB/s on one driver thread.
+    size_t stage_off[12] = {};
+    size_t stage_bytes = 0;
+    bool staged = false;
     {
-        bool pinned = true;
+        bool out_pinned = true, in_pinned = true;
         for (Req const& r : reqs)
-            if (r.host != nullptr && r.count != 0) pinned = pinned && is_device_accessible_host(r.host);
+            if (r.host != nullptr && r.count != 0) out_pinned = out_pinned && is_device_accessible_host(r.host);
         for (int bfr = 0; bfr != 4; ++bfr)
-            if (ubufs[bfr]->data != nullptr && ubufs[bfr]->n != 0) pinned = pinned && is_device_accessible_host(ubufs[bfr]->data);
-        if (!pinned && std::getenv("PGMB_CHUNKS") == nullptr) n_chunk = 1;
+            if (ubufs[bfr]->data != nullptr && ubufs[bfr]->n != 0) in_pinned = in_pinned && is_device_accessible_host(ubufs[bfr]->data);
+        if (!out_pinned) {
+            for (Req const& r : reqs) {
+                if (r.host == nullptr || r.count == 0) continue;
+                stage_off[r.slot] = stage_bytes;
+                stage_bytes += (static_cast<size_t>(n_scn) * r.count * r.row + 4095) / 4096 * 4096;
+            }
+            staged = stage_bytes <= (size_t{3} << 29) && std::getenv("PGMB_NO_STAGING") == nullptr; // at most 1.5 GB page-locked
+        }
+        if (!staged && !(out_pinned && in_pinned) && std::getenv("PGMB_CHUNKS") == nullptr) n_chunk = 1;
     }
+    unsigned char* const stage = staged ? d.staging(stage_bytes) : nullptr;
     PGMB_CUDA(cudaEventRecord(d.fork, st));
 
     for (int c = 0; c != n_chunk; ++c) {
@@ -528,13 +546,54 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
         for (Req const& r : reqs) {
             if (r.host == nullptr || r.count == 0) continue;
             size_t const off = static_cast<size_t>(s0) * r.count * r.row;
-            PGMB_CUDA(cudaMemcpyAsync(static_cast<unsigned char*>(r.host) + off, d.out[r.slot].get() + off,
-                                      static_cast<size_t>(ns) * r.count * r.row, cudaMemcpyDeviceToHost, q));
+            unsigned char* const dst = staged ? stage + stage_off[r.slot] + off : static_cast<unsigned char*>(r.host) + off;
+            PGMB_CUDA(cudaMemcpyAsync(dst, d.out[r.slot].get() + off, static_cast<size_t>(ns) * r.count * r.row,
+                                      cudaMemcpyDeviceToHost, q));
         }
     }
     timing[1] += ms_since(t0);
 
     t0 = Clock::now();
+    if (staged) {
+        char const* const env_thr = std::getenv("PGMB_COPY_THREADS");
+        unsigned const n_copy = env_thr != nullptr ? std::max(1, std::atoi(env_thr))
+                                                   : std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+        for (int c = 0; c != n_chunk; ++c) {
+            PGMB_CUDA(cudaStreamSynchronize(d.cs[c]));
+            int64_t const tile_b = n_tile * c / n_chunk, tile_e = n_tile * (c + 1) / n_chunk;
+            int64_t const s0 = tile_b * tw, ns = std::min<int64_t>(tile_e * tw, n_scn) - s0;
+            if (ns <= 0) continue;
+            struct Piece {
+                unsigned char* dst;
+                unsigned char const* src;
+                size_t bytes;
+            };
+            std::vector<Piece> pieces;
+            size_t total = 0;
+            for (Req const& r : reqs) {
+                if (r.host == nullptr || r.count == 0) continue;
+                size_t const off = static_cast<size_t>(s0) * r.count * r.row, bytes = static_cast<size_t>(ns) * r.count * r.row;
+                pieces.push_back({static_cast<unsigned char*>(r.host) + off, stage + stage_off[r.slot] + off, bytes});
+                total += bytes;
+            }
+            unsigned const n_thr = total < (size_t{4} << 20) ? 1u : n_copy;
+            auto copy_share = [&pieces, n_thr](unsigned t) { // thread t takes the t-th 1/n_thr of every piece, cut at 4 KB
+                for (Piece const& p : pieces) {
+                    size_t const step = (p.bytes / n_thr + 4095) / 4096 * 4096;
+                    size_t const b = std::min(p.bytes, step * t), e2 = std::min(p.bytes, step * (t + 1));
+                    if (e2 > b) std::memcpy(p.dst + b, p.src + b, e2 - b);
+                }
+            };
+            if (n_thr == 1) {
+                copy_share(0);
+            } else {
+                std::vector<std::thread> pool;
+                for (unsigned t = 1; t != n_thr; ++t) pool.emplace_back(copy_share, t);
+                copy_share(0);
+                for (auto& th : pool) th.join();
+            }
+        }
+    }
     for (int c = 0; c != n_chunk; ++c) PGMB_CUDA(cudaStreamSynchronize(d.cs[c]));
     for (int c = 0; c != n_chunk; ++c) {
         float ms = 0.0f;
