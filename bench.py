@@ -276,6 +276,24 @@ def main():
     h2d = sum(v.nbytes for v in update.values())
     d2h = sum(v.nbytes for v in res.values())
 
+    # ---- informational, N = 1 only, after the timed regions: the same batch through the reference's own C API names
+    #      (PGM_create_model / PGM_calculate, pgm_b200.pgm_core) with PAGEABLE numpy buffers allocated per call -- what an unchanged
+    #      client of the reference's wrapper hands over; the library stages them through page-locked memory ----
+    drop_in = None
+    if world == 1:
+        from pgm_b200 import pgm_core
+
+        capi_model = pgm_core.PowerGridModel(grid.input_data)
+        comps = list(host_out)
+        ts = []
+        for _ in range(5):
+            t1 = time.perf_counter()
+            capi_model.calculate_power_flow(update_data=update, output_component_types=comps)
+            ts.append(time.perf_counter() - t1)
+        med = sorted(ts[2:])[1]
+        drop_in = {"value": N_SCN / med, "unit": "scenarios/s", "ms_per_step": 1e3 * med,
+                   "path": "PGM_calculate (reference C API names), pageable host buffers allocated per call, all outputs"}
+
     # ---- the other BASELINE configs, solver kernels only, rank 0 (reported beside the bench line, not part of it; after
     #      every timed region so that they cannot disturb it) ----
     other = None
@@ -310,7 +328,7 @@ def main():
                            **({"rank0_cpu_binding": f"{len(cpu_binding)} CPUs local to the GPU (NVML affinity)"} if cpu_binding else {})),
             "e2e": {"value": world * N_SCN * args.steps / e2e_time, "unit": "scenarios/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_time / args.steps, "last_step_breakdown_ms": timing,
-                    "gpu_launches": e2e_launches},
+                    "gpu_launches": e2e_launches, **({"drop_in_pageable": drop_in} if drop_in else {})},
             "gpu_launches": gpu_launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic(), "peak_kind": peak_kind, "kernel": "nr_sym_v3_kernel (path kernel of radial grids; the whole NR loop of a launch)",
