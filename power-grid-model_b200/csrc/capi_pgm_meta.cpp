@@ -9,6 +9,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <mutex>
+#include <unordered_set>
+
+#include "../../include/pgm_b200.h"
 
 using MetaAttribute = PGM_MetaAttribute;
 using MetaComponent = PGM_MetaComponent;
@@ -59,6 +63,11 @@ PGM_MetaDataset const* find_dataset(std::string_view name) {
 
 using namespace pgmb;
 using namespace pgmb::capi;
+
+namespace {
+std::mutex g_locked_mutex;
+std::unordered_set<void*> g_locked_buffers; // page-locked buffers handed out by PGM_create_buffer
+} // namespace
 
 namespace {
 MetaDataset const& dataset_by_name(char const* name) {
@@ -155,15 +164,43 @@ int PGM_is_little_endian(PGM_Handle* handle) {
 }
 
 // ---- buffers -------------------------------------------------------------------------------------------------------
+// Buffers of at least 64 KB are page-locked when a CUDA device is present (cudaHostAlloc): a client that allocates its datasets
+// through the API -- the reference's C++ wrapper and benchmark do (power_grid_model_cpp/buffer.hpp, fictional_grid_generator.hpp:
+// 192-204) -- then gets the direct, chunk-overlapped transfers of the device pipeline without knowing about CUDA.  Elsewhere
+// (no device, small buffers, allocation refused) it is the reference's aligned_alloc.
 void* PGM_create_buffer(PGM_Handle* handle, PGM_MetaComponent const* component, PGM_Idx size) {
     return call(handle, [&]() -> void* {
         MetaComponent const& c = deref(component);
         size_t const alignment = std::max(c.alignment, sizeof(void*));
         size_t const bytes = c.size * static_cast<size_t>(std::max<PGM_Idx>(size, 0));
+        if (bytes >= (size_t{64} << 10) && pgmb_device_count() > 0) {
+            void* p = nullptr;
+            if (pgmb_host_alloc(bytes, &p) == PGMB_OK && p != nullptr) {
+                std::lock_guard<std::mutex> const lock(g_locked_mutex);
+                g_locked_buffers.insert(p);
+                return p;
+            }
+        }
         return std::aligned_alloc(alignment, (bytes + alignment - 1) / alignment * alignment);
     });
 }
-void PGM_destroy_buffer(void* ptr) { std::free(ptr); }
+void PGM_destroy_buffer(void* ptr) {
+    if (ptr == nullptr) return;
+    {
+        std::lock_guard<std::mutex> const lock(g_locked_mutex);
+        auto const it = g_locked_buffers.find(ptr);
+        if (it != g_locked_buffers.end()) {
+            g_locked_buffers.erase(it);
+            pgmb_host_free(ptr);
+            return;
+        }
+    }
+    std::free(ptr);
+}
+int PGM_b200_buffer_is_page_locked(void const* ptr) {
+    std::lock_guard<std::mutex> const lock(g_locked_mutex);
+    return g_locked_buffers.count(const_cast<void*>(ptr)) != 0 ? 1 : 0;
+}
 void PGM_buffer_set_nan(PGM_Handle* handle, PGM_MetaComponent const* component, void* ptr, PGM_Idx buffer_offset, PGM_Idx size) {
     call(handle, [&] { deref(component).set_nan(&deref(static_cast<char*>(ptr)), buffer_offset, size); });
 }

@@ -252,3 +252,47 @@ def test_model_copies_calculate_concurrently_from_two_threads():
     for k in range(2):
         for comp in ("node", "line"):
             assert results[k][comp].tobytes() == serial[k][comp].tobytes(), (k, comp)
+
+
+def test_buffers_from_pgm_create_buffer_are_page_locked_and_filled_directly():
+    """A client that allocates its output through PGM_create_buffer (the reference's C++ wrapper / benchmark do) gets page-locked
+    memory on a GPU box; PGM_calculate fills it directly, with the same bytes as any other buffer"""
+    import ctypes as C
+    import time
+
+    c, h = pgm_core.core(), pgm_core.Handle()
+    c.PGM_b200_buffer_is_page_locked.argtypes = [C.c_void_p]
+    grid = pgm_b200.FictionalGrid(seed=0, **pgm_b200.BENCHMARK_OPTION)
+    n_scn = 1000
+    update = grid.batch_update(n_scn, seed=0)
+    model = pgm_core.PowerGridModel(grid.input_data)
+    expected = model.calculate_power_flow(update_data=update, output_component_types=["node", "line"])
+    views, ptrs = {}, []
+    for comp in ("node", "line"):
+        meta = c.PGM_meta_get_component_by_name(h.h, b"sym_output", comp.encode())
+        n = n_scn * len(grid.input_data[comp])
+        ptr = c.PGM_create_buffer(h.h, meta, n)
+        assert ptr and c.PGM_b200_buffer_is_page_locked(ptr) == 1
+        ptrs.append(ptr)
+        dt = pgm_b200.structs.SYM_OUTPUT[comp]
+        views[comp] = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(n * dt.itemsize,)).view(dt).reshape(n_scn, -1)
+    small = c.PGM_create_buffer(h.h, c.PGM_meta_get_component_by_name(h.h, b"input", b"node"), 4)
+    assert small and c.PGM_b200_buffer_is_page_locked(small) == 0
+    c.PGM_destroy_buffer(small)
+    out = pgm_core._Dataset(h, "sym_output", views, mutable=True, is_batch=True, batch_size=n_scn)
+    upd = pgm_core._Dataset(h, "update", update, mutable=False, is_batch=True, batch_size=n_scn)
+    opt = c.PGM_create_options(h.h)
+    times = []
+    for _ in range(4):
+        t = time.perf_counter()
+        c.PGM_calculate(h.h, model.ptr, opt, out.ptr, upd.ptr)
+        times.append(time.perf_counter() - t)
+        h.check()
+    for comp in views:
+        assert views[comp].tobytes() == expected[comp].tobytes(), comp
+    print(f"PGM_calculate into PGM_create_buffer memory: {min(times) * 1e3:.2f} ms per {n_scn} scenarios (node + line)")
+    c.PGM_destroy_options(opt)
+    del out, views
+    for ptr in ptrs:
+        c.PGM_destroy_buffer(ptr)
+        assert c.PGM_b200_buffer_is_page_locked(ptr) == 0

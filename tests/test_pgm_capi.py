@@ -19,6 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_library_exports_every_pgm_symbol():
     header = open(os.path.join(ROOT, "include", "pgm_b200_capi.h")).read()
     names = re.findall(r"PGM_API\s+[\w\s\*]+?\b(PGM_\w+)\s*\(", header)
+    names.remove("PGM_b200_buffer_is_page_locked")  # the one extension
     assert len(names) == 83, len(names)  # the reference's whole function surface (83 functions)
     lib = C.CDLL(os.path.join(ROOT, "power-grid-model_b200", "libpgm_b200.so"))
     for n in names:
