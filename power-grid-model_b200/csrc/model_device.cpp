@@ -470,7 +470,10 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
             }
             staged = stage_bytes <= (size_t{3} << 29) && std::getenv("PGMB_NO_STAGING") == nullptr; // at most 1.5 GB page-locked
         }
-        if (!staged && !(out_pinned && in_pinned) && std::getenv("PGMB_CHUNKS") == nullptr) n_chunk = 1;
+        // a copy INTO pageable memory returns only when the chunk's kernels are done, which would run the chunks one after another;
+        // a copy FROM pageable memory (update rows) returns once the driver has staged the rows, so it does not stop the overlap
+        (void)in_pinned;
+        if (!staged && !out_pinned && std::getenv("PGMB_CHUNKS") == nullptr) n_chunk = 1;
     }
     unsigned char* const stage = staged ? d.staging(stage_bytes) : nullptr;
     PGMB_CUDA(cudaEventRecord(d.fork, st));
