@@ -199,18 +199,29 @@ typedef struct pgmb_output_data {
     void *asym_line, *generic_branch; /* BranchOutput */
 } pgmb_output_data;
 
+/* pgmb_options.flags -- measurement of the device-resident pipeline (bench.py `value`): one load-profile batch on one device.
+ * RESIDENT_INPUT:  the update rows of this batch were uploaded by the previous calculate call on this model (same buffers and
+ *                  sizes) and are still in HBM: no host-to-device copy.
+ * RESIDENT_OUTPUT: the output structs are produced in HBM and stay there (no device-to-host copy; the caller's output buffers
+ *                  only select the components).  A following call without this flag delivers them. */
+#define PGMB_FLAG_RESIDENT_INPUT 1u
+#define PGMB_FLAG_RESIDENT_OUTPUT 2u
+
 /* PGM_Options (power_grid_model_c/src/options.hpp:16-27), PF subset */
 typedef struct pgmb_options {
     int32_t calculation_method; /* PGMB_METHOD_* */
     int32_t symmetric;          /* 1 symmetric, 0 asymmetric */
     double err_tol;
     int64_t max_iter;
-    int32_t n_devices;          /* reserved, 0 or 1: a process drives ONE device; scenarios are sharded over GPUs by running
-                                 * one process per GPU (bench.py under torchrun, pgm_b200.distributed) */
-    int32_t first_device;       /* CUDA device ordinal of this process */
+    int32_t n_devices;          /* GPUs ONE batch is spread over inside the call, starting at first_device: contiguous scenario
+                                 * blocks per device, one host thread + stream set per device, symbolic structures replicated,
+                                 * results into disjoint slices of the caller's buffers, no collective (the reference fans a batch
+                                 * out over host threads, job_dispatch.hpp:131-172).  0 / 1 = one device unless the environment
+                                 * variable PGMB_DEVICES names more (that is how a PGM_calculate client selects it). */
+    int32_t first_device;       /* CUDA device ordinal of the first device */
     int32_t threading;          /* host threads for batches whose scenarios change topology / parameters (each thread owns a
                                  * model copy, job_dispatch.hpp:88-160): -1 or 0 = all cores, n > 0 = n threads, 1 = sequential */
-    int32_t reserved;
+    uint32_t flags;             /* PGMB_FLAG_* */
 } pgmb_options;
 
 typedef struct pgmb_model pgmb_model;
@@ -238,8 +249,12 @@ PGMB_API int pgmb_model_batch_pf_input(pgmb_model* model, const pgmb_update_data
                                        int64_t math_group, double* s_injection, double* source_u_ref);
 /* timing of the last calculate call, milliseconds: [0] host prepare (tables, source references), [1] host time to
  * enqueue the chunk pipeline (H2D, kernels, D2H of every chunk), [2] solver kernels (CUDA events, summed over the chunks,
- * which overlap), [3] unused on the pipelined path, [4] wait for the pipeline to drain + status read-back, [5] total wall */
+ * which overlap), [3] host output conversion (per-scenario route only), [4] wait for the pipeline to drain + status read-back, [5] total wall */
 PGMB_API int pgmb_model_last_timing(pgmb_model* model, double* ms6);
+/* device time of the last calculate call's pipeline in milliseconds: CUDA events on the engine stream around
+ * (H2D ->) apply update -> solve -> result extraction / output structs (-> D2H) of all chunks; with several devices the
+ * maximum over the devices; 0 when the batch did not take the device pipeline */
+PGMB_API int pgmb_model_device_pipeline_ms(pgmb_model* model, double* ms);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Benchmark input: the reference's fictional grid generator (tests/benchmark_cpp/fictional_grid_generator.hpp)

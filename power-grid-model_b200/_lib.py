@@ -103,7 +103,11 @@ class OutputDataC(C.Structure):
 class OptionsC(C.Structure):
     _fields_ = [("calculation_method", C.c_int32), ("symmetric", C.c_int32), ("err_tol", C.c_double),
                 ("max_iter", C.c_int64), ("n_devices", C.c_int32), ("first_device", C.c_int32), ("threading", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("flags", C.c_uint32)]
+
+
+FLAG_RESIDENT_INPUT = 1
+FLAG_RESIDENT_OUTPUT = 2
 
 
 class GridOptionC(C.Structure):

@@ -45,7 +45,8 @@ int pgmb_model_calculate(pgmb_model* model, const pgmb_options* opt, const pgmb_
     int const rc = guarded([&] {
         if (model == nullptr || opt == nullptr || output == nullptr) throw InvalidArgument("null argument");
         if (opt->max_iter < 0 || opt->max_iter > (int64_t{1} << 30)) throw InvalidArgument("max_iter out of range");
-        ModelOptions const mo{opt->calculation_method, opt->symmetric != 0, opt->err_tol, opt->max_iter, opt->first_device, opt->threading};
+        ModelOptions const mo{opt->calculation_method, opt->symmetric != 0, opt->err_tol, opt->max_iter, opt->first_device, opt->threading,
+                              opt->n_devices, opt->flags};
         OutputData const od{output->node, output->line, output->transformer, output->shunt, output->source,
                             output->sym_gen, output->asym_gen, output->sym_load, output->asym_load,
                             output->voltage_regulator, output->asym_line, output->generic_branch};
@@ -104,6 +105,13 @@ int pgmb_model_last_timing(pgmb_model* model, double* ms6) {
     return guarded([&] {
         if (model == nullptr || ms6 == nullptr) throw InvalidArgument("null argument");
         for (int i = 0; i != 6; ++i) ms6[i] = model->model->timing[i];
+    });
+}
+
+int pgmb_model_device_pipeline_ms(pgmb_model* model, double* ms) {
+    return guarded([&] {
+        if (model == nullptr || ms == nullptr) throw InvalidArgument("null argument");
+        *ms = model->model->timing[6];
     });
 }
 

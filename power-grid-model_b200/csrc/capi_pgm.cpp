@@ -316,7 +316,7 @@ void calculate_single_dimension(Model& m, ModelOptions const& mo, Dataset const&
         size_t const colon = entry.find(": ");
         PGM_Idx const scenario = std::strtoll(entry.c_str() + tag.size(), nullptr, 10);
         std::string msg = colon == std::string::npos ? entry : entry.substr(colon + 2);
-        if (msg.size() >= 2 && msg.compare(msg.size() - 2, 2, "\n\n") == 0) msg.pop_back();
+        if (!msg.empty() && msg.back() == '\n') msg.pop_back(); // the line break the batch message adds behind what()
         f.scenarios.push_back(scenario);
         f.errors.push_back(std::move(msg));
         pos = next;
@@ -621,7 +621,21 @@ void PGM_calculate(PGM_Handle* handle, PGM_PowerGridModel* model, PGM_Options co
             throw DatasetError("The output dataset '" + out_ds.name + "' does not match the calculation symmetry!\n");
         }
         if (o.max_iter < 0 || o.max_iter > (PGM_Idx{1} << 30)) throw InvalidArgument("max_iter out of range\n");
-        ModelOptions const mo{method, sym, o.err_tol, o.max_iter, device_ordinal(), static_cast<int32_t>(o.threading)};
+        // threading (job_dispatch.hpp:166-171): < 0 = sequential, 0 = hardware concurrency, n = n threads.  It only matters for
+        // batches that take the per-scenario route (own topology per scenario); load batches run on the GPU in one pipeline.
+        int32_t const threading = o.threading < 0 ? 1 : static_cast<int32_t>(std::min<PGM_Idx>(o.threading, 1 << 20));
+        ModelOptions const mo{method, sym, o.err_tol, o.max_iter, device_ordinal(), threading};
+        // the output of a cartesian product holds the product of all dimension sizes (model.cpp:290-334 asserts it)
+        if (batch_dataset != nullptr) {
+            PGM_Idx total = 1;
+            for (Dataset const* d = batch_dataset; d != nullptr; d = d->next) {
+                total *= d->batch_size;
+            }
+            if (out_ds.batch_size != total) {
+                throw DatasetError("The batch size of the output dataset (" + std::to_string(out_ds.batch_size) +
+                                   ") does not match the product of the batch dimensions (" + std::to_string(total) + ")!\n");
+            }
+        }
         try {
             calculate_multi_dimensional(m, mo, out_ds, batch_dataset);
         } catch (ApiBatchFailure& f) {

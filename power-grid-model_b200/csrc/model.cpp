@@ -1,5 +1,7 @@
 #include "model.hpp"
 
+#include <charconv>
+
 #include <exception>
 #include <thread>
 
@@ -300,6 +302,7 @@ template <int B> void Model::prepare_engines() {
     constexpr int si = B == 1 ? 0 : 1;
     for (size_t g = 0; g != topo_.math.size(); ++g) {
         auto& e = engines_[g].engine[si];
+        if (e && e->device() != device_) e.reset(); // the caller moved the model to another GPU
         bool const fresh = !e;
         if (fresh) e = std::make_unique<Engine>(topo_.math[g], B == 1, device_);
         if (fresh || !param_valid_[si]) {
@@ -366,6 +369,24 @@ void Model::gather_pf_input(std::vector<std::vector<double>>& sinj, std::vector<
         uref[c.group][base_u[c.group] + c.pos * 2] = u.real();
         uref[c.group][base_u[c.group] + c.pos * 2 + 1] = u.imag();
     }
+}
+
+std::string scenario_failure_text(int32_t status, int64_t max_iter, double max_dev, double err_tol) {
+    auto shortest = [](double v) { // std::format("{}", double)
+        char buf[64];
+        auto const r = std::to_chars(buf, buf + sizeof(buf), v);
+        return std::string(buf, r.ptr);
+    };
+    if (status == 1) {
+        return "Iteration failed to converge after " + std::to_string(max_iter) + " iterations! Max deviation: " + shortest(max_dev) +
+               ", error tolerance: " + shortest(err_tol) + ".\n";
+    }
+    if (status == 4) return "Unallocated Q remains after distribution on a regulated bus";
+    return "Sparse matrix error, possibly singular matrix!\n"
+           "If you get this error from state estimation, "
+           "it might mean the system is not fully observable, i.e. not enough measurements.\n"
+           "It might also mean that you are running into a corner case where PGM cannot resolve yet.\n"
+           "See https://github.com/PowerGridModel/power-grid-model/issues/864.";
 }
 
 void Model::mark(bool topo, bool param, Saved* saved) {
@@ -505,7 +526,25 @@ void Model::restore(Saved const& s) {
     if (s.param) param_valid_[0] = param_valid_[1] = false;
 }
 
-void Model::update_permanent(UpdateData const& update) { apply_scenario(update, 0, nullptr); }
+// Permanent update: the reference resolves every id before it changes anything (get_all_sequence_idx_map,
+// main_model_impl.hpp:191-197), so an unknown id leaves the model untouched.  Here the components are applied one by one with
+// their previous state recorded, and a failure rolls everything back before it is reported.
+void Model::update_permanent(UpdateData const& update) {
+    Saved saved;
+    bool const topo_was_valid = topo_valid_;
+    bool const param_was_valid[2] = {param_valid_[0], param_valid_[1]};
+    try {
+        apply_scenario(update, 0, &saved);
+    } catch (...) {
+        restore(saved);
+        // the state is the old one again and nothing was rebuilt in between: the caches are as valid as they were
+        topo_valid_ = topo_was_valid;
+        param_valid_[0] = param_was_valid[0];
+        param_valid_[1] = param_was_valid[1];
+        throw;
+    }
+    ++state_version_;
+}
 
 void Model::batch_pf_input(UpdateData const& update, bool symmetric, Idx group, double* s_injection, double* source_u_ref) {
     prepare_topology();
@@ -703,6 +742,7 @@ int64_t Model::run_block(ModelOptions const& opt, Idx n_scn, std::vector<std::ve
     for (auto& v : so) v.resize(topo_.math.size());
     std::vector<std::vector<int8_t>> reg_out(topo_.math.size());
     std::vector<int32_t> st_all(n_scn, 0), it_all(n_scn, 0);
+    std::vector<double> dev_all(n_scn, 0.0);
     for (size_t g = 0; g != topo_.math.size(); ++g) {
         auto const& m = topo_.math[g];
         Engine& e = *engines_[g].engine[si];
@@ -712,8 +752,9 @@ int64_t Model::run_block(ModelOptions const& opt, Idx n_scn, std::vector<std::ve
         so[4][g].resize(n_scn * m.n_shunt() * 2 * c2);
         so[5][g].resize(n_scn * m.n_load_gen() * 2 * c2);
         std::vector<int32_t> st(n_scn), it(n_scn);
+        std::vector<double> dev(n_scn);
         SolverOutputView view{so[0][g].data(), nullptr, so[2][g].data(), so[3][g].data(), so[4][g].data(), so[5][g].data(),
-                              st.data(), it.data(), nullptr};
+                              st.data(), it.data(), dev.data()};
         PfInputView in_view{n_scn, uref[g].data(), false, sinj[g].data()};
         if (e.has_regulators()) {
             if (reg == nullptr) throw InvalidArgument("internal: regulator input missing");
@@ -730,6 +771,7 @@ int64_t Model::run_block(ModelOptions const& opt, Idx n_scn, std::vector<std::ve
         e.fetch(view);
         timing[4] += ms_since(t0);
         for (Idx s = 0; s != n_scn; ++s) {
+            if (st_all[s] == 0 && st[s] != 0) dev_all[s] = dev[s];
             if (st_all[s] == 0) st_all[s] = st[s];
             it_all[s] = std::max(it_all[s], it[s]);
         }
@@ -744,9 +786,7 @@ int64_t Model::run_block(ModelOptions const& opt, Idx n_scn, std::vector<std::ve
         if (st_all[s] != 0) {
             ++failed;
             batch_message += "Error in batch #" + std::to_string(first + s) + ": " +
-                             (st_all[s] == 1   ? "Iteration failed to converge after " + std::to_string(opt.max_iter) + " iterations!"
-                              : st_all[s] == 4 ? std::string("Unallocated Q remains after distribution on a regulated bus")
-                                               : std::string("Sparse matrix error, possibly singular matrix!")) + "\n";
+                             scenario_failure_text(st_all[s], opt.max_iter, dev_all[s], opt.err_tol) + "\n";
         }
     }
     return failed;
@@ -877,17 +917,24 @@ template <int B> bool Model::plan_outage_batch(UpdateData const& u, OutagePlan& 
             if (from != kNaIntS) it->from = from != 0;
             if (to != kNaIntS) it->to = to != 0;
         };
-        {
-            auto [b, e] = scenario_span<BranchUpdate>(u.line, s);
-            for (auto p = b; p != e; ++p) note(lookup(p->id, p - b, e - b, n_line(), line_idx_), p->from_status, p->to_status);
-        }
-        {
-            auto [b, e] = scenario_span<TransformerUpdate>(u.transformer, s);
-            for (auto p = b; p != e; ++p) {
-                Idx const i = lookup(p->id, p - b, e - b, n_trafo(), trafo_idx_);
-                if (p->tap_pos != kNaIntS && p->tap_pos != trafo_st_[i].tap_pos) exact = true;
-                note(off_trafo() + i, p->from_status, p->to_status);
+        try {
+            {
+                auto [b, e] = scenario_span<BranchUpdate>(u.line, s);
+                for (auto p = b; p != e; ++p) note(lookup(p->id, p - b, e - b, n_line(), line_idx_), p->from_status, p->to_status);
             }
+            {
+                auto [b, e] = scenario_span<TransformerUpdate>(u.transformer, s);
+                for (auto p = b; p != e; ++p) {
+                    Idx const i = lookup(p->id, p - b, e - b, n_trafo(), trafo_idx_);
+                    if (p->tap_pos != kNaIntS && p->tap_pos != trafo_st_[i].tap_pos) exact = true;
+                    note(off_trafo() + i, p->from_status, p->to_status);
+                }
+            }
+        } catch (InvalidArgument const&) {
+            // an update that cannot be applied fails this scenario alone (job_dispatch.hpp:162-206): the per-scenario route
+            // records its message and the other scenarios are still calculated
+            plan.exact.push_back(s);
+            continue;
         }
         std::erase_if(changes, [this](Change const& c) { return c.from == branch_st_[c.branch].from_status && c.to == branch_st_[c.branch].to_status; });
         if (!exact && changes.size() == 1) {
@@ -1029,6 +1076,7 @@ int64_t Model::calculate_impl(ModelOptions const& opt, UpdateData const* update,
                     throw;
                 }
                 outage_plan_ = nullptr;
+                if (r < 0) batch_message.clear(); // messages of parts that ran before the attempt was given up
                 t0 = Clock::now();
                 if (r >= 0) {
                     failed = r;
@@ -1062,6 +1110,8 @@ int64_t Model::calculate_impl(ModelOptions const& opt, UpdateData const* update,
             if (r >= 0) {
                 failed = r;
                 device_done = true;
+            } else {
+                batch_message.clear(); // messages of parts that ran before the attempt was given up
             }
             t0 = Clock::now();
         }
@@ -1104,6 +1154,17 @@ int64_t Model::calculate_impl(ModelOptions const& opt, UpdateData const* update,
             Idx const n_todo = static_cast<Idx>(todo.size());
             Idx n_threads = opt.threading > 0 ? opt.threading : static_cast<Idx>(std::thread::hardware_concurrency());
             n_threads = std::max<Idx>(1, std::min<Idx>({n_threads, n_todo, Idx{32}}));
+            // several GPUs (opt.n_devices / PGMB_DEVICES): the host threads are dealt round robin over the devices
+            Idx n_dev_general = opt.n_devices;
+            if (n_dev_general <= 1) {
+                char const* env = std::getenv("PGMB_DEVICES");
+                n_dev_general = env != nullptr ? std::atoi(env) : 1;
+            }
+            {
+                int available = 0;
+                if (cudaGetDeviceCount(&available) != cudaSuccess) available = 0;
+                n_dev_general = std::max<Idx>(1, std::min<Idx>(n_dev_general, available - opt.device));
+            }
             std::vector<std::string> messages(n);
             std::vector<int64_t> failed_per_thread(n_threads, 0);
             std::vector<std::exception_ptr> fatal(n_threads);
@@ -1144,6 +1205,7 @@ int64_t Model::calculate_impl(ModelOptions const& opt, UpdateData const* update,
                 for (Idx t = 0; t != n_threads; ++t) {
                     copies.push_back(std::make_unique<Model>(*this));
                     copies.back()->dev_.reset();
+                    copies.back()->device_ = opt.device + static_cast<int>(t % n_dev_general);
                     copies.back()->batch_message.clear();
                 }
                 std::vector<std::thread> pool;

@@ -41,7 +41,15 @@ struct ModelOptions {
     int64_t max_iter;
     int32_t device;
     int32_t threading{-1}; // structural batches: -1 / 0 = all cores, n > 0 = n host threads
+    int32_t n_devices{1};  // GPUs one batch is spread over (contiguous scenario blocks), starting at `device`
+    uint32_t flags{0};     // PGMB_FLAG_* (include/pgm_b200.h): device-resident update rows / output structs
 };
+constexpr uint32_t kFlagResidentInput = 1u;  // the update rows of this batch are already in HBM (previous call, same buffers)
+constexpr uint32_t kFlagResidentOutput = 2u; // leave the output structs in HBM (no copy to the caller's buffers)
+
+// what() of the exception the reference throws for a failed scenario (common/exception.hpp:82-110: SparseMatrixError,
+// IterationDiverge with std::format("{}") of max_dev / err_tol = shortest round-trip decimal)
+std::string scenario_failure_text(int32_t status, int64_t max_iter, double max_dev, double err_tol);
 
 struct BatchFailure : std::runtime_error {
     using std::runtime_error::runtime_error;
@@ -61,7 +69,7 @@ class Model {
     Idx n_math_groups();
     std::vector<int64_t> const& get_index(Idx group, std::string const& name);
     std::vector<double> const& get_real(Idx group, bool symmetric, std::string const& name);
-    double timing[6]{};
+    double timing[8]{}; // pgmb_model_last_timing: [0..5]; [6] device time of the pipeline (pgmb_model_device_pipeline_ms)
     std::string batch_message;
 
     // PGM_copy_model / PGM_get_indexer (main_model_impl.hpp:218-228) and the element counts the output dataset is checked
@@ -127,6 +135,26 @@ class Model {
     };
     std::vector<GroupEngines> engines_;
     int device_{0};
+    // In-process multi-GPU (job_dispatch.hpp:131-172 spreads a batch over host threads; here over devices): device k > 0 is
+    // driven by a replica of this model (own engines, streams and device tables on that GPU) that is kept across calls and
+    // rebuilt when the permanent state changed.  A copy of the model starts without replicas.
+    uint64_t state_version_{0};
+    struct Replicas {
+        struct Item {
+            std::unique_ptr<Model> model;
+            uint64_t version;
+        };
+        std::vector<Item> list;
+        Replicas() = default;
+        Replicas(Replicas const&) {}
+        Replicas& operator=(Replicas const&) {
+            list.clear();
+            return *this;
+        }
+        Replicas(Replicas&&) = default;
+        Replicas& operator=(Replicas&&) = default;
+    };
+    Replicas replicas_;
     std::map<std::string, std::vector<int64_t>> index_cache_;
     std::map<std::string, std::vector<double>> real_cache_;
 
@@ -212,6 +240,8 @@ class Model {
     bool device_path_eligible(UpdateData const& update) const;
     int64_t run_batch_device(ModelOptions const& opt, int phases, UpdateData const& update, OutputData const& out, int32_t* n_iter,
                              int32_t* status);
+    int64_t run_batch_device_one(ModelOptions const& opt, int phases, UpdateData const& update, OutputData const& out,
+                                 int32_t* n_iter, int32_t* status, Idx first_scenario);
     int64_t run_batch_device_part(ModelOptions const& opt, int phases, UpdateData const& update, OutputData const& out,
                                   int32_t* n_iter, int32_t* status, Idx first_scenario);
     template <int B>

@@ -52,17 +52,31 @@ struct Model::DeviceSide {
     // chunk pipeline: one stream per chunk in flight, fork event on the engine stream, solve brackets per chunk
     static constexpr int kMaxChunk = 8;
     cudaStream_t cs[kMaxChunk]{};
-    cudaEvent_t fork{}, ev_a[kMaxChunk]{}, ev_b[kMaxChunk]{};
+    cudaEvent_t fork{}, ev_a[kMaxChunk]{}, ev_b[kMaxChunk]{}, ev_end[kMaxChunk]{};
+    cudaEvent_t ev_p0{}, ev_p1{}; // the whole pipeline of one part on the engine stream (fork .. join of every chunk)
     bool streams_ready{false};
-    void ensure_streams() {
+    int device{-1}; // the GPU the streams, events and tables live on
+    size_t resident_rows[4]{}; // bytes of update rows per component uploaded by the last call (PGMB_FLAG_RESIDENT_INPUT)
+    void ensure_streams(int dev) {
+        PGMB_CUDA(cudaSetDevice(dev));
         if (streams_ready) return;
+        device = dev;
         for (auto& q : cs) PGMB_CUDA(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
         PGMB_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
         for (auto& ev : ev_a) PGMB_CUDA(cudaEventCreate(&ev));
         for (auto& ev : ev_b) PGMB_CUDA(cudaEventCreate(&ev));
+        for (auto& ev : ev_end) PGMB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        PGMB_CUDA(cudaEventCreate(&ev_p0));
+        PGMB_CUDA(cudaEventCreate(&ev_p1));
         streams_ready = true;
     }
+    void drain() noexcept { // nothing of this pipeline may still read or write caller / staging memory after an error
+        if (!streams_ready) return;
+        if (device >= 0) cudaSetDevice(device);
+        for (auto& q : cs) cudaStreamSynchronize(q);
+    }
     ~DeviceSide() {
+        if (device >= 0) cudaSetDevice(device);
         if (pinned != nullptr) cudaFreeHost(pinned);
         if (streams_ready) {
             for (auto& q : cs) cudaStreamSynchronize(q); // the buffers go back to the pool: nothing may still use them
@@ -70,6 +84,9 @@ struct Model::DeviceSide {
             cudaEventDestroy(fork);
             for (auto& ev : ev_a) cudaEventDestroy(ev);
             for (auto& ev : ev_b) cudaEventDestroy(ev);
+            for (auto& ev : ev_end) cudaEventDestroy(ev);
+            cudaEventDestroy(ev_p0);
+            cudaEventDestroy(ev_p1);
         }
     }
     unsigned char* staging(size_t bytes) {
@@ -92,11 +109,135 @@ bool Model::device_path_eligible(UpdateData const& u) const {
     return u.n_scenarios > 0;
 }
 
+namespace {
+// views of the caller's update / output buffers for the scenarios [s0, s0 + ns) of a uniform batch
+struct OutPart {
+    size_t row;
+    Idx count;
+};
+void slice_batch(UpdateData const& update, OutputData const& out, OutPart const (&outs)[12], Idx s0, Idx ns, UpdateData& u, OutputData& o) {
+    size_t const urow[4] = {sizeof(SymLoadGenUpdate), sizeof(AsymLoadGenUpdate), sizeof(SymLoadGenUpdate), sizeof(AsymLoadGenUpdate)};
+    u = update;
+    u.n_scenarios = ns;
+    ComponentBuffer* ub[4] = {&u.sym_gen, &u.asym_gen, &u.sym_load, &u.asym_load};
+    for (int b = 0; b != 4; ++b)
+        if (ub[b]->data != nullptr) ub[b]->data = static_cast<unsigned char const*>(ub[b]->data) + static_cast<size_t>(s0) * ub[b]->n * urow[b];
+    if (u.source.data != nullptr) {
+        if (u.source.indptr != nullptr) {
+            u.source.indptr += s0; // sparse: scenario s of the part is scenario s0 + s of the caller's index pointer
+        } else {
+            u.source.data = static_cast<unsigned char const*>(u.source.data) + static_cast<size_t>(s0) * u.source.n * sizeof(SourceUpdate);
+        }
+    }
+    o = out;
+    void** ohost[12] = {&o.node, &o.line, &o.transformer, &o.shunt, &o.source, &o.sym_gen, &o.asym_gen, &o.sym_load, &o.asym_load,
+                        &o.voltage_regulator, &o.asym_line, &o.generic_branch};
+    for (int k = 0; k != 12; ++k)
+        if (*ohost[k] != nullptr) *ohost[k] = static_cast<unsigned char*>(*ohost[k]) + static_cast<size_t>(s0) * outs[k].count * outs[k].row;
+}
+} // namespace
+
 // returns number of failed scenarios, or -1 when the batch turned out not to be uniform (caller falls back to the host path)
-// A batch whose working set would not fit the device is cut into parts that are run one after another; the parts see
-// offset views of the caller's update / output buffers.
+//
+// In-process multi-GPU: the reference fans one batch out over host threads inside the call (job_dispatch.hpp:131-172); here the
+// batch is cut into contiguous scenario blocks, one per device (opt.n_devices / PGMB_DEVICES, starting at opt.device).  Device 0
+// of the call is driven by this model on the calling thread, every further device by a replica of the model on its own host
+// thread (own engines: the symbolic structures are rebuilt from the same math topology and uploaded to that device; own
+// streams, tables and staging).  The blocks write disjoint slices of the caller's buffers; the per-scenario status arrays and
+// the batch messages are concatenated in scenario order.  No collective, no peer traffic.
 int64_t Model::run_batch_device(ModelOptions const& opt, int phases, UpdateData const& update, OutputData const& out, int32_t* n_iter,
                                 int32_t* status) {
+    Idx const n_scn = update.n_scenarios;
+    int n_dev = opt.n_devices;
+    if (n_dev <= 1) {
+        char const* env = std::getenv("PGMB_DEVICES");
+        n_dev = env != nullptr ? std::atoi(env) : 1;
+    }
+    int available = 0;
+    if (cudaGetDeviceCount(&available) != cudaSuccess) available = 0;
+    n_dev = std::max(1, std::min(n_dev, available - opt.device));
+    Idx min_per_dev = 256;
+    if (char const* env = std::getenv("PGMB_MIN_SCENARIOS_PER_DEVICE")) min_per_dev = std::max<Idx>(1, std::atoll(env));
+    n_dev = static_cast<int>(std::max<Idx>(1, std::min<Idx>(n_dev, n_scn / min_per_dev)));
+    if (n_dev == 1) return run_batch_device_one(opt, phases, update, out, n_iter, status, 0);
+
+    bool const sym = phases == 1;
+    size_t const row_node = sym ? sizeof(NodeOutput<1>) : sizeof(NodeOutput<3>);
+    size_t const row_branch = sym ? sizeof(BranchOutput<1>) : sizeof(BranchOutput<3>);
+    size_t const row_app = sym ? sizeof(ApplianceOutput<1>) : sizeof(ApplianceOutput<3>);
+    OutPart const outs[12] = {{row_node, static_cast<Idx>(node_.size())}, {row_branch, n_line()}, {row_branch, n_trafo()},
+                              {row_app, static_cast<Idx>(shunt_in_.size())}, {row_app, static_cast<Idx>(source_in_.size())},
+                              {row_app, n_sym_gen_}, {row_app, n_asym_gen_}, {row_app, n_sym_load_}, {row_app, n_asym_load_},
+                              {sizeof(VoltageRegulatorOutput), static_cast<Idx>(reg_in_.size())}, {row_branch, n_aline()}, {row_branch, n_gb()}};
+    // replicas for devices 1 .. n_dev - 1 (kept across calls; rebuilt when the permanent state has changed since)
+    if (replicas_.list.size() < static_cast<size_t>(n_dev - 1)) replicas_.list.resize(n_dev - 1);
+    for (int k = 1; k != n_dev; ++k) {
+        auto& r = replicas_.list[k - 1];
+        if (!r.model || r.version != state_version_ || r.model->device_ != opt.device + k) {
+            r.model = clone();
+            r.model->device_ = opt.device + k;
+            r.version = state_version_;
+        }
+    }
+    // contiguous blocks, cut at multiples of 32 scenarios (whole tiles whatever the tile width)
+    Idx const block = ((n_scn + n_dev - 1) / n_dev + 31) / 32 * 32;
+    std::vector<int64_t> failed(n_dev, 0);
+    std::vector<std::exception_ptr> error(n_dev);
+    auto run_on = [&](int k) {
+        try {
+            Idx const s0 = std::min<Idx>(n_scn, block * k), ns = std::min<Idx>(n_scn, block * (k + 1)) - s0;
+            if (ns <= 0) return;
+            UpdateData u;
+            OutputData o;
+            slice_batch(update, out, outs, s0, ns, u, o);
+            Model& m = k == 0 ? *this : *replicas_.list[k - 1].model;
+            ModelOptions mo = opt;
+            mo.device = opt.device + k;
+            mo.n_devices = 1;
+            if (k != 0) {
+                m.outage_plan_ = outage_plan_;
+                m.batch_message.clear();
+                for (double& t : m.timing) t = 0.0;
+                if (phases == 1) {
+                    m.prepare_engines<1>();
+                } else {
+                    m.prepare_engines<3>();
+                }
+            }
+            failed[k] = m.run_batch_device_one(mo, phases, u, o, n_iter ? n_iter + s0 : nullptr, status ? status + s0 : nullptr, s0);
+        } catch (...) {
+            error[k] = std::current_exception();
+        }
+        if (k != 0) replicas_.list[k - 1].model->outage_plan_ = nullptr;
+    };
+    {
+        std::vector<std::thread> pool;
+        for (int k = 1; k != n_dev; ++k) pool.emplace_back(run_on, k);
+        run_on(0);
+        for (auto& th : pool) th.join();
+    }
+    PGMB_CUDA(cudaSetDevice(opt.device));
+    for (auto const& ex : error)
+        if (ex) std::rethrow_exception(ex);
+    int64_t total = 0;
+    for (int k = 0; k != n_dev; ++k) {
+        if (failed[k] < 0) return -1;
+        total += failed[k];
+    }
+    for (int k = 1; k != n_dev; ++k) {
+        Model const& m = *replicas_.list[k - 1].model;
+        batch_message += m.batch_message;
+        for (int i = 0; i != 7; ++i)
+            if (i != 5) timing[i] = std::max(timing[i], m.timing[i]); // the devices work side by side
+    }
+    return total;
+}
+
+// One device.  A batch whose working set would not fit the device is cut into parts that are run one after another; the parts
+// see offset views of the caller's update / output buffers.  first_scenario = number of the block's first scenario in the
+// caller's batch (messages, outage plan).
+int64_t Model::run_batch_device_one(ModelOptions const& opt, int phases, UpdateData const& update, OutputData const& out,
+                                    int32_t* n_iter, int32_t* status, Idx first_scenario) {
     bool const sym = phases == 1;
     Engine& e = *engines_[0].engine[sym ? 0 : 1];
     MathTopology const& m = topo_.math[0];
@@ -133,9 +274,9 @@ int64_t Model::run_batch_device(ModelOptions const& opt, int phases, UpdateData 
     // total memory of the device, queried once: cudaMemGetInfo costs milliseconds in a process with many allocations
     static size_t total_cache[64] = {};
     int const dev_slot = e.device() % 64;
+    PGMB_CUDA(cudaSetDevice(e.device())); // every allocation / stream below belongs to the engine's device
     if (total_cache[dev_slot] == 0) {
         size_t free_b = 0, total_b = 0;
-        PGMB_CUDA(cudaSetDevice(e.device()));
         PGMB_CUDA(cudaMemGetInfo(&free_b, &total_b));
         total_cache[dev_slot] = total_b;
     }
@@ -143,28 +284,19 @@ int64_t Model::run_batch_device(ModelOptions const& opt, int phases, UpdateData 
     if (char const* env = std::getenv("PGMB_MAX_BATCH_BYTES")) budget = static_cast<size_t>(std::atoll(env));
     Idx const n_scn = update.n_scenarios;
     Idx max_scn = static_cast<Idx>(std::max<size_t>(32, budget / per_scn / 32 * 32));
-    if (n_scn <= max_scn) return run_batch_device_part(opt, phases, update, out, n_iter, status, 0);
+    if (n_scn <= max_scn) return run_batch_device_part(opt, phases, update, out, n_iter, status, first_scenario);
+    OutPart parts[12];
+    for (int k = 0; k != 12; ++k) parts[k] = {outs[k].row, outs[k].count};
     int64_t failed = 0;
     for (Idx s0 = 0; s0 < n_scn; s0 += max_scn) {
         Idx const ns = std::min(max_scn, n_scn - s0);
-        UpdateData u = update;
-        u.n_scenarios = ns;
-        ComponentBuffer* ub[4] = {&u.sym_gen, &u.asym_gen, &u.sym_load, &u.asym_load};
-        for (int b = 0; b != 4; ++b)
-            if (ub[b]->data != nullptr) ub[b]->data = static_cast<unsigned char const*>(ub[b]->data) + static_cast<size_t>(s0) * ub[b]->n * urow[b];
-        if (u.source.data != nullptr) {
-            if (u.source.indptr != nullptr) {
-                u.source.indptr += s0; // sparse: scenario s of the part is scenario s0 + s of the caller's index pointer
-            } else {
-                u.source.data = static_cast<unsigned char const*>(u.source.data) + static_cast<size_t>(s0) * u.source.n * sizeof(SourceUpdate);
-            }
-        }
-        OutputData o = out;
-        void** ohost[12] = {&o.node, &o.line, &o.transformer, &o.shunt, &o.source, &o.sym_gen, &o.asym_gen, &o.sym_load, &o.asym_load,
-                            &o.voltage_regulator, &o.asym_line, &o.generic_branch};
-        for (int k = 0; k != 12; ++k)
-            if (*ohost[k] != nullptr) *ohost[k] = static_cast<unsigned char*>(*ohost[k]) + static_cast<size_t>(s0) * outs[k].count * outs[k].row;
-        int64_t const r = run_batch_device_part(opt, phases, u, o, n_iter ? n_iter + s0 : nullptr, status ? status + s0 : nullptr, s0);
+        UpdateData u;
+        OutputData o;
+        slice_batch(update, out, parts, s0, ns, u, o);
+        ModelOptions mo = opt;
+        mo.flags = 0; // parts reuse the device buffers: nothing stays resident
+        int64_t const r = run_batch_device_part(mo, phases, u, o, n_iter ? n_iter + s0 : nullptr, status ? status + s0 : nullptr,
+                                                first_scenario + s0);
         if (r < 0) return -1;
         failed += r;
     }
@@ -181,8 +313,15 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
     Idx const n_scn = update.n_scenarios;
     Idx const nn = static_cast<Idx>(node_.size());
     Idx const n_lg_math = m.n_load_gen();
+    // the engine's device is the current device of this thread for everything below (pool allocations key on it); device-side
+    // state that lives on another GPU (the caller switched devices between calls) is dropped
+    PGMB_CUDA(cudaSetDevice(e.device()));
+    if (dev_ && dev_->device >= 0 && dev_->device != e.device()) dev_.reset();
     if (!dev_) dev_ = std::make_shared<DeviceSide>();
     DeviceSide& d = *dev_;
+    d.ensure_streams(e.device());
+    bool const resident_in = (opt.flags & kFlagResidentInput) != 0;
+    bool const resident_out = (opt.flags & kFlagResidentOutput) != 0;
 
     // ---- tables (rebuilt per call: a few thousand elements; the permanent state may have changed) ----
     {
@@ -406,7 +545,6 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
                       plan.dead_off.data() + first_scenario, plan.dead.data(), plan.dead.size());
     }
     SolveOptions const sopt = e.prepare_solve({opt.method, opt.err_tol, static_cast<int32_t>(opt.max_iter)});
-    d.ensure_streams();
     d.flag.ensure(1);
     PGMB_CUDA(cudaMemsetAsync(d.flag.get(), 0, sizeof(int32_t), st));
     int const tw = e.tile_width();
@@ -414,13 +552,20 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
     int const force_const_y = e.last_method() == 0 ? 1 : 0;
     int64_t const n_tile = e.dev_batch().n_tile;
     int n_chunk = static_cast<int>(std::min<int64_t>(DeviceSide::kMaxChunk, std::max<int64_t>(1, n_tile / 16)));
+    if (resident_in && resident_out) n_chunk = 1; // no transfers to overlap: one launch per kernel
     if (char const* env = std::getenv("PGMB_CHUNKS")) n_chunk = std::max(1, std::min<int>(DeviceSide::kMaxChunk, std::atoi(env)));
     n_chunk = static_cast<int>(std::min<int64_t>(n_chunk, n_tile));
 
     ComponentBuffer const* ubufs[4] = {&update.sym_gen, &update.asym_gen, &update.sym_load, &update.asym_load};
     size_t const urow[4] = {sizeof(SymLoadGenUpdate), sizeof(AsymLoadGenUpdate), sizeof(SymLoadGenUpdate), sizeof(AsymLoadGenUpdate)};
     for (int bfr = 0; bfr != 4; ++bfr) {
-        if (ubufs[bfr]->data != nullptr && ubufs[bfr]->n != 0) d.upd[bfr].ensure(static_cast<size_t>(n_scn) * ubufs[bfr]->n * urow[bfr]);
+        size_t const bytes = (ubufs[bfr]->data != nullptr && ubufs[bfr]->n != 0) ? static_cast<size_t>(n_scn) * ubufs[bfr]->n * urow[bfr] : 0;
+        if (resident_in) {
+            if (bytes != d.resident_rows[bfr]) throw InvalidArgument("PGMB_FLAG_RESIDENT_INPUT: the previous call did not upload this batch's update rows");
+        } else {
+            if (bytes != 0) d.upd[bfr].ensure(bytes);
+            d.resident_rows[bfr] = bytes;
+        }
     }
     struct Req {
         void* host;
@@ -462,7 +607,7 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
             if (r.host != nullptr && r.count != 0) out_pinned = out_pinned && is_device_accessible_host(r.host);
         for (int bfr = 0; bfr != 4; ++bfr)
             if (ubufs[bfr]->data != nullptr && ubufs[bfr]->n != 0) in_pinned = in_pinned && is_device_accessible_host(ubufs[bfr]->data);
-        if (!out_pinned) {
+        if (!out_pinned && !resident_out) {
             for (Req const& r : reqs) {
                 if (r.host == nullptr || r.count == 0) continue;
                 stage_off[r.slot] = stage_bytes;
@@ -473,11 +618,13 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
         // a copy INTO pageable memory returns only when the chunk's kernels are done, which would run the chunks one after another;
         // a copy FROM pageable memory (update rows) returns once the driver has staged the rows, so it does not stop the overlap
         (void)in_pinned;
-        if (!staged && !out_pinned && std::getenv("PGMB_CHUNKS") == nullptr) n_chunk = 1;
+        if (!staged && !out_pinned && !resident_out && std::getenv("PGMB_CHUNKS") == nullptr) n_chunk = 1;
     }
     unsigned char* const stage = staged ? d.staging(stage_bytes) : nullptr;
+    PGMB_CUDA(cudaEventRecord(d.ev_p0, st));
     PGMB_CUDA(cudaEventRecord(d.fork, st));
 
+    try {
     for (int c = 0; c != n_chunk; ++c) {
         cudaStream_t const q = d.cs[c];
         int64_t const tile_b = n_tile * c / n_chunk, tile_e = n_tile * (c + 1) / n_chunk;
@@ -489,8 +636,10 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
         for (int bfr = 0; bfr != 4; ++bfr) {
             if (ubufs[bfr]->data == nullptr || ubufs[bfr]->n == 0) continue;
             size_t const per = static_cast<size_t>(ubufs[bfr]->n) * urow[bfr];
-            PGMB_CUDA(cudaMemcpyAsync(d.upd[bfr].get() + s0 * per, static_cast<unsigned char const*>(ubufs[bfr]->data) + s0 * per,
-                                      ns * per, cudaMemcpyHostToDevice, q));
+            if (!resident_in) {
+                PGMB_CUDA(cudaMemcpyAsync(d.upd[bfr].get() + s0 * per, static_cast<unsigned char const*>(ubufs[bfr]->data) + s0 * per,
+                                          ns * per, cudaMemcpyHostToDevice, q));
+            }
             ub.data[bfr] = d.upd[bfr].get() + s0 * per;
             ub.n_per_scenario[bfr] = ubufs[bfr]->n;
         }
@@ -547,19 +696,22 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
         }
         PGMB_CUDA(cudaGetLastError());
         for (Req const& r : reqs) {
-            if (r.host == nullptr || r.count == 0) continue;
+            if (r.host == nullptr || r.count == 0 || resident_out) continue;
             size_t const off = static_cast<size_t>(s0) * r.count * r.row;
             unsigned char* const dst = staged ? stage + stage_off[r.slot] + off : static_cast<unsigned char*>(r.host) + off;
             PGMB_CUDA(cudaMemcpyAsync(dst, d.out[r.slot].get() + off, static_cast<size_t>(ns) * r.count * r.row,
                                       cudaMemcpyDeviceToHost, q));
         }
+        PGMB_CUDA(cudaEventRecord(d.ev_end[c], q));
+        PGMB_CUDA(cudaStreamWaitEvent(st, d.ev_end[c], 0)); // join: the engine stream sees the end of every chunk
     }
+    PGMB_CUDA(cudaEventRecord(d.ev_p1, st));
     timing[1] += ms_since(t0);
 
     t0 = Clock::now();
     if (staged) {
         char const* const env_thr = std::getenv("PGMB_COPY_THREADS");
-        unsigned const n_copy = env_thr != nullptr ? std::max(1, std::atoi(env_thr))
+        unsigned const n_copy = env_thr != nullptr ? static_cast<unsigned>(std::max(1, std::min(64, std::atoi(env_thr))))
                                                    : std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
         for (int c = 0; c != n_chunk; ++c) {
             PGMB_CUDA(cudaStreamSynchronize(d.cs[c]));
@@ -582,7 +734,7 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
             unsigned const n_thr = total < (size_t{4} << 20) ? 1u : n_copy;
             auto copy_share = [&pieces, n_thr](unsigned t) { // thread t takes the t-th 1/n_thr of every piece, cut at 4 KB
                 for (Piece const& p : pieces) {
-                    size_t const step = (p.bytes / n_thr + 4095) / 4096 * 4096;
+                    size_t const step = ((p.bytes + n_thr - 1) / n_thr + 4095) / 4096 * 4096; // n_thr * step >= bytes
                     size_t const b = std::min(p.bytes, step * t), e2 = std::min(p.bytes, step * (t + 1));
                     if (e2 > b) std::memcpy(p.dst + b, p.src + b, e2 - b);
                 }
@@ -598,10 +750,20 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
         }
     }
     for (int c = 0; c != n_chunk; ++c) PGMB_CUDA(cudaStreamSynchronize(d.cs[c]));
+    } catch (...) {
+        d.drain(); // copies into caller / staging memory may still be in flight
+        throw;
+    }
     for (int c = 0; c != n_chunk; ++c) {
         float ms = 0.0f;
         PGMB_CUDA(cudaEventElapsedTime(&ms, d.ev_a[c], d.ev_b[c]));
         timing[2] += ms; // solver time per chunk; chunks overlap, so the sum can exceed the wall time
+    }
+    {
+        PGMB_CUDA(cudaEventSynchronize(d.ev_p1));
+        float ms = 0.0f;
+        PGMB_CUDA(cudaEventElapsedTime(&ms, d.ev_p0, d.ev_p1));
+        timing[6] += ms; // device time of the whole pipeline: (H2D) -> apply -> solve -> results / output structs -> (D2H)
     }
     int32_t mismatch = 0;
     PGMB_CUDA(cudaMemcpyAsync(&mismatch, d.flag.get(), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -614,15 +776,18 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
     if (mismatch != 0) return -1;
 
     int64_t failed = 0;
+    std::vector<double> dev_local;
     for (Idx s = 0; s != n_scn; ++s) {
         if (n_iter != nullptr) n_iter[s] = it_local[s];
         if (status != nullptr) status[s] = st_local[s];
         if (st_local[s] != 0) {
             ++failed;
+            if (dev_local.empty()) { // fetched only when something failed
+                dev_local.resize(n_scn);
+                PGMB_CUDA(cudaMemcpy(dev_local.data(), e.dev_batch().max_dev, sizeof(double) * n_scn, cudaMemcpyDeviceToHost));
+            }
             batch_message += "Error in batch #" + std::to_string(first_scenario + s) + ": " +
-                             (st_local[s] == 1   ? "Iteration failed to converge after " + std::to_string(opt.max_iter) + " iterations!"
-                              : st_local[s] == 4 ? std::string("Unallocated Q remains after distribution on a regulated bus")
-                                                 : std::string("Sparse matrix error, possibly singular matrix!")) + "\n";
+                             scenario_failure_text(st_local[s], opt.max_iter, dev_local[s], opt.err_tol) + "\n";
         }
     }
     return failed;

@@ -83,7 +83,7 @@ class PowerGridModel:
     def calculate_power_flow(self, *, symmetric=True, error_tolerance=1e-8, max_iterations=20,
                              calculation_method="newton_raphson", update_data=None, threading=-1,
                              output_component_types=None, continue_on_batch_error=False, device=0, output_buffers=None,
-                             reuse_output_buffers=False):
+                             reuse_output_buffers=False, n_devices=1, flags=0):
         """Same contract as the reference: without ``update_data`` a single calculation returning 1-D arrays, with it a
         batch returning (n_scenarios, n_elements) arrays.  ``threading`` is accepted for signature compatibility; the
         scenario loop of load / source-reference batches runs on the GPU whatever ``threading`` says; batches that switch
@@ -91,11 +91,13 @@ class PowerGridModel:
         cores, n = n threads), every copy driving its own GPU stream.  ``output_buffers``: caller-owned arrays per component (like the C API; use
         ``pgm_b200.pinned_empty`` for page-locked ones).  ``reuse_output_buffers=True``: results are written into page-locked
         arrays owned by the model and reused by the next call with the same shapes (no page faults, transfers overlap the
-        solver) -- copy what must outlive the next calculation."""
+        solver) -- copy what must outlive the next calculation.  ``n_devices``: GPUs the batch is spread over inside the call
+        (contiguous scenario blocks, starting at ``device``).  ``flags``: ``pgm_b200.FLAG_RESIDENT_INPUT / _OUTPUT`` (device-resident
+        update rows / output structs, include/pgm_b200.h)."""
         if isinstance(calculation_method, str):
             calculation_method = _lib.METHODS[calculation_method]
-        opt = _lib.OptionsC(int(calculation_method), int(bool(symmetric)), float(error_tolerance), int(max_iterations), 1,
-                            int(device), int(threading), 0)
+        opt = _lib.OptionsC(int(calculation_method), int(bool(symmetric)), float(error_tolerance), int(max_iterations),
+                            int(n_devices), int(device), int(threading), int(flags))
         upd = None
         n_scn = 1
         keep = None
@@ -143,7 +145,11 @@ class PowerGridModel:
         unused, pipeline drain + status, total (include/pgm_b200.h: pgmb_model_last_timing)"""
         t = (C.c_double * 6)()
         check(lib().pgmb_model_last_timing(self._h, t))
-        return dict(zip(("prepare", "enqueue", "solve_kernel", "output", "drain", "total"), list(t)))
+        out = dict(zip(("prepare", "enqueue", "solve_kernel", "output", "drain", "total"), list(t)))
+        ms = C.c_double()
+        check(lib().pgmb_model_device_pipeline_ms(self._h, C.byref(ms)))
+        out["device_pipeline"] = ms.value
+        return out
 
     def batch_pf_input(self, update_data, symmetric=True, group=0):
         """PowerFlowInput of every scenario for one math group: (s_injection (n_scn, n_load_gen, B), u_ref (n_scn, n_source))"""

@@ -80,6 +80,25 @@ def core():
     return _core
 
 
+def create_buffer(dataset: str, component: str, shape):
+    """numpy view of a buffer allocated with PGM_create_buffer (buffer.h: the library owns the memory until PGM_destroy_buffer).
+    On a GPU box this library hands out page-locked memory for large buffers, so PGM_calculate transfers into it directly."""
+    import weakref
+
+    c = core()
+    h = Handle()
+    meta = c.PGM_meta_get_component_by_name(h.h, dataset.encode(), component.encode())
+    h.check()
+    table = {"input": structs.INPUT, "update": structs.UPDATE, "sym_output": structs.SYM_OUTPUT, "asym_output": structs.ASYM_OUTPUT}[dataset]
+    dt = table[component]
+    n = int(np.prod(shape))
+    ptr = c.PGM_create_buffer(h.h, meta, max(n, 1))
+    h.check()
+    arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(max(n, 1) * dt.itemsize,))[:n * dt.itemsize].view(dt).reshape(shape)
+    weakref.finalize(arr.base if arr.base is not None else arr, c.PGM_destroy_buffer, ptr)
+    return arr
+
+
 class Handle:
     def __init__(self):
         self.h = core().PGM_create_handle()
@@ -232,7 +251,7 @@ class PowerGridModel:
     def calculate_power_flow(self, *, symmetric=True, error_tolerance=1e-8, max_iterations=20,
                              calculation_method="newton_raphson", update_data=None, threading=-1,
                              output_component_types=None, continue_on_batch_error=False, tap_changing_strategy=0,
-                             calculation_type=0):
+                             calculation_type=0, output_buffers=None):
         c = core()
         opt = c.PGM_create_options(self.handle.h)
         try:
@@ -270,6 +289,9 @@ class PowerGridModel:
                 result = {k: (np.zeros(shape(k), dtype=table[k]) if attrs is None else
                               {a: np.zeros(shape(k) + table[k][a].shape, dtype=table[k][a].base) for a in attrs})
                           for k, attrs in comps.items()}
+            elif output_buffers is not None:  # caller-owned row buffers (e.g. from create_buffer: page-locked when large)
+                result = {k: output_buffers[k] for k in comps}
+                assert all(result[k].dtype == table[k] and result[k].shape == shape(k) for k in comps)
             else:
                 result = {k: np.zeros(shape(k), dtype=table[k]) for k in comps}
             out = _Dataset(self.handle, "sym_output" if symmetric else "asym_output", result, mutable=True, is_batch=batch,

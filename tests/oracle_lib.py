@@ -246,9 +246,11 @@ class Model:
         return bag
 
     def calculate(self, sym=True, method="newton_raphson", err_tol=1e-8, max_iter=20, threading=-1, update=None,
-                  output_components=None, reuse_ic_factorization=False):
+                  output_components=None, reuse_ic_factorization=False, out=None):
         """update: None or dict component -> array of shape (n_scn, n_per) or {"data": flat, "indptr": ...}.
-        Returns dict with per-component output arrays (n_scn, n_comp), n_iter, status, error."""
+        Returns dict with per-component output arrays (n_scn, n_comp), n_iter, status, error.
+        out: optional dict of preallocated output arrays to write into (the caller reuses them between calls, as a client of
+        the reference does with its output dataset)."""
         n_scn = 1
         bu = None
         keep = []
@@ -277,7 +279,11 @@ class Model:
         bo = _BatchOutput()
         result = {}
         for c in comps:
-            arr = np.zeros((n_scn, self.counts[c]), dtype=table[c])
+            if out is not None and c in out:
+                arr = out[c]
+                assert arr.dtype == table[c] and arr.shape == (n_scn, self.counts[c]) and arr.flags.c_contiguous
+            else:
+                arr = np.zeros((n_scn, self.counts[c]), dtype=table[c])
             result[c] = arr
             if arr.size:
                 setattr(bo, c, arr.ctypes.data)
