@@ -166,6 +166,28 @@ PGMB_API int pgmb_engine_solve_staged(pgmb_engine* engine, const pgmb_run_option
 PGMB_API int pgmb_engine_fetch(pgmb_engine* engine, const pgmb_solver_output* output);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * SparseLUSolver with pivot perturbation + iterative refinement (sparse_lu_solver.hpp:277-828; the perturbation path :514-649),
+ * batched: every system of the batch shares one block-CSR pattern (row_indptr / col_indices / diag_lu as the reference's
+ * constructor takes them, fill-ins included) and has its own values and right-hand side.
+ * block_size: 1 (scalar), 2, 3, 6 for real values; 1, 3 for complex values (is_complex != 0; re, im interleaved).
+ * Blocks are column-major like the reference's Eigen blocks.  use_pivot_perturbation as in SparseLUSolver::prefactorize(data,
+ * perm, use_pivot_perturbation): threshold 1e-13 * (block-off-diagonal infinity norm), the perturbed pivot keeps its phase, and a
+ * perturbed factorisation is solved with iterative refinement (backward error <= 1e-13, at most 6 solves, else singular).
+ * The power-flow solvers never enable it (as in the reference); state estimation would.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct pgmb_sparse_lu pgmb_sparse_lu;
+PGMB_API int pgmb_sparse_lu_create(int64_t n, const int64_t* row_indptr, const int64_t* col_indices, const int64_t* diag_lu,
+                                   int32_t block_size, int32_t is_complex, int32_t device, pgmb_sparse_lu** out);
+PGMB_API void pgmb_sparse_lu_destroy(pgmb_sparse_lu* solver);
+/* data [n_batch][nnz][block_size^2], rhs and x [n_batch][n][block_size]; status [n_batch]: PGMB_SCN_OK or PGMB_SCN_SINGULAR
+ * (SparseMatrixError).  Optional (NULL = not wanted): perturbed [n_batch] 1 when a pivot was perturbed, n_solves [n_batch] number
+ * of triangular solves (1 without refinement), lu_out (the factors, same layout as data), perm_out [n_batch][n][2][block_size]
+ * (block permutations p then q). Returns PGMB_ERR_BATCH when some system is singular. */
+PGMB_API int pgmb_sparse_lu_solve(pgmb_sparse_lu* solver, int64_t n_batch, const double* data, const double* rhs,
+                                  int32_t use_pivot_perturbation, double* x, int32_t* status, int32_t* perturbed,
+                                  int32_t* n_solves, double* lu_out, int8_t* perm_out);
+
+/* ------------------------------------------------------------------------------------------------------------
  * MODEL level (component structs; layouts == the reference's dataset structs, see pgm_b200/structs.py)
  * ---------------------------------------------------------------------------------------------------------- */
 typedef struct pgmb_component_buffer {

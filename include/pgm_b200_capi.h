@@ -108,7 +108,7 @@ PGM_API int PGM_is_little_endian(PGM_Handle* handle);
 /* buffer.h:40-108 */
 PGM_API void* PGM_create_buffer(PGM_Handle* handle, PGM_MetaComponent const* component, PGM_Idx size);
 PGM_API void PGM_destroy_buffer(void* ptr);
-/* extension (not in the reference): 1 when `ptr` came from PGM_create_buffer as page-locked memory (>= 64 KB with a CUDA device
+/* extension (not in the reference): 1 when `ptr` came from PGM_create_buffer as page-locked memory (>= 4 KB with a CUDA device
  * present), which the device pipeline fills directly, chunk by chunk, while the solver runs */
 PGM_API int PGM_b200_buffer_is_page_locked(void const* ptr);
 PGM_API void PGM_buffer_set_nan(PGM_Handle* handle, PGM_MetaComponent const* component, void* ptr, PGM_Idx buffer_offset,

@@ -179,4 +179,33 @@ int pgmb_engine_fetch(pgmb_engine* engine, const pgmb_solver_output* output) {
     });
 }
 
+int pgmb_sparse_lu_create(int64_t n, const int64_t* row_indptr, const int64_t* col_indices, const int64_t* diag_lu, int32_t block_size,
+                          int32_t is_complex, int32_t device, pgmb_sparse_lu** out) {
+    return guarded([&] {
+        if (row_indptr == nullptr || col_indices == nullptr || diag_lu == nullptr || out == nullptr || n < 0) throw InvalidArgument("null argument");
+        *out = reinterpret_cast<pgmb_sparse_lu*>(new SparseLuBatch(n, row_indptr, col_indices, diag_lu, block_size, is_complex != 0, device));
+    });
+}
+void pgmb_sparse_lu_destroy(pgmb_sparse_lu* solver) { delete reinterpret_cast<SparseLuBatch*>(solver); }
+int pgmb_sparse_lu_solve(pgmb_sparse_lu* solver, int64_t n_batch, const double* data, const double* rhs, int32_t use_pivot_perturbation,
+                         double* x, int32_t* status, int32_t* perturbed, int32_t* n_solves, double* lu_out, int8_t* perm_out) {
+    std::vector<int32_t> st_local;
+    int const rc = guarded([&] {
+        if (solver == nullptr || data == nullptr || rhs == nullptr || x == nullptr) throw InvalidArgument("null argument");
+        if (status == nullptr) {
+            st_local.assign(static_cast<size_t>(std::max<int64_t>(n_batch, 0)), 0);
+            status = st_local.data();
+        }
+        reinterpret_cast<SparseLuBatch*>(solver)->solve(n_batch, data, rhs, use_pivot_perturbation != 0, x, status, perturbed, n_solves,
+                                                        lu_out, perm_out);
+    });
+    if (rc != PGMB_OK) return rc;
+    for (int64_t b = 0; b < n_batch; ++b)
+        if (status[b] != 0) {
+            g_last_error = "Sparse matrix error, possibly singular matrix!\n";
+            return PGMB_ERR_BATCH;
+        }
+    return PGMB_OK;
+}
+
 } // extern "C"

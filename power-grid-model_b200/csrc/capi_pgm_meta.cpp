@@ -164,7 +164,7 @@ int PGM_is_little_endian(PGM_Handle* handle) {
 }
 
 // ---- buffers -------------------------------------------------------------------------------------------------------
-// Buffers of at least 64 KB are page-locked when a CUDA device is present (cudaHostAlloc): a client that allocates its datasets
+// Buffers of at least 4 KB are page-locked when a CUDA device is present (cudaHostAlloc): a client that allocates its datasets
 // through the API -- the reference's C++ wrapper and benchmark do (power_grid_model_cpp/buffer.hpp, fictional_grid_generator.hpp:
 // 192-204) -- then gets the direct, chunk-overlapped transfers of the device pipeline without knowing about CUDA.  Elsewhere
 // (no device, small buffers, allocation refused) it is the reference's aligned_alloc.
@@ -173,7 +173,7 @@ void* PGM_create_buffer(PGM_Handle* handle, PGM_MetaComponent const* component, 
         MetaComponent const& c = deref(component);
         size_t const alignment = std::max(c.alignment, sizeof(void*));
         size_t const bytes = c.size * static_cast<size_t>(std::max<PGM_Idx>(size, 0));
-        if (bytes >= (size_t{64} << 10) && pgmb_device_count() > 0) {
+        if (bytes >= (size_t{4} << 10) && pgmb_device_count() > 0) {
             void* p = nullptr;
             if (pgmb_host_alloc(bytes, &p) == PGMB_OK && p != nullptr) {
                 std::lock_guard<std::mutex> const lock(g_locked_mutex);

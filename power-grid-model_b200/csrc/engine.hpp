@@ -219,6 +219,27 @@ class Engine {
     void allocate_batch(int64_t n_scn);
 };
 
+// Batched sparse LU with the reference's pivot perturbation + iterative refinement (sparse_lu.cu)
+class SparseLuBatch {
+  public:
+    SparseLuBatch(int64_t n, int64_t const* indptr, int64_t const* indices, int64_t const* diag, int block_size, bool is_complex,
+                  int device);
+    // data [n_batch][nnz][N*N] column-major blocks, rhs / x [n_batch][n][N] (complex: re, im interleaved); optional outputs may be
+    // null: perturbed [n_batch] (a pivot was perturbed), n_solves [n_batch] (solve_once calls incl. refinement), lu_out (factors),
+    // perm_out [n_batch][n][2][N] (p then q of every pivot block)
+    void solve(int64_t n_batch, double const* data, double const* rhs, bool use_pivot_perturbation, double* x, int32_t* status,
+               int32_t* perturbed, int32_t* n_solves, double* lu_out, int8_t* perm_out);
+    int64_t size() const { return n_; }
+    int64_t nnz() const { return nnz_; }
+
+  private:
+    int64_t n_, nnz_;
+    int block_;
+    bool complex_;
+    int device_;
+    DevBuf<int64_t> d_indptr_, d_indices_, d_diag_;
+};
+
 uint64_t kernel_launch_count(); // kernels launched by this library since it was loaded
 
 // kernel launchers (nr_sym.cu, result_sym.cu)

@@ -598,27 +598,29 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
     // page-locked staging area owned by the model: every chunk's results go device -> staging asynchronously, and host threads
     // copy a finished chunk into the caller's memory (faulting its fresh pages in parallel) while the next chunks are still in
     // flight.  A direct cudaMemcpy into unfaulted pageable memory runs at a few GB/s on one driver thread.
+    // Staging is decided per buffer: a page-locked buffer takes its results directly, a pageable one goes through the staging area
+    // (a client may mix both: PGM_create_buffer page-locks large buffers only).
     size_t stage_off[12] = {};
+    bool slot_staged[12] = {};
     size_t stage_bytes = 0;
     bool staged = false;
     {
-        bool out_pinned = true, in_pinned = true;
-        for (Req const& r : reqs)
-            if (r.host != nullptr && r.count != 0) out_pinned = out_pinned && is_device_accessible_host(r.host);
-        for (int bfr = 0; bfr != 4; ++bfr)
-            if (ubufs[bfr]->data != nullptr && ubufs[bfr]->n != 0) in_pinned = in_pinned && is_device_accessible_host(ubufs[bfr]->data);
-        if (!out_pinned && !resident_out) {
-            for (Req const& r : reqs) {
-                if (r.host == nullptr || r.count == 0) continue;
+        bool any_pageable = false;
+        for (Req const& r : reqs) {
+            if (r.host == nullptr || r.count == 0 || resident_out) continue;
+            if (!is_device_accessible_host(r.host)) {
+                any_pageable = true;
+                slot_staged[r.slot] = true;
                 stage_off[r.slot] = stage_bytes;
                 stage_bytes += (static_cast<size_t>(n_scn) * r.count * r.row + 4095) / 4096 * 4096;
             }
-            staged = stage_bytes <= (size_t{3} << 29) && std::getenv("PGMB_NO_STAGING") == nullptr; // at most 1.5 GB page-locked
         }
+        staged = any_pageable && stage_bytes <= (size_t{3} << 29) && std::getenv("PGMB_NO_STAGING") == nullptr; // at most 1.5 GB page-locked
+        if (!staged)
+            for (bool& b : slot_staged) b = false;
         // a copy INTO pageable memory returns only when the chunk's kernels are done, which would run the chunks one after another;
         // a copy FROM pageable memory (update rows) returns once the driver has staged the rows, so it does not stop the overlap
-        (void)in_pinned;
-        if (!staged && !out_pinned && !resident_out && std::getenv("PGMB_CHUNKS") == nullptr) n_chunk = 1;
+        if (!staged && any_pageable && std::getenv("PGMB_CHUNKS") == nullptr) n_chunk = 1;
     }
     unsigned char* const stage = staged ? d.staging(stage_bytes) : nullptr;
     PGMB_CUDA(cudaEventRecord(d.ev_p0, st));
@@ -698,7 +700,7 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
         for (Req const& r : reqs) {
             if (r.host == nullptr || r.count == 0 || resident_out) continue;
             size_t const off = static_cast<size_t>(s0) * r.count * r.row;
-            unsigned char* const dst = staged ? stage + stage_off[r.slot] + off : static_cast<unsigned char*>(r.host) + off;
+            unsigned char* const dst = slot_staged[r.slot] ? stage + stage_off[r.slot] + off : static_cast<unsigned char*>(r.host) + off;
             PGMB_CUDA(cudaMemcpyAsync(dst, d.out[r.slot].get() + off, static_cast<size_t>(ns) * r.count * r.row,
                                       cudaMemcpyDeviceToHost, q));
         }
@@ -726,7 +728,7 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
             std::vector<Piece> pieces;
             size_t total = 0;
             for (Req const& r : reqs) {
-                if (r.host == nullptr || r.count == 0) continue;
+                if (r.host == nullptr || r.count == 0 || !slot_staged[r.slot]) continue;
                 size_t const off = static_cast<size_t>(s0) * r.count * r.row, bytes = static_cast<size_t>(ns) * r.count * r.row;
                 pieces.push_back({static_cast<unsigned char*>(r.host) + off, stage + stage_off[r.slot] + off, bytes});
                 total += bytes;
