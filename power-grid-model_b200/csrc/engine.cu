@@ -570,7 +570,7 @@ void Engine::launch_solve(DevBatch const& b, SolveOptions const& opt, cudaStream
         // (a branch-outage overlay is read by the block kernel and the symmetric level kernel)
         if (!symmetric_ && !has_regulators() && env_int("PGMB_BLOCK6", 0) != 0) {
             // row-split kernel: six threads per (bus row, scenario); see nr_block6.cu
-            launch_nr_block6(tile_width_, ds_, b, opt, env_int("PGMB_BLOCK6_THREADS", 512), st);
+            launch_nr_block6(tile_width_, ds_, b, opt, env_int("PGMB_BLOCK6_THREADS", 768), st);
         } else if (!symmetric_ || has_regulators() || env_int("PGMB_KERNEL", 3) == 0) {
             launch_nr_block(B_, tile_width_, ds_, b, opt, n_slot_, st);
         } else if (env_int("PGMB_KERNEL", 3) == 1 && b.ovl.entry == nullptr) {
