@@ -37,6 +37,7 @@ template <int T> struct Tile6 {
     int32_t const* ovr_entry;
     double const* ovr_y;
     uint8_t const* dead;
+    double* sm;         // shared scratch of my warp + my scenario: element e at sm[e * 4]; 36 block elements, then 6 vector slots
     double* wide_terms; // scratch of the cooperative hub rows (block_common.cuh: wide_up_row), may be null
     double* wide_rhs;
     double* wide_sum;
@@ -46,7 +47,6 @@ template <int T> struct Tile6 {
     bool act; // this thread stores results (real row, valid and unfinished scenario)
 };
 
-__device__ __forceinline__ double shfl_row(double v, int row, int sc) { return __shfl_sync(kFull, v, row * 4 + sc); }
 __device__ __forceinline__ double sel6(double const* d, int c) {
     double x = d[0];
 #pragma unroll
@@ -71,43 +71,43 @@ __device__ __forceinline__ void pf_term(double yr, double yi, double uir, double
     h = ar * di + ai * dr;
 }
 
-// ---- full-pivot LU of the 6 x 6 diagonal block, row r in d[6] of thread r (DenseLUFactor::factorize_block_in_place) --------
-// p / q come back nibble-packed (uniform over the threads of a scenario); returns the singular flag (uniform as well)
-__device__ bool factorize6(double* d, int r, int sc, bool real_row, uint32_t& p_out, uint32_t& q_out) {
+// ---- full-pivot LU of the 6 x 6 diagonal block (DenseLUFactor::factorize_block_in_place) through the warp's shared scratch -----
+// The block sits in shared memory (element (r, c) of my scenario at sm[(c * 6 + r) * 4]).  Every thread scans the whole trailing
+// sub-block for the pivot -- first maximum in column-major order, exactly the reference's maxCoeff -- so the search needs no
+// cross-thread reduction and all its addresses are compile-time constants; the row swap is done by the six threads column-wise,
+// the column swap row-wise, and thread r eliminates row r.  Far fewer instructions than a shuffle version: no select chains, no
+// double-width shuffles, no collective synchronisation inside the search.  On return d[] holds row r of the factor and the
+// scratch holds the whole factor (read by finish_row6 for the U blocks and the forward substitution).
+__device__ bool factorize6s(double* sm, double* d, int r, bool real_row, uint32_t& p_out, uint32_t& q_out) {
+    double* const mine = sm + r * 4; // row r: element (r, c) at mine[c * 24]
+    if (real_row) {
+#pragma unroll
+        for (int c = 0; c < kN; ++c) mine[c * 24] = d[c];
+    }
+    __syncwarp();
     int rt[kN], ct[kN];
     double max_pivot = 0.0;
     bool stopped = false;
 #pragma unroll
     for (int pivot = 0; pivot < kN; ++pivot) {
-        // candidate of my row: first maximum over the columns >= pivot; NaN never wins except at (pivot, pivot), which the
-        // reference keeps as its initial best whatever follows
-        double bv = -1.0;
-        int bc = pivot, br = real_row ? r : 6 + r;
-        if (real_row && r >= pivot) {
+        int best_at = pivot * kN + pivot; // c * 6 + r of the best element
+        double best;
+        {
+            double const v = sm[(pivot * kN + pivot) * 4];
+            best = v * v;
+        }
 #pragma unroll
-            for (int c = pivot; c < kN; ++c) {
-                double const v = d[c] * d[c];
-                double const key = isnan(v) ? ((r == pivot && c == pivot) ? INFINITY : -1.0) : v;
-                if (c == pivot || key > bv) {
-                    bv = key;
-                    bc = c;
+        for (int c = pivot; c < kN; ++c)
+#pragma unroll
+            for (int rr = pivot; rr < kN; ++rr) {
+                double const v = sm[(c * kN + rr) * 4];
+                double const sq = v * v;
+                if (sq > best) {
+                    best = sq;
+                    best_at = c * kN + rr;
                 }
             }
-        }
-#pragma unroll
-        for (int off = 4; off <= 16; off <<= 1) {
-            double const ov = __shfl_xor_sync(kFull, bv, off);
-            int const oc = __shfl_xor_sync(kFull, bc, off), orr = __shfl_xor_sync(kFull, br, off);
-            bool const better = ov > bv || (ov == bv && (oc < bc || (oc == bc && orr < br)));
-            if (better) {
-                bv = ov;
-                bc = oc;
-                br = orr;
-            }
-        }
-        int rb = br, cb = bc;
-        double const x = shfl_row(sel6(d, cb), rb < kN ? rb : 0, sc);
-        double const best = x * x;
+        int rb = best_at % kN, cb = best_at / kN;
         if (stopped || best == 0.0) { // the reference stops here: the remaining transpositions are identities
             stopped = true;
             rb = pivot;
@@ -117,26 +117,27 @@ __device__ bool factorize6(double* d, int r, int sc, bool real_row, uint32_t& p_
         }
         rt[pivot] = rb;
         ct[pivot] = cb;
-        // row swap pivot <-> rb
-        int const partner = (r == pivot) ? rb : ((r == rb) ? pivot : r);
-#pragma unroll
-        for (int c = 0; c < kN; ++c) d[c] = shfl_row(d[c], partner, sc);
-        // column swap pivot <-> cb (inside my row)
-        {
-            double const a = d[pivot], b = sel6(d, cb);
-            d[pivot] = b;
-#pragma unroll
-            for (int c = pivot + 1; c < kN; ++c) d[c] = (c == cb) ? a : d[c];
+        __syncwarp(); // every thread has finished its scan before the block changes
+        if (real_row) { // row swap pivot <-> rb: thread r moves column r
+            double const a = sm[(r * kN + pivot) * 4], b = sm[(r * kN + rb) * 4];
+            sm[(r * kN + pivot) * 4] = b;
+            sm[(r * kN + rb) * 4] = a;
         }
+        __syncwarp();
+        if (real_row) { // column swap pivot <-> cb: thread r moves row r
+            double const a = mine[pivot * 24], b = mine[cb * 24];
+            mine[pivot * 24] = b;
+            mine[cb * 24] = a;
+        }
+        __syncwarp();
         if (pivot < kN - 1) {
-            double const pv = shfl_row(d[pivot], pivot, sc);
-            bool const below = !stopped && r > pivot;
-            if (below) d[pivot] /= pv;
+            if (!stopped && real_row && r > pivot) {
+                double const m = mine[pivot * 24] / sm[(pivot * kN + pivot) * 4];
+                mine[pivot * 24] = m;
 #pragma unroll
-            for (int c = pivot + 1; c < kN; ++c) {
-                double const prc = shfl_row(d[c], pivot, sc);
-                if (below) d[c] -= d[pivot] * prc;
+                for (int c = pivot + 1; c < kN; ++c) mine[c * 24] -= m * sm[(c * kN + pivot) * 4];
             }
+            __syncwarp();
         }
     }
     uint32_t p = kIdentityPerm, q = kIdentityPerm;
@@ -147,11 +148,15 @@ __device__ bool factorize6(double* d, int r, int sc, bool real_row, uint32_t& p_
     p_out = p;
     q_out = q;
     double const threshold = DBL_EPSILON * max_pivot;
-    double const dd = sel6(d, r);
-    int bad = (real_row && (fabs(dd) < threshold || not_normal(dd))) ? 1 : 0;
+    bool bad = false;
 #pragma unroll
-    for (int off = 4; off <= 16; off <<= 1) bad |= __shfl_xor_sync(kFull, bad, off);
-    return bad != 0;
+    for (int i = 0; i < kN; ++i) {
+        double const dd = sm[(i * kN + i) * 4];
+        bad = bad || fabs(dd) < threshold || not_normal(dd);
+    }
+#pragma unroll
+    for (int c = 0; c < kN; ++c) d[c] = mine[c * 24];
+    return bad;
 }
 
 // ---- pieces of the up-sweep row task, each for block row r of the calling thread -----------------------------------------------
@@ -336,20 +341,24 @@ template <int T> __device__ __forceinline__ void schur_row6(double const* l, dou
 template <int T>
 __device__ __forceinline__ void finish_row6(Tile6<T> const& t, int row, int dg, int e_begin, int e_end, int e_step, bool diag_part,
                                             double const* d, uint32_t pk, uint32_t qk, double a_r) {
-    int const r = t.r, sc = t.sc;
-    if (diag_part && t.act) {
-        double* dp = t.jac + (size_t)dg * kNN * T;
-#pragma unroll
-        for (int c = 0; c < kN; ++c) dp[(size_t)(c * kN + r) * T] = d[c];
-        t.perm[(size_t)(row * 2 * kN + r) * T] = (uint8_t)nib(pk, r);
-        t.perm[(size_t)(row * 2 * kN + kN + r) * T] = (uint8_t)nib(qk, r);
-    }
-    __syncwarp();
+    int const r = t.r;
     uint32_t pinv = 0;
 #pragma unroll
     for (int i = 0; i < kN; ++i) pinv |= (uint32_t)i << (4 * nib(pk, i));
-    double lo[kNN]; // unit-lower factors lo[prev * 6 + idx], prev < idx (loads of the block stored by the six row threads)
-    {
+    double lo[kNN]; // unit-lower factors lo[prev * 6 + idx], prev < idx
+    if (diag_part) { // factorised by this warp a moment ago: the factor is in the warp's scratch in logical order
+        if (t.act) {
+            double* dp = t.jac + ((size_t)dg * kNN + r) * T;
+#pragma unroll
+            for (int c = 0; c < kN; ++c) dp[(size_t)(c * kN) * T] = d[c];
+            t.perm[(size_t)(row * 2 * kN + r) * T] = (uint8_t)nib(pk, r);
+            t.perm[(size_t)(row * 2 * kN + kN + r) * T] = (uint8_t)nib(qk, r);
+        }
+#pragma unroll
+        for (int idx = 0; idx < kN; ++idx)
+#pragma unroll
+            for (int prev = 0; prev < idx; ++prev) lo[prev * kN + idx] = t.sm[(prev * kN + idx) * 4];
+    } else { // factorised by another warp before the last block barrier
         double const* dp = t.jac + (size_t)dg * kNN * T;
 #pragma unroll
         for (int idx = 0; idx < kN; ++idx)
@@ -357,30 +366,32 @@ __device__ __forceinline__ void finish_row6(Tile6<T> const& t, int row, int dg, 
             for (int prev = 0; prev < idx; ++prev) lo[prev * kN + idx] = dp[(size_t)(prev * kN + idx) * T];
     }
     for (int e = e_begin; e < e_end; e += e_step) { // U blocks, column r of each: L_pp^-1 (P A), row permutation in the load addresses
-        double* ap = t.jac + (size_t)e * kNN * T;
+        double* ap = t.jac + ((size_t)e * kNN + r * kN) * T;
         double col[kN];
 #pragma unroll
-        for (int jj = 0; jj < kN; ++jj) col[jj] = ap[(size_t)(r * kN + nib(pinv, jj)) * T];
+        for (int jj = 0; jj < kN; ++jj) col[jj] = ap[(size_t)nib(pinv, jj) * T];
 #pragma unroll
         for (int idx = 0; idx < kN; ++idx)
 #pragma unroll
             for (int prev = 0; prev < idx; ++prev) col[idx] -= lo[prev * kN + idx] * col[prev];
         if (t.act) {
 #pragma unroll
-            for (int jj = 0; jj < kN; ++jj) ap[(size_t)(r * kN + jj) * T] = col[jj];
+            for (int jj = 0; jj < kN; ++jj) ap[(size_t)jj * T] = col[jj];
         }
     }
-    if (diag_part) { // every thread computes all six elements, stores its own
-        double av[kN], xr[kN];
+    if (diag_part) { // x = L_pp^-1 (P t): thread i drops its element at position p[i]; every thread solves, stores its own
+        double* const vs = t.sm + kNN * 4;
+        if (t.real) vs[nib(pk, r) * 4] = a_r;
+        __syncwarp();
+        double xr[kN];
 #pragma unroll
-        for (int i = 0; i < kN; ++i) av[i] = shfl_row(a_r, i, sc);
-#pragma unroll
-        for (int jj = 0; jj < kN; ++jj) xr[jj] = sel6(av, nib(pinv, jj));
+        for (int jj = 0; jj < kN; ++jj) xr[jj] = vs[jj * 4];
 #pragma unroll
         for (int idx = 0; idx < kN; ++idx)
 #pragma unroll
             for (int prev = 0; prev < idx; ++prev) xr[idx] -= lo[prev * kN + idx] * xr[prev];
         if (t.act) t.xvec[(size_t)(row * kN + r) * T] = sel6(xr, r);
+        __syncwarp(); // the scratch is reused by the next row task of this warp
     }
 }
 
@@ -452,7 +463,7 @@ template <int T, Mode mode> __device__ bool up_row6(DevStructure const& s, Tile6
 
     // 3. factorise the diagonal block across the six row threads; 4. U blocks; 5. forward substitution
     uint32_t pk, qk;
-    bool const singular = factorize6(d, r, sc, t.real, pk, qk);
+    bool const singular = factorize6s(t.sm, d, r, t.real, pk, qk);
     finish_row6<T>(t, row, dg, dg + 1, re, 1, true, d, pk, qk, a_r);
     return singular;
 }
@@ -580,7 +591,7 @@ __device__ void wide_up_row6(DevStructure const& s, Tile6<T> const& t, int w, in
         load_row(dg, d);
         double const a_r = t.xvec[(size_t)(row * kN + r) * T];
         uint32_t pk, qk;
-        singular |= factorize6(d, r, sc, t.real, pk, qk);
+        singular |= factorize6s(t.sm, d, r, t.real, pk, qk);
         finish_row6<T>(t, row, dg, 0, 0, 1, true, d, pk, qk, a_r);
     }
     __syncthreads();
@@ -597,7 +608,7 @@ __device__ void wide_up_row6(DevStructure const& s, Tile6<T> const& t, int w, in
 
 // ---- down-sweep row task ----------------------------------------------------------------------------------------------------
 template <int T, Mode mode> __device__ double down_row6(DevStructure const& s, Tile6<T> const& t, int row) {
-    int const r = t.r, sc = t.sc;
+    int const r = t.r;
     int const re = __ldg(s.row_ptr + row + 1), dg = __ldg(s.diag + row);
     double y_r = t.xvec[(size_t)(row * kN + r) * T];
     for (int e = re - 1; e > dg; --e) {
@@ -613,9 +624,14 @@ template <int T, Mode mode> __device__ double down_row6(DevStructure const& s, T
         }
         y_r -= sum;
     }
+    // gather the six elements through the warp's scratch; every thread solves the block, the solution goes back through the
+    // scratch at its permuted position: x[q[i]] = y[i]
+    double* const vs = t.sm + kNN * 4;
+    if (t.real) vs[r * 4] = y_r;
+    __syncwarp();
     double y[kN];
 #pragma unroll
-    for (int i = 0; i < kN; ++i) y[i] = shfl_row(y_r, i, sc);
+    for (int i = 0; i < kN; ++i) y[i] = vs[i * 4];
     double const* dp = t.jac + (size_t)dg * kNN * T;
 #pragma unroll
     for (int step = 0; step < kN; ++step) {
@@ -627,22 +643,16 @@ template <int T, Mode mode> __device__ double down_row6(DevStructure const& s, T
         }
         y[idx] /= dp[(size_t)(idx * kN + idx) * T];
     }
-    // x[q[i]] = y[i]
     uint8_t const* qr = t.perm + (size_t)(row * 2 * kN + kN) * T;
-    double x[kN];
-#pragma unroll
-    for (int jj = 0; jj < kN; ++jj) x[jj] = 0.0;
-#pragma unroll
-    for (int i = 0; i < kN; ++i) {
-        int const qi = qr[(size_t)i * T];
-#pragma unroll
-        for (int jj = 0; jj < kN; ++jj) x[jj] = (qi == jj) ? y[i] : x[jj];
-    }
-    if (t.act) t.xvec[(size_t)(row * kN + r) * T] = sel6(x, r);
+    __syncwarp();
+    if (t.real) vs[(int)qr[(size_t)r * T] * 4] = sel6(y, r); // thread i places y[i] at position q[i]
+    __syncwarp();
+    double const x_r = vs[r * 4];
+    if (t.act) t.xvec[(size_t)(row * kN + r) * T] = x_r;
     double dev = 0.0;
     if (r < kB && t.act) { // thread p updates phase p
         int const p = r;
-        double const xa = sel6(x, p), xb = sel6(x, kB + p);
+        double const xa = x_r, xb = vs[(kB + p) * 4];
         double* const pth = t.pol + (size_t)(row * kN + p) * T;
         double* const pv = t.pol + (size_t)(row * kN + kB + p) * T;
         double* const pur = t.u + (size_t)(row * kN + 2 * p) * T;
@@ -667,6 +677,7 @@ template <int T, Mode mode> __device__ double down_row6(DevStructure const& s, T
             *pth = atan2(xb, xa);
         }
     }
+    __syncwarp(); // the scratch is reused by the next row task of this warp
     return dev;
 }
 
@@ -711,6 +722,7 @@ template <int T, int MAXT> __global__ void __launch_bounds__(MAXT, 1) nr_block6_
     __shared__ unsigned long long sh_dev[T];
     __shared__ int sh_singular[T], sh_done[T], sh_status[T], sh_iter[T];
     __shared__ double sh_max_dev[T];
+    __shared__ double sh_scratch[MAXT / 32][(kNN + kN) * 4]; // per warp: one 6 x 6 block + one 6-vector for each of its 4 scenarios
     int const tile = blockIdx.x;
     int const warp = threadIdx.x / 32, wl = threadIdx.x % 32;
     int const n_warp = blockDim.x / 32;
@@ -735,6 +747,7 @@ template <int T, int MAXT> __global__ void __launch_bounds__(MAXT, 1) nr_block6_
         t6.wide_rhs = b.wide_rhs ? b.wide_rhs + (size_t)tile * s.wide_max_lower * kN * T + ln6 : nullptr;
         t6.wide_sum = b.wide_sum ? b.wide_sum + (size_t)tile * s.wide_max_entries * kN * T + ln6 : nullptr;
     }
+    t6.sm = &sh_scratch[warp][sc];
     t6.r = r8 < kN ? r8 : r8 - kN;
     t6.sc = sc;
     t6.real = r8 < kN;
