@@ -54,6 +54,8 @@ __device__ __forceinline__ double sel6(double const* d, int c) {
     return x;
 }
 __device__ __forceinline__ int nib(uint32_t packed, int i) { return (packed >> (4 * i)) & 15; }
+// a permutation index read from memory; lanes of finished / padding scenarios may read anything: keep their addresses in range
+__device__ __forceinline__ int perm_at(uint8_t const* p) { return min((int)*p, kN - 1); }
 __device__ __forceinline__ uint32_t nib_swap(uint32_t packed, int i, int j) {
     uint32_t const a = nib(packed, i), b = nib(packed, j);
     packed &= ~((15u << (4 * i)) | (15u << (4 * j)));
@@ -157,6 +159,21 @@ __device__ bool factorize6s(double* sm, double* d, int r, bool real_row, uint32_
 #pragma unroll
     for (int c = 0; c < kN; ++c) d[c] = mine[c * 24];
     return bad;
+}
+
+// ---- L1 prefetch of everything a row task will read ------------------------------------------------------------------------------
+// A row task is a chain of dependent global round trips (index -> child -> its factor -> its U blocks -> targets ...), ~1-2 k cycles
+// each; measured (PGMB_DEBUG_PHASES): 45 k cycles of a 73 k-cycle row task sit in the elimination step.  All those addresses follow
+// from the shared index arrays, so the task starts by pulling the lines into L1; the six row threads share the work (a block is
+// 36 elements x T scenarios x 8 B = 18 lines of 128 B for T = 8).
+__device__ __forceinline__ void pf_l1(void const* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+template <int T> __device__ __forceinline__ void prefetch_block6(double const* blk, int r) { // thread r: column r (6 elements)
+    double const* p = blk + (size_t)(r * kN) * T;
+#pragma unroll
+    for (int i = 0; i < kN; i += (T >= 16 ? 1 : 16 / T)) pf_l1(p + (size_t)i * T);
+}
+template <int T> __device__ __forceinline__ void prefetch_vec6(double const* v, int r) { // thread r: element r
+    pf_l1(v + (size_t)r * T);
 }
 
 // ---- pieces of the up-sweep row task, each for block row r of the calling thread -----------------------------------------------
@@ -344,7 +361,7 @@ __device__ __forceinline__ void finish_row6(Tile6<T> const& t, int row, int dg, 
     int const r = t.r;
     uint32_t pinv = 0;
 #pragma unroll
-    for (int i = 0; i < kN; ++i) pinv |= (uint32_t)i << (4 * nib(pk, i));
+    for (int i = 0; i < kN; ++i) pinv |= (uint32_t)i << (4 * min(nib(pk, i), kN - 1));
     double lo[kNN]; // unit-lower factors lo[prev * 6 + idx], prev < idx
     if (diag_part) { // factorised by this warp a moment ago: the factor is in the warp's scratch in logical order
         if (t.act) {
@@ -395,9 +412,38 @@ __device__ __forceinline__ void finish_row6(Tile6<T> const& t, int row, int dg, 
     }
 }
 
+// operands of the up-sweep task of `row`: the children's factors, permutations, right-hand sides and U blocks, the voltages of the
+// neighbours, the loads of the bus
+template <int T, Mode mode> __device__ __forceinline__ void prefetch_up6(DevStructure const& s, Tile6<T> const& t, int row) {
+    int const r = t.r;
+    int const rb = __ldg(s.row_ptr + row), re = __ldg(s.row_ptr + row + 1), dg = __ldg(s.diag + row);
+    for (int e = rb; e < dg; ++e) {
+        int const c = __ldg(s.col_idx + e);
+        prefetch_block6<T>(t.jac + (size_t)__ldg(s.diag + c) * kNN * T, r);
+        prefetch_vec6<T>(t.xvec + (size_t)(c * kN) * T, r);
+        if (r == 0) pf_l1(t.perm + (size_t)(c * 2 * kN + kN) * T);
+        for (int q = __ldg(s.upd_ptr + e), qe = __ldg(s.upd_ptr + e + 1); q < qe; ++q)
+            prefetch_block6<T>(t.jac + (size_t)__ldg(s.upd_u + q) * kNN * T, r);
+    }
+    if constexpr (mode == Mode::newton) {
+        for (int k = rb; k < re; ++k) prefetch_vec6<T>(t.u + (size_t)(__ldg(s.col_idx + k) * kN) * T, r);
+        prefetch_vec6<T>(t.pol + (size_t)(row * kN) * T, r);
+    }
+    for (int lg = __ldg(s.lg_ptr + row), lge = __ldg(s.lg_ptr + row + 1); lg < lge; ++lg) prefetch_vec6<T>(t.sinj + (size_t)(lg * kN) * T, r);
+}
+
 // ---- up-sweep row task (build + eliminate + factorise + U blocks + forward substitution) ------------------------------------
-template <int T, Mode mode> __device__ bool up_row6(DevStructure const& s, Tile6<T> const& t, int row) {
-    int const r = t.r, sc = t.sc;
+template <int T, Mode mode>
+__device__ bool up_row6(DevStructure const& s, Tile6<T> const& t, int row, bool prefetched, int next_row, unsigned long long* steps = nullptr) {
+    int const r = t.r;
+    long long c0 = steps != nullptr ? clock64() : 0;
+    auto step = [&](int k) { // PGMB_DEBUG_PHASES: cycles of one designated warp per step of the row task (slots 5, 6, 7)
+        if (steps != nullptr) {
+            long long const c1 = clock64();
+            steps[k] += (unsigned long long)(c1 - c0);
+            c0 = c1;
+        }
+    };
     bool const top = r < kB;
     int const rb = __ldg(s.row_ptr + row), re = __ldg(s.row_ptr + row + 1), dg = __ldg(s.diag + row);
     bool const dead_row = t.dead != nullptr && t.dead[row] != 0;
@@ -412,6 +458,10 @@ template <int T, Mode mode> __device__ bool up_row6(DevStructure const& s, Tile6
 #pragma unroll
     for (int i = 0; i < kN; ++i) d[i] = 0.0;
 
+    // 0. the operands of this task (first task of a level) and of the warp's next task in the level go into L1 now
+    if (!prefetched) prefetch_up6<T, mode>(s, t, row);
+    if (next_row >= 0) prefetch_up6<T, mode>(s, t, next_row);
+
     // 1. build my block row of every entry
     for (int k = rb; k < re; ++k) {
         double bl[kN], sn, sh;
@@ -424,13 +474,14 @@ template <int T, Mode mode> __device__ bool up_row6(DevStructure const& s, Tile6
 #pragma unroll
             for (int i = 0; i < kN; ++i) d[i] = bl[i];
         } else if (t.act) {
-            double* bp = t.jac + (size_t)k * kNN * T;
+            double* bp = t.jac + ((size_t)k * kNN + r) * T;
 #pragma unroll
-            for (int c = 0; c < kN; ++c) bp[(size_t)(c * kN + r) * T] = bl[c];
+            for (int c = 0; c < kN; ++c) bp[(size_t)(c * kN) * T] = bl[c];
         }
     }
     finish_diag6<T, mode>(s, t, row, dead_row, uir, uii, d, acc_p, acc_q);
     double a_r = top ? acc_p : acc_q; // my element of the right-hand side
+    step(5);
 
     // 2. eliminate against finished rows: my row of L, of every update and of the rhs are thread-local
     for (int e = rb; e < dg; ++e) {
@@ -440,7 +491,7 @@ template <int T, Mode mode> __device__ bool up_row6(DevStructure const& s, Tile6
         uint8_t const* qp = t.perm + (size_t)(c * 2 * kN + kN) * T;
         double l[kN];
 #pragma unroll
-        for (int i = 0; i < kN; ++i) l[i] = ap[(size_t)((int)qp[(size_t)i * T] * kN + r) * T];
+        for (int i = 0; i < kN; ++i) l[i] = ap[(size_t)(perm_at(qp + (size_t)i * T) * kN + r) * T];
         lower_row6<T>(pp, l);
         for (int q = __ldg(s.upd_ptr + e), qe = __ldg(s.upd_ptr + e + 1); q < qe; ++q) {
             int const ui = __ldg(s.upd_u + q), ai = __ldg(s.upd_a + q);
@@ -461,10 +512,12 @@ template <int T, Mode mode> __device__ bool up_row6(DevStructure const& s, Tile6
         a_r -= sum;
     }
 
+    step(6);
     // 3. factorise the diagonal block across the six row threads; 4. U blocks; 5. forward substitution
     uint32_t pk, qk;
     bool const singular = factorize6s(t.sm, d, r, t.real, pk, qk);
     finish_row6<T>(t, row, dg, dg + 1, re, 1, true, d, pk, qk, a_r);
+    step(7);
     return singular;
 }
 
@@ -551,7 +604,7 @@ __device__ void wide_up_row6(DevStructure const& s, Tile6<T> const& t, int w, in
                 sub_terms(pos, a);
                 uint8_t const* qp = t.perm + (size_t)(c * 2 * kN + kN) * T;
 #pragma unroll
-                for (int i = 0; i < kN; ++i) l[i] = sel6(a, (int)qp[(size_t)i * T]);
+                for (int i = 0; i < kN; ++i) l[i] = sel6(a, perm_at(qp + (size_t)i * T));
                 lower_row6<T>(t.jac + (size_t)__ldg(s.diag + c) * kNN * T, l);
                 for (int q = __ldg(s.upd_ptr + e), qe = __ldg(s.upd_ptr + e + 1); q < qe; ++q) {
                     double sum[kN];
@@ -599,7 +652,7 @@ __device__ void wide_up_row6(DevStructure const& s, Tile6<T> const& t, int w, in
     if (warp_active && dg + 1 + slot6 < re) {
         uint32_t pk = 0;
 #pragma unroll
-        for (int i = 0; i < kN; ++i) pk |= (uint32_t)t.perm[(size_t)(row * 2 * kN + i) * T] << (4 * i);
+        for (int i = 0; i < kN; ++i) pk |= (uint32_t)perm_at(t.perm + (size_t)(row * 2 * kN + i) * T) << (4 * i);
         double const dummy[kN] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
         finish_row6<T>(t, row, dg, dg + 1 + slot6, re, n_slot6, false, dummy, pk, 0u, 0.0);
     }
@@ -607,19 +660,38 @@ __device__ void wide_up_row6(DevStructure const& s, Tile6<T> const& t, int w, in
 }
 
 // ---- down-sweep row task ----------------------------------------------------------------------------------------------------
-template <int T, Mode mode> __device__ double down_row6(DevStructure const& s, Tile6<T> const& t, int row) {
+template <int T, Mode mode> __device__ __forceinline__ void prefetch_down6(DevStructure const& s, Tile6<T> const& t, int row) {
     int const r = t.r;
     int const re = __ldg(s.row_ptr + row + 1), dg = __ldg(s.diag + row);
+    for (int e = re - 1; e > dg; --e) {
+        int const j = __ldg(s.col_idx + e);
+        prefetch_block6<T>(t.jac + (size_t)e * kNN * T, r);
+        prefetch_vec6<T>(t.xvec + (size_t)(j * kN) * T, r);
+        if (r == 0) pf_l1(t.perm + (size_t)(j * 2 * kN + kN) * T);
+    }
+    prefetch_block6<T>(t.jac + (size_t)dg * kNN * T, r);
+    prefetch_vec6<T>(t.xvec + (size_t)(row * kN) * T, r);
+    if (r == 0) pf_l1(t.perm + (size_t)(row * 2 * kN + kN) * T);
+    if constexpr (mode == Mode::newton) {
+        prefetch_vec6<T>(t.pol + (size_t)(row * kN) * T, r);
+        prefetch_vec6<T>(t.u + (size_t)(row * kN) * T, r);
+    }
+}
+template <int T, Mode mode> __device__ double down_row6(DevStructure const& s, Tile6<T> const& t, int row, bool prefetched, int next_row) {
+    int const r = t.r;
+    int const re = __ldg(s.row_ptr + row + 1), dg = __ldg(s.diag + row);
+    if (!prefetched) prefetch_down6<T, mode>(s, t, row);
+    if (next_row >= 0) prefetch_down6<T, mode>(s, t, next_row);
     double y_r = t.xvec[(size_t)(row * kN + r) * T];
     for (int e = re - 1; e > dg; --e) {
         int const j = __ldg(s.col_idx + e);
         uint8_t const* qp = t.perm + (size_t)(j * 2 * kN + kN) * T;
         double const* up = t.jac + (size_t)e * kNN * T;
-        int const q0 = qp[0];
+        int const q0 = perm_at(qp);
         double sum = up[(size_t)(q0 * kN + r) * T] * t.xvec[(size_t)(j * kN + q0) * T];
 #pragma unroll
         for (int i = 1; i < kN; ++i) {
-            int const qi = qp[(size_t)i * T];
+            int const qi = perm_at(qp + (size_t)i * T);
             sum += up[(size_t)(qi * kN + r) * T] * t.xvec[(size_t)(j * kN + qi) * T];
         }
         y_r -= sum;
@@ -645,7 +717,7 @@ template <int T, Mode mode> __device__ double down_row6(DevStructure const& s, T
     }
     uint8_t const* qr = t.perm + (size_t)(row * 2 * kN + kN) * T;
     __syncwarp();
-    if (t.real) vs[(int)qr[(size_t)r * T] * 4] = sel6(y, r); // thread i places y[i] at position q[i]
+    if (t.real) vs[perm_at(qr + (size_t)r * T) * 4] = sel6(y, r); // thread i places y[i] at position q[i]
     __syncwarp();
     double const x_r = vs[r * 4];
     if (t.act) t.xvec[(size_t)(row * kN + r) * T] = x_r;
@@ -695,12 +767,14 @@ __device__ void sweeps6(DevStructure const& s, Tile6<T>& t6, int slot6, int n_sl
     bool const warp_active = __any_sync(kFull, t6.act); // a warp whose four scenarios are all finished skips its row tasks
     for (int lv = 0; lv < s.n_level; ++lv) {
         int const b = __ldg(s.level_ptr + lv), e = __ldg(s.level_ptr + lv + 1);
-        if (warp_active)
+        if (warp_active) {
+            // (prefetching the warp's NEXT row of the level during the current task was measured: no gain, 37.5 -> 38.9 ms)
             for (int i = b + slot6; i < e; i += n_slot6) {
                 int const row = __ldg(s.level_rows + i);
-                if (s.n_wide != 0 && __ldg(s.row_is_wide + row)) continue;
-                singular6 |= up_row6<T, mode>(s, t6, row);
+                if (s.n_wide != 0 && __ldg(s.row_is_wide + row)) continue; // eliminated below by the whole block
+                singular6 |= up_row6<T, mode>(s, t6, row, false, -1, (phase != nullptr && threadIdx.x == 0 && lv != 0) ? phase : nullptr);
             }
+        }
         __syncthreads();
         lap(lv == 0 ? 0 : 2);
         if (s.n_wide != 0)
@@ -711,7 +785,7 @@ __device__ void sweeps6(DevStructure const& s, Tile6<T>& t6, int slot6, int n_sl
     for (int lv = s.n_level - 1; lv >= 0; --lv) {
         int const b = __ldg(s.level_ptr + lv), e = __ldg(s.level_ptr + lv + 1);
         if (warp_active)
-            for (int i = b + slot6; i < e; i += n_slot6) dev = fmax(dev, down_row6<T, mode>(s, t6, __ldg(s.level_rows + i)));
+            for (int i = b + slot6; i < e; i += n_slot6) dev = fmax(dev, down_row6<T, mode>(s, t6, __ldg(s.level_rows + i), false, -1));
         __syncthreads();
         lap(lv == 0 ? 4 : 3);
     }
