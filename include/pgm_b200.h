@@ -204,6 +204,8 @@ typedef struct pgmb_input_data {
      * reference's component list (all_components.hpp:36-39): line, asym_line, generic_branch, transformer */
     pgmb_component_buffer asym_line;      /* AsymLineInput (auxiliary/input.hpp:99-142) */
     pgmb_component_buffer generic_branch; /* GenericBranchInput (auxiliary/input.hpp:144-165); symmetric calculations only */
+    pgmb_component_buffer link;           /* LinkInput = BranchInput; branch sequence: line, asym_line, link, generic_branch, transformer */
+    pgmb_component_buffer three_winding_transformer; /* ThreeWindingTransformerInput (Branch3Input + transformer data, 304 bytes) */
 } pgmb_input_data;
 
 typedef struct pgmb_update_data {
@@ -211,6 +213,8 @@ typedef struct pgmb_update_data {
     pgmb_component_buffer line, transformer, shunt, source, sym_gen, asym_gen, sym_load, asym_load;
     pgmb_component_buffer voltage_regulator; /* VoltageRegulatorUpdate (auxiliary/update.hpp:213-219) */
     pgmb_component_buffer asym_line, generic_branch; /* BranchUpdate */
+    pgmb_component_buffer link;                      /* BranchUpdate */
+    pgmb_component_buffer three_winding_transformer; /* ThreeWindingTransformerUpdate: id, status_1, status_2, status_3, tap_pos */
 } pgmb_update_data;
 
 /* caller-owned output buffers [n_scenarios][n_component]; NULL = component not requested
@@ -219,6 +223,8 @@ typedef struct pgmb_output_data {
     void *node, *line, *transformer, *shunt, *source, *sym_gen, *asym_gen, *sym_load, *asym_load;
     void* voltage_regulator; /* VoltageRegulatorOutput (auxiliary/output.hpp:239-243) */
     void *asym_line, *generic_branch; /* BranchOutput */
+    void* link;                       /* BranchOutput (loading 0) */
+    void* three_winding_transformer;  /* Branch3Output (auxiliary/output.hpp): loading_1..3, loading, p/q/i/s per side */
 } pgmb_output_data;
 
 /* pgmb_options.flags -- measurement of the device-resident pipeline (bench.py `value`): one load-profile batch on one device.

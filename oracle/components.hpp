@@ -42,6 +42,24 @@ struct GenericBranchInput { // auxiliary/input.hpp:144-165
     double r1, x1, g1, b1, k, theta, sn;
 };
 static_assert(sizeof(AsymLineInput) == 248 && sizeof(GenericBranchInput) == 72);
+struct LinkInput { // auxiliary/input.hpp: LinkInput = BranchInput
+    ID id, from_node, to_node;
+    IntS from_status, to_status;
+};
+struct ThreeWindingTransformerInput { // auxiliary/input.hpp: Branch3Input + ThreeWindingTransformerInput
+    ID id, node_1, node_2, node_3;
+    IntS status_1, status_2, status_3;
+    double u1, u2, u3, sn_1, sn_2, sn_3, uk_12, uk_13, uk_23, pk_12, pk_13, pk_23, i0, p0;
+    IntS winding_1, winding_2, winding_3, clock_12, clock_13, tap_side, tap_pos, tap_min, tap_max, tap_nom;
+    double tap_size, uk_12_min, uk_12_max, uk_13_min, uk_13_max, uk_23_min, uk_23_max, pk_12_min, pk_12_max, pk_13_min, pk_13_max,
+        pk_23_min, pk_23_max, r_grounding_1, x_grounding_1, r_grounding_2, x_grounding_2, r_grounding_3, x_grounding_3;
+};
+static_assert(sizeof(LinkInput) == 16 && sizeof(ThreeWindingTransformerInput) == 304);
+struct ThreeWindingTransformerUpdate { // auxiliary/update.hpp: Branch3Update + tap_pos
+    ID id;
+    IntS status_1, status_2, status_3, tap_pos;
+};
+static_assert(sizeof(ThreeWindingTransformerUpdate) == 8);
 struct TransformerInput {
     ID id, from_node, to_node;
     IntS from_status, to_status;
@@ -133,6 +151,13 @@ struct VoltageRegulatorOutput {
 static_assert(sizeof(VoltageRegulatorInput) == 40 && sizeof(VoltageRegulatorUpdate) == 32 && sizeof(VoltageRegulatorOutput) == 8);
 static_assert(sizeof(LineInput) == 88 && sizeof(TransformerInput) == 168 && sizeof(SourceInput) == 56);
 static_assert(sizeof(SymLoadGenUpdate) == 24 && sizeof(AsymLoadGenUpdate) == 56);
+template <int B> struct Branch3Output { // auxiliary/output.hpp: Branch3Output<sym>
+    ID id;
+    IntS energized;
+    double loading_1, loading_2, loading_3, loading;
+    double p_1[B], q_1[B], i_1[B], s_1[B], p_2[B], q_2[B], i_2[B], s_2[B], p_3[B], q_3[B], i_3[B], s_3[B];
+};
+static_assert(sizeof(Branch3Output<1>) == 136 && sizeof(Branch3Output<3>) == 328);
 static_assert(sizeof(NodeOutput<1>) == 48 && sizeof(NodeOutput<3>) == 128);
 static_assert(sizeof(BranchOutput<1>) == 80 && sizeof(BranchOutput<3>) == 208);
 static_assert(sizeof(ApplianceOutput<1>) == 48 && sizeof(ApplianceOutput<3>) == 128);
@@ -260,6 +285,32 @@ struct GenericBranch : BranchBase {
             return calc_param_y_sym(y1_series, y1_shunt, ratio);
         } else {
             throw PgmError{"Function not yet implemented: generic_branch in an asymmetric calculation"};
+        }
+    }
+};
+
+// component/link.hpp:16-39: a branch with the fixed series admittance y_link (common/common.hpp:100-101), no shunt, ratio 1.
+// At this snapshot of the reference links are ordinary branches of the math model (main_core/topology.hpp never fills
+// link_node_idx, so supernodes::reduce_topology takes its dont_reduce_topology branch).
+constexpr double g_link = 1e6 / (base_power_3p / 10e3 / 10e3);
+struct Link : BranchBase {
+    Link(LinkInput const& in, double u1, double u2) {
+        id = in.id;
+        from_node = in.from_node;
+        to_node = in.to_node;
+        from_status = in.from_status != 0;
+        to_status = in.to_status != 0;
+        base_i_from = base_power_3p / u1 / sqrt3;
+        base_i_to = base_power_3p / u2 / sqrt3;
+    }
+    double phase_shift() const { return 0.0; }
+    template <int B> BranchCalcParam<B> calc_param() const {
+        if (!(from_status || to_status)) return BranchCalcParam<B>{};
+        cplx const y_link{g_link, g_link};
+        if constexpr (B == 1) {
+            return calc_param_y_sym(y_link, 0.0, 1.0);
+        } else {
+            return calc_param_y_asym(y_link, 0.0, y_link, 0.0, 1.0);
         }
     }
 };
@@ -567,6 +618,129 @@ struct Transformer : BranchBase {
             }
             return param;
         }
+    }
+};
+
+// component/three_winding_transformer.hpp:28-435 (+ component/branch3.hpp): three two-winding transformers T1, T2, T3 between the
+// three nodes and an internal node; uk / pk converted delta -> wye relative to side 1 (:226-280); T1 is a YNyn0 transformer that
+// carries i0 / p0, T2 / T3 take the reversed clocks (:301-408)
+struct ThreeWindingTransformer {
+    ThreeWindingTransformerInput in;
+    double u_rated[3];
+    bool status[3];
+    IntS tap_pos, tap_nom, tap_direction, clock_12, clock_13;
+    double base_i[3];
+
+    ThreeWindingTransformer(ThreeWindingTransformerInput const& input, double u1_rated, double u2_rated, double u3_rated)
+        : in{input}, u_rated{u1_rated, u2_rated, u3_rated}, status{input.status_1 != 0, input.status_2 != 0, input.status_3 != 0} {
+        auto nz = [](double& v, double fallback) { v = is_nan(v) ? fallback : v; };
+        tap_nom = in.tap_nom == na_IntS ? IntS{0} : in.tap_nom;
+        tap_direction = in.tap_max > in.tap_min ? IntS{1} : IntS{-1};
+        nz(in.uk_12_min, in.uk_12), nz(in.uk_12_max, in.uk_12), nz(in.uk_13_min, in.uk_13), nz(in.uk_13_max, in.uk_13);
+        nz(in.uk_23_min, in.uk_23), nz(in.uk_23_max, in.uk_23), nz(in.pk_12_min, in.pk_12), nz(in.pk_12_max, in.pk_12);
+        nz(in.pk_13_min, in.pk_13), nz(in.pk_13_max, in.pk_13), nz(in.pk_23_min, in.pk_23), nz(in.pk_23_max, in.pk_23);
+        for (int k = 0; k != 3; ++k) base_i[k] = base_power_3p / u_rated[k] / sqrt3;
+        tap_pos = in.tap_pos == na_IntS ? tap_nom : in.tap_pos;
+        auto valid_clock = [](IntS clock, IntS w_a, IntS w_b) { // transformer_utils.hpp is_valid_clock
+            auto wye = [](IntS w) { return w == 0 || w == 1; };
+            bool const clock_is_even = (clock % 2) == 0;
+            return clock_is_even == (wye(w_a) == wye(w_b));
+        };
+        if (!valid_clock(in.clock_12, in.winding_1, in.winding_2)) throw PgmError{"Invalid clock for transformer " + std::to_string(in.id)};
+        if (!valid_clock(in.clock_13, in.winding_1, in.winding_3)) throw PgmError{"Invalid clock for transformer " + std::to_string(in.id)};
+        clock_12 = static_cast<IntS>((in.clock_12 % 12 + 12) % 12);
+        clock_13 = static_cast<IntS>((in.clock_13 % 12 + 12) % 12);
+        tap_pos = tap_limit(tap_pos);
+    }
+    IntS tap_limit(IntS new_tap) const {
+        new_tap = std::min(new_tap, std::max(in.tap_max, in.tap_min));
+        new_tap = std::max(new_tap, std::min(in.tap_max, in.tap_min));
+        return new_tap;
+    }
+    bool energized() const { return status[0] || status[1] || status[2]; }
+    std::array<double, 3> phase_shift() const { return {0.0, -clock_12 * deg_30, -clock_13 * deg_30}; }
+    double loading_side(int k, double s) const { return s / (k == 0 ? in.sn_1 : (k == 1 ? in.sn_2 : in.sn_3)); }
+    bool set_status(IntS s1, IntS s2, IntS s3) {
+        IntS const v[3] = {s1, s2, s3};
+        bool changed = false;
+        for (int k = 0; k != 3; ++k) {
+            if (v[k] == na_IntS) continue;
+            changed = changed || (status[k] != static_cast<bool>(v[k]));
+            status[k] = static_cast<bool>(v[k]);
+        }
+        return changed;
+    }
+    bool set_tap(IntS new_tap) {
+        if (new_tap == na_IntS || new_tap == tap_pos) return false;
+        tap_pos = tap_limit(new_tap);
+        return true;
+    }
+    std::array<Transformer, 3> two_winding() const {
+        double u1 = in.u1, u2 = in.u2, u3 = in.u3;
+        double const du = tap_direction * (tap_pos - tap_nom) * in.tap_size;
+        if (in.tap_side == 0) {
+            u1 += du;
+        } else if (in.tap_side == 1) {
+            u2 += du;
+        } else {
+            u3 += du;
+        }
+        auto adj = [&](double x, double x_min, double x_max) { return tap_adjust_impedance(tap_pos, in.tap_min, in.tap_max, tap_nom, x, x_min, x_max); };
+        double const sn_1 = in.sn_1, sn_2 = in.sn_2, sn_3 = in.sn_3;
+        // calculate_uk (:226-252)
+        double const uk_12 = adj(in.uk_12, in.uk_12_min, in.uk_12_max) * sn_1 / std::min(sn_1, sn_2);
+        double const uk_13 = adj(in.uk_13, in.uk_13_min, in.uk_13_max) * sn_1 / std::min(sn_1, sn_3);
+        double const uk_23 = adj(in.uk_23, in.uk_23_min, in.uk_23_max) * sn_1 / std::min(sn_2, sn_3);
+        double const uk_t1 = 0.5 * (uk_12 + uk_13 - uk_23);
+        double const uk_t2 = 0.5 * (uk_12 + uk_23 - uk_13) * (sn_2 / sn_1);
+        double const uk_t3 = 0.5 * (uk_13 + uk_23 - uk_12) * (sn_3 / sn_1);
+        // calculate_pk (:254-280)
+        double const pk_12 = adj(in.pk_12, in.pk_12_min, in.pk_12_max) * (sn_1 / std::min(sn_1, sn_2)) * (sn_1 / std::min(sn_1, sn_2));
+        double const pk_13 = adj(in.pk_13, in.pk_13_min, in.pk_13_max) * (sn_1 / std::min(sn_1, sn_3)) * (sn_1 / std::min(sn_1, sn_3));
+        double const pk_23 = adj(in.pk_23, in.pk_23_min, in.pk_23_max) * (sn_1 / std::min(sn_2, sn_3)) * (sn_1 / std::min(sn_2, sn_3));
+        double const pk_t1 = 0.5 * (pk_12 + pk_13 - pk_23);
+        double const pk_t2 = 0.5 * (pk_12 + pk_23 - pk_13) * (sn_2 / sn_1) * (sn_2 / sn_1);
+        double const pk_t3 = 0.5 * (pk_13 + pk_23 - pk_12) * (sn_3 / sn_1) * (sn_3 / sn_1);
+        auto make = [&](bool st, double ua, double sn, double uk, double pk, double i0, double p0, IntS w_from, IntS w_to, IntS clock, double rg,
+                        double xg, double u_rated_from) {
+            TransformerInput t{};
+            t.id = 2;
+            t.from_node = 0;
+            t.to_node = 1;
+            t.from_status = st ? 1 : 0;
+            t.to_status = 1;
+            t.u1 = ua;
+            t.u2 = u1;
+            t.sn = sn;
+            t.uk = uk;
+            t.pk = pk;
+            t.i0 = i0;
+            t.p0 = p0;
+            t.i0_zero_sequence = nan;
+            t.p0_zero_sequence = nan;
+            t.winding_from = w_from;
+            t.winding_to = w_to;
+            t.clock = clock;
+            t.tap_side = 0;
+            t.tap_pos = t.tap_min = t.tap_max = t.tap_nom = 0;
+            t.tap_size = 0.0;
+            t.uk_min = t.uk_max = t.pk_min = t.pk_max = nan;
+            t.r_grounding_from = rg;
+            t.x_grounding_from = xg;
+            t.r_grounding_to = 0.0;
+            t.x_grounding_to = 0.0;
+            return Transformer{t, u_rated_from, u_rated[0]};
+        };
+        return {make(status[0], u1, sn_1, uk_t1, pk_t1, in.i0, in.p0, 1, 1, 0, in.r_grounding_1, in.x_grounding_1, u_rated[0]),
+                make(status[1], u2, sn_2, uk_t2, pk_t2, 0.0, 0.0, in.winding_2, in.winding_1, static_cast<IntS>(12 - clock_12), in.r_grounding_2,
+                     in.x_grounding_2, u_rated[1]),
+                make(status[2], u3, sn_3, uk_t3, pk_t3, 0.0, 0.0, in.winding_3, in.winding_1, static_cast<IntS>(12 - clock_13), in.r_grounding_3,
+                     in.x_grounding_3, u_rated[2])};
+    }
+    template <int B> std::array<BranchCalcParam<B>, 3> calc_param() const {
+        if (!energized()) return {};
+        auto const t = two_winding();
+        return {t[0].template calc_param<B>(), t[1].template calc_param<B>(), t[2].template calc_param<B>()};
     }
 };
 

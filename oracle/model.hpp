@@ -47,6 +47,10 @@ struct ModelInput {
     AsymLineInput const* asym_line;
     Idx n_generic_branch;
     GenericBranchInput const* generic_branch;
+    Idx n_link;
+    LinkInput const* link;
+    Idx n_three_winding_transformer;
+    ThreeWindingTransformerInput const* three_winding_transformer;
 };
 
 // one buffer of a batch update dataset: uniform (indptr == nullptr, n_per_scenario elements each) or sparse
@@ -73,6 +77,8 @@ struct BatchUpdate {
     UpdateBuffer<VoltageRegulatorUpdate> voltage_regulator;
     UpdateBuffer<BranchUpdate> asym_line;
     UpdateBuffer<BranchUpdate> generic_branch;
+    UpdateBuffer<BranchUpdate> link;
+    UpdateBuffer<ThreeWindingTransformerUpdate> three_winding_transformer;
 };
 // output buffers, each [n_scenarios][n_component] or nullptr when the caller does not want that component
 template <int B> struct BatchOutput {
@@ -88,6 +94,8 @@ template <int B> struct BatchOutput {
     VoltageRegulatorOutput* voltage_regulator;
     BranchOutput<B>* asym_line;
     BranchOutput<B>* generic_branch;
+    BranchOutput<B>* link;
+    Branch3Output<B>* three_winding_transformer;
 };
 
 struct CalcOptions {
@@ -120,6 +128,10 @@ class Model {
             asym_lines_.emplace_back(in.asym_line[i], system_frequency_, u_rated(in.asym_line[i].from_node),
                                      u_rated(in.asym_line[i].to_node));
         }
+        for (Idx i = 0; i != in.n_link; ++i) {
+            add_id(in.link[i].id);
+            links_.emplace_back(in.link[i], u_rated(in.link[i].from_node), u_rated(in.link[i].to_node));
+        }
         for (Idx i = 0; i != in.n_generic_branch; ++i) {
             add_id(in.generic_branch[i].id);
             generic_branches_.emplace_back(in.generic_branch[i], u_rated(in.generic_branch[i].from_node),
@@ -129,6 +141,11 @@ class Model {
             add_id(in.transformer[i].id);
             transformers_.emplace_back(in.transformer[i], u_rated(in.transformer[i].from_node),
                                        u_rated(in.transformer[i].to_node));
+        }
+        for (Idx i = 0; i != in.n_three_winding_transformer; ++i) {
+            auto const& t = in.three_winding_transformer[i];
+            add_id(t.id);
+            t3w_.emplace_back(t, u_rated(t.node_1), u_rated(t.node_2), u_rated(t.node_3));
         }
         for (Idx i = 0; i != in.n_shunt; ++i) {
             add_id(in.shunt[i].id);
@@ -165,6 +182,8 @@ class Model {
         for (size_t i = 0; i != transformers_.size(); ++i) transformer_idx_[transformers_[i].id] = static_cast<Idx>(i);
         for (size_t i = 0; i != asym_lines_.size(); ++i) asym_line_idx_[asym_lines_[i].id] = static_cast<Idx>(i);
         for (size_t i = 0; i != generic_branches_.size(); ++i) generic_branch_idx_[generic_branches_[i].id] = static_cast<Idx>(i);
+        for (size_t i = 0; i != links_.size(); ++i) link_idx_[links_[i].id] = static_cast<Idx>(i);
+        for (size_t i = 0; i != t3w_.size(); ++i) t3w_idx_[t3w_[i].in.id] = static_cast<Idx>(i);
         for (size_t i = 0; i != shunts_.size(); ++i) shunt_idx_[shunts_[i].id] = static_cast<Idx>(i);
         for (size_t i = 0; i != sources_.size(); ++i) source_idx_[sources_[i].id] = static_cast<Idx>(i);
         for (size_t i = 0; i != load_gens_.size(); ++i) load_gen_idx_[load_gens_[i].id] = static_cast<Idx>(i);
@@ -187,7 +206,7 @@ class Model {
 
     Idx n_node() const { return static_cast<Idx>(nodes_.size()); }
     Idx n_branch() const {
-        return static_cast<Idx>(lines_.size() + asym_lines_.size() + generic_branches_.size() + transformers_.size());
+        return static_cast<Idx>(lines_.size() + asym_lines_.size() + links_.size() + generic_branches_.size() + transformers_.size());
     }
 
     // ---- single calculation ----
@@ -317,8 +336,10 @@ class Model {
     std::vector<Line> lines_;
     std::vector<AsymLine> asym_lines_;
     std::vector<GenericBranch> generic_branches_;
+    std::vector<Link> links_;
     std::vector<Transformer> transformers_;
-    std::unordered_map<ID, Idx> asym_line_idx_, generic_branch_idx_;
+    std::vector<ThreeWindingTransformer> t3w_;
+    std::unordered_map<ID, Idx> asym_line_idx_, generic_branch_idx_, link_idx_, t3w_idx_;
     std::vector<Shunt> shunts_;
     std::vector<Source> sources_;
     std::vector<LoadGen> load_gens_; // sym_gen, asym_gen, sym_load, asym_load
@@ -360,9 +381,10 @@ class Model {
     // branch sequence = component order of the reference (all_components.hpp:36-39): line, asym_line, (link), generic_branch,
     // transformer
     Idx branch_seq_asym_line(Idx i) const { return static_cast<Idx>(lines_.size()) + i; }
-    Idx branch_seq_generic_branch(Idx i) const { return static_cast<Idx>(lines_.size() + asym_lines_.size()) + i; }
+    Idx branch_seq_link(Idx i) const { return static_cast<Idx>(lines_.size() + asym_lines_.size()) + i; }
+    Idx branch_seq_generic_branch(Idx i) const { return static_cast<Idx>(lines_.size() + asym_lines_.size() + links_.size()) + i; }
     Idx branch_seq_transformer(Idx i) const {
-        return static_cast<Idx>(lines_.size() + asym_lines_.size() + generic_branches_.size()) + i;
+        return static_cast<Idx>(lines_.size() + asym_lines_.size() + links_.size() + generic_branches_.size()) + i;
     }
 
     void prepare_topology() {
@@ -377,8 +399,14 @@ class Model {
         };
         for (auto const& l : lines_) add_branch(l, l.phase_shift());
         for (auto const& l : asym_lines_) add_branch(l, l.phase_shift());
+        for (auto const& l : links_) add_branch(l, l.phase_shift());
         for (auto const& g : generic_branches_) add_branch(g, g.phase_shift());
         for (auto const& t : transformers_) add_branch(t, t.phase_shift());
+        for (auto const& t : t3w_) { // main_core/topology.hpp: branch3_node_idx / branch3_connected / branch3_phase_shift
+            comp_topo_.branch3_node_idx.push_back({node_idx_.at(t.in.node_1), node_idx_.at(t.in.node_2), node_idx_.at(t.in.node_3)});
+            conn.branch3_connected.push_back({static_cast<IntS>(t.status[0]), static_cast<IntS>(t.status[1]), static_cast<IntS>(t.status[2])});
+            conn.branch3_phase_shift.push_back(t.phase_shift());
+        }
         for (auto const& s : shunts_) comp_topo_.shunt_node_idx.push_back(node_idx_.at(s.node));
         for (auto const& s : sources_) {
             comp_topo_.source_node_idx.push_back(node_idx_.at(s.node));
@@ -420,6 +448,16 @@ class Model {
         for (size_t i = 0; i != generic_branches_.size(); ++i) {
             Idx2D const m = coup_.branch[branch_seq_generic_branch(static_cast<Idx>(i))];
             if (m.group != -1) param[m.group].branch_param[m.pos] = generic_branches_[i].calc_param<B>();
+        }
+        for (size_t i = 0; i != links_.size(); ++i) {
+            Idx2D const m = coup_.branch[branch_seq_link(static_cast<Idx>(i))];
+            if (m.group != -1) param[m.group].branch_param[m.pos] = links_[i].calc_param<B>();
+        }
+        for (size_t i = 0; i != t3w_.size(); ++i) { // main_core/y_bus.hpp:196-204: three branches per Branch3
+            auto const& [group, pos] = coup_.branch3[i];
+            if (group == -1) continue;
+            auto const p3 = t3w_[i].calc_param<B>();
+            for (int k = 0; k != 3; ++k) param[group].branch_param[pos[k]] = p3[k];
         }
         for (size_t i = 0; i != transformers_.size(); ++i) {
             Idx2D const m = coup_.branch[branch_seq_transformer(static_cast<Idx>(i))];
@@ -590,6 +628,47 @@ class Model {
                                   : branch_output<B>(asym_lines_[i], so[m.group].branch[m.pos], -1.0, asym_lines_[i].i_n);
             }
         }
+        if (out.link != nullptr) { // Link::loading = 0 (link.hpp:30)
+            Idx const n = static_cast<Idx>(links_.size());
+            for (Idx i = 0; i != n; ++i) {
+                Idx2D const m = coup_.branch[branch_seq_link(i)];
+                out.link[scenario * n + i] =
+                    m.group == -1 ? null_branch(links_[i])
+                                  : branch_output<B>(links_[i], so[m.group].branch[m.pos], std::numeric_limits<double>::infinity(), 0.0);
+            }
+        }
+        if (out.three_winding_transformer != nullptr) { // Branch3::get_output (branch3.hpp:93-122), main_core/output.hpp
+            Idx const n = static_cast<Idx>(t3w_.size());
+            for (Idx i = 0; i != n; ++i) {
+                auto const& t = t3w_[i];
+                auto const& [group, pos] = coup_.branch3[i];
+                Branch3Output<B> o{};
+                o.id = t.in.id;
+                if (group != -1) {
+                    o.energized = t.energized() ? 1 : 0;
+                    double sum_s[3];
+                    auto side = [&](int k, double* p, double* q, double* cur, double* sv) {
+                        auto const& b = so[group].branch[pos[k]];
+                        sum_s[k] = 0.0;
+                        for (int ph = 0; ph < B; ++ph) {
+                            p[ph] = base_power<B> * b.s_f.v[ph].real();
+                            q[ph] = base_power<B> * b.s_f.v[ph].imag();
+                            cur[ph] = t.base_i[k] * cabs(b.i_f.v[ph]);
+                            sv[ph] = base_power<B> * cabs(b.s_f.v[ph]);
+                            sum_s[k] = ph == 0 ? sv[ph] : sum_s[k] + sv[ph];
+                        }
+                    };
+                    side(0, o.p_1, o.q_1, o.i_1, o.s_1);
+                    side(1, o.p_2, o.q_2, o.i_2, o.s_2);
+                    side(2, o.p_3, o.q_3, o.i_3, o.s_3);
+                    o.loading_1 = t.loading_side(0, sum_s[0]);
+                    o.loading_2 = t.loading_side(1, sum_s[1]);
+                    o.loading_3 = t.loading_side(2, sum_s[2]);
+                    o.loading = std::max({o.loading_1, o.loading_2, o.loading_3});
+                }
+                out.three_winding_transformer[scenario * n + i] = o;
+            }
+        }
         if (out.generic_branch != nullptr) {
             Idx const n = static_cast<Idx>(generic_branches_.size());
             for (Idx i = 0; i != n; ++i) {
@@ -653,6 +732,8 @@ class Model {
         std::vector<std::pair<Idx, Transformer>> transformers;
         std::vector<std::pair<Idx, AsymLine>> asym_lines;
         std::vector<std::pair<Idx, GenericBranch>> generic_branches;
+        std::vector<std::pair<Idx, Link>> links;
+        std::vector<std::pair<Idx, ThreeWindingTransformer>> t3w;
         std::vector<std::pair<Idx, Shunt>> shunts;
         std::vector<std::pair<Idx, Source>> sources;
         std::vector<std::pair<Idx, LoadGen>> load_gens;
@@ -705,6 +786,25 @@ class Model {
                 saved.generic_branches.emplace_back(i, generic_branches_[i]);
                 bool const changed = generic_branches_[i].set_status(p->from_status, p->to_status);
                 mark(changed, changed, saved);
+            }
+        }
+        {
+            auto [b, e] = upd.link.scenario(s);
+            for (auto p = b; p != e; ++p) {
+                Idx const i = find_seq(*p, p - b, e - b, static_cast<Idx>(links_.size()), link_idx_, 0);
+                saved.links.emplace_back(i, links_[i]);
+                bool const changed = links_[i].set_status(p->from_status, p->to_status);
+                mark(changed, changed, saved);
+            }
+        }
+        {
+            auto [b, e] = upd.three_winding_transformer.scenario(s);
+            for (auto p = b; p != e; ++p) { // ThreeWindingTransformer::update (three_winding_transformer.hpp:158-163)
+                Idx const i = find_seq(*p, p - b, e - b, static_cast<Idx>(t3w_.size()), t3w_idx_, 0);
+                saved.t3w.emplace_back(i, t3w_[i]);
+                bool const topo = t3w_[i].set_status(p->status_1, p->status_2, p->status_3);
+                bool const param = t3w_[i].set_tap(p->tap_pos) || topo;
+                mark(topo, param, saved);
             }
         }
         {
@@ -787,6 +887,8 @@ class Model {
             generic_branches_[it->first] = it->second;
         for (auto it = saved.transformers.rbegin(); it != saved.transformers.rend(); ++it)
             transformers_[it->first] = it->second;
+        for (auto it = saved.links.rbegin(); it != saved.links.rend(); ++it) links_[it->first] = it->second;
+        for (auto it = saved.t3w.rbegin(); it != saved.t3w.rend(); ++it) t3w_[it->first] = it->second;
         for (auto it = saved.shunts.rbegin(); it != saved.shunts.rend(); ++it) shunts_[it->first] = it->second;
         for (auto it = saved.sources.rbegin(); it != saved.sources.rend(); ++it) sources_[it->first] = it->second;
         for (auto it = saved.load_gens.rbegin(); it != saved.load_gens.rend(); ++it) load_gens_[it->first] = it->second;

@@ -85,7 +85,7 @@ class ComponentBufferC(C.Structure):
 
 
 _COMPS = ("node", "line", "transformer", "shunt", "source", "sym_gen", "asym_gen", "sym_load", "asym_load", "voltage_regulator",
-          "asym_line", "generic_branch")
+          "asym_line", "generic_branch", "link", "three_winding_transformer")
 
 
 class InputDataC(C.Structure):

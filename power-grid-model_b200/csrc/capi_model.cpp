@@ -12,11 +12,13 @@ namespace {
 ComponentBuffer cb(pgmb_component_buffer const& b) { return {b.n, b.indptr, b.data}; }
 InputData input_of(pgmb_input_data const& in) {
     return {cb(in.node), cb(in.line), cb(in.transformer), cb(in.shunt), cb(in.source), cb(in.sym_gen), cb(in.asym_gen),
-            cb(in.sym_load), cb(in.asym_load), cb(in.voltage_regulator), cb(in.asym_line), cb(in.generic_branch)};
+            cb(in.sym_load), cb(in.asym_load), cb(in.voltage_regulator), cb(in.asym_line), cb(in.generic_branch), cb(in.link),
+            cb(in.three_winding_transformer)};
 }
 UpdateData update_of(pgmb_update_data const& u) {
     return {u.n_scenarios, cb(u.line), cb(u.transformer), cb(u.shunt), cb(u.source), cb(u.sym_gen), cb(u.asym_gen),
-            cb(u.sym_load), cb(u.asym_load), cb(u.voltage_regulator), cb(u.asym_line), cb(u.generic_branch)};
+            cb(u.sym_load), cb(u.asym_load), cb(u.voltage_regulator), cb(u.asym_line), cb(u.generic_branch), cb(u.link),
+            cb(u.three_winding_transformer)};
 }
 } // namespace
 
@@ -49,7 +51,8 @@ int pgmb_model_calculate(pgmb_model* model, const pgmb_options* opt, const pgmb_
                               opt->n_devices, opt->flags};
         OutputData const od{output->node, output->line, output->transformer, output->shunt, output->source,
                             output->sym_gen, output->asym_gen, output->sym_load, output->asym_load,
-                            output->voltage_regulator, output->asym_line, output->generic_branch};
+                            output->voltage_regulator, output->asym_line, output->generic_branch, output->link,
+                            output->three_winding_transformer};
         if (update != nullptr) {
             UpdateData const ud = update_of(*update);
             failed = model->model->calculate(mo, &ud, od, n_iter, status);

@@ -231,6 +231,8 @@ UpdateData update_of(Dataset const& ds, RowScratch& scratch) {
         if (b.component == "line") u.line = cb;
         else if (b.component == "asym_line") u.asym_line = cb;
         else if (b.component == "generic_branch") u.generic_branch = cb;
+        else if (b.component == "link") u.link = cb;
+        else if (b.component == "three_winding_transformer") u.three_winding_transformer = cb;
         else if (b.component == "transformer") u.transformer = cb;
         else if (b.component == "shunt") u.shunt = cb;
         else if (b.component == "source") u.source = cb;
@@ -258,6 +260,8 @@ void set_output_slot(OutputData& od, std::string const& c, void* rows) {
     else if (c == "line") od.line = rows;
     else if (c == "asym_line") od.asym_line = rows;
     else if (c == "generic_branch") od.generic_branch = rows;
+    else if (c == "link") od.link = rows;
+    else if (c == "three_winding_transformer") od.three_winding_transformer = rows;
     else if (c == "transformer") od.transformer = rows;
     else if (c == "shunt") od.shunt = rows;
     else if (c == "source") od.source = rows;
@@ -542,6 +546,8 @@ PGM_PowerGridModel* PGM_create_model(PGM_Handle* handle, double system_frequency
             else if (b.component == "line") in.line = cb;
             else if (b.component == "asym_line") in.asym_line = cb;
             else if (b.component == "generic_branch") in.generic_branch = cb;
+            else if (b.component == "link") in.link = cb;
+            else if (b.component == "three_winding_transformer") in.three_winding_transformer = cb;
             else if (b.component == "transformer") in.transformer = cb;
             else if (b.component == "shunt") in.shunt = cb;
             else if (b.component == "source") in.source = cb;

@@ -115,6 +115,23 @@ struct GenericBranchInput {
 };
 static_assert(sizeof(AsymLineInput) == 248 && sizeof(GenericBranchInput) == 72);
 // voltage regulator (auxiliary/input.hpp:492-498, update.hpp:213-219, output.hpp:239-243)
+struct LinkInput { // auxiliary/input.hpp: LinkInput = BranchInput
+    ID id, from_node, to_node;
+    IntS from_status, to_status;
+};
+struct ThreeWindingTransformerInput { // auxiliary/input.hpp: Branch3Input + ThreeWindingTransformerInput
+    ID id, node_1, node_2, node_3;
+    IntS status_1, status_2, status_3;
+    double u1, u2, u3, sn_1, sn_2, sn_3, uk_12, uk_13, uk_23, pk_12, pk_13, pk_23, i0, p0;
+    IntS winding_1, winding_2, winding_3, clock_12, clock_13, tap_side, tap_pos, tap_min, tap_max, tap_nom;
+    double tap_size, uk_12_min, uk_12_max, uk_13_min, uk_13_max, uk_23_min, uk_23_max, pk_12_min, pk_12_max, pk_13_min, pk_13_max,
+        pk_23_min, pk_23_max, r_grounding_1, x_grounding_1, r_grounding_2, x_grounding_2, r_grounding_3, x_grounding_3;
+};
+struct ThreeWindingTransformerUpdate { // auxiliary/update.hpp: Branch3Update + tap_pos
+    ID id;
+    IntS status_1, status_2, status_3, tap_pos;
+};
+static_assert(sizeof(LinkInput) == 16 && sizeof(ThreeWindingTransformerInput) == 304 && sizeof(ThreeWindingTransformerUpdate) == 8);
 struct VoltageRegulatorInput {
     ID id, regulated_object;
     IntS status;
@@ -142,6 +159,13 @@ template <int B> struct BranchOutput {
     double loading;
     double p_from[B], q_from[B], i_from[B], s_from[B], p_to[B], q_to[B], i_to[B], s_to[B];
 };
+template <int B> struct Branch3Output { // auxiliary/output.hpp: Branch3Output<sym>
+    ID id;
+    IntS energized;
+    double loading_1, loading_2, loading_3, loading;
+    double p_1[B], q_1[B], i_1[B], s_1[B], p_2[B], q_2[B], i_2[B], s_2[B], p_3[B], q_3[B], i_3[B], s_3[B];
+};
+static_assert(sizeof(Branch3Output<1>) == 136 && sizeof(Branch3Output<3>) == 328);
 template <int B> struct ApplianceOutput {
     ID id;
     IntS energized;
@@ -567,6 +591,116 @@ inline void transformer_param(TransformerConst const& c, BranchState const& st, 
 }
 
 // ---- source / shunt / load_gen ------------------------------------------------------------------------------------
+// ---- link (component/link.hpp:16-39): fixed series admittance y_link (common/common.hpp:100-101), no shunt, ratio 1 ------------
+constexpr double kGLink = 1e6 / (kBasePower3p / 10e3 / 10e3);
+inline LineConst link_constants(double u_rated_from) {
+    return LineConst{kBasePower3p / u_rated_from / kSqrt3, cplx{kGLink, kGLink}, cplx{0.0, 0.0}, cplx{kGLink, kGLink}, cplx{0.0, 0.0}};
+}
+
+// ---- three-winding transformer (component/three_winding_transformer.hpp:28-435, component/branch3.hpp) -------------------------
+// Three two-winding transformers T1, T2, T3 between the three nodes and an internal node: uk / pk converted delta -> wye relative to
+// side 1 (:226-280); T1 is a YNyn0 transformer carrying i0 / p0, T2 / T3 take the reversed clocks (:301-408).
+struct ThreeWindingConst {
+    ThreeWindingTransformerInput in; // optional values resolved
+    double u_rated[3];
+    double base_i[3];
+    IntS tap_nom, tap_direction, clock_12, clock_13, initial_tap_pos;
+    bool clock_valid;
+};
+struct ThreeWindingState {
+    bool status[3];
+    IntS tap_pos;
+};
+inline IntS tap_limit(ThreeWindingConst const& c, IntS tap) {
+    tap = std::min(tap, std::max(c.in.tap_max, c.in.tap_min));
+    tap = std::max(tap, std::min(c.in.tap_max, c.in.tap_min));
+    return tap;
+}
+inline ThreeWindingConst three_winding_constants(ThreeWindingTransformerInput const& input, double u1_rated, double u2_rated, double u3_rated) {
+    ThreeWindingConst c{input, {u1_rated, u2_rated, u3_rated}, {}, 0, 0, 0, 0, 0, true};
+    auto nz = [](double& v, double fallback) { v = std::isnan(v) ? fallback : v; };
+    auto& in = c.in;
+    c.tap_nom = in.tap_nom == kNaIntS ? IntS{0} : in.tap_nom;
+    c.tap_direction = in.tap_max > in.tap_min ? IntS{1} : IntS{-1};
+    nz(in.uk_12_min, in.uk_12), nz(in.uk_12_max, in.uk_12), nz(in.uk_13_min, in.uk_13), nz(in.uk_13_max, in.uk_13);
+    nz(in.uk_23_min, in.uk_23), nz(in.uk_23_max, in.uk_23), nz(in.pk_12_min, in.pk_12), nz(in.pk_12_max, in.pk_12);
+    nz(in.pk_13_min, in.pk_13), nz(in.pk_13_max, in.pk_13), nz(in.pk_23_min, in.pk_23), nz(in.pk_23_max, in.pk_23);
+    for (int k = 0; k != 3; ++k) c.base_i[k] = kBasePower3p / c.u_rated[k] / kSqrt3;
+    auto valid = [](IntS clock, IntS wa, IntS wb) {
+        auto wye = [](IntS w) { return w == 0 || w == 1; };
+        return ((clock % 2) == 0) == (wye(wa) == wye(wb));
+    };
+    c.clock_valid = valid(in.clock_12, in.winding_1, in.winding_2) && valid(in.clock_13, in.winding_1, in.winding_3);
+    c.clock_12 = static_cast<IntS>((in.clock_12 % 12 + 12) % 12);
+    c.clock_13 = static_cast<IntS>((in.clock_13 % 12 + 12) % 12);
+    c.initial_tap_pos = tap_limit(c, in.tap_pos == kNaIntS ? c.tap_nom : in.tap_pos);
+    return c;
+}
+// parameters of the three math branches (side k -> internal node): out = [3][4][B][B] complex
+template <int B> inline void three_winding_param(ThreeWindingConst const& c, ThreeWindingState const& st, double* out) {
+    constexpr int bb2 = B * B * 2;
+    std::fill_n(out, 3 * 4 * bb2, 0.0);
+    if (!(st.status[0] || st.status[1] || st.status[2])) return; // Branch3::calc_param: not energized
+    auto const& in = c.in;
+    double u1 = in.u1, u2 = in.u2, u3 = in.u3;
+    double const du = c.tap_direction * (st.tap_pos - c.tap_nom) * in.tap_size;
+    if (in.tap_side == 0) {
+        u1 += du;
+    } else if (in.tap_side == 1) {
+        u2 += du;
+    } else {
+        u3 += du;
+    }
+    auto adj = [&](double x, double x_min, double x_max) { return tap_adjust_impedance(st.tap_pos, in.tap_min, in.tap_max, c.tap_nom, x, x_min, x_max); };
+    double const sn_1 = in.sn_1, sn_2 = in.sn_2, sn_3 = in.sn_3;
+    double const uk_12 = adj(in.uk_12, in.uk_12_min, in.uk_12_max) * sn_1 / std::min(sn_1, sn_2);
+    double const uk_13 = adj(in.uk_13, in.uk_13_min, in.uk_13_max) * sn_1 / std::min(sn_1, sn_3);
+    double const uk_23 = adj(in.uk_23, in.uk_23_min, in.uk_23_max) * sn_1 / std::min(sn_2, sn_3);
+    double const uk_t[3] = {0.5 * (uk_12 + uk_13 - uk_23), 0.5 * (uk_12 + uk_23 - uk_13) * (sn_2 / sn_1), 0.5 * (uk_13 + uk_23 - uk_12) * (sn_3 / sn_1)};
+    double const pk_12 = adj(in.pk_12, in.pk_12_min, in.pk_12_max) * (sn_1 / std::min(sn_1, sn_2)) * (sn_1 / std::min(sn_1, sn_2));
+    double const pk_13 = adj(in.pk_13, in.pk_13_min, in.pk_13_max) * (sn_1 / std::min(sn_1, sn_3)) * (sn_1 / std::min(sn_1, sn_3));
+    double const pk_23 = adj(in.pk_23, in.pk_23_min, in.pk_23_max) * (sn_1 / std::min(sn_2, sn_3)) * (sn_1 / std::min(sn_2, sn_3));
+    double const pk_t[3] = {0.5 * (pk_12 + pk_13 - pk_23), 0.5 * (pk_12 + pk_23 - pk_13) * (sn_2 / sn_1) * (sn_2 / sn_1),
+                            0.5 * (pk_13 + pk_23 - pk_12) * (sn_3 / sn_1) * (sn_3 / sn_1)};
+    double const u_side[3] = {u1, u2, u3};
+    double const sn[3] = {sn_1, sn_2, sn_3};
+    IntS const w_from[3] = {1, in.winding_2, in.winding_3};
+    IntS const w_to[3] = {1, in.winding_1, in.winding_1};
+    IntS const clock[3] = {0, static_cast<IntS>(12 - c.clock_12), static_cast<IntS>(12 - c.clock_13)};
+    double const rg[3] = {in.r_grounding_1, in.r_grounding_2, in.r_grounding_3};
+    double const xg[3] = {in.x_grounding_1, in.x_grounding_2, in.x_grounding_3};
+    for (int k = 0; k != 3; ++k) {
+        TransformerInput t{};
+        t.id = 2;
+        t.from_node = 0;
+        t.to_node = 1;
+        t.from_status = st.status[k] ? 1 : 0;
+        t.to_status = 1;
+        t.u1 = u_side[k];
+        t.u2 = u1;
+        t.sn = sn[k];
+        t.uk = uk_t[k];
+        t.pk = pk_t[k];
+        t.i0 = k == 0 ? in.i0 : 0.0;
+        t.p0 = k == 0 ? in.p0 : 0.0;
+        t.i0_zero_sequence = kNaN;
+        t.p0_zero_sequence = kNaN;
+        t.winding_from = w_from[k];
+        t.winding_to = w_to[k];
+        t.clock = clock[k];
+        t.tap_side = 0;
+        t.tap_pos = t.tap_min = t.tap_max = t.tap_nom = 0;
+        t.tap_size = 0.0;
+        t.uk_min = t.uk_max = t.pk_min = t.pk_max = kNaN;
+        t.r_grounding_from = rg[k];
+        t.x_grounding_from = xg[k];
+        t.r_grounding_to = 0.0;
+        t.x_grounding_to = 0.0;
+        TransformerConst const tc = transformer_constants(t, c.u_rated[k], c.u_rated[0]);
+        transformer_param<B>(tc, BranchState{st.status[k], true}, 0, out + k * 4 * bb2);
+    }
+}
+
 inline void source_param(SourceState const& s, double* out4) { // y1, y0 (source.hpp:40-48)
     double const z_abs = kBasePower3p / s.sk;
     double const x1 = z_abs / std::sqrt(s.rx_ratio * s.rx_ratio + 1.0);

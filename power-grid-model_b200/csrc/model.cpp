@@ -56,6 +56,15 @@ Model::Model(double system_frequency, InputData const& in) : freq_{system_freque
         aline_c_.push_back(asym_line_constants(l, freq_, u1));
         branch_st_.push_back({l.from_status != 0, l.to_status != 0});
     }
+    auto const* links = static_cast<LinkInput const*>(in.link.data);
+    for (Idx i = 0; i != in.link.n; ++i) {
+        LinkInput const& l = links[i];
+        add_id(l.id);
+        link_idx_[l.id] = i;
+        link_in_.push_back(l);
+        link_base_i_.push_back({kBasePower3p / u_rated(l.from_node) / kSqrt3, kBasePower3p / u_rated(l.to_node) / kSqrt3});
+        branch_st_.push_back({l.from_status != 0, l.to_status != 0});
+    }
     auto const* gbs = static_cast<GenericBranchInput const*>(in.generic_branch.data);
     for (Idx i = 0; i != in.generic_branch.n; ++i) {
         GenericBranchInput const& g = gbs[i];
@@ -75,6 +84,15 @@ Model::Model(double system_frequency, InputData const& in) : freq_{system_freque
         if (!trafo_c_.back().clock_valid) throw InvalidArgument("Invalid clock for transformer " + std::to_string(t.id) + "\n");
         branch_st_.push_back({t.from_status != 0, t.to_status != 0});
         trafo_st_.push_back({trafo_c_.back().initial_tap_pos});
+    }
+    auto const* t3ws = static_cast<ThreeWindingTransformerInput const*>(in.three_winding_transformer.data);
+    for (Idx i = 0; i != in.three_winding_transformer.n; ++i) {
+        ThreeWindingTransformerInput const& t = t3ws[i];
+        add_id(t.id);
+        t3w_idx_[t.id] = i;
+        t3w_c_.push_back(three_winding_constants(t, u_rated(t.node_1), u_rated(t.node_2), u_rated(t.node_3)));
+        if (!t3w_c_.back().clock_valid) throw InvalidArgument("Invalid clock for transformer " + std::to_string(t.id) + "\n");
+        t3w_st_.push_back({{t.status_1 != 0, t.status_2 != 0, t.status_3 != 0}, t3w_c_.back().initial_tap_pos});
     }
     auto const* shunts = static_cast<ShuntInput const*>(in.shunt.data);
     for (Idx i = 0; i != in.shunt.n; ++i) {
@@ -185,10 +203,15 @@ Model::BranchInfo Model::branch_info(Idx b) const {
         auto const& l = line_in_[b];
         return {l.id, node_seq(l.from_node), node_seq(l.to_node), line_c_[b].base_i, line_c_[b].base_i, -l.i_n};
     }
-    if (b < off_gb()) {
+    if (b < off_link()) {
         Idx const i = b - off_aline();
         auto const& l = aline_in_[i];
         return {l.id, node_seq(l.from_node), node_seq(l.to_node), aline_c_[i].base_i, aline_c_[i].base_i, -l.i_n};
+    }
+    if (b < off_gb()) { // Link::loading = 0 (link.hpp:30)
+        Idx const i = b - off_link();
+        auto const& l = link_in_[i];
+        return {l.id, node_seq(l.from_node), node_seq(l.to_node), link_base_i_[i][0], link_base_i_[i][1], std::numeric_limits<double>::infinity()};
     }
     if (b < off_trafo()) {
         Idx const i = b - off_gb();
@@ -239,6 +262,13 @@ void Model::prepare_topology() {
         g.branch_status.push_back({static_cast<int8_t>(st.from_status), static_cast<int8_t>(st.to_status)});
         g.branch_shift.push_back(trafo_c_[i].clock * kDeg30);
     }
+    for (Idx i = 0; i != n_t3w(); ++i) { // phase_shift = node_k - internal node: {0, -clock_12, -clock_13} * 30 deg
+        auto const& c = t3w_c_[i];
+        g.branch3_node.push_back({node_seq(c.in.node_1), node_seq(c.in.node_2), node_seq(c.in.node_3)});
+        g.branch3_status.push_back({static_cast<int8_t>(t3w_st_[i].status[0]), static_cast<int8_t>(t3w_st_[i].status[1]),
+                                    static_cast<int8_t>(t3w_st_[i].status[2])});
+        g.branch3_shift.push_back({0.0, -c.clock_12 * kDeg30, -c.clock_13 * kDeg30});
+    }
     for (auto const& s : shunt_in_) g.shunt_node.push_back(node_seq(s.node));
     for (size_t i = 0; i != source_in_.size(); ++i) {
         g.source_node.push_back(node_seq(source_in_[i].node));
@@ -273,6 +303,17 @@ void Model::param_arrays(Idx group, std::vector<double>& bp, std::vector<double>
     for (Idx i = 0; i != n_aline(); ++i) {
         Coupling const c = topo_.branch[off_aline() + i];
         if (c.group == group) asym_line_param<B>(aline_c_[i], branch_st_[off_aline() + i], &bp[c.pos * 4 * bb2]);
+    }
+    for (Idx i = 0; i != n_link(); ++i) {
+        Coupling const c = topo_.branch[off_link() + i];
+        if (c.group == group) line_param<B>(link_constants(1.0), branch_st_[off_link() + i], &bp[c.pos * 4 * bb2]);
+    }
+    for (Idx i = 0; i != n_t3w(); ++i) { // main_core/y_bus.hpp:196-204: the three branches of a Branch3
+        Coupling3 const& c = topo_.branch3[i];
+        if (c.group != group) continue;
+        double p3[3 * 4 * bb2];
+        three_winding_param<B>(t3w_c_[i], t3w_st_[i], p3);
+        for (int k = 0; k != 3; ++k) std::copy_n(p3 + k * 4 * bb2, 4 * bb2, &bp[c.pos[k] * 4 * bb2]);
     }
     for (Idx i = 0; i != n_gb(); ++i) {
         Coupling const c = topo_.branch[off_gb() + i];
@@ -436,7 +477,25 @@ void Model::apply_scenario(UpdateData const& u, Idx s, Saved* saved) {
         }
     };
     upd_plain_branch(u.asym_line, n_aline(), aline_idx_, off_aline());
+    upd_plain_branch(u.link, n_link(), link_idx_, off_link());
     upd_plain_branch(u.generic_branch, n_gb(), gb_idx_, off_gb());
+    {
+        // ThreeWindingTransformer::update (three_winding_transformer.hpp:158-163)
+        auto [b, e] = scenario_span<ThreeWindingTransformerUpdate>(u.three_winding_transformer, s);
+        for (auto p = b; p != e; ++p) {
+            Idx const i = find(*p, p - b, e - b, n_t3w(), t3w_idx_, 0);
+            if (saved != nullptr) saved->t3w.emplace_back(i, t3w_st_[i]);
+            bool topo = set_status(t3w_st_[i].status[0], p->status_1);
+            topo = set_status(t3w_st_[i].status[1], p->status_2) || topo;
+            topo = set_status(t3w_st_[i].status[2], p->status_3) || topo;
+            bool tap = false;
+            if (p->tap_pos != kNaIntS && p->tap_pos != t3w_st_[i].tap_pos) {
+                t3w_st_[i].tap_pos = tap_limit(t3w_c_[i], p->tap_pos);
+                tap = true;
+            }
+            mark(topo, tap || topo, saved);
+        }
+    }
     {
         auto [b, e] = scenario_span<TransformerUpdate>(u.transformer, s);
         for (auto p = b; p != e; ++p) {
@@ -522,6 +581,7 @@ void Model::restore(Saved const& s) {
     for (auto it = s.shunt.rbegin(); it != s.shunt.rend(); ++it) shunt_st_[it->first] = it->second;
     for (auto it = s.lg.rbegin(); it != s.lg.rend(); ++it) lg_st_[it->first] = it->second;
     for (auto it = s.reg.rbegin(); it != s.reg.rend(); ++it) reg_st_[it->first] = it->second;
+    for (auto it = s.t3w.rbegin(); it != s.t3w.rend(); ++it) t3w_st_[it->first] = it->second;
     if (s.topo) topo_valid_ = false;
     if (s.param) param_valid_[0] = param_valid_[1] = false;
 }
@@ -682,7 +742,42 @@ void Model::write_output(Idx n_scn, Idx first, OutputData const& out, std::vecto
             }
         };
         branch_range(out.asym_line, off_aline(), n_aline());
+        branch_range(out.link, off_link(), n_link());
         branch_range(out.generic_branch, off_gb(), n_gb());
+        if (out.three_winding_transformer != nullptr) { // Branch3::get_output (branch3.hpp:93-122)
+            auto* dst = static_cast<Branch3Output<B>*>(out.three_winding_transformer) + os * n_t3w();
+            for (Idx i = 0; i != n_t3w(); ++i) {
+                Branch3Output<B> o{};
+                auto const& c = t3w_c_[i];
+                o.id = c.in.id;
+                Coupling3 const& cp = topo_.branch3[i];
+                if (cp.group != -1) {
+                    o.energized = (t3w_st_[i].status[0] || t3w_st_[i].status[1] || t3w_st_[i].status[2]) ? 1 : 0;
+                    double* const fields[3][4] = {{o.p_1, o.q_1, o.i_1, o.s_1}, {o.p_2, o.q_2, o.i_2, o.s_2}, {o.p_3, o.q_3, o.i_3, o.s_3}};
+                    double const sn[3] = {c.in.sn_1, c.in.sn_2, c.in.sn_3};
+                    double loading[3];
+                    for (int k = 0; k != 3; ++k) {
+                        double const* v = &so[2][cp.group][(s * topo_.math[cp.group].n_branch() + cp.pos[k]) * 4 * c2];
+                        double sum_s = 0.0;
+                        for (int p = 0; p != B; ++p) {
+                            double const* sf = v + 2 * p;
+                            double const* i_f = v + 2 * c2 + 2 * p;
+                            fields[k][0][p] = base_power * sf[0];
+                            fields[k][1][p] = base_power * sf[1];
+                            fields[k][2][p] = c.base_i[k] * cabs(i_f[0], i_f[1]);
+                            fields[k][3][p] = base_power * cabs(sf[0], sf[1]);
+                            sum_s = p == 0 ? fields[k][3][p] : sum_s + fields[k][3][p];
+                        }
+                        loading[k] = sum_s / sn[k];
+                    }
+                    o.loading_1 = loading[0];
+                    o.loading_2 = loading[1];
+                    o.loading_3 = loading[2];
+                    o.loading = std::max({loading[0], loading[1], loading[2]});
+                }
+                dst[i] = o;
+            }
+        }
         branch_range(out.transformer, off_trafo(), n_trafo());
         if (out.shunt != nullptr) {
             Idx const n = static_cast<Idx>(shunt_in_.size());
@@ -873,10 +968,11 @@ Model::BridgeInfo Model::bridge_analysis() const {
 template <int B> bool Model::plan_outage_batch(UpdateData const& u, OutagePlan& plan) const {
     // load / generator updates may ride along (contingency x load profile): the device pipeline applies them as in any load batch
     if (u.shunt.data != nullptr || u.source.data != nullptr || u.voltage_regulator.data != nullptr || u.asym_line.data != nullptr ||
-        u.generic_branch.data != nullptr) {
+        u.generic_branch.data != nullptr || u.link.data != nullptr || u.three_winding_transformer.data != nullptr) {
         return false;
     }
     if (topo_.math.size() != 1 || u.n_scenarios <= 0) return false;
+    if (n_t3w() != 0) return false; // the bridge analysis below walks two-way branches only
     MathTopology const& m = topo_.math[0];
     if (std::all_of(m.load_gen_type.begin(), m.load_gen_type.end(), [](int8_t t) { return t == 1; })) return false; // linear method
     constexpr size_t bb2 = static_cast<size_t>(B) * B * 2;
@@ -1029,6 +1125,7 @@ int64_t Model::calculate_impl(ModelOptions const& opt, UpdateData const* update,
         // (regulator updates change the parameters every scenario of one engine call shares: scenario by scenario as well)
         bool const structural = update->line.data != nullptr || update->transformer.data != nullptr ||
                                 update->asym_line.data != nullptr || update->generic_branch.data != nullptr ||
+                                update->link.data != nullptr || update->three_winding_transformer.data != nullptr ||
                                 update->shunt.data != nullptr || (has_reg && update->voltage_regulator.data != nullptr);
         bool source_param_change = false;
         if (update->source.data != nullptr) {
@@ -1242,6 +1339,8 @@ Idx Model::component_count(std::string const& c) const {
     if (c == "line") return n_line();
     if (c == "asym_line") return n_aline();
     if (c == "generic_branch") return n_gb();
+    if (c == "link") return n_link();
+    if (c == "three_winding_transformer") return n_t3w();
     if (c == "transformer") return n_trafo();
     if (c == "shunt") return static_cast<Idx>(shunt_in_.size());
     if (c == "source") return static_cast<Idx>(source_in_.size());
@@ -1261,6 +1360,8 @@ void Model::get_indexer(std::string const& c, ID const* ids, Idx size, Idx* inde
     else if (c == "line") map = &line_idx_;
     else if (c == "asym_line") map = &aline_idx_;
     else if (c == "generic_branch") map = &gb_idx_;
+    else if (c == "link") map = &link_idx_;
+    else if (c == "three_winding_transformer") map = &t3w_idx_;
     else if (c == "transformer") map = &trafo_idx_;
     else if (c == "shunt") map = &shunt_idx_;
     else if (c == "source") map = &source_idx_;
@@ -1302,12 +1403,21 @@ std::vector<int64_t> const& Model::get_index(Idx group, std::string const& name)
         }
         return o;
     };
-    if (name == "coup.node") v = coupling(topo_.node);
+    if (name == "coup.node") {
+        v = coupling(topo_.node);
+        v.resize(2 * node_.size()); // user nodes only (the internal nodes of three-way branches follow them)
+    }
     else if (name == "coup.branch") v = coupling(topo_.branch);
     else if (name == "coup.shunt") v = coupling(topo_.shunt);
     else if (name == "coup.load_gen") v = coupling(topo_.load_gen);
     else if (name == "coup.source") v = coupling(topo_.source);
     else if (name == "coup.voltage_regulator") v = coupling(topo_.voltage_regulator);
+    else if (name == "coup.branch3") {
+        for (auto const& c : topo_.branch3) {
+            v.push_back(c.group);
+            v.insert(v.end(), c.pos.begin(), c.pos.end());
+        }
+    }
     else if (name == "branch_is_bridge" || name == "bridge_cut_size") {
         // host logic of the shared-pattern N-1 route (plan_outage_batch): per branch component (lines then transformers)
         // whether it is a bridge of the closed-branch graph, and how many nodes its DFS subtree holds

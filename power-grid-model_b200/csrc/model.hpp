@@ -25,14 +25,17 @@ struct ComponentBuffer {
     void const* data;
 };
 struct InputData {
-    ComponentBuffer node, line, transformer, shunt, source, sym_gen, asym_gen, sym_load, asym_load, voltage_regulator, asym_line, generic_branch;
+    ComponentBuffer node, line, transformer, shunt, source, sym_gen, asym_gen, sym_load, asym_load, voltage_regulator, asym_line, generic_branch,
+        link, three_winding_transformer;
 };
 struct UpdateData {
     int64_t n_scenarios;
-    ComponentBuffer line, transformer, shunt, source, sym_gen, asym_gen, sym_load, asym_load, voltage_regulator, asym_line, generic_branch;
+    ComponentBuffer line, transformer, shunt, source, sym_gen, asym_gen, sym_load, asym_load, voltage_regulator, asym_line, generic_branch,
+        link, three_winding_transformer;
 };
 struct OutputData {
-    void *node, *line, *transformer, *shunt, *source, *sym_gen, *asym_gen, *sym_load, *asym_load, *voltage_regulator, *asym_line, *generic_branch;
+    void *node, *line, *transformer, *shunt, *source, *sym_gen, *asym_gen, *sym_load, *asym_load, *voltage_regulator, *asym_line, *generic_branch,
+        *link, *three_winding_transformer;
 };
 struct ModelOptions {
     int32_t method;
@@ -88,6 +91,10 @@ class Model {
     std::vector<AsymLineConst> aline_c_;
     std::vector<GenericBranchInput> gb_in_;
     std::vector<GenericBranchConst> gb_c_;
+    std::vector<LinkInput> link_in_;
+    std::vector<std::array<double, 2>> link_base_i_; // from, to
+    std::vector<ThreeWindingConst> t3w_c_;
+    std::vector<ThreeWindingState> t3w_st_;
     std::vector<TransformerInput> trafo_in_;
     std::vector<TransformerConst> trafo_c_;
     std::vector<SourceInput> source_in_;
@@ -104,7 +111,7 @@ class Model {
     std::vector<LoadGenStatic> lg_;
     Idx n_sym_gen_{}, n_asym_gen_{}, n_sym_load_{}, n_asym_load_{};
     // mutable state
-    std::vector<BranchState> branch_st_; // branch sequence of the reference: lines, asym_lines, generic_branches, transformers
+    std::vector<BranchState> branch_st_; // branch sequence of the reference: lines, asym_lines, links, generic_branches, transformers
     std::vector<TransformerState> trafo_st_;
     std::vector<SourceState> source_st_;
     std::vector<ShuntState> shunt_st_;
@@ -114,7 +121,8 @@ class Model {
     std::vector<Idx> reg_lg_;
     std::vector<RegulatorState> reg_st_;
     // id lookup
-    std::unordered_map<ID, Idx> node_idx_, line_idx_, trafo_idx_, shunt_idx_, source_idx_, lg_idx_, reg_idx_, aline_idx_, gb_idx_;
+    std::unordered_map<ID, Idx> node_idx_, line_idx_, trafo_idx_, shunt_idx_, source_idx_, lg_idx_, reg_idx_, aline_idx_, gb_idx_, link_idx_,
+        t3w_idx_;
     std::unordered_map<ID, int> all_ids_;
 
     // caches
@@ -162,9 +170,12 @@ class Model {
     Idx n_trafo() const { return static_cast<Idx>(trafo_in_.size()); }
     Idx n_aline() const { return static_cast<Idx>(aline_in_.size()); }
     Idx n_gb() const { return static_cast<Idx>(gb_in_.size()); }
+    Idx n_link() const { return static_cast<Idx>(link_in_.size()); }
+    Idx n_t3w() const { return static_cast<Idx>(t3w_c_.size()); }
     Idx off_aline() const { return n_line(); }
-    Idx off_gb() const { return n_line() + n_aline(); }
-    Idx off_trafo() const { return n_line() + n_aline() + n_gb(); }
+    Idx off_link() const { return n_line() + n_aline(); }
+    Idx off_gb() const { return n_line() + n_aline() + n_link(); }
+    Idx off_trafo() const { return n_line() + n_aline() + n_link() + n_gb(); }
     Idx n_branch_comp() const { return off_trafo() + n_trafo(); }
     // per branch of the sequence: id, end nodes (sequence numbers), base currents, rating (> 0: sn, loading = max_s / sn;
     // < 0: -i_n, loading = max_i / i_n; +inf: loading 0)
@@ -196,6 +207,7 @@ class Model {
         std::vector<std::pair<Idx, ShuntState>> shunt;
         std::vector<std::pair<Idx, LoadGenState>> lg;
         std::vector<std::pair<Idx, RegulatorState>> reg;
+        std::vector<std::pair<Idx, ThreeWindingState>> t3w;
         bool topo{false}, param{false};
     };
     void apply_scenario(UpdateData const& u, Idx s, Saved* saved);

@@ -39,7 +39,7 @@ struct Model::DeviceSide {
     Idx n_app_first[6]{}; // first appliance index of shunt, source, sym_gen, asym_gen, sym_load, asym_load
     // per-batch buffers
     DevBuf<unsigned char> upd[4];
-    DevBuf<unsigned char> out[12];
+    DevBuf<unsigned char> out[13];
     DevBuf<double> src_res;
     // voltage regulators: component tables and the per-scenario flags of the math regulators
     DevBuf<int32_t> reg_id, reg_math;
@@ -102,6 +102,7 @@ struct Model::DeviceSide {
 
 bool Model::device_path_eligible(UpdateData const& u) const {
     if (topo_.math.size() != 1) return false;
+    if (n_t3w() != 0) return false; // three-winding transformer output is converted on the host (write_output)
     ComponentBuffer const* bufs[4] = {&u.sym_gen, &u.asym_gen, &u.sym_load, &u.asym_load};
     for (auto const* b : bufs) {
         if (b->data != nullptr && (b->indptr != nullptr || b->n < 0)) return false; // sparse batches: host path
@@ -115,7 +116,7 @@ struct OutPart {
     size_t row;
     Idx count;
 };
-void slice_batch(UpdateData const& update, OutputData const& out, OutPart const (&outs)[12], Idx s0, Idx ns, UpdateData& u, OutputData& o) {
+void slice_batch(UpdateData const& update, OutputData const& out, OutPart const (&outs)[13], Idx s0, Idx ns, UpdateData& u, OutputData& o) {
     size_t const urow[4] = {sizeof(SymLoadGenUpdate), sizeof(AsymLoadGenUpdate), sizeof(SymLoadGenUpdate), sizeof(AsymLoadGenUpdate)};
     u = update;
     u.n_scenarios = ns;
@@ -130,9 +131,9 @@ void slice_batch(UpdateData const& update, OutputData const& out, OutPart const 
         }
     }
     o = out;
-    void** ohost[12] = {&o.node, &o.line, &o.transformer, &o.shunt, &o.source, &o.sym_gen, &o.asym_gen, &o.sym_load, &o.asym_load,
-                        &o.voltage_regulator, &o.asym_line, &o.generic_branch};
-    for (int k = 0; k != 12; ++k)
+    void** ohost[13] = {&o.node, &o.line, &o.transformer, &o.shunt, &o.source, &o.sym_gen, &o.asym_gen, &o.sym_load, &o.asym_load,
+                        &o.voltage_regulator, &o.asym_line, &o.generic_branch, &o.link};
+    for (int k = 0; k != 13; ++k)
         if (*ohost[k] != nullptr) *ohost[k] = static_cast<unsigned char*>(*ohost[k]) + static_cast<size_t>(s0) * outs[k].count * outs[k].row;
 }
 } // namespace
@@ -165,10 +166,11 @@ int64_t Model::run_batch_device(ModelOptions const& opt, int phases, UpdateData 
     size_t const row_node = sym ? sizeof(NodeOutput<1>) : sizeof(NodeOutput<3>);
     size_t const row_branch = sym ? sizeof(BranchOutput<1>) : sizeof(BranchOutput<3>);
     size_t const row_app = sym ? sizeof(ApplianceOutput<1>) : sizeof(ApplianceOutput<3>);
-    OutPart const outs[12] = {{row_node, static_cast<Idx>(node_.size())}, {row_branch, n_line()}, {row_branch, n_trafo()},
+    OutPart const outs[13] = {{row_node, static_cast<Idx>(node_.size())}, {row_branch, n_line()}, {row_branch, n_trafo()},
                               {row_app, static_cast<Idx>(shunt_in_.size())}, {row_app, static_cast<Idx>(source_in_.size())},
                               {row_app, n_sym_gen_}, {row_app, n_asym_gen_}, {row_app, n_sym_load_}, {row_app, n_asym_load_},
-                              {sizeof(VoltageRegulatorOutput), static_cast<Idx>(reg_in_.size())}, {row_branch, n_aline()}, {row_branch, n_gb()}};
+                              {sizeof(VoltageRegulatorOutput), static_cast<Idx>(reg_in_.size())}, {row_branch, n_aline()}, {row_branch, n_gb()},
+                              {row_branch, n_link()}};
     // replicas for devices 1 .. n_dev - 1 (kept across calls; rebuilt when the permanent state has changed since)
     if (replicas_.list.size() < static_cast<size_t>(n_dev - 1)) replicas_.list.resize(n_dev - 1);
     for (int k = 1; k != n_dev; ++k) {
@@ -250,7 +252,7 @@ int64_t Model::run_batch_device_one(ModelOptions const& opt, int phases, UpdateD
         size_t row;
         Idx count;
     };
-    Part const outs[12] = {{&out.node, row_node, static_cast<Idx>(node_.size())},
+    Part const outs[13] = {{&out.node, row_node, static_cast<Idx>(node_.size())},
                           {&out.line, row_branch, n_line()},
                           {&out.transformer, row_branch, n_trafo()},
                           {&out.shunt, row_app, static_cast<Idx>(shunt_in_.size())},
@@ -261,7 +263,8 @@ int64_t Model::run_batch_device_one(ModelOptions const& opt, int phases, UpdateD
                           {&out.asym_load, row_app, n_asym_load_},
                           {&out.voltage_regulator, sizeof(VoltageRegulatorOutput), static_cast<Idx>(reg_in_.size())},
                           {&out.asym_line, row_branch, n_aline()},
-                          {&out.generic_branch, row_branch, n_gb()}};
+                          {&out.generic_branch, row_branch, n_gb()},
+                          {&out.link, row_branch, n_link()}};
     ComponentBuffer const* ubufs[4] = {&update.sym_gen, &update.asym_gen, &update.sym_load, &update.asym_load};
     size_t const urow[4] = {sizeof(SymLoadGenUpdate), sizeof(AsymLoadGenUpdate), sizeof(SymLoadGenUpdate), sizeof(AsymLoadGenUpdate)};
     size_t per_scn = static_cast<size_t>(e.pattern().nnz_lu) * N * N * 8 + 6 * static_cast<size_t>(m.n_bus) * N * 8 +
@@ -285,8 +288,8 @@ int64_t Model::run_batch_device_one(ModelOptions const& opt, int phases, UpdateD
     Idx const n_scn = update.n_scenarios;
     Idx max_scn = static_cast<Idx>(std::max<size_t>(32, budget / per_scn / 32 * 32));
     if (n_scn <= max_scn) return run_batch_device_part(opt, phases, update, out, n_iter, status, first_scenario);
-    OutPart parts[12];
-    for (int k = 0; k != 12; ++k) parts[k] = {outs[k].row, outs[k].count};
+    OutPart parts[13];
+    for (int k = 0; k != 13; ++k) parts[k] = {outs[k].row, outs[k].count};
     int64_t failed = 0;
     for (Idx s0 = 0; s0 < n_scn; s0 += max_scn) {
         Idx const ns = std::min(max_scn, n_scn - s0);
@@ -573,7 +576,7 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
         size_t row;
         Idx count;
     };
-    Req const reqs[12] = {
+    Req const reqs[13] = {
         {out.node, 0, sym ? sizeof(NodeOutput<1>) : sizeof(NodeOutput<3>), nn},
         {out.line, 1, sym ? sizeof(BranchOutput<1>) : sizeof(BranchOutput<3>), n_line()},
         {out.transformer, 2, sym ? sizeof(BranchOutput<1>) : sizeof(BranchOutput<3>), n_trafo()},
@@ -586,6 +589,7 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
         {out.voltage_regulator, 9, sizeof(VoltageRegulatorOutput), static_cast<Idx>(reg_in_.size())},
         {out.asym_line, 10, sym ? sizeof(BranchOutput<1>) : sizeof(BranchOutput<3>), n_aline()},
         {out.generic_branch, 11, sym ? sizeof(BranchOutput<1>) : sizeof(BranchOutput<3>), n_gb()},
+        {out.link, 12, sym ? sizeof(BranchOutput<1>) : sizeof(BranchOutput<3>), n_link()},
     };
     for (Req const& r : reqs) {
         if (r.host != nullptr && r.count != 0) d.out[r.slot].ensure(static_cast<size_t>(n_scn) * r.count * r.row);
@@ -600,8 +604,8 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
     // flight.  A direct cudaMemcpy into unfaulted pageable memory runs at a few GB/s on one driver thread.
     // Staging is decided per buffer: a page-locked buffer takes its results directly, a pageable one goes through the staging area
     // (a client may mix both: PGM_create_buffer page-locks large buffers only).
-    size_t stage_off[12] = {};
-    bool slot_staged[12] = {};
+    size_t stage_off[13] = {};
+    bool slot_staged[13] = {};
     size_t stage_bytes = 0;
     bool staged = false;
     {
@@ -666,7 +670,8 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
             void* const dst = d.out[r.slot].get() + static_cast<size_t>(s0) * r.count * r.row;
             int const nl = static_cast<int>(n_line()), nt = static_cast<int>(n_trafo());
             int const o_al = static_cast<int>(off_aline()), n_al = static_cast<int>(n_aline()), o_gb = static_cast<int>(off_gb()),
-                      n_g = static_cast<int>(n_gb()), o_tr = static_cast<int>(off_trafo());
+                      n_g = static_cast<int>(n_gb()), o_tr = static_cast<int>(off_trafo()), o_lk = static_cast<int>(off_link()),
+                      n_lk = static_cast<int>(n_link());
             int const app_first = (r.slot >= 3 && r.slot < 9) ? static_cast<int>(d.n_app_first[r.slot - 3]) : 0;
             if (sym) {
                 switch (r.slot) {
@@ -675,6 +680,7 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
                 case 2: launch_pack_branch_sym(tw, ds, view, d.t, o_tr, nt, dst, q); break;
                 case 10: launch_pack_branch_sym(tw, ds, view, d.t, o_al, n_al, dst, q); break;
                 case 11: launch_pack_branch_sym(tw, ds, view, d.t, o_gb, n_g, dst, q); break;
+                case 12: launch_pack_branch_sym(tw, ds, view, d.t, o_lk, n_lk, dst, q); break;
                 case 9:
                     launch_pack_regulator(ns, static_cast<int>(r.count), static_cast<int>(m.n_voltage_regulator()), d.reg_id.get(),
                                           d.reg_math.get(), d.reg_status.get(), reg_flags, dst, q);
@@ -688,6 +694,7 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
                 case 2: launch_pack_branch_asym(tw, ds, view, d.t, o_tr, nt, dst, q); break;
                 case 10: launch_pack_branch_asym(tw, ds, view, d.t, o_al, n_al, dst, q); break;
                 case 11: launch_pack_branch_asym(tw, ds, view, d.t, o_gb, n_g, dst, q); break;
+                case 12: launch_pack_branch_asym(tw, ds, view, d.t, o_lk, n_lk, dst, q); break;
                 case 9:
                     launch_pack_regulator(ns, static_cast<int>(r.count), static_cast<int>(m.n_voltage_regulator()), d.reg_id.get(),
                                           d.reg_math.get(), d.reg_status.get(), reg_flags, dst, q);

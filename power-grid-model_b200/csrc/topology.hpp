@@ -28,6 +28,11 @@ struct GridGraph {                      // component-level connectivity, compone
     std::vector<Idx> load_gen_node;
     std::vector<int8_t> load_gen_type;
     std::vector<Idx> regulated_load_gen;           // per voltage regulator: sequence number of its load_gen
+    // three-way branches (Branch3: three-winding transformers): side k <-> an internal node n_node + b
+    // (topology.hpp:137-156 of the reference: the internal nodes are appended to the node list)
+    std::vector<std::array<Idx, 3>> branch3_node;
+    std::vector<std::array<int8_t, 3>> branch3_status;
+    std::vector<std::array<double, 3>> branch3_shift; // theta_node_k - theta_internal
 };
 
 struct Coupling {
@@ -35,9 +40,14 @@ struct Coupling {
     Idx pos{-1};
 };
 
+struct Coupling3 {
+    Idx group{-1};
+    std::array<Idx, 3> pos{-1, -1, -1};
+};
 struct TopologyResult {
     std::vector<MathTopology> math;
-    std::vector<Coupling> node, branch, shunt, load_gen, source, voltage_regulator;
+    std::vector<Coupling> node, branch, shunt, load_gen, source, voltage_regulator; // node: user nodes, then the internal nodes
+    std::vector<Coupling3> branch3;
 };
 
 namespace detail {
@@ -145,9 +155,10 @@ inline std::pair<std::vector<Idx>, std::vector<std::array<Idx, 2>>> min_degree(s
 } // namespace detail
 
 inline TopologyResult build_topology(GridGraph const& g) {
-    Idx const n = g.n_node;
+    Idx const n = g.n_node + static_cast<Idx>(g.branch3_node.size()); // user nodes + internal nodes of the three-way branches
     TopologyResult res;
     res.node.assign(n, {});
+    res.branch3.assign(g.branch3_node.size(), {});
     res.branch.assign(g.branch_node.size(), {});
     res.shunt.assign(g.shunt_node.size(), {});
     res.load_gen.assign(g.load_gen_node.size(), {});
@@ -163,6 +174,12 @@ inline TopologyResult build_topology(GridGraph const& g) {
         ++ptr[g.branch_node[b][0] + 1];
         ++ptr[g.branch_node[b][1] + 1];
     }
+    for (size_t b = 0; b != g.branch3_node.size(); ++b)
+        for (int m = 0; m != 3; ++m)
+            if (g.branch3_status[b][m] != 0) {
+                ++ptr[g.branch3_node[b][m] + 1];
+                ++ptr[g.n_node + static_cast<Idx>(b) + 1];
+            }
     for (Idx i = 0; i != n; ++i) ptr[i + 1] += ptr[i];
     std::vector<Idx> target(ptr.back());
     std::vector<double> shift(ptr.back());
@@ -175,6 +192,17 @@ inline TopologyResult build_topology(GridGraph const& g) {
             shift[cur[i]++] = -g.branch_shift[b];
             target[cur[j]] = i;
             shift[cur[j]++] = g.branch_shift[b];
+        }
+        for (size_t b = 0; b != g.branch3_node.size(); ++b) { // after all two-way branches, like the reference's edge list
+            Idx const j = g.n_node + static_cast<Idx>(b);
+            for (int m = 0; m != 3; ++m) {
+                if (g.branch3_status[b][m] == 0) continue;
+                Idx const i = g.branch3_node[b][m];
+                target[cur[i]] = j;
+                shift[cur[i]++] = -g.branch3_shift[b][m];
+                target[cur[j]] = i;
+                shift[cur[j]++] = g.branch3_shift[b][m];
+            }
         }
     }
 
@@ -287,6 +315,23 @@ inline TopologyResult build_topology(GridGraph const& g) {
         res.branch[b] = {group, m.n_branch()};
         m.branch_bus_idx.push_back(si != 0 ? ci.pos : -1);
         m.branch_bus_idx.push_back(sj != 0 ? cj.pos : -1);
+    }
+    // three-way branches: three math branches side k -> internal node (couple_branch of the reference, second loop)
+    for (size_t b = 0; b != g.branch3_node.size(); ++b) {
+        Coupling const cj = res.node[g.n_node + static_cast<Idx>(b)];
+        Idx group = -1;
+        for (int m = 0; m != 3; ++m) {
+            Coupling const ci = res.node[g.branch3_node[b][m]];
+            if (g.branch3_status[b][m] != 0 && ci.group != -1) group = ci.group;
+        }
+        if (group == -1) continue;
+        auto& mt = res.math[group];
+        res.branch3[b].group = group;
+        for (int m = 0; m != 3; ++m) {
+            res.branch3[b].pos[m] = mt.n_branch();
+            mt.branch_bus_idx.push_back(g.branch3_status[b][m] != 0 ? res.node[g.branch3_node[b][m]].pos : -1);
+            mt.branch_bus_idx.push_back(cj.pos);
+        }
     }
     // appliances grouped per bus, stable in component order
     auto group_by_bus = [&](std::vector<Idx> const& comp_node, std::vector<Coupling>& coupling,

@@ -49,6 +49,15 @@ INPUT["asym_line"] = _dt(_branch_head + [(n, "f8") for n in (
     "x_aa", "x_ba", "x_bb", "x_ca", "x_cb", "x_cc", "x_na", "x_nb", "x_nc", "x_nn",
     "c_aa", "c_ba", "c_bb", "c_ca", "c_cb", "c_cc", "c0", "c1", "i_n")])
 INPUT["generic_branch"] = _dt(_branch_head + [(n, "f8") for n in ("r1", "x1", "g1", "b1", "k", "theta", "sn")])
+INPUT["link"] = _dt(_branch_head)
+INPUT["three_winding_transformer"] = _dt(
+    [("id", "i4"), ("node_1", "i4"), ("node_2", "i4"), ("node_3", "i4"), ("status_1", "i1"), ("status_2", "i1"), ("status_3", "i1")]
+    + [(n, "f8") for n in ("u1", "u2", "u3", "sn_1", "sn_2", "sn_3", "uk_12", "uk_13", "uk_23", "pk_12", "pk_13", "pk_23", "i0", "p0")]
+    + [(n, "i1") for n in ("winding_1", "winding_2", "winding_3", "clock_12", "clock_13", "tap_side", "tap_pos", "tap_min", "tap_max",
+                            "tap_nom")]
+    + [(n, "f8") for n in ("tap_size", "uk_12_min", "uk_12_max", "uk_13_min", "uk_13_max", "uk_23_min", "uk_23_max", "pk_12_min",
+                            "pk_12_max", "pk_13_min", "pk_13_max", "pk_23_min", "pk_23_max", "r_grounding_1", "x_grounding_1",
+                            "r_grounding_2", "x_grounding_2", "r_grounding_3", "x_grounding_3")])
 
 UPDATE = {
     "line": _dt([("id", "i4"), ("from_status", "i1"), ("to_status", "i1")]),
@@ -63,6 +72,8 @@ UPDATE["sym_gen"] = UPDATE["sym_load"]
 UPDATE["asym_gen"] = UPDATE["asym_load"]
 UPDATE["asym_line"] = UPDATE["line"]
 UPDATE["generic_branch"] = UPDATE["line"]
+UPDATE["link"] = UPDATE["line"]
+UPDATE["three_winding_transformer"] = _dt([("id", "i4"), ("status_1", "i1"), ("status_2", "i1"), ("status_3", "i1"), ("tap_pos", "i1")])
 
 
 def _real(sym):
@@ -77,8 +88,11 @@ def output_dtypes(sym: bool):
         + [(n, *r) for n in ("p_from", "q_from", "i_from", "s_from", "p_to", "q_to", "i_to", "s_to")]
     )
     appliance = _dt([("id", "i4"), ("energized", "i1")] + [(n, *r) for n in ("p", "q", "i", "s", "pf")])
+    branch3 = _dt([("id", "i4"), ("energized", "i1")] + [(n, "f8") for n in ("loading_1", "loading_2", "loading_3", "loading")]
+                  + [(f"{n}_{k}", *r) for k in (1, 2, 3) for n in ("p", "q", "i", "s")])
     return {
-        "node": node, "line": branch, "transformer": branch, "asym_line": branch, "generic_branch": branch,
+        "node": node, "line": branch, "transformer": branch, "asym_line": branch, "generic_branch": branch, "link": branch,
+        "three_winding_transformer": branch3,
         "shunt": appliance, "source": appliance,
         "sym_gen": appliance, "asym_gen": appliance, "sym_load": appliance, "asym_load": appliance,
         "voltage_regulator": _dt([("id", "i4"), ("energized", "i1"), ("limit_violated", "i1")]),
@@ -90,9 +104,9 @@ ASYM_OUTPUT = output_dtypes(False)
 
 # component storage order of the reference (all_components.hpp:36-39), PF subset
 COMPONENT_ORDER = ("node", "line", "transformer", "shunt", "source", "sym_gen", "asym_gen", "sym_load", "asym_load",
-                   "voltage_regulator", "asym_line", "generic_branch")
+                   "voltage_regulator", "asym_line", "generic_branch", "link", "three_winding_transformer")
 UPDATABLE = ("line", "transformer", "shunt", "source", "sym_gen", "asym_gen", "sym_load", "asym_load", "voltage_regulator",
-             "asym_line", "generic_branch")
+             "asym_line", "generic_branch", "link", "three_winding_transformer")
 
 
 def initialize_array(kind: str, component: str, shape, sym: bool = True):
@@ -111,6 +125,9 @@ def initialize_array(kind: str, component: str, shape, sym: bool = True):
 
 
 assert INPUT["asym_line"].itemsize == 248 and INPUT["generic_branch"].itemsize == 72
+assert INPUT["link"].itemsize == 16 and INPUT["three_winding_transformer"].itemsize == 304
+assert UPDATE["three_winding_transformer"].itemsize == 8
+assert SYM_OUTPUT["three_winding_transformer"].itemsize == 136 and ASYM_OUTPUT["three_winding_transformer"].itemsize == 328
 assert INPUT["voltage_regulator"].itemsize == 40 and UPDATE["voltage_regulator"].itemsize == 32
 assert SYM_OUTPUT["voltage_regulator"].itemsize == 8
 assert INPUT["line"].itemsize == 88 and INPUT["transformer"].itemsize == 168 and INPUT["source"].itemsize == 56

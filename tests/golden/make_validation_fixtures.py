@@ -13,7 +13,7 @@ import sys
 
 REF = "/root/reference/tests/data/power_flow"
 SUPPORTED = {"node", "line", "transformer", "source", "shunt", "sym_load", "sym_gen", "asym_load", "asym_gen",
-             "voltage_regulator", "asym_line", "generic_branch"}
+             "voltage_regulator", "asym_line", "generic_branch", "link", "three_winding_transformer"}
 IGNORED_INPUT = {"fault", "sym_voltage_sensor", "sym_power_sensor", "asym_voltage_sensor", "asym_power_sensor"}  # not used by PF
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "power_flow_cases.json")
 
