@@ -12,12 +12,13 @@
  *     the innermost dimension is the batch one GPU call solves;
  *   - the meta-data tables (PGM_meta_*) of every dataset and component of the reference, PGM_create_buffer / PGM_buffer_* and
  *     the dataset info calls, so a client sizes and fills its buffers the way the reference's wrapper does;
- *   - components: node, line, asym_line, generic_branch, transformer, shunt, source, sym_gen, asym_gen, sym_load, asym_load,
- *     voltage_regulator; sensors and faults may be present in the input dataset and are ignored by power flow like in the
+ *   - components: node, line, asym_line, link, generic_branch, transformer, three_winding_transformer, shunt, source, sym_gen,
+ *     asym_gen, sym_load, asym_load, voltage_regulator; sensors and faults may be present in the input dataset and are ignored by power flow like in the
  *     reference; any other component is PGM_regular_error at PGM_create_model;
  *   - tap_changing_strategy: any valid value (the model cannot hold a transformer_tap_regulator, so it is the plain power flow).
- * Everything else of the reference's C API (working serialization / writable datasets, the PGM_def_* constants) is outside the hot path and not
- * provided.  There is no CPU fallback: PGM_calculate on a host without a CUDA device reports PGM_regular_error.
+ *   - JSON and msgpack (de)serialization of datasets and the writable datasets of the deserializer (serialization.h, dataset.h).
+ * Not provided: the PGM_def_* pointer constants of dataset_definitions.h (the meta data is reachable by name through PGM_meta_*).
+ * There is no CPU fallback: PGM_calculate on a host without a CUDA device reports PGM_regular_error.
  */
 #ifndef PGM_B200_CAPI_H
 #define PGM_B200_CAPI_H
@@ -163,10 +164,10 @@ PGM_API void PGM_calculate(PGM_Handle* handle, PGM_PowerGridModel* model, PGM_Op
                            PGM_MutableDataset const* output_dataset, PGM_ConstDataset const* batch_dataset);
 PGM_API void PGM_destroy_model(PGM_PowerGridModel* model);
 
-/* serialization.h:29-114 and the writable-dataset calls of dataset.h:241-269 -- NOT provided: JSON / msgpack (de)serialization is
- * off the calculation path.  The symbols exist so that a client which resolves the whole C API when it loads the library (the
- * reference's Python wrapper does, _core/power_grid_core.py:146-194) can load this one; every call answers
- * PGM_serialization_error ("... not provided by libpgm_b200 ...") and returns NULL / nothing. */
+/* serialization.h:29-114 and the writable-dataset calls of dataset.h:241-269: JSON (serialization_format 0) and msgpack (1) in the
+ * reference's dataset format (auxiliary/serialization/{deserializer,serializer}.hpp; csrc/capi_pgm_serialization.cpp).  Failures
+ * are reported as PGM_serialization_error.  The deserializer owns its writable dataset; the caller supplies the buffers
+ * (PGM_dataset_writable_set_buffer / _set_attribute_buffer) before PGM_deserializer_parse_to_buffer fills them. */
 PGM_API PGM_Deserializer* PGM_create_deserializer_from_binary_buffer(PGM_Handle* handle, char const* data, PGM_Idx size,
                                                                      PGM_Idx serialization_format);
 PGM_API PGM_Deserializer* PGM_create_deserializer_from_null_terminated_string(PGM_Handle* handle, char const* data_string,

@@ -231,52 +231,4 @@ void PGM_buffer_get_value(PGM_Handle* handle, PGM_MetaAttribute const* attribute
     });
 }
 
-// ---- serialization: not on the path, not provided (see the header) ---------------------------------------------------
-namespace {
-void not_provided(PGM_Handle* handle) {
-    clear(handle);
-    if (handle != nullptr) {
-        handle->err_code = PGM_serialization_error;
-        handle->err_msg = "JSON / msgpack (de)serialization is not provided by libpgm_b200 (power-flow calculation path only); use the "
-                          "reference library for it\n";
-    }
-}
-} // namespace
-PGM_Deserializer* PGM_create_deserializer_from_binary_buffer(PGM_Handle* handle, char const*, PGM_Idx, PGM_Idx) {
-    not_provided(handle);
-    return nullptr;
-}
-PGM_Deserializer* PGM_create_deserializer_from_null_terminated_string(PGM_Handle* handle, char const*, PGM_Idx) {
-    not_provided(handle);
-    return nullptr;
-}
-PGM_WritableDataset* PGM_deserializer_get_dataset(PGM_Handle* handle, PGM_Deserializer*) {
-    not_provided(handle);
-    return nullptr;
-}
-void PGM_deserializer_parse_to_buffer(PGM_Handle* handle, PGM_Deserializer*) { not_provided(handle); }
-void PGM_destroy_deserializer(PGM_Deserializer*) {}
-PGM_Serializer* PGM_create_serializer(PGM_Handle* handle, PGM_ConstDataset const*, PGM_Idx) {
-    not_provided(handle);
-    return nullptr;
-}
-void PGM_serializer_get_to_binary_buffer(PGM_Handle* handle, PGM_Serializer*, PGM_Idx, char const**, PGM_Idx*) { not_provided(handle); }
-char const* PGM_serializer_get_to_zero_terminated_string(PGM_Handle* handle, PGM_Serializer*, PGM_Idx, PGM_Idx) {
-    not_provided(handle);
-    return nullptr;
-}
-void PGM_destroy_serializer(PGM_Serializer*) {}
-PGM_ConstDataset* PGM_create_dataset_const_from_writable(PGM_Handle* handle, PGM_WritableDataset const*) {
-    not_provided(handle);
-    return nullptr;
-}
-PGM_DatasetInfo const* PGM_dataset_writable_get_info(PGM_Handle* handle, PGM_WritableDataset const*) {
-    not_provided(handle);
-    return nullptr;
-}
-void PGM_dataset_writable_set_buffer(PGM_Handle* handle, PGM_WritableDataset*, char const*, PGM_Idx*, void*) { not_provided(handle); }
-void PGM_dataset_writable_set_attribute_buffer(PGM_Handle* handle, PGM_WritableDataset*, char const*, char const*, void*) {
-    not_provided(handle);
-}
-
 } // extern "C"

@@ -72,6 +72,15 @@ def core():
             "PGM_create_model": (P, [P, D, P]), "PGM_update_model": (None, [P, P, P]), "PGM_copy_model": (P, [P, P]),
             "PGM_get_indexer": (None, [P, P, S, I, P, P]), "PGM_calculate": (None, [P, P, P, P, P]),
             "PGM_destroy_model": (None, [P]),
+            "PGM_create_deserializer_from_binary_buffer": (P, [P, C.c_char_p, I, I]),
+            "PGM_create_deserializer_from_null_terminated_string": (P, [P, S, I]),
+            "PGM_deserializer_get_dataset": (P, [P, P]), "PGM_deserializer_parse_to_buffer": (None, [P, P]),
+            "PGM_destroy_deserializer": (None, [P]), "PGM_create_serializer": (P, [P, P, I]),
+            "PGM_serializer_get_to_binary_buffer": (None, [P, P, I, C.POINTER(C.c_void_p), C.POINTER(I)]),
+            "PGM_serializer_get_to_zero_terminated_string": (S, [P, P, I, I]), "PGM_destroy_serializer": (None, [P]),
+            "PGM_dataset_writable_get_info": (P, [P, P]), "PGM_dataset_writable_set_buffer": (None, [P, P, S, P, P]),
+            "PGM_dataset_writable_set_attribute_buffer": (None, [P, P, S, S, P]),
+            "PGM_create_dataset_const_from_writable": (P, [P, P]),
         }
         for name, (res, args) in sig.items():
             f = getattr(l, name)
@@ -301,3 +310,78 @@ class PowerGridModel:
             return result
         finally:
             c.PGM_destroy_options(opt)
+
+
+# ---- (de)serialization (serialization.h), the way the reference's wrapper drives it (_core/serialization.py) -----------------
+JSON, MSGPACK = 0, 1
+
+
+def _check_serialization(h):
+    c = core()
+    code = c.PGM_error_code(h.h)
+    if code != PGM_NO_ERROR:
+        msg = c.PGM_error_message(h.h).decode()
+        c.PGM_clear_error(h.h)
+        raise PowerGridError(msg)
+
+
+def deserialize(data, serialization_format=JSON):
+    """bytes / str in the reference's dataset format -> (dataset type, dict component -> structured array, or
+    {"data", "indptr"} for a component whose scenarios hold different numbers of elements)"""
+    c, h = core(), Handle()
+    raw = data.encode() if isinstance(data, str) else bytes(data)
+    des = c.PGM_create_deserializer_from_binary_buffer(h.h, raw, len(raw), serialization_format)
+    _check_serialization(h)
+    try:
+        ds = c.PGM_deserializer_get_dataset(h.h, des)
+        info = c.PGM_dataset_writable_get_info(h.h, ds)
+        name = c.PGM_dataset_info_name(h.h, info).decode()
+        is_batch = bool(c.PGM_dataset_info_is_batch(h.h, info))
+        batch_size = c.PGM_dataset_info_batch_size(h.h, info)
+        table = power_grid_meta_data()[name]  # dtypes of every component of the reference, built from PGM_meta_*
+        out, keep = {}, []
+        for k in range(c.PGM_dataset_info_n_components(h.h, info)):
+            comp = c.PGM_dataset_info_component_name(h.h, info, k).decode()
+            per, total = c.PGM_dataset_info_elements_per_scenario(h.h, info, k), c.PGM_dataset_info_total_elements(h.h, info, k)
+            arr = np.zeros(total, dtype=table[comp])
+            indptr = np.zeros(batch_size + 1, np.int64) if per < 0 else None
+            keep += [arr, indptr]
+            c.PGM_dataset_writable_set_buffer(h.h, ds, comp.encode(), None if indptr is None else indptr.ctypes.data, arr.ctypes.data)
+            h.check()
+            if per < 0:
+                out[comp] = {"data": arr, "indptr": indptr}
+            else:
+                out[comp] = arr.reshape(batch_size, per) if is_batch else arr
+        c.PGM_deserializer_parse_to_buffer(h.h, des)
+        _check_serialization(h)
+        return name, out
+    finally:
+        c.PGM_destroy_deserializer(des)
+
+
+def serialize(dataset_type, data, serialization_format=JSON, use_compact_list=False, indent=2, is_batch=None):
+    """dict component -> array (2-D for a batch) or {"data", "indptr"} -> str (JSON) / bytes (msgpack)"""
+    c, h = core(), Handle()
+    first = next(iter(data.values()))
+    if is_batch is None:
+        is_batch = isinstance(first, dict) or np.asarray(first).ndim == 2
+    batch_size = 1
+    if is_batch:
+        batch_size = (len(first["indptr"]) - 1) if isinstance(first, dict) else np.asarray(first).shape[0]
+    ds = _Dataset(h, dataset_type, data, mutable=False, is_batch=is_batch, batch_size=batch_size)
+    ser = c.PGM_create_serializer(h.h, ds.ptr, serialization_format)
+    _check_serialization(h)
+    try:
+        if serialization_format == JSON:
+            text = c.PGM_serializer_get_to_zero_terminated_string(h.h, ser, int(use_compact_list), indent)
+            _check_serialization(h)
+            return text.decode()
+        ptr, size = C.c_void_p(), I64(0)
+        c.PGM_serializer_get_to_binary_buffer(h.h, ser, int(use_compact_list), C.byref(ptr), C.byref(size))
+        _check_serialization(h)
+        return C.string_at(ptr, size.value)
+    finally:
+        c.PGM_destroy_serializer(ser)
+
+
+I64 = C.c_int64

@@ -253,17 +253,13 @@ def test_buffer_create_set_nan_set_get_value():
     c.PGM_destroy_buffer(ptr)
 
 
-def test_serialization_calls_answer_serialization_error():
-    """(de)serialization is off the path: the symbols exist (the reference's wrapper binds them at import), every call reports
-    PGM_serialization_error and returns nothing"""
+def test_serialization_errors_use_their_own_error_code():
+    """(de)serializer failures are PGM_serialization_error (handle.hpp:70-89), not PGM_regular_error"""
     c, h = pgm_core.core(), pgm_core.Handle()
-    lib = C.CDLL(pgm_core.LIB_PATH)
-    lib.PGM_create_deserializer_from_null_terminated_string.restype = C.c_void_p
-    lib.PGM_create_deserializer_from_null_terminated_string.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
-    assert lib.PGM_create_deserializer_from_null_terminated_string(h.h, b"{}", 0) is None
-    assert c.PGM_error_code(h.h) == pgm_core.PGM_SERIALIZATION_ERROR and b"not provided by libpgm_b200" in c.PGM_error_message(h.h)
-    lib.PGM_create_serializer.restype = C.c_void_p
-    lib.PGM_create_serializer.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
-    assert lib.PGM_create_serializer(h.h, None, 0) is None and c.PGM_error_code(h.h) == pgm_core.PGM_SERIALIZATION_ERROR
-    lib.PGM_destroy_serializer.argtypes = [C.c_void_p]
-    lib.PGM_destroy_serializer(None)
+    assert c.PGM_create_deserializer_from_null_terminated_string(h.h, b"{}", 0) is None
+    assert c.PGM_error_code(h.h) == pgm_core.PGM_SERIALIZATION_ERROR and b"Key version not found" in c.PGM_error_message(h.h)
+    assert c.PGM_create_serializer(h.h, None, 0) is None and c.PGM_error_code(h.h) == pgm_core.PGM_SERIALIZATION_ERROR
+    assert c.PGM_create_deserializer_from_null_terminated_string(h.h, b"{}", 1) is None  # msgpack needs the binary entry point
+    assert c.PGM_error_code(h.h) == pgm_core.PGM_SERIALIZATION_ERROR
+    c.PGM_destroy_serializer(None)
+    c.PGM_destroy_deserializer(None)
