@@ -115,14 +115,11 @@ __global__ void source_result_asym_kernel(DevStructure s, DevBatch b, int force_
 
 // NodeOutput<asymmetric_t>: 16 doubles = head, u_pu[3], u[3], u_angle[3], p[3], q[3]
 template <int T>
-__global__ void pack_node_asym_kernel(DevStructure s, DevBatch b, DevModelTables m, int force_const_y,
-                                      double const* __restrict__ src_res, double* __restrict__ out) {
-    int64_t const idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= b.n_scn * m.n_node) return;
+__device__ __forceinline__ void pack_node_asym_row(DevStructure s, DevBatch b, DevModelTables m, int force_const_y,
+                                      double const* __restrict__ src_res, int64_t idx, double* __restrict__ o) {
     int64_t const scn = idx / m.n_node;
     int const node = idx % m.n_node;
     int const bus = __ldg(m.node_bus + node);
-    double* o = out + idx * 16;
     int32_t const id = __ldg(m.node_id + node);
     if (bus < 0 || bus_is_dead(b.ovl, scn, bus, s.n_bus)) {
         o[0] = head_word(id, 0);
@@ -154,16 +151,29 @@ __global__ void pack_node_asym_kernel(DevStructure s, DevBatch b, DevModelTables
     }
 }
 
+// rows are staged in shared memory and leave the block as one contiguous, fully coalesced run of 16-byte stores: the rows of
+// consecutive threads are adjacent in the caller's layout, so a block owns 128 * 16 consecutive doubles of the output
+template <int T>
+__global__ void __launch_bounds__(128) pack_node_asym_kernel(DevStructure s, DevBatch b, DevModelTables m, int force_const_y,
+                                      double const* __restrict__ src_res, double* __restrict__ out) {
+    __shared__ __align__(16) double rows[128 * 16];
+    int64_t const total = b.n_scn * m.n_node;
+    int64_t const row0 = (int64_t)blockIdx.x * 128;
+    int64_t const idx = row0 + threadIdx.x;
+    if (idx < total) pack_node_asym_row<T>(s, b, m, force_const_y, src_res, idx, rows + threadIdx.x * 16);
+    __syncthreads();
+    int const n2 = (int)(min((int64_t)128, total - row0) * 16 / 2);
+    double2* dst = reinterpret_cast<double2*>(out + row0 * 16);
+    double2 const* src = reinterpret_cast<double2 const*>(rows);
+    for (int i = threadIdx.x; i < n2; i += 128) dst[i] = src[i];
+}
+
 // BranchOutput<asymmetric_t>: 26 doubles = head, loading, p_from[3], q_from[3], i_from[3], s_from[3], p_to .. s_to
 template <int T>
-__global__ void pack_branch_asym_kernel(DevStructure s, DevBatch b, DevModelTables m, int first, int count,
-                                        double* __restrict__ out) {
-    int64_t const idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= b.n_scn * count) return;
+__device__ __forceinline__ void pack_branch_asym_row(DevStructure s, DevBatch b, DevModelTables m, int first, int count, int64_t idx, double* __restrict__ o) {
     int64_t const scn = idx / count;
     int const comp = first + (int)(idx % count);
     int const mb = __ldg(m.branch_math + comp);
-    double* o = out + idx * 26;
     int32_t const id = __ldg(m.branch_id + comp);
     bool all_dead = false;
     if (mb >= 0 && b.ovl.dead_off != nullptr) { // a branch whose connected sides all sit on buses that lost their supply
@@ -211,17 +221,31 @@ __global__ void pack_branch_asym_kernel(DevStructure s, DevBatch b, DevModelTabl
     o[1] = rating > 0.0 ? fmax(sum_sf, sum_st) / rating : fmax(max_if, max_it) / (-rating);
 }
 
+// rows are staged in shared memory and leave the block as one contiguous, fully coalesced run of 16-byte stores: the rows of
+// consecutive threads are adjacent in the caller's layout, so a block owns 128 * 26 consecutive doubles of the output
+template <int T>
+__global__ void __launch_bounds__(128) pack_branch_asym_kernel(DevStructure s, DevBatch b, DevModelTables m, int first, int count,
+                                        double* __restrict__ out) {
+    __shared__ __align__(16) double rows[128 * 26];
+    int64_t const total = b.n_scn * count;
+    int64_t const row0 = (int64_t)blockIdx.x * 128;
+    int64_t const idx = row0 + threadIdx.x;
+    if (idx < total) pack_branch_asym_row<T>(s, b, m, first, count, idx, rows + threadIdx.x * 26);
+    __syncthreads();
+    int const n2 = (int)(min((int64_t)128, total - row0) * 26 / 2);
+    double2* dst = reinterpret_cast<double2*>(out + row0 * 26);
+    double2 const* src = reinterpret_cast<double2 const*>(rows);
+    for (int i = threadIdx.x; i < n2; i += 128) dst[i] = src[i];
+}
+
 // ApplianceOutput<asymmetric_t>: 16 doubles = head, p[3], q[3], i[3], s[3], pf[3]
 template <int T>
-__global__ void pack_appliance_asym_kernel(DevStructure s, DevBatch b, DevModelTables m, int force_const_y, int first,
-                                           int count, double const* __restrict__ src_res, double* __restrict__ out) {
-    int64_t const idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= b.n_scn * count) return;
+__device__ __forceinline__ void pack_appliance_asym_row(DevStructure s, DevBatch b, DevModelTables m, int force_const_y, int first,
+                                           int count, double const* __restrict__ src_res, int64_t idx, double* __restrict__ o) {
     int64_t const scn = idx / count;
     int const comp = first + (int)(idx % count);
     int const a = __ldg(m.app_math + comp);
     int const kind = __ldg(m.app_kind + comp);
-    double* o = out + idx * 16;
     int32_t const id = __ldg(m.app_id + comp);
     bool dead = false;
     if (a >= 0 && b.ovl.dead_off != nullptr) {
@@ -267,6 +291,23 @@ __global__ void pack_appliance_asym_kernel(DevStructure s, DevBatch b, DevModelT
         o[10 + ph] = sa;
         o[13 + ph] = sa < 1e-8 ? 0.0 : pw / sa;
     }
+}
+
+// rows are staged in shared memory and leave the block as one contiguous, fully coalesced run of 16-byte stores: the rows of
+// consecutive threads are adjacent in the caller's layout, so a block owns 128 * 16 consecutive doubles of the output
+template <int T>
+__global__ void __launch_bounds__(128) pack_appliance_asym_kernel(DevStructure s, DevBatch b, DevModelTables m, int force_const_y, int first,
+                                           int count, double const* __restrict__ src_res, double* __restrict__ out) {
+    __shared__ __align__(16) double rows[128 * 16];
+    int64_t const total = b.n_scn * count;
+    int64_t const row0 = (int64_t)blockIdx.x * 128;
+    int64_t const idx = row0 + threadIdx.x;
+    if (idx < total) pack_appliance_asym_row<T>(s, b, m, force_const_y, first, count, src_res, idx, rows + threadIdx.x * 16);
+    __syncthreads();
+    int const n2 = (int)(min((int64_t)128, total - row0) * 16 / 2);
+    double2* dst = reinterpret_cast<double2*>(out + row0 * 16);
+    double2 const* src = reinterpret_cast<double2 const*>(rows);
+    for (int i = threadIdx.x; i < n2; i += 128) dst[i] = src[i];
 }
 
 inline unsigned grid_for(int64_t total, int block) { return (unsigned)((total + block - 1) / block); }

@@ -112,14 +112,11 @@ __global__ void source_result_sym_kernel(DevStructure s, DevBatch b, int force_c
 
 // NodeOutput<symmetric_t>: 48 bytes = head, u_pu, u, u_angle, p, q
 template <int T>
-__global__ void pack_node_sym_kernel(DevStructure s, DevBatch b, DevModelTables m, int force_const_y,
-                                     double const* __restrict__ src_res, double* __restrict__ out) {
-    int64_t const idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= b.n_scn * m.n_node) return;
+__device__ __forceinline__ void pack_node_sym_row(DevStructure s, DevBatch b, DevModelTables m, int force_const_y,
+                                     double const* __restrict__ src_res, int64_t idx, double* __restrict__ o) {
     int64_t const scn = idx / m.n_node;
     int const node = idx % m.n_node;
     int const bus = __ldg(m.node_bus + node);
-    double* o = out + idx * 6;
     int32_t const id = __ldg(m.node_id + node);
     if (bus < 0 || bus_is_dead(b.ovl, scn, bus, s.n_bus)) {
         o[0] = head_word(id, 0);
@@ -147,16 +144,29 @@ __global__ void pack_node_sym_kernel(DevStructure s, DevBatch b, DevModelTables 
     o[5] = kBasePower * inj.i;
 }
 
+// rows are staged in shared memory and leave the block as one contiguous, fully coalesced run of 16-byte stores: the rows of
+// consecutive threads are adjacent in the caller's layout, so a block owns 256 * 6 consecutive doubles of the output
+template <int T>
+__global__ void __launch_bounds__(256) pack_node_sym_kernel(DevStructure s, DevBatch b, DevModelTables m, int force_const_y,
+                                     double const* __restrict__ src_res, double* __restrict__ out) {
+    __shared__ __align__(16) double rows[256 * 6];
+    int64_t const total = b.n_scn * m.n_node;
+    int64_t const row0 = (int64_t)blockIdx.x * 256;
+    int64_t const idx = row0 + threadIdx.x;
+    if (idx < total) pack_node_sym_row<T>(s, b, m, force_const_y, src_res, idx, rows + threadIdx.x * 6);
+    __syncthreads();
+    int const n2 = (int)(min((int64_t)256, total - row0) * 6 / 2);
+    double2* dst = reinterpret_cast<double2*>(out + row0 * 6);
+    double2 const* src = reinterpret_cast<double2 const*>(rows);
+    for (int i = threadIdx.x; i < n2; i += 256) dst[i] = src[i];
+}
+
 // BranchOutput<symmetric_t>: 80 bytes = head, loading, p_from, q_from, i_from, s_from, p_to, q_to, i_to, s_to
 template <int T>
-__global__ void pack_branch_sym_kernel(DevStructure s, DevBatch b, DevModelTables m, int first, int count,
-                                       double* __restrict__ out) {
-    int64_t const idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= b.n_scn * count) return;
+__device__ __forceinline__ void pack_branch_sym_row(DevStructure s, DevBatch b, DevModelTables m, int first, int count, int64_t idx, double* __restrict__ o) {
     int64_t const scn = idx / count;
     int const comp = first + (int)(idx % count);
     int const mb = __ldg(m.branch_math + comp);
-    double* o = out + idx * 10;
     int32_t const id = __ldg(m.branch_id + comp);
     bool all_dead = false;
     if (mb >= 0 && b.ovl.dead_off != nullptr) { // a branch whose connected sides all sit on buses that lost their supply
@@ -196,17 +206,31 @@ __global__ void pack_branch_sym_kernel(DevStructure s, DevBatch b, DevModelTable
     o[9] = s_to;
 }
 
+// rows are staged in shared memory and leave the block as one contiguous, fully coalesced run of 16-byte stores: the rows of
+// consecutive threads are adjacent in the caller's layout, so a block owns 256 * 10 consecutive doubles of the output
+template <int T>
+__global__ void __launch_bounds__(256) pack_branch_sym_kernel(DevStructure s, DevBatch b, DevModelTables m, int first, int count,
+                                       double* __restrict__ out) {
+    __shared__ __align__(16) double rows[256 * 10];
+    int64_t const total = b.n_scn * count;
+    int64_t const row0 = (int64_t)blockIdx.x * 256;
+    int64_t const idx = row0 + threadIdx.x;
+    if (idx < total) pack_branch_sym_row<T>(s, b, m, first, count, idx, rows + threadIdx.x * 10);
+    __syncthreads();
+    int const n2 = (int)(min((int64_t)256, total - row0) * 10 / 2);
+    double2* dst = reinterpret_cast<double2*>(out + row0 * 10);
+    double2 const* src = reinterpret_cast<double2 const*>(rows);
+    for (int i = threadIdx.x; i < n2; i += 256) dst[i] = src[i];
+}
+
 // ApplianceOutput<symmetric_t>: 48 bytes = head, p, q, i, s, pf
 template <int T>
-__global__ void pack_appliance_sym_kernel(DevStructure s, DevBatch b, DevModelTables m, int force_const_y, int first,
-                                          int count, double const* __restrict__ src_res, double* __restrict__ out) {
-    int64_t const idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= b.n_scn * count) return;
+__device__ __forceinline__ void pack_appliance_sym_row(DevStructure s, DevBatch b, DevModelTables m, int force_const_y, int first,
+                                          int count, double const* __restrict__ src_res, int64_t idx, double* __restrict__ o) {
     int64_t const scn = idx / count;
     int const comp = first + (int)(idx % count);
     int const a = __ldg(m.app_math + comp);
     int const kind = __ldg(m.app_kind + comp);
-    double* o = out + idx * 6;
     int32_t const id = __ldg(m.app_id + comp);
     bool dead = false;
     if (a >= 0 && b.ovl.dead_off != nullptr) {
@@ -247,6 +271,23 @@ __global__ void pack_appliance_sym_kernel(DevStructure s, DevBatch b, DevModelTa
     o[3] = __ldg(m.app_base_i + comp) * cabs_(iv);
     o[4] = sa;
     o[5] = sa < 1e-8 ? 0.0 : pw / sa;
+}
+
+// rows are staged in shared memory and leave the block as one contiguous, fully coalesced run of 16-byte stores: the rows of
+// consecutive threads are adjacent in the caller's layout, so a block owns 256 * 6 consecutive doubles of the output
+template <int T>
+__global__ void __launch_bounds__(256) pack_appliance_sym_kernel(DevStructure s, DevBatch b, DevModelTables m, int force_const_y, int first,
+                                          int count, double const* __restrict__ src_res, double* __restrict__ out) {
+    __shared__ __align__(16) double rows[256 * 6];
+    int64_t const total = b.n_scn * count;
+    int64_t const row0 = (int64_t)blockIdx.x * 256;
+    int64_t const idx = row0 + threadIdx.x;
+    if (idx < total) pack_appliance_sym_row<T>(s, b, m, force_const_y, first, count, src_res, idx, rows + threadIdx.x * 6);
+    __syncthreads();
+    int const n2 = (int)(min((int64_t)256, total - row0) * 6 / 2);
+    double2* dst = reinterpret_cast<double2*>(out + row0 * 6);
+    double2 const* src = reinterpret_cast<double2 const*>(rows);
+    for (int i = threadIdx.x; i < n2; i += 256) dst[i] = src[i];
 }
 
 inline unsigned grid_for(int64_t total, int block) { return (unsigned)((total + block - 1) / block); }
