@@ -11,8 +11,9 @@
 //       calculate_multiple_source_result :83-139, calculate_source_result :143-160,
 //       calculate_load_gen_result :383-409, calculate_pf_result :411-446
 //   math_solver/math_solver.hpp                method switch :43-64
-// Voltage regulators (PV buses, newton_raphson_pf_solver.hpp:400-453, 549-704) are NOT restated: none of the
-// BASELINE configs has one (limit_check_countdown_ = -1 path).
+// Voltage regulators (PV buses, newton_raphson_pf_solver.hpp:400-453, 549-704: bus types and Q limits, PV rows of the Jacobian,
+// limit check from iteration 2 with the PV -> PQ switch, Q allocation in the result step) are restated below and pinned by the
+// reference's six pv-node validation cases (tests/test_oracle_validation.py).
 #pragma once
 
 #include "sparse_lu.hpp"

@@ -19,6 +19,12 @@ using MetaComponent = PGM_MetaComponent;
 using MetaDataset = PGM_MetaDataset;
 namespace {
 #include "meta_table.inc"
+
+// the PGM_def_* pointer constants of dataset_definitions.h (declared with C linkage and default visibility in the header)
+#include "../../include/pgm_b200_dataset_definitions.h"
+extern "C" {
+#include "meta_defs.inc"
+}
 } // namespace
 
 PGM_MetaAttribute const* PGM_MetaComponent::find(std::string_view attribute) const {

@@ -27,6 +27,22 @@ def test_library_exports_every_pgm_symbol():
     assert b"pgm_b200" in pgm_core.core().PGM_version()
 
 
+def test_library_exports_the_dataset_definition_constants():
+    """dataset_definitions.h: 838 PGM_def_* pointer constants in the reference; every one declared in
+    include/pgm_b200_dataset_definitions.h is exported and points at the meta data PGM_meta_get_*_by_name returns"""
+    header = open(os.path.join(ROOT, "include", "pgm_b200_dataset_definitions.h")).read()
+    names = re.findall(r"\b(PGM_def_\w+);", header)
+    assert len(names) >= 838 and len(set(names)) == len(names)
+    lib = C.CDLL(os.path.join(ROOT, "power-grid-model_b200", "libpgm_b200.so"))
+    for n in names:
+        assert hasattr(lib, n), n
+    c, h = pgm_core.core(), pgm_core.Handle()
+    value = lambda n: C.c_void_p.in_dll(lib, n).value  # noqa: E731
+    assert value("PGM_def_input") == c.PGM_meta_get_dataset_by_name(h.h, b"input")
+    assert value("PGM_def_sym_output_line") == c.PGM_meta_get_component_by_name(h.h, b"sym_output", b"line")
+    assert value("PGM_def_update_asym_load_q_specified") == c.PGM_meta_get_attribute_by_name(h.h, b"update", b"asym_load", b"q_specified")
+
+
 def _api_model_input(load_id=2):
     """the grid of tests/native_api_tests/test_api_model.cpp:27-52"""
     node = initialize_array("input", "node", 2)
