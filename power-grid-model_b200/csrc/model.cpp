@@ -1451,6 +1451,12 @@ std::vector<int64_t> const& Model::get_index(Idx group, std::string const& name)
             else if (name == "diag_lu") v = p.diag_lu;
             else if (name == "map_lu_y_bus") v = p.map_lu_y_bus;
             else if (name == "lu_transpose_entry") v = p.lu_transpose_entry;
+            else if (name == "path_program") { // symbolic.hpp PathProgram words (empty: not a radial grid)
+                EliminationSchedule const sch{p};
+                RowProgram const rows{p, sch, m};
+                PathProgram const pp{p, sch, m, rows};
+                if (pp.valid) v.assign(pp.words.begin(), pp.words.end());
+            }
             else throw InvalidArgument("unknown index array: " + name);
         }
     }
