@@ -14,8 +14,13 @@
 
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #ifndef V3_CHAIN_AHEAD
 #define V3_CHAIN_AHEAD 2
+#endif
+#ifndef V3_RING_DOWN
+#define V3_RING_DOWN 0 // 1: the down chains read their first operands through the ring too (measured slower)
 #endif
 #ifndef V3_THREADS
 #define V3_THREADS 512
@@ -30,6 +35,21 @@ namespace {
 constexpr int kChainAhead = V3_CHAIN_AHEAD; // rows whose operands are pulled into L1 ahead of the chain step that uses them
 
 __device__ __forceinline__ uint32_t smem_u32(void const* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+// Operand ring of the chain walks: the operands a chain step needs first (10 doubles per thread) are copied global -> shared
+// with cp.async one row ahead, into one of two buffers; no register holds them meanwhile and the step reads them with LDS.
+// Layout [buffer][operand][thread]: conflict-free.
+constexpr int kRingOperands = 10;
+struct Ring {
+    double* base; // this thread's element of operand 0, buffer 0
+    int stride;   // doubles between operands (= threads of the block)
+    __device__ __forceinline__ double* at(int buf, int k) const { return base + (size_t)(buf * kRingOperands + k) * stride; }
+};
+__device__ __forceinline__ void cp_async8(double* dst, double const* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst))), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ void stage_program(int32_t* dst, int32_t const* src, uint32_t bytes, uint64_t* mbar) {
     uint32_t const bar = smem_u32(mbar);
@@ -316,17 +336,22 @@ template <int T> __device__ __forceinline__ void prefetch_blk(double const* jac,
 #pragma unroll
     for (int i = 0; i < 4; ++i) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + i * T));
 }
-template <int T> __device__ __forceinline__ void prefetch_row(TileP<T> const& t, int4 const c0, int4 const c1) {
-    prefetch_blk<T>(t.jac, c0.y);
+// RING: the diagonal, the block towards the carried child and the mismatch come through the operand ring instead
+template <int T, bool RING> __device__ __forceinline__ void prefetch_row(TileP<T> const& t, int4 const c0, int4 const c1) {
+    if constexpr (!RING) prefetch_blk<T>(t.jac, c0.y);
     if (c0.z >= 0) prefetch_blk<T>(t.jac, c0.z);
-    if (c0.w >= 0) prefetch_blk<T>(t.jac, c0.w);
+    if constexpr (!RING) {
+        if (c0.w >= 0) prefetch_blk<T>(t.jac, c0.w);
+    }
     if (c1.x >= 0) {
         prefetch_blk<T>(t.jac, c1.x);
         asm volatile("prefetch.global.L1 [%0];" ::"l"(t.side + (size_t)(c0.x * 2) * T));
         asm volatile("prefetch.global.L1 [%0];" ::"l"(t.side + (size_t)(c0.x * 2 + 1) * T));
     }
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(t.xvec + (size_t)(c0.x * 2) * T));
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(t.xvec + (size_t)(c0.x * 2 + 1) * T));
+    if constexpr (!RING) {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(t.xvec + (size_t)(c0.x * 2) * T));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(t.xvec + (size_t)(c0.x * 2 + 1) * T));
+    }
 }
 
 __device__ __forceinline__ void eliminate(Blk& d, double& acc0, double& acc1, Blk const& a, Blk const& piv, Blk const& uc,
@@ -340,24 +365,53 @@ __device__ __forceinline__ void eliminate(Blk& d, double& acc0, double& acc1, Bl
     acc1 -= l.a10 * y0 + l.a11 * y1;
 }
 
-template <int T>
+template <int T, bool RING>
 __device__ __forceinline__ bool up_path(TileP<T> const& t, int32_t const* __restrict__ prog, int4 const* __restrict__ chain,
-                                        int first_rec, int n_rows) {
+                                        int first_rec, int n_rows, Ring const& ring) {
     bool singular = false;
     Blk c_piv{1.0, 0.0, 0.0, 1.0}, c_uc{0.0, 0.0, 0.0, 0.0};
     double c_y0 = 0.0, c_y1 = 0.0;
     int c_q = 0;
     int4 n0 = chain[2 * first_rec], n1 = chain[2 * first_rec + 1];
-    Blk a_next = n0.w >= 0 ? t.load_blk(n0.w) : Blk{0.0, 0.0, 0.0, 0.0};
-    Blk d_next = t.load_blk(n0.y);
-    for (int k = 1; k < kChainAhead && k < n_rows; ++k) prefetch_row<T>(t, chain[2 * (first_rec + k)], chain[2 * (first_rec + k) + 1]);
+    // RING: block towards the carried child, prebuilt diagonal and mismatch of the next row travel through the ring
+    auto stage = [&](int buf, int4 const c) {
+        if (c.w >= 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cp_async8(ring.at(buf, i), t.jac + (size_t)c.w * 4 * T + i * T);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cp_async8(ring.at(buf, 4 + i), t.jac + (size_t)c.y * 4 * T + i * T);
+        cp_async8(ring.at(buf, 8), t.xvec + (size_t)(c.x * 2) * T);
+        cp_async8(ring.at(buf, 9), t.xvec + (size_t)(c.x * 2 + 1) * T);
+        cp_async_commit();
+    };
+    Blk a_next{0.0, 0.0, 0.0, 0.0}, d_next{0.0, 0.0, 0.0, 0.0};
+    int buf = 0;
+    if constexpr (RING) {
+        stage(0, n0);
+    } else {
+        if (n0.w >= 0) a_next = t.load_blk(n0.w);
+        d_next = t.load_blk(n0.y);
+    }
+    for (int k = 1; k < kChainAhead && k < n_rows; ++k) prefetch_row<T, RING>(t, chain[2 * (first_rec + k)], chain[2 * (first_rec + k) + 1]);
     for (int i = 0; i < n_rows; ++i) {
         int4 const c0 = n0, c1 = n1;
-        Blk const a_carry = a_next;
-        Blk d = d_next;
         int const row = c0.x, k_d = c0.y, k_u = c0.z, k_s = c1.x, pattern = c1.y;
+        Blk a_carry, d;
+        double acc0, acc1;
+        if constexpr (RING) {
+            cp_async_wait_all();
+            a_carry = c0.w >= 0 ? Blk{*ring.at(buf, 0), *ring.at(buf, 1), *ring.at(buf, 2), *ring.at(buf, 3)} : Blk{0.0, 0.0, 0.0, 0.0};
+            d = Blk{*ring.at(buf, 4), *ring.at(buf, 5), *ring.at(buf, 6), *ring.at(buf, 7)};
+            acc0 = *ring.at(buf, 8);
+            acc1 = *ring.at(buf, 9);
+        } else {
+            a_carry = a_next;
+            d = d_next;
+            acc0 = t.xvec[(size_t)(row * 2) * T];
+            acc1 = t.xvec[(size_t)(row * 2 + 1) * T];
+        }
         // operands of this row that are needed behind the first divide chain
-        double acc0 = t.xvec[(size_t)(row * 2) * T], acc1 = t.xvec[(size_t)(row * 2 + 1) * T];
         Blk ub = k_u >= 0 ? t.load_blk(k_u) : Blk{0.0, 0.0, 0.0, 0.0};
         Blk sterm{0.0, 0.0, 0.0, 0.0};
         double s0 = 0.0, s1 = 0.0;
@@ -369,10 +423,15 @@ __device__ __forceinline__ bool up_path(TileP<T> const& t, int32_t const* __rest
         if (i + 1 < n_rows) {
             n0 = chain[2 * (first_rec + i + 1)];
             n1 = chain[2 * (first_rec + i + 1) + 1];
-            a_next = n0.w >= 0 ? t.load_blk(n0.w) : Blk{0.0, 0.0, 0.0, 0.0};
-            d_next = t.load_blk(n0.y);
-            if (i + kChainAhead < n_rows) prefetch_row<T>(t, chain[2 * (first_rec + i + kChainAhead)], chain[2 * (first_rec + i + kChainAhead) + 1]);
+            if constexpr (RING) {
+                stage(buf ^ 1, n0);
+            } else {
+                a_next = n0.w >= 0 ? t.load_blk(n0.w) : Blk{0.0, 0.0, 0.0, 0.0};
+                d_next = t.load_blk(n0.y);
+            }
+            if (i + kChainAhead < n_rows) prefetch_row<T, RING>(t, chain[2 * (first_rec + i + kChainAhead)], chain[2 * (first_rec + i + kChainAhead) + 1]);
         }
+        buf ^= 1;
         if (pattern >= 2) { // carry child, then (pattern 3) the precomputed leaf term
             eliminate(d, acc0, acc1, a_carry, c_piv, c_uc, c_y0, c_y1, c_q);
             if (pattern == 3) {
@@ -448,11 +507,13 @@ template <int T, Mode mode>
 __device__ __forceinline__ DownOperands fetch_down(TileP<T> const& t, int32_t const* __restrict__ rec) {
     return fetch_down_k<T, mode>(t, rec[0], rec[1], rec[3]);
 }
-template <int T, Mode mode> __device__ __forceinline__ void prefetch_down(TileP<T> const& t, int4 const c0) {
-    prefetch_blk<T>(t.jac, c0.y);
-    if (c0.z >= 0) prefetch_blk<T>(t.jac, c0.z);
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(t.xvec + (size_t)(c0.x * 2) * T));
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(t.xvec + (size_t)(c0.x * 2 + 1) * T));
+template <int T, Mode mode, bool RING = false> __device__ __forceinline__ void prefetch_down(TileP<T> const& t, int4 const c0) {
+    if constexpr (!RING) {
+        prefetch_blk<T>(t.jac, c0.y);
+        if (c0.z >= 0) prefetch_blk<T>(t.jac, c0.z);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(t.xvec + (size_t)(c0.x * 2) * T));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(t.xvec + (size_t)(c0.x * 2 + 1) * T));
+    }
     asm volatile("prefetch.global.L1 [%0];" ::"l"(t.perm + (size_t)c0.x * T));
     if constexpr (mode == Mode::newton) {
         asm volatile("prefetch.global.L1 [%0];" ::"l"(t.pol + (size_t)(c0.x * 2) * T));
@@ -485,36 +546,88 @@ __device__ __forceinline__ double down_step(TileP<T> const& t, int row, bool has
     return polar_update<T, mode>(t.pol + (size_t)(row * 2) * T, t.u + (size_t)(row * 2) * T, y0, y1, o.th, o.v, o.our, o.oui);
 }
 
-template <int T, Mode mode>
-__device__ __forceinline__ double down_path(TileP<T> const& t, int4 const* __restrict__ chain, int first_rec, int n_rows) {
+template <int T, Mode mode, bool RING>
+__device__ __forceinline__ double down_path(TileP<T> const& t, int4 const* __restrict__ chain, int first_rec, int n_rows,
+                                            Ring const& ring) {
     double dev = 0.0;
     int4 c0 = chain[2 * (first_rec + n_rows - 1)];
     int const j_top = chain[2 * (first_rec + n_rows - 1) + 1].w;
-    DownOperands next = fetch_down_k<T, mode>(t, c0.x, c0.y, c0.z);
+    // RING: U block, factorised diagonal and right-hand side of the next row (what the step needs first) travel through the
+    // ring; permutation and old voltage (needed behind the divides) are plain loads when the step starts
+    auto stage = [&](int buf, int4 const c) {
+        if (c.z >= 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cp_async8(ring.at(buf, i), t.jac + (size_t)c.z * 4 * T + i * T);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cp_async8(ring.at(buf, 4 + i), t.jac + (size_t)c.y * 4 * T + i * T);
+        cp_async8(ring.at(buf, 8), t.xvec + (size_t)(c.x * 2) * T);
+        cp_async8(ring.at(buf, 9), t.xvec + (size_t)(c.x * 2 + 1) * T);
+        cp_async_commit();
+    };
+    DownOperands next;
+    int buf = 0;
+    auto fetch_late = [&](int row) { // needed behind the divides: one row ahead into registers
+        next.pm = t.perm[(size_t)row * T];
+        next.th = next.v = next.our = next.oui = 0.0;
+        if constexpr (mode == Mode::newton) {
+            next.th = t.pol[(size_t)(row * 2) * T];
+            next.v = t.pol[(size_t)(row * 2 + 1) * T];
+            next.our = t.u[(size_t)(row * 2) * T];
+            next.oui = t.u[(size_t)(row * 2 + 1) * T];
+        }
+    };
+    if constexpr (RING) {
+        stage(0, c0);
+        fetch_late(c0.x);
+    } else {
+        next = fetch_down_k<T, mode>(t, c0.x, c0.y, c0.z);
+    }
     double x0 = 0.0, x1 = 0.0;
     bool has_parent = c0.z >= 0;
     if (has_parent) {
         x0 = t.xvec[(size_t)(j_top * 2) * T];
         x1 = t.xvec[(size_t)(j_top * 2 + 1) * T];
     }
-    for (int k = 2; k <= kChainAhead && k <= n_rows; ++k) prefetch_down<T, mode>(t, chain[2 * (first_rec + n_rows - k)]);
+    for (int k = 2; k <= kChainAhead && k <= n_rows; ++k) prefetch_down<T, mode, RING>(t, chain[2 * (first_rec + n_rows - k)]);
     for (int i = n_rows - 1; i >= 0; --i) {
-        DownOperands const o = next;
+        DownOperands o;
         int const row = c0.x;
+        if constexpr (RING) {
+            cp_async_wait_all();
+            o.ub = c0.z >= 0 ? Blk{*ring.at(buf, 0), *ring.at(buf, 1), *ring.at(buf, 2), *ring.at(buf, 3)} : Blk{0.0, 0.0, 0.0, 0.0};
+            o.d = Blk{*ring.at(buf, 4), *ring.at(buf, 5), *ring.at(buf, 6), *ring.at(buf, 7)};
+            o.y0 = *ring.at(buf, 8);
+            o.y1 = *ring.at(buf, 9);
+            o.pm = next.pm;
+            o.th = next.th;
+            o.v = next.v;
+            o.our = next.our;
+            o.oui = next.oui;
+        } else {
+            o = next;
+        }
         if (i > 0) {
             c0 = chain[2 * (first_rec + i - 1)];
-            next = fetch_down_k<T, mode>(t, c0.x, c0.y, c0.z);
-            if (i >= kChainAhead) prefetch_down<T, mode>(t, chain[2 * (first_rec + i - kChainAhead)]);
+            if constexpr (RING) {
+                stage(buf ^ 1, c0);
+                fetch_late(c0.x);
+            } else {
+                next = fetch_down_k<T, mode>(t, c0.x, c0.y, c0.z);
+            }
+            if (i >= kChainAhead) prefetch_down<T, mode, RING>(t, chain[2 * (first_rec + i - kChainAhead)]);
         }
+        buf ^= 1;
         dev = fmax(dev, down_step<T, mode>(t, row, has_parent, o, x0, x1));
         has_parent = true;
     }
     return dev;
 }
 
-template <int T, Mode mode>
+template <int T, Mode mode, bool RING>
 __device__ __forceinline__ void sweeps_v3(DevStructure const& s, TileP<T> const& t, int32_t const* __restrict__ prog, int slot,
-                                          int n_slot, bool active, bool& singular, double& dev, unsigned long long* phase) {
+                                          int n_slot, bool active, bool& singular, double& dev, unsigned long long* phase,
+                                          Ring const& ring) {
     int32_t const* __restrict__ const recs = s.path_prog; // leaf / row records: global memory
     int const n_leaf = prog[0], n_rec = prog[1], n_stage = prog[2];
     int32_t const* __restrict__ leaf = recs + prog[3];
@@ -581,7 +694,7 @@ __device__ __forceinline__ void sweeps_v3(DevStructure const& s, TileP<T> const&
     for (int st = 1; st < n_stage; ++st) {
         if (active) {
             for (int p = stage_ptr[st - 1] + slot; p < stage_ptr[st]; p += n_slot) {
-                singular |= up_path<T>(t, recs, chain, path[2 * p], path[2 * p + 1]);
+                singular |= up_path<T, RING>(t, recs, chain, path[2 * p], path[2 * p + 1], ring);
             }
         }
         __syncthreads();
@@ -590,32 +703,43 @@ __device__ __forceinline__ void sweeps_v3(DevStructure const& s, TileP<T> const&
     for (int st = n_stage - 1; st >= 1; --st) {
         if (active) {
             for (int p = stage_ptr[st - 1] + slot; p < stage_ptr[st]; p += n_slot) {
-                dev = fmax(dev, down_path<T, mode>(t, chain, path[2 * p], path[2 * p + 1]));
+                dev = fmax(dev, down_path<T, mode, RING && (V3_RING_DOWN != 0)>(t, chain, path[2 * p], path[2 * p + 1], ring));
             }
         }
         __syncthreads();
     }
     lap(3);
-    if (active) {
-        for (int i = slot; i < n_leaf; i += n_slot) {
-            int32_t const* rec = leaf + 8 * i;
-            if (i + n_slot < n_leaf) {
-                int32_t const* nx = leaf + 8 * (i + n_slot);
-                prefetch_down<T, mode>(t, make_int4(nx[0], nx[1], nx[3], 0));
-                if (nx[3] >= 0) {
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(t.xvec + (size_t)(nx[4] * 2) * T));
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(t.xvec + (size_t)(nx[4] * 2 + 1) * T));
-                }
-            }
-            DownOperands const o = fetch_down<T, mode>(t, rec);
-            double x0 = 0.0, x1 = 0.0;
-            bool const has_parent = rec[3] >= 0;
-            if (has_parent) {
+    if (active && slot < n_leaf) {
+        // software pipeline in registers: the operands of the thread's next leaf are loaded while the current one is solved
+        // (prefetch.global.L1 only reaches L2 on this part, tools/microbench_prefetch.cu); the leaf after that is prefetched
+        auto fetch_leaf = [&](int32_t const* rec, DownOperands& o, double& x0, double& x1) {
+            o = fetch_down<T, mode>(t, rec);
+            x0 = x1 = 0.0;
+            if (rec[3] >= 0) {
                 int const j = rec[4];
                 x0 = t.xvec[(size_t)(j * 2) * T];
                 x1 = t.xvec[(size_t)(j * 2 + 1) * T];
             }
-            dev = fmax(dev, down_step<T, mode>(t, rec[0], has_parent, o, x0, x1));
+        };
+        DownOperands next;
+        double nx0, nx1;
+        fetch_leaf(leaf + 8 * slot, next, nx0, nx1);
+        for (int i = slot; i < n_leaf; i += n_slot) {
+            int32_t const* rec = leaf + 8 * i;
+            DownOperands const o = next;
+            double x0 = nx0, x1 = nx1;
+            if (i + n_slot < n_leaf) {
+                fetch_leaf(leaf + 8 * (i + n_slot), next, nx0, nx1);
+                if (i + 2 * n_slot < n_leaf) {
+                    int32_t const* nx = leaf + 8 * (i + 2 * n_slot);
+                    prefetch_down<T, mode>(t, make_int4(nx[0], nx[1], nx[3], 0));
+                    if (nx[3] >= 0) {
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(t.xvec + (size_t)(nx[4] * 2) * T));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(t.xvec + (size_t)(nx[4] * 2 + 1) * T));
+                    }
+                }
+            }
+            dev = fmax(dev, down_step<T, mode>(t, rec[0], rec[3] >= 0, o, x0, x1));
         }
     }
     __syncthreads();
@@ -624,7 +748,9 @@ __device__ __forceinline__ void sweeps_v3(DevStructure const& s, TileP<T> const&
 
 } // namespace
 
-template <int T, bool SMEM> __global__ void __launch_bounds__(V3_THREADS, 1) nr_sym_v3_kernel(DevStructure s, DevBatch b, SolveOptions opt) {
+// SMEM: the chain part of the path program is staged in shared memory; RING (needs SMEM): operand ring of the chain walks
+// behind it
+template <int T, bool SMEM, bool RING> __global__ void __launch_bounds__(V3_THREADS, 1) nr_sym_v3_kernel(DevStructure s, DevBatch b, SolveOptions opt) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ unsigned long long sh_dev[T];
     __shared__ int sh_singular[T];
@@ -640,6 +766,11 @@ template <int T, bool SMEM> __global__ void __launch_bounds__(V3_THREADS, 1) nr_
     // SMEM: the pointer is derived from the shared array in this scope, so every read of the staged prefix (header, stages,
     // paths, chain records) compiles to LDS; leaf / row records stay in global memory (s.path_prog, read through L1)
     int32_t const* const prog = SMEM ? reinterpret_cast<int32_t const*>(smem_raw) : s.path_prog;
+    Ring ring{nullptr, 0};
+    if constexpr (RING) {
+        ring.base = reinterpret_cast<double*>(smem_raw + (((size_t)s.path_prog_smem_words * 4 + 127) / 128) * 128) + threadIdx.x;
+        ring.stride = blockDim.x;
+    }
     TileP<T> t;
     t.jac = b.jac + (size_t)tile * s.nnz_lu * 4 * T + lane;
     t.xvec = b.xvec + (size_t)tile * s.n_bus * 2 * T + lane;
@@ -664,7 +795,7 @@ template <int T, bool SMEM> __global__ void __launch_bounds__(V3_THREADS, 1) nr_
     {
         bool singular = false;
         double dev = 0.0;
-        sweeps_v3<T, Mode::linear_init>(s, t, prog, slot, n_slot, !done, singular, dev, phase);
+        sweeps_v3<T, Mode::linear_init, RING>(s, t, prog, slot, n_slot, !done, singular, dev, phase, ring);
         if (singular) sh_singular[lane] = 1;
         __syncthreads();
         if (!done && sh_singular[lane]) {
@@ -684,7 +815,7 @@ template <int T, bool SMEM> __global__ void __launch_bounds__(V3_THREADS, 1) nr_
         if (!__syncthreads_or(!done)) break;
         bool singular = false;
         double dev = 0.0;
-        sweeps_v3<T, Mode::newton>(s, t, prog, slot, n_slot, !done, singular, dev, phase ? phase + 8 : nullptr);
+        sweeps_v3<T, Mode::newton, RING>(s, t, prog, slot, n_slot, !done, singular, dev, phase ? phase + 8 : nullptr, ring);
         if (!done) {
             if (singular) sh_singular[lane] = 1;
             atomicMax(&sh_dev[lane], (unsigned long long)__double_as_longlong(dev));
@@ -711,17 +842,26 @@ template <int T, bool SMEM> __global__ void __launch_bounds__(V3_THREADS, 1) nr_
 
 template <int T>
 static void launch_v3_t(DevStructure const& s, DevBatch const& b, SolveOptions const& opt, int n_slot, cudaStream_t st) {
-    size_t const prog_bytes = (size_t)s.path_prog_smem_words * 4;
+    size_t const prog_bytes = (((size_t)s.path_prog_smem_words * 4 + 127) / 128) * 128;
+    size_t const ring_bytes = (size_t)2 * kRingOperands * sizeof(double) * T * n_slot;
     int dev = 0, max_optin = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    static int const want_ring = [] {
+        char const* v = std::getenv("PGMB_V3_RING"); // 0: chain operands through registers / L1 prefetch only (comparison)
+        return v != nullptr && *v != '\0' ? std::atoi(v) : 1;
+    }();
     bool const in_smem = prog_bytes + 1024 <= (size_t)max_optin;
-    size_t const dyn = in_smem ? prog_bytes : 0;
-    if (in_smem) {
-        cudaFuncSetAttribute(nr_sym_v3_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-        nr_sym_v3_kernel<T, true><<<b.n_tile, T * n_slot, dyn, st>>>(s, b, opt);
+    bool const with_ring = in_smem && want_ring != 0 && prog_bytes + ring_bytes + 1024 <= (size_t)max_optin;
+    if (with_ring) {
+        size_t const dyn = prog_bytes + ring_bytes;
+        cudaFuncSetAttribute(nr_sym_v3_kernel<T, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        nr_sym_v3_kernel<T, true, true><<<b.n_tile, T * n_slot, dyn, st>>>(s, b, opt);
+    } else if (in_smem) {
+        cudaFuncSetAttribute(nr_sym_v3_kernel<T, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prog_bytes);
+        nr_sym_v3_kernel<T, true, false><<<b.n_tile, T * n_slot, prog_bytes, st>>>(s, b, opt);
     } else {
-        nr_sym_v3_kernel<T, false><<<b.n_tile, T * n_slot, 0, st>>>(s, b, opt);
+        nr_sym_v3_kernel<T, false, false><<<b.n_tile, T * n_slot, 0, st>>>(s, b, opt);
     }
 }
 
