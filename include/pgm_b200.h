@@ -206,6 +206,7 @@ typedef struct pgmb_input_data {
     pgmb_component_buffer generic_branch; /* GenericBranchInput (auxiliary/input.hpp:144-165); symmetric calculations only */
     pgmb_component_buffer link;           /* LinkInput = BranchInput; branch sequence: line, asym_line, link, generic_branch, transformer */
     pgmb_component_buffer three_winding_transformer; /* ThreeWindingTransformerInput (Branch3Input + transformer data, 304 bytes) */
+    pgmb_component_buffer transformer_tap_regulator; /* TransformerTapRegulatorInput (auxiliary/input.hpp, 48 bytes): automatic tap changer */
 } pgmb_input_data;
 
 typedef struct pgmb_update_data {
@@ -215,6 +216,7 @@ typedef struct pgmb_update_data {
     pgmb_component_buffer asym_line, generic_branch; /* BranchUpdate */
     pgmb_component_buffer link;                      /* BranchUpdate */
     pgmb_component_buffer three_winding_transformer; /* ThreeWindingTransformerUpdate: id, status_1, status_2, status_3, tap_pos */
+    pgmb_component_buffer transformer_tap_regulator; /* TransformerTapRegulatorUpdate: id, status, u_set, u_band, line_drop_compensation_r/x */
 } pgmb_update_data;
 
 /* caller-owned output buffers [n_scenarios][n_component]; NULL = component not requested
@@ -225,6 +227,7 @@ typedef struct pgmb_output_data {
     void *asym_line, *generic_branch; /* BranchOutput */
     void* link;                       /* BranchOutput (loading 0) */
     void* three_winding_transformer;  /* Branch3Output (auxiliary/output.hpp): loading_1..3, loading, p/q/i/s per side */
+    void* transformer_tap_regulator;  /* TransformerTapRegulatorOutput: id, energized, tap_pos (na unless a tap strategy ran) */
 } pgmb_output_data;
 
 /* pgmb_options.flags -- measurement of the device-resident pipeline (bench.py `value`): one load-profile batch on one device.
@@ -250,6 +253,9 @@ typedef struct pgmb_options {
     int32_t threading;          /* host threads for batches whose scenarios change topology / parameters (each thread owns a
                                  * model copy, job_dispatch.hpp:88-160): -1 or 0 = all cores, n > 0 = n threads, 1 = sequential */
     uint32_t flags;             /* PGMB_FLAG_* */
+    int32_t tap_changing_strategy; /* PGM_TapChangingStrategy (basics.h:225-235): 0 disabled, 1 any_valid_tap, 2 min_voltage_tap,
+                                    * 3 max_voltage_tap, 4 fast_any_tap.  Not 0: every scenario runs the automatic tap changer
+                                    * (optimizer/tap_position_optimizer.hpp) around its power flows, scenario by scenario */
 } pgmb_options;
 
 typedef struct pgmb_model pgmb_model;

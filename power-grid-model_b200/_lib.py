@@ -8,6 +8,7 @@ LIB_PATH = os.environ.get("PGMB_LIB", os.path.join(_HERE, "libpgm_b200.so"))  # 
 
 PGMB_OK, PGMB_ERR_INVALID, PGMB_ERR_CUDA, PGMB_ERR_BATCH, PGMB_ERR_INTERNAL = range(5)
 METHODS = {"default_method": -128, "linear": 0, "newton_raphson": 1, "iterative_current": 3, "linear_current": 4}
+TAP_STRATEGIES = {"disabled": 0, "any_valid_tap": 1, "min_voltage_tap": 2, "max_voltage_tap": 3, "fast_any_tap": 4}
 
 
 class PgmB200Error(RuntimeError):
@@ -85,7 +86,7 @@ class ComponentBufferC(C.Structure):
 
 
 _COMPS = ("node", "line", "transformer", "shunt", "source", "sym_gen", "asym_gen", "sym_load", "asym_load", "voltage_regulator",
-          "asym_line", "generic_branch", "link", "three_winding_transformer")
+          "asym_line", "generic_branch", "link", "three_winding_transformer", "transformer_tap_regulator")
 
 
 class InputDataC(C.Structure):
@@ -103,7 +104,7 @@ class OutputDataC(C.Structure):
 class OptionsC(C.Structure):
     _fields_ = [("calculation_method", C.c_int32), ("symmetric", C.c_int32), ("err_tol", C.c_double),
                 ("max_iter", C.c_int64), ("n_devices", C.c_int32), ("first_device", C.c_int32), ("threading", C.c_int32),
-                ("flags", C.c_uint32)]
+                ("flags", C.c_uint32), ("tap_changing_strategy", C.c_int32)]
 
 
 FLAG_RESIDENT_INPUT = 1

@@ -13,12 +13,12 @@ ComponentBuffer cb(pgmb_component_buffer const& b) { return {b.n, b.indptr, b.da
 InputData input_of(pgmb_input_data const& in) {
     return {cb(in.node), cb(in.line), cb(in.transformer), cb(in.shunt), cb(in.source), cb(in.sym_gen), cb(in.asym_gen),
             cb(in.sym_load), cb(in.asym_load), cb(in.voltage_regulator), cb(in.asym_line), cb(in.generic_branch), cb(in.link),
-            cb(in.three_winding_transformer)};
+            cb(in.three_winding_transformer), cb(in.transformer_tap_regulator)};
 }
 UpdateData update_of(pgmb_update_data const& u) {
     return {u.n_scenarios, cb(u.line), cb(u.transformer), cb(u.shunt), cb(u.source), cb(u.sym_gen), cb(u.asym_gen),
             cb(u.sym_load), cb(u.asym_load), cb(u.voltage_regulator), cb(u.asym_line), cb(u.generic_branch), cb(u.link),
-            cb(u.three_winding_transformer)};
+            cb(u.three_winding_transformer), cb(u.transformer_tap_regulator)};
 }
 } // namespace
 
@@ -48,11 +48,12 @@ int pgmb_model_calculate(pgmb_model* model, const pgmb_options* opt, const pgmb_
         if (model == nullptr || opt == nullptr || output == nullptr) throw InvalidArgument("null argument");
         if (opt->max_iter < 0 || opt->max_iter > (int64_t{1} << 30)) throw InvalidArgument("max_iter out of range");
         ModelOptions const mo{opt->calculation_method, opt->symmetric != 0, opt->err_tol, opt->max_iter, opt->first_device, opt->threading,
-                              opt->n_devices, opt->flags};
+                              opt->n_devices, opt->flags, opt->tap_changing_strategy};
+        if (mo.tap_strategy < 0 || mo.tap_strategy > 4) throw InvalidArgument("tap_changing_strategy out of range");
         OutputData const od{output->node, output->line, output->transformer, output->shunt, output->source,
                             output->sym_gen, output->asym_gen, output->sym_load, output->asym_load,
                             output->voltage_regulator, output->asym_line, output->generic_branch, output->link,
-                            output->three_winding_transformer};
+                            output->three_winding_transformer, output->transformer_tap_regulator};
         if (update != nullptr) {
             UpdateData const ud = update_of(*update);
             failed = model->model->calculate(mo, &ud, od, n_iter, status);

@@ -106,6 +106,7 @@ UpdateData update_of(Dataset const& ds, RowScratch& scratch) {
         else if (b.component == "generic_branch") u.generic_branch = cb;
         else if (b.component == "link") u.link = cb;
         else if (b.component == "three_winding_transformer") u.three_winding_transformer = cb;
+        else if (b.component == "transformer_tap_regulator") u.transformer_tap_regulator = cb;
         else if (b.component == "transformer") u.transformer = cb;
         else if (b.component == "shunt") u.shunt = cb;
         else if (b.component == "source") u.source = cb;
@@ -135,6 +136,7 @@ void set_output_slot(OutputData& od, std::string const& c, void* rows) {
     else if (c == "generic_branch") od.generic_branch = rows;
     else if (c == "link") od.link = rows;
     else if (c == "three_winding_transformer") od.three_winding_transformer = rows;
+    else if (c == "transformer_tap_regulator") od.transformer_tap_regulator = rows;
     else if (c == "transformer") od.transformer = rows;
     else if (c == "shunt") od.shunt = rows;
     else if (c == "source") od.source = rows;
@@ -423,6 +425,7 @@ PGM_PowerGridModel* PGM_create_model(PGM_Handle* handle, double system_frequency
             else if (b.component == "generic_branch") in.generic_branch = cb;
             else if (b.component == "link") in.link = cb;
             else if (b.component == "three_winding_transformer") in.three_winding_transformer = cb;
+            else if (b.component == "transformer_tap_regulator") in.transformer_tap_regulator = cb;
             else if (b.component == "transformer") in.transformer = cb;
             else if (b.component == "shunt") in.shunt = cb;
             else if (b.component == "source") in.source = cb;
@@ -481,8 +484,8 @@ void PGM_calculate(PGM_Handle* handle, PGM_PowerGridModel* model, PGM_Options co
             throw CalculationError("pgm_b200 provides calculation type power_flow only (state estimation and short circuit are "
                                    "outside the accelerated path)\n");
         }
-        // automatic tap changing acts on transformer_tap_regulator components, which PGM_create_model of this library refuses:
-        // with none in the model every valid strategy is the plain power flow (optimizer/tap_position_optimizer.hpp)
+        // automatic tap changing (optimizer/tap_position_optimizer.hpp) acts on the transformer_tap_regulator components of the
+        // model; with none in the model every valid strategy is the plain power flow
         if (o.tap_changing_strategy < 0 || o.tap_changing_strategy > 4) {
             throw InvalidArgument("get_optimizer_type is not implemented for #" + std::to_string(o.tap_changing_strategy) + "!\n");
         }
@@ -505,7 +508,8 @@ void PGM_calculate(PGM_Handle* handle, PGM_PowerGridModel* model, PGM_Options co
         // threading (job_dispatch.hpp:166-171): < 0 = sequential, 0 = hardware concurrency, n = n threads.  It only matters for
         // batches that take the per-scenario route (own topology per scenario); load batches run on the GPU in one pipeline.
         int32_t const threading = o.threading < 0 ? 1 : static_cast<int32_t>(std::min<PGM_Idx>(o.threading, 1 << 20));
-        ModelOptions const mo{method, sym, o.err_tol, o.max_iter, device_ordinal(), threading};
+        ModelOptions mo{method, sym, o.err_tol, o.max_iter, device_ordinal(), threading};
+        mo.tap_strategy = static_cast<int32_t>(o.tap_changing_strategy);
         // the output of a cartesian product holds the product of all dimension sizes (model.cpp:290-334 asserts it)
         if (batch_dataset != nullptr) {
             PGM_Idx total = 1;

@@ -148,6 +148,29 @@ struct VoltageRegulatorOutput {
     IntS limit_violated;
 };
 static_assert(sizeof(VoltageRegulatorInput) == 40 && sizeof(VoltageRegulatorUpdate) == 32 && sizeof(VoltageRegulatorOutput) == 8);
+// component/transformer_tap_regulator.hpp:23-99 (+ regulator.hpp): the regulator of the automatic tap changer.  control_side is a
+// ControlSide (from = side_1 = 0, to = side_2 = 1, side_3 = 2)
+struct TransformerTapRegulatorInput {
+    ID id, regulated_object;
+    IntS status, control_side;
+    double u_set, u_band, line_drop_compensation_r, line_drop_compensation_x;
+};
+struct TransformerTapRegulatorUpdate {
+    ID id;
+    IntS status;
+    double u_set, u_band, line_drop_compensation_r, line_drop_compensation_x;
+};
+struct TransformerTapRegulatorOutput {
+    ID id;
+    IntS energized;
+    IntS tap_pos;
+};
+static_assert(sizeof(TransformerTapRegulatorInput) == 48 && sizeof(TransformerTapRegulatorUpdate) == 40 &&
+              sizeof(TransformerTapRegulatorOutput) == 8);
+struct TapRegulatorState { // what TransformerTapRegulator::update changes (transformer_tap_regulator.hpp:41-50)
+    bool status;
+    double u_set, u_band, line_drop_compensation_r, line_drop_compensation_x;
+};
 template <int B> struct NodeOutput {
     ID id;
     IntS energized;

@@ -141,9 +141,46 @@ Model::Model(double system_frequency, InputData const& in) : freq_{system_freque
     add_lg(static_cast<AsymLoadGenInput const*>(in.asym_gen.data), in.asym_gen.n, 3, 1.0);
     add_lg(static_cast<SymLoadGenInput const*>(in.sym_load.data), in.sym_load.n, 1, -1.0);
     add_lg(static_cast<AsymLoadGenInput const*>(in.asym_load.data), in.asym_load.n, 3, -1.0);
+    std::unordered_map<ID, int> regulated;
+    // transformer tap regulators (main_core/input.hpp:168-214): the regulated object is a transformer or a three-winding
+    // transformer; the control side names one of its terminals, whose node gives the rated voltage of the set point
+    auto const* tap_regs = static_cast<TransformerTapRegulatorInput const*>(in.transformer_tap_regulator.data);
+    for (Idx i = 0; i != in.transformer_tap_regulator.n; ++i) {
+        TransformerTapRegulatorInput const& r = tap_regs[i];
+        add_id(r.id);
+        if (all_ids_.find(r.regulated_object) == all_ids_.end()) {
+            throw InvalidArgument("The id cannot be found: " + std::to_string(r.regulated_object) + "\n");
+        }
+        TapTarget target{};
+        if (auto it = trafo_idx_.find(r.regulated_object); it != trafo_idx_.end()) {
+            if (r.control_side != 0 && r.control_side != 1) {
+                throw InvalidArgument("transformer_tap_regulator item retrieval is not implemented for ControlSide #" +
+                                      std::to_string(static_cast<int>(r.control_side)) + "!\n");
+            }
+            TransformerInput const& t = trafo_in_[it->second];
+            target = {0, it->second, u_rated(r.control_side == 0 ? t.from_node : t.to_node)};
+        } else if (auto it3 = t3w_idx_.find(r.regulated_object); it3 != t3w_idx_.end()) {
+            if (r.control_side < 0 || r.control_side > 2) {
+                throw InvalidArgument("transformer_tap_regulator item retrieval is not implemented for ControlSide #" +
+                                      std::to_string(static_cast<int>(r.control_side)) + "!\n");
+            }
+            ThreeWindingTransformerInput const& t = t3w_c_[it3->second].in;
+            target = {1, it3->second, u_rated(r.control_side == 0 ? t.node_1 : r.control_side == 1 ? t.node_2 : t.node_3)};
+        } else {
+            throw InvalidArgument("transformer_tap_regulator regulator is not supported for object with ID " +
+                                  std::to_string(r.regulated_object) + "\n");
+        }
+        regulated.emplace(r.regulated_object, 0); // duplicates are reported after every regulator has been read
+        tap_reg_idx_[r.id] = i;
+        tap_reg_in_.push_back(r);
+        tap_reg_target_.push_back(target);
+        tap_reg_st_.push_back({r.status != 0, r.u_set, r.u_band, r.line_drop_compensation_r, r.line_drop_compensation_x});
+    }
+    if (regulated.size() != tap_reg_in_.size()) {
+        throw InvalidArgument("There are objects regulated by more than one regulator. Maximum one regulator is allowed.\n");
+    }
     // voltage regulators (main_core/input.hpp:216-241): the regulated object is a load / generator, one regulator per object
     auto const* regs = static_cast<VoltageRegulatorInput const*>(in.voltage_regulator.data);
-    std::unordered_map<ID, int> regulated;
     for (Idx i = 0; i != in.voltage_regulator.n; ++i) {
         VoltageRegulatorInput const& r = regs[i];
         add_id(r.id);
@@ -572,6 +609,20 @@ void Model::apply_scenario(UpdateData const& u, Idx s, Saved* saved) {
             if (!std::isnan(p->q_max)) reg_st_[i].q_max = p->q_max;
         }
     }
+    {
+        // TransformerTapRegulator::update (transformer_tap_regulator.hpp:41-50): neither topology nor parameters change
+        auto [b, e] = scenario_span<TransformerTapRegulatorUpdate>(u.transformer_tap_regulator, s);
+        for (auto p = b; p != e; ++p) {
+            Idx const i = find(*p, p - b, e - b, static_cast<Idx>(tap_reg_in_.size()), tap_reg_idx_, 0);
+            if (saved != nullptr) saved->tap_reg.emplace_back(i, tap_reg_st_[i]);
+            // Regulator::set_status takes the value as it is (regulator.hpp:31): "not given" reads as on
+            tap_reg_st_[i].status = static_cast<bool>(p->status);
+            if (!std::isnan(p->u_set)) tap_reg_st_[i].u_set = p->u_set;
+            if (!std::isnan(p->u_band)) tap_reg_st_[i].u_band = p->u_band;
+            if (!std::isnan(p->line_drop_compensation_r)) tap_reg_st_[i].line_drop_compensation_r = p->line_drop_compensation_r;
+            if (!std::isnan(p->line_drop_compensation_x)) tap_reg_st_[i].line_drop_compensation_x = p->line_drop_compensation_x;
+        }
+    }
 }
 
 void Model::restore(Saved const& s) {
@@ -580,6 +631,7 @@ void Model::restore(Saved const& s) {
     for (auto it = s.source.rbegin(); it != s.source.rend(); ++it) source_st_[it->first] = it->second;
     for (auto it = s.shunt.rbegin(); it != s.shunt.rend(); ++it) shunt_st_[it->first] = it->second;
     for (auto it = s.lg.rbegin(); it != s.lg.rend(); ++it) lg_st_[it->first] = it->second;
+    for (auto it = s.tap_reg.rbegin(); it != s.tap_reg.rend(); ++it) tap_reg_st_[it->first] = it->second;
     for (auto it = s.reg.rbegin(); it != s.reg.rend(); ++it) reg_st_[it->first] = it->second;
     for (auto it = s.t3w.rbegin(); it != s.t3w.rend(); ++it) t3w_st_[it->first] = it->second;
     if (s.topo) topo_valid_ = false;
@@ -810,6 +862,17 @@ void Model::write_output(Idx n_scn, Idx first, OutputData const& out, std::vecto
         lg_out(out.asym_gen, n_sym_gen_, n_asym_gen_);
         lg_out(out.sym_load, n_sym_gen_ + n_asym_gen_, n_sym_load_);
         lg_out(out.asym_load, n_sym_gen_ + n_asym_gen_ + n_sym_load_, n_asym_load_);
+        if (out.transformer_tap_regulator != nullptr) { // main_core/output.hpp:381-396: null output unless the optimizer ran
+            Idx const n = static_cast<Idx>(tap_reg_in_.size());
+            auto* dst = static_cast<TransformerTapRegulatorOutput*>(out.transformer_tap_regulator) + os * n;
+            for (Idx i = 0; i != n; ++i) {
+                IntS const tap = i < static_cast<Idx>(tap_positions_out_.size()) ? tap_positions_out_[i] : kNaIntS;
+                std::memset(&dst[i], 0, sizeof(dst[i])); // padding bytes too: outputs compare byte for byte between runs
+                dst[i].id = tap_reg_in_[i].id;
+                dst[i].energized = tap != kNaIntS ? 1 : 0;
+                dst[i].tap_pos = tap;
+            }
+        }
         if (out.voltage_regulator != nullptr) { // main_core/output.hpp:407-421, VoltageRegulator::get_output
             Idx const n = static_cast<Idx>(reg_in_.size());
             auto* dst = static_cast<VoltageRegulatorOutput*>(out.voltage_regulator) + os * n;
@@ -828,16 +891,16 @@ void Model::write_output(Idx n_scn, Idx first, OutputData const& out, std::vecto
 }
 
 template <int B>
-int64_t Model::run_block(ModelOptions const& opt, Idx n_scn, std::vector<std::vector<double>> const& sinj,
-                         std::vector<std::vector<double>> const& uref, OutputData const& out, Idx first, int32_t* n_iter,
-                         int32_t* status, RegulatorInput const* reg) {
+void Model::solve_block(ModelOptions const& opt, Idx n_scn, std::vector<std::vector<double>> const& sinj,
+                        std::vector<std::vector<double>> const& uref, RegulatorInput const* reg, BlockSolution& sol) {
     constexpr int si = B == 1 ? 0 : 1;
     constexpr int c2 = 2 * B;
-    std::vector<std::vector<double>> so[6];
+    auto& so = sol.so;
     for (auto& v : so) v.resize(topo_.math.size());
-    std::vector<std::vector<int8_t>> reg_out(topo_.math.size());
-    std::vector<int32_t> st_all(n_scn, 0), it_all(n_scn, 0);
-    std::vector<double> dev_all(n_scn, 0.0);
+    sol.reg_out.assign(topo_.math.size(), {});
+    sol.status.assign(n_scn, 0);
+    sol.n_iter.assign(n_scn, 0);
+    sol.max_dev.assign(n_scn, 0.0);
     for (size_t g = 0; g != topo_.math.size(); ++g) {
         auto const& m = topo_.math[g];
         Engine& e = *engines_[g].engine[si];
@@ -853,8 +916,8 @@ int64_t Model::run_block(ModelOptions const& opt, Idx n_scn, std::vector<std::ve
         PfInputView in_view{n_scn, uref[g].data(), false, sinj[g].data()};
         if (e.has_regulators()) {
             if (reg == nullptr) throw InvalidArgument("internal: regulator input missing");
-            reg_out[g].resize(n_scn * m.n_voltage_regulator() * 2);
-            view.voltage_regulator = reg_out[g].data();
+            sol.reg_out[g].resize(n_scn * m.n_voltage_regulator() * 2);
+            view.voltage_regulator = sol.reg_out[g].data();
             in_view.voltage_regulator = reg->param[g].data();
             in_view.load_gen_status = reg->lg_status[g].data();
         }
@@ -866,22 +929,30 @@ int64_t Model::run_block(ModelOptions const& opt, Idx n_scn, std::vector<std::ve
         e.fetch(view);
         timing[4] += ms_since(t0);
         for (Idx s = 0; s != n_scn; ++s) {
-            if (st_all[s] == 0 && st[s] != 0) dev_all[s] = dev[s];
-            if (st_all[s] == 0) st_all[s] = st[s];
-            it_all[s] = std::max(it_all[s], it[s]);
+            if (sol.status[s] == 0 && st[s] != 0) sol.max_dev[s] = dev[s];
+            if (sol.status[s] == 0) sol.status[s] = st[s];
+            sol.n_iter[s] = std::max(sol.n_iter[s], it[s]);
         }
     }
+}
+
+template <int B>
+int64_t Model::run_block(ModelOptions const& opt, Idx n_scn, std::vector<std::vector<double>> const& sinj,
+                         std::vector<std::vector<double>> const& uref, OutputData const& out, Idx first, int32_t* n_iter,
+                         int32_t* status, RegulatorInput const* reg) {
+    BlockSolution sol;
+    solve_block<B>(opt, n_scn, sinj, uref, reg, sol);
     auto t0 = Clock::now();
-    write_output<B>(n_scn, first, out, so, reg_out, reg != nullptr ? &reg->lg_status : nullptr);
+    write_output<B>(n_scn, first, out, sol.so, sol.reg_out, reg != nullptr ? &reg->lg_status : nullptr);
     timing[3] += ms_since(t0);
     int64_t failed = 0;
     for (Idx s = 0; s != n_scn; ++s) {
-        if (n_iter != nullptr) n_iter[first + s] = it_all[s];
-        if (status != nullptr) status[first + s] = st_all[s];
-        if (st_all[s] != 0) {
+        if (n_iter != nullptr) n_iter[first + s] = sol.n_iter[s];
+        if (status != nullptr) status[first + s] = sol.status[s];
+        if (sol.status[s] != 0) {
             ++failed;
             batch_message += "Error in batch #" + std::to_string(first + s) + ": " +
-                             scenario_failure_text(st_all[s], opt.max_iter, dev_all[s], opt.err_tol) + "\n";
+                             scenario_failure_text(sol.status[s], opt.max_iter, sol.max_dev[s], opt.err_tol) + "\n";
         }
     }
     return failed;
@@ -1111,7 +1182,21 @@ int64_t Model::calculate_impl(ModelOptions const& opt, UpdateData const* update,
     int64_t failed = 0;
     auto t0 = Clock::now();
     bool const has_reg = !reg_in_.empty();
-    if (update == nullptr) {
+    if (out.transformer_tap_regulator != nullptr && !tap_reg_in_.empty()) {
+        // TransformerTapRegulator::get_null_output for every scenario; the optimizer route overwrites what it regulates
+        Idx const n_scn = update == nullptr ? 1 : update->n_scenarios, n_reg = static_cast<Idx>(tap_reg_in_.size());
+        auto* dst = static_cast<TransformerTapRegulatorOutput*>(out.transformer_tap_regulator);
+        for (Idx s = 0; s != n_scn; ++s)
+            for (Idx i = 0; i != n_reg; ++i) {
+                std::memset(&dst[s * n_reg + i], 0, sizeof(*dst));
+                dst[s * n_reg + i].id = tap_reg_in_[i].id;
+                dst[s * n_reg + i].tap_pos = kNaIntS;
+            }
+    }
+    if (update == nullptr && opt.tap_strategy != 0) {
+        timing[0] += ms_since(t0);
+        failed = run_tap_optimizer<B>(opt, out, 0, n_iter, status);
+    } else if (update == nullptr) {
         check_regulators<B>(opt);
         prepare_engines<B>();
         std::vector<std::vector<double>> sinj(topo_.math.size()), uref(topo_.math.size());
@@ -1126,7 +1211,8 @@ int64_t Model::calculate_impl(ModelOptions const& opt, UpdateData const* update,
         bool const structural = update->line.data != nullptr || update->transformer.data != nullptr ||
                                 update->asym_line.data != nullptr || update->generic_branch.data != nullptr ||
                                 update->link.data != nullptr || update->three_winding_transformer.data != nullptr ||
-                                update->shunt.data != nullptr || (has_reg && update->voltage_regulator.data != nullptr);
+                                update->shunt.data != nullptr || (has_reg && update->voltage_regulator.data != nullptr) ||
+                                opt.tap_strategy != 0; // the tap search of a scenario is its own sequence of power flows
         bool source_param_change = false;
         if (update->source.data != nullptr) {
             for (Idx s = 0; s != n && !source_param_change; ++s) {
@@ -1143,7 +1229,7 @@ int64_t Model::calculate_impl(ModelOptions const& opt, UpdateData const* update,
         std::vector<Idx> todo;
         bool todo_is_subset = false;
         std::vector<int32_t> status_local;
-        if (structural && !source_param_change && !has_reg && (opt.method == 1 || opt.method == -128) && n > 0 &&
+        if (structural && !source_param_change && !has_reg && opt.tap_strategy == 0 && (opt.method == 1 || opt.method == -128) && n > 0 &&
             (update->line.data != nullptr || update->transformer.data != nullptr) && std::getenv("PGMB_N1_EXACT") == nullptr) {
             prepare_engines<B>();
             OutagePlan plan;
@@ -1272,12 +1358,16 @@ int64_t Model::calculate_impl(ModelOptions const& opt, UpdateData const* update,
                         Saved saved;
                         try {
                             model.apply_scenario(*update, s, &saved);
-                            model.template check_regulators<B>(opt);
-                            model.template prepare_engines<B>();
-                            std::vector<std::vector<double>> sinj(model.topo_.math.size()), uref(model.topo_.math.size());
-                            RegulatorInput reg;
-                            model.template gather_pf_input<B>(sinj, uref, &reg);
-                            failed_per_thread[t] += model.template run_block<B>(opt, 1, sinj, uref, out, s, n_iter, status, &reg);
+                            if (opt.tap_strategy != 0) {
+                                failed_per_thread[t] += model.template run_tap_optimizer<B>(opt, out, s, n_iter, status);
+                            } else {
+                                model.template check_regulators<B>(opt);
+                                model.template prepare_engines<B>();
+                                std::vector<std::vector<double>> sinj(model.topo_.math.size()), uref(model.topo_.math.size());
+                                RegulatorInput reg;
+                                model.template gather_pf_input<B>(sinj, uref, &reg);
+                                failed_per_thread[t] += model.template run_block<B>(opt, 1, sinj, uref, out, s, n_iter, status, &reg);
+                            }
                             messages[s] = std::move(model.batch_message);
                             model.batch_message.clear();
                         } catch (CudaError const&) {
@@ -1319,10 +1409,25 @@ int64_t Model::calculate_impl(ModelOptions const& opt, UpdateData const* update,
     return failed;
 }
 
+// used by the tap optimizer (model_tap.cpp)
+#define PGMB_INSTANTIATE(B)                                                                                                          \
+    template void Model::check_regulators<B>(ModelOptions const&) const;                                                             \
+    template void Model::prepare_engines<B>();                                                                                       \
+    template void Model::gather_pf_input<B>(std::vector<std::vector<double>>&, std::vector<std::vector<double>>&, RegulatorInput*)   \
+        const;                                                                                                                       \
+    template void Model::solve_block<B>(ModelOptions const&, Idx, std::vector<std::vector<double>> const&,                           \
+                                        std::vector<std::vector<double>> const&, RegulatorInput const*, BlockSolution&);             \
+    template void Model::write_output<B>(Idx, Idx, OutputData const&, std::vector<std::vector<double>> const (&)[6],                 \
+                                         std::vector<std::vector<int8_t>> const&, std::vector<std::vector<int8_t>> const*) const;
+PGMB_INSTANTIATE(1)
+PGMB_INSTANTIATE(3)
+#undef PGMB_INSTANTIATE
+
 int64_t Model::calculate(ModelOptions const& opt, UpdateData const* update, OutputData const& out, int32_t* n_iter,
                          int32_t* status) {
-    return opt.symmetric ? calculate_impl<1>(opt, update, out, n_iter, status)
-                         : calculate_impl<3>(opt, update, out, n_iter, status);
+    ModelOptions o = opt;
+    if (tap_reg_in_.empty()) o.tap_strategy = 0; // nothing to regulate: the optimizer is the plain power flow
+    return o.symmetric ? calculate_impl<1>(o, update, out, n_iter, status) : calculate_impl<3>(o, update, out, n_iter, status);
 }
 
 // ---- copy / indexer (PGM_copy_model, PGM_get_indexer) -------------------------------------------------------------
@@ -1341,6 +1446,7 @@ Idx Model::component_count(std::string const& c) const {
     if (c == "generic_branch") return n_gb();
     if (c == "link") return n_link();
     if (c == "three_winding_transformer") return n_t3w();
+    if (c == "transformer_tap_regulator") return static_cast<Idx>(tap_reg_in_.size());
     if (c == "transformer") return n_trafo();
     if (c == "shunt") return static_cast<Idx>(shunt_in_.size());
     if (c == "source") return static_cast<Idx>(source_in_.size());
@@ -1362,6 +1468,7 @@ void Model::get_indexer(std::string const& c, ID const* ids, Idx size, Idx* inde
     else if (c == "generic_branch") map = &gb_idx_;
     else if (c == "link") map = &link_idx_;
     else if (c == "three_winding_transformer") map = &t3w_idx_;
+    else if (c == "transformer_tap_regulator") map = &tap_reg_idx_;
     else if (c == "transformer") map = &trafo_idx_;
     else if (c == "shunt") map = &shunt_idx_;
     else if (c == "source") map = &source_idx_;
@@ -1393,7 +1500,7 @@ std::vector<int64_t> const& Model::get_index(Idx group, std::string const& name)
     prepare_topology();
     std::string const key = std::to_string(group) + "." + name;
     auto it = index_cache_.find(key);
-    if (it != index_cache_.end()) return it->second;
+    if (it != index_cache_.end() && name != "tap_rank") return it->second;
     std::vector<int64_t> v;
     auto coupling = [](std::vector<Coupling> const& c) {
         std::vector<int64_t> o;
@@ -1417,6 +1524,12 @@ std::vector<int64_t> const& Model::get_index(Idx group, std::string const& name)
             v.push_back(c.group);
             v.insert(v.end(), c.pos.begin(), c.pos.end());
         }
+    }
+    else if (name == "tap_rank") {
+        // ranking of the regulated transformers by the automatic tap changer (model_tap.cpp): kind (0 transformer, 1 three-winding
+        // transformer), index within the kind, rank group -- in the order the optimizer visits them
+        v = tap_rank_table();
+        return index_cache_[key] = v; // depends on the regulators' state: recomputed on every call
     }
     else if (name == "branch_is_bridge" || name == "bridge_cut_size") {
         // host logic of the shared-pattern N-1 route (plan_outage_batch): per branch component (lines then transformers)

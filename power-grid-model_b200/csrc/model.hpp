@@ -26,16 +26,16 @@ struct ComponentBuffer {
 };
 struct InputData {
     ComponentBuffer node, line, transformer, shunt, source, sym_gen, asym_gen, sym_load, asym_load, voltage_regulator, asym_line, generic_branch,
-        link, three_winding_transformer;
+        link, three_winding_transformer, transformer_tap_regulator;
 };
 struct UpdateData {
     int64_t n_scenarios;
     ComponentBuffer line, transformer, shunt, source, sym_gen, asym_gen, sym_load, asym_load, voltage_regulator, asym_line, generic_branch,
-        link, three_winding_transformer;
+        link, three_winding_transformer, transformer_tap_regulator;
 };
 struct OutputData {
     void *node, *line, *transformer, *shunt, *source, *sym_gen, *asym_gen, *sym_load, *asym_load, *voltage_regulator, *asym_line, *generic_branch,
-        *link, *three_winding_transformer;
+        *link, *three_winding_transformer, *transformer_tap_regulator;
 };
 struct ModelOptions {
     int32_t method;
@@ -46,6 +46,9 @@ struct ModelOptions {
     int32_t threading{-1}; // structural batches: -1 / 0 = all cores, n > 0 = n host threads
     int32_t n_devices{1};  // GPUs one batch is spread over (contiguous scenario blocks), starting at `device`
     uint32_t flags{0};     // PGMB_FLAG_* (include/pgm_b200.h): device-resident update rows / output structs
+    // automatic tap changer (PGM_TapChangingStrategy): 0 disabled, 1 any_valid_tap, 2 min_voltage_tap, 3 max_voltage_tap,
+    // 4 fast_any_tap
+    int32_t tap_strategy{0};
 };
 constexpr uint32_t kFlagResidentInput = 1u;  // the update rows of this batch are already in HBM (previous call, same buffers)
 constexpr uint32_t kFlagResidentOutput = 2u; // leave the output structs in HBM (no copy to the caller's buffers)
@@ -120,9 +123,19 @@ class Model {
     std::vector<VoltageRegulatorInput> reg_in_;
     std::vector<Idx> reg_lg_;
     std::vector<RegulatorState> reg_st_;
+    // transformer tap regulators (component/transformer_tap_regulator.hpp): input, regulated transformer (kind 0: transformer,
+    // 1: three-winding transformer; index within the kind), rated voltage of the control-side node, state
+    std::vector<TransformerTapRegulatorInput> tap_reg_in_;
+    struct TapTarget {
+        int kind;
+        Idx index;
+        double u_rated;
+    };
+    std::vector<TapTarget> tap_reg_target_;
+    std::vector<TapRegulatorState> tap_reg_st_;
     // id lookup
     std::unordered_map<ID, Idx> node_idx_, line_idx_, trafo_idx_, shunt_idx_, source_idx_, lg_idx_, reg_idx_, aline_idx_, gb_idx_, link_idx_,
-        t3w_idx_;
+        t3w_idx_, tap_reg_idx_;
     std::unordered_map<ID, int> all_ids_;
 
     // caches
@@ -208,6 +221,7 @@ class Model {
         std::vector<std::pair<Idx, LoadGenState>> lg;
         std::vector<std::pair<Idx, RegulatorState>> reg;
         std::vector<std::pair<Idx, ThreeWindingState>> t3w;
+        std::vector<std::pair<Idx, TapRegulatorState>> tap_reg;
         bool topo{false}, param{false};
     };
     void apply_scenario(UpdateData const& u, Idx s, Saved* saved);
@@ -218,10 +232,29 @@ class Model {
     template <int B>
     int64_t calculate_impl(ModelOptions const& opt, UpdateData const* update, OutputData const& out, int32_t* n_iter,
                            int32_t* status);
+    // solver output of one engine call per math group: [0] bus voltages, [2] branch flows, [3] sources, [4] shunts, [5] load_gens
+    struct BlockSolution {
+        std::vector<std::vector<double>> so[6];
+        std::vector<std::vector<int8_t>> reg_out;
+        std::vector<int32_t> status, n_iter;
+        std::vector<double> max_dev;
+    };
+    template <int B>
+    void solve_block(ModelOptions const& opt, Idx n_scn, std::vector<std::vector<double>> const& sinj,
+                     std::vector<std::vector<double>> const& uref, RegulatorInput const* reg, BlockSolution& sol);
     template <int B>
     int64_t run_block(ModelOptions const& opt, Idx n_scn, std::vector<std::vector<double>> const& sinj,
                       std::vector<std::vector<double>> const& uref, OutputData const& out, Idx first_scenario,
                       int32_t* n_iter, int32_t* status, RegulatorInput const* reg = nullptr);
+    // ---- automatic tap changer (model_tap.cpp; optimizer/tap_position_optimizer.hpp) ----
+    // one scenario in the model's current state: ranks the regulated transformers, searches their tap positions with repeated
+    // power flows on the GPU, writes the outputs of the final power flow and puts the tap positions back
+    template <int B>
+    int64_t run_tap_optimizer(ModelOptions const& opt, OutputData const& out, Idx scenario, int32_t* n_iter, int32_t* status);
+    struct TapRanked;
+    std::vector<std::vector<TapRanked>> rank_tap_regulators() const;
+    std::vector<int64_t> tap_rank_table() const; // introspection: (kind, index, rank group) in the order of the search
+    std::vector<IntS> tap_positions_out_; // per tap regulator: tap position found by the last run_tap_optimizer (na: not regulated)
     // ---- branch-outage batches on the shared symbolic pattern (N-1 studies) ----
     // A scenario that switches ONE fully connected branch which is not a bridge of the grid keeps every node energized: it is
     // solved on the base topology's pattern with the branch's admittance contributions replaced (Engine::set_overlay) instead of

@@ -83,7 +83,7 @@ class PowerGridModel:
     def calculate_power_flow(self, *, symmetric=True, error_tolerance=1e-8, max_iterations=20,
                              calculation_method="newton_raphson", update_data=None, threading=-1,
                              output_component_types=None, continue_on_batch_error=False, device=0, output_buffers=None,
-                             reuse_output_buffers=False, n_devices=1, flags=0):
+                             reuse_output_buffers=False, n_devices=1, flags=0, tap_changing_strategy=0):
         """Same contract as the reference: without ``update_data`` a single calculation returning 1-D arrays, with it a
         batch returning (n_scenarios, n_elements) arrays.  ``threading`` is accepted for signature compatibility; the
         scenario loop of load / source-reference batches runs on the GPU whatever ``threading`` says; batches that switch
@@ -93,11 +93,15 @@ class PowerGridModel:
         arrays owned by the model and reused by the next call with the same shapes (no page faults, transfers overlap the
         solver) -- copy what must outlive the next calculation.  ``n_devices``: GPUs the batch is spread over inside the call
         (contiguous scenario blocks, starting at ``device``).  ``flags``: ``pgm_b200.FLAG_RESIDENT_INPUT / _OUTPUT`` (device-resident
-        update rows / output structs, include/pgm_b200.h)."""
+        update rows / output structs, include/pgm_b200.h).  ``tap_changing_strategy``: "disabled" / 0, "any_valid_tap" / 1,
+        "min_voltage_tap" / 2, "max_voltage_tap" / 3, "fast_any_tap" / 4 -- the automatic tap changer of the reference around
+        every scenario's power flow (needs ``transformer_tap_regulator`` components)."""
+        if isinstance(tap_changing_strategy, str):
+            tap_changing_strategy = _lib.TAP_STRATEGIES[tap_changing_strategy]
         if isinstance(calculation_method, str):
             calculation_method = _lib.METHODS[calculation_method]
         opt = _lib.OptionsC(int(calculation_method), int(bool(symmetric)), float(error_tolerance), int(max_iterations),
-                            int(n_devices), int(device), int(threading), int(flags))
+                            int(n_devices), int(device), int(threading), int(flags), int(tap_changing_strategy))
         upd = None
         n_scn = 1
         keep = None

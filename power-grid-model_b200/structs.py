@@ -38,6 +38,11 @@ INPUT = {
     "sym_load": _dt(_appliance_head + [("type", "i1"), ("p_specified", "f8"), ("q_specified", "f8")]),
     "asym_load": _dt(_appliance_head + [("type", "i1"), ("p_specified", "f8", (3,)), ("q_specified", "f8", (3,))]),
 }
+# transformer_tap_regulator (automatic tap changer, calculate_power_flow(tap_changing_strategy=...)); control_side: 0 from /
+# side_1, 1 to / side_2, 2 side_3
+INPUT["transformer_tap_regulator"] = _dt([("id", "i4"), ("regulated_object", "i4"), ("status", "i1"), ("control_side", "i1"),
+                                          ("u_set", "f8"), ("u_band", "f8"), ("line_drop_compensation_r", "f8"),
+                                          ("line_drop_compensation_x", "f8")])
 # voltage_regulator (PV buses with reactive-power limits, Newton-Raphson only)
 INPUT["voltage_regulator"] = _dt([("id", "i4"), ("regulated_object", "i4"), ("status", "i1"), ("u_ref", "f8"), ("q_min", "f8"),
                                   ("q_max", "f8")])
@@ -67,6 +72,8 @@ UPDATE = {
     "sym_load": _dt([("id", "i4"), ("status", "i1"), ("p_specified", "f8"), ("q_specified", "f8")]),
     "asym_load": _dt([("id", "i4"), ("status", "i1"), ("p_specified", "f8", (3,)), ("q_specified", "f8", (3,))]),
 }
+UPDATE["transformer_tap_regulator"] = _dt([("id", "i4"), ("status", "i1"), ("u_set", "f8"), ("u_band", "f8"),
+                                           ("line_drop_compensation_r", "f8"), ("line_drop_compensation_x", "f8")])
 UPDATE["voltage_regulator"] = _dt([("id", "i4"), ("status", "i1"), ("u_ref", "f8"), ("q_min", "f8"), ("q_max", "f8")])
 UPDATE["sym_gen"] = UPDATE["sym_load"]
 UPDATE["asym_gen"] = UPDATE["asym_load"]
@@ -96,6 +103,7 @@ def output_dtypes(sym: bool):
         "shunt": appliance, "source": appliance,
         "sym_gen": appliance, "asym_gen": appliance, "sym_load": appliance, "asym_load": appliance,
         "voltage_regulator": _dt([("id", "i4"), ("energized", "i1"), ("limit_violated", "i1")]),
+        "transformer_tap_regulator": _dt([("id", "i4"), ("energized", "i1"), ("tap_pos", "i1")]),
     }
 
 
@@ -104,9 +112,10 @@ ASYM_OUTPUT = output_dtypes(False)
 
 # component storage order of the reference (all_components.hpp:36-39), PF subset
 COMPONENT_ORDER = ("node", "line", "transformer", "shunt", "source", "sym_gen", "asym_gen", "sym_load", "asym_load",
-                   "voltage_regulator", "asym_line", "generic_branch", "link", "three_winding_transformer")
+                   "voltage_regulator", "asym_line", "generic_branch", "link", "three_winding_transformer",
+                   "transformer_tap_regulator")
 UPDATABLE = ("line", "transformer", "shunt", "source", "sym_gen", "asym_gen", "sym_load", "asym_load", "voltage_regulator",
-             "asym_line", "generic_branch", "link", "three_winding_transformer")
+             "asym_line", "generic_branch", "link", "three_winding_transformer", "transformer_tap_regulator")
 
 
 def initialize_array(kind: str, component: str, shape, sym: bool = True):
@@ -130,6 +139,8 @@ assert UPDATE["three_winding_transformer"].itemsize == 8
 assert SYM_OUTPUT["three_winding_transformer"].itemsize == 136 and ASYM_OUTPUT["three_winding_transformer"].itemsize == 328
 assert INPUT["voltage_regulator"].itemsize == 40 and UPDATE["voltage_regulator"].itemsize == 32
 assert SYM_OUTPUT["voltage_regulator"].itemsize == 8
+assert INPUT["transformer_tap_regulator"].itemsize == 48 and UPDATE["transformer_tap_regulator"].itemsize == 40
+assert SYM_OUTPUT["transformer_tap_regulator"].itemsize == 8
 assert INPUT["line"].itemsize == 88 and INPUT["transformer"].itemsize == 168 and INPUT["source"].itemsize == 56
 assert UPDATE["sym_load"].itemsize == 24 and UPDATE["asym_load"].itemsize == 56
 assert SYM_OUTPUT["node"].itemsize == 48 and ASYM_OUTPUT["node"].itemsize == 128

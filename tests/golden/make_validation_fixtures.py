@@ -1,5 +1,7 @@
 """Collects the reference's power-flow validation cases (tests/data/power_flow/**) whose components are in the PF subset
-this repo implements into ONE fixture file, tests/golden/power_flow_cases.json.
+this repo implements into tests/golden/power_flow_cases.json, and the cases of the automatic tap changer
+(automatic-tap-regulator/*, params.tap_changing_strategy; cases that expect MaxIterationReached keep their `raises` entry) into
+tests/golden/tap_regulator_cases.json.
 
 Run here (the build container has /root/reference; the GPU box does not):
     python tests/golden/make_validation_fixtures.py
@@ -16,10 +18,13 @@ SUPPORTED = {"node", "line", "transformer", "source", "shunt", "sym_load", "sym_
              "voltage_regulator", "asym_line", "generic_branch", "link", "three_winding_transformer"}
 IGNORED_INPUT = {"fault", "sym_voltage_sensor", "sym_power_sensor", "asym_voltage_sensor", "asym_power_sensor"}  # not used by PF
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "power_flow_cases.json")
+OUT_TAP = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tap_regulator_cases.json")
+TAP_SUPPORTED = SUPPORTED | {"transformer_tap_regulator"}
 
 
 def main():
     cases = {}
+    tap_cases = {}
     skipped = {}
     for dirpath, _, files in sorted(os.walk(REF)):
         if "params.json" not in files or "input.json" not in files:
@@ -28,22 +33,26 @@ def main():
         params = json.load(open(os.path.join(dirpath, "params.json")))
         inp = json.load(open(os.path.join(dirpath, "input.json")))
         comps = set(inp["data"].keys())
-        unsupported = comps - SUPPORTED - IGNORED_INPUT
+        is_tap = "tap_changing_strategy" in params
+        unsupported = comps - (TAP_SUPPORTED if is_tap else SUPPORTED) - IGNORED_INPUT
         if unsupported:
             skipped[name] = "unsupported components: " + ", ".join(sorted(unsupported))
             continue
-        if "raises" in params or "xfail" in params or "tap_changing_strategy" in params:
-            skipped[name] = "expects an error / optimizer"
+        if "xfail" in params or ("raises" in params and not is_tap):
+            skipped[name] = "expects an error / known failure of the reference"
             continue
         case = {"params": params, "input": inp}
         for f in ("update_batch", "sym_output", "asym_output", "sym_output_batch", "asym_output_batch"):
             p = os.path.join(dirpath, f + ".json")
             if os.path.exists(p):
                 case[f] = json.load(open(p))
-        cases[name] = case
+        (tap_cases if is_tap else cases)[name] = case
     json.dump({"source": "PowerGridModel/power-grid-model tests/data/power_flow (MPL-2.0)", "cases": cases, "skipped": skipped},
               open(OUT, "w"), separators=(",", ":"))
+    json.dump({"source": "PowerGridModel/power-grid-model tests/data/power_flow/automatic-tap-regulator (MPL-2.0)", "cases": tap_cases},
+              open(OUT_TAP, "w"), separators=(",", ":"))
     print(f"{len(cases)} cases -> {OUT} ({os.path.getsize(OUT)} bytes); skipped {len(skipped)}")
+    print(f"{len(tap_cases)} tap changer cases -> {OUT_TAP} ({os.path.getsize(OUT_TAP)} bytes)")
     for k, v in skipped.items():
         print("  skipped", k, ":", v)
 

@@ -1,0 +1,56 @@
+"""Automatic tap changer (model_tap.cpp) against the reference's own validation cases
+(tests/data/power_flow/automatic-tap-regulator/*, stored in tests/golden/tap_regulator_cases.json): tap positions, voltages and
+flows of the final power flow; cases the reference expects to end in MaxIterationReached must fail here as well."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import pgm_b200
+import validation_cases as vc
+
+pytestmark = pytest.mark.gpu
+
+CASES = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tap_regulator_cases.json")))["cases"]
+RUNS = [(n, s, m, b) for n, c in sorted(CASES.items()) for s, m, b in vc.case_runs(c)]
+
+
+@pytest.mark.parametrize("name,sym,method,batch", RUNS)
+def test_tap_regulator_validation_case(name, sym, method, batch):
+    case = CASES[name]
+    params = case["params"]
+    model = pgm_b200.PowerGridModel(vc.to_numpy(case["input"], "input"))
+    kw = dict(symmetric=sym, calculation_method=method, tap_changing_strategy=params["tap_changing_strategy"])
+    kind = "sym_output" if sym else "asym_output"
+    update = None
+    if batch:
+        update = vc.batch_update_arrays(vc.to_numpy(case["update_batch"], "update"))
+        kw["update_data"] = update
+    if "raises" in params:
+        with pytest.raises(pgm_b200.PgmB200Error, match="Maximum number of iterations reached"):
+            model.calculate_power_flow(**kw)
+        # the search left the model as it was: the plain power flow still runs and the taps are the input's
+        plain = model.calculate_power_flow(symmetric=sym, calculation_method=method, update_data=update)
+        assert (plain["transformer_tap_regulator"]["tap_pos"] == -128).all()
+        return
+    result = model.calculate_power_flow(**kw)
+    rtol, atol = params["rtol"], params["atol"]
+    if batch:
+        expected = vc.to_numpy(case[kind + "_batch"], kind)
+        for s, exp in enumerate(expected):
+            vc.compare_result({c: result[c][s] for c in exp}, exp, rtol, atol)
+    else:
+        vc.compare_result(result, vc.to_numpy(case[kind], kind), rtol, atol)
+    # a second run gives the same answer: the tap positions of the model were put back
+    again = model.calculate_power_flow(**kw)
+    for c in result:
+        for f in result[c].dtype.names:
+            assert np.array_equal(result[c][f], again[c][f], equal_nan=result[c][f].dtype.kind == "f"), (c, f)
+
+
+def test_disabled_strategy_gives_null_regulator_output():
+    case = CASES["automatic-tap-regulator/single-trafo-any-valid-tap"]
+    model = pgm_b200.PowerGridModel(vc.to_numpy(case["input"], "input"))
+    out = model.calculate_power_flow()["transformer_tap_regulator"]
+    assert (out["energized"] == 0).all() and (out["tap_pos"] == -128).all() and (out["id"] >= 0).all()

@@ -165,7 +165,12 @@ def test_unsupported_components_and_options_are_refused_loudly():
     regulator = np.zeros(1, dtype=np.dtype([("id", "<i4"), ("regulated_object", "<i4"), ("status", "i1"), ("control_side", "i1"),
                                             ("u_set", "<f8"), ("u_band", "<f8"), ("line_drop_compensation_r", "<f8"),
                                             ("line_drop_compensation_x", "<f8")], align=True))
-    with pytest.raises(pgm_core.PowerGridError, match="'transformer_tap_regulator' is not built by pgm_b200"):
+    # a tap regulator must regulate a transformer (main_core/input.hpp:168-214): object 0 is a node, 12345 does not exist
+    regulator["id"] = 777
+    with pytest.raises(pgm_core.PowerGridError, match="transformer_tap_regulator regulator is not supported for object with ID 0"):
+        pgm_core.PowerGridModel({**data, "transformer_tap_regulator": regulator})
+    regulator["regulated_object"] = 12345
+    with pytest.raises(pgm_core.PowerGridError, match="The id cannot be found: 12345"):
         pgm_core.PowerGridModel({**data, "transformer_tap_regulator": regulator})
     # sensors / faults may be present: power flow ignores them
     pgm_core.PowerGridModel({**data, "sym_voltage_sensor": np.zeros(1, dtype=np.dtype([("id", "<i4"), ("pad", "V28")]))})
@@ -221,7 +226,7 @@ def test_meta_data_tables_match_the_struct_layouts():
             for name in dt.names:
                 assert got.fields[name][1] == dt.fields[name][1] and got.fields[name][0] == dt.fields[name][0], (ds, comp, name)
             n_checked += 1
-    assert n_checked == 14 + 13 + 14 + 14
+    assert n_checked == 15 + 14 + 15 + 15
     # sizes the reference states for components outside the engine (auxiliary/static_asserts, SURVEY appendix B conventions)
     assert meta["input"]["link"].itemsize == 16 and meta["update"]["node"].itemsize == 4
     assert meta["input"]["three_winding_transformer"].names[:4] == ("id", "node_1", "node_2", "node_3")
