@@ -54,3 +54,34 @@ def test_disabled_strategy_gives_null_regulator_output():
     model = pgm_b200.PowerGridModel(vc.to_numpy(case["input"], "input"))
     out = model.calculate_power_flow()["transformer_tap_regulator"]
     assert (out["energized"] == 0).all() and (out["tap_pos"] == -128).all() and (out["id"] >= 0).all()
+
+
+PGM_RUNS = [r for r in RUNS if r[0].split("/")[-1] in (
+    "pgm-automatic-tap-line-drop-max", "auto-tap-changer-with-transformer-into-itself", "step-up-transformer-fast-any-tap",
+    "auto-tap-changer-meshed-any-max-iter", "trafo-control-tap-same-side-min-voltage-tap")]
+
+
+@pytest.mark.parametrize("name,sym,method,batch", PGM_RUNS)
+def test_tap_changer_through_pgm_calculate(name, sym, method, batch):
+    """the same search behind the reference's C API names: PGM_set_tap_changing_strategy + PGM_calculate"""
+    from pgm_b200 import pgm_core
+
+    case = CASES[name]
+    params = case["params"]
+    strategy = pgm_b200.TAP_STRATEGIES[params["tap_changing_strategy"]]
+    model = pgm_core.PowerGridModel(vc.to_numpy(case["input"], "input"))
+    kind = "sym_output" if sym else "asym_output"
+    kw = dict(symmetric=sym, calculation_method=method, tap_changing_strategy=strategy)
+    if batch:
+        kw["update_data"] = vc.batch_update_arrays(vc.to_numpy(case["update_batch"], "update"))
+    if "raises" in params:
+        with pytest.raises(pgm_core.PowerGridError, match="Maximum number of iterations reached"):
+            model.calculate_power_flow(**kw)
+        return
+    res = model.calculate_power_flow(**kw)
+    assert "transformer_tap_regulator" in res
+    if batch:
+        for s, exp in enumerate(vc.to_numpy(case[kind + "_batch"], kind)):
+            vc.compare_result({k: v[s] for k, v in res.items()}, exp, params["rtol"], params["atol"])
+    else:
+        vc.compare_result(res, vc.to_numpy(case[kind], kind), params["rtol"], params["atol"])
