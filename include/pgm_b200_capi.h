@@ -13,11 +13,13 @@
  *   - the meta-data tables (PGM_meta_*) of every dataset and component of the reference, PGM_create_buffer / PGM_buffer_* and
  *     the dataset info calls, so a client sizes and fills its buffers the way the reference's wrapper does;
  *   - components: node, line, asym_line, link, generic_branch, transformer, three_winding_transformer, shunt, source, sym_gen,
- *     asym_gen, sym_load, asym_load, voltage_regulator; sensors and faults may be present in the input dataset and are ignored by power flow like in the
- *     reference; any other component is PGM_regular_error at PGM_create_model;
- *   - tap_changing_strategy: any valid value (the model cannot hold a transformer_tap_regulator, so it is the plain power flow).
+ *     asym_gen, sym_load, asym_load, voltage_regulator, transformer_tap_regulator; sensors and faults may be present in the input
+ *     dataset and are ignored by power flow like in the reference;
+ *   - tap_changing_strategy: the automatic tap changer of the reference (optimizer/tap_position_optimizer.hpp) around the power
+ *     flows of every scenario: any_valid_tap, min_voltage_tap, max_voltage_tap, fast_any_tap;
  *   - JSON and msgpack (de)serialization of datasets and the writable datasets of the deserializer (serialization.h, dataset.h).
- * Not provided: the PGM_def_* pointer constants of dataset_definitions.h (the meta data is reachable by name through PGM_meta_*).
+ *   - the PGM_def_* pointer constants of dataset_definitions.h (include/pgm_b200_dataset_definitions.h, 859 symbols).
+ * Not provided: calculation types other than power flow (state estimation, short circuit).
  * There is no CPU fallback: PGM_calculate on a host without a CUDA device reports PGM_regular_error.
  */
 #ifndef PGM_B200_CAPI_H
