@@ -437,7 +437,7 @@ int orc_model_export_math(void* bag, void* model, int sym) {
 // status[s] in {0 ok, 1 diverged, 2 singular, 3 other}; returns number of failed scenarios (or -1 on setup error)
 int64_t orc_model_calculate(void* bag, void* model, int sym, int method, double err_tol, int64_t max_iter,
                             int64_t threading, int reuse_ic_factorization, BatchUpdate const* update, void const* out,
-                            int64_t* n_iter, int32_t* status) {
+                            int64_t* n_iter, int32_t* status, int tap_strategy) {
     auto& m = *static_cast<ModelHandle*>(model)->model;
     auto* b = static_cast<Bag*>(bag);
     CalcOptions opt;
@@ -446,6 +446,7 @@ int64_t orc_model_calculate(void* bag, void* model, int sym, int method, double 
     opt.max_iter = max_iter;
     opt.threading = threading;
     opt.reuse_ic_factorization = reuse_ic_factorization != 0;
+    opt.tap_strategy = tap_strategy; // PGM_TapChangingStrategy; not 0: automatic tap changer around every scenario's power flows
     int64_t failed = 0;
     auto run = [&]<int B>() {
         auto const& o = *static_cast<BatchOutput<B> const*>(out);

@@ -888,6 +888,57 @@ struct LoadGen : ApplianceBase {
 };
 
 // component/voltage_regulator.hpp:22-101, component/regulator.hpp
+// component/transformer_tap_regulator.hpp:23-99 + regulator.hpp:15-60; auxiliary/{input,update,output}.hpp for the structs
+struct TransformerTapRegulatorInput {
+    ID id, regulated_object;
+    IntS status, control_side; // ControlSide: from = side_1 = 0, to = side_2 = 1, side_3 = 2
+    double u_set, u_band, line_drop_compensation_r, line_drop_compensation_x;
+};
+struct TransformerTapRegulatorUpdate {
+    ID id;
+    IntS status;
+    double u_set, u_band, line_drop_compensation_r, line_drop_compensation_x;
+};
+struct TransformerTapRegulatorOutput {
+    ID id;
+    IntS energized;
+    IntS tap_pos;
+};
+static_assert(sizeof(TransformerTapRegulatorInput) == 48 && sizeof(TransformerTapRegulatorUpdate) == 40 &&
+              sizeof(TransformerTapRegulatorOutput) == 8);
+struct TransformerTapRegulatorCalcParam { // calculation_parameters.hpp
+    double u_set, u_band;
+    cplx z_compensation;
+    IntS status;
+};
+struct TransformerTapRegulator {
+    ID id{}, regulated_object{};
+    bool regulates_branch3{}; // regulated_object_type: branch (transformer) or branch3 (three-winding transformer)
+    bool status{};
+    IntS control_side{};
+    double u_rated{}; // of the node at the control side
+    double u_set{}, u_band{}, line_drop_compensation_r{}, line_drop_compensation_x{};
+    TransformerTapRegulator(TransformerTapRegulatorInput const& in, bool branch3, double u_rated_control)
+        : id{in.id}, regulated_object{in.regulated_object}, regulates_branch3{branch3}, status{in.status != 0},
+          control_side{in.control_side}, u_rated{u_rated_control}, u_set{in.u_set}, u_band{in.u_band},
+          line_drop_compensation_r{in.line_drop_compensation_r}, line_drop_compensation_x{in.line_drop_compensation_x} {}
+    void update(TransformerTapRegulatorUpdate const& u) { // :41-50; Regulator::set_status takes the value as it is
+        status = static_cast<bool>(u.status);
+        if (!is_nan(u.u_set)) u_set = u.u_set;
+        if (!is_nan(u.u_band)) u_band = u.u_band;
+        if (!is_nan(u.line_drop_compensation_r)) line_drop_compensation_r = u.line_drop_compensation_r;
+        if (!is_nan(u.line_drop_compensation_x)) line_drop_compensation_x = u.line_drop_compensation_x;
+    }
+    template <int B> TransformerTapRegulatorCalcParam calc_param() const { // :76-87
+        double const z_base = u_rated * u_rated / base_power<B>;
+        cplx const z{is_nan(line_drop_compensation_r) ? 0.0 : line_drop_compensation_r,
+                     is_nan(line_drop_compensation_x) ? 0.0 : line_drop_compensation_x};
+        return {u_set / u_rated, u_band / u_rated, z / z_base, static_cast<IntS>(status)};
+    }
+    TransformerTapRegulatorOutput get_null_output() const { return {id, 0, na_IntS}; }
+    TransformerTapRegulatorOutput get_output(IntS tap_pos) const { return {id, 1, tap_pos}; } // a regulator is always energized
+};
+
 struct VoltageRegulator {
     ID id{};
     ID regulated_object{};

@@ -8,12 +8,15 @@
 //   main_model_impl.hpp           calculate_ :288-315, update_component :139-160, restore_components :254-261
 //   job_dispatch.hpp              batch_calculation :37-68, single_thread_job :88-138, job_dispatch :142-172
 //   job_adapter.hpp               setup_impl / winddown_impl :127-139
+//   main_model_impl.hpp           calculate_with_optimizer :318-348 (automatic tap changer, tap_optimizer.hpp);
+//   main_core/input.hpp           transformer tap regulators :168-214 ; main_core/output.hpp :381-396
 // Component storage order (all_components.hpp:36-39): Node, Line, Transformer, Shunt, Source, SymGenerator,
 // AsymGenerator, SymLoad, AsymLoad; Branch = Line..Transformer; GenericLoadGen = SymGen, AsymGen, SymLoad, AsymLoad.
 #pragma once
 
 #include "components.hpp"
 #include "pf_solvers.hpp"
+#include "tap_optimizer.hpp"
 #include "topology.hpp"
 
 #include <set>
@@ -51,6 +54,8 @@ struct ModelInput {
     LinkInput const* link;
     Idx n_three_winding_transformer;
     ThreeWindingTransformerInput const* three_winding_transformer;
+    Idx n_transformer_tap_regulator;
+    TransformerTapRegulatorInput const* transformer_tap_regulator;
 };
 
 // one buffer of a batch update dataset: uniform (indptr == nullptr, n_per_scenario elements each) or sparse
@@ -79,6 +84,7 @@ struct BatchUpdate {
     UpdateBuffer<BranchUpdate> generic_branch;
     UpdateBuffer<BranchUpdate> link;
     UpdateBuffer<ThreeWindingTransformerUpdate> three_winding_transformer;
+    UpdateBuffer<TransformerTapRegulatorUpdate> transformer_tap_regulator;
 };
 // output buffers, each [n_scenarios][n_component] or nullptr when the caller does not want that component
 template <int B> struct BatchOutput {
@@ -96,6 +102,7 @@ template <int B> struct BatchOutput {
     BranchOutput<B>* generic_branch;
     BranchOutput<B>* link;
     Branch3Output<B>* three_winding_transformer;
+    TransformerTapRegulatorOutput* transformer_tap_regulator;
 };
 
 struct CalcOptions {
@@ -104,6 +111,7 @@ struct CalcOptions {
     Idx max_iter{20};
     Idx threading{-1};
     bool reuse_ic_factorization{false};
+    int tap_strategy{0}; // PGM_TapChangingStrategy: 0 disabled, 1 any_valid_tap, 2 min_voltage_tap, 3 max_voltage_tap, 4 fast_any_tap
 };
 
 class Model {
@@ -187,6 +195,38 @@ class Model {
         for (size_t i = 0; i != shunts_.size(); ++i) shunt_idx_[shunts_[i].id] = static_cast<Idx>(i);
         for (size_t i = 0; i != sources_.size(); ++i) source_idx_[sources_[i].id] = static_cast<Idx>(i);
         for (size_t i = 0; i != load_gens_.size(); ++i) load_gen_idx_[load_gens_[i].id] = static_cast<Idx>(i);
+        // transformer tap regulators (main_core/input.hpp:168-214): the regulated object must be a transformer or a three-winding
+        // transformer, the control side one of its terminals; at most one regulator per object
+        {
+            std::set<ID> tap_regulated;
+            for (Idx i = 0; i != in.n_transformer_tap_regulator; ++i) {
+                auto const& r = in.transformer_tap_regulator[i];
+                add_id(r.id);
+                if (all_ids_.find(r.regulated_object) == all_ids_.end()) {
+                    throw PgmError{"The id cannot be found: " + std::to_string(r.regulated_object) + "\n"};
+                }
+                auto bad_side = [&] {
+                    return PgmError{"transformer_tap_regulator item retrieval is not implemented for ControlSide #" +
+                                    std::to_string(static_cast<int>(r.control_side)) + "!\n"};
+                };
+                if (auto it = transformer_idx_.find(r.regulated_object); it != transformer_idx_.end()) {
+                    if (r.control_side != 0 && r.control_side != 1) throw bad_side();
+                    auto const& t = transformers_[it->second];
+                    tap_regulators_.emplace_back(r, false, u_rated(r.control_side == 0 ? t.from_node : t.to_node));
+                } else if (auto it3 = t3w_idx_.find(r.regulated_object); it3 != t3w_idx_.end()) {
+                    if (r.control_side < 0 || r.control_side > 2) throw bad_side();
+                    tap_regulators_.emplace_back(r, true, t3w_[it3->second].u_rated[r.control_side]);
+                } else {
+                    throw PgmError{"transformer_tap_regulator regulator is not supported for object with ID " +
+                                   std::to_string(r.regulated_object) + "\n"};
+                }
+                tap_regulated.insert(r.regulated_object);
+                tap_regulator_idx_[r.id] = i;
+            }
+            if (static_cast<Idx>(tap_regulated.size()) != in.n_transformer_tap_regulator) {
+                throw PgmError{"There are objects regulated by more than one regulator. Maximum one regulator is allowed."};
+            }
+        }
         // voltage regulators (main_core/input.hpp:216-241): the regulated object must be a load / generator, at most one
         // regulator per object
         std::set<ID> regulated;
@@ -212,6 +252,9 @@ class Model {
     // ---- single calculation ----
     // calculation_preparation.hpp:163-225 check_state_validity + main_model_impl.hpp:362-366, 400-420
     template <int B> void check_regulators(CalcOptions const& opt) const {
+        if (!regulators_.empty() && !tap_regulators_.empty()) { // calculation_preparation.hpp:219-222
+            throw PgmError{"The combination of voltage regulators and transformer tap regulators is not supported in the same model."};
+        }
         if (regulators_.empty()) return;
         if (opt.method != CalculationMethod::newton_raphson && opt.method != CalculationMethod::default_method) {
             throw PgmError{"The calculation method is invalid for this calculation!"};
@@ -249,20 +292,165 @@ class Model {
         }
     }
 
-    template <int B> void calculate(CalcOptions const& opt, BatchOutput<B> const& out, Idx scenario, bool cache_run = false) {
+    template <int B> std::vector<SolverOutput<B>> solve(CalcOptions const& opt, bool cache_run = false) {
         check_regulators<B>(opt);
         prepare_solvers<B>();
         auto const pf_input = prepare_power_flow_input<B>();
         auto& ys = y_bus<B>();
         auto& solvers = math_solvers<B>();
         std::vector<SolverOutput<B>> so;
-        last_num_iter_ = 0;
         for (size_t g = 0; g != ys.size(); ++g) {
             so.push_back(solvers[g].run_power_flow(pf_input[g], opt.err_tol, opt.max_iter, opt.method, ys[g],
                                                    opt.reuse_ic_factorization, cache_run));
             last_num_iter_ = std::max(last_num_iter_, so.back().num_iter);
         }
+        return so;
+    }
+    template <int B> void calculate(CalcOptions const& opt, BatchOutput<B> const& out, Idx scenario, bool cache_run = false) {
+        last_num_iter_ = 0;
+        if (opt.tap_strategy != 0 && !cache_run) {
+            calculate_with_optimizer<B>(opt, out, scenario);
+            return;
+        }
+        auto const so = solve<B>(opt, cache_run);
         output_result<B>(so, out, scenario);
+    }
+
+    // ---- automatic tap changer (main_model_impl.hpp:318-348, tap_optimizer.hpp) ----
+    // build_transformer_graph (tap_position_optimizer.hpp:143-305): Transformer, ThreeWindingTransformer, Line, Link edges
+    tap::RankedGroups rank_transformers() const {
+        std::vector<tap::GraphEdge> edges;
+        auto node = [this](ID id) { return node_idx_.at(id); };
+        auto both_ways = [&](Idx a, Idx b) {
+            edges.push_back({a, b, 0, {-1, -1}, na_IntID});
+            edges.push_back({b, a, 0, {-1, -1}, na_IntID});
+        };
+        auto regulator_of = [this](ID object) -> TransformerTapRegulator const* {
+            for (auto const& r : tap_regulators_)
+                if (r.status && r.regulated_object == object) return &r;
+            return nullptr;
+        };
+        for (size_t i = 0; i != transformers_.size(); ++i) {
+            auto const& t = transformers_[i];
+            if (!t.from_status || !t.to_status) continue;
+            if (auto const* r = regulator_of(t.id)) {
+                Idx const control = node(r->control_side == 0 ? t.from_node : t.to_node);
+                Idx const other = node(r->control_side == 0 ? t.to_node : t.from_node);
+                edges.push_back({other, control, 1, {0, static_cast<Idx>(i)}, t.id});
+            } else {
+                both_ways(node(t.from_node), node(t.to_node));
+            }
+        }
+        for (size_t i = 0; i != t3w_.size(); ++i) {
+            auto const& t = t3w_[i];
+            Idx const nodes[3] = {node(t.in.node_1), node(t.in.node_2), node(t.in.node_3)};
+            auto const* r = regulator_of(t.in.id);
+            constexpr int combinations[3][2] = {{0, 1}, {0, 2}, {1, 2}};
+            for (auto const& c : combinations) {
+                int const first = c[0], second = c[1];
+                if (!t.status[first] || !t.status[second]) continue;
+                bool const tap_at_first = t.in.tap_side == first;
+                if (r != nullptr && (tap_at_first || t.in.tap_side == second)) {
+                    bool const tap_at_control = r->control_side == t.in.tap_side;
+                    Idx const tap_side_node = tap_at_first ? nodes[first] : nodes[second];
+                    Idx const non_tap_side_node = tap_at_first ? nodes[second] : nodes[first];
+                    edges.push_back({tap_at_control ? non_tap_side_node : tap_side_node, tap_at_control ? tap_side_node : non_tap_side_node,
+                                     1, {1, static_cast<Idx>(i)}, t.in.id});
+                } else {
+                    both_ways(nodes[first], nodes[second]);
+                }
+            }
+        }
+        for (auto const& l : lines_)
+            if (l.from_status && l.to_status) both_ways(node(l.from_node), node(l.to_node));
+        for (auto const& l : links_)
+            if (l.from_status && l.to_status) both_ways(node(l.from_node), node(l.to_node));
+        std::vector<char> is_source(nodes_.size(), 0);
+        for (auto const& src : sources_) is_source[node(src.node)] = src.status ? 1 : 0;
+        return tap::rank_transformers(n_node(), std::move(edges), is_source);
+    }
+
+    template <int B> struct TapHost {
+        Model& m;
+        CalcOptions opt;
+        std::vector<SolverOutput<B>> so;
+        IntS tap_pos(tap::Regulated const& r) const {
+            return r.index.group == 0 ? m.transformers_[r.index.pos].tap_pos : m.t3w_[r.index.pos].tap_pos;
+        }
+        void set_taps(std::vector<std::pair<tap::Regulated const*, IntS>> const& updates) {
+            for (auto const& [r, pos] : updates) {
+                bool const changed = r->index.group == 0 ? m.transformers_[r->index.pos].set_tap(pos) : m.t3w_[r->index.pos].set_tap(pos);
+                if (changed) m.param_valid_[0] = m.param_valid_[1] = false;
+            }
+        }
+        void calculate(CalculationMethod method) {
+            CalcOptions o = opt;
+            o.method = method;
+            so = m.template solve<B>(o);
+        }
+        // u_pu / i_pu of the controlled node (:628-700), NodeState <=> TransformerTapRegulatorCalcParam (:702-731)
+        tap::Comparison compare(tap::Regulated const& r) const {
+            auto const& reg = m.tap_regulators_[r.regulator];
+            Idx2D bus{-1, -1};
+            CVec<B> i_pu{};
+            if (r.index.group == 0) {
+                auto const& t = m.transformers_[r.index.pos];
+                bus = m.coup_.node[m.node_idx_.at(reg.control_side == 0 ? t.from_node : t.to_node)];
+                Idx2D const br = m.coup_.branch[m.branch_seq_transformer(r.index.pos)];
+                if (br.group != -1) i_pu = reg.control_side == 0 ? so[br.group].branch[br.pos].i_f : so[br.group].branch[br.pos].i_t;
+            } else {
+                auto const& t = m.t3w_[r.index.pos];
+                ID const node_id = reg.control_side == 0 ? t.in.node_1 : reg.control_side == 1 ? t.in.node_2 : t.in.node_3;
+                bus = m.coup_.node[m.node_idx_.at(node_id)];
+                auto const& b3 = m.coup_.branch3[r.index.pos];
+                if (b3.first != -1) i_pu = so[b3.first].branch[b3.second[reg.control_side]].i_f;
+            }
+            if (bus.group == -1) return {false, 0};
+            auto const param = reg.template calc_param<B>();
+            CVec<B> const& u = so[bus.group].u[bus.pos];
+            double v = 0.0;
+            for (int p = 0; p != B; ++p) v += cabs(u(p) + param.z_compensation * i_pu(p));
+            v /= B; // mean_val(cabs(u_compensated))
+            double const lower = param.u_set - 0.5 * param.u_band, upper = param.u_set + 0.5 * param.u_band;
+            return {true, v < lower ? -1 : v > upper ? 1 : 0};
+        }
+    };
+
+    template <int B> void calculate_with_optimizer(CalcOptions const& opt, BatchOutput<B> const& out, Idx scenario) {
+        prepare_topology();
+        tap::RankedGroups const ranked = rank_transformers();
+        std::vector<std::vector<tap::Regulated>> order;
+        for (auto const& group : ranked) {
+            order.emplace_back();
+            for (Idx2D const& idx : group) {
+                ID const object = idx.group == 0 ? transformers_[idx.pos].id : t3w_[idx.pos].in.id;
+                Idx regulator = -1;
+                for (size_t k = 0; k != tap_regulators_.size() && regulator < 0; ++k)
+                    if (tap_regulators_[k].regulated_object == object) regulator = static_cast<Idx>(k);
+                IntS const tap_side = idx.group == 0 ? static_cast<IntS>(transformers_[idx.pos].tap_side) : t3w_[idx.pos].in.tap_side;
+                IntS const tap_min = idx.group == 0 ? transformers_[idx.pos].tap_min : t3w_[idx.pos].in.tap_min;
+                IntS const tap_max = idx.group == 0 ? transformers_[idx.pos].tap_max : t3w_[idx.pos].in.tap_max;
+                order.back().push_back({idx, regulator, tap_min, tap_max, tap_regulators_[regulator].control_side == tap_side});
+            }
+        }
+        TapHost<B> host{*this, opt, {}};
+        // cache_states / update_state(cache) (:966-984, :1379-1395): the tap positions come back whatever happens
+        std::vector<std::pair<tap::Regulated const*, IntS>> cache;
+        tap::TapPositionOptimizer<TapHost<B>> optimizer{host, order, static_cast<tap::Strategy>(opt.tap_strategy)};
+        for (auto const& group : optimizer.order())
+            for (auto const& r : group) cache.emplace_back(&r, host.tap_pos(r));
+        try {
+            optimizer.optimize(opt.method);
+        } catch (...) {
+            host.set_taps(cache);
+            throw;
+        }
+        tap_positions_found_.assign(tap_regulators_.size(), na_IntS);
+        for (auto const& group : optimizer.order())
+            for (auto const& r : group) tap_positions_found_[r.regulator] = host.tap_pos(r);
+        host.set_taps(cache);
+        output_result<B>(host.so, out, scenario);
+        tap_positions_found_.clear();
     }
     Idx last_num_iter() const { return last_num_iter_; }
 
@@ -345,6 +533,9 @@ class Model {
     std::vector<LoadGen> load_gens_; // sym_gen, asym_gen, sym_load, asym_load
     std::vector<VoltageRegulator> regulators_;
     std::unordered_map<ID, Idx> regulator_idx_;
+    std::vector<TransformerTapRegulator> tap_regulators_;
+    std::unordered_map<ID, Idx> tap_regulator_idx_;
+    std::vector<IntS> tap_positions_found_; // per tap regulator, filled by the optimizer for output_result (na: not regulated)
     Idx n_sym_gen_{}, n_asym_gen_{}, n_sym_load_{}, n_asym_load_{};
     std::unordered_map<ID, Idx> all_ids_, node_idx_, line_idx_, transformer_idx_, shunt_idx_, source_idx_, load_gen_idx_;
 
@@ -724,6 +915,14 @@ class Model {
                     m.group == -1 ? regulators_[i].get_null_output() : regulators_[i].get_output(so[m.group].voltage_regulator[m.pos]);
             }
         }
+        if (out.transformer_tap_regulator != nullptr) { // main_core/output.hpp:381-396
+            Idx const n = static_cast<Idx>(tap_regulators_.size());
+            for (Idx i = 0; i != n; ++i) {
+                IntS const tap = i < static_cast<Idx>(tap_positions_found_.size()) ? tap_positions_found_[i] : na_IntS;
+                out.transformer_tap_regulator[scenario * n + i] =
+                    tap == na_IntS ? tap_regulators_[i].get_null_output() : tap_regulators_[i].get_output(tap);
+            }
+        }
     }
 
     // ---- update / restore ----
@@ -738,6 +937,7 @@ class Model {
         std::vector<std::pair<Idx, Source>> sources;
         std::vector<std::pair<Idx, LoadGen>> load_gens;
         std::vector<std::pair<Idx, VoltageRegulator>> regulators;
+        std::vector<std::pair<Idx, TransformerTapRegulator>> tap_regulators;
         bool topo{false}, param{false};
     };
     void mark(bool topo, bool param, Saved& saved) {
@@ -878,6 +1078,14 @@ class Model {
                 regulators_[i].update(*p); // UpdateChange{false, false} (voltage_regulator.hpp:35-41)
             }
         }
+        {
+            auto [b, e] = upd.transformer_tap_regulator.scenario(s);
+            for (auto p = b; p != e; ++p) {
+                Idx const i = find_seq(*p, p - b, e - b, static_cast<Idx>(tap_regulators_.size()), tap_regulator_idx_, 0);
+                saved.tap_regulators.emplace_back(i, tap_regulators_[i]);
+                tap_regulators_[i].update(*p); // UpdateChange{false, false} (transformer_tap_regulator.hpp:41-50)
+            }
+        }
     }
     void restore(Saved const& saved) {
         // restore in reverse order so repeated updates of one component end at the original value
@@ -893,6 +1101,7 @@ class Model {
         for (auto it = saved.sources.rbegin(); it != saved.sources.rend(); ++it) sources_[it->first] = it->second;
         for (auto it = saved.load_gens.rbegin(); it != saved.load_gens.rend(); ++it) load_gens_[it->first] = it->second;
         for (auto it = saved.regulators.rbegin(); it != saved.regulators.rend(); ++it) regulators_[it->first] = it->second;
+        for (auto it = saved.tap_regulators.rbegin(); it != saved.tap_regulators.rend(); ++it) tap_regulators_[it->first] = it->second;
         if (saved.topo) topo_valid_ = false;
         if (saved.param) param_valid_[0] = param_valid_[1] = false;
     }

@@ -62,6 +62,11 @@ struct IterationDiverge : std::runtime_error {
                              ", error tolerance: " + std::to_string(tol) + ".\n"},
           num_iter{n},
           max_dev{dev} {}
+    explicit IterationDiverge(std::string const& msg) : std::runtime_error{msg}, num_iter{0}, max_dev{0.0} {}
+};
+// common/exception.hpp:113-117 (thrown by the tap position optimizer; caught wherever IterationDiverge is)
+struct MaxIterationReached : IterationDiverge {
+    explicit MaxIterationReached(std::string const& msg = "") : IterationDiverge{"Maximum number of iterations reached! " + msg + "\n"} {}
 };
 struct PgmError : std::runtime_error {
     using std::runtime_error::runtime_error;

@@ -202,6 +202,9 @@ Model::Model(double system_frequency, InputData const& in) : freq_{system_freque
 // (main_model_impl.hpp:362-366, 400-420)
 template <int B> void Model::check_regulators(ModelOptions const& opt) const {
     if (reg_in_.empty()) return;
+    if (!tap_reg_in_.empty()) { // check_state_validity, calculation_preparation.hpp:219-222
+        throw InvalidArgument("The combination of voltage regulators and transformer tap regulators is not supported in the same model.");
+    }
     if (opt.method != 1 && opt.method != -128) throw InvalidArgument("The calculation method is invalid for this calculation!\n");
     std::unordered_map<Idx, std::pair<ID, double>> node_ref; // node -> (regulator id, u_ref)
     for (size_t r = 0; r != reg_in_.size(); ++r) {

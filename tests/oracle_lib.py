@@ -246,7 +246,7 @@ class Model:
         return bag
 
     def calculate(self, sym=True, method="newton_raphson", err_tol=1e-8, max_iter=20, threading=-1, update=None,
-                  output_components=None, reuse_ic_factorization=False, out=None):
+                  output_components=None, reuse_ic_factorization=False, out=None, tap_changing_strategy=0):
         """update: None or dict component -> array of shape (n_scn, n_per) or {"data": flat, "indptr": ...}.
         Returns dict with per-component output arrays (n_scn, n_comp), n_iter, status, error.
         out: optional dict of preallocated output arrays to write into (the caller reuses them between calls, as a client of
@@ -293,7 +293,8 @@ class Model:
         failed = lib.orc_model_calculate(
             bag.h, self.h, C.c_int(int(sym)), C.c_int(METHODS[method]), C.c_double(err_tol), C.c_int64(max_iter),
             C.c_int64(threading), C.c_int(int(reuse_ic_factorization)), C.byref(bu) if bu is not None else None,
-            C.byref(bo), _p(n_iter), _p(status),
+            C.byref(bo), _p(n_iter), _p(status), C.c_int({"disabled": 0, "any_valid_tap": 1, "min_voltage_tap": 2, "max_voltage_tap": 3,
+                                                          "fast_any_tap": 4}.get(tap_changing_strategy, tap_changing_strategy)),
         )
         result["n_iter"] = n_iter
         result["status"] = status

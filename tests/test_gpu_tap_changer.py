@@ -85,3 +85,41 @@ def test_tap_changer_through_pgm_calculate(name, sym, method, batch):
             vc.compare_result({k: v[s] for k, v in res.items()}, exp, params["rtol"], params["atol"])
     else:
         vc.compare_result(res, vc.to_numpy(case[kind], kind), params["rtol"], params["atol"])
+
+
+def _regulated_benchmark_grid(extra_lv_regulators):
+    """BASELINE configs[1] grid with the reference benchmark's tap changer (fictional_grid_generator.hpp:615-633: one regulator
+    on the station transformer); optionally one more regulator on every MV/LV transformer (second rank)"""
+    grid = pgm_b200.FictionalGrid(seed=0, has_tap_changer=True, **pgm_b200.BENCHMARK_OPTION)
+    data = dict(grid.input_data)
+    if extra_lv_regulators:
+        trafo, node = data["transformer"], data["node"]
+        reg = pgm_b200.structs.initialize_array("input", "transformer_tap_regulator", len(trafo) - 1)
+        for k, t in enumerate(trafo[1:]):
+            u_rated = float(node["u_rated"][node["id"] == t["to_node"]][0])
+            reg[k] = (int(data["transformer_tap_regulator"]["id"][0]) + 1 + k, t["id"], 1, 1, 1.02 * u_rated,
+                      float(t["tap_size"]) * u_rated / float(t["u2"]) + 0.01 * u_rated, np.nan, np.nan)
+        data["transformer_tap_regulator"] = np.concatenate([data["transformer_tap_regulator"], reg])
+    return grid, data
+
+
+@pytest.mark.parametrize("sym,extra", [(True, False), (True, True), (False, False), (False, True)])
+@pytest.mark.parametrize("strategy", ["any_valid_tap", "min_voltage_tap", "max_voltage_tap", "fast_any_tap"])
+def test_tap_changer_on_the_benchmark_grid_equals_the_oracle(strategy, sym, extra):
+    """load-profile batch on the 2605-bus benchmark grid: every scenario's search ends at the oracle's tap positions, and the
+    final power flow agrees to the solver tolerance"""
+    import oracle_lib as orc
+    import parity
+
+    grid, data = _regulated_benchmark_grid(extra)
+    n_scn = 24 if sym else 8
+    update = grid.batch_update(n_scn, seed=3)
+    comps = ["node", "transformer", "transformer_tap_regulator", "source"]
+    ref = orc.Model(data).calculate(sym=sym, update=update, threading=0, tap_changing_strategy=strategy, output_components=comps)
+    assert ref["n_failed"] == 0, ref["error"]
+    model = pgm_b200.PowerGridModel(data)
+    res = model.calculate_power_flow(symmetric=sym, update_data=update, tap_changing_strategy=strategy, output_component_types=comps)
+    assert (model.status == 0).all()
+    assert np.array_equal(res["transformer_tap_regulator"]["tap_pos"], ref["transformer_tap_regulator"]["tap_pos"])
+    assert np.array_equal(res["transformer_tap_regulator"]["energized"], ref["transformer_tap_regulator"]["energized"])
+    parity.compare_outputs(res, ref, ["node", "transformer", "source"])
