@@ -1232,6 +1232,29 @@ int64_t Model::calculate_impl(ModelOptions const& opt, UpdateData const* update,
         std::vector<Idx> todo;
         bool todo_is_subset = false;
         std::vector<int32_t> status_local;
+        // a device pass solved the batch; `exact` are the scenarios the scenario-by-scenario route below recomputes
+        auto adopt_device_result = [&](int64_t r, std::vector<Idx> exact) {
+            failed = r;
+            for (Idx const s : exact) // placeholders of the scenarios that are recomputed below
+                if (status[s] != 0) --failed;
+            todo = std::move(exact);
+            todo_is_subset = true;
+            if (!todo.empty()) { // drop the placeholder messages
+                std::string kept;
+                size_t pos = 0;
+                while (pos < batch_message.size()) {
+                    size_t const end = batch_message.find('\n', pos);
+                    std::string const line = batch_message.substr(pos, end == std::string::npos ? std::string::npos : end - pos + 1);
+                    bool drop = false;
+                    for (Idx const s : todo)
+                        if (line.rfind("Error in batch #" + std::to_string(s) + ":", 0) == 0) drop = true;
+                    if (!drop) kept += line;
+                    if (end == std::string::npos) break;
+                    pos = end + 1;
+                }
+                batch_message = std::move(kept);
+            }
+        };
         if (structural && !source_param_change && !has_reg && opt.tap_strategy == 0 && (opt.method == 1 || opt.method == -128) && n > 0 &&
             (update->line.data != nullptr || update->transformer.data != nullptr) && std::getenv("PGMB_N1_EXACT") == nullptr) {
             prepare_engines<B>();
@@ -1264,28 +1287,24 @@ int64_t Model::calculate_impl(ModelOptions const& opt, UpdateData const* update,
                 outage_plan_ = nullptr;
                 if (r < 0) batch_message.clear(); // messages of parts that ran before the attempt was given up
                 t0 = Clock::now();
-                if (r >= 0) {
-                    failed = r;
-                    for (Idx const s : plan.exact) // placeholders of the scenarios that are recomputed below
-                        if (status[s] != 0) --failed;
-                    todo = std::move(plan.exact);
-                    todo_is_subset = true;
-                    if (!todo.empty()) { // drop the placeholder messages
-                        std::string kept;
-                        size_t pos = 0;
-                        while (pos < batch_message.size()) {
-                            size_t const end = batch_message.find('\n', pos);
-                            std::string const line = batch_message.substr(pos, end == std::string::npos ? std::string::npos : end - pos + 1);
-                            bool drop = false;
-                            for (Idx const s : todo)
-                                if (line.rfind("Error in batch #" + std::to_string(s) + ":", 0) == 0) drop = true;
-                            if (!drop) kept += line;
-                            if (end == std::string::npos) break;
-                            pos = end + 1;
-                        }
-                        batch_message = std::move(kept);
-                    }
-                }
+                if (r >= 0) adopt_device_result(r, std::move(plan.exact));
+            }
+        }
+        // automatic tap changer on a load-profile batch with one regulated transformer: the scenarios search in lockstep, one
+        // batched power flow per step (model_tap.cpp); PGMB_TAP_EXACT=1: every scenario searches on its own (comparison)
+        if (opt.tap_strategy != 0 && n > 0 && std::getenv("PGMB_TAP_EXACT") == nullptr) {
+            if (status == nullptr) {
+                status_local.assign(n, 0);
+                status = status_local.data();
+            }
+            std::vector<Idx> exact;
+            timing[0] += ms_since(t0);
+            int64_t const r = run_tap_lockstep<B>(opt, *update, out, n_iter, status, exact);
+            t0 = Clock::now();
+            if (r >= 0) {
+                adopt_device_result(r, std::move(exact));
+            } else {
+                batch_message.clear();
             }
         }
         if (!structural && !source_param_change) prepare_engines<B>(); // the eligibility test looks at the math topology

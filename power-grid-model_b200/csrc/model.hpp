@@ -251,6 +251,10 @@ class Model {
     // power flows on the GPU, writes the outputs of the final power flow and puts the tap positions back
     template <int B>
     int64_t run_tap_optimizer(ModelOptions const& opt, OutputData const& out, Idx scenario, int32_t* n_iter, int32_t* status);
+    // lockstep search over a load-profile batch with one regulated transformer: one batched power flow per search step
+    template <int B>
+    int64_t run_tap_lockstep(ModelOptions const& opt, UpdateData const& update, OutputData const& out, int32_t* n_iter, int32_t* status,
+                             std::vector<Idx>& exact);
     struct TapRanked;
     std::vector<std::vector<TapRanked>> rank_tap_regulators() const;
     std::vector<int64_t> tap_rank_table() const; // introspection: (kind, index, rank group) in the order of the search
@@ -283,6 +287,7 @@ class Model {
     struct DeviceSide;
     std::shared_ptr<DeviceSide> dev_;
     bool device_path_eligible(UpdateData const& update) const;
+    void fetch_resident_rows(int slot, size_t row_bytes, Idx count, Idx index, Idx n_scn, void* dst) const;
     int64_t run_batch_device(ModelOptions const& opt, int phases, UpdateData const& update, OutputData const& out, int32_t* n_iter,
                              int32_t* status);
     int64_t run_batch_device_one(ModelOptions const& opt, int phases, UpdateData const& update, OutputData const& out,

@@ -100,6 +100,15 @@ struct Model::DeviceSide {
     }
 };
 
+// rows `index` of one output component (slot as in the request table of run_batch_device_part) for every scenario of the last
+// single-device pass that left its output structs in HBM (kFlagResidentOutput): a strided copy of n_scn rows
+void Model::fetch_resident_rows(int slot, size_t row_bytes, Idx count, Idx index, Idx n_scn, void* dst) const {
+    if (!dev_ || dev_->device < 0 || slot < 0 || slot >= 13) throw InvalidArgument("internal: no device-resident output to read");
+    PGMB_CUDA(cudaSetDevice(dev_->device));
+    PGMB_CUDA(cudaMemcpy2D(dst, row_bytes, dev_->out[slot].get() + static_cast<size_t>(index) * row_bytes, static_cast<size_t>(count) * row_bytes,
+                           row_bytes, static_cast<size_t>(n_scn), cudaMemcpyDeviceToHost));
+}
+
 bool Model::device_path_eligible(UpdateData const& u) const {
     if (topo_.math.size() != 1) return false;
     if (n_t3w() != 0) return false; // three-winding transformer output is converted on the host (write_output)

@@ -510,6 +510,200 @@ int64_t Model::run_tap_optimizer(ModelOptions const& opt, OutputData const& out,
     return failed;
 }
 
+// ---- lockstep over a batch ------------------------------------------------------------------------------------------------------
+// Load-profile batches on a grid with ONE regulated two-winding transformer (the reference benchmark's tap changer,
+// fictional_grid_generator.hpp:615-633): every scenario keeps its own tap position and search state, and each step of the search
+// is ONE batched power flow of all scenarios on the device pipeline, the transformer's admittances given per scenario through the
+// branch overlay of the N-1 route (Engine::set_overlay, model.hpp: OutagePlan).  Intermediate passes bring back node and
+// transformer results only; a last pass writes the caller's outputs.  Scenarios that need the reference's fallback (a power flow
+// that does not converge, the iteration limit) are returned in `exact` for the scenario-by-scenario search.
+// Returns the number of failed scenarios of the last pass, or -1 when the batch does not have this shape.
+template <int B>
+int64_t Model::run_tap_lockstep(ModelOptions const& opt, UpdateData const& update, OutputData const& out, int32_t* n_iter, int32_t* status,
+                                std::vector<Idx>& exact) {
+    constexpr size_t bb2 = static_cast<size_t>(B) * B * 2;
+    if (opt.method != 1 && opt.method != -128) return -1;
+    if (!reg_in_.empty() || update.n_scenarios <= 0 || status == nullptr) return -1;
+    if (update.line.data != nullptr || update.transformer.data != nullptr || update.shunt.data != nullptr || update.source.data != nullptr ||
+        update.voltage_regulator.data != nullptr || update.asym_line.data != nullptr || update.generic_branch.data != nullptr ||
+        update.link.data != nullptr || update.three_winding_transformer.data != nullptr || update.transformer_tap_regulator.data != nullptr) {
+        return -1;
+    }
+    prepare_engines<B>();
+    if (!device_path_eligible(update)) return -1;
+    MathTopology const& m = topo_.math[0];
+    if (std::all_of(m.load_gen_type.begin(), m.load_gen_type.end(), [](int8_t t) { return t == 1; })) return -1; // linear method
+    std::vector<std::vector<TapRanked>> const order = rank_tap_regulators();
+    if (order.size() != 1 || order[0].size() != 1 || order[0][0].kind != 0) return -1;
+    TapRanked const& t = order[0][0];
+    Idx const ti = t.index, seq = off_trafo() + ti;
+    Coupling const branch = topo_.branch[seq];
+    IntS const side = tap_reg_in_[t.regulator].control_side;
+    Idx const control_node = node_seq(side == 0 ? trafo_in_[ti].from_node : trafo_in_[ti].to_node);
+    if (branch.group != 0 || topo_.node[control_node].group != 0) return -1;
+
+    Goal const goal = opt.tap_strategy == 2 ? Goal::lowest : opt.tap_strategy == 3 ? Goal::highest
+                      : opt.tap_strategy == 4 ? Goal::fast_any : Goal::any;
+    Search const first_search = goal == Goal::any ? Search::scan : Search::bisect;
+    bool const highest = goal == Goal::highest, two_stage = goal == Goal::highest || goal == Goal::lowest;
+    Idx const n = update.n_scenarios, nn = static_cast<Idx>(node_.size());
+    uint64_t const width = static_cast<uint64_t>(t.range.width());
+    TapRegulatorState const& rst = tap_reg_st_[t.regulator];
+    double const u_rated = tap_reg_target_[t.regulator].u_rated;
+    double const z_base = u_rated * u_rated / (B == 1 ? kBasePower3p : kBasePower1p);
+    cplx const z_comp = cplx{std::isnan(rst.line_drop_compensation_r) ? 0.0 : rst.line_drop_compensation_r,
+                             std::isnan(rst.line_drop_compensation_x) ? 0.0 : rst.line_drop_compensation_x} / z_base;
+    double const lower = rst.u_set / u_rated - 0.5 * rst.u_band / u_rated, upper = rst.u_set / u_rated + 0.5 * rst.u_band / u_rated;
+
+    struct Lane {
+        IntS tap;
+        Bisection bs;
+        uint64_t passes{0};
+        int stage{0}; // 0: first search, 1: scan after the step past the found position, 2: finished, 3: scenario-by-scenario route
+    };
+    std::vector<Lane> lanes(n);
+    for (Lane& l : lanes) {
+        l.tap = trafo_st_[ti].tap_pos;
+        l.bs.reset(l.tap, t.range, t.control_at_tap_side);
+        if (two_stage) l.tap = highest ? t.range.highest_voltage(t.control_at_tap_side) : t.range.lowest_voltage(t.control_at_tap_side);
+        l.bs.set_pos(l.tap);
+        l.bs.clear_flags();
+    }
+    OutagePlan plan;
+    plan.math_branch.assign(n, branch.pos);
+    plan.comp.assign(n, static_cast<int32_t>(seq));
+    plan.energized.assign(n, 1);
+    plan.dead_off.assign(n, -1);
+    plan.bparam.assign(n * 4 * bb2, 0.0);
+    auto fill_plan = [&] {
+        for (Idx s = 0; s != n; ++s) transformer_param<B>(trafo_c_[ti], branch_st_[seq], tap_limit(trafo_c_[ti], lanes[s].tap), &plan.bparam[s * 4 * bb2]);
+    };
+    // a probe pass runs on one device and leaves node / transformer results in HBM (update rows stay there after the first
+    // pass); only the control node's and the transformer's row of every scenario come back
+    bool rows_resident = false;
+    auto run_pass = [&](bool probe_pass, OutputData const& o, int32_t* it, int32_t* st) {
+        fill_plan();
+        outage_plan_ = &plan;
+        int64_t r = -1;
+        try {
+            if (probe_pass) {
+                ModelOptions po = opt;
+                po.n_devices = 1;
+                po.flags = kFlagResidentOutput | (rows_resident ? kFlagResidentInput : 0u);
+                r = run_batch_device_one(po, B, update, o, it, st, 0);
+                rows_resident = true;
+            } else {
+                r = run_batch_device(opt, B, update, o, it, st);
+            }
+        } catch (...) {
+            outage_plan_ = nullptr;
+            throw;
+        }
+        outage_plan_ = nullptr;
+        return r;
+    };
+    std::vector<NodeOutput<B>> node_probe(n);
+    std::vector<BranchOutput<B>> trafo_probe(n);
+    std::vector<int32_t> pass_status(n, 0), pass_iter(n, 0);
+    unsigned char selects_component = 0; // resident output: the pointers only say which components are produced
+    OutputData probe{};
+    probe.node = &selects_component;
+    probe.transformer = &selects_component;
+    auto compare = [&](Idx s) { // -1 below the band, 0 inside, +1 above
+        NodeOutput<B> const& no = node_probe[s];
+        BranchOutput<B> const& bo = trafo_probe[s];
+        double const base_power = B == 1 ? kBasePower3p : kBasePower1p;
+        double v = 0.0;
+        for (int p = 0; p != B; ++p) {
+            cplx const u = std::polar(no.u_pu[p], no.u_angle[p]);
+            cplx const s_pu = cplx{side == 0 ? bo.p_from[p] : bo.p_to[p], side == 0 ? bo.q_from[p] : bo.q_to[p]} / base_power;
+            cplx const i_pu = std::abs(u) > 0.0 ? std::conj(s_pu / u) : cplx{};
+            v += std::abs(u + z_comp * i_pu);
+        }
+        v /= B;
+        return v < lower ? -1 : v > upper ? 1 : 0;
+    };
+    uint64_t const pass_cap = 8 * (width + 4);
+    for (uint64_t pass = 0;; ++pass) {
+        bool any_active = false;
+        for (Lane const& l : lanes) any_active = any_active || l.stage < 2;
+        if (!any_active) break;
+        if (pass > pass_cap) {
+            for (Lane& l : lanes)
+                if (l.stage < 2) l.stage = 3;
+            break;
+        }
+        batch_message.clear();
+        if (run_pass(true, probe, pass_iter.data(), pass_status.data()) < 0) return -1;
+        fetch_resident_rows(0, sizeof(NodeOutput<B>), nn, control_node, n, node_probe.data());
+        fetch_resident_rows(2, sizeof(BranchOutput<B>), n_trafo(), ti, n, trafo_probe.data());
+        for (Idx s = 0; s != n; ++s) {
+            Lane& l = lanes[s];
+            if (l.stage >= 2) continue;
+            if (pass_status[s] != 0) { // IterationDiverge / SparseMatrixError: the reference retries after a linear pass
+                l.stage = 3;
+                continue;
+            }
+            int const cmp = compare(s);
+            Search const search = l.stage == 0 ? first_search : Search::scan;
+            bool changed = false;
+            IntS next = l.tap;
+            if (search == Search::scan) {
+                next = cmp > 0 ? t.range.voltage_down(l.tap, t.control_at_tap_side) : cmp < 0 ? t.range.voltage_up(l.tap, t.control_at_tap_side) : l.tap;
+                changed = next != l.tap;
+            } else if (!l.bs.exhausted() && !l.bs.settled()) {
+                if (cmp != 0) l.bs.step_towards_band(highest, cmp > 0);
+                if (IntS const proposed = l.bs.pos(); proposed != l.tap) {
+                    next = proposed;
+                    changed = true;
+                } else if (!(goal == Goal::fast_any && cmp == 0)) {
+                    bool const previous_down = l.bs.went_down();
+                    l.bs.keep_as_bound(highest);
+                    IntS const candidate = l.bs.next_candidate(highest, previous_down, changed);
+                    if (candidate == l.tap && cmp != 0 && !l.bs.exhausted()) { // no valid position: MaxIterationReached in the reference
+                        l.stage = 3;
+                        continue;
+                    }
+                    next = candidate;
+                }
+            }
+            if (changed) {
+                if (++l.passes > 2 * width) {
+                    l.stage = 3;
+                    continue;
+                }
+                l.tap = tap_limit(trafo_c_[ti], next);
+            } else if (l.stage == 0 && two_stage) {
+                l.tap = tap_limit(trafo_c_[ti], highest ? t.range.voltage_up(l.tap, t.control_at_tap_side) : t.range.voltage_down(l.tap, t.control_at_tap_side));
+                l.stage = 1;
+                l.passes = 0;
+            } else {
+                l.stage = 2;
+            }
+        }
+    }
+    // the caller's outputs with every scenario at its final tap position
+    batch_message.clear();
+    int64_t const failed = run_pass(false, out, n_iter, status);
+    if (failed < 0) return -1;
+    exact.clear();
+    for (Idx s = 0; s != n; ++s) {
+        if (lanes[s].stage == 3 || status[s] != 0) exact.push_back(s);
+    }
+    if (out.transformer_tap_regulator != nullptr) {
+        Idx const n_reg = static_cast<Idx>(tap_reg_in_.size());
+        auto* dst = static_cast<TransformerTapRegulatorOutput*>(out.transformer_tap_regulator);
+        for (Idx s = 0; s != n; ++s) {
+            if (lanes[s].stage == 3 || status[s] != 0) continue;
+            dst[s * n_reg + t.regulator].energized = 1;
+            dst[s * n_reg + t.regulator].tap_pos = lanes[s].tap;
+        }
+    }
+    return failed;
+}
+
+template int64_t Model::run_tap_lockstep<1>(ModelOptions const&, UpdateData const&, OutputData const&, int32_t*, int32_t*, std::vector<Idx>&);
+template int64_t Model::run_tap_lockstep<3>(ModelOptions const&, UpdateData const&, OutputData const&, int32_t*, int32_t*, std::vector<Idx>&);
 template int64_t Model::run_tap_optimizer<1>(ModelOptions const&, OutputData const&, Idx, int32_t*, int32_t*);
 template int64_t Model::run_tap_optimizer<3>(ModelOptions const&, OutputData const&, Idx, int32_t*, int32_t*);
 

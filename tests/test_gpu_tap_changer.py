@@ -123,3 +123,27 @@ def test_tap_changer_on_the_benchmark_grid_equals_the_oracle(strategy, sym, extr
     assert np.array_equal(res["transformer_tap_regulator"]["tap_pos"], ref["transformer_tap_regulator"]["tap_pos"])
     assert np.array_equal(res["transformer_tap_regulator"]["energized"], ref["transformer_tap_regulator"]["energized"])
     parity.compare_outputs(res, ref, ["node", "transformer", "source"])
+
+
+@pytest.mark.parametrize("sym", [True, False])
+@pytest.mark.parametrize("strategy", ["any_valid_tap", "min_voltage_tap", "max_voltage_tap", "fast_any_tap"])
+def test_lockstep_search_equals_the_scenario_by_scenario_search(strategy, sym, monkeypatch):
+    """one regulated transformer + a load-profile batch: the batch searches in lockstep (one batched power flow per step, the
+    transformer's admittances per scenario through the branch overlay); PGMB_TAP_EXACT=1 runs every scenario's own search"""
+    import parity
+
+    grid, data = _regulated_benchmark_grid(False)
+    n_scn = 96 if sym else 16
+    update = grid.batch_update(n_scn, seed=5)
+    model = pgm_b200.PowerGridModel(data)
+    kw = dict(symmetric=sym, update_data=update, tap_changing_strategy=strategy)
+    launches0 = int(pgm_b200.lib().pgmb_kernel_launch_count())
+    lock = model.calculate_power_flow(**kw)
+    launches_lock = int(pgm_b200.lib().pgmb_kernel_launch_count()) - launches0
+    monkeypatch.setenv("PGMB_TAP_EXACT", "1")
+    exact = model.calculate_power_flow(**kw)
+    launches_exact = int(pgm_b200.lib().pgmb_kernel_launch_count()) - launches0 - launches_lock
+    assert np.array_equal(lock["transformer_tap_regulator"]["tap_pos"], exact["transformer_tap_regulator"]["tap_pos"])
+    assert (lock["transformer_tap_regulator"]["energized"] == 1).all()
+    parity.compare_outputs(lock, exact, [c for c in lock if c != "transformer_tap_regulator"])
+    assert launches_lock < launches_exact  # a handful of batched passes against several power flows per scenario
