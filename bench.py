@@ -178,7 +178,9 @@ def host_link(torch, barrier, n_bytes=256 << 20, reps=5):
 
 
 def other_configs(pgm_b200, np, device):
-    """kernel milliseconds (CUDA events, second of two runs) of BASELINE configs 3 and 4 on one GPU; informational"""
+    """kernel milliseconds (CUDA events, second of two runs) of BASELINE configs 3 and 4 on one GPU; informational.  The oracle is
+    only the CPU comparator of the tap-changer and single-scenario entries (cpu_baseline leg)."""
+    import oracle_lib as orc
 
     def staged_engine(grid, sym, n_scn, seed, method=None):
         model = pgm_b200.PowerGridModel(grid.input_data)
@@ -226,6 +228,42 @@ def other_configs(pgm_b200, np, device):
     out["configs[4] shape, ringed 1804-node grid, asymmetric N-1 (1000 single-line outages, shared pattern = NOT the reference's per-scenario re-ordering: same equations, results to rounding), public API"] = {
         "wall_ms": wall, "kernel_ms": model.timing()["solve_kernel"], "scenarios_per_s": n1 / wall * 1e3,
         "failed": int((model.status != 0).sum())}
+    # the reference benchmark's tap-changer shape (benchmark.cpp:333-422): configs[1] grid + one regulator on the station
+    # transformer, 1000 load-profile scenarios, symmetric NR; the batch searches in lockstep (one batched power flow per search
+    # step).  Second of two calls, node + transformer + regulator output into page-locked buffers; CPU: the oracle, all threads.
+    tap_grid = pgm_b200.FictionalGrid(seed=0, has_tap_changer=True, **pgm_b200.BENCHMARK_OPTION)
+    tap_update = tap_grid.batch_update(1000, seed=0)
+    tap_model = pgm_b200.PowerGridModel(tap_grid.input_data)
+    tap_oracle = orc.Model(tap_grid.input_data)
+    comps = ["node", "transformer", "transformer_tap_regulator"]
+    cpu_out = {c: np.zeros((1000, len(tap_grid.input_data[c])), pgm_b200.structs.SYM_OUTPUT[c]) for c in comps}
+    for strategy in ("any_valid_tap", "min_voltage_tap"):
+        for _ in range(2):
+            t0 = time.perf_counter()
+            res = tap_model.calculate_power_flow(update_data=tap_update, tap_changing_strategy=strategy, output_component_types=comps,
+                                                 reuse_output_buffers=True, device=device)
+            wall = 1e3 * (time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        ref = tap_oracle.calculate(sym=True, update=tap_update, threading=0, tap_changing_strategy=strategy, output_components=comps, out=cpu_out)
+        cpu_ms = 1e3 * (time.perf_counter() - t0)
+        out[f"automatic tap changer ({strategy}), configs[1] grid + 1 regulator, 1000 scenarios, public API"] = {
+            "wall_ms": wall, "scenarios_per_s": 1000 / wall * 1e3, "cpu_oracle_ms": cpu_ms,
+            "tap_positions_equal_to_oracle": bool(np.array_equal(res["transformer_tap_regulator"]["tap_pos"],
+                                                                 ref["transformer_tap_regulator"]["tap_pos"]))}
+    # configs[0]: ONE scenario of the configs[1] grid (the reference's own CPU-runnable case): latency of a single calculation
+    single = pgm_b200.PowerGridModel(radial.input_data)
+    single_oracle = orc.Model(radial.input_data)
+    for sym in (True, False):
+        t_gpu, t_cpu = [], []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            single.calculate_power_flow(symmetric=sym, device=device)
+            t_gpu.append(time.perf_counter() - t0)
+            t0 = time.perf_counter()
+            single_oracle.calculate(sym=sym)
+            t_cpu.append(time.perf_counter() - t0)
+        out[f"configs[0] single scenario, {'symmetric' if sym else 'asymmetric'} newton_raphson (latency; a batch of one does not fill a GPU)"] = {
+            "gpu_ms": 1e3 * min(t_gpu), "cpu_oracle_ms": 1e3 * min(t_cpu)}
     return out
 
 
