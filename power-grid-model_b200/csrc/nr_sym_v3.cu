@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdlib>
+#include <stdexcept>
 
 #ifndef V3_CHAIN_AHEAD
 #define V3_CHAIN_AHEAD 2
@@ -87,6 +88,9 @@ template <int T> struct TileP {
     double* __restrict__ side; // [n_bus][2][T] right-hand-side part of the precomputed leaf update term (kind 2)
     double const* __restrict__ sinj;
     double const* __restrict__ usrc;
+    // voltage regulators (REG instantiations only): status of every load_gen, Q limit the bus ran into (0 none, 1 lower, 2 upper)
+    uint8_t const* __restrict__ lg_status;
+    uint8_t* __restrict__ qviol;
     __device__ __forceinline__ Blk load_blk(int k) const {
         double const* p = jac + (size_t)k * 4 * T;
         return {p[0], p[T], p[2 * T], p[3 * T]};
@@ -151,12 +155,41 @@ __device__ __forceinline__ bool finish_row(TileP<T> const& t, int row, int k_d, 
     return singular;
 }
 
+// ---- PV buses (voltage regulators; newton_raphson_pf_solver.hpp:400-452, 549-587, 605-742) -----------------------------------
+// The same decisions, in the same order, as the generic block kernel takes for B = 1 (block_common.cuh: bus_control,
+// check_q_limit, pv_diag, zero_pv_rows): results are bit-identical to it.
+constexpr double kQTol = 1e-8;
+struct PvControl {
+    bool regulated, has_limits;
+    double u_ref, q_min, q_max;
+};
+template <int T> __device__ __forceinline__ bool lg_regulating(DevStructure const& s, TileP<T> const& t, int lg, int& reg) {
+    reg = __ldg(s.lg_reg + lg);
+    return reg >= 0 && __ldg(s.reg_param + 4 * reg) != 0.0 && t.lg_status[(size_t)lg * T] != 0;
+}
+template <int T> __device__ __forceinline__ PvControl pv_control(DevStructure const& s, TileP<T> const& t, int lg0, int n_lg, int n_src) {
+    PvControl c{false, false, 0.0, 0.0, 0.0};
+    if (n_src != 0) return c; // slack bus
+    for (int lg = lg0; lg < lg0 + n_lg; ++lg) {
+        int reg;
+        if (lg_regulating<T>(s, t, lg, reg)) {
+            c.regulated = true;
+            c.u_ref = __ldg(s.reg_param + 4 * reg + 1);
+            c.q_min += __ldg(s.reg_param + 4 * reg + 2);
+            c.q_max += __ldg(s.reg_param + 4 * reg + 3);
+        }
+    }
+    c.has_limits = c.regulated && (!isnan(c.q_min) || !isnan(c.q_max));
+    return c;
+}
+
 // ---- build phase -----------------------------------------------------------------------------------------------------
 // own blocks of one row: diagonal d, block towards the parent ub, mismatch / right-hand side acc, blocks towards the
 // children (stored to their LU slots).  rec = 8-word head; lower = per-child words (null for a leaf).
-template <int T, Mode mode>
+template <int T, Mode mode, bool REG = false>
 __device__ __forceinline__ void build_row(DevStructure const& s, TileP<T> const& t, int32_t const* __restrict__ rec, int n_lower,
-                                          int32_t const* __restrict__ lower, Blk& d, Blk& ub, double& acc0, double& acc1) {
+                                          int32_t const* __restrict__ lower, Blk& d, Blk& ub, double& acc0, double& acc1,
+                                          [[maybe_unused]] bool check_now = false) {
     int const row = rec[0], k_d = rec[1], ky_d = rec[2], k_u = rec[3], j = rec[4], ky_u = rec[5];
     int const lg0 = rec[6] & 0xffffff, n_lg = (rec[6] >> 24) & 0x7f;
     int const sr0 = rec[7] & 0xffffff, n_src = (rec[7] >> 24) & 0x7f;
@@ -214,8 +247,34 @@ __device__ __forceinline__ void build_row(DevStructure const& s, TileP<T> const&
         d.a11 += -acc1;
     }
     double const v = t.pol[(size_t)(row * 2 + 1) * T];
+    // REG: loads and sources depend on the Q limit the bus may run into right now; the part above does not, so a bus that
+    // hits its limit repeats only what follows (the block kernel rebuilds the whole row: the same sums in the same order)
+    [[maybe_unused]] PvControl ctl{false, false, 0.0, 0.0, 0.0};
+    [[maybe_unused]] int viol = 0;
+    [[maybe_unused]] Blk d_rows = d;
+    [[maybe_unused]] double rows0 = acc0, rows1 = acc1;
+    if constexpr (REG && mode == Mode::newton) {
+        ctl = pv_control<T>(s, t, lg0, n_lg, n_src);
+        viol = t.qviol[(size_t)row * T];
+    }
+    constexpr int n_pass = (REG && mode == Mode::newton) ? 2 : 1;
+#pragma unroll 1
+    for (int pass = 0; pass < n_pass; ++pass) {
+    if constexpr (REG && mode == Mode::newton) {
+        d = d_rows;
+        acc0 = rows0;
+        acc1 = rows1;
+    }
     for (int lg = lg0; lg < lg0 + n_lg; ++lg) {
-        double const ps = t.sinj[(size_t)(lg * 2) * T], qs = t.sinj[(size_t)(lg * 2 + 1) * T];
+        double const ps = t.sinj[(size_t)(lg * 2) * T];
+        double qs = t.sinj[(size_t)(lg * 2 + 1) * T];
+        if constexpr (REG) {
+            int reg;
+            bool const regulating = lg_regulating<T>(s, t, lg, reg);
+            // linear start: the specified Q of a regulating generator is ignored; Newton: clamped once the bus hit a limit
+            if (regulating && mode == Mode::linear_init) qs = 0.0;
+            if (regulating && mode == Mode::newton && viol != 0) qs = __ldg(s.reg_param + 4 * reg + (viol == 2 ? 3 : 2));
+        }
         if constexpr (mode == Mode::newton) {
             int const type = __ldg(s.lg_type + lg);
             if (type == 0) {
@@ -269,26 +328,58 @@ __device__ __forceinline__ void build_row(DevStructure const& s, TileP<T> const&
             acc1 += yr * usi + yi * usr;
         }
     }
+    if constexpr (REG && mode == Mode::newton) {
+        if (pass == 0 && check_now && ctl.has_limits && viol == 0) { // enforce_q_limits (:605-704)
+            double spec = 0.0;
+            for (int lg = lg0; lg < lg0 + n_lg; ++lg) {
+                int reg;
+                if (lg_regulating<T>(s, t, lg, reg)) spec += t.sinj[(size_t)(lg * 2 + 1) * T];
+            }
+            double const q_total = spec - acc1;
+            if (!isnan(ctl.q_max) && q_total > ctl.q_max + kQTol) viol = 2;
+            else if (!isnan(ctl.q_min) && q_total < ctl.q_min - kQTol) viol = 1;
+            if (viol != 0) {
+                t.qviol[(size_t)row * T] = (uint8_t)viol;
+                continue; // the bus is PQ from now on: its injections again, with the clamped generators
+            }
+        }
+    }
+    break;
+    }
+    if constexpr (REG && mode == Mode::newton) {
+        if (ctl.regulated && viol == 0) { // PV row (:549-587): the Q row of every block of the row goes, |V| is held
+            d.a10 = 0.0;
+            d.a11 = v;
+            acc1 = 0.0;
+            ub.a10 = 0.0;
+            ub.a11 = 0.0;
+            for (int e = 0; e < n_lower; ++e) {
+                double* p = t.jac + (size_t)(k_d - n_lower + e) * 4 * T;
+                p[T] = 0.0;
+                p[3 * T] = 0.0;
+            }
+        }
+    }
 }
 
-template <int T, Mode mode>
-__device__ __forceinline__ bool build_leaf(DevStructure const& s, TileP<T> const& t, int32_t const* __restrict__ rec) {
+template <int T, Mode mode, bool REG = false>
+__device__ __forceinline__ bool build_leaf(DevStructure const& s, TileP<T> const& t, int32_t const* __restrict__ rec, bool check_now = false) {
     Blk d, ub;
     double acc0, acc1;
-    build_row<T, mode>(s, t, rec, 0, nullptr, d, ub, acc0, acc1);
+    build_row<T, mode, REG>(s, t, rec, 0, nullptr, d, ub, acc0, acc1, check_now);
     int pcq;
     return finish_row<T>(t, rec[0], rec[1], rec[3], d, ub, acc0, acc1, pcq);
 }
 
 // non-leaf row: build, then eliminate / precompute the leaf children (they were finished by build_leaf before the barrier)
-template <int T, Mode mode>
-__device__ __forceinline__ void build_inner(DevStructure const& s, TileP<T> const& t, int32_t const* __restrict__ rec) {
+template <int T, Mode mode, bool REG = false>
+__device__ __forceinline__ void build_inner(DevStructure const& s, TileP<T> const& t, int32_t const* __restrict__ rec, bool check_now = false) {
     int const row = rec[0], k_d = rec[1], k_u = rec[3];
     int const n_lower = rec[8] & 0xfff;
     int32_t const* __restrict__ lower = rec + 9;
     Blk d, ub;
     double acc0, acc1;
-    build_row<T, mode>(s, t, rec, n_lower, lower, d, ub, acc0, acc1);
+    build_row<T, mode, REG>(s, t, rec, n_lower, lower, d, ub, acc0, acc1, check_now);
     for (int e = 0; e < n_lower; ++e) {
         int const kind = (lower[4 * e + 3] >> 28) & 3;
         if (kind != 0 && kind != 2) continue;
@@ -523,9 +614,9 @@ template <int T, Mode mode, bool RING = false> __device__ __forceinline__ void p
     }
 }
 // backward substitution of one row given the parent's solution; returns the voltage change
-template <int T, Mode mode>
+template <int T, Mode mode, bool REG = false>
 __device__ __forceinline__ double down_step(TileP<T> const& t, int row, bool has_parent, DownOperands const& o, double& x0,
-                                            double& x1) {
+                                            double& x1, [[maybe_unused]] DevStructure const* s = nullptr) {
     double y0 = o.y0, y1 = o.y1;
     if (has_parent) {
         y0 -= o.ub.a00 * x0 + o.ub.a01 * x1;
@@ -543,12 +634,26 @@ __device__ __forceinline__ double down_step(TileP<T> const& t, int row, bool has
     t.xvec[(size_t)(row * 2 + 1) * T] = y1;
     x0 = y0;
     x1 = y1;
+    if constexpr (REG && mode == Mode::linear_init) { // a PV bus starts at its reference magnitude: u = u_ref * u / |u| (:446-452)
+        int const lg0 = __ldg(s->lg_ptr + row), lg1 = __ldg(s->lg_ptr + row + 1);
+        PvControl const ctl = pv_control<T>(*s, t, lg0, lg1 - lg0, __ldg(s->src_ptr + row + 1) - __ldg(s->src_ptr + row));
+        if (ctl.regulated) {
+            double const ax = sqrt(y0 * y0 + y1 * y1);
+            double sr = 1.0, si = 0.0;
+            if (ax > 0.0) {
+                sr = y0 / ax;
+                si = y1 / ax;
+            }
+            y0 = ctl.u_ref * sr - 0.0 * si;
+            y1 = ctl.u_ref * si + 0.0 * sr;
+        }
+    }
     return polar_update<T, mode>(t.pol + (size_t)(row * 2) * T, t.u + (size_t)(row * 2) * T, y0, y1, o.th, o.v, o.our, o.oui);
 }
 
-template <int T, Mode mode, bool RING>
+template <int T, Mode mode, bool RING, bool REG = false>
 __device__ __forceinline__ double down_path(TileP<T> const& t, int4 const* __restrict__ chain, int first_rec, int n_rows,
-                                            Ring const& ring) {
+                                            Ring const& ring, [[maybe_unused]] DevStructure const* s = nullptr) {
     double dev = 0.0;
     int4 c0 = chain[2 * (first_rec + n_rows - 1)];
     int const j_top = chain[2 * (first_rec + n_rows - 1) + 1].w;
@@ -618,16 +723,16 @@ __device__ __forceinline__ double down_path(TileP<T> const& t, int4 const* __res
             if (i >= kChainAhead) prefetch_down<T, mode, RING>(t, chain[2 * (first_rec + i - kChainAhead)]);
         }
         buf ^= 1;
-        dev = fmax(dev, down_step<T, mode>(t, row, has_parent, o, x0, x1));
+        dev = fmax(dev, down_step<T, mode, REG>(t, row, has_parent, o, x0, x1, s));
         has_parent = true;
     }
     return dev;
 }
 
-template <int T, Mode mode, bool RING>
+template <int T, Mode mode, bool RING, bool REG>
 __device__ __forceinline__ void sweeps_v3(DevStructure const& s, TileP<T> const& t, int32_t const* __restrict__ prog, int slot,
                                           int n_slot, bool active, bool& singular, double& dev, unsigned long long* phase,
-                                          Ring const& ring) {
+                                          Ring const& ring, bool check_now) {
     int32_t const* __restrict__ const recs = s.path_prog; // leaf / row records: global memory
     int const n_leaf = prog[0], n_rec = prog[1], n_stage = prog[2];
     int32_t const* __restrict__ leaf = recs + prog[3];
@@ -675,7 +780,7 @@ __device__ __forceinline__ void sweeps_v3(DevStructure const& s, TileP<T> const&
     if (active) {
         for (int i = slot; i < n_leaf; i += n_slot) {
             if (i + n_slot < n_leaf) prefetch_row_inputs(leaf + 8 * (i + n_slot), 0, nullptr);
-            singular |= build_leaf<T, mode>(s, t, leaf + 8 * i);
+            singular |= build_leaf<T, mode, REG>(s, t, leaf + 8 * i, check_now);
         }
     }
     __syncthreads();
@@ -686,7 +791,7 @@ __device__ __forceinline__ void sweeps_v3(DevStructure const& s, TileP<T> const&
                 int32_t const* nx = recs + rec_off[i + n_slot];
                 prefetch_row_inputs(nx, nx[8] & 0xfff, nx + 9);
             }
-            build_inner<T, mode>(s, t, recs + rec_off[i]);
+            build_inner<T, mode, REG>(s, t, recs + rec_off[i], check_now);
         }
     }
     __syncthreads();
@@ -703,7 +808,7 @@ __device__ __forceinline__ void sweeps_v3(DevStructure const& s, TileP<T> const&
     for (int st = n_stage - 1; st >= 1; --st) {
         if (active) {
             for (int p = stage_ptr[st - 1] + slot; p < stage_ptr[st]; p += n_slot) {
-                dev = fmax(dev, down_path<T, mode, RING && (V3_RING_DOWN != 0)>(t, chain, path[2 * p], path[2 * p + 1], ring));
+                dev = fmax(dev, down_path<T, mode, RING && (V3_RING_DOWN != 0), REG>(t, chain, path[2 * p], path[2 * p + 1], ring, &s));
             }
         }
         __syncthreads();
@@ -739,7 +844,7 @@ __device__ __forceinline__ void sweeps_v3(DevStructure const& s, TileP<T> const&
                     }
                 }
             }
-            dev = fmax(dev, down_step<T, mode>(t, rec[0], rec[3] >= 0, o, x0, x1));
+            dev = fmax(dev, down_step<T, mode, REG>(t, rec[0], rec[3] >= 0, o, x0, x1, &s));
         }
     }
     __syncthreads();
@@ -750,10 +855,12 @@ __device__ __forceinline__ void sweeps_v3(DevStructure const& s, TileP<T> const&
 
 // SMEM: the chain part of the path program is staged in shared memory; RING (needs SMEM): operand ring of the chain walks
 // behind it
-template <int T, bool SMEM, bool RING> __global__ void __launch_bounds__(V3_THREADS, 1) nr_sym_v3_kernel(DevStructure s, DevBatch b, SolveOptions opt) {
+// REG: the grid has voltage regulators (PV buses with reactive-power limits)
+template <int T, bool SMEM, bool RING, bool REG> __global__ void __launch_bounds__(V3_THREADS, 1) nr_sym_v3_kernel(DevStructure s, DevBatch b, SolveOptions opt) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ unsigned long long sh_dev[T];
     __shared__ int sh_singular[T];
+    __shared__ int sh_has_limits[T]; // REG: the scenario has a PV bus with a usable Q limit (limit check from iteration 2 on)
     __shared__ __align__(8) uint64_t sh_mbar;
     int const lane = threadIdx.x % T;
     int const slot = threadIdx.x / T;
@@ -780,12 +887,26 @@ template <int T, bool SMEM, bool RING> __global__ void __launch_bounds__(V3_THRE
     t.side = b.side + (size_t)tile * s.n_bus * 2 * T + lane;
     t.sinj = b.sinj + (size_t)tile * s.n_load_gen * 2 * T + lane;
     t.usrc = b.usrc + (size_t)tile * s.n_source * 2 * T + lane;
+    t.lg_status = (REG && b.lg_status != nullptr) ? b.lg_status + (size_t)tile * s.n_load_gen * T + lane : nullptr;
+    t.qviol = (REG && b.qviol != nullptr) ? b.qviol + (size_t)tile * s.n_bus * T + lane : nullptr;
 
     if (threadIdx.x < T) {
         sh_dev[threadIdx.x] = 0ull;
         sh_singular[threadIdx.x] = 0;
+        sh_has_limits[threadIdx.x] = 0;
     }
     __syncthreads();
+    if constexpr (REG) { // set_bus_types_and_q_limits (newton_raphson_pf_solver.hpp:400-444); no limit has been hit yet
+        if (valid) {
+            for (int row = slot; row < s.n_bus; row += n_slot) {
+                t.qviol[(size_t)row * T] = 0;
+                int const lg0 = __ldg(s.lg_ptr + row), lg1 = __ldg(s.lg_ptr + row + 1);
+                if (lg0 != lg1 && pv_control<T>(s, t, lg0, lg1 - lg0, __ldg(s.src_ptr + row + 1) - __ldg(s.src_ptr + row)).has_limits)
+                    sh_has_limits[lane] = 1;
+            }
+        }
+        __syncthreads();
+    }
 
     bool done = !valid;
     int status = kStatusOk;
@@ -795,7 +916,7 @@ template <int T, bool SMEM, bool RING> __global__ void __launch_bounds__(V3_THRE
     {
         bool singular = false;
         double dev = 0.0;
-        sweeps_v3<T, Mode::linear_init, RING>(s, t, prog, slot, n_slot, !done, singular, dev, phase, ring);
+        sweeps_v3<T, Mode::linear_init, RING, REG>(s, t, prog, slot, n_slot, !done, singular, dev, phase, ring, false);
         if (singular) sh_singular[lane] = 1;
         __syncthreads();
         if (!done && sh_singular[lane]) {
@@ -815,7 +936,7 @@ template <int T, bool SMEM, bool RING> __global__ void __launch_bounds__(V3_THRE
         if (!__syncthreads_or(!done)) break;
         bool singular = false;
         double dev = 0.0;
-        sweeps_v3<T, Mode::newton, RING>(s, t, prog, slot, n_slot, !done, singular, dev, phase ? phase + 8 : nullptr, ring);
+        sweeps_v3<T, Mode::newton, RING, REG>(s, t, prog, slot, n_slot, !done, singular, dev, phase ? phase + 8 : nullptr, ring, REG && num_iter >= 2);
         if (!done) {
             if (singular) sh_singular[lane] = 1;
             atomicMax(&sh_dev[lane], (unsigned long long)__double_as_longlong(dev));
@@ -827,7 +948,13 @@ template <int T, bool SMEM, bool RING> __global__ void __launch_bounds__(V3_THRE
                 done = true;
             } else {
                 max_dev = __longlong_as_double((long long)sh_dev[lane]);
-                if (!(max_dev > opt.err_tol)) done = true;
+                if (!(max_dev > opt.err_tol)) {
+                    if (REG && sh_has_limits[lane] && num_iter < 2) {
+                        max_dev = INFINITY; // converged before the limit check: one more iteration (:343-347)
+                    } else {
+                        done = true;
+                    }
+                }
             }
         }
         __syncthreads();
@@ -840,7 +967,7 @@ template <int T, bool SMEM, bool RING> __global__ void __launch_bounds__(V3_THRE
     }
 }
 
-template <int T>
+template <int T, bool REG>
 static void launch_v3_t(DevStructure const& s, DevBatch const& b, SolveOptions const& opt, int n_slot, cudaStream_t st) {
     size_t const prog_bytes = (((size_t)s.path_prog_smem_words * 4 + 127) / 128) * 128;
     size_t const ring_bytes = (size_t)2 * kRingOperands * sizeof(double) * T * n_slot;
@@ -855,13 +982,13 @@ static void launch_v3_t(DevStructure const& s, DevBatch const& b, SolveOptions c
     bool const with_ring = in_smem && want_ring != 0 && prog_bytes + ring_bytes + 1024 <= (size_t)max_optin;
     if (with_ring) {
         size_t const dyn = prog_bytes + ring_bytes;
-        cudaFuncSetAttribute(nr_sym_v3_kernel<T, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-        nr_sym_v3_kernel<T, true, true><<<b.n_tile, T * n_slot, dyn, st>>>(s, b, opt);
+        cudaFuncSetAttribute(nr_sym_v3_kernel<T, true, true, REG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        nr_sym_v3_kernel<T, true, true, REG><<<b.n_tile, T * n_slot, dyn, st>>>(s, b, opt);
     } else if (in_smem) {
-        cudaFuncSetAttribute(nr_sym_v3_kernel<T, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prog_bytes);
-        nr_sym_v3_kernel<T, true, false><<<b.n_tile, T * n_slot, prog_bytes, st>>>(s, b, opt);
+        cudaFuncSetAttribute(nr_sym_v3_kernel<T, true, false, REG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prog_bytes);
+        nr_sym_v3_kernel<T, true, false, REG><<<b.n_tile, T * n_slot, prog_bytes, st>>>(s, b, opt);
     } else {
-        nr_sym_v3_kernel<T, false, false><<<b.n_tile, T * n_slot, 0, st>>>(s, b, opt);
+        nr_sym_v3_kernel<T, false, false, REG><<<b.n_tile, T * n_slot, 0, st>>>(s, b, opt);
     }
 }
 
@@ -869,11 +996,15 @@ void launch_nr_sym_v3(int tile_width, DevStructure const& s, DevBatch const& b, 
                       cudaStream_t st) {
     count_kernel_launch();
     if (n_slot * tile_width > V3_THREADS) n_slot = V3_THREADS / tile_width;
+    bool const reg = s.lg_reg != nullptr;
+    if (reg && (b.qviol == nullptr || b.lg_status == nullptr)) {
+        throw std::logic_error("nr_sym_v3: a grid with voltage regulators needs the qviol / lg_status buffers of the batch");
+    }
     switch (tile_width) {
-    case 4: launch_v3_t<4>(s, b, opt, n_slot, st); break;
-    case 8: launch_v3_t<8>(s, b, opt, n_slot, st); break;
-    case 16: launch_v3_t<16>(s, b, opt, n_slot, st); break;
-    default: launch_v3_t<32>(s, b, opt, n_slot, st); break;
+    case 4: reg ? launch_v3_t<4, true>(s, b, opt, n_slot, st) : launch_v3_t<4, false>(s, b, opt, n_slot, st); break;
+    case 8: reg ? launch_v3_t<8, true>(s, b, opt, n_slot, st) : launch_v3_t<8, false>(s, b, opt, n_slot, st); break;
+    case 16: reg ? launch_v3_t<16, true>(s, b, opt, n_slot, st) : launch_v3_t<16, false>(s, b, opt, n_slot, st); break;
+    default: reg ? launch_v3_t<32, true>(s, b, opt, n_slot, st) : launch_v3_t<32, false>(s, b, opt, n_slot, st); break;
     }
 }
 
