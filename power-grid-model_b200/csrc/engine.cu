@@ -571,11 +571,14 @@ void Engine::launch_solve(DevBatch const& b, SolveOptions const& opt, cudaStream
         if (!symmetric_ && !has_regulators() && env_int("PGMB_BLOCK6", 0) != 0) {
             // row-split kernel: six threads per (bus row, scenario); see nr_block6.cu
             launch_nr_block6(tile_width_, ds_, b, opt, env_int("PGMB_BLOCK6_THREADS", 768), st);
-        } else if (symmetric_ && has_regulators() && path_program_.valid && env_int("PGMB_KERNEL", 3) == 3 && b.ovl.entry == nullptr &&
-                   env_int("PGMB_REG_PATH", 1) != 0) {
-            // radial grid with voltage regulators: the path kernel's PV instantiation (bit-identical to the block kernel with
-            // B = 1, which PGMB_REG_PATH=0 selects)
-            launch_nr_sym_v3(tile_width_, ds_, b, opt, n_slot_, st);
+        } else if (symmetric_ && has_regulators() && env_int("PGMB_KERNEL", 3) >= 2 && b.ovl.entry == nullptr && env_int("PGMB_REG_PATH", 1) != 0) {
+            // symmetric grid with voltage regulators: the PV instantiations of the path kernel (radial grids) and the level
+            // kernel (bit-identical to the block kernel with B = 1, which PGMB_REG_PATH=0 selects)
+            if (path_program_.valid && env_int("PGMB_KERNEL", 3) == 3) {
+                launch_nr_sym_v3(tile_width_, ds_, b, opt, n_slot_, st);
+            } else {
+                launch_nr_sym_v2(tile_width_, ds_, b, opt, n_slot_, st);
+            }
         } else if (!symmetric_ || has_regulators() || env_int("PGMB_KERNEL", 3) == 0) {
             launch_nr_block(B_, tile_width_, ds_, b, opt, n_slot_, st);
         } else if (env_int("PGMB_KERNEL", 3) == 1 && b.ovl.entry == nullptr) {

@@ -124,6 +124,74 @@ template <bool OVL, class TileT> __device__ __forceinline__ bool is_dead(TileT c
     return OVL && t.dead != nullptr && t.dead[bus] != 0;
 }
 
+
+// ---- PV buses (voltage regulators; newton_raphson_pf_solver.hpp:400-452, 549-587, 605-742) -----------------------------------
+// Shared by the symmetric kernels' REG instantiations.  The same decisions, in the same order, as the generic block kernel takes
+// for B = 1 (block_common.cuh: bus_control, check_q_limit, pv_diag, zero_pv_rows): results are bit-identical to it.
+// TileT needs lg_status (status of every load_gen) and sinj.
+constexpr double kQTol = 1e-8;
+struct PvControl {
+    bool regulated, has_limits;
+    double u_ref, q_min, q_max;
+};
+template <int T, class TileT> __device__ __forceinline__ bool lg_regulating(DevStructure const& s, TileT const& t, int lg, int& reg) {
+    reg = __ldg(s.lg_reg + lg);
+    return reg >= 0 && __ldg(s.reg_param + 4 * reg) != 0.0 && t.lg_status[(size_t)lg * T] != 0;
+}
+template <int T, class TileT> __device__ __forceinline__ PvControl pv_control(DevStructure const& s, TileT const& t, int lg0, int n_lg, int n_src) {
+    PvControl c{false, false, 0.0, 0.0, 0.0};
+    if (n_src != 0) return c; // slack bus
+    for (int lg = lg0; lg < lg0 + n_lg; ++lg) {
+        int reg;
+        if (lg_regulating<T>(s, t, lg, reg)) {
+            c.regulated = true;
+            c.u_ref = __ldg(s.reg_param + 4 * reg + 1);
+            c.q_min += __ldg(s.reg_param + 4 * reg + 2);
+            c.q_max += __ldg(s.reg_param + 4 * reg + 3);
+        }
+    }
+    c.has_limits = c.regulated && (!isnan(c.q_min) || !isnan(c.q_max));
+    return c;
+}
+template <int T, class TileT> __device__ __forceinline__ PvControl pv_control_of_row(DevStructure const& s, TileT const& t, int row) {
+    int const lg0 = __ldg(s.lg_ptr + row), lg1 = __ldg(s.lg_ptr + row + 1);
+    return pv_control<T>(s, t, lg0, lg1 - lg0, __ldg(s.src_ptr + row + 1) - __ldg(s.src_ptr + row));
+}
+// specified Q of a load_gen as the row build sees it: ignored for a regulating generator in the linear start, the regulator's
+// limit once its bus ran into one (viol: 1 lower, 2 upper)
+template <int T, Mode mode, class TileT>
+__device__ __forceinline__ double regulated_q(DevStructure const& s, TileT const& t, int lg, int viol, double qs) {
+    int reg;
+    if (!lg_regulating<T>(s, t, lg, reg)) return qs;
+    if (mode == Mode::linear_init) return 0.0;
+    return viol != 0 ? __ldg(s.reg_param + 4 * reg + (viol == 2 ? 3 : 2)) : qs;
+}
+// enforce_q_limits for one PV bus (:605-704); acc1 = Q mismatch of the freshly built row.  Returns the violated limit (0 = none).
+template <int T, class TileT>
+__device__ __forceinline__ int check_q_limit(DevStructure const& s, TileT const& t, int lg0, int n_lg, PvControl const& c, double acc1) {
+    double spec = 0.0;
+    for (int lg = lg0; lg < lg0 + n_lg; ++lg) {
+        int reg;
+        if (lg_regulating<T>(s, t, lg, reg)) spec += t.sinj[(size_t)(lg * 2 + 1) * T];
+    }
+    double const q_total = spec - acc1;
+    if (!isnan(c.q_max) && q_total > c.q_max + kQTol) return 2;
+    if (!isnan(c.q_min) && q_total < c.q_min - kQTol) return 1;
+    return 0;
+}
+// a PV bus starts at its reference magnitude after the linear start: u = u_ref * u / |u| (:446-452)
+__device__ __forceinline__ void pv_start_voltage(PvControl const& c, double& y0, double& y1) {
+    if (!c.regulated) return;
+    double const ax = sqrt(y0 * y0 + y1 * y1);
+    double sr = 1.0, si = 0.0;
+    if (ax > 0.0) {
+        sr = y0 / ax;
+        si = y1 / ax;
+    }
+    y0 = c.u_ref * sr - 0.0 * si;
+    y1 = c.u_ref * si + 0.0 * sr;
+}
+
 template <int T> struct Tile {
     double* jac;
     double* xvec;
@@ -135,6 +203,8 @@ template <int T> struct Tile {
     int32_t const* ovr_entry{nullptr}; // [4]
     double const* ovr_y{nullptr};      // [4][2]
     uint8_t const* dead{nullptr};      // [n_bus]
+    uint8_t const* lg_status{nullptr}; // REG instantiations: status of every load_gen
+    uint8_t* qviol{nullptr};           // REG instantiations: Q limit each bus ran into (0 none, 1 lower, 2 upper)
 
     __device__ __forceinline__ Blk load_blk(int k) const {
         double const* p = jac + (size_t)k * 4 * T;
@@ -150,8 +220,8 @@ template <int T> struct Tile {
 };
 
 // ---- up-sweep row task -------------------------------------------------------------------------------------------
-template <int T, Mode mode, bool OVL = false>
-__device__ __forceinline__ bool up_row(DevStructure const& s, Tile<T> const& t, int row) {
+template <int T, Mode mode, bool OVL = false, bool REG = false>
+__device__ __forceinline__ bool up_row(DevStructure const& s, Tile<T> const& t, int row, [[maybe_unused]] bool check_now = false) {
     int const rb = __ldg(s.row_ptr + row), re = __ldg(s.row_ptr + row + 1), dg = __ldg(s.diag + row);
     double const uir = t.u[(size_t)(row * 2) * T], uii = t.u[(size_t)(row * 2 + 1) * T];
     double acc0 = 0.0, acc1 = 0.0; // NR: -P, -Q then mismatch ; linear: rhs (re, im)
@@ -196,8 +266,29 @@ __device__ __forceinline__ bool up_row(DevStructure const& s, Tile<T> const& t, 
     }
     // loads
     double const v = t.pol[(size_t)(row * 2 + 1) * T];
+    // REG (PV buses): loads and sources depend on the Q limit the bus may run into right now, the row sums above do not: a bus
+    // that hits its limit repeats what follows with its regulating generators clamped
+    [[maybe_unused]] PvControl ctl{false, false, 0.0, 0.0, 0.0};
+    [[maybe_unused]] int viol = 0;
+    [[maybe_unused]] Blk const d_rows = d;
+    [[maybe_unused]] double const rows0 = acc0, rows1 = acc1;
+    [[maybe_unused]] int const lg_first = __ldg(s.lg_ptr + row), lg_count = __ldg(s.lg_ptr + row + 1) - lg_first;
+    if constexpr (REG && mode == Mode::newton) {
+        ctl = pv_control_of_row<T>(s, t, row);
+        viol = t.qviol[(size_t)row * T];
+    }
+    constexpr int n_pass = (REG && mode == Mode::newton) ? 2 : 1;
+#pragma unroll 1
+    for (int pass = 0; pass < n_pass; ++pass) {
+    if constexpr (REG && mode == Mode::newton) {
+        d = d_rows;
+        acc0 = rows0;
+        acc1 = rows1;
+    }
     for (int lg = __ldg(s.lg_ptr + row), lge = __ldg(s.lg_ptr + row + 1); lg < lge; ++lg) {
-        double const ps = t.sinj[(size_t)(lg * 2) * T], qs = t.sinj[(size_t)(lg * 2 + 1) * T];
+        double const ps = t.sinj[(size_t)(lg * 2) * T];
+        double qs = t.sinj[(size_t)(lg * 2 + 1) * T];
+        if constexpr (REG) qs = regulated_q<T, mode>(s, t, lg, viol, qs);
         if constexpr (mode == Mode::newton) {
             int const type = __ldg(s.lg_type + lg);
             if (type == 0) {
@@ -251,6 +342,30 @@ __device__ __forceinline__ bool up_row(DevStructure const& s, Tile<T> const& t, 
             d.a10 += yi;
             acc0 += yr * usr - yi * usi;
             acc1 += yr * usi + yi * usr;
+        }
+    }
+    if constexpr (REG && mode == Mode::newton) {
+        if (pass == 0 && check_now && ctl.has_limits && viol == 0) {
+            viol = check_q_limit<T>(s, t, lg_first, lg_count, ctl, acc1);
+            if (viol != 0) {
+                t.qviol[(size_t)row * T] = (uint8_t)viol;
+                continue;
+            }
+        }
+    }
+    break;
+    }
+    if constexpr (REG && mode == Mode::newton) {
+        if (ctl.regulated && viol == 0) { // PV row (:549-587): the Q row of every block of the row goes, |V| is held
+            d.a10 = 0.0;
+            d.a11 = v;
+            acc1 = 0.0;
+            for (int k = rb; k < re; ++k) {
+                if (k == dg) continue;
+                double* p = t.jac + (size_t)k * 4 * T;
+                p[T] = 0.0;
+                p[3 * T] = 0.0;
+            }
         }
     }
 
@@ -342,7 +457,7 @@ __device__ __forceinline__ bool up_row(DevStructure const& s, Tile<T> const& t, 
 }
 
 // ---- down-sweep row task: returns |dU| of the bus (newton) -----------------------------------------------------------
-template <int T, Mode mode> __device__ __forceinline__ double down_row(DevStructure const& s, Tile<T> const& t, int row) {
+template <int T, Mode mode, bool REG = false> __device__ __forceinline__ double down_row(DevStructure const& s, Tile<T> const& t, int row) {
     int const re = __ldg(s.row_ptr + row + 1), dg = __ldg(s.diag + row);
     double y0 = t.xvec[(size_t)(row * 2) * T], y1 = t.xvec[(size_t)(row * 2 + 1) * T];
     for (int e = re - 1; e > dg; --e) {
@@ -370,6 +485,7 @@ template <int T, Mode mode> __device__ __forceinline__ double down_row(DevStruct
         our = t.u[(size_t)(row * 2) * T];
         oui = t.u[(size_t)(row * 2 + 1) * T];
     }
+    if constexpr (REG && mode == Mode::linear_init) pv_start_voltage(pv_control_of_row<T>(s, t, row), y0, y1);
     return polar_update<T, mode>(t.pol + (size_t)(row * 2) * T, t.u + (size_t)(row * 2) * T, y0, y1, th, v, our, oui);
 }
 

@@ -10,6 +10,8 @@
 
 #include <cuda_runtime.h>
 
+#include <stdexcept>
+
 namespace pgmb {
 
 using namespace nrsym;
@@ -59,6 +61,8 @@ template <int T> struct TileR { // restrict-qualified view: the arrays never ali
     int32_t const* ovr_entry{nullptr}; // branch-outage overlay of the lane's scenario (nr_sym_common.cuh: load_y / is_dead)
     double const* ovr_y{nullptr};
     uint8_t const* dead{nullptr};
+    uint8_t const* lg_status{nullptr}; // REG instantiations (PV buses, nr_sym_common.cuh)
+    uint8_t* qviol{nullptr};
     __device__ __forceinline__ Blk load_blk(int k) const {
         double const* p = jac + (size_t)k * 4 * T;
         return {p[0], p[T], p[2 * T], p[3 * T]};
@@ -72,8 +76,9 @@ template <int T> struct TileR { // restrict-qualified view: the arrays never ali
     }
 };
 
-template <int T, Mode mode, bool OVL>
-__device__ __forceinline__ bool up_tree_row(DevStructure const& s, TileR<T> const& t, int32_t const* __restrict__ rec) {
+template <int T, Mode mode, bool OVL, bool REG = false>
+__device__ __forceinline__ bool up_tree_row(DevStructure const& s, TileR<T> const& t, int32_t const* __restrict__ rec,
+                                            [[maybe_unused]] bool check_now = false) {
     int const row = rec[0], k_d = rec[1], ky_d = rec[2];
     int const n_lower = rec[3] & 0xfff, n_upper = (rec[3] >> 12) & 0xfff;
     int const lg0 = rec[4] & 0xffffff, n_lg = (rec[4] >> 24) & 0x7f;
@@ -139,8 +144,27 @@ __device__ __forceinline__ bool up_tree_row(DevStructure const& s, TileR<T> cons
     }
     // loads and sources on the diagonal (same statements as the generic row task)
     double const v = t.pol[(size_t)(row * 2 + 1) * T];
+    // REG (PV buses): see the generic row task (nr_sym_common.cuh up_row)
+    [[maybe_unused]] PvControl ctl{false, false, 0.0, 0.0, 0.0};
+    [[maybe_unused]] int viol = 0;
+    [[maybe_unused]] Blk const d_rows = d;
+    [[maybe_unused]] double const rows0 = acc0, rows1 = acc1;
+    if constexpr (REG && mode == Mode::newton) {
+        ctl = pv_control<T>(s, t, lg0, n_lg, n_src);
+        viol = t.qviol[(size_t)row * T];
+    }
+    constexpr int n_pass = (REG && mode == Mode::newton) ? 2 : 1;
+#pragma unroll 1
+    for (int pass = 0; pass < n_pass; ++pass) {
+    if constexpr (REG && mode == Mode::newton) {
+        d = d_rows;
+        acc0 = rows0;
+        acc1 = rows1;
+    }
     for (int lg = lg0; lg < lg0 + n_lg; ++lg) {
-        double const ps = t.sinj[(size_t)(lg * 2) * T], qs = t.sinj[(size_t)(lg * 2 + 1) * T];
+        double const ps = t.sinj[(size_t)(lg * 2) * T];
+        double qs = t.sinj[(size_t)(lg * 2 + 1) * T];
+        if constexpr (REG) qs = regulated_q<T, mode>(s, t, lg, viol, qs);
         if constexpr (mode == Mode::newton) {
             int const type = __ldg(s.lg_type + lg);
             if (type == 0) {
@@ -194,6 +218,28 @@ __device__ __forceinline__ bool up_tree_row(DevStructure const& s, TileR<T> cons
             acc1 += yr * usi + yi * usr;
         }
     }
+    if constexpr (REG && mode == Mode::newton) {
+        if (pass == 0 && check_now && ctl.has_limits && viol == 0) {
+            viol = check_q_limit<T>(s, t, lg0, n_lg, ctl, acc1);
+            if (viol != 0) {
+                t.qviol[(size_t)row * T] = (uint8_t)viol;
+                continue;
+            }
+        }
+    }
+    break;
+    }
+    [[maybe_unused]] bool pv_row = false;
+    if constexpr (REG && mode == Mode::newton) {
+        pv_row = ctl.regulated && viol == 0;
+        if (pv_row) { // PV row (:549-587): the Q row of every block of the row goes, |V| is held
+            d.a10 = 0.0;
+            d.a11 = v;
+            acc1 = 0.0;
+            ub.a10 = 0.0;
+            ub.a11 = 0.0;
+        }
+    }
 
     if (is_dead<OVL>(t, row)) { // bus without supply: identity row, zero right-hand side (its entries were skipped above)
         d = {1.0, 0.0, 0.0, 1.0};
@@ -214,6 +260,12 @@ __device__ __forceinline__ bool up_tree_row(DevStructure const& s, TileR<T> cons
                 a = {h, -n, n, h};
             } else {
                 a = {yr, yi, -yi, yr};
+            }
+        }
+        if constexpr (REG && mode == Mode::newton) {
+            if (pv_row) {
+                a.a10 = 0.0;
+                a.a11 = 0.0;
             }
         }
         Blk const piv = t.load_blk(kd_c);
@@ -269,8 +321,8 @@ __device__ __forceinline__ bool up_tree_row(DevStructure const& s, TileR<T> cons
     return singular;
 }
 
-template <int T, Mode mode>
-__device__ __forceinline__ double down_tree_row(TileR<T> const& t, int32_t const* __restrict__ rec) {
+template <int T, Mode mode, bool REG = false>
+__device__ __forceinline__ double down_tree_row(TileR<T> const& t, int32_t const* __restrict__ rec, [[maybe_unused]] DevStructure const* s = nullptr) {
     int const row = rec[0], k_d = rec[1];
     int const n_lower = rec[3] & 0xfff, n_upper = (rec[3] >> 12) & 0xfff;
     double y0 = t.xvec[(size_t)(row * 2) * T], y1 = t.xvec[(size_t)(row * 2 + 1) * T];
@@ -301,13 +353,14 @@ __device__ __forceinline__ double down_tree_row(TileR<T> const& t, int32_t const
     }
     t.xvec[(size_t)(row * 2) * T] = y0;
     t.xvec[(size_t)(row * 2 + 1) * T] = y1;
+    if constexpr (REG && mode == Mode::linear_init) pv_start_voltage(pv_control_of_row<T>(*s, t, row), y0, y1);
     return polar_update<T, mode>(t.pol + (size_t)(row * 2) * T, t.u + (size_t)(row * 2) * T, y0, y1, th, v, our, oui);
 }
 
-template <int T, Mode mode, bool OVL>
+template <int T, Mode mode, bool OVL, bool REG>
 __device__ __forceinline__ void sweeps_v2(DevStructure const& s, Tile<T> const& tg, TileR<T> const& t,
                                           blk::TileB<T, 1, true> const& tw, int32_t const* prog, int slot, int n_slot,
-                                          bool active, bool& singular, double& dev, unsigned long long* phase) {
+                                          bool active, bool& singular, double& dev, unsigned long long* phase, bool check_now) {
     constexpr blk::Mode wmode = mode == Mode::newton ? blk::Mode::newton : blk::Mode::linear_init;
     int32_t const* level_ptr = prog;
     int32_t const* task_off = prog + s.n_level + 1;
@@ -319,16 +372,16 @@ __device__ __forceinline__ void sweeps_v2(DevStructure const& s, Tile<T> const& 
                 int32_t const* rec = prog + task_off[i];
                 if (s.n_wide != 0 && __ldg(s.row_is_wide + rec[0])) continue; // eliminated below by the whole block
                 if (rec[3] >> 24) {
-                    singular |= up_tree_row<T, mode, OVL>(s, t, rec);
+                    singular |= up_tree_row<T, mode, OVL, REG>(s, t, rec, check_now);
                 } else {
-                    singular |= up_row<T, mode, OVL>(s, tg, rec[0]);
+                    singular |= up_row<T, mode, OVL, REG>(s, tg, rec[0], check_now);
                 }
             }
         }
         __syncthreads();
         if (s.n_wide != 0)
             for (int w = __ldg(s.wide_level_ptr + lv); w < __ldg(s.wide_level_ptr + lv + 1); ++w)
-                blk::wide_up_row<T, 1, wmode, true>(s, tw, w, slot, n_slot, active, singular);
+                blk::wide_up_row<T, 1, wmode, true, REG>(s, tw, w, slot, n_slot, active, singular, check_now);
         if (phase != nullptr && threadIdx.x == 0) {
             long long const t1 = clock64();
             phase[lv == 0 ? 0 : 1] += (unsigned long long)(t1 - t0);
@@ -341,9 +394,9 @@ __device__ __forceinline__ void sweeps_v2(DevStructure const& s, Tile<T> const& 
             for (int i = b + slot; i < e; i += n_slot) {
                 int32_t const* rec = prog + task_off[i];
                 if (rec[3] >> 24) {
-                    dev = fmax(dev, down_tree_row<T, mode>(t, rec));
+                    dev = fmax(dev, down_tree_row<T, mode, REG>(t, rec, &s));
                 } else {
-                    dev = fmax(dev, down_row<T, mode>(s, tg, rec[0]));
+                    dev = fmax(dev, down_row<T, mode, REG>(s, tg, rec[0]));
                 }
             }
         }
@@ -359,10 +412,12 @@ __device__ __forceinline__ void sweeps_v2(DevStructure const& s, Tile<T> const& 
 } // namespace
 
 // OVL: batches with a branch-outage overlay (kernels.cuh: DevOverlay); capped at 128 registers like the plain kernel uses
-template <int T, bool OVL> __global__ void __launch_bounds__(512, 1) nr_sym_v2_kernel(DevStructure s, DevBatch b, SolveOptions opt, int prog_in_smem) {
+// REG: the grid has voltage regulators (PV buses; nr_sym_common.cuh)
+template <int T, bool OVL, bool REG> __global__ void __launch_bounds__(512, 1) nr_sym_v2_kernel(DevStructure s, DevBatch b, SolveOptions opt, int prog_in_smem) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ unsigned long long sh_dev[T];
     __shared__ int sh_singular[T];
+    __shared__ int sh_has_limits[T]; // REG: the scenario has a PV bus with a usable Q limit (limit check from iteration 2 on)
     __shared__ __align__(8) uint64_t sh_mbar;
     int const lane = threadIdx.x % T;
     int const slot = threadIdx.x / T;
@@ -390,7 +445,11 @@ template <int T, bool OVL> __global__ void __launch_bounds__(512, 1) nr_sym_v2_k
         tg.ovr_y = b.ovl.y + scn * 4 * 2;
         if (b.ovl.dead_off != nullptr && b.ovl.dead_off[scn] >= 0) tg.dead = b.ovl.dead + (size_t)b.ovl.dead_off[scn] * s.n_bus;
     }
-    TileR<T> const t{tg.jac, tg.xvec, tg.pol, tg.u, tg.perm, tg.sinj, tg.usrc, tg.ovr_entry, tg.ovr_y, tg.dead};
+    if (REG) {
+        tg.lg_status = b.lg_status + (size_t)tile * s.n_load_gen * T + lane;
+        tg.qviol = b.qviol + (size_t)tile * s.n_bus * T + lane;
+    }
+    TileR<T> const t{tg.jac, tg.xvec, tg.pol, tg.u, tg.perm, tg.sinj, tg.usrc, tg.ovr_entry, tg.ovr_y, tg.dead, tg.lg_status, tg.qviol};
     blk::TileB<T, 1, true> tw;
     tw.ovr_entry = tg.ovr_entry;
     tw.ovr_y = tg.ovr_y;
@@ -402,6 +461,8 @@ template <int T, bool OVL> __global__ void __launch_bounds__(512, 1) nr_sym_v2_k
     tw.perm = tg.perm;
     tw.sinj = tg.sinj;
     tw.usrc = tg.usrc;
+    tw.lg_status = tg.lg_status;
+    tw.qviol = tg.qviol;
     tw.wide_terms = b.wide_terms ? b.wide_terms + (size_t)tile * s.wide_max_upd * 4 * T + lane : nullptr;
     tw.wide_rhs = b.wide_rhs ? b.wide_rhs + (size_t)tile * s.wide_max_lower * 2 * T + lane : nullptr;
     tw.wide_sum = b.wide_sum ? b.wide_sum + (size_t)tile * s.wide_max_entries * 2 * T + lane : nullptr;
@@ -409,8 +470,18 @@ template <int T, bool OVL> __global__ void __launch_bounds__(512, 1) nr_sym_v2_k
     if (threadIdx.x < T) {
         sh_dev[threadIdx.x] = 0ull;
         sh_singular[threadIdx.x] = 0;
+        sh_has_limits[threadIdx.x] = 0;
     }
     __syncthreads();
+    if constexpr (REG) { // set_bus_types_and_q_limits (newton_raphson_pf_solver.hpp:400-444); no limit has been hit yet
+        if (valid) {
+            for (int row = slot; row < s.n_bus; row += n_slot) {
+                tg.qviol[(size_t)row * T] = 0;
+                if (__ldg(s.lg_ptr + row) != __ldg(s.lg_ptr + row + 1) && pv_control_of_row<T>(s, tg, row).has_limits) sh_has_limits[lane] = 1;
+            }
+        }
+        __syncthreads();
+    }
 
     bool done = !valid;
     int status = kStatusOk;
@@ -420,7 +491,7 @@ template <int T, bool OVL> __global__ void __launch_bounds__(512, 1) nr_sym_v2_k
     {
         bool singular = false;
         double dev = 0.0;
-        sweeps_v2<T, Mode::linear_init, OVL>(s, tg, t, tw, prog, slot, n_slot, !done, singular, dev, phase);
+        sweeps_v2<T, Mode::linear_init, OVL, REG>(s, tg, t, tw, prog, slot, n_slot, !done, singular, dev, phase, false);
         if (singular) sh_singular[lane] = 1;
         __syncthreads();
         if (!done && sh_singular[lane]) {
@@ -440,7 +511,7 @@ template <int T, bool OVL> __global__ void __launch_bounds__(512, 1) nr_sym_v2_k
         if (!__syncthreads_or(!done)) break;
         bool singular = false;
         double dev = 0.0;
-        sweeps_v2<T, Mode::newton, OVL>(s, tg, t, tw, prog, slot, n_slot, !done, singular, dev, phase ? phase + 4 : nullptr);
+        sweeps_v2<T, Mode::newton, OVL, REG>(s, tg, t, tw, prog, slot, n_slot, !done, singular, dev, phase ? phase + 4 : nullptr, REG && num_iter >= 2);
         if (!done) {
             if (singular) sh_singular[lane] = 1;
             atomicMax(&sh_dev[lane], (unsigned long long)__double_as_longlong(dev));
@@ -452,7 +523,13 @@ template <int T, bool OVL> __global__ void __launch_bounds__(512, 1) nr_sym_v2_k
                 done = true;
             } else {
                 max_dev = __longlong_as_double((long long)sh_dev[lane]);
-                if (!(max_dev > opt.err_tol)) done = true;
+                if (!(max_dev > opt.err_tol)) {
+                    if (REG && sh_has_limits[lane] && num_iter < 2) {
+                        max_dev = INFINITY; // converged before the limit check: one more iteration (:343-347)
+                    } else {
+                        done = true;
+                    }
+                }
             }
         }
         __syncthreads();
@@ -473,12 +550,18 @@ static void launch_v2_t(DevStructure const& s, DevBatch const& b, SolveOptions c
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     bool const in_smem = prog_bytes + 1024 <= (size_t)max_optin;
     size_t const dyn = in_smem ? prog_bytes : 0;
-    if (b.ovl.entry != nullptr) {
-        cudaFuncSetAttribute(nr_sym_v2_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-        nr_sym_v2_kernel<T, true><<<b.n_tile, T * n_slot, dyn, st>>>(s, b, opt, in_smem ? 1 : 0);
+    if (s.lg_reg != nullptr) { // voltage regulators (the engine sends overlay batches of such grids to the block kernel)
+        if (b.ovl.entry != nullptr || b.qviol == nullptr || b.lg_status == nullptr) {
+            throw std::logic_error("nr_sym_v2: a grid with voltage regulators needs the qviol / lg_status buffers and no overlay");
+        }
+        cudaFuncSetAttribute(nr_sym_v2_kernel<T, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        nr_sym_v2_kernel<T, false, true><<<b.n_tile, T * n_slot, dyn, st>>>(s, b, opt, in_smem ? 1 : 0);
+    } else if (b.ovl.entry != nullptr) {
+        cudaFuncSetAttribute(nr_sym_v2_kernel<T, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        nr_sym_v2_kernel<T, true, false><<<b.n_tile, T * n_slot, dyn, st>>>(s, b, opt, in_smem ? 1 : 0);
     } else {
-        cudaFuncSetAttribute(nr_sym_v2_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-        nr_sym_v2_kernel<T, false><<<b.n_tile, T * n_slot, dyn, st>>>(s, b, opt, in_smem ? 1 : 0);
+        cudaFuncSetAttribute(nr_sym_v2_kernel<T, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        nr_sym_v2_kernel<T, false, false><<<b.n_tile, T * n_slot, dyn, st>>>(s, b, opt, in_smem ? 1 : 0);
     }
 }
 

@@ -155,34 +155,6 @@ __device__ __forceinline__ bool finish_row(TileP<T> const& t, int row, int k_d, 
     return singular;
 }
 
-// ---- PV buses (voltage regulators; newton_raphson_pf_solver.hpp:400-452, 549-587, 605-742) -----------------------------------
-// The same decisions, in the same order, as the generic block kernel takes for B = 1 (block_common.cuh: bus_control,
-// check_q_limit, pv_diag, zero_pv_rows): results are bit-identical to it.
-constexpr double kQTol = 1e-8;
-struct PvControl {
-    bool regulated, has_limits;
-    double u_ref, q_min, q_max;
-};
-template <int T> __device__ __forceinline__ bool lg_regulating(DevStructure const& s, TileP<T> const& t, int lg, int& reg) {
-    reg = __ldg(s.lg_reg + lg);
-    return reg >= 0 && __ldg(s.reg_param + 4 * reg) != 0.0 && t.lg_status[(size_t)lg * T] != 0;
-}
-template <int T> __device__ __forceinline__ PvControl pv_control(DevStructure const& s, TileP<T> const& t, int lg0, int n_lg, int n_src) {
-    PvControl c{false, false, 0.0, 0.0, 0.0};
-    if (n_src != 0) return c; // slack bus
-    for (int lg = lg0; lg < lg0 + n_lg; ++lg) {
-        int reg;
-        if (lg_regulating<T>(s, t, lg, reg)) {
-            c.regulated = true;
-            c.u_ref = __ldg(s.reg_param + 4 * reg + 1);
-            c.q_min += __ldg(s.reg_param + 4 * reg + 2);
-            c.q_max += __ldg(s.reg_param + 4 * reg + 3);
-        }
-    }
-    c.has_limits = c.regulated && (!isnan(c.q_min) || !isnan(c.q_max));
-    return c;
-}
-
 // ---- build phase -----------------------------------------------------------------------------------------------------
 // own blocks of one row: diagonal d, block towards the parent ub, mismatch / right-hand side acc, blocks towards the
 // children (stored to their LU slots).  rec = 8-word head; lower = per-child words (null for a leaf).
@@ -268,13 +240,7 @@ __device__ __forceinline__ void build_row(DevStructure const& s, TileP<T> const&
     for (int lg = lg0; lg < lg0 + n_lg; ++lg) {
         double const ps = t.sinj[(size_t)(lg * 2) * T];
         double qs = t.sinj[(size_t)(lg * 2 + 1) * T];
-        if constexpr (REG) {
-            int reg;
-            bool const regulating = lg_regulating<T>(s, t, lg, reg);
-            // linear start: the specified Q of a regulating generator is ignored; Newton: clamped once the bus hit a limit
-            if (regulating && mode == Mode::linear_init) qs = 0.0;
-            if (regulating && mode == Mode::newton && viol != 0) qs = __ldg(s.reg_param + 4 * reg + (viol == 2 ? 3 : 2));
-        }
+        if constexpr (REG) qs = regulated_q<T, mode>(s, t, lg, viol, qs);
         if constexpr (mode == Mode::newton) {
             int const type = __ldg(s.lg_type + lg);
             if (type == 0) {
@@ -329,15 +295,8 @@ __device__ __forceinline__ void build_row(DevStructure const& s, TileP<T> const&
         }
     }
     if constexpr (REG && mode == Mode::newton) {
-        if (pass == 0 && check_now && ctl.has_limits && viol == 0) { // enforce_q_limits (:605-704)
-            double spec = 0.0;
-            for (int lg = lg0; lg < lg0 + n_lg; ++lg) {
-                int reg;
-                if (lg_regulating<T>(s, t, lg, reg)) spec += t.sinj[(size_t)(lg * 2 + 1) * T];
-            }
-            double const q_total = spec - acc1;
-            if (!isnan(ctl.q_max) && q_total > ctl.q_max + kQTol) viol = 2;
-            else if (!isnan(ctl.q_min) && q_total < ctl.q_min - kQTol) viol = 1;
+        if (pass == 0 && check_now && ctl.has_limits && viol == 0) {
+            viol = check_q_limit<T>(s, t, lg0, n_lg, ctl, acc1);
             if (viol != 0) {
                 t.qviol[(size_t)row * T] = (uint8_t)viol;
                 continue; // the bus is PQ from now on: its injections again, with the clamped generators
@@ -634,20 +593,7 @@ __device__ __forceinline__ double down_step(TileP<T> const& t, int row, bool has
     t.xvec[(size_t)(row * 2 + 1) * T] = y1;
     x0 = y0;
     x1 = y1;
-    if constexpr (REG && mode == Mode::linear_init) { // a PV bus starts at its reference magnitude: u = u_ref * u / |u| (:446-452)
-        int const lg0 = __ldg(s->lg_ptr + row), lg1 = __ldg(s->lg_ptr + row + 1);
-        PvControl const ctl = pv_control<T>(*s, t, lg0, lg1 - lg0, __ldg(s->src_ptr + row + 1) - __ldg(s->src_ptr + row));
-        if (ctl.regulated) {
-            double const ax = sqrt(y0 * y0 + y1 * y1);
-            double sr = 1.0, si = 0.0;
-            if (ax > 0.0) {
-                sr = y0 / ax;
-                si = y1 / ax;
-            }
-            y0 = ctl.u_ref * sr - 0.0 * si;
-            y1 = ctl.u_ref * si + 0.0 * sr;
-        }
-    }
+    if constexpr (REG && mode == Mode::linear_init) pv_start_voltage(pv_control_of_row<T>(*s, t, row), y0, y1);
     return polar_update<T, mode>(t.pol + (size_t)(row * 2) * T, t.u + (size_t)(row * 2) * T, y0, y1, o.th, o.v, o.our, o.oui);
 }
 
@@ -900,9 +846,7 @@ template <int T, bool SMEM, bool RING, bool REG> __global__ void __launch_bounds
         if (valid) {
             for (int row = slot; row < s.n_bus; row += n_slot) {
                 t.qviol[(size_t)row * T] = 0;
-                int const lg0 = __ldg(s.lg_ptr + row), lg1 = __ldg(s.lg_ptr + row + 1);
-                if (lg0 != lg1 && pv_control<T>(s, t, lg0, lg1 - lg0, __ldg(s.src_ptr + row + 1) - __ldg(s.src_ptr + row)).has_limits)
-                    sh_has_limits[lane] = 1;
+                if (__ldg(s.lg_ptr + row) != __ldg(s.lg_ptr + row + 1) && pv_control_of_row<T>(s, t, row).has_limits) sh_has_limits[lane] = 1;
             }
         }
         __syncthreads();

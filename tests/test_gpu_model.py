@@ -485,14 +485,16 @@ def test_edge_batches():
     assert res["sym_load"]["energized"][0, 0] == 0 and res["sym_load"]["p"][0, 0] == 0.0
 
 
+@pytest.mark.parametrize("rings", [False, True])
 @pytest.mark.parametrize("q_lim", [None, 2e5])
-def test_regulated_radial_grid_path_kernel_equals_block_kernel(q_lim, monkeypatch):
-    """radial grids with voltage regulators run the path kernel's PV instantiation (nr_sym_v3, REG); PGMB_REG_PATH=0 selects
-    the generic block kernel with B = 1.  Same decisions in the same order: identical iteration counts, limit flags and values."""
+def test_regulated_grid_symmetric_kernels_equal_the_block_kernel(q_lim, rings, monkeypatch):
+    """symmetric grids with voltage regulators run the PV instantiations of the path kernel (radial grids, nr_sym_v3) and the
+    level kernel (meshed grids, nr_sym_v2); PGMB_REG_PATH=0 selects the generic block kernel with B = 1.  Same decisions in the
+    same order: identical iteration counts, limit flags and values."""
     import grids
 
     n_scn = 64
-    _, inp, update = grids.regulated_benchmark_grid(False, q_lim=q_lim, n_scn=n_scn)
+    _, inp, update = grids.regulated_benchmark_grid(rings, q_lim=q_lim, n_scn=n_scn)
     a = pgm_b200.PowerGridModel(inp)
     res_path = a.calculate_power_flow(symmetric=True, update_data=update, continue_on_batch_error=True)
     st_path, it_path, t_path = a.status.copy(), a.n_iter.copy(), a.timing()["solve_kernel"]
@@ -506,4 +508,5 @@ def test_regulated_radial_grid_path_kernel_equals_block_kernel(q_lim, monkeypatc
         for f in res_path[c].dtype.names:
             x, y = res_path[c][f][ok], res_block[c][f][ok]
             assert np.array_equal(x, y, equal_nan=x.dtype.kind == "f"), (c, f, float(np.nanmax(np.abs(x - y))) if x.dtype.kind == "f" else None)
-    print(f"regulated radial grid, {n_scn} scenarios: path kernel {t_path:.2f} ms, block kernel {b.timing()['solve_kernel']:.2f} ms")
+    print(f"regulated {'ringed' if rings else 'radial'} grid, {n_scn} scenarios: {'level' if rings else 'path'} kernel {t_path:.2f} ms, "
+          f"block kernel {b.timing()['solve_kernel']:.2f} ms")
