@@ -1373,10 +1373,137 @@ int64_t Model::calculate_impl(ModelOptions const& opt, UpdateData const* update,
             std::vector<std::string> messages(n);
             std::vector<int64_t> failed_per_thread(n_threads, 0);
             std::vector<std::exception_ptr> fatal(n_threads);
+            // Scenarios with the SAME structural update (byte-identical rows of everything but loads / generators) share one
+            // topology, one set of symbolic structures and engines: such a group is applied once and its load updates run as one
+            // batch through the device pipeline -- "grouped by symbolic pattern" for batches that revisit a few switching states.
+            // PGMB_GROUP_SCENARIOS=0: every scenario on its own (comparison).
+            std::vector<std::vector<Idx>> groups;
+            UpdateData structural_part = *update, load_part{};
+            structural_part.sym_gen = structural_part.asym_gen = structural_part.sym_load = structural_part.asym_load = ComponentBuffer{};
+            load_part.n_scenarios = n;
+            load_part.sym_gen = update->sym_gen;
+            load_part.asym_gen = update->asym_gen;
+            load_part.sym_load = update->sym_load;
+            load_part.asym_load = update->asym_load;
+            {
+                bool dense_loads = true;
+                for (ComponentBuffer const* b : {&update->sym_gen, &update->asym_gen, &update->sym_load, &update->asym_load})
+                    if (b->data != nullptr && (b->indptr != nullptr || b->n < 0)) dense_loads = false;
+                char const* env = std::getenv("PGMB_GROUP_SCENARIOS");
+                if (dense_loads && opt.tap_strategy == 0 && n_todo >= 2 && !(env != nullptr && std::atoi(env) == 0)) {
+                    std::pair<ComponentBuffer const*, size_t> const parts[] = {
+                        {&update->line, sizeof(BranchUpdate)}, {&update->transformer, sizeof(TransformerUpdate)},
+                        {&update->shunt, sizeof(ShuntUpdate)}, {&update->source, sizeof(SourceUpdate)},
+                        {&update->voltage_regulator, sizeof(VoltageRegulatorUpdate)}, {&update->asym_line, sizeof(BranchUpdate)},
+                        {&update->generic_branch, sizeof(BranchUpdate)}, {&update->link, sizeof(BranchUpdate)},
+                        {&update->three_winding_transformer, sizeof(ThreeWindingTransformerUpdate)},
+                        {&update->transformer_tap_regulator, sizeof(TransformerTapRegulatorUpdate)}};
+                    std::unordered_map<std::string, size_t> group_of;
+                    for (Idx const sc : todo) {
+                        std::string key;
+                        for (auto const& [b, row] : parts) {
+                            if (b->data == nullptr) continue;
+                            auto const* base = static_cast<char const*>(b->data);
+                            Idx const r0 = b->indptr != nullptr ? b->indptr[sc] : sc * b->n, r1 = b->indptr != nullptr ? b->indptr[sc + 1] : (sc + 1) * b->n;
+                            int64_t const count = r1 - r0;
+                            key.append(reinterpret_cast<char const*>(&count), sizeof(count));
+                            key.append(base + r0 * static_cast<Idx>(row), static_cast<size_t>(count) * row);
+                        }
+                        auto const [it, fresh] = group_of.emplace(std::move(key), groups.size());
+                        if (fresh) groups.emplace_back();
+                        groups[it->second].push_back(sc);
+                    }
+                    if (groups.size() == static_cast<size_t>(n_todo)) groups.clear(); // nothing shared
+                }
+            }
+            if (!groups.empty()) n_threads = std::max<Idx>(1, std::min<Idx>(n_threads, static_cast<Idx>(groups.size())));
+            if (std::getenv("PGMB_DEBUG_N1") != nullptr && !groups.empty()) {
+                std::fprintf(stderr, "[pgmb groups] %zu scenarios in %zu groups\n", todo.size(), groups.size());
+            }
+            // one group: its structure once, its loads as one device batch; false = take the scenarios one by one
+            auto run_group = [&](Model& model, std::vector<Idx> const& g, Idx t) -> bool {
+                if (g.size() < 2) return false;
+                Saved saved;
+                bool handled = false;
+                try {
+                    model.apply_scenario(structural_part, g[0], &saved);
+                    model.template check_regulators<B>(opt);
+                    model.template prepare_engines<B>();
+                    Idx const gn = static_cast<Idx>(g.size());
+                    UpdateData compact{};
+                    compact.n_scenarios = gn;
+                    std::vector<unsigned char> rows[4];
+                    ComponentBuffer const* src[4] = {&load_part.sym_gen, &load_part.asym_gen, &load_part.sym_load, &load_part.asym_load};
+                    ComponentBuffer* dst[4] = {&compact.sym_gen, &compact.asym_gen, &compact.sym_load, &compact.asym_load};
+                    size_t const urow[4] = {sizeof(SymLoadGenUpdate), sizeof(AsymLoadGenUpdate), sizeof(SymLoadGenUpdate), sizeof(AsymLoadGenUpdate)};
+                    for (int b = 0; b != 4; ++b) {
+                        if (src[b]->data == nullptr) continue;
+                        size_t const bytes = static_cast<size_t>(src[b]->n) * urow[b];
+                        rows[b].resize(bytes * g.size());
+                        for (size_t k = 0; k != g.size(); ++k)
+                            std::memcpy(rows[b].data() + k * bytes, static_cast<unsigned char const*>(src[b]->data) + static_cast<size_t>(g[k]) * bytes, bytes);
+                        *dst[b] = ComponentBuffer{src[b]->n, nullptr, rows[b].data()};
+                    }
+                    if (model.device_path_eligible(compact)) {
+                        std::vector<int32_t> it(g.size(), 0), st(g.size(), 0);
+                        ModelOptions go = opt;
+                        go.n_devices = 1;
+                        go.flags = 0;
+                        go.device = model.device_;
+                        model.batch_message.clear();
+                        // the pass writes every scenario's output rows straight to its place in the caller's batch
+                        model.out_scatter_ = g.data();
+                        int64_t r = -1;
+                        try {
+                            r = model.run_batch_device_one(go, B, compact, out, it.data(), st.data(), 0);
+                        } catch (...) {
+                            model.out_scatter_ = nullptr;
+                            throw;
+                        }
+                        model.out_scatter_ = nullptr;
+                        if (r >= 0) {
+                            for (size_t i = 0; i != g.size(); ++i) {
+                                if (n_iter != nullptr) n_iter[g[i]] = it[i];
+                                if (status != nullptr) status[g[i]] = st[i];
+                            }
+                            // the pipeline numbers its failures inside the group: back to the caller's scenario numbers
+                            std::string const& all = model.batch_message;
+                            std::string const tag = "Error in batch #";
+                            size_t pos = all.find(tag);
+                            while (pos != std::string::npos) {
+                                size_t const next = all.find(tag, pos + tag.size());
+                                std::string const entry = all.substr(pos, next == std::string::npos ? std::string::npos : next - pos);
+                                size_t const colon = entry.find(':');
+                                Idx const local = std::strtoll(entry.c_str() + tag.size(), nullptr, 10);
+                                if (colon != std::string::npos && local >= 0 && local < gn) messages[g[local]] = tag + std::to_string(g[local]) + entry.substr(colon);
+                                pos = next;
+                            }
+                            failed_per_thread[t] += r;
+                            handled = true;
+                        }
+                        model.batch_message.clear();
+                    }
+                } catch (CudaError const&) {
+                    model.restore(saved);
+                    throw;
+                } catch (std::exception const&) {
+                    handled = false; // the scenario-by-scenario route records each scenario's own message
+                    model.batch_message.clear();
+                }
+                model.restore(saved);
+                return handled;
+            };
             auto worker = [&](Model& model, Idx t) {
                 try {
-                    for (Idx k = t; k < n_todo; k += n_threads) {
-                        Idx const s = todo[k];
+                    std::vector<Idx> mine; // scenarios this thread takes one by one
+                    if (groups.empty()) {
+                        for (Idx k = t; k < n_todo; k += n_threads) mine.push_back(todo[k]);
+                    } else {
+                        for (size_t gi = static_cast<size_t>(t); gi < groups.size(); gi += static_cast<size_t>(n_threads)) {
+                            if (!run_group(model, groups[gi], t)) mine.insert(mine.end(), groups[gi].begin(), groups[gi].end());
+                        }
+                    }
+                    for (Idx const s : mine) {
                         Saved saved;
                         try {
                             model.apply_scenario(*update, s, &saved);

@@ -282,6 +282,9 @@ class Model {
     };
     BridgeInfo bridge_analysis() const;
     OutagePlan const* outage_plan_{nullptr};
+    // device pass over a GROUP of scenarios (model.cpp: grouped route): scenario i of the pass delivers its output rows to
+    // scenario out_scatter_[i] of the caller's buffers (which are then the whole batch's buffers, not a slice)
+    Idx const* out_scatter_{nullptr};
     template <int B> bool plan_outage_batch(UpdateData const& update, OutagePlan& plan) const;
     // ---- device path (model_device.cpp): updates applied and output structs written by CUDA kernels ----
     struct DeviceSide;

@@ -305,6 +305,7 @@ int64_t Model::run_batch_device_one(ModelOptions const& opt, int phases, UpdateD
         UpdateData u;
         OutputData o;
         slice_batch(update, out, parts, s0, ns, u, o);
+        if (out_scatter_ != nullptr) o = out; // scattered delivery addresses the caller's buffers by scenario number
         ModelOptions mo = opt;
         mo.flags = 0; // parts reuse the device buffers: nothing stays resident
         int64_t const r = run_batch_device_part(mo, phases, u, o, n_iter ? n_iter + s0 : nullptr, status ? status + s0 : nullptr,
@@ -715,7 +716,14 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
         PGMB_CUDA(cudaGetLastError());
         for (Req const& r : reqs) {
             if (r.host == nullptr || r.count == 0 || resident_out) continue;
-            size_t const off = static_cast<size_t>(s0) * r.count * r.row;
+            size_t const blk = static_cast<size_t>(r.count) * r.row, off = static_cast<size_t>(s0) * blk;
+            if (out_scatter_ != nullptr && !slot_staged[r.slot]) { // every scenario's rows to its own place in the caller's batch
+                for (int64_t i = 0; i != ns; ++i) {
+                    PGMB_CUDA(cudaMemcpyAsync(static_cast<unsigned char*>(r.host) + static_cast<size_t>(out_scatter_[first_scenario + s0 + i]) * blk,
+                                              d.out[r.slot].get() + off + static_cast<size_t>(i) * blk, blk, cudaMemcpyDeviceToHost, q));
+                }
+                continue;
+            }
             unsigned char* const dst = slot_staged[r.slot] ? stage + stage_off[r.slot] + off : static_cast<unsigned char*>(r.host) + off;
             PGMB_CUDA(cudaMemcpyAsync(dst, d.out[r.slot].get() + off, static_cast<size_t>(ns) * r.count * r.row,
                                       cudaMemcpyDeviceToHost, q));
@@ -746,7 +754,15 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
             for (Req const& r : reqs) {
                 if (r.host == nullptr || r.count == 0 || !slot_staged[r.slot]) continue;
                 size_t const off = static_cast<size_t>(s0) * r.count * r.row, bytes = static_cast<size_t>(ns) * r.count * r.row;
-                pieces.push_back({static_cast<unsigned char*>(r.host) + off, stage + stage_off[r.slot] + off, bytes});
+                if (out_scatter_ != nullptr) {
+                    size_t const blk = static_cast<size_t>(r.count) * r.row;
+                    for (int64_t i = 0; i != ns; ++i) {
+                        pieces.push_back({static_cast<unsigned char*>(r.host) + static_cast<size_t>(out_scatter_[first_scenario + s0 + i]) * blk,
+                                          stage + stage_off[r.slot] + off + static_cast<size_t>(i) * blk, blk});
+                    }
+                } else {
+                    pieces.push_back({static_cast<unsigned char*>(r.host) + off, stage + stage_off[r.slot] + off, bytes});
+                }
                 total += bytes;
             }
             unsigned const n_thr = total < (size_t{4} << 20) ? 1u : n_copy;

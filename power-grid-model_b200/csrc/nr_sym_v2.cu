@@ -554,13 +554,13 @@ static void launch_v2_t(DevStructure const& s, DevBatch const& b, SolveOptions c
         if (b.ovl.entry != nullptr || b.qviol == nullptr || b.lg_status == nullptr) {
             throw std::logic_error("nr_sym_v2: a grid with voltage regulators needs the qviol / lg_status buffers and no overlay");
         }
-        cudaFuncSetAttribute(nr_sym_v2_kernel<T, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        cudaFuncSetAttribute(nr_sym_v2_kernel<T, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 1024);
         nr_sym_v2_kernel<T, false, true><<<b.n_tile, T * n_slot, dyn, st>>>(s, b, opt, in_smem ? 1 : 0);
     } else if (b.ovl.entry != nullptr) {
-        cudaFuncSetAttribute(nr_sym_v2_kernel<T, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        cudaFuncSetAttribute(nr_sym_v2_kernel<T, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 1024);
         nr_sym_v2_kernel<T, true, false><<<b.n_tile, T * n_slot, dyn, st>>>(s, b, opt, in_smem ? 1 : 0);
     } else {
-        cudaFuncSetAttribute(nr_sym_v2_kernel<T, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        cudaFuncSetAttribute(nr_sym_v2_kernel<T, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 1024);
         nr_sym_v2_kernel<T, false, false><<<b.n_tile, T * n_slot, dyn, st>>>(s, b, opt, in_smem ? 1 : 0);
     }
 }

@@ -922,14 +922,16 @@ static void launch_v3_t(DevStructure const& s, DevBatch const& b, SolveOptions c
         char const* v = std::getenv("PGMB_V3_RING"); // 0: chain operands through registers / L1 prefetch only (comparison)
         return v != nullptr && *v != '\0' ? std::atoi(v) : 1;
     }();
+    // The attribute is one value per kernel and device, shared by every host thread that launches it (the scenario-by-scenario
+    // route runs engines of different grids at once): always the device limit, never this launch's own size.
     bool const in_smem = prog_bytes + 1024 <= (size_t)max_optin;
     bool const with_ring = in_smem && want_ring != 0 && prog_bytes + ring_bytes + 1024 <= (size_t)max_optin;
     if (with_ring) {
         size_t const dyn = prog_bytes + ring_bytes;
-        cudaFuncSetAttribute(nr_sym_v3_kernel<T, true, true, REG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        cudaFuncSetAttribute(nr_sym_v3_kernel<T, true, true, REG>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 1024);
         nr_sym_v3_kernel<T, true, true, REG><<<b.n_tile, T * n_slot, dyn, st>>>(s, b, opt);
     } else if (in_smem) {
-        cudaFuncSetAttribute(nr_sym_v3_kernel<T, true, false, REG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prog_bytes);
+        cudaFuncSetAttribute(nr_sym_v3_kernel<T, true, false, REG>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - 1024);
         nr_sym_v3_kernel<T, true, false, REG><<<b.n_tile, T * n_slot, prog_bytes, st>>>(s, b, opt);
     } else {
         nr_sym_v3_kernel<T, false, false, REG><<<b.n_tile, T * n_slot, 0, st>>>(s, b, opt);

@@ -510,3 +510,44 @@ def test_regulated_grid_symmetric_kernels_equal_the_block_kernel(q_lim, rings, m
             assert np.array_equal(x, y, equal_nan=x.dtype.kind == "f"), (c, f, float(np.nanmax(np.abs(x - y))) if x.dtype.kind == "f" else None)
     print(f"regulated {'ringed' if rings else 'radial'} grid, {n_scn} scenarios: {'level' if rings else 'path'} kernel {t_path:.2f} ms, "
           f"block kernel {b.timing()['solve_kernel']:.2f} ms")
+
+
+@pytest.mark.parametrize("sym", [True, False])
+def test_scenarios_with_the_same_switching_state_run_as_one_group(sym, monkeypatch):
+    """a batch that revisits a few switching states (two lines out / a transformer tap moved / a shunt off) with different loads:
+    scenarios with byte-identical structural updates share one topology + engine build and run as ONE device batch; the
+    scenario-by-scenario route (PGMB_GROUP_SCENARIOS=0) and the oracle give the same results"""
+    grid = pgm_b200.FictionalGrid(seed=2, has_mv_ring=True, has_lv_ring=True, n_node_total_specified=300, n_mv_feeder=3,
+                                  n_node_per_mv_feeder=5, n_lv_feeder=3, n_connection_per_lv_feeder=10)
+    n_scn, n_state = 48, 4
+    update = dict(grid.batch_update(n_scn, seed=4))
+    lines, trafos = grid.input_data["line"], grid.input_data["transformer"]
+    line_upd = pgm_b200.structs.initialize_array("update", "line", (n_scn, 2))
+    trafo_upd = pgm_b200.structs.initialize_array("update", "transformer", (n_scn, 1))
+    ring_lines = lines["id"][-4:]  # ring closures: switching them keeps the grid connected
+    for s in range(n_scn):
+        state = s % n_state
+        line_upd["id"][s] = ring_lines[[0, 1]] if state < 2 else ring_lines[[2, 3]]
+        line_upd["from_status"][s] = 0 if state in (0, 2) else 1
+        line_upd["to_status"][s] = 0 if state in (0, 2) else 1
+        trafo_upd["id"][s, 0] = trafos["id"][1]
+        trafo_upd["tap_pos"][s, 0] = [0, 1, -1, 2][state]
+    update["line"], update["transformer"] = line_upd, trafo_upd
+    ref = orc.Model(grid.input_data).calculate(sym=sym, update=update, threading=0)
+    assert ref["n_failed"] == 0
+    model = pgm_b200.PowerGridModel(grid.input_data)
+    launches0 = int(pgm_b200.lib().pgmb_kernel_launch_count())
+    grouped = model.calculate_power_flow(symmetric=sym, update_data=update)
+    launches_grouped = int(pgm_b200.lib().pgmb_kernel_launch_count()) - launches0
+    assert (model.status == 0).all() and np.array_equal(model.n_iter, ref["n_iter"])
+    _compare_with_oracle(grouped, ref, n_scn)
+    monkeypatch.setenv("PGMB_GROUP_SCENARIOS", "0")
+    single = model.calculate_power_flow(symmetric=sym, update_data=update)
+    launches_single = int(pgm_b200.lib().pgmb_kernel_launch_count()) - launches0 - launches_grouped
+    assert np.array_equal(model.n_iter, ref["n_iter"])
+    _compare_with_oracle(single, ref, n_scn)
+    assert launches_grouped < launches_single
+    # the model is unchanged afterwards
+    base = model.calculate_power_flow(symmetric=sym)
+    base_ref = orc.Model(grid.input_data).calculate(sym=sym)
+    _compare_with_oracle({k: v[None] for k, v in base.items()}, base_ref, 1)
