@@ -1358,7 +1358,9 @@ int64_t Model::calculate_impl(ModelOptions const& opt, UpdateData const* update,
             }
             Idx const n_todo = static_cast<Idx>(todo.size());
             Idx n_threads = opt.threading > 0 ? opt.threading : static_cast<Idx>(std::thread::hardware_concurrency());
-            n_threads = std::max<Idx>(1, std::min<Idx>({n_threads, n_todo, Idx{32}}));
+            Idx max_threads = 32;
+            if (char const* env = std::getenv("PGMB_MAX_HOST_THREADS")) max_threads = std::max(1, std::atoi(env));
+            n_threads = std::max<Idx>(1, std::min<Idx>({n_threads, n_todo, max_threads}));
             // several GPUs (opt.n_devices / PGMB_DEVICES): the host threads are dealt round robin over the devices
             Idx n_dev_general = opt.n_devices;
             if (n_dev_general <= 1) {
