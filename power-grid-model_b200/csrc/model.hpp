@@ -291,6 +291,7 @@ class Model {
     std::shared_ptr<DeviceSide> dev_;
     bool device_path_eligible(UpdateData const& update) const;
     void fetch_resident_rows(int slot, size_t row_bytes, Idx count, Idx index, Idx n_scn, void* dst) const;
+    int last_pass_parts_{1}; // parts the last run_batch_device_one split its batch into (device-memory budget)
     int64_t run_batch_device(ModelOptions const& opt, int phases, UpdateData const& update, OutputData const& out, int32_t* n_iter,
                              int32_t* status);
     int64_t run_batch_device_one(ModelOptions const& opt, int phases, UpdateData const& update, OutputData const& out,

@@ -296,6 +296,7 @@ int64_t Model::run_batch_device_one(ModelOptions const& opt, int phases, UpdateD
     if (char const* env = std::getenv("PGMB_MAX_BATCH_BYTES")) budget = static_cast<size_t>(std::atoll(env));
     Idx const n_scn = update.n_scenarios;
     Idx max_scn = static_cast<Idx>(std::max<size_t>(32, budget / per_scn / 32 * 32));
+    last_pass_parts_ = n_scn <= max_scn ? 1 : static_cast<int>((n_scn + max_scn - 1) / max_scn);
     if (n_scn <= max_scn) return run_batch_device_part(opt, phases, update, out, n_iter, status, first_scenario);
     OutPart parts[13];
     for (int k = 0; k != 13; ++k) parts[k] = {outs[k].row, outs[k].count};

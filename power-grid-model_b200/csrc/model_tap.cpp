@@ -635,6 +635,7 @@ int64_t Model::run_tap_lockstep(ModelOptions const& opt, UpdateData const& updat
         }
         batch_message.clear();
         if (run_pass(true, probe, pass_iter.data(), pass_status.data()) < 0) return -1;
+        if (last_pass_parts_ != 1) return -1; // the batch does not fit one pass: its results are not resident as a whole
         fetch_resident_rows(0, sizeof(NodeOutput<B>), nn, control_node, n, node_probe.data());
         fetch_resident_rows(2, sizeof(BranchOutput<B>), n_trafo(), ti, n, trafo_probe.data());
         for (Idx s = 0; s != n; ++s) {
