@@ -76,3 +76,38 @@ def test_benchmark_batch_through_the_reference_wrapper():
     assert set(theirs) == set(ours)
     for comp in ours:
         assert theirs[comp].tobytes() == ours[comp].tobytes(), comp
+
+
+import json  # noqa: E402
+import os  # noqa: E402
+
+TAP_CASES = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tap_regulator_cases.json")))["cases"]
+TAP_RUNS = [(n, s, m, b) for n, c in sorted(TAP_CASES.items()) for s, m, b in vc.case_runs(c)]
+
+
+@pytest.mark.parametrize("name,sym,method,is_batch", TAP_RUNS,
+                         ids=[f"{n}-{'sym' if s else 'asym'}-{m}-{'batch' if b else 'single'}" for n, s, m, b in TAP_RUNS])
+def test_tap_regulator_case_through_the_reference_wrapper(name, sym, method, is_batch):
+    """the reference's automatic-tap-regulator validation cases through its unchanged wrapper:
+    calculate_power_flow(tap_changing_strategy=...) -> PGM_set_tap_changing_strategy + PGM_calculate of libpgm_b200.so"""
+    from power_grid_model.errors import PowerGridError
+
+    case = TAP_CASES[name]
+    params = case["params"]
+    model = pgm.PowerGridModel(vc.to_numpy(case["input"], "input"))
+    kind = "sym_output" if sym else "asym_output"
+    kw = dict(symmetric=sym, calculation_method=method, tap_changing_strategy=params["tap_changing_strategy"])
+    if is_batch:
+        kw["update_data"] = vc.batch_update_arrays(vc.to_numpy(case["update_batch"], "update"))
+    if "raises" in params:
+        with pytest.raises(PowerGridError, match="Maximum number of iterations reached"):
+            model.calculate_power_flow(**kw)
+        return
+    res = model.calculate_power_flow(**kw)
+    res = {str(k.value if hasattr(k, "value") else k): v for k, v in res.items()}
+    assert "transformer_tap_regulator" in res
+    if is_batch:
+        for s, exp in enumerate(vc.to_numpy(case[kind + "_batch"], kind)):
+            vc.compare_result({k: v[s] for k, v in res.items()}, exp, params["rtol"], params["atol"])
+    else:
+        vc.compare_result(res, vc.to_numpy(case[kind], kind), params["rtol"], params["atol"])
