@@ -10,6 +10,7 @@
 
 #include <cuda_runtime.h>
 
+#include <cstdio>
 #include <stdexcept>
 
 namespace pgmb {
@@ -385,7 +386,14 @@ __device__ __forceinline__ void sweeps_v2(DevStructure const& s, Tile<T> const& 
         if (phase != nullptr && threadIdx.x == 0) {
             long long const t1 = clock64();
             phase[lv == 0 ? 0 : 1] += (unsigned long long)(t1 - t0);
+#ifdef V2_LEVEL_DEBUG
+            if (blockIdx.x == 0 && mode == Mode::newton)
+                printf("up level %d rows %d wide %d kcycles %lld\n", lv, e - b,
+                       s.n_wide != 0 ? __ldg(s.wide_level_ptr + lv + 1) - __ldg(s.wide_level_ptr + lv) : 0, (t1 - t0) / 1000);
+            t0 = clock64();
+#else
             t0 = t1;
+#endif
         }
     }
     for (int lv = s.n_level - 1; lv >= 0; --lv) {
