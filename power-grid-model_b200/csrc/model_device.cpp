@@ -643,11 +643,12 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
 
     try {
     for (int c = 0; c != n_chunk; ++c) {
-        cudaStream_t const q = d.cs[c];
+        // one chunk (device-resident pipeline): everything stays on the engine stream, no fork / join between streams
+        cudaStream_t const q = n_chunk == 1 ? st : d.cs[c];
         int64_t const tile_b = n_tile * c / n_chunk, tile_e = n_tile * (c + 1) / n_chunk;
         DevBatch const view = e.batch_view(tile_b, tile_e);
         int64_t const s0 = tile_b * tw, ns = view.n_scn;
-        PGMB_CUDA(cudaStreamWaitEvent(q, d.fork, 0));
+        if (q != st) PGMB_CUDA(cudaStreamWaitEvent(q, d.fork, 0));
         DevUpdateBuffers ub{};
         ub.id_mismatch = d.flag.get();
         for (int bfr = 0; bfr != 4; ++bfr) {
@@ -729,8 +730,10 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
             PGMB_CUDA(cudaMemcpyAsync(dst, d.out[r.slot].get() + off, static_cast<size_t>(ns) * r.count * r.row,
                                       cudaMemcpyDeviceToHost, q));
         }
-        PGMB_CUDA(cudaEventRecord(d.ev_end[c], q));
-        PGMB_CUDA(cudaStreamWaitEvent(st, d.ev_end[c], 0)); // join: the engine stream sees the end of every chunk
+        if (q != st) {
+            PGMB_CUDA(cudaEventRecord(d.ev_end[c], q));
+            PGMB_CUDA(cudaStreamWaitEvent(st, d.ev_end[c], 0)); // join: the engine stream sees the end of every chunk
+        }
     }
     PGMB_CUDA(cudaEventRecord(d.ev_p1, st));
     timing[1] += ms_since(t0);
@@ -741,7 +744,7 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
         unsigned const n_copy = env_thr != nullptr ? static_cast<unsigned>(std::max(1, std::min(64, std::atoi(env_thr))))
                                                    : std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
         for (int c = 0; c != n_chunk; ++c) {
-            PGMB_CUDA(cudaStreamSynchronize(d.cs[c]));
+            PGMB_CUDA(cudaStreamSynchronize(n_chunk == 1 ? st : d.cs[c]));
             int64_t const tile_b = n_tile * c / n_chunk, tile_e = n_tile * (c + 1) / n_chunk;
             int64_t const s0 = tile_b * tw, ns = std::min<int64_t>(tile_e * tw, n_scn) - s0;
             if (ns <= 0) continue;
@@ -784,7 +787,7 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
             }
         }
     }
-    for (int c = 0; c != n_chunk; ++c) PGMB_CUDA(cudaStreamSynchronize(d.cs[c]));
+    for (int c = 0; c != n_chunk; ++c) PGMB_CUDA(cudaStreamSynchronize(n_chunk == 1 ? st : d.cs[c]));
     } catch (...) {
         d.drain(); // copies into caller / staging memory may still be in flight
         throw;
