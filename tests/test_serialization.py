@@ -3,6 +3,7 @@ the reference's own dataset files (kept verbatim in tests/golden/power_flow_case
 with an independent loader; datasets are written and read back in every format / layout; the reference's unchanged Python
 wrapper runs its json_* / msgpack_* utilities on top of the library.  No GPU needed."""
 import json
+import os
 
 import numpy as np
 import pytest
@@ -12,7 +13,9 @@ import reference_wrapper
 import validation_cases as vc
 from pgm_b200 import pgm_core
 
-CASES = vc.load_cases()
+CASES = dict(vc.load_cases())
+# the automatic-tap-regulator cases bring transformer_tap_regulator datasets (input, update batches, outputs)
+CASES.update(json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tap_regulator_cases.json")))["cases"])
 
 
 def _same(a, b):
