@@ -482,6 +482,24 @@ int64_t orc_model_calculate(void* bag, void* model, int sym, int method, double 
     return st == ok ? failed : -1;
 }
 
+// ranking of the regulated transformers by the automatic tap changer (tap_optimizer.hpp rank_transformers): rows of
+// (kind: 0 transformer / 1 three-winding transformer, index within the kind, rank group) into bag.i["tap_rank"]
+int orc_model_tap_rank(void* bag, void* model) {
+    return guarded(static_cast<Bag*>(bag), [&] {
+        auto& m = *static_cast<ModelHandle*>(model)->model;
+        auto& out = static_cast<Bag*>(bag)->i["tap_rank"];
+        out.clear();
+        auto const groups = m.rank_transformers();
+        for (size_t g = 0; g != groups.size(); ++g) {
+            for (auto const& idx : groups[g]) {
+                out.push_back(idx.group);
+                out.push_back(idx.pos);
+                out.push_back(static_cast<int64_t>(g));
+            }
+        }
+    });
+}
+
 int64_t orc_hardware_concurrency() { return static_cast<int64_t>(std::thread::hardware_concurrency()); }
 
 } // extern "C"

@@ -245,6 +245,14 @@ class Model:
         assert st == 0, bag.error
         return bag
 
+    def tap_rank(self):
+        """rows (kind, index, rank group) of the regulated transformers in the order the tap changer visits them"""
+        bag = Bag()
+        st = lib.orc_model_tap_rank(bag.h, self.h)
+        if st != 0:
+            raise RuntimeError(bag.error)
+        return bag.i64("tap_rank").reshape(-1, 3)
+
     def calculate(self, sym=True, method="newton_raphson", err_tol=1e-8, max_iter=20, threading=-1, update=None,
                   output_components=None, reuse_ic_factorization=False, out=None, tap_changing_strategy=0):
         """update: None or dict component -> array of shape (n_scn, n_per) or {"data": flat, "indptr": ...}.

@@ -142,3 +142,70 @@ def test_regulator_checks_at_model_creation():
         pgm_b200.PowerGridModel({**base, "transformer_tap_regulator": _regulators([(30, 10, 2)])})
     model = pgm_b200.PowerGridModel({**base, "transformer_tap_regulator": _regulators([(30, 10, 1)])})
     assert model.math_index(0, "tap_rank").tolist() == [0, 0, 0]
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_ranking_equals_the_oracle_on_random_grids(seed):
+    """random grids (tree + a few loops) of lines, links, transformers and three-winding transformers with regulators on random
+    sides, some switched off, some branches open, one or two sources: the product's ranking (model_tap.cpp) and the oracle's
+    (oracle/tap_optimizer.hpp) give the same groups in the same order, or both refuse the configuration"""
+    import oracle_lib as orc
+
+    rng = np.random.default_rng(1000 + seed)
+    n_node = int(rng.integers(6, 40))
+    data = {"node": _nodes([(i, 10e3) for i in range(n_node)])}
+    next_id = [n_node]
+
+    def new_id():
+        next_id[0] += 1
+        return next_id[0]
+
+    edges = [(int(rng.integers(0, i)), i) for i in range(1, n_node)]
+    for _ in range(int(rng.integers(0, 4))):
+        a, b = (int(x) for x in rng.integers(0, n_node, 2))
+        if a != b:
+            edges.append((a, b))
+    kinds = rng.choice(["line", "link", "transformer"], size=len(edges), p=[0.4, 0.15, 0.45])
+    lines, links, trafos, regs = [], [], [], []
+    for (a, b), kind in zip(edges, kinds):
+        i = new_id()
+        if kind == "line":
+            lines.append((i, a, b))
+        elif kind == "link":
+            links.append((i, a, b))
+        else:
+            trafos.append((i, a, b, int(rng.integers(0, 2)), int(rng.random() > 0.1)))
+            if rng.random() < 0.7:
+                regs.append((new_id(), i, 1 if rng.random() < 0.9 else 0))  # mostly away from the source (node 0 feeds the tree)
+    t3w = None
+    if n_node >= 8 and rng.random() < 0.4:
+        n1, n2, n3 = sorted(int(x) for x in rng.choice(n_node, 3, replace=False))
+        t3w = _trafo3w(new_id(), n1, n2, n3, int(rng.integers(0, 3)))
+        if rng.random() < 0.8:
+            regs.append((new_id(), int(t3w["id"][0]), int(rng.integers(1, 3))))
+    if lines:
+        data["line"] = _branches("line", lines)
+        data["line"]["from_status"][rng.random(len(lines)) < 0.1] = 0
+    if links:
+        data["link"] = _branches("link", links)
+    if trafos:
+        data["transformer"] = _trafos(trafos)
+    if t3w is not None:
+        data["three_winding_transformer"] = t3w
+    sources = [_source(new_id(), 0)]
+    if rng.random() < 0.3:
+        sources.append(_source(new_id(), int(rng.integers(1, n_node))))
+        sources[-1]["status"] = int(rng.random() < 0.7)
+    data["source"] = np.concatenate(sources)
+    if regs:
+        data["transformer_tap_regulator"] = _regulators(regs)
+        data["transformer_tap_regulator"]["status"][rng.random(len(regs)) < 0.2] = 0
+    oracle = orc.Model(data)
+    try:
+        expected = oracle.tap_rank().tolist()
+    except RuntimeError as err:
+        with pytest.raises(pgm_b200.PgmB200Error) as mine:
+            _rank(data)
+        assert str(mine.value) == str(err)
+        return
+    assert _rank(data) == expected
