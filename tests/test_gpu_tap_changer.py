@@ -147,3 +147,39 @@ def test_lockstep_search_equals_the_scenario_by_scenario_search(strategy, sym, m
     assert (lock["transformer_tap_regulator"]["energized"] == 1).all()
     parity.compare_outputs(lock, exact, [c for c in lock if c != "transformer_tap_regulator"])
     assert launches_lock < launches_exact  # a handful of batched passes against several power flows per scenario
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_regulated_grids_equal_the_oracle(seed):
+    """small fictional grids with a regulator on every transformer, random set points / bands / line-drop compensation, random
+    regulators switched off: for every strategy the product ends at the oracle's tap positions, or both report the search as
+    failed for the same scenarios"""
+    import oracle_lib as orc
+
+    rng = np.random.default_rng(500 + seed)
+    grid = pgm_b200.FictionalGrid(seed=seed, n_node_total_specified=int(rng.integers(80, 300)), n_mv_feeder=int(rng.integers(2, 4)),
+                                  n_node_per_mv_feeder=int(rng.integers(3, 6)), n_lv_feeder=int(rng.integers(2, 4)),
+                                  n_connection_per_lv_feeder=int(rng.integers(4, 10)), has_mv_ring=bool(seed % 2), has_lv_ring=bool(seed % 3 == 0))
+    data = dict(grid.input_data)
+    trafo, node = data["transformer"], data["node"]
+    reg = pgm_b200.structs.initialize_array("input", "transformer_tap_regulator", len(trafo))
+    first_id = 1 + max(int(a["id"].max()) for a in data.values() if len(a))
+    for k, t in enumerate(trafo):
+        u_rated = float(node["u_rated"][node["id"] == t["to_node"]][0])
+        step = float(t["tap_size"]) * u_rated / float(t["u2"])
+        reg[k] = (first_id + k, t["id"], int(rng.random() > 0.15), 1, rng.uniform(0.97, 1.06) * u_rated, step * rng.uniform(0.6, 2.5),
+                  rng.choice([np.nan, 0.0, 0.05]), rng.choice([np.nan, 0.0, 0.1]))
+    data["transformer_tap_regulator"] = reg
+    n_scn = 6
+    update = grid.batch_update(n_scn, seed=seed)
+    comps = ["node", "transformer_tap_regulator"]
+    model, oracle = pgm_b200.PowerGridModel(data), orc.Model(data)
+    for strategy in ("any_valid_tap", "min_voltage_tap", "max_voltage_tap", "fast_any_tap"):
+        ref = oracle.calculate(sym=True, update=update, threading=0, tap_changing_strategy=strategy, output_components=comps)
+        res = model.calculate_power_flow(update_data=update, tap_changing_strategy=strategy, output_component_types=comps,
+                                         continue_on_batch_error=True)
+        assert np.array_equal(model.status != 0, ref["status"] != 0), (strategy, model.status, ref["status"], ref["error"][:300])
+        ok = ref["status"] == 0
+        assert np.array_equal(res["transformer_tap_regulator"]["tap_pos"][ok], ref["transformer_tap_regulator"]["tap_pos"][ok]), strategy
+        if ok.any():
+            assert np.max(np.abs(res["node"]["u_pu"][ok] - ref["node"]["u_pu"][ok])) < 1e-9, strategy
