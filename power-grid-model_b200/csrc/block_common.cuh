@@ -39,8 +39,9 @@ template <int T, int B, bool SymPerm = false> struct TileB {
     uint8_t const* lg_status; // [n_load_gen][T]
     uint8_t* qviol;           // [n_bus][T]
     // branch-outage overlay of this lane's scenario (DevOverlay), null = none
-    int32_t const* ovr_entry{nullptr}; // [4]
-    double const* ovr_y{nullptr};      // [4][B*B][2]
+    int32_t const* ovr_entry{nullptr}; // [ovr_n]
+    double const* ovr_y{nullptr};      // [ovr_n][B*B][2]
+    int ovr_n{0};                      // 4 per switched-branch slot of the batch
     uint8_t const* dead{nullptr};      // [n_bus] buses without supply in this scenario: identity rows, voltage 0
     __device__ __forceinline__ void get_q(int bus, uint8_t* q) const {
         if constexpr (SymPerm) {
@@ -315,8 +316,7 @@ __device__ __forceinline__ void build_entry(DevStructure const& s, TileB<T, B, S
         double y[BB2];
         double const* ysrc = s.ydata + (size_t)ky * BB2;
         if (t.ovr_entry != nullptr) { // this scenario replaces the entries of its switched branch
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < t.ovr_n; ++j)
                 if (t.ovr_entry[j] == ky) ysrc = t.ovr_y + j * BB2;
         }
 #pragma unroll

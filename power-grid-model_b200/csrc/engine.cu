@@ -418,9 +418,10 @@ void Engine::launch_regulator_apply(DevBatch const& view, int8_t* out_reg, cudaS
 }
 
 void Engine::set_overlay(int64_t n_scn, int64_t const* math_branch, double const* bparam, int32_t const* comp,
-                         uint8_t const* energized, int32_t const* dead_off, uint8_t const* dead, size_t dead_bytes) {
+                         uint8_t const* energized, int32_t const* dead_off, uint8_t const* dead, size_t dead_bytes, int n_slot) {
     if (device_ < 0) throw CudaError("engine was created without a CUDA device (symbolic only)");
     if (n_scn != db_.n_scn) throw InvalidArgument("overlay size differs from the staged batch");
+    if (n_slot < 1) throw InvalidArgument("overlay needs at least one branch slot per scenario");
     PGMB_CUDA(cudaSetDevice(device_));
     size_t const bb2 = static_cast<size_t>(B_) * B_ * 2;
     if (branch_entries_.empty()) {
@@ -429,38 +430,47 @@ void Engine::set_overlay(int64_t n_scn, int64_t const* math_branch, double const
             for (Idx e = pattern_.y_bus_entry_indptr[entry]; e != pattern_.y_bus_entry_indptr[entry + 1]; ++e)
                 if (pattern_.element_type[e] < 4) branch_entries_[pattern_.element_idx[e]][pattern_.element_type[e]] = static_cast<int32_t>(entry);
     }
-    std::vector<int32_t> entry(n_scn * 4, -1), branch(n_scn, -1);
-    std::vector<double> y(n_scn * 4 * bb2, 0.0);
+    size_t const K = static_cast<size_t>(n_slot), E = 4 * K;
+    std::vector<int32_t> entry(n_scn * E, -1), branch(n_scn * K, -1);
+    std::vector<double> y(n_scn * E * bb2, 0.0);
     for (int64_t s = 0; s != n_scn; ++s) {
-        Idx const br = math_branch[s];
-        if (br < 0) continue;
-        if (br >= topo_.n_branch()) throw InvalidArgument("overlay branch out of range");
-        branch[s] = static_cast<int32_t>(br);
-        double const* np = bparam + s * 4 * bb2;
-        for (int k = 0; k != 4; ++k) {
-            int32_t const en = branch_entries_[br][k];
-            entry[s * 4 + k] = en;
-            if (en < 0) continue;
-            // the same sum as Engine::set_param, with this branch's contributions replaced
-            double* yo = &y[(s * 4 + k) * bb2];
-            for (Idx e = pattern_.y_bus_entry_indptr[en]; e != pattern_.y_bus_entry_indptr[en + 1]; ++e) {
-                int const kind = pattern_.element_type[e];
-                Idx const idx = pattern_.element_idx[e];
-                double const* src = kind == 4 ? &shunt_param_[idx * bb2] : (idx == br ? np + kind * bb2 : &branch_param_[(idx * 4 + kind) * bb2]);
-                for (size_t i = 0; i != bb2; ++i) yo[i] += src[i];
+        int64_t const* const br = math_branch + s * K;
+        double const* const np = bparam + s * K * 4 * bb2;
+        size_t n_entry = 0;
+        for (size_t j = 0; j != K; ++j) {
+            if (br[j] < 0) continue;
+            if (br[j] >= topo_.n_branch()) throw InvalidArgument("overlay branch out of range");
+            branch[s * K + j] = static_cast<int32_t>(br[j]);
+            for (int k = 0; k != 4; ++k) {
+                int32_t const en = branch_entries_[br[j]][k];
+                int32_t* const list = &entry[s * E];
+                if (en < 0 || std::find(list, list + n_entry, en) != list + n_entry) continue; // shared with an earlier branch
+                list[n_entry] = en;
+                // the same sum as Engine::set_param, with the contributions of this scenario's branches replaced
+                double* yo = &y[(s * E + n_entry) * bb2];
+                ++n_entry;
+                for (Idx e = pattern_.y_bus_entry_indptr[en]; e != pattern_.y_bus_entry_indptr[en + 1]; ++e) {
+                    int const kind = pattern_.element_type[e];
+                    Idx const idx = pattern_.element_idx[e];
+                    double const* src = kind == 4 ? &shunt_param_[idx * bb2] : &branch_param_[(idx * 4 + kind) * bb2];
+                    if (kind != 4)
+                        for (size_t jj = 0; jj != K; ++jj)
+                            if (br[jj] == idx) src = np + (jj * 4 + kind) * bb2;
+                    for (size_t i = 0; i != bb2; ++i) yo[i] += src[i];
+                }
             }
         }
     }
     d_ovl_entry_.upload(entry, stream_);
     d_ovl_branch_.upload(branch, stream_);
     d_ovl_y_.upload(y, stream_);
-    d_ovl_bparam_.ensure(n_scn * 4 * bb2 + 1);
-    d_ovl_comp_.ensure(n_scn + 1);
-    d_ovl_energized_.ensure(n_scn + 1);
+    d_ovl_bparam_.ensure(n_scn * K * 4 * bb2 + 1);
+    d_ovl_comp_.ensure(n_scn * K + 1);
+    d_ovl_energized_.ensure(n_scn * K + 1);
     if (n_scn != 0) {
-        PGMB_CUDA(cudaMemcpyAsync(d_ovl_bparam_.get(), bparam, n_scn * 4 * bb2 * sizeof(double), cudaMemcpyHostToDevice, stream_));
-        PGMB_CUDA(cudaMemcpyAsync(d_ovl_comp_.get(), comp, n_scn * sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
-        PGMB_CUDA(cudaMemcpyAsync(d_ovl_energized_.get(), energized, n_scn, cudaMemcpyHostToDevice, stream_));
+        PGMB_CUDA(cudaMemcpyAsync(d_ovl_bparam_.get(), bparam, n_scn * K * 4 * bb2 * sizeof(double), cudaMemcpyHostToDevice, stream_));
+        PGMB_CUDA(cudaMemcpyAsync(d_ovl_comp_.get(), comp, n_scn * K * sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
+        PGMB_CUDA(cudaMemcpyAsync(d_ovl_energized_.get(), energized, n_scn * K, cudaMemcpyHostToDevice, stream_));
     }
     bool const any_dead = dead_off != nullptr && dead != nullptr && dead_bytes != 0;
     if (any_dead) {
@@ -471,7 +481,7 @@ void Engine::set_overlay(int64_t n_scn, int64_t const* math_branch, double const
     }
     PGMB_CUDA(cudaStreamSynchronize(stream_));
     db_.ovl = DevOverlay{d_ovl_entry_.get(), d_ovl_y_.get(), d_ovl_branch_.get(), d_ovl_bparam_.get(), d_ovl_comp_.get(), d_ovl_energized_.get(),
-                         any_dead ? d_ovl_dead_off_.get() : nullptr, any_dead ? d_ovl_dead_.get() : nullptr};
+                         any_dead ? d_ovl_dead_off_.get() : nullptr, any_dead ? d_ovl_dead_.get() : nullptr, n_slot};
 }
 
 void Engine::fetch_status(int32_t* status, int32_t* n_iter) {
@@ -511,12 +521,13 @@ DevBatch Engine::batch_view(int64_t tile_begin, int64_t tile_end) const {
     v.max_dev += scn_begin;
     if (v.ovl.entry != nullptr) {
         size_t const bb2 = static_cast<size_t>(B_) * B_ * 2;
-        v.ovl.entry += scn_begin * 4;
-        v.ovl.y += scn_begin * 4 * bb2;
-        v.ovl.branch += scn_begin;
-        v.ovl.bparam += scn_begin * 4 * bb2;
-        v.ovl.comp += scn_begin;
-        v.ovl.energized += scn_begin;
+        int64_t const K = v.ovl.n_branch;
+        v.ovl.entry += scn_begin * 4 * K;
+        v.ovl.y += scn_begin * 4 * K * bb2;
+        v.ovl.branch += scn_begin * K;
+        v.ovl.bparam += scn_begin * K * 4 * bb2;
+        v.ovl.comp += scn_begin * K;
+        v.ovl.energized += scn_begin * K;
         if (v.ovl.dead_off != nullptr) v.ovl.dead_off += scn_begin;
     }
     if (v.phase_cycles != nullptr) v.phase_cycles += tile_begin * 16;

@@ -133,8 +133,10 @@ class Engine {
     // each entry's elements in the assembly order (y_bus.hpp:400-431).  comp / energized: the branch component's index and
     // `energized` flag for the output kernels.  Only the Newton-Raphson block kernel and the result kernels read the overlay.
     // dead_off / dead: per scenario the index of its mask of buses without supply ([n_mask][n_bus] bytes), -1 = none.
+    // n_slot: branch slots per scenario (N-k batches): math_branch / comp / energized are [n_scn][n_slot], bparam [n_scn][n_slot][4]...;
+    // Y-bus entries shared by several switched branches of a scenario are replaced once, with all of them taken into account.
     void set_overlay(int64_t n_scn, int64_t const* math_branch, double const* bparam, int32_t const* comp, uint8_t const* energized,
-                     int32_t const* dead_off = nullptr, uint8_t const* dead = nullptr, size_t dead_bytes = 0);
+                     int32_t const* dead_off = nullptr, uint8_t const* dead = nullptr, size_t dead_bytes = 0, int n_slot = 1);
     bool has_overlay() const { return db_.ovl.entry != nullptr; }
     void fetch_status(int32_t* status, int32_t* n_iter);
     float solve_staged(SolveOptions const& opt);            // kernels only; returns solver-kernel milliseconds

@@ -61,20 +61,22 @@ struct DevStructure {
     double const* reg_param;  // [n_regulator][4] status, u_ref, q_min, q_max (per unit; NaN = no limit)
 };
 
-// Branch-outage overlay of a batch whose scenarios each switch one branch of the shared topology (N-1 studies): the symbolic
-// pattern stays the base grid's; a scenario replaces the values of the (at most four) Y-bus entries its branch contributes to and
-// the parameters of that branch.  Scenario-major arrays; entry == nullptr when the batch has no overlay.
+// Branch-outage overlay of a batch whose scenarios each switch a few branches of the shared topology (N-1 / N-k studies): the
+// symbolic pattern stays the base grid's; a scenario replaces the values of the Y-bus entries its branches contribute to (at most
+// four per branch, shared entries once) and the parameters of those branches.  Scenario-major arrays with n_branch slots per
+// scenario (the largest number of switched branches in the batch); entry == nullptr when the batch has no overlay.
 struct DevOverlay {
-    int32_t const* entry;     // [n_scn][4] Y-bus entries (ff, ft, tf, tt) with replaced values, -1 = unused slot
-    double const* y;          // [n_scn][4][B*B][2] replacement values
-    int32_t const* branch;    // [n_scn] math branch with replaced parameters, -1 = none
-    double const* bparam;     // [n_scn][4][B*B][2]
-    int32_t const* comp;      // [n_scn] component index of that branch (lines then transformers), -1 = none
-    uint8_t const* energized; // [n_scn] its `energized` flag in this scenario
-    // buses that lose their supply in a scenario (the switched branch was a bridge): their rows become identity rows, their
+    int32_t const* entry;     // [n_scn][4 * n_branch] Y-bus entries with replaced values, -1 = unused slot
+    double const* y;          // [n_scn][4 * n_branch][B*B][2] replacement values
+    int32_t const* branch;    // [n_scn][n_branch] math branches with replaced parameters, -1 = unused slot
+    double const* bparam;     // [n_scn][n_branch][4][B*B][2]
+    int32_t const* comp;      // [n_scn][n_branch] component index of each branch (lines then transformers), -1 = none
+    uint8_t const* energized; // [n_scn][n_branch] its `energized` flag in this scenario
+    // buses that lose their supply in a scenario (the switched branches cut them off): their rows become identity rows, their
     // voltage stays 0 and everything on them is reported as not energized
     int32_t const* dead_off;  // [n_scn] index of the scenario's mask in `dead`, -1 = no bus is lost
     uint8_t const* dead;      // [n_mask][n_bus]
+    int32_t n_branch;         // slots per scenario (>= 1 when entry != nullptr)
 };
 
 // per-batch device buffers, tile layout (see above); B = phases, N = 2B

@@ -995,6 +995,7 @@ Model::BridgeInfo Model::bridge_analysis() const {
     info.order.assign(n, -1);
     for (size_t i = 0; i != source_in_.size(); ++i)
         if (source_st_[i].status) ++info.n_source[node_idx_.at(source_in_[i].node)];
+    info.self_source = info.n_source;
     std::vector<char>& bridge = info.bridge;
     std::vector<Idx>& disc = info.disc;
     disc.assign(n, -1);
@@ -1036,6 +1037,9 @@ Model::BridgeInfo Model::bridge_analysis() const {
             }
         }
     }
+    info.adj_ptr = std::move(ptr);
+    info.adj_node = std::move(adj_node);
+    info.adj_edge = std::move(adj_edge);
     return info;
 }
 
@@ -1056,10 +1060,6 @@ template <int B> bool Model::plan_outage_batch(UpdateData const& u, OutagePlan& 
     std::unordered_map<Idx, int32_t> mask_of_branch; // bridge -> its mask in plan.dead
     plan.dead_off.assign(n, -1);
     plan.dead.clear();
-    plan.math_branch.assign(n, -1);
-    plan.bparam.assign(n * 4 * bb2, 0.0);
-    plan.comp.assign(n, -1);
-    plan.energized.assign(n, 0);
     plan.exact.clear();
     auto lookup = [](ID id, Idx pos, Idx n_in_scenario, Idx n_comp, std::unordered_map<ID, Idx> const& map) -> Idx {
         if (id == kNaID) {
@@ -1074,10 +1074,14 @@ template <int B> bool Model::plan_outage_batch(UpdateData const& u, OutagePlan& 
         Idx branch;
         bool from, to;
     };
-    std::vector<Change> changes;
+    // PGMB_OUTAGE_SLOTS=1: only one switched branch per scenario on the shared pattern (comparison)
+    int max_slots = kMaxOutageSlots;
+    if (char const* env = std::getenv("PGMB_OUTAGE_SLOTS")) max_slots = std::clamp(std::atoi(env), 1, kMaxOutageSlots);
+    // pass 1: what every scenario switches
+    std::vector<std::vector<Change>> all(n);
+    std::vector<char> exact_flag(n, 0);
     for (Idx s = 0; s != n; ++s) {
-        changes.clear();
-        bool exact = false;
+        std::vector<Change>& changes = all[s];
         auto note = [&](Idx bi, IntS from, IntS to) {
             auto it = std::find_if(changes.begin(), changes.end(), [bi](Change const& c) { return c.branch == bi; });
             if (it == changes.end()) {
@@ -1096,81 +1100,164 @@ template <int B> bool Model::plan_outage_batch(UpdateData const& u, OutagePlan& 
                 auto [b, e] = scenario_span<TransformerUpdate>(u.transformer, s);
                 for (auto p = b; p != e; ++p) {
                     Idx const i = lookup(p->id, p - b, e - b, n_trafo(), trafo_idx_);
-                    if (p->tap_pos != kNaIntS && p->tap_pos != trafo_st_[i].tap_pos) exact = true;
+                    if (p->tap_pos != kNaIntS && p->tap_pos != trafo_st_[i].tap_pos) exact_flag[s] = 1;
                     note(off_trafo() + i, p->from_status, p->to_status);
                 }
             }
         } catch (InvalidArgument const&) {
             // an update that cannot be applied fails this scenario alone (job_dispatch.hpp:162-206): the per-scenario route
             // records its message and the other scenarios are still calculated
-            plan.exact.push_back(s);
+            exact_flag[s] = 1;
+            changes.clear();
             continue;
         }
         std::erase_if(changes, [this](Change const& c) { return c.from == branch_st_[c.branch].from_status && c.to == branch_st_[c.branch].to_status; });
-        if (!exact && changes.size() == 1) {
-            Change const& c = changes[0];
+        if (static_cast<int>(changes.size()) > max_slots) exact_flag[s] = 1;
+        // only branches that are closed, in the math model and between two different buses in the base state keep the pattern
+        for (Change const& c : changes) {
             Coupling const cp = topo_.branch[c.branch];
             bool const base_closed = branch_st_[c.branch].from_status && branch_st_[c.branch].to_status && cp.group == 0 &&
                                      m.branch_bus_idx[2 * cp.pos] >= 0 && m.branch_bus_idx[2 * cp.pos + 1] >= 0 &&
                                      m.branch_bus_idx[2 * cp.pos] != m.branch_bus_idx[2 * cp.pos + 1];
-            // a bridge cuts a subtree of the DFS off: fine when exactly one side keeps a source (the other side goes dark)
-            bool shared_pattern = base_closed;
-            if (base_closed && bridge[c.branch]) {
-                Idx const v = info.child[c.branch];
-                Idx const inside = info.n_source[v], outside = info.n_source[info.root[v]] - inside;
-                if ((inside == 0) == (outside == 0)) {
-                    shared_pattern = false; // two supplied islands (two math models), or an island that was dark already
-                } else {
-                    auto it = mask_of_branch.find(c.branch);
-                    if (it == mask_of_branch.end()) {
-                        int32_t const k = static_cast<int32_t>(plan.dead.size() / m.n_bus);
-                        plan.dead.resize(plan.dead.size() + m.n_bus, 0);
-                        uint8_t* mask = &plan.dead[static_cast<size_t>(k) * m.n_bus];
-                        Idx const r = info.root[v];
-                        auto mark = [&](Idx t0, Idx t1) {
-                            for (Idx t = t0; t != t1; ++t) {
-                                Coupling const nc = topo_.node[info.order[t]];
-                                if (nc.group == 0) mask[nc.pos] = 1;
-                            }
-                        };
-                        if (inside == 0) {
-                            mark(info.disc[v], info.disc[v] + info.size[v]);
-                        } else {
-                            mark(info.disc[r], info.disc[v]);
-                            mark(info.disc[v] + info.size[v], info.disc[r] + info.size[r]);
-                        }
-                        it = mask_of_branch.emplace(c.branch, k).first;
-                    }
-                    plan.dead_off[s] = it->second;
-                }
-            }
-            if (shared_pattern) {
-                plan.math_branch[s] = cp.pos;
-                plan.comp[s] = static_cast<int32_t>(c.branch);
-                plan.energized[s] = (c.from || c.to) ? 1 : 0;
-                BranchState const st{c.from, c.to};
-                if (c.branch < n_line()) {
-                    line_param<B>(line_c_[c.branch], st, &plan.bparam[s * 4 * bb2]);
-                } else {
-                    Idx const i = c.branch - off_trafo();
-                    transformer_param<B>(trafo_c_[i], st, trafo_st_[i].tap_pos, &plan.bparam[s * 4 * bb2]);
-                }
-                if (plan.dead_off[s] >= 0) { // still connected to a supplied bus?  otherwise the branch itself goes dark
-                    uint8_t const* mask = &plan.dead[static_cast<size_t>(plan.dead_off[s]) * m.n_bus];
-                    bool const from_live = c.from && mask[m.branch_bus_idx[2 * cp.pos]] == 0;
-                    bool const to_live = c.to && mask[m.branch_bus_idx[2 * cp.pos + 1]] == 0;
-                    if (!from_live && !to_live) {
-                        std::fill_n(&plan.bparam[s * 4 * bb2], 4 * bb2, 0.0);
-                        plan.energized[s] = 0;
-                    }
-                }
-            } else {
-                exact = true;
-            }
-        } else if (!changes.empty()) {
-            exact = true;
+            if (!base_closed) exact_flag[s] = 1;
         }
-        if (exact) plan.exact.push_back(s);
+    }
+    // pass 2: which buses lose their supply.  One switched branch: the bridge analysis knows; several: a search from a supplied
+    // node over the remaining closed branches.  Exactly one supplied part must remain (several = several math models: exact route)
+    std::vector<int32_t> stamp(node_.size(), -1);
+    std::vector<Idx> queue;
+    Idx n_supplied_base = 0, n_source_base = 0, start_node = -1;
+    for (Idx i = 0; i != static_cast<Idx>(node_.size()); ++i) {
+        if (topo_.node[i].group != 0) continue;
+        ++n_supplied_base;
+        n_source_base += info.self_source[i];
+        if (start_node < 0 && info.self_source[i] != 0) start_node = i;
+    }
+    std::map<std::vector<Idx>, int32_t> mask_of_set;
+    auto new_mask = [&]() -> uint8_t* {
+        plan.dead.resize(plan.dead.size() + m.n_bus, 0);
+        return &plan.dead[plan.dead.size() - m.n_bus];
+    };
+    for (Idx s = 0; s != n; ++s) {
+        std::vector<Change> const& changes = all[s];
+        if (exact_flag[s] != 0 || changes.size() < 2) continue;
+        std::vector<Idx> key;
+        for (Change const& c : changes) key.push_back(c.branch);
+        std::sort(key.begin(), key.end());
+        auto it = mask_of_set.find(key);
+        if (it == mask_of_set.end()) {
+            // -2: not on the shared pattern, -1: nothing goes dark, >= 0: mask index
+            int32_t verdict = -2;
+            if (start_node >= 0) {
+                int32_t const mark = static_cast<int32_t>(s);
+                queue.clear();
+                queue.push_back(start_node);
+                stamp[start_node] = mark;
+                Idx reached = 0, sources = 0;
+                while (!queue.empty()) {
+                    Idx const v = queue.back();
+                    queue.pop_back();
+                    ++reached;
+                    sources += info.self_source[v];
+                    for (Idx k = info.adj_ptr[v]; k != info.adj_ptr[v + 1]; ++k) {
+                        Idx const w = info.adj_node[k];
+                        if (stamp[w] == mark || std::binary_search(key.begin(), key.end(), info.adj_edge[k])) continue;
+                        stamp[w] = mark;
+                        queue.push_back(w);
+                    }
+                }
+                if (sources == n_source_base) {
+                    if (reached == n_supplied_base) {
+                        verdict = -1;
+                    } else {
+                        verdict = static_cast<int32_t>(plan.dead.size() / m.n_bus);
+                        uint8_t* mask = new_mask();
+                        for (Idx i = 0; i != static_cast<Idx>(node_.size()); ++i)
+                            if (topo_.node[i].group == 0 && stamp[i] != mark) mask[topo_.node[i].pos] = 1;
+                    }
+                }
+            }
+            it = mask_of_set.emplace(std::move(key), verdict).first;
+        }
+        if (it->second == -2) {
+            exact_flag[s] = 1;
+        } else {
+            plan.dead_off[s] = it->second;
+        }
+    }
+    for (Idx s = 0; s != n; ++s) {
+        std::vector<Change> const& changes = all[s];
+        if (exact_flag[s] != 0 || changes.size() != 1) continue;
+        Change const& c = changes[0];
+        if (!bridge[c.branch]) continue;
+        // a bridge cuts a subtree of the DFS off: fine when exactly one side keeps a source (the other side goes dark)
+        Idx const v = info.child[c.branch];
+        Idx const inside = info.n_source[v], outside = info.n_source[info.root[v]] - inside;
+        if ((inside == 0) == (outside == 0)) {
+            exact_flag[s] = 1; // two supplied islands (two math models), or an island that was dark already
+            continue;
+        }
+        auto it = mask_of_branch.find(c.branch);
+        if (it == mask_of_branch.end()) {
+            int32_t const k = static_cast<int32_t>(plan.dead.size() / m.n_bus);
+            uint8_t* mask = new_mask();
+            Idx const r = info.root[v];
+            auto mark = [&](Idx t0, Idx t1) {
+                for (Idx t = t0; t != t1; ++t) {
+                    Coupling const nc = topo_.node[info.order[t]];
+                    if (nc.group == 0) mask[nc.pos] = 1;
+                }
+            };
+            if (inside == 0) {
+                mark(info.disc[v], info.disc[v] + info.size[v]);
+            } else {
+                mark(info.disc[r], info.disc[v]);
+                mark(info.disc[v] + info.size[v], info.disc[r] + info.size[r]);
+            }
+            it = mask_of_branch.emplace(c.branch, k).first;
+        }
+        plan.dead_off[s] = it->second;
+    }
+    // pass 3: slots per scenario = the most branches any shared-pattern scenario switches; parameters of the switched branches
+    size_t K = 1;
+    for (Idx s = 0; s != n; ++s)
+        if (exact_flag[s] == 0) K = std::max(K, all[s].size());
+    plan.n_slot = static_cast<int>(K);
+    plan.math_branch.assign(n * K, -1);
+    plan.bparam.assign(n * K * 4 * bb2, 0.0);
+    plan.comp.assign(n * K, -1);
+    plan.energized.assign(n * K, 0);
+    for (Idx s = 0; s != n; ++s) {
+        if (exact_flag[s] != 0) {
+            plan.dead_off[s] = -1;
+            plan.exact.push_back(s);
+            continue;
+        }
+        uint8_t const* const mask = plan.dead_off[s] >= 0 ? &plan.dead[static_cast<size_t>(plan.dead_off[s]) * m.n_bus] : nullptr;
+        for (size_t j = 0; j != all[s].size(); ++j) {
+            Change const& c = all[s][j];
+            Coupling const cp = topo_.branch[c.branch];
+            size_t const slot = s * K + j;
+            plan.math_branch[slot] = cp.pos;
+            plan.comp[slot] = static_cast<int32_t>(c.branch);
+            plan.energized[slot] = (c.from || c.to) ? 1 : 0;
+            double* const bp = &plan.bparam[slot * 4 * bb2];
+            BranchState const st{c.from, c.to};
+            if (c.branch < n_line()) {
+                line_param<B>(line_c_[c.branch], st, bp);
+            } else {
+                Idx const i = c.branch - off_trafo();
+                transformer_param<B>(trafo_c_[i], st, trafo_st_[i].tap_pos, bp);
+            }
+            if (mask != nullptr) { // still connected to a supplied bus?  otherwise the branch itself goes dark
+                bool const from_live = c.from && mask[m.branch_bus_idx[2 * cp.pos]] == 0;
+                bool const to_live = c.to && mask[m.branch_bus_idx[2 * cp.pos + 1]] == 0;
+                if (!from_live && !to_live) {
+                    std::fill_n(bp, 4 * bb2, 0.0);
+                    plan.energized[slot] = 0;
+                }
+            }
+        }
     }
     return true;
 }

@@ -265,9 +265,11 @@ class Model {
     // rebuilding topology, ordering and pattern for it as the reference does (main_model_impl.hpp:139-160 -> rebuild_topology).
     // Same equations in another elimination order: results agree to rounding, not bit for bit.  Other scenarios (bridges,
     // several branches, tap changes, branches that are open in the base state) take the exact per-scenario route.
+    static constexpr int kMaxOutageSlots = 4; // switched branches per scenario the overlay carries (N-k, k <= 4)
     struct OutagePlan {
-        std::vector<int64_t> math_branch;
-        std::vector<double> bparam;
+        int n_slot{1};                    // branch slots per scenario: the arrays below are [n_scn][n_slot]
+        std::vector<int64_t> math_branch; // -1 = unused slot
+        std::vector<double> bparam;       // [n_scn][n_slot][4][B*B][2]
         std::vector<int32_t> comp;
         std::vector<uint8_t> energized;
         std::vector<int32_t> dead_off; // per scenario: mask of the buses that lose their supply (bridge outages), -1 = none
@@ -279,6 +281,8 @@ class Model {
         std::vector<char> bridge;     // per branch
         std::vector<Idx> child;       // per branch: the DFS child end of a bridge
         std::vector<Idx> disc, size, n_source, root, order; // per node: discovery time, subtree size / active sources, DFS root; node by time
+        std::vector<Idx> self_source;                  // per node: active sources on the node itself
+        std::vector<Idx> adj_ptr, adj_node, adj_edge;  // the graph of the fully connected branches (CSR by node)
     };
     BridgeInfo bridge_analysis() const;
     OutagePlan const* outage_plan_{nullptr};

@@ -554,9 +554,9 @@ int64_t Model::run_batch_device_part(ModelOptions const& opt, int phases, Update
     if (outage_plan_ != nullptr) { // branch-outage overlay of this part's scenarios (model.hpp: OutagePlan)
         OutagePlan const& plan = *outage_plan_;
         size_t const bb2 = static_cast<size_t>(phases) * phases * 2;
-        e.set_overlay(n_scn, plan.math_branch.data() + first_scenario, plan.bparam.data() + first_scenario * 4 * bb2,
-                      plan.comp.data() + first_scenario, plan.energized.data() + first_scenario,
-                      plan.dead_off.data() + first_scenario, plan.dead.data(), plan.dead.size());
+        size_t const K = static_cast<size_t>(plan.n_slot), f = static_cast<size_t>(first_scenario);
+        e.set_overlay(n_scn, plan.math_branch.data() + f * K, plan.bparam.data() + f * K * 4 * bb2, plan.comp.data() + f * K,
+                      plan.energized.data() + f * K, plan.dead_off.data() + f, plan.dead.data(), plan.dead.size(), plan.n_slot);
     }
     SolveOptions const sopt = e.prepare_solve({opt.method, opt.err_tol, static_cast<int32_t>(opt.max_iter)});
     d.flag.ensure(1);

@@ -75,8 +75,9 @@ template <int T, int B, bool REG> __global__ void nr_block_kernel(DevStructure s
     t.wide_sum = b.wide_sum ? b.wide_sum + (size_t)tile * s.wide_max_entries * N * T + lane : nullptr;
     t.lg_status = b.lg_status ? b.lg_status + (size_t)tile * s.n_load_gen * T + lane : nullptr;
     t.qviol = b.qviol ? b.qviol + (size_t)tile * s.n_bus * T + lane : nullptr;
-    t.ovr_entry = (b.ovl.entry != nullptr && valid) ? b.ovl.entry + scn * 4 : nullptr;
-    t.ovr_y = (b.ovl.entry != nullptr && valid) ? b.ovl.y + scn * 4 * (2 * B * B) : nullptr;
+    t.ovr_n = 4 * b.ovl.n_branch;
+    t.ovr_entry = (b.ovl.entry != nullptr && valid) ? b.ovl.entry + scn * t.ovr_n : nullptr;
+    t.ovr_y = (b.ovl.entry != nullptr && valid) ? b.ovl.y + scn * t.ovr_n * (2 * B * B) : nullptr;
     t.dead = (b.ovl.dead_off != nullptr && valid && b.ovl.dead_off[scn] >= 0) ? b.ovl.dead + (size_t)b.ovl.dead_off[scn] * s.n_bus : nullptr;
     if (threadIdx.x < T) {
         sh_dev[threadIdx.x] = 0ull;

@@ -36,6 +36,7 @@ template <int T> struct Tile6 {
     double const* usrc;
     int32_t const* ovr_entry;
     double const* ovr_y;
+    int ovr_n;
     uint8_t const* dead;
     double* sm;         // shared scratch of my warp + my scenario: element e at sm[e * 4]; 36 block elements, then 6 vector slots
     double* wide_terms; // scratch of the cooperative hub rows (block_common.cuh: wide_up_row), may be null
@@ -193,8 +194,7 @@ __device__ __forceinline__ void build_entry6(DevStructure const& s, Tile6<T> con
     if (ky >= 0) {
         double const* ysrc = s.ydata + (size_t)ky * kBB2;
         if (t.ovr_entry != nullptr) {
-#pragma unroll
-            for (int o = 0; o < 4; ++o)
+            for (int o = 0; o < t.ovr_n; ++o)
                 if (t.ovr_entry[o] == ky) ysrc = t.ovr_y + o * kBB2;
         }
 #pragma unroll
@@ -814,8 +814,9 @@ template <int T, int MAXT> __global__ void __launch_bounds__(MAXT, 1) nr_block6_
         t6.usrc = b.usrc + (size_t)tile * s.n_source * 2 * T + ln6;
         int64_t const scn = (int64_t)tile * T + ln6;
         bool const valid = scn < b.n_scn;
-        t6.ovr_entry = (b.ovl.entry != nullptr && valid) ? b.ovl.entry + scn * 4 : nullptr;
-        t6.ovr_y = (b.ovl.entry != nullptr && valid) ? b.ovl.y + scn * 4 * kBB2 : nullptr;
+        t6.ovr_n = 4 * b.ovl.n_branch;
+        t6.ovr_entry = (b.ovl.entry != nullptr && valid) ? b.ovl.entry + scn * t6.ovr_n : nullptr;
+        t6.ovr_y = (b.ovl.entry != nullptr && valid) ? b.ovl.y + scn * t6.ovr_n * kBB2 : nullptr;
         t6.dead = (b.ovl.dead_off != nullptr && valid && b.ovl.dead_off[scn] >= 0) ? b.ovl.dead + (size_t)b.ovl.dead_off[scn] * s.n_bus : nullptr;
         t6.wide_terms = b.wide_terms ? b.wide_terms + (size_t)tile * s.wide_max_upd * kNN * T + ln6 : nullptr;
         t6.wide_rhs = b.wide_rhs ? b.wide_rhs + (size_t)tile * s.wide_max_lower * kN * T + ln6 : nullptr;

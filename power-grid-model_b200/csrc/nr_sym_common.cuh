@@ -113,8 +113,7 @@ template <bool OVL, class TileT>
 __device__ __forceinline__ void load_y(DevStructure const& s, TileT const& t, int ky, double& yr, double& yi) {
     double const* p = s.ydata + 2 * ky;
     if (OVL && t.ovr_entry != nullptr) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < t.ovr_n; ++j)
             if (t.ovr_entry[j] == ky) p = t.ovr_y + 2 * j;
     }
     yr = __ldg(p);
@@ -200,11 +199,12 @@ template <int T> struct Tile {
     uint8_t* perm;
     double const* sinj;
     double const* usrc;
-    int32_t const* ovr_entry{nullptr}; // [4]
-    double const* ovr_y{nullptr};      // [4][2]
+    int32_t const* ovr_entry{nullptr}; // [ovr_n]
+    double const* ovr_y{nullptr};      // [ovr_n][2]
     uint8_t const* dead{nullptr};      // [n_bus]
     uint8_t const* lg_status{nullptr}; // REG instantiations: status of every load_gen
     uint8_t* qviol{nullptr};           // REG instantiations: Q limit each bus ran into (0 none, 1 lower, 2 upper)
+    int ovr_n{0};                      // replaced Y-bus entries of the lane's scenario (4 per switched-branch slot)
 
     __device__ __forceinline__ Blk load_blk(int k) const {
         double const* p = jac + (size_t)k * 4 * T;

@@ -64,6 +64,7 @@ template <int T> struct TileR { // restrict-qualified view: the arrays never ali
     uint8_t const* dead{nullptr};
     uint8_t const* lg_status{nullptr}; // REG instantiations (PV buses, nr_sym_common.cuh)
     uint8_t* qviol{nullptr};
+    int ovr_n{0};
     __device__ __forceinline__ Blk load_blk(int k) const {
         double const* p = jac + (size_t)k * 4 * T;
         return {p[0], p[T], p[2 * T], p[3 * T]};
@@ -449,17 +450,19 @@ template <int T, bool OVL, bool REG> __global__ void __launch_bounds__(512, 1) n
     tg.sinj = b.sinj + (size_t)tile * s.n_load_gen * 2 * T + lane;
     tg.usrc = b.usrc + (size_t)tile * s.n_source * 2 * T + lane;
     if (OVL && b.ovl.entry != nullptr && valid) { // branch-outage overlay of this lane's scenario
-        tg.ovr_entry = b.ovl.entry + scn * 4;
-        tg.ovr_y = b.ovl.y + scn * 4 * 2;
+        tg.ovr_n = 4 * b.ovl.n_branch;
+        tg.ovr_entry = b.ovl.entry + scn * tg.ovr_n;
+        tg.ovr_y = b.ovl.y + scn * tg.ovr_n * 2;
         if (b.ovl.dead_off != nullptr && b.ovl.dead_off[scn] >= 0) tg.dead = b.ovl.dead + (size_t)b.ovl.dead_off[scn] * s.n_bus;
     }
     if (REG) {
         tg.lg_status = b.lg_status + (size_t)tile * s.n_load_gen * T + lane;
         tg.qviol = b.qviol + (size_t)tile * s.n_bus * T + lane;
     }
-    TileR<T> const t{tg.jac, tg.xvec, tg.pol, tg.u, tg.perm, tg.sinj, tg.usrc, tg.ovr_entry, tg.ovr_y, tg.dead, tg.lg_status, tg.qviol};
+    TileR<T> const t{tg.jac, tg.xvec, tg.pol, tg.u, tg.perm, tg.sinj, tg.usrc, tg.ovr_entry, tg.ovr_y, tg.dead, tg.lg_status, tg.qviol, tg.ovr_n};
     blk::TileB<T, 1, true> tw;
     tw.ovr_entry = tg.ovr_entry;
+    tw.ovr_n = tg.ovr_n;
     tw.ovr_y = tg.ovr_y;
     tw.dead = tg.dead;
     tw.jac = tg.jac;

@@ -215,8 +215,7 @@ __device__ __forceinline__ void pack_branch_asym_row(DevStructure s, DevBatch b,
         max_it = ph == 0 ? i_to : fmax(max_it, i_to);
     }
     double const rating = __ldg(m.branch_rating + comp);
-    int energized = __ldg(m.branch_energized + comp);
-    if (b.ovl.comp != nullptr && __ldg(b.ovl.comp + scn) == comp) energized = __ldg(b.ovl.energized + scn);
+    int const energized = branch_energized_of(b.ovl, scn, comp, __ldg(m.branch_energized + comp));
     o[0] = head_word(id, energized);
     o[1] = rating > 0.0 ? fmax(sum_sf, sum_st) / rating : fmax(max_if, max_it) / (-rating);
 }

@@ -192,8 +192,7 @@ __device__ __forceinline__ void pack_branch_sym_row(DevStructure s, DevBatch b, 
     double const s_from = kBasePower * cabs_(s_f);
     double const s_to = kBasePower * cabs_(s_t);
     double const rating = __ldg(m.branch_rating + comp);
-    int energized = __ldg(m.branch_energized + comp);
-    if (b.ovl.comp != nullptr && __ldg(b.ovl.comp + scn) == comp) energized = __ldg(b.ovl.energized + scn);
+    int const energized = branch_energized_of(b.ovl, scn, comp, __ldg(m.branch_energized + comp));
     o[0] = head_word(id, energized);
     o[1] = rating > 0.0 ? fmax(s_from, s_to) / rating : fmax(i_from, i_to) / (-rating);
     o[2] = kBasePower * s_f.r;

@@ -50,8 +50,9 @@ template <int T> struct UView {
 // value block of Y-bus entry k for scenario scn: the shared admittance or the scenario's branch-outage replacement
 __device__ __forceinline__ double const* y_entry(DevStructure const& s, DevOverlay const& o, int64_t scn, int k, int bb2) {
     if (o.entry != nullptr) {
-        for (int j = 0; j < 4; ++j)
-            if (__ldg(o.entry + scn * 4 + j) == k) return o.y + (scn * 4 + j) * bb2;
+        int const n = 4 * o.n_branch;
+        for (int j = 0; j < n; ++j)
+            if (__ldg(o.entry + scn * n + j) == k) return o.y + (scn * n + j) * bb2;
     }
     return s.ydata + (size_t)k * bb2;
 }
@@ -62,8 +63,19 @@ __device__ __forceinline__ bool bus_is_dead(DevOverlay const& o, int64_t scn, in
 }
 // parameters of math branch r for scenario scn
 __device__ __forceinline__ double const* branch_param_of(DevStructure const& s, DevOverlay const& o, int64_t scn, int64_t r, int bb2) {
-    if (o.branch != nullptr && __ldg(o.branch + scn) == r) return o.bparam + scn * 4 * bb2;
+    if (o.branch != nullptr) {
+        for (int j = 0; j < o.n_branch; ++j)
+            if (__ldg(o.branch + scn * o.n_branch + j) == r) return o.bparam + (scn * o.n_branch + j) * 4 * bb2;
+    }
     return s.branch_param + (size_t)r * 4 * bb2;
+}
+// `energized` flag of branch component `comp` in scenario scn when the scenario switches it, else `base`
+__device__ __forceinline__ int branch_energized_of(DevOverlay const& o, int64_t scn, int comp, int base) {
+    if (o.comp != nullptr) {
+        for (int j = 0; j < o.n_branch; ++j)
+            if (__ldg(o.comp + scn * o.n_branch + j) == comp) return __ldg(o.energized + scn * o.n_branch + j);
+    }
+    return base;
 }
 
 template <int T>

@@ -551,3 +551,62 @@ def test_scenarios_with_the_same_switching_state_run_as_one_group(sym, monkeypat
     base = model.calculate_power_flow(symmetric=sym)
     base_ref = orc.Model(grid.input_data).calculate(sym=sym)
     _compare_with_oracle({k: v[None] for k, v in base.items()}, base_ref, 1)
+
+
+def _multi_outage_update(grid, n_scn, seed):
+    """every scenario opens 2-4 branches (lines and transformers, some only on one side); scenario 0: two lines that share a node
+    (one Y-bus diagonal entry replaced once for both), scenario 1: a line and the transformer it hangs on"""
+    rng = np.random.default_rng(seed)
+    lines, trafos = grid.input_data["line"], grid.input_data["transformer"]
+    line_rows, trafo_rows = [], []
+    for s in range(n_scn):
+        k = int(rng.integers(2, 5))
+        n_t = int(rng.integers(0, 2)) if s != 0 else 0
+        li = rng.choice(len(lines), size=k - n_t, replace=False)
+        if s == 0:
+            node = lines["from_node"][5]
+            li = np.flatnonzero((lines["from_node"] == node) | (lines["to_node"] == node))[:2]
+            assert len(li) == 2
+        lu = pgm_b200.structs.initialize_array("update", "line", len(li))
+        lu["id"] = lines["id"][li]
+        lu["from_status"] = 0
+        lu["to_status"] = rng.choice([0, 0, 0, 1, -128], size=len(li))
+        tu = pgm_b200.structs.initialize_array("update", "transformer", n_t)
+        if n_t:
+            tu["id"] = trafos["id"][rng.integers(1, len(trafos))]
+            tu["from_status"] = 0
+            tu["to_status"] = 0
+        line_rows.append(lu)
+        trafo_rows.append(tu)
+    return {"line": {"data": np.concatenate(line_rows), "indptr": np.cumsum([0] + [len(x) for x in line_rows])},
+            "transformer": {"data": np.concatenate(trafo_rows), "indptr": np.cumsum([0] + [len(x) for x in trafo_rows])}}
+
+
+@pytest.mark.parametrize("sym", [True, False])
+def test_multi_branch_outages_share_the_base_pattern(sym, monkeypatch):
+    """N-k batches (2-4 switched branches per scenario, with a load profile): the scenarios run as ONE device batch on the base
+    grid's pattern (overlay with several branch slots per scenario; parts of the grid that lose their supply are masked) and
+    equal the oracle, which rebuilds the topology per scenario; the same batch with one slot (PGMB_OUTAGE_SLOTS=1: every
+    scenario on its own topology) gives the same results."""
+    grid = pgm_b200.FictionalGrid(seed=0, n_node_total_specified=300, n_connection_per_lv_feeder=5, n_lv_feeder=4, n_node_per_mv_feeder=5,
+                                  n_mv_feeder=3, has_mv_ring=True, has_lv_ring=True)
+    n_scn = 40
+    update = grid.batch_update(n_scn, seed=2)
+    update.update(_multi_outage_update(grid, n_scn, seed=21))
+    model = pgm_b200.PowerGridModel(grid.input_data)
+    launches0 = int(pgm_b200.lib().pgmb_kernel_launch_count())
+    res = model.calculate_power_flow(symmetric=sym, update_data=update)
+    launches = int(pgm_b200.lib().pgmb_kernel_launch_count()) - launches0
+    n_iter = model.n_iter.copy()
+    assert launches < 2 * n_scn, launches  # one batch, not a solve per scenario
+    ref = orc.Model(grid.input_data).calculate(sym=sym, update=update, threading=0)
+    assert ref["n_failed"] == 0
+    dark = (ref["node"]["energized"] == 0).any(axis=1)
+    assert 0 < dark.sum() < n_scn  # some scenarios cut a part of the grid off, some do not
+    assert np.array_equal(n_iter, ref["n_iter"]), (n_iter, ref["n_iter"])
+    _compare_with_oracle(res, ref, n_scn)
+    monkeypatch.setenv("PGMB_OUTAGE_SLOTS", "1")
+    launches0 = int(pgm_b200.lib().pgmb_kernel_launch_count())
+    one = pgm_b200.PowerGridModel(grid.input_data).calculate_power_flow(symmetric=sym, update_data=update)
+    assert int(pgm_b200.lib().pgmb_kernel_launch_count()) - launches0 > 2 * n_scn
+    _compare_with_oracle(one, ref, n_scn)
