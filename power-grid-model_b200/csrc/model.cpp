@@ -1124,8 +1124,6 @@ template <int B> bool Model::plan_outage_batch(UpdateData const& u, OutagePlan& 
     }
     // pass 2: which buses lose their supply.  One switched branch: the bridge analysis knows; several: a search from a supplied
     // node over the remaining closed branches.  Exactly one supplied part must remain (several = several math models: exact route)
-    std::vector<int32_t> stamp(node_.size(), -1);
-    std::vector<Idx> queue;
     Idx n_supplied_base = 0, n_source_base = 0, start_node = -1;
     for (Idx i = 0; i != static_cast<Idx>(node_.size()); ++i) {
         if (topo_.node[i].group != 0) continue;
@@ -1133,56 +1131,81 @@ template <int B> bool Model::plan_outage_batch(UpdateData const& u, OutagePlan& 
         n_source_base += info.self_source[i];
         if (start_node < 0 && info.self_source[i] != 0) start_node = i;
     }
-    std::map<std::vector<Idx>, int32_t> mask_of_set;
     auto new_mask = [&]() -> uint8_t* {
         plan.dead.resize(plan.dead.size() + m.n_bus, 0);
         return &plan.dead[plan.dead.size() - m.n_bus];
     };
-    for (Idx s = 0; s != n; ++s) {
-        std::vector<Change> const& changes = all[s];
-        if (exact_flag[s] != 0 || changes.size() < 2) continue;
-        std::vector<Idx> key;
-        for (Change const& c : changes) key.push_back(c.branch);
-        std::sort(key.begin(), key.end());
-        auto it = mask_of_set.find(key);
-        if (it == mask_of_set.end()) {
-            // -2: not on the shared pattern, -1: nothing goes dark, >= 0: mask index
-            int32_t verdict = -2;
-            if (start_node >= 0) {
-                int32_t const mark = static_cast<int32_t>(s);
-                queue.clear();
-                queue.push_back(start_node);
-                stamp[start_node] = mark;
+    {
+        // distinct branch sets, searched by the host threads; verdict -2: not on the shared pattern, -1: nothing goes dark,
+        // >= 0: mask index (the buses the search did not reach)
+        std::map<std::vector<Idx>, Idx> set_index;
+        std::vector<std::vector<Idx> const*> sets;
+        std::vector<Idx> set_of_scenario(n, -1);
+        for (Idx s = 0; s != n; ++s) {
+            if (exact_flag[s] != 0 || all[s].size() < 2) continue;
+            std::vector<Idx> key;
+            for (Change const& c : all[s]) key.push_back(c.branch);
+            std::sort(key.begin(), key.end());
+            auto const [it, fresh] = set_index.emplace(std::move(key), static_cast<Idx>(sets.size()));
+            if (fresh) sets.push_back(&it->first);
+            set_of_scenario[s] = it->second;
+        }
+        Idx const n_set = static_cast<Idx>(sets.size());
+        std::vector<int32_t> verdict(n_set, -2);
+        std::vector<std::vector<Idx>> unreached(n_set); // bus positions
+        auto search = [&](Idx first, Idx step) {
+            std::vector<Idx> stamp(node_.size(), -1), stack;
+            for (Idx k = first; k < n_set; k += step) {
+                std::vector<Idx> const& key = *sets[k];
+                stack.assign(1, start_node);
+                stamp[start_node] = k;
                 Idx reached = 0, sources = 0;
-                while (!queue.empty()) {
-                    Idx const v = queue.back();
-                    queue.pop_back();
+                while (!stack.empty()) {
+                    Idx const v = stack.back();
+                    stack.pop_back();
                     ++reached;
                     sources += info.self_source[v];
-                    for (Idx k = info.adj_ptr[v]; k != info.adj_ptr[v + 1]; ++k) {
-                        Idx const w = info.adj_node[k];
-                        if (stamp[w] == mark || std::binary_search(key.begin(), key.end(), info.adj_edge[k])) continue;
-                        stamp[w] = mark;
-                        queue.push_back(w);
+                    for (Idx e = info.adj_ptr[v]; e != info.adj_ptr[v + 1]; ++e) {
+                        Idx const w = info.adj_node[e];
+                        if (stamp[w] == k || std::find(key.begin(), key.end(), info.adj_edge[e]) != key.end()) continue;
+                        stamp[w] = k;
+                        stack.push_back(w);
                     }
                 }
-                if (sources == n_source_base) {
-                    if (reached == n_supplied_base) {
-                        verdict = -1;
-                    } else {
-                        verdict = static_cast<int32_t>(plan.dead.size() / m.n_bus);
-                        uint8_t* mask = new_mask();
-                        for (Idx i = 0; i != static_cast<Idx>(node_.size()); ++i)
-                            if (topo_.node[i].group == 0 && stamp[i] != mark) mask[topo_.node[i].pos] = 1;
-                    }
-                }
+                if (sources != n_source_base) continue; // a second supplied part: its own math model in the reference
+                verdict[k] = -1;
+                if (reached == n_supplied_base) continue;
+                verdict[k] = 0;
+                for (Idx i = 0; i != static_cast<Idx>(node_.size()); ++i)
+                    if (topo_.node[i].group == 0 && stamp[i] != k) unreached[k].push_back(topo_.node[i].pos);
             }
-            it = mask_of_set.emplace(std::move(key), verdict).first;
+        };
+        if (start_node >= 0 && n_set != 0) {
+            Idx n_thread = std::min<Idx>(std::max<Idx>(1, std::thread::hardware_concurrency()), 32);
+            if (char const* env = std::getenv("PGMB_MAX_HOST_THREADS")) n_thread = std::max(1, std::atoi(env));
+            n_thread = std::min<Idx>(n_thread, std::max<Idx>(1, n_set * static_cast<Idx>(node_.size()) / 200000));
+            if (n_thread <= 1) {
+                search(0, 1);
+            } else {
+                std::vector<std::thread> pool;
+                for (Idx t = 0; t != n_thread; ++t) pool.emplace_back(search, t, n_thread);
+                for (std::thread& t : pool) t.join();
+            }
         }
-        if (it->second == -2) {
-            exact_flag[s] = 1;
-        } else {
-            plan.dead_off[s] = it->second;
+        for (Idx k = 0; k != n_set; ++k) {
+            if (verdict[k] != 0) continue;
+            verdict[k] = static_cast<int32_t>(plan.dead.size() / m.n_bus);
+            uint8_t* mask = new_mask();
+            for (Idx const pos : unreached[k]) mask[pos] = 1;
+        }
+        for (Idx s = 0; s != n; ++s) {
+            if (set_of_scenario[s] < 0) continue;
+            int32_t const v = verdict[set_of_scenario[s]];
+            if (v == -2) {
+                exact_flag[s] = 1;
+            } else {
+                plan.dead_off[s] = v;
+            }
         }
     }
     for (Idx s = 0; s != n; ++s) {
