@@ -1043,6 +1043,75 @@ Model::BridgeInfo Model::bridge_analysis() const {
     return info;
 }
 
+std::vector<Idx> Model::closing_branches(UpdateData const& u) {
+    std::vector<Idx> found;
+    if (u.line.data == nullptr && u.transformer.data == nullptr) return found;
+    prepare_topology();
+    if (topo_.math.size() != 1) return found;
+    auto consider = [&](Idx bi, IntS from, IntS to) {
+        bool const closes = (from != kNaIntS && from != 0 && !branch_st_[bi].from_status) || (to != kNaIntS && to != 0 && !branch_st_[bi].to_status);
+        if (!closes || std::find(found.begin(), found.end(), bi) != found.end()) return;
+        BranchInfo const info = branch_info(bi);
+        // both ends in the base grid's math model: the copy's buses are the base grid's
+        if (info.from == info.to || topo_.node[info.from].group != 0 || topo_.node[info.to].group != 0) return;
+        found.push_back(bi);
+    };
+    for (Idx s = 0; s != u.n_scenarios; ++s) {
+        {
+            auto [b, e] = scenario_span<BranchUpdate>(u.line, s);
+            for (auto p = b; p != e; ++p) {
+                Idx bi = -1;
+                if (p->id == kNaID) {
+                    if (e - b == n_line()) bi = p - b;
+                } else if (auto it = line_idx_.find(p->id); it != line_idx_.end()) {
+                    bi = it->second;
+                }
+                if (bi >= 0) consider(bi, p->from_status, p->to_status);
+            }
+        }
+        {
+            auto [b, e] = scenario_span<TransformerUpdate>(u.transformer, s);
+            for (auto p = b; p != e; ++p) {
+                Idx ti = -1;
+                if (p->id == kNaID) {
+                    if (e - b == n_trafo()) ti = p - b;
+                } else if (auto it = trafo_idx_.find(p->id); it != trafo_idx_.end()) {
+                    ti = it->second;
+                }
+                if (ti >= 0) consider(off_trafo() + ti, p->from_status, p->to_status);
+            }
+        }
+        if (static_cast<int>(found.size()) > kMaxOutageSlots) return {};
+    }
+    std::sort(found.begin(), found.end());
+    return found;
+}
+
+Model* Model::union_model(std::vector<Idx> const& closing) {
+    if (union_model_ != nullptr && union_key_ == closing && union_version_ == state_version_) return union_model_.get();
+    union_model_.reset();
+    std::unique_ptr<Model> copy = clone();
+    std::vector<BranchUpdate> lines;
+    std::vector<TransformerUpdate> trafos;
+    for (Idx const bi : closing) {
+        copy->outage_base_state_.push_back({bi, branch_st_[bi].from_status, branch_st_[bi].to_status});
+        if (bi < n_line()) {
+            lines.push_back({line_in_[bi].id, 1, 1});
+        } else {
+            trafos.push_back({trafo_in_[bi - off_trafo()].id, 1, 1, kNaIntS});
+        }
+    }
+    UpdateData close{};
+    close.n_scenarios = 1;
+    if (!lines.empty()) close.line = {static_cast<int64_t>(lines.size()), nullptr, lines.data()};
+    if (!trafos.empty()) close.transformer = {static_cast<int64_t>(trafos.size()), nullptr, trafos.data()};
+    copy->update_permanent(close);
+    union_model_ = std::move(copy);
+    union_key_ = closing;
+    union_version_ = state_version_;
+    return union_model_.get();
+}
+
 template <int B> bool Model::plan_outage_batch(UpdateData const& u, OutagePlan& plan) const {
     // load / generator updates may ride along (contingency x load profile): the device pipeline applies them as in any load batch
     if (u.shunt.data != nullptr || u.source.data != nullptr || u.voltage_regulator.data != nullptr || u.asym_line.data != nullptr ||
@@ -1082,6 +1151,7 @@ template <int B> bool Model::plan_outage_batch(UpdateData const& u, OutagePlan& 
     std::vector<char> exact_flag(n, 0);
     for (Idx s = 0; s != n; ++s) {
         std::vector<Change>& changes = all[s];
+        for (BranchSwitch const& b : outage_base_state_) changes.push_back({b.branch, b.from, b.to}); // unless the scenario says otherwise
         auto note = [&](Idx bi, IntS from, IntS to) {
             auto it = std::find_if(changes.begin(), changes.end(), [bi](Change const& c) { return c.branch == bi; });
             if (it == changes.end()) {
@@ -1367,14 +1437,20 @@ int64_t Model::calculate_impl(ModelOptions const& opt, UpdateData const* update,
         };
         if (structural && !source_param_change && !has_reg && opt.tap_strategy == 0 && (opt.method == 1 || opt.method == -128) && n > 0 &&
             (update->line.data != nullptr || update->transformer.data != nullptr) && std::getenv("PGMB_N1_EXACT") == nullptr) {
-            prepare_engines<B>();
+            // scenarios that close branches run on the union grid's pattern (model.hpp: union_model)
+            Model* host = this;
+            if (std::vector<Idx> const closing = closing_branches(*update); !closing.empty() && std::getenv("PGMB_NO_UNION_GRID") == nullptr) {
+                host = union_model(closing);
+                host->device_ = device_;
+            }
+            host->template prepare_engines<B>();
             OutagePlan plan;
-            bool const planned = plan_outage_batch<B>(*update, plan);
+            bool const planned = host->template plan_outage_batch<B>(*update, plan);
             if (std::getenv("PGMB_DEBUG_N1") != nullptr) {
                 std::fprintf(stderr, "[pgmb n-1] planned=%d scenarios=%lld exact=%zu plan_ms=%.2f\n", planned ? 1 : 0,
                              static_cast<long long>(n), plan.exact.size(), ms_since(t0));
             }
-            if (planned && 2 * plan.exact.size() <= static_cast<size_t>(n) && device_path_eligible(*update)) {
+            if (planned && 2 * plan.exact.size() <= static_cast<size_t>(n) && host->device_path_eligible(*update)) {
                 if (status == nullptr) {
                     status_local.assign(n, 0);
                     status = status_local.data();
@@ -1385,16 +1461,21 @@ int64_t Model::calculate_impl(ModelOptions const& opt, UpdateData const* update,
                 none.asym_gen = update->asym_gen;
                 none.sym_load = update->sym_load;
                 none.asym_load = update->asym_load;
-                outage_plan_ = &plan;
+                host->outage_plan_ = &plan;
                 timing[0] += ms_since(t0);
                 int64_t r = -1;
                 try {
-                    r = run_batch_device(opt, B, none, out, n_iter, status);
+                    r = host->run_batch_device(opt, B, none, out, n_iter, status);
                 } catch (...) {
-                    outage_plan_ = nullptr;
+                    host->outage_plan_ = nullptr;
                     throw;
                 }
-                outage_plan_ = nullptr;
+                host->outage_plan_ = nullptr;
+                if (host != this) {
+                    batch_message = std::move(host->batch_message);
+                    host->batch_message.clear();
+                    for (int k = 1; k != 8; ++k) timing[k] = host->timing[k];
+                }
                 if (r < 0) batch_message.clear(); // messages of parts that ran before the attempt was given up
                 t0 = Clock::now();
                 if (r >= 0) adopt_device_result(r, std::move(plan.exact));
@@ -1696,6 +1777,8 @@ std::unique_ptr<Model> Model::clone() const {
     auto copy = std::make_unique<Model>(*this);
     copy->dev_.reset();
     copy->outage_plan_ = nullptr;
+    copy->union_model_.reset();
+    copy->outage_base_state_.clear();
     copy->batch_message.clear();
     return copy;
 }

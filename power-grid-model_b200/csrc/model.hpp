@@ -265,7 +265,21 @@ class Model {
     // rebuilding topology, ordering and pattern for it as the reference does (main_model_impl.hpp:139-160 -> rebuild_topology).
     // Same equations in another elimination order: results agree to rounding, not bit for bit.  Other scenarios (bridges,
     // several branches, tap changes, branches that are open in the base state) take the exact per-scenario route.
-    static constexpr int kMaxOutageSlots = 4; // switched branches per scenario the overlay carries (N-k, k <= 4)
+    static constexpr int kMaxOutageSlots = 8; // switched branches per scenario the overlay carries (N-k)
+    // Scenarios that CLOSE a branch which is open in the base state: the pattern of the base grid has no entries for it, so the
+    // batch runs on a copy of the model in which every branch some scenario closes is closed (the union grid); on that copy a
+    // scenario is the union grid with branches switched OFF -- the ones it does not close (implicit, outage_base_state_) and the
+    // ones it opens itself -- which is the N-k overlay again.
+    struct BranchSwitch {
+        Idx branch;
+        bool from, to;
+    };
+    std::vector<BranchSwitch> outage_base_state_; // union copy only: the base state of the branches the copy closed
+    std::shared_ptr<Model> union_model_;
+    std::vector<Idx> union_key_;
+    uint64_t union_version_{0};
+    std::vector<Idx> closing_branches(UpdateData const& update);
+    Model* union_model(std::vector<Idx> const& closing);
     struct OutagePlan {
         int n_slot{1};                    // branch slots per scenario: the arrays below are [n_scn][n_slot]
         std::vector<int64_t> math_branch; // -1 = unused slot

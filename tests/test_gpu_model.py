@@ -610,3 +610,64 @@ def test_multi_branch_outages_share_the_base_pattern(sym, monkeypatch):
     one = pgm_b200.PowerGridModel(grid.input_data).calculate_power_flow(symmetric=sym, update_data=update)
     assert int(pgm_b200.lib().pgmb_kernel_launch_count()) - launches0 > 2 * n_scn
     _compare_with_oracle(one, ref, n_scn)
+
+
+@pytest.mark.parametrize("sym", [True, False])
+def test_scenarios_that_close_open_branches_run_on_the_union_grid(sym, monkeypatch):
+    """Reconfiguration batch: the base grid has three open tie lines; scenarios close one or two of them (fully or on one side),
+    open other lines at the same time, or change nothing.  The base pattern has no entries for the open ties, so the batch runs
+    as ONE device batch on the union grid (all ties closed) with the not-closed ties switched off per scenario through the
+    N-k overlay; results equal the oracle, which rebuilds the topology per scenario."""
+    grid = pgm_b200.FictionalGrid(seed=0, n_node_total_specified=300, n_connection_per_lv_feeder=5, n_lv_feeder=4, n_node_per_mv_feeder=5,
+                                  n_mv_feeder=3, has_mv_ring=True, has_lv_ring=True)
+    data = {k: v.copy() for k, v in grid.input_data.items()}
+    lines = data["line"]
+    not_bridge = np.flatnonzero(np.asarray(pgm_b200.PowerGridModel(data).math_index(0, "branch_is_bridge"))[: len(lines)] == 0)
+    # three ties from different rings (removing all of them keeps the grid connected: checked through the oracle below)
+    ties = not_bridge[[0, len(not_bridge) // 2, len(not_bridge) - 1]]
+    lines["from_status"][ties[0]] = 0
+    lines["to_status"][ties[0]] = 0
+    lines["from_status"][ties[1]] = 0  # half open in the base state
+    lines["to_status"][ties[2]] = 0
+    lines["from_status"][ties[2]] = 0
+    n_scn = 24
+    rng = np.random.default_rng(8)
+    rows = []
+    for s in range(n_scn):
+        kind = s % 6
+        lu = pgm_b200.structs.initialize_array("update", "line", {0: 1, 1: 2, 2: 2, 3: 0, 4: 1, 5: 1}[kind])
+        if kind == 0:    # close one tie
+            lu["id"], lu["from_status"], lu["to_status"] = lines["id"][ties[s % 3]], 1, 1
+        elif kind == 1:  # close a tie and open another line
+            lu["id"][0], lu["from_status"][0], lu["to_status"][0] = lines["id"][ties[s % 3]], 1, 1
+            other = rng.choice(np.setdiff1d(np.arange(len(lines)), ties))
+            lu["id"][1], lu["from_status"][1], lu["to_status"][1] = lines["id"][other], 0, 0
+        elif kind == 2:  # close two ties
+            lu["id"] = lines["id"][ties[[s % 3, (s + 1) % 3]]]
+            lu["from_status"], lu["to_status"] = 1, 1
+        elif kind == 4:  # one side only: a tie that was fully open stays open, the half-open one closes
+            lu["id"], lu["from_status"], lu["to_status"] = lines["id"][ties[s % 3]], 1, -128
+        elif kind == 5:  # open a line, no tie closed
+            lu["id"], lu["from_status"], lu["to_status"] = lines["id"][rng.choice(np.setdiff1d(np.arange(len(lines)), ties))], 0, 0
+        rows.append(lu)
+    update = grid.batch_update(n_scn, seed=3)
+    update["line"] = {"data": np.concatenate(rows), "indptr": np.cumsum([0] + [len(x) for x in rows])}
+    ref = orc.Model(data).calculate(sym=sym, update=update, threading=0)
+    assert ref["n_failed"] == 0
+    model = pgm_b200.PowerGridModel(data)
+    launches0 = int(pgm_b200.lib().pgmb_kernel_launch_count())
+    res = model.calculate_power_flow(symmetric=sym, update_data=update)
+    launches = int(pgm_b200.lib().pgmb_kernel_launch_count()) - launches0
+    assert launches < 2 * n_scn, launches
+    assert np.array_equal(model.n_iter, ref["n_iter"]), (model.n_iter, ref["n_iter"])
+    _compare_with_oracle(res, ref, n_scn)
+    # the model itself is unchanged: the base state afterwards, and the same batch again (the union copy is reused)
+    single = model.calculate_power_flow(symmetric=sym)
+    _compare_with_oracle({k: v[None] for k, v in single.items()}, orc.Model(data).calculate(sym=sym), 1)
+    again = model.calculate_power_flow(symmetric=sym, update_data=update)
+    for comp in res:
+        for name in res[comp].dtype.names:
+            assert np.array_equal(res[comp][name], again[comp][name], equal_nan=True), (comp, name)
+    monkeypatch.setenv("PGMB_NO_UNION_GRID", "1")
+    one = pgm_b200.PowerGridModel(data).calculate_power_flow(symmetric=sym, update_data=update)
+    _compare_with_oracle(one, ref, n_scn)
