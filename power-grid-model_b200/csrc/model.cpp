@@ -1142,7 +1142,9 @@ template <int B> bool Model::plan_outage_batch(UpdateData const& u, OutagePlan& 
     struct Change {
         Idx branch;
         bool from, to;
+        IntS tap; // transformers: the scenario's tap position
     };
+    auto base_tap = [this](Idx bi) -> IntS { return bi >= off_trafo() ? trafo_st_[bi - off_trafo()].tap_pos : IntS{0}; };
     // PGMB_OUTAGE_SLOTS=1: only one switched branch per scenario on the shared pattern (comparison)
     int max_slots = kMaxOutageSlots;
     if (char const* env = std::getenv("PGMB_OUTAGE_SLOTS")) max_slots = std::clamp(std::atoi(env), 1, kMaxOutageSlots);
@@ -1151,15 +1153,16 @@ template <int B> bool Model::plan_outage_batch(UpdateData const& u, OutagePlan& 
     std::vector<char> exact_flag(n, 0);
     for (Idx s = 0; s != n; ++s) {
         std::vector<Change>& changes = all[s];
-        for (BranchSwitch const& b : outage_base_state_) changes.push_back({b.branch, b.from, b.to}); // unless the scenario says otherwise
-        auto note = [&](Idx bi, IntS from, IntS to) {
+        for (BranchSwitch const& b : outage_base_state_) changes.push_back({b.branch, b.from, b.to, base_tap(b.branch)}); // unless the scenario says otherwise
+        auto note = [&](Idx bi, IntS from, IntS to, IntS tap = kNaIntS) {
             auto it = std::find_if(changes.begin(), changes.end(), [bi](Change const& c) { return c.branch == bi; });
             if (it == changes.end()) {
-                changes.push_back({bi, branch_st_[bi].from_status, branch_st_[bi].to_status});
+                changes.push_back({bi, branch_st_[bi].from_status, branch_st_[bi].to_status, base_tap(bi)});
                 it = changes.end() - 1;
             }
             if (from != kNaIntS) it->from = from != 0;
             if (to != kNaIntS) it->to = to != 0;
+            if (tap != kNaIntS) it->tap = tap_limit(trafo_c_[bi - off_trafo()], tap); // a tap position is one more set of branch parameters
         };
         try {
             {
@@ -1170,8 +1173,7 @@ template <int B> bool Model::plan_outage_batch(UpdateData const& u, OutagePlan& 
                 auto [b, e] = scenario_span<TransformerUpdate>(u.transformer, s);
                 for (auto p = b; p != e; ++p) {
                     Idx const i = lookup(p->id, p - b, e - b, n_trafo(), trafo_idx_);
-                    if (p->tap_pos != kNaIntS && p->tap_pos != trafo_st_[i].tap_pos) exact_flag[s] = 1;
-                    note(off_trafo() + i, p->from_status, p->to_status);
+                    note(off_trafo() + i, p->from_status, p->to_status, p->tap_pos);
                 }
             }
         } catch (InvalidArgument const&) {
@@ -1181,7 +1183,9 @@ template <int B> bool Model::plan_outage_batch(UpdateData const& u, OutagePlan& 
             changes.clear();
             continue;
         }
-        std::erase_if(changes, [this](Change const& c) { return c.from == branch_st_[c.branch].from_status && c.to == branch_st_[c.branch].to_status; });
+        std::erase_if(changes, [&](Change const& c) {
+            return c.from == branch_st_[c.branch].from_status && c.to == branch_st_[c.branch].to_status && c.tap == base_tap(c.branch);
+        });
         if (static_cast<int>(changes.size()) > max_slots) exact_flag[s] = 1;
         // only branches that are closed, in the math model and between two different buses in the base state keep the pattern
         for (Change const& c : changes) {
@@ -1213,8 +1217,10 @@ template <int B> bool Model::plan_outage_batch(UpdateData const& u, OutagePlan& 
         std::vector<Idx> set_of_scenario(n, -1);
         for (Idx s = 0; s != n; ++s) {
             if (exact_flag[s] != 0 || all[s].size() < 2) continue;
-            std::vector<Idx> key;
-            for (Change const& c : all[s]) key.push_back(c.branch);
+            std::vector<Idx> key; // the branches that stop connecting their ends (a tap change alone keeps the connection)
+            for (Change const& c : all[s])
+                if (!(c.from && c.to)) key.push_back(c.branch);
+            if (key.empty()) continue;
             std::sort(key.begin(), key.end());
             auto const [it, fresh] = set_index.emplace(std::move(key), static_cast<Idx>(sets.size()));
             if (fresh) sets.push_back(&it->first);
@@ -1282,7 +1288,7 @@ template <int B> bool Model::plan_outage_batch(UpdateData const& u, OutagePlan& 
         std::vector<Change> const& changes = all[s];
         if (exact_flag[s] != 0 || changes.size() != 1) continue;
         Change const& c = changes[0];
-        if (!bridge[c.branch]) continue;
+        if ((c.from && c.to) || !bridge[c.branch]) continue;
         // a bridge cuts a subtree of the DFS off: fine when exactly one side keeps a source (the other side goes dark)
         Idx const v = info.child[c.branch];
         Idx const inside = info.n_source[v], outside = info.n_source[info.root[v]] - inside;
@@ -1340,7 +1346,7 @@ template <int B> bool Model::plan_outage_batch(UpdateData const& u, OutagePlan& 
                 line_param<B>(line_c_[c.branch], st, bp);
             } else {
                 Idx const i = c.branch - off_trafo();
-                transformer_param<B>(trafo_c_[i], st, trafo_st_[i].tap_pos, bp);
+                transformer_param<B>(trafo_c_[i], st, c.tap, bp);
             }
             if (mask != nullptr) { // still connected to a supplied bus?  otherwise the branch itself goes dark
                 bool const from_live = c.from && mask[m.branch_bus_idx[2 * cp.pos]] == 0;

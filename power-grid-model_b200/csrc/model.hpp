@@ -260,11 +260,12 @@ class Model {
     std::vector<int64_t> tap_rank_table() const; // introspection: (kind, index, rank group) in the order of the search
     std::vector<IntS> tap_positions_out_; // per tap regulator: tap position found by the last run_tap_optimizer (na: not regulated)
     // ---- branch-outage batches on the shared symbolic pattern (N-1 studies) ----
-    // A scenario that switches ONE fully connected branch which is not a bridge of the grid keeps every node energized: it is
-    // solved on the base topology's pattern with the branch's admittance contributions replaced (Engine::set_overlay) instead of
-    // rebuilding topology, ordering and pattern for it as the reference does (main_model_impl.hpp:139-160 -> rebuild_topology).
-    // Same equations in another elimination order: results agree to rounding, not bit for bit.  Other scenarios (bridges,
-    // several branches, tap changes, branches that are open in the base state) take the exact per-scenario route.
+    // A scenario that opens a few fully connected branches, or moves transformer taps, has the base grid's equations with those
+    // branches' admittance contributions changed: it is solved on the base topology's pattern with the contributions replaced
+    // (Engine::set_overlay) instead of rebuilding topology, ordering and pattern for it as the reference does
+    // (main_model_impl.hpp:139-160 -> rebuild_topology); buses that lose their supply are masked.  Same equations in another
+    // elimination order: results agree to rounding, not bit for bit.  Other scenarios (a second supplied island, more than
+    // kMaxOutageSlots branches, ...) take the exact per-scenario route.
     static constexpr int kMaxOutageSlots = 8; // switched branches per scenario the overlay carries (N-k)
     // Scenarios that CLOSE a branch which is open in the base state: the pattern of the base grid has no entries for it, so the
     // batch runs on a copy of the model in which every branch some scenario closes is closed (the union grid); on that copy a

@@ -516,7 +516,10 @@ def test_regulated_grid_symmetric_kernels_equal_the_block_kernel(q_lim, rings, m
 def test_scenarios_with_the_same_switching_state_run_as_one_group(sym, monkeypatch):
     """a batch that revisits a few switching states (two lines out / a transformer tap moved / a shunt off) with different loads:
     scenarios with byte-identical structural updates share one topology + engine build and run as ONE device batch; the
-    scenario-by-scenario route (PGMB_GROUP_SCENARIOS=0) and the oracle give the same results"""
+    scenario-by-scenario route (PGMB_GROUP_SCENARIOS=0) and the oracle give the same results.  (These particular states -- closed
+    lines opened, a tap moved -- also fit the branch overlay, which takes the whole batch as one; PGMB_N1_EXACT=1 keeps it out so
+    that the grouped route is what runs here.  The overlay's own result is compared at the end.)"""
+    monkeypatch.setenv("PGMB_N1_EXACT", "1")
     grid = pgm_b200.FictionalGrid(seed=2, has_mv_ring=True, has_lv_ring=True, n_node_total_specified=300, n_mv_feeder=3,
                                   n_node_per_mv_feeder=5, n_lv_feeder=3, n_connection_per_lv_feeder=10)
     n_scn, n_state = 48, 4
@@ -547,6 +550,13 @@ def test_scenarios_with_the_same_switching_state_run_as_one_group(sym, monkeypat
     assert np.array_equal(model.n_iter, ref["n_iter"])
     _compare_with_oracle(single, ref, n_scn)
     assert launches_grouped < launches_single
+    monkeypatch.delenv("PGMB_N1_EXACT")
+    monkeypatch.delenv("PGMB_GROUP_SCENARIOS")
+    launches0 = int(pgm_b200.lib().pgmb_kernel_launch_count())
+    overlay = model.calculate_power_flow(symmetric=sym, update_data=update)
+    assert int(pgm_b200.lib().pgmb_kernel_launch_count()) - launches0 < launches_grouped
+    assert np.array_equal(model.n_iter, ref["n_iter"])
+    _compare_with_oracle(overlay, ref, n_scn)
     # the model is unchanged afterwards
     base = model.calculate_power_flow(symmetric=sym)
     base_ref = orc.Model(grid.input_data).calculate(sym=sym)
@@ -670,4 +680,43 @@ def test_scenarios_that_close_open_branches_run_on_the_union_grid(sym, monkeypat
             assert np.array_equal(res[comp][name], again[comp][name], equal_nan=True), (comp, name)
     monkeypatch.setenv("PGMB_NO_UNION_GRID", "1")
     one = pgm_b200.PowerGridModel(data).calculate_power_flow(symmetric=sym, update_data=update)
+    _compare_with_oracle(one, ref, n_scn)
+
+
+@pytest.mark.parametrize("sym", [True, False])
+def test_tap_positions_per_scenario_share_the_base_pattern(sym, monkeypatch):
+    """A batch that moves transformer taps per scenario (1-3 transformers each, positions beyond the range are clamped, some
+    scenarios open a line as well, all with their own loads): a tap position is one more set of branch parameters, so the scenarios run as ONE device batch
+    through the branch overlay; equal to the oracle (per-scenario parameter rebuild) and to the own-topology route."""
+    grid = pgm_b200.FictionalGrid(seed=0, n_node_total_specified=300, n_connection_per_lv_feeder=5, n_lv_feeder=4, n_node_per_mv_feeder=5,
+                                  n_mv_feeder=3, has_mv_ring=True, has_lv_ring=True)
+    trafos, lines = grid.input_data["transformer"], grid.input_data["line"]
+    n_scn = 30
+    rng = np.random.default_rng(12)
+    t_rows, l_rows = [], []
+    for s in range(n_scn):
+        pick = rng.choice(len(trafos), size=int(rng.integers(1, 4)), replace=False)
+        if s == 0:
+            pick = np.array([0])  # the source transformer: a bridge whose parameters change while it stays connected
+        tu = pgm_b200.structs.initialize_array("update", "transformer", len(pick))
+        tu["id"] = trafos["id"][pick]
+        tu["tap_pos"] = [rng.integers(int(min(trafos["tap_min"][k], trafos["tap_max"][k])) - 1, int(max(trafos["tap_min"][k], trafos["tap_max"][k])) + 2) for k in pick]
+        lu = pgm_b200.structs.initialize_array("update", "line", 1 if s % 4 == 1 else 0)
+        if len(lu):
+            lu["id"], lu["from_status"], lu["to_status"] = lines["id"][rng.integers(len(lines))], 0, 0
+        t_rows.append(tu)
+        l_rows.append(lu)
+    update = grid.batch_update(n_scn, seed=6)
+    update["transformer"] = {"data": np.concatenate(t_rows), "indptr": np.cumsum([0] + [len(x) for x in t_rows])}
+    update["line"] = {"data": np.concatenate(l_rows), "indptr": np.cumsum([0] + [len(x) for x in l_rows])}
+    ref = orc.Model(grid.input_data).calculate(sym=sym, update=update, threading=0)
+    assert ref["n_failed"] == 0
+    model = pgm_b200.PowerGridModel(grid.input_data)
+    launches0 = int(pgm_b200.lib().pgmb_kernel_launch_count())
+    res = model.calculate_power_flow(symmetric=sym, update_data=update)
+    assert int(pgm_b200.lib().pgmb_kernel_launch_count()) - launches0 < 2 * n_scn
+    assert np.array_equal(model.n_iter, ref["n_iter"]), (model.n_iter, ref["n_iter"])
+    _compare_with_oracle(res, ref, n_scn)
+    monkeypatch.setenv("PGMB_N1_EXACT", "1")
+    one = pgm_b200.PowerGridModel(grid.input_data).calculate_power_flow(symmetric=sym, update_data=update)
     _compare_with_oracle(one, ref, n_scn)
