@@ -228,6 +228,23 @@ def other_configs(pgm_b200, np, device):
     out["configs[4] shape, ringed 1804-node grid, asymmetric N-1 (1000 single-line outages, shared pattern = NOT the reference's per-scenario re-ordering: same equations, results to rounding), public API"] = {
         "wall_ms": wall, "kernel_ms": model.timing()["solve_kernel"], "scenarios_per_s": n1 / wall * 1e3,
         "failed": int((model.status != 0).sum())}
+    # the same grid, symmetric N-2 with a load profile: two lines off per scenario, still one device batch (overlay slots)
+    upd2 = pgm_b200.structs.initialize_array("update", "line", (n1, 2))
+    rng2 = np.random.default_rng(1)
+    for s in range(n1):
+        upd2["id"][s] = lines["id"][rng2.choice(len(lines), 2, replace=False)]
+    upd2["from_status"] = 0
+    upd2["to_status"] = 0
+    update2 = dict(ringed.batch_update(n1, seed=0))
+    update2["line"] = upd2
+    for _ in range(2):
+        t0 = time.perf_counter()
+        model.calculate_power_flow(symmetric=True, update_data=update2, output_component_types=["node"], reuse_output_buffers=True,
+                                   device=device)
+        wall = 1e3 * (time.perf_counter() - t0)
+    out["ringed 1804-node grid, symmetric N-2 x load profile (1000 scenarios, two lines off each, shared pattern, dark parts masked), public API"] = {
+        "wall_ms": wall, "kernel_ms": model.timing()["solve_kernel"], "scenarios_per_s": n1 / wall * 1e3,
+        "failed": int((model.status != 0).sum())}
     # the reference benchmark's tap-changer shape (benchmark.cpp:333-422): configs[1] grid + one regulator on the station
     # transformer, 1000 load-profile scenarios, symmetric NR; the batch searches in lockstep (one batched power flow per search
     # step).  Second of two calls, node + transformer + regulator output into page-locked buffers; CPU: the oracle, all threads.
