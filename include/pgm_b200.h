@@ -281,6 +281,11 @@ PGMB_API int64_t pgmb_model_n_math_groups(pgmb_model* model);
  * source_u_ref [n_scenarios][n_source] complex; caller-allocated. Only valid for batches that change loads / sources. */
 PGMB_API int pgmb_model_batch_pf_input(pgmb_model* model, const pgmb_update_data* update, int32_t symmetric,
                                        int64_t math_group, double* s_injection, double* source_u_ref);
+/* Host planning of a branch-switching batch, for tests (no device needed): plan [n_scenarios][4] =
+ * route (0: shared symbolic pattern through the branch overlay, 1: own topology), overlay slots in use, buses that lose their
+ * supply, 1 when the batch is planned on the union grid (scenarios close branches that are open in the base state).
+ * Reference behaviour it stands in for: per-scenario rebuild_topology, main_model_impl.hpp:139-160. */
+PGMB_API int pgmb_model_outage_plan(pgmb_model* model, const pgmb_update_data* update, int32_t symmetric, int64_t* plan);
 /* timing of the last calculate call, milliseconds: [0] host prepare (tables, source references), [1] host time to
  * enqueue the chunk pipeline (H2D, kernels, D2H of every chunk), [2] solver kernels (CUDA events, summed over the chunks,
  * which overlap), [3] host output conversion (per-scenario route only), [4] wait for the pipeline to drain + status read-back, [5] total wall */

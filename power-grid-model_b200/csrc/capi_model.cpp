@@ -86,6 +86,13 @@ int pgmb_model_batch_pf_input(pgmb_model* model, const pgmb_update_data* update,
     });
 }
 
+int pgmb_model_outage_plan(pgmb_model* model, const pgmb_update_data* update, int32_t symmetric, int64_t* plan) {
+    return guarded([&] {
+        if (model == nullptr || update == nullptr || plan == nullptr) throw InvalidArgument("null argument");
+        model->model->outage_plan_summary(update_of(*update), symmetric != 0, plan);
+    });
+}
+
 int pgmb_model_get_index(pgmb_model* model, int64_t math_group, const char* name, const int64_t** data, int64_t* size) {
     return guarded([&] {
         if (model == nullptr || name == nullptr) throw InvalidArgument("null argument");

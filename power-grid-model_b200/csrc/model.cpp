@@ -1087,6 +1087,44 @@ std::vector<Idx> Model::closing_branches(UpdateData const& u) {
     return found;
 }
 
+Model* Model::outage_host(UpdateData const& update) {
+    if (std::getenv("PGMB_NO_UNION_GRID") != nullptr) return this;
+    std::vector<Idx> const closing = closing_branches(update);
+    if (closing.empty()) return this;
+    Model* const host = union_model(closing);
+    host->device_ = device_;
+    return host;
+}
+
+void Model::outage_plan_summary(UpdateData const& update, bool symmetric, int64_t* out) {
+    Model* const host = outage_host(update);
+    host->prepare_topology();
+    OutagePlan plan;
+    bool const planned = symmetric ? host->plan_outage_batch<1>(update, plan) : host->plan_outage_batch<3>(update, plan);
+    Idx const n = update.n_scenarios;
+    for (Idx s = 0; s != n; ++s) {
+        int64_t* o = out + 4 * s;
+        o[0] = 1; // own topology
+        o[1] = o[2] = 0;
+        o[3] = host != this ? 1 : 0;
+    }
+    if (!planned) return;
+    Idx const n_bus = host->topo_.math[0].n_bus;
+    for (Idx s = 0; s != n; ++s) {
+        int64_t* o = out + 4 * s;
+        o[0] = 0;
+        for (int j = 0; j != plan.n_slot; ++j) o[1] += plan.math_branch[s * plan.n_slot + j] >= 0 ? 1 : 0;
+        if (plan.dead_off[s] >= 0) {
+            uint8_t const* mask = &plan.dead[static_cast<size_t>(plan.dead_off[s]) * n_bus];
+            o[2] = std::count(mask, mask + n_bus, uint8_t{1});
+        }
+    }
+    for (Idx const s : plan.exact) {
+        out[4 * s] = 1;
+        out[4 * s + 1] = out[4 * s + 2] = 0;
+    }
+}
+
 Model* Model::union_model(std::vector<Idx> const& closing) {
     if (union_model_ != nullptr && union_key_ == closing && union_version_ == state_version_) return union_model_.get();
     union_model_.reset();
@@ -1444,11 +1482,7 @@ int64_t Model::calculate_impl(ModelOptions const& opt, UpdateData const* update,
         if (structural && !source_param_change && !has_reg && opt.tap_strategy == 0 && (opt.method == 1 || opt.method == -128) && n > 0 &&
             (update->line.data != nullptr || update->transformer.data != nullptr) && std::getenv("PGMB_N1_EXACT") == nullptr) {
             // scenarios that close branches run on the union grid's pattern (model.hpp: union_model)
-            Model* host = this;
-            if (std::vector<Idx> const closing = closing_branches(*update); !closing.empty() && std::getenv("PGMB_NO_UNION_GRID") == nullptr) {
-                host = union_model(closing);
-                host->device_ = device_;
-            }
+            Model* const host = outage_host(*update);
             host->template prepare_engines<B>();
             OutagePlan plan;
             bool const planned = host->template plan_outage_batch<B>(*update, plan);

@@ -281,6 +281,12 @@ class Model {
     uint64_t union_version_{0};
     std::vector<Idx> closing_branches(UpdateData const& update);
     Model* union_model(std::vector<Idx> const& closing);
+    Model* outage_host(UpdateData const& update); // this, or the union copy when scenarios close branches
+public:
+    // introspection of the host planning (CPU tests): per scenario [0] route (0 shared pattern, 1 own topology), [1] overlay
+    // slots in use, [2] buses that lose their supply, [3] planned on the union grid
+    void outage_plan_summary(UpdateData const& update, bool symmetric, int64_t* out);
+private:
     struct OutagePlan {
         int n_slot{1};                    // branch slots per scenario: the arrays below are [n_scn][n_slot]
         std::vector<int64_t> math_branch; // -1 = unused slot

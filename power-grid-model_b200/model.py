@@ -168,6 +168,14 @@ class PowerGridModel:
         return s, u
 
     # -- introspection (parity tests) ---------------------------------------------------------------------------------
+    def outage_plan(self, update_data, symmetric=True):
+        """host planning of a branch-switching batch: (n_scn, 4) = route (0 shared pattern / 1 own topology), overlay slots,
+        buses without supply, planned on the union grid"""
+        upd, keep = self._update_struct(update_data, batch=True)
+        plan = np.zeros((upd.n_scenarios, 4), np.int64)
+        check(lib().pgmb_model_outage_plan(self._h, C.byref(upd), C.c_int32(int(symmetric)), plan.ctypes.data_as(C.c_void_p)))
+        return plan
+
     def n_math_groups(self):
         return int(lib().pgmb_model_n_math_groups(self._h))
 

@@ -150,3 +150,99 @@ def test_bridge_analysis_of_the_n1_route(rings):
         if nc == 2:
             assert cut[k] in (int((labels == 0).sum()), int((labels == 1).sum())), k
     assert is_bridge.all() if not rings else (0 < is_bridge.sum() < len(ends))
+
+
+def _supplied(inp, line_state, trafo_state):
+    """nodes connected to the source node over branches that are closed on both sides (brute force, scipy)"""
+    import scipy.sparse as sp
+    from scipy.sparse.csgraph import connected_components
+
+    node_pos = {int(i): k for k, i in enumerate(inp["node"]["id"])}
+    rows, cols = [], []
+    for comp, state in (("line", line_state), ("transformer", trafo_state)):
+        for b, (f, t) in zip(inp[comp], state):
+            if f and t:
+                rows.append(node_pos[int(b["from_node"])])
+                cols.append(node_pos[int(b["to_node"])])
+    n = len(node_pos)
+    _, labels = connected_components(sp.coo_matrix((np.ones(len(rows)), (rows, cols)), shape=(n, n)), directed=False)
+    return labels == labels[node_pos[int(inp["source"]["node"][0])]]
+
+
+@pytest.mark.parametrize("ties", [False, True])
+def test_host_planning_of_branch_switching_batches(ties):
+    """Host side of the shared-pattern route for N-k / reconfiguration / tap batches, no device needed: for random
+    scenarios (1-5 branches opened fully or on one side, taps moved, open ties closed) the plan puts every scenario on the shared
+    pattern, uses one overlay slot per branch whose state or tap differs from the pattern's grid, and masks exactly the buses a
+    brute-force connectivity search finds without supply.  ties=True: three lines are open in the base state and scenarios close
+    them, so the plan is made on the union grid, where a tie that stays open takes a slot."""
+    grid = pgm_b200.FictionalGrid(seed=3, n_node_total_specified=200, n_mv_feeder=3, n_node_per_mv_feeder=5, n_lv_feeder=3,
+                                  n_connection_per_lv_feeder=6, has_mv_ring=True, has_lv_ring=True)
+    inp = {k: v.copy() for k, v in grid.input_data.items()}
+    lines, trafos = inp["line"], inp["transformer"]
+    rng = np.random.default_rng(11)
+    tie_idx = np.zeros(0, int)
+    if ties:
+        not_bridge = np.flatnonzero(pgm_b200.PowerGridModel(inp).math_index(0, "branch_is_bridge")[: len(lines)] == 0)
+        tie_idx = not_bridge[[1, len(not_bridge) // 2, len(not_bridge) - 2]]
+        lines["from_status"][tie_idx[0]] = 0
+        lines["to_status"][tie_idx[0]] = 0
+        lines["to_status"][tie_idx[1]] = 0
+        lines["from_status"][tie_idx[2]] = 0
+        lines["to_status"][tie_idx[2]] = 0
+        assert _supplied(inp, list(zip(lines["from_status"], lines["to_status"])), list(zip(trafos["from_status"], trafos["to_status"]))).all()
+    model = pgm_b200.PowerGridModel(inp)
+    n_scn = 60
+    l_rows, t_rows, expect_slots, expect_dark = [], [], [], []
+    for s in range(n_scn):
+        l_state = [[int(f), int(t)] for f, t in zip(lines["from_status"], lines["to_status"])]
+        t_state = [[int(f), int(t)] for f, t in zip(trafos["from_status"], trafos["to_status"])]
+        taps = trafos["tap_pos"].astype(int).copy()
+        pick = rng.choice(np.setdiff1d(np.arange(len(lines)), tie_idx), size=int(rng.integers(0, 5)), replace=False)
+        closed = rng.choice(tie_idx, size=int(rng.integers(0, len(tie_idx) + 1)), replace=False) if ties else np.zeros(0, int)
+        lu = pgm_b200.structs.initialize_array("update", "line", len(pick) + len(closed))
+        for k, li in enumerate(pick):
+            side = rng.integers(0, 3)  # both sides, from only, to only
+            lu["id"][k] = lines["id"][li]
+            if side != 2:
+                lu["from_status"][k] = 0
+                l_state[li][0] = 0
+            if side != 1:
+                lu["to_status"][k] = 0
+                l_state[li][1] = 0
+        for k, li in enumerate(closed):
+            lu["id"][len(pick) + k] = lines["id"][li]
+            lu["from_status"][len(pick) + k] = 1
+            lu["to_status"][len(pick) + k] = 1
+            l_state[li] = [1, 1]
+        n_t = int(rng.integers(0, 3))
+        tp = rng.choice(np.arange(1, len(trafos)), size=n_t, replace=False)
+        tu = pgm_b200.structs.initialize_array("update", "transformer", n_t)
+        for k, ti in enumerate(tp):
+            tu["id"][k] = trafos["id"][ti]
+            if rng.random() < 0.5:
+                tu["from_status"][k] = 0
+                t_state[ti][0] = 0
+            else:
+                taps[ti] = int(np.clip(taps[ti] + rng.integers(-2, 3), min(trafos["tap_min"][ti], trafos["tap_max"][ti]),
+                                       max(trafos["tap_min"][ti], trafos["tap_max"][ti])))
+                tu["tap_pos"][k] = taps[ti]
+        l_rows.append(lu)
+        t_rows.append(tu)
+        # slots: branches whose state differs from the grid the pattern was built for (ties closed), or whose tap moved
+        pattern_l = [[1, 1] if li in tie_idx else [int(lines["from_status"][li]), int(lines["to_status"][li])] for li in range(len(lines))]
+        slots = sum(a != b for a, b in zip(l_state, pattern_l))
+        slots += sum(list(a) != [int(f), int(t)] or taps[ti] != trafos["tap_pos"][ti]
+                     for ti, (a, f, t) in enumerate(zip(t_state, trafos["from_status"], trafos["to_status"])))
+        expect_slots.append(slots)
+        expect_dark.append(int((~_supplied(inp, l_state, t_state)).sum()))
+    update = {"line": {"data": np.concatenate(l_rows), "indptr": np.cumsum([0] + [len(x) for x in l_rows])},
+              "transformer": {"data": np.concatenate(t_rows), "indptr": np.cumsum([0] + [len(x) for x in t_rows])}}
+    for sym in (True, False):
+        plan = model.outage_plan(update, symmetric=sym)
+        assert (plan[:, 3] == int(ties)).all()
+        shared = plan[:, 0] == 0
+        assert shared.sum() >= n_scn - 2  # (a scenario with more than eight changed branches would take its own topology)
+        assert np.array_equal(plan[shared, 1], np.array(expect_slots)[shared]), (plan[:, 1], expect_slots)
+        assert np.array_equal(plan[shared, 2], np.array(expect_dark)[shared]), (plan[:, 2], expect_dark)
+    assert 0 < (np.array(expect_dark) > 0).sum() < n_scn
