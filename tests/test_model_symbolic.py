@@ -246,3 +246,40 @@ def test_host_planning_of_branch_switching_batches(ties):
         assert np.array_equal(plan[shared, 1], np.array(expect_slots)[shared]), (plan[:, 1], expect_slots)
         assert np.array_equal(plan[shared, 2], np.array(expect_dark)[shared]), (plan[:, 2], expect_dark)
     assert 0 < (np.array(expect_dark) > 0).sum() < n_scn
+
+
+def test_host_planning_sends_what_the_pattern_cannot_hold_to_the_own_topology_route():
+    """Edge cases of the planning (CPU): a scenario that closes a transformer whose LV grid is dark in the base state (its nodes are
+    in no math model: the union grid cannot hold it), one that changes more than eight branches, one with an unknown id -- each
+    takes the own-topology route alone; a scenario that names a branch without changing anything needs no slot."""
+    grid = pgm_b200.FictionalGrid(seed=3, n_node_total_specified=200, n_mv_feeder=3, n_node_per_mv_feeder=5, n_lv_feeder=3,
+                                  n_connection_per_lv_feeder=6, has_mv_ring=True, has_lv_ring=False)
+    inp = {k: v.copy() for k, v in grid.input_data.items()}
+    lines, trafos = inp["line"], inp["transformer"]
+    inp["transformer"]["from_status"][2] = 0  # this transformer's LV grid is dark in the base state
+    inp["transformer"]["to_status"][2] = 0
+    model = pgm_b200.PowerGridModel(inp)
+    assert (model.math_index(0, "coup.node").reshape(-1, 2)[:, 0] == -1).any()  # the dark LV grid
+    n_scn = 12
+    l_rows = [pgm_b200.structs.initialize_array("update", "line", 1) for _ in range(n_scn)]
+    t_rows = [pgm_b200.structs.initialize_array("update", "transformer", 0) for _ in range(n_scn)]
+    live = [k for k in range(len(lines)) if k % 3 == 0][: n_scn + 10]
+    for s in range(n_scn):
+        l_rows[s]["id"], l_rows[s]["from_status"], l_rows[s]["to_status"] = lines["id"][live[s]], 0, 0
+    # 3: closes the transformer towards the dark grid
+    t_rows[3] = pgm_b200.structs.initialize_array("update", "transformer", 1)
+    t_rows[3]["id"], t_rows[3]["from_status"], t_rows[3]["to_status"] = trafos["id"][2], 1, 1
+    # 5: nine lines at once
+    l_rows[5] = pgm_b200.structs.initialize_array("update", "line", 9)
+    l_rows[5]["id"], l_rows[5]["from_status"], l_rows[5]["to_status"] = lines["id"][live[12:21]], 0, 0
+    # 7: unknown id
+    l_rows[7]["id"] = 987654321
+    # 9: names a line, changes nothing
+    l_rows[9]["from_status"], l_rows[9]["to_status"] = 1, -128
+    update = {"line": {"data": np.concatenate(l_rows), "indptr": np.cumsum([0] + [len(x) for x in l_rows])},
+              "transformer": {"data": np.concatenate(t_rows), "indptr": np.cumsum([0] + [len(x) for x in t_rows])}}
+    plan = model.outage_plan(update)
+    assert (plan[:, 3] == 0).all()  # nothing the union grid could take
+    assert plan[:, 0].tolist() == [1 if s in (3, 5, 7) else 0 for s in range(n_scn)]
+    assert plan[9].tolist() == [0, 0, 0, 0]
+    assert all(plan[s, 1] == 1 for s in range(n_scn) if s not in (3, 5, 7, 9))
