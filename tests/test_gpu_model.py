@@ -592,12 +592,16 @@ def _multi_outage_update(grid, n_scn, seed):
             "transformer": {"data": np.concatenate(trafo_rows), "indptr": np.cumsum([0] + [len(x) for x in trafo_rows])}}
 
 
+@pytest.mark.parametrize("parts", [False, True])
 @pytest.mark.parametrize("sym", [True, False])
-def test_multi_branch_outages_share_the_base_pattern(sym, monkeypatch):
+def test_multi_branch_outages_share_the_base_pattern(sym, parts, monkeypatch):
     """N-k batches (2-4 switched branches per scenario, with a load profile): the scenarios run as ONE device batch on the base
     grid's pattern (overlay with several branch slots per scenario; parts of the grid that lose their supply are masked) and
     equal the oracle, which rebuilds the topology per scenario; the same batch with one slot (PGMB_OUTAGE_SLOTS=1: every
-    scenario on its own topology) gives the same results."""
+    scenario on its own topology) gives the same results.  parts=True: a device-memory budget that splits the batch into two
+    passes (32 + 8 scenarios), each with its slice of the overlay."""
+    if parts:
+        monkeypatch.setenv("PGMB_MAX_BATCH_BYTES", "1")
     grid = pgm_b200.FictionalGrid(seed=0, n_node_total_specified=300, n_connection_per_lv_feeder=5, n_lv_feeder=4, n_node_per_mv_feeder=5,
                                   n_mv_feeder=3, has_mv_ring=True, has_lv_ring=True)
     n_scn = 40
