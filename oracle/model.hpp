@@ -266,8 +266,8 @@ class Model {
             auto it = node_ref.find(lg.node);
             if (it != node_ref.end()) {
                 if (it->second.second != r.u_ref) {
-                    throw PgmError{"Voltage regulators with different u_ref on the same node: " + std::to_string(it->second.first) + ", " +
-                                   std::to_string(r.id)};
+                    throw PgmError{"Conflicting u_ref values detected for voltage regulators " + std::to_string(it->second.first) + ", " +
+                                   std::to_string(r.id) + "."}; // exception.hpp:168-172
                 }
             } else {
                 node_ref[lg.node] = {r.id, r.u_ref};
@@ -276,12 +276,13 @@ class Model {
         for (auto const& r : regulators_) {
             if (!r.status) continue;
             if (load_gens_[load_gen_idx_.at(r.regulated_object)].type != LoadGenType::const_pq) {
-                throw PgmError{"Voltage regulator " + std::to_string(r.id) + " regulates a load/generator of unsupported type"};
+                throw PgmError{"Unsupported load_gen type for voltage regulators " + std::to_string(r.id) + "."}; // exception.hpp:174-178
             }
         }
         for (auto const& src : sources_) {
             if (src.status && node_ref.count(src.node) != 0) {
-                throw PgmError{"Unsupported combination of source and voltage regulator at node " + std::to_string(src.node)};
+                throw PgmError{"Nodes with a source and a voltage regulated load/generator are not supported when both are enabled. Found at node with id " +
+                               std::to_string(src.node)}; // exception.hpp:180-186
             }
         }
         if constexpr (B == 3) {

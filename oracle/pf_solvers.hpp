@@ -381,7 +381,7 @@ template <int B> class NewtonRaphsonPFSolver {
                 for (Idx reg = topo.voltage_regulators_per_load_gen[lg]; reg != topo.voltage_regulators_per_load_gen[lg + 1]; ++reg) {
                     if (input.voltage_regulator[reg].status != 0) {
                         if (topo.load_gen_type[lg] != LoadGenType::const_pq) {
-                            throw PgmError{"Voltage regulator(s) " + std::to_string(reg) + " regulate(s) a load/generator with unsupported type"};
+                            throw PgmError{"Unsupported load_gen type for voltage regulators " + std::to_string(reg) + "."}; // newton_raphson_pf_solver.hpp:655
                         }
                         for (int p = 0; p < B; ++p) specified_regulating_q[p] += input.s_injection[lg].v[p].imag();
                     }

@@ -213,8 +213,9 @@ template <int B> void Model::check_regulators(ModelOptions const& opt) const {
         auto it = node_ref.find(node);
         if (it != node_ref.end()) {
             if (it->second.second != reg_st_[r].u_ref) {
-                throw InvalidArgument("Voltage regulators with different u_ref on the same node: " + std::to_string(it->second.first) + ", " +
-                                      std::to_string(reg_in_[r].id) + "\n");
+                // the reference's texts (common/exception.hpp:168-186)
+                throw InvalidArgument("Conflicting u_ref values detected for voltage regulators " + std::to_string(it->second.first) + ", " +
+                                      std::to_string(reg_in_[r].id) + ".");
             }
         } else {
             node_ref[node] = {reg_in_[r].id, reg_st_[r].u_ref};
@@ -222,12 +223,13 @@ template <int B> void Model::check_regulators(ModelOptions const& opt) const {
     }
     for (size_t r = 0; r != reg_in_.size(); ++r) {
         if (reg_st_[r].status && lg_[reg_lg_[r]].type != 0) {
-            throw InvalidArgument("Voltage regulator " + std::to_string(reg_in_[r].id) + " regulates a load/generator of unsupported type\n");
+            throw InvalidArgument("Unsupported load_gen type for voltage regulators " + std::to_string(reg_in_[r].id) + ".");
         }
     }
     for (size_t i = 0; i != source_in_.size(); ++i) {
         if (source_st_[i].status && node_ref.count(node_idx_.at(source_in_[i].node)) != 0) {
-            throw InvalidArgument("Unsupported combination of source and voltage regulator at node " + std::to_string(source_in_[i].node) + "\n");
+            throw InvalidArgument("Nodes with a source and a voltage regulated load/generator are not supported when both are enabled. Found at node with id " +
+                                  std::to_string(source_in_[i].node));
         }
     }
     if constexpr (B == 3) {
