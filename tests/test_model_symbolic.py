@@ -169,18 +169,19 @@ def _supplied(inp, line_state, trafo_state):
     return labels == labels[node_pos[int(inp["source"]["node"][0])]]
 
 
+@pytest.mark.parametrize("seed", [3, 4, 5])
 @pytest.mark.parametrize("ties", [False, True])
-def test_host_planning_of_branch_switching_batches(ties):
+def test_host_planning_of_branch_switching_batches(ties, seed):
     """Host side of the shared-pattern route for N-k / reconfiguration / tap batches, no device needed: for random
     scenarios (1-5 branches opened fully or on one side, taps moved, open ties closed) the plan puts every scenario on the shared
     pattern, uses one overlay slot per branch whose state or tap differs from the pattern's grid, and masks exactly the buses a
     brute-force connectivity search finds without supply.  ties=True: three lines are open in the base state and scenarios close
     them, so the plan is made on the union grid, where a tie that stays open takes a slot."""
-    grid = pgm_b200.FictionalGrid(seed=3, n_node_total_specified=200, n_mv_feeder=3, n_node_per_mv_feeder=5, n_lv_feeder=3,
+    grid = pgm_b200.FictionalGrid(seed=seed, n_node_total_specified=200, n_mv_feeder=3, n_node_per_mv_feeder=5, n_lv_feeder=3,
                                   n_connection_per_lv_feeder=6, has_mv_ring=True, has_lv_ring=True)
     inp = {k: v.copy() for k, v in grid.input_data.items()}
     lines, trafos = inp["line"], inp["transformer"]
-    rng = np.random.default_rng(11)
+    rng = np.random.default_rng(11 + seed)
     tie_idx = np.zeros(0, int)
     if ties:
         not_bridge = np.flatnonzero(pgm_b200.PowerGridModel(inp).math_index(0, "branch_is_bridge")[: len(lines)] == 0)
