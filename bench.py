@@ -430,7 +430,10 @@ def main():
     #      every timed region so that they cannot disturb it) ----
     other = None
     if rank == 0 and os.environ.get("PGMB_BENCH_OTHER", "1") == "1":
-        other = other_configs(pgm_b200, np, local_rank)
+        try:
+            other = other_configs(pgm_b200, np, local_rank)
+        except Exception as ex:  # the side configurations must not take the bench line with them
+            other = {"error": f"{type(ex).__name__}: {ex}"[:500]}
 
     if rank == 0:
         peak, peak_kind = measured_peak_hbm()
